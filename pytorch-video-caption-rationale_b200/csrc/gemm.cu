@@ -1,0 +1,102 @@
+// Host side of the tcgen05 GEMM: TMA tensor-map construction (cached) and the plain-store entry point.
+#include <mutex>
+#include <unordered_map>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "gemm_sm100.cuh"
+
+namespace pvcr {
+
+static thread_local char g_last_error[512] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_last_error; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  long long ld, slab_stride;
+  int rows, slabs, K, box_rows;
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(MapKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+    return (size_t)h;
+  }
+};
+static_assert(sizeof(MapKey) % 8 == 0, "MapKey must be 8-byte granular");
+
+// 3-D tensor map over (k, row, slab), box = 64 x box_rows x 1, 128-byte swizzle, OOB elements read as zero.
+int make_tensor_map(CUtensorMap* out, const OperandView& v, int K, int box_rows) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = v.ptr; key.ld = v.ld; key.slab_stride = v.slab_stride; key.rows = v.rows; key.slabs = v.slabs;
+  key.K = K; key.box_rows = box_rows;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return PVCR_OK; }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_last_error("cuTensorMapEncodeTiled not available from the driver"); return PVCR_ERR_DRIVER; }
+  PVCR_REQUIRE((reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0, "tensor map: base %p not 16-byte aligned", v.ptr);
+  PVCR_REQUIRE(v.ld % 8 == 0 && v.ld >= K, "tensor map: ld=%lld must be a multiple of 8 and >= K=%d", v.ld, K);
+  const int slabs = v.slabs > 0 ? v.slabs : 1;
+  long long slab_stride = v.slab_stride;
+  if (slabs == 1 && slab_stride <= 0) slab_stride = v.ld * (long long)v.rows;
+  PVCR_REQUIRE(slab_stride % 8 == 0, "tensor map: slab stride %lld must be a multiple of 8", slab_stride);
+  cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)v.rows, (cuuint64_t)slabs};
+  cuuint64_t gstr[2] = {(cuuint64_t)v.ld * 2, (cuuint64_t)slab_stride * 2};
+  cuuint32_t box[3] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(v.ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (%d): ptr=%p K=%d rows=%d slabs=%d ld=%lld slab=%lld", (int)r,
+                   v.ptr, K, v.rows, slabs, v.ld, slab_stride);
+    return PVCR_ERR_DRIVER;
+  }
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 65536) cache.clear();
+  cache[key] = *out;
+  return PVCR_OK;
+}
+
+// C[z] = A[z] * B[z]^T (+bias) (+C).  Tile choice: 128x256 when N is wide enough to fill the machine, else 128x128.
+int gemm_store(const OperandView& a, const OperandView& b, const GemmCoords& gc, int grid_z, float* C, long long ldc,
+               long long c_zstride, const float* bias, long long bias_zstride, int accumulate,
+               cudaStream_t stream) {
+  EpiStore epi{C, ldc, c_zstride, bias, bias_zstride, accumulate, gc.M, gc.N};
+  const long long tiles256 = (long long)cdiv(gc.N, 256) * cdiv(gc.M, GEMM_BM) * grid_z;
+  if (gc.N >= 256 && tiles256 >= 148) return launch_gemm_tn<256, 4, EpiStore>(a, b, gc, grid_z, epi, stream);
+  return launch_gemm_tn<128, 3, EpiStore>(a, b, gc, grid_z, epi, stream);
+}
+
+}  // namespace pvcr

@@ -1,0 +1,204 @@
+// bf16 x bf16 -> fp32 GEMM for sm_100a:  C[z][m][n] = sum_k A[z][m][k] * B[z][n][k]   ("TN", both K-major)
+//
+//   * operands are staged global -> shared by TMA (cp.async.bulk.tensor, 128-byte swizzle) through a
+//     STAGES-deep mbarrier ring,
+//   * one elected thread issues tcgen05.mma (UMMA 128 x BN x 16) with the accumulator in TMEM,
+//   * four epilogue warps read the accumulator back with tcgen05.ld (one thread == one output row)
+//     and hand 32-column chunks to an epilogue functor (plain store, fused cross-entropy, ...).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue
+// (warp w may only touch TMEM lanes 32*(w%4) .. 32*(w%4)+31).
+#pragma once
+#include "common.cuh"
+
+namespace pvcr {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;   // 64 bf16 = 128 bytes = one swizzle row
+constexpr int GEMM_THREADS = 192;
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
+};
+
+struct GemmCoords {
+  int M, N, K;          // K = concatenated (all split planes), multiple of GEMM_BK
+  int a_z0, a_zmul;     // slab coordinate of A for grid z:  a_z0 + z * a_zmul
+  int b_z0, b_zmul;
+};
+
+#ifdef __CUDACC__
+
+template <int BN, int STAGES, class Epi>
+__global__ void __launch_bounds__(GEMM_THREADS, (BN <= 128 ? 2 : 1))
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmCoords gc,
+               Epi epi) {
+  using SM = GemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * GEMM_BM;
+  const int z = blockIdx.z;
+  const int num_kb = gc.K / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int az = gc.a_z0 + z * gc.a_zmul, bz = gc.b_z0 + z * gc.b_zmul;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], SM::STAGE_BYTES);
+        uint8_t* sa = smem + s * SM::STAGE_BYTES;
+        tma_load_3d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m0, az);
+        tma_load_3d(sa + SM::A_BYTES, &tmB, &full_bar[s], kb * GEMM_BK, n0, bz);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
+        const uint64_t da = umma_desc_k128(sa);
+        const uint64_t db = umma_desc_k128(sa + SM::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < GEMM_BK / 16; ++k) {
+          // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the >>4 address field
+          umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[s]);     // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);       // accumulator complete
+    }
+  } else {
+    const int q = warp & 3;             // TMEM lane quadrant of this warp
+    const int row = m0 + q * 32 + lane;
+    epi.begin(row, z);
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    float v[32];
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      if (n0 + c >= gc.N) break;        // warp-uniform
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      epi.chunk(row, n0 + c, z, v);
+    }
+    epi.end(row, blockIdx.x, z);
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// Plain store epilogue: C = acc (+ bias[n]) (+ C).  fp32 output, arbitrary ldc.
+struct EpiStore {
+  float* C;
+  long long ldc, c_zstride;
+  const float* bias;
+  long long bias_zstride;
+  int accumulate, M, N;
+  __device__ __forceinline__ void begin(int, int) {}
+  __device__ __forceinline__ void chunk(int row, int col0, int z, float (&v)[32]) {
+    if (row >= M) return;
+    float* c = C + (long long)z * c_zstride + (long long)row * ldc + col0;
+    const float* b = bias ? bias + (long long)z * bias_zstride + col0 : nullptr;
+    const bool vec = (col0 + 32 <= N) && ((reinterpret_cast<uintptr_t>(c) & 15) == 0);
+    if (vec) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (b) { o.x += __ldg(b + j); o.y += __ldg(b + j + 1); o.z += __ldg(b + j + 2); o.w += __ldg(b + j + 3); }
+        if (accumulate) {
+          const float4 p = *reinterpret_cast<const float4*>(c + j);
+          o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+        }
+        *reinterpret_cast<float4*>(c + j) = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (col0 + j < N) {
+          float o = v[j] + (b ? __ldg(b + j) : 0.f);
+          if (accumulate) o += c[j];
+          c[j] = o;
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void end(int, int, int) {}
+};
+
+#endif  // __CUDACC__
+
+// ---- host side ------------------------------------------------------------------------------
+// Operand view: bf16, element (z, r, k) at ptr[z*slab_stride + r*ld + k]; k in [0,K).
+struct OperandView {
+  const bf16* ptr;
+  long long ld, slab_stride;
+  int rows, slabs;
+};
+
+int make_tensor_map(CUtensorMap* out, const OperandView& v, int K, int box_rows);
+
+#ifdef __CUDACC__
+template <int BN, int STAGES, class Epi>
+int launch_gemm_tn(const OperandView& a, const OperandView& b, const GemmCoords& gc, int grid_z, const Epi& epi,
+                   cudaStream_t stream) {
+  using SM = GemmSmem<BN, STAGES>;
+  PVCR_REQUIRE(gc.K > 0 && gc.K % GEMM_BK == 0, "gemm: K=%d must be a positive multiple of %d", gc.K, GEMM_BK);
+  PVCR_REQUIRE(gc.M > 0 && gc.N > 0 && grid_z > 0, "gemm: empty problem M=%d N=%d z=%d", gc.M, gc.N, grid_z);
+  CUtensorMap ta, tb;
+  PVCR_TRY(make_tensor_map(&ta, a, gc.K, GEMM_BM));
+  PVCR_TRY(make_tensor_map(&tb, b, gc.K, BN));
+  auto kern = gemm_tn_kernel<BN, STAGES, Epi>;
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(gc.N, BN), cdiv(gc.M, GEMM_BM), grid_z);
+  kern<<<grid, GEMM_THREADS, SM::TOTAL, stream>>>(ta, tb, gc, epi);
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  return PVCR_OK;
+}
+#endif
+
+}  // namespace pvcr

@@ -1,0 +1,158 @@
+// Launchers of the non-GEMM kernels (operand staging, recurrent gate math, attention, loss).
+// All pointers are device pointers; all launches are stream-ordered; no allocation inside.
+#pragma once
+#include "common.cuh"
+
+namespace pvcr {
+
+// Counter-based dropout: keep iff philox(seed, element index) >= p; kept values are scaled by 1/(1-p).
+struct Dropout {
+  float p;                  // 0 = disabled
+  unsigned long long seed;
+  unsigned long long offset;   // added to the element index (distinct per tensor / per step)
+};
+
+// ---- operand staging: fp32 -> bf16 split planes -------------------------------------------------
+// out[r][p*Cp + c] = term_{role,p}( in[r*ld_in + c] * (row_scale ? row_scale[r] : 1) * dropout ), zero for c >= C.
+int cast_split(const float* in, long long ld_in, int R, int C, bf16* out, long long ld_out, int Cp, int nsplit,
+               int role_b, const float* row_scale, Dropout drop, cudaStream_t st);
+// out[c][p*Rp + r_off + r] = term_{role,p}( src(r)[c] * (row_scale ? row_scale[r] : 1) ) for r < R, where
+// src(r) = in + (row_ids ? row_ids[r] : r) * ld_in.  With zero_pad, columns r_off+R .. Rp-1 are zero-filled.
+int transpose_split(const float* in, long long ld_in, int R, int C, bf16* out, long long ld_out, int Rp, int r_off,
+                    int zero_pad, int nsplit, int role_b, const long long* row_ids, const float* row_scale,
+                    cudaStream_t st);
+// out[i][p*Ep + e] = term_{A,p}( table[ids[i]][e] * dropout )     (embedding rows as an A operand)
+int gather_split(const float* table, int E, const long long* ids, int n_ids, bf16* out, long long ld_out, int Ep,
+                 int nsplit, Dropout drop, cudaStream_t st);
+// table_grad[ids[i]][e] += rows[i*ld + e] * dropout-mask      (dense embedding gradient)
+int scatter_add_rows(const float* rows, long long ld, const long long* ids, int n_ids, int E, float* table_grad,
+                     Dropout drop, cudaStream_t st);
+// out[c] (+)= sum_r in[r*ld + c]
+int colsum(const float* in, long long ld, int R, int C, float* out, int accumulate, cudaStream_t st);
+// y[i] = a[i] * mask_i/(1-p)  (dropout backward / forward on fp32 data), in place allowed
+int dropout_apply(const float* in, float* out, long long n, Dropout drop, cudaStream_t st);
+int fill_zero(void* p, size_t bytes, cudaStream_t st);
+
+// ---- GRU gate math ---------------------------------------------------------------------------------
+struct GruFwdArgs {
+  int B, H;
+  const float* gi_a; long long gi_a_ld;     // [B,3H] required (includes b_ih)
+  const float* gi_b; long long gi_b_ld;     // optional second addend
+  const float* gi_bias;                     // optional [3H] bias addend
+  const float* gh; long long gh_ld;         // [B,3H] W_hh h (no bias) or null (h_prev == 0)
+  const float* b_hh;                        // [3H]
+  const float* h_prev; long long h_prev_ld; // null => zeros
+  float* h_out; long long h_out_ld;
+  bf16* h_planes; long long h_planes_ld; int Hp, nsplit;   // optional A-role planes of h_out
+  float *r, *z, *n, *ghn;                   // saved [B,H] each (nullable as a group)
+};
+int gru_gate_fwd(const GruFwdArgs& a, cudaStream_t st);
+
+struct GruBwdArgs {
+  int B, H;
+  const float* dh_a; long long dh_a_ld;     // nullable
+  const float* dh_b; long long dh_b_ld;     // nullable
+  const float *r, *z, *n, *ghn;             // saved
+  const float* h_prev; long long h_prev_ld; // null => zeros
+  float* dgi; long long dgi_ld;             // [B,3H] fp32
+  float* dgh; long long dgh_ld;             // [B,3H] fp32
+  bf16* dgi_planes; long long dgi_planes_ld; int dgi_Kp, dgi_col0;   // optional A-role planes (k = dgi_col0 + c)
+  bf16* dgh_planes; long long dgh_planes_ld; int dgh_Kp, dgh_col0;
+  int nsplit;
+  float* dh_direct; long long dh_direct_ld; // dh * z
+};
+int gru_gate_bwd(const GruBwdArgs& a, cudaStream_t st);
+
+// ---- LSTM gate math (gate order i,f,g,o) -------------------------------------------------------------
+struct LstmFwdArgs {
+  int B, H;
+  const float* gi; long long gi_ld;         // [B,4H] (includes b_ih)
+  const float* gh; long long gh_ld;         // [B,4H] or null (h_prev == 0)
+  const float* b_hh;
+  const float* c_prev;                      // [B,H] contiguous or null
+  float* h_out; long long h_out_ld;
+  bf16* h_planes; long long h_planes_ld; int Hp, nsplit;
+  float *i, *f, *g, *o, *c;                 // saved [B,H] each
+};
+int lstm_gate_fwd(const LstmFwdArgs& a, cudaStream_t st);
+struct LstmBwdArgs {
+  int B, H;
+  const float* dh_a; long long dh_a_ld;     // carry (nullable)
+  const float* dh_b; long long dh_b_ld;     // external (nullable)
+  float* dc;                                // [B,H] carry, in/out (zero-initialised by the caller)
+  const float *i, *f, *g, *o, *c, *c_prev;  // saved; c_prev null => zeros
+  float* da; long long da_ld;               // [B,4H]
+  bf16* da_planes; long long da_planes_ld; int Kp, nsplit;
+};
+int lstm_gate_bwd(const LstmBwdArgs& a, cudaStream_t st);
+
+// ---- additive attention step ---------------------------------------------------------------------------
+struct AttnFwdArgs {
+  int B, N, H;
+  const float* q; long long q_ld;           // [B,H] = W_q h
+  const float* pk;                          // [B,N,H]
+  const float* enc;                         // [B,N,H]
+  const float* v;                           // [H]
+  float* alpha;                             // [B,N]
+  float* ctx; long long ctx_ld;             // [B,H]
+  bf16* ctx_planes; long long ctx_planes_ld; int Hp, nsplit;
+};
+int attn_fwd(const AttnFwdArgs& a, cudaStream_t st);
+struct AttnBwdArgs {
+  int B, N, H;
+  const float* dctx; long long dctx_ld;
+  const float* q; long long q_ld;
+  const float *pk, *enc, *v, *alpha;
+  float* dq; long long dq_ld;               // [B,H] fp32
+  bf16* dq_planes; long long dq_planes_ld; int dq_Kp, nsplit;   // k = c
+  float* dpk;                               // [B,N,H] +=
+  float* denc;                              // [B,N,H] +=
+  float* dv_part;                           // [B,H] +=
+};
+int attn_bwd(const AttnBwdArgs& a, cudaStream_t st);
+
+// ---- loss --------------------------------------------------------------------------------------------
+// Row-wise cross entropy on materialised fp32 logits [R = B*L, Vc]; token (b,l) = row b*L + l.
+// Writes lse/nll/pred per row; if dlogits != null also dlogits = (softmax - onehot) * w[row] * gscale
+// where w = (l < s_len[b]) / (s_len[b] * B).
+int ce_rows(const float* logits, long long ld, int B, int L, int Vc, const long long* target, const long long* s_len,
+            float* lse, float* nll, long long* pred, float* dlogits, long long ld_d, const float* gscale,
+            cudaStream_t st);
+// out[0] = mean_b( sum_l nll*mask / s_len ), out[1] = #correct (masked), out[2] = #mask
+int loss_finalize(const float* nll, const long long* pred, const long long* target, const long long* s_len, int B,
+                  int L, float* out3, cudaStream_t st);
+
+// ---- RationaleNet generator head ------------------------------------------------------------------------
+// logits = [hf;hb] W^T + b (2 classes) ; y = softmax((logits - log(noise)) / tau) ; probs = hard ? onehot-st : y
+struct GumbelArgs {
+  int B, N, H;                               // hf/hb: [N,B,H] (seq-first, fwd and bwd direction outputs)
+  const float *hf, *hb;
+  const float* w;                            // [2, 2H]
+  const float* bias;                         // [2]
+  const float* noise;                        // [B*N, 2] Exp(1) draws (row = b*N + n), or null => philox
+  unsigned long long seed;
+  float tau; int hard;
+  Dropout drop;                              // dropout on the LSTM outputs
+  float* probs;                              // [B,N,2]
+  float* y;                                  // [B,N,2] soft sample (saved for backward)
+  float* pen;                                // [2]: brevity, continuity losses (unscaled)
+};
+int gumbel_select_fwd(const GumbelArgs& a, cudaStream_t st);
+struct GumbelBwdArgs {
+  int B, N, H;
+  const float *hf, *hb, *w, *y;
+  float tau;
+  Dropout drop;
+  const float* dp1_sel;                      // [B,N] d(loss)/d(p1) through the feature scaling (nullable)
+  const float* dprobs;                       // [B,N,2] external gradient on probs (nullable)
+  float g_brev, g_cont;                      // d(loss)/d(brevity), d(loss)/d(continuity)
+  float* dhf; float* dhb;                    // [N,B,H] each
+  float* dw;                                 // [2,2H]  (overwritten)
+  float* dbias;                              // [2]
+  float* scratch;                            // [B*N*2] dlogits
+};
+int gumbel_select_bwd(const GumbelBwdArgs& a, cudaStream_t st);
+// dp1[b,n] = sum_v x[b,n,v] * dsel[b,n,v]
+int rowdot(const float* x, const float* dsel, int R, int C, float* out, cudaStream_t st);
+
+}  // namespace pvcr
