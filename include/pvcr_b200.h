@@ -39,6 +39,76 @@ int pvcr_linear_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, 
                     float* dx, int64_t lddx, float* dw, int64_t lddw, float* db, int M, int N, int K, int nsplit,
                     int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Model-level entry points.  Symbols: B batch, N frames, V feature size, H hidden, E embedding size,
+ * L = max_len, Vc vocabulary.  dropout_p / seed parameterise the counter-based (Philox) dropout masks of
+ * nn.Dropout call sites; parity tests run with dropout_p = 0 as the reference draws from torch's RNG.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int B, N, V, H, E, L, Vc;
+  int nsplit;
+  float dropout_p;
+  uint64_t seed;
+} PvcrDims;
+
+/* S2VTAttModel parameters (reference state_dict names, model/S2VTAttModel.py:60-61,100-123). */
+typedef struct {
+  const float* enc_w_ih; /* encoder.rnn.weight_ih_l0            [3H, V]   */
+  const float* enc_w_hh; /* encoder.rnn.weight_hh_l0            [3H, H]   */
+  const float* enc_b_ih; /* encoder.rnn.bias_ih_l0              [3H]      */
+  const float* enc_b_hh; /* encoder.rnn.bias_hh_l0              [3H]      */
+  const float* emb;      /* decoder.embedding.weight            [Vc, E]   */
+  const float* dec_w_ih; /* decoder.rnn.weight_ih_l0            [3H, H+E] */
+  const float* dec_w_hh; /* decoder.rnn.weight_hh_l0            [3H, H]   */
+  const float* dec_b_ih; /* decoder.rnn.bias_ih_l0              [3H]      */
+  const float* dec_b_hh; /* decoder.rnn.bias_hh_l0              [3H]      */
+  const float* att_wk;   /* decoder.attention.key_layer.weight   [H, H]   */
+  const float* att_wq;   /* decoder.attention.query_layer.weight [H, H]   */
+  const float* att_v;    /* decoder.attention.energy_layer.weight [1, H]  */
+  const float* out_w;    /* decoder.pred_linear.1.weight        [Vc, H]   */
+  const float* out_b;    /* decoder.pred_linear.1.bias          [Vc]      */
+} PvcrS2vtAttParams;
+
+/* Gradients, same shapes; every non-NULL buffer is overwritten. out_w / out_b are produced by pvcr_vocab_*_bwd. */
+typedef struct {
+  float *enc_w_ih, *enc_w_hh, *enc_b_ih, *enc_b_hh, *emb, *dec_w_ih, *dec_w_hh, *dec_b_ih, *dec_b_hh, *att_wk,
+      *att_wq, *att_v, *out_w, *out_b;
+} PvcrS2vtAttGrads;
+
+/* Encoder + attention decoder, teacher-forced (S2VTAttModel.forward in training mode up to, but excluding,
+ * the vocabulary projection; model/S2VTAttModel.py:80-96,150-196).
+ *   vid_feats [B,N,V]; frame_scale [B,N] or NULL (RationaleNet: sel = vid_feats * p1, model/RationaleNet.py:52);
+ *   s_in [B,L] decoder input words (= [<sos>, s[:, :L-1]]);  hs [B,L,H] decoder hidden states (output);
+ *   alphas [L,B,N] attention weights (output, may be NULL).
+ * Activations needed by the backward pass stay in `workspace`, which must be passed unchanged to _bwd. */
+size_t pvcr_s2vtatt_workspace(const PvcrDims* d, int need_frame_grad);
+int pvcr_s2vtatt_fwd(const PvcrDims* d, const PvcrS2vtAttParams* p, const float* vid_feats, const float* frame_scale,
+                     const int64_t* s_in, float* hs, float* alphas, void* workspace, size_t workspace_bytes,
+                     void* stream);
+/* Backward of the above given d_hs [B,L,H].  Writes every gradient in g except out_w / out_b; if
+ * d_frame_scale != NULL also writes d loss / d frame_scale [B,N] (requires need_frame_grad at sizing). */
+int pvcr_s2vtatt_bwd(const PvcrDims* d, const PvcrS2vtAttParams* p, const float* vid_feats, const float* frame_scale,
+                     const int64_t* s_in, const float* hs, const float* d_hs, PvcrS2vtAttGrads* g,
+                     float* d_frame_scale, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Vocabulary projection fused with the loss contract:  logits = Dropout(hs) out_w^T + out_b
+ * (model/S2VTAttModel.py:145, model/S2VTModel.py:130), then calc_masked_loss / calc_masked_accuracy /
+ * argmax (train_utils.py:37-71, train.py:38).
+ *   hs [B*L,H] (row b*L+l); target [B*L] int64; s_len [B] int64 (1 <= s_len <= L).
+ *   loss3 [3] = { mean_b( sum_l nll*mask / s_len ), #correct under mask, #mask };  pred [B*L] int64 argmax
+ *   (first max index);  lse [B*L] log-sum-exp per token.  logits_out (optional, ld elements) receives the
+ *   fp32 logits for callers that need the reference's logits tensor; pass target = NULL to only project.
+ * _bwd needs the workspace of the matching _fwd untouched; gscale is a device scalar d total / d loss (NULL = 1). */
+size_t pvcr_vocab_ce_workspace(int B, int L, int H, int Vc, int nsplit, float dropout_p);
+int pvcr_vocab_ce_fwd(const float* hs, const float* out_w, const float* out_b, const int64_t* target,
+                      const int64_t* s_len, int B, int L, int H, int Vc, int nsplit, float dropout_p, uint64_t seed,
+                      float* loss3, int64_t* pred, float* lse, float* logits_out, int64_t ld_logits_out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int pvcr_vocab_ce_bwd(const float* hs, const float* out_w, const int64_t* target, const int64_t* s_len, int B, int L,
+                      int H, int Vc, int nsplit, float dropout_p, uint64_t seed, const float* gscale, float* d_hs,
+                      float* d_out_w, float* d_out_b, float* lse, int64_t* pred, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

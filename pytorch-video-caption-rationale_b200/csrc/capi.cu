@@ -9,6 +9,17 @@ int linear_fwd(const float*, long long, const float*, long long, const float*, f
 size_t linear_bwd_workspace(int M, int N, int K, int nsplit);
 int linear_bwd(const float*, long long, const float*, long long, const float*, long long, float*, long long, float*,
                long long, float*, int, int, int, int, int, void*, size_t, cudaStream_t);
+size_t s2vtatt_workspace(const PvcrDims& d, int need_frame_grad);
+int s2vtatt_fwd(const PvcrDims&, const PvcrS2vtAttParams&, const float*, const float*, const long long*, float*, float*,
+                void*, size_t, cudaStream_t);
+int s2vtatt_bwd(const PvcrDims&, const PvcrS2vtAttParams&, const float*, const float*, const long long*, const float*,
+                const float*, PvcrS2vtAttGrads&, float*, void*, size_t, cudaStream_t);
+size_t vocab_ce_workspace(int B, int L, int H, int Vc, int nsplit, float dropout_p);
+int vocab_ce_fwd(const float*, const float*, const float*, const long long*, const long long*, int, int, int, int, int,
+                 float, unsigned long long, float*, long long*, float*, float*, long long, void*, size_t, cudaStream_t);
+int vocab_ce_bwd(const float*, const float*, const long long*, const long long*, int, int, int, int, int, float,
+                 unsigned long long, const float*, float*, float*, float*, float*, long long*, void*, size_t,
+                 cudaStream_t);
 }  // namespace pvcr
 
 using namespace pvcr;
@@ -30,6 +41,39 @@ int pvcr_linear_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, 
                     int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
   return linear_bwd(dy, lddy, x, ldx, w, ldw, dx, lddx, dw, lddw, db, M, N, K, nsplit, accumulate, workspace,
                     workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t pvcr_s2vtatt_workspace(const PvcrDims* d, int need_frame_grad) { return s2vtatt_workspace(*d, need_frame_grad); }
+int pvcr_s2vtatt_fwd(const PvcrDims* d, const PvcrS2vtAttParams* p, const float* vid_feats, const float* frame_scale,
+                     const int64_t* s_in, float* hs, float* alphas, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  return s2vtatt_fwd(*d, *p, vid_feats, frame_scale, (const long long*)s_in, hs, alphas, workspace, workspace_bytes,
+                     (cudaStream_t)stream);
+}
+int pvcr_s2vtatt_bwd(const PvcrDims* d, const PvcrS2vtAttParams* p, const float* vid_feats, const float* frame_scale,
+                     const int64_t* s_in, const float* hs, const float* d_hs, PvcrS2vtAttGrads* g,
+                     float* d_frame_scale, void* workspace, size_t workspace_bytes, void* stream) {
+  return s2vtatt_bwd(*d, *p, vid_feats, frame_scale, (const long long*)s_in, d_hs, hs, *g, d_frame_scale, workspace,
+                     workspace_bytes, (cudaStream_t)stream);
+}
+size_t pvcr_vocab_ce_workspace(int B, int L, int H, int Vc, int nsplit, float dropout_p) {
+  return vocab_ce_workspace(B, L, H, Vc, nsplit, dropout_p);
+}
+int pvcr_vocab_ce_fwd(const float* hs, const float* out_w, const float* out_b, const int64_t* target,
+                      const int64_t* s_len, int B, int L, int H, int Vc, int nsplit, float dropout_p, uint64_t seed,
+                      float* loss3, int64_t* pred, float* lse, float* logits_out, int64_t ld_logits_out,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  return vocab_ce_fwd(hs, out_w, out_b, (const long long*)target, (const long long*)s_len, B, L, H, Vc, nsplit,
+                      dropout_p, seed, loss3, (long long*)pred, lse, logits_out, ld_logits_out, workspace,
+                      workspace_bytes, (cudaStream_t)stream);
+}
+int pvcr_vocab_ce_bwd(const float* hs, const float* out_w, const int64_t* target, const int64_t* s_len, int B, int L,
+                      int H, int Vc, int nsplit, float dropout_p, uint64_t seed, const float* gscale, float* d_hs,
+                      float* d_out_w, float* d_out_b, float* lse, int64_t* pred, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  return vocab_ce_bwd(hs, out_w, (const long long*)target, (const long long*)s_len, B, L, H, Vc, nsplit, dropout_p,
+                      seed, gscale, d_hs, d_out_w, d_out_b, lse, (long long*)pred, workspace, workspace_bytes,
+                      (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -24,6 +24,8 @@ struct Arena {
     return p;
   }
   bool measuring() const { return base == nullptr; }
+  size_t mark() const { return off; }
+  void release(size_t m) { off = m; }     // stream order makes reuse of released scratch safe
 };
 
 // bf16 split planes of a [rows, K] fp32 matrix: element (r, p, k) at ptr[r*ld + p*Kp + k], ld = P*Kp.
@@ -61,5 +63,52 @@ inline int stage(const float* in, long long ld_in, int R, int C, const Planes& p
 }
 
 static const Dropout NO_DROPOUT = {0.f, 0ull, 0ull};
+
+// weight [N,K] fp32 -> B-role planes [N, P*Kp]
+inline int prep_weight(const float* w, long long ldw, int N, int K, const Planes& p, cudaStream_t st, int row0 = 0) {
+  return stage(w, ldw, N, K, p, 1, nullptr, NO_DROPOUT, st, row0);
+}
+// weight [N,K] fp32 -> transposed B-role planes [K, P*Np] occupying contraction columns n_off .. n_off+N-1
+inline int prep_weight_T(const float* w, long long ldw, int N, int K, const Planes& p, int n_off, int zero_pad,
+                         cudaStream_t st) {
+  return transpose_split(w, ldw, N, K, p.ptr, p.ld, p.Kp, n_off, zero_pad, p.nsplit, 1, nullptr, nullptr, st);
+}
+
+// dw[N,K] (+)= dy^T x over R rows.  Scratch planes come from `a` and are released on return.
+int grad_w(Arena& a, const float* dy, long long lddy, int R, int N, const float* x, long long ldx, int K,
+           const long long* x_row_ids, const float* x_row_scale, float* dw, long long lddw, int accumulate,
+           int nsplit, cudaStream_t st);
+// dx[R,K] (+)= dy wT^T where wT are the transposed B-role planes of w ([K, P*Np]).
+int grad_x(Arena& a, const float* dy, long long lddy, int R, int N, const Planes& wT, float* dx, long long lddx,
+           int accumulate, cudaStream_t st);
+
+// ---- GRU layer over a sequence (per-step launches: tcgen05 GEMM h W_hh^T + fused gate kernel) ----------
+struct GruSeq {
+  int T, B, H, nsplit;
+  // input projections for step t (bias b_ih included): gi_a + t*gi_a_ts (row stride gi_a_ld); optional gi_b
+  // from step gi_b_from on; optional constant bias vector
+  const float* gi_a; long long gi_a_ts, gi_a_ld;
+  const float* gi_b; long long gi_b_ts, gi_b_ld; int gi_b_from;
+  const float* gi_bias;
+  const float* b_hh;
+  Planes whh;                              // B-role planes of W_hh [3H, P*Hp]
+  const float* h0; long long h0_ld;        // initial state (null => zeros)
+  const bf16* h0_planes; long long h0_planes_ld;
+  float* h; long long h_ts, h_ld;          // h_t at h + t*h_ts
+  bf16* hp; long long hp_ts, hp_ld; int Hp;   // A-role planes of h_t
+  float* gh;                               // scratch [B,3H]
+  float *r, *z, *n, *ghn;                  // saved [T][B,H]
+};
+int gru_seq_fwd(const GruSeq& s, cudaStream_t st);
+
+struct GruSeqGrad {
+  const float* dh_ext; long long dh_ext_ts, dh_ext_ld;   // gradient on every h_t (nullable)
+  float* dh_carry;                         // [B,H]: in = gradient on the final state, out = gradient on h0
+  float* dgi; long long dgi_ts, dgi_ld;    // [B,3H] per step
+  float* dgh; long long dgh_ts, dgh_ld;
+  Planes dgh_a;                            // scratch A-role planes [B, P*(3H)p]
+  Planes whhT;                             // transposed B-role planes of W_hh [H, P*(3H)p]
+};
+int gru_seq_bwd(const GruSeq& s, const GruSeqGrad& g, cudaStream_t st);
 
 }  // namespace pvcr

@@ -1,0 +1,89 @@
+// Recurrent layers as sequences of (tcgen05 GEMM  h_{t-1} W_hh^T) + fused gate kernels, and the shared
+// gradient GEMM helpers.  Reference: torch.nn.GRU call sites model/S2VTAttModel.py:88-93,142 and
+// model/S2VTModel.py:84,107,122,129; torch.nn.LSTM model/RationaleNet.py:43.
+#include "host.h"
+
+namespace pvcr {
+
+int grad_w(Arena& a, const float* dy, long long lddy, int R, int N, const float* x, long long ldx, int K,
+           const long long* x_row_ids, const float* x_row_scale, float* dw, long long lddw, int accumulate,
+           int nsplit, cudaStream_t st) {
+  const size_t m = a.mark();
+  Planes dyT = alloc_planes(a, N, R, nsplit);
+  Planes xT = alloc_planes(a, K, R, nsplit);
+  int rc = PVCR_OK;
+  if (!a.measuring()) {
+    if (a.failed) { set_last_error("grad_w: workspace too small"); return PVCR_ERR_WORKSPACE; }
+    rc = transpose_split(dy, lddy, R, N, dyT.ptr, dyT.ld, dyT.Kp, 0, 1, nsplit, 0, nullptr, nullptr, st);
+    if (rc == PVCR_OK) rc = transpose_split(x, ldx, R, K, xT.ptr, xT.ld, xT.Kp, 0, 1, nsplit, 1, x_row_ids, x_row_scale, st);
+    if (rc == PVCR_OK) rc = gemm_planes(dyT.view(), xT.view(), N, K, (int)dyT.ld, dw, lddw, nullptr, accumulate, st);
+  }
+  a.release(m);
+  return rc;
+}
+
+int grad_x(Arena& a, const float* dy, long long lddy, int R, int N, const Planes& wT, float* dx, long long lddx,
+           int accumulate, cudaStream_t st) {
+  const size_t m = a.mark();
+  Planes dya = alloc_planes(a, R, N, wT.nsplit);
+  int rc = PVCR_OK;
+  if (!a.measuring()) {
+    if (a.failed) { set_last_error("grad_x: workspace too small"); return PVCR_ERR_WORKSPACE; }
+    rc = stage(dy, lddy, R, N, dya, 0, nullptr, NO_DROPOUT, st);
+    if (rc == PVCR_OK) rc = gemm_planes(dya.view(), wT.view(), R, wT.rows, (int)dya.ld, dx, lddx, nullptr, accumulate, st);
+  }
+  a.release(m);
+  return rc;
+}
+
+int gru_seq_fwd(const GruSeq& s, cudaStream_t st) {
+  const int H3 = 3 * s.H;
+  for (int t = 0; t < s.T; ++t) {
+    const bool has_prev = (t > 0) || (s.h0 != nullptr);
+    if (has_prev) {
+      OperandView a = (t > 0) ? OperandView{s.hp + (t - 1) * s.hp_ts, s.hp_ld, 0, s.B, 1}
+                              : OperandView{s.h0_planes, s.h0_planes_ld, 0, s.B, 1};
+      PVCR_TRY(gemm_planes(a, s.whh.view(), s.B, H3, (int)s.whh.ld, s.gh, H3, nullptr, 0, st));
+    }
+    GruFwdArgs g{};
+    g.B = s.B; g.H = s.H;
+    g.gi_a = s.gi_a + t * s.gi_a_ts; g.gi_a_ld = s.gi_a_ld;
+    if (s.gi_b && t >= s.gi_b_from) { g.gi_b = s.gi_b + (t - s.gi_b_from) * s.gi_b_ts; g.gi_b_ld = s.gi_b_ld; }
+    g.gi_bias = s.gi_bias;
+    g.gh = has_prev ? s.gh : nullptr; g.gh_ld = H3;
+    g.b_hh = s.b_hh;
+    if (t > 0) { g.h_prev = s.h + (t - 1) * s.h_ts; g.h_prev_ld = s.h_ld; }
+    else { g.h_prev = s.h0; g.h_prev_ld = s.h0_ld; }
+    g.h_out = s.h + t * s.h_ts; g.h_out_ld = s.h_ld;
+    g.h_planes = s.hp ? s.hp + t * s.hp_ts : nullptr; g.h_planes_ld = s.hp_ld; g.Hp = s.Hp; g.nsplit = s.nsplit;
+    const long long o = (long long)t * s.B * s.H;
+    g.r = s.r + o; g.z = s.z + o; g.n = s.n + o; g.ghn = s.ghn + o;
+    PVCR_TRY(gru_gate_fwd(g, st));
+  }
+  return PVCR_OK;
+}
+
+int gru_seq_bwd(const GruSeq& s, const GruSeqGrad& g, cudaStream_t st) {
+  for (int t = s.T - 1; t >= 0; --t) {
+    const bool has_prev = (t > 0) || (s.h0 != nullptr);
+    GruBwdArgs b{};
+    b.B = s.B; b.H = s.H;
+    b.dh_a = g.dh_carry; b.dh_a_ld = s.H;
+    if (g.dh_ext) { b.dh_b = g.dh_ext + t * g.dh_ext_ts; b.dh_b_ld = g.dh_ext_ld; }
+    const long long o = (long long)t * s.B * s.H;
+    b.r = s.r + o; b.z = s.z + o; b.n = s.n + o; b.ghn = s.ghn + o;
+    if (t > 0) { b.h_prev = s.h + (t - 1) * s.h_ts; b.h_prev_ld = s.h_ld; }
+    else { b.h_prev = s.h0; b.h_prev_ld = s.h0_ld; }
+    b.dgi = g.dgi + t * g.dgi_ts; b.dgi_ld = g.dgi_ld;
+    b.dgh = g.dgh + t * g.dgh_ts; b.dgh_ld = g.dgh_ld;
+    b.dgh_planes = has_prev ? g.dgh_a.ptr : nullptr; b.dgh_planes_ld = g.dgh_a.ld; b.dgh_Kp = g.dgh_a.Kp; b.dgh_col0 = 0;
+    b.nsplit = s.nsplit;
+    b.dh_direct = g.dh_carry; b.dh_direct_ld = s.H;
+    PVCR_TRY(gru_gate_bwd(b, st));
+    if (has_prev)
+      PVCR_TRY(gemm_planes(g.dgh_a.view(), g.whhT.view(), s.B, s.H, (int)g.dgh_a.ld, g.dh_carry, s.H, nullptr, 1, st));
+  }
+  return PVCR_OK;
+}
+
+}  // namespace pvcr

@@ -1,0 +1,310 @@
+// S2VTAttModel encoder + attention decoder, forward and hand-written backward.
+// Reference: model/S2VTAttModel.py:80-96 (Encoder.forward), :125-148 (Decoder.forward_step),
+// :150-196 (Decoder.forward), :25-48 (Attention.forward).
+//
+// Restructuring relative to the reference loop (same arithmetic):
+//   * encoder input projection hoisted into one GEMM over all B*N frames (K1);
+//   * W_ih of the decoder split into [Wc | We]; the embedding half is hoisted into one GEMM over all B*L
+//     tokens (K8/K9), the context half stays in the step;
+//   * W_q and W_hh of the decoder are concatenated so that q = W_q h and gh = W_hh h are one GEMM per step;
+//   * every weight gradient is hoisted out of the time loop into one GEMM over all steps.
+#include "../../include/pvcr_b200.h"
+#include "host.h"
+
+namespace pvcr {
+
+struct AttWs {
+  // prepared weights (forward)
+  Planes wih_enc, whh_enc, wk, wcat, wc, we;
+  // forward activations
+  Planes x_a, enc_a, emb_a, ctx_a, hs_a;
+  float *gi_enc, *enc, *er, *ez, *en, *eghn, *gh, *pk, *ep, *g1_all, *alpha_all, *ctx_all, *g2, *dr, *dz, *dn, *dghn;
+  // backward
+  Planes wcT, wcatT, wkT, weT, whh_encT, wih_encT, dgi_a, d1_a, dgh_a;
+  float *dh_carry, *dgi_all, *d1_all, *dctx, *dpk, *denc, *dv_part, *dgi_enc, *dgh_enc, *hprev_dec, *hprev_enc,
+      *demb_rows, *dxsel;
+};
+
+static size_t scratch_need(const PvcrDims& d, int need_frame_grad) {
+  // peak of the transient operand planes used by grad_w / grad_x in the hoisted gradient GEMMs
+  Arena a(nullptr, 0);
+  size_t peak = 0;
+  auto gw = [&](int R, int N, int K) {
+    size_t m = a.mark();
+    alloc_planes(a, N, R, d.nsplit); alloc_planes(a, K, R, d.nsplit);
+    if (a.off > peak) peak = a.off;
+    a.release(m);
+  };
+  auto gx = [&](int R, int N) {
+    size_t m = a.mark();
+    alloc_planes(a, R, N, d.nsplit);
+    if (a.off > peak) peak = a.off;
+    a.release(m);
+  };
+  const int BL = d.B * d.L, BN = d.B * d.N, H = d.H;
+  gw(BL, 4 * H, H); gw(BL, 3 * H, H); gw(BL, 3 * H, d.E); gx(BL, 3 * H);
+  gw(BN, H, H); gx(BN, H); gw(BN, 3 * H, H); gw(BN, 3 * H, d.V);
+  if (need_frame_grad) gx(BN, 3 * H);
+  return peak + 4096;
+}
+
+static void carve(Arena& a, const PvcrDims& d, int need_frame_grad, AttWs& w) {
+  const int B = d.B, N = d.N, V = d.V, H = d.H, E = d.E, L = d.L, ns = d.nsplit;
+  const size_t BN = (size_t)B * N, BL = (size_t)B * L;
+  w.wih_enc = alloc_planes(a, 3 * H, V, ns);
+  w.whh_enc = alloc_planes(a, 3 * H, H, ns);
+  w.wk = alloc_planes(a, H, H, ns);
+  w.wcat = alloc_planes(a, 4 * H, H, ns);
+  w.wc = alloc_planes(a, 3 * H, H, ns);
+  w.we = alloc_planes(a, 3 * H, E, ns);
+  w.x_a = alloc_planes(a, (int)BN, V, ns);
+  w.enc_a = alloc_planes(a, (int)BN, H, ns);
+  w.emb_a = alloc_planes(a, (int)BL, E, ns);
+  w.ctx_a = alloc_planes(a, B, H, ns);
+  w.hs_a = alloc_planes(a, (int)BL, H, ns);
+  w.gi_enc = a.alloc<float>(BN * 3 * H);
+  w.enc = a.alloc<float>(BN * H);
+  w.er = a.alloc<float>(BN * H); w.ez = a.alloc<float>(BN * H); w.en = a.alloc<float>(BN * H); w.eghn = a.alloc<float>(BN * H);
+  w.gh = a.alloc<float>((size_t)B * 3 * H);
+  w.pk = a.alloc<float>(BN * H);
+  w.ep = a.alloc<float>(BL * 3 * H);
+  w.g1_all = a.alloc<float>(BL * 4 * H);
+  w.alpha_all = a.alloc<float>(BL * N);
+  w.ctx_all = a.alloc<float>(BL * H);
+  w.g2 = a.alloc<float>((size_t)B * 3 * H);
+  w.dr = a.alloc<float>(BL * H); w.dz = a.alloc<float>(BL * H); w.dn = a.alloc<float>(BL * H); w.dghn = a.alloc<float>(BL * H);
+  // backward
+  w.wcT = alloc_planes(a, H, 3 * H, ns);
+  w.wcatT = alloc_planes(a, H, 4 * H, ns);
+  w.wkT = alloc_planes(a, H, H, ns);
+  w.weT = alloc_planes(a, E, 3 * H, ns);
+  w.whh_encT = alloc_planes(a, H, 3 * H, ns);
+  if (need_frame_grad) w.wih_encT = alloc_planes(a, V, 3 * H, ns); else w.wih_encT = Planes{};
+  w.dgi_a = alloc_planes(a, B, 3 * H, ns);
+  w.d1_a = alloc_planes(a, B, 4 * H, ns);
+  w.dgh_a = alloc_planes(a, B, 3 * H, ns);
+  w.dh_carry = a.alloc<float>((size_t)B * H);
+  w.dgi_all = a.alloc<float>(BL * 3 * H);
+  w.d1_all = a.alloc<float>(BL * 4 * H);
+  w.dctx = a.alloc<float>((size_t)B * H);
+  w.dpk = a.alloc<float>(BN * H);
+  w.denc = a.alloc<float>(BN * H);
+  w.dv_part = a.alloc<float>((size_t)B * H);
+  w.dgi_enc = a.alloc<float>(BN * 3 * H);
+  w.dgh_enc = a.alloc<float>(BN * 3 * H);
+  w.hprev_dec = a.alloc<float>(BL * H);
+  w.hprev_enc = a.alloc<float>(BN * H);
+  w.demb_rows = a.alloc<float>(BL * E);
+  w.dxsel = need_frame_grad ? a.alloc<float>(BN * V) : nullptr;
+}
+
+size_t s2vtatt_workspace(const PvcrDims& d, int need_frame_grad) {
+  Arena a(nullptr, 0);
+  AttWs w;
+  carve(a, d, need_frame_grad, w);
+  return a.off + scratch_need(d, need_frame_grad) + 1024;
+}
+
+static int check_dims(const PvcrDims& d) {
+  PVCR_REQUIRE(d.B > 0 && d.N > 0 && d.V > 0 && d.H > 0 && d.E > 0 && d.L > 0 && d.Vc > 0,
+               "dims must be positive: B=%d N=%d V=%d H=%d E=%d L=%d Vc=%d", d.B, d.N, d.V, d.H, d.E, d.L, d.Vc);
+  PVCR_REQUIRE(d.nsplit >= 1 && d.nsplit <= 3, "nsplit=%d not in 1..3", d.nsplit);
+  return PVCR_OK;
+}
+
+static GruSeq encoder_seq(const PvcrDims& d, const PvcrS2vtAttParams& p, const AttWs& w) {
+  const int H = d.H, N = d.N;
+  GruSeq s{};
+  s.T = N; s.B = d.B; s.H = H; s.nsplit = d.nsplit;
+  s.gi_a = w.gi_enc; s.gi_a_ts = 3 * H; s.gi_a_ld = (long long)N * 3 * H;       // rows b*N + t
+  s.b_hh = p.enc_b_hh;
+  s.whh = w.whh_enc;
+  s.h = w.enc; s.h_ts = H; s.h_ld = (long long)N * H;
+  s.hp = w.enc_a.ptr; s.hp_ts = w.enc_a.ld; s.hp_ld = (long long)N * w.enc_a.ld; s.Hp = w.enc_a.Kp;
+  s.gh = w.gh;
+  s.r = w.er; s.z = w.ez; s.n = w.en; s.ghn = w.eghn;
+  return s;
+}
+
+int s2vtatt_fwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid, const float* frame_scale,
+                const long long* s_in, float* hs, float* alphas, void* ws, size_t ws_bytes, cudaStream_t st) {
+  PVCR_TRY(check_dims(d));
+  const int B = d.B, N = d.N, V = d.V, H = d.H, E = d.E, L = d.L;
+  const int BN = B * N, BL = B * L, H3 = 3 * H, H4 = 4 * H;
+  Arena a(ws, ws_bytes);
+  AttWs w;
+  carve(a, d, 0, w);
+  if (a.failed) { set_last_error("s2vtatt_fwd: workspace too small (%zu < %zu)", ws_bytes, a.off); return PVCR_ERR_WORKSPACE; }
+
+  // weights -> B-role planes
+  PVCR_TRY(prep_weight(p.enc_w_ih, V, H3, V, w.wih_enc, st));
+  PVCR_TRY(prep_weight(p.enc_w_hh, H, H3, H, w.whh_enc, st));
+  PVCR_TRY(prep_weight(p.att_wk, H, H, H, w.wk, st));
+  PVCR_TRY(prep_weight(p.att_wq, H, H, H, w.wcat, st, 0));
+  PVCR_TRY(prep_weight(p.dec_w_hh, H, H3, H, w.wcat, st, H));
+  PVCR_TRY(prep_weight(p.dec_w_ih, H + E, H3, H, w.wc, st));
+  PVCR_TRY(prep_weight(p.dec_w_ih + H, H + E, H3, E, w.we, st));
+
+  if (w.enc_a.Kp != H) {       // contraction padding of the planes written by the gate kernels must read as zero
+    PVCR_TRY(fill_zero(w.enc_a.ptr, sizeof(bf16) * (size_t)BN * w.enc_a.ld, st));
+    PVCR_TRY(fill_zero(w.hs_a.ptr, sizeof(bf16) * (size_t)BL * w.hs_a.ld, st));
+    PVCR_TRY(fill_zero(w.ctx_a.ptr, sizeof(bf16) * (size_t)B * w.ctx_a.ld, st));
+  }
+  // encoder: gi = (vid * frame_scale) W_ih^T + b_ih for all frames, then N recurrent steps
+  PVCR_TRY(stage(vid, V, BN, V, w.x_a, 0, frame_scale, NO_DROPOUT, st));
+  PVCR_TRY(gemm_planes(w.x_a.view(), w.wih_enc.view(), BN, H3, (int)w.x_a.ld, w.gi_enc, H3, p.enc_b_ih, 0, st));
+  PVCR_TRY(gru_seq_fwd(encoder_seq(d, p, w), st));
+
+  // proj_key = enc W_k^T ; hoisted embedding half of the decoder input projection (+ b_ih)
+  PVCR_TRY(gemm_planes(w.enc_a.view(), w.wk.view(), BN, H, (int)w.enc_a.ld, w.pk, H, nullptr, 0, st));
+  PVCR_TRY(gather_split(p.emb, E, s_in, BL, w.emb_a.ptr, w.emb_a.ld, w.emb_a.Kp, d.nsplit, NO_DROPOUT, st));
+  PVCR_TRY(gemm_planes(w.emb_a.view(), w.we.view(), BL, H3, (int)w.emb_a.ld, w.ep, H3, p.dec_b_ih, 0, st));
+
+  // decoder steps
+  for (int i = 0; i < L; ++i) {
+    OperandView hprev_a = (i == 0)
+        ? OperandView{w.enc_a.ptr + (long long)(N - 1) * w.enc_a.ld, (long long)N * w.enc_a.ld, 0, B, 1}
+        : OperandView{w.hs_a.ptr + (long long)(i - 1) * w.hs_a.ld, (long long)L * w.hs_a.ld, 0, B, 1};
+    float* g1 = w.g1_all + (long long)i * B * H4;
+    PVCR_TRY(gemm_planes(hprev_a, w.wcat.view(), B, H4, (int)w.wcat.ld, g1, H4, nullptr, 0, st));
+    AttnFwdArgs at{};
+    at.B = B; at.N = N; at.H = H;
+    at.q = g1; at.q_ld = H4; at.pk = w.pk; at.enc = w.enc; at.v = p.att_v;
+    at.alpha = w.alpha_all + (long long)i * B * N;
+    at.ctx = w.ctx_all + (long long)i * H; at.ctx_ld = (long long)L * H;             // rows b*L + i
+    at.ctx_planes = w.ctx_a.ptr; at.ctx_planes_ld = w.ctx_a.ld; at.Hp = w.ctx_a.Kp; at.nsplit = d.nsplit;
+    PVCR_TRY(attn_fwd(at, st));
+    PVCR_TRY(gemm_planes(w.ctx_a.view(), w.wc.view(), B, H3, (int)w.ctx_a.ld, w.g2, H3, nullptr, 0, st));
+    GruFwdArgs g{};
+    g.B = B; g.H = H;
+    g.gi_a = w.g2; g.gi_a_ld = H3;
+    g.gi_b = w.ep + (long long)i * H3; g.gi_b_ld = (long long)L * H3;
+    g.gh = g1 + H; g.gh_ld = H4; g.b_hh = p.dec_b_hh;
+    if (i == 0) { g.h_prev = w.enc + (long long)(N - 1) * H; g.h_prev_ld = (long long)N * H; }
+    else { g.h_prev = hs + (long long)(i - 1) * H; g.h_prev_ld = (long long)L * H; }
+    g.h_out = hs + (long long)i * H; g.h_out_ld = (long long)L * H;
+    g.h_planes = w.hs_a.ptr + (long long)i * w.hs_a.ld; g.h_planes_ld = (long long)L * w.hs_a.ld;
+    g.Hp = w.hs_a.Kp; g.nsplit = d.nsplit;
+    const long long o = (long long)i * B * H;
+    g.r = w.dr + o; g.z = w.dz + o; g.n = w.dn + o; g.ghn = w.dghn + o;
+    PVCR_TRY(gru_gate_fwd(g, st));
+  }
+  if (alphas)
+    PVCR_CUDA_CHECK(cudaMemcpyAsync(alphas, w.alpha_all, sizeof(float) * (size_t)L * B * N, cudaMemcpyDeviceToDevice, st));
+  return PVCR_OK;
+}
+
+int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid, const float* frame_scale,
+                const long long* s_in, const float* d_hs, const float* hs, PvcrS2vtAttGrads& g, float* d_frame_scale,
+                void* ws, size_t ws_bytes, cudaStream_t st) {
+  PVCR_TRY(check_dims(d));
+  const int B = d.B, N = d.N, V = d.V, H = d.H, E = d.E, L = d.L, ns = d.nsplit;
+  const int BN = B * N, BL = B * L, H3 = 3 * H, H4 = 4 * H;
+  const int need_frame_grad = d_frame_scale != nullptr;
+  Arena a(ws, ws_bytes);
+  AttWs w;
+  carve(a, d, need_frame_grad, w);
+  if (a.failed || a.off + scratch_need(d, need_frame_grad) > ws_bytes) {
+    set_last_error("s2vtatt_bwd: workspace too small (%zu bytes)", ws_bytes);
+    return PVCR_ERR_WORKSPACE;
+  }
+  // transposed weights for the data-gradient GEMMs
+  PVCR_TRY(prep_weight_T(p.dec_w_ih, H + E, H3, H, w.wcT, 0, 1, st));
+  PVCR_TRY(fill_zero(w.wcatT.ptr, sizeof(bf16) * (size_t)w.wcatT.rows * w.wcatT.ld, st));
+  PVCR_TRY(prep_weight_T(p.att_wq, H, H, H, w.wcatT, 0, 0, st));
+  PVCR_TRY(prep_weight_T(p.dec_w_hh, H, H3, H, w.wcatT, H, 0, st));
+  PVCR_TRY(prep_weight_T(p.att_wk, H, H, H, w.wkT, 0, 1, st));
+  PVCR_TRY(prep_weight_T(p.dec_w_ih + H, H + E, H3, E, w.weT, 0, 1, st));
+  PVCR_TRY(prep_weight_T(p.enc_w_hh, H, H3, H, w.whh_encT, 0, 1, st));
+  if (need_frame_grad) PVCR_TRY(prep_weight_T(p.enc_w_ih, V, H3, V, w.wih_encT, 0, 1, st));
+
+  PVCR_TRY(fill_zero(w.dh_carry, sizeof(float) * (size_t)B * H, st));
+  PVCR_TRY(fill_zero(w.dpk, sizeof(float) * (size_t)BN * H, st));
+  PVCR_TRY(fill_zero(w.denc, sizeof(float) * (size_t)BN * H, st));
+  PVCR_TRY(fill_zero(w.dv_part, sizeof(float) * (size_t)B * H, st));
+  if (w.d1_a.Kp != H4 || w.dgi_a.Kp != H3) {     // contraction padding must read as zero
+    PVCR_TRY(fill_zero(w.d1_a.ptr, sizeof(bf16) * (size_t)B * w.d1_a.ld, st));
+    PVCR_TRY(fill_zero(w.dgi_a.ptr, sizeof(bf16) * (size_t)B * w.dgi_a.ld, st));
+    PVCR_TRY(fill_zero(w.dgh_a.ptr, sizeof(bf16) * (size_t)B * w.dgh_a.ld, st));
+  }
+
+  // ---- decoder, reverse time ----
+  for (int i = L - 1; i >= 0; --i) {
+    GruBwdArgs b{};
+    b.B = B; b.H = H;
+    b.dh_a = w.dh_carry; b.dh_a_ld = H;
+    b.dh_b = d_hs + (long long)i * H; b.dh_b_ld = (long long)L * H;
+    const long long o = (long long)i * B * H;
+    b.r = w.dr + o; b.z = w.dz + o; b.n = w.dn + o; b.ghn = w.dghn + o;
+    if (i == 0) { b.h_prev = w.enc + (long long)(N - 1) * H; b.h_prev_ld = (long long)N * H; }
+    else { b.h_prev = hs + (long long)(i - 1) * H; b.h_prev_ld = (long long)L * H; }
+    b.dgi = w.dgi_all + (long long)i * H3; b.dgi_ld = (long long)L * H3;           // rows b*L + i
+    b.dgh = w.d1_all + (long long)i * H4 + H; b.dgh_ld = (long long)L * H4;
+    b.dgi_planes = w.dgi_a.ptr; b.dgi_planes_ld = w.dgi_a.ld; b.dgi_Kp = w.dgi_a.Kp; b.dgi_col0 = 0;
+    b.dgh_planes = w.d1_a.ptr; b.dgh_planes_ld = w.d1_a.ld; b.dgh_Kp = w.d1_a.Kp; b.dgh_col0 = H;
+    b.nsplit = ns;
+    b.dh_direct = w.dh_carry; b.dh_direct_ld = H;
+    PVCR_TRY(gru_gate_bwd(b, st));
+    // dctx = dgi Wc
+    PVCR_TRY(gemm_planes(w.dgi_a.view(), w.wcT.view(), B, H, (int)w.dgi_a.ld, w.dctx, H, nullptr, 0, st));
+    AttnBwdArgs at{};
+    at.B = B; at.N = N; at.H = H;
+    at.dctx = w.dctx; at.dctx_ld = H;
+    at.q = w.g1_all + (long long)i * B * H4; at.q_ld = H4;
+    at.pk = w.pk; at.enc = w.enc; at.v = p.att_v; at.alpha = w.alpha_all + (long long)i * B * N;
+    at.dq = w.d1_all + (long long)i * H4; at.dq_ld = (long long)L * H4;
+    at.dq_planes = w.d1_a.ptr; at.dq_planes_ld = w.d1_a.ld; at.dq_Kp = w.d1_a.Kp; at.nsplit = ns;
+    at.dpk = w.dpk; at.denc = w.denc; at.dv_part = w.dv_part;
+    PVCR_TRY(attn_bwd(at, st));
+    // dh_{i-1} = dh*z + [dq | dgh] [Wq ; Whh]
+    PVCR_TRY(gemm_planes(w.d1_a.view(), w.wcatT.view(), B, H, (int)w.d1_a.ld, w.dh_carry, H, nullptr, 1, st));
+  }
+
+  // ---- decoder weight gradients, hoisted over all (b, i) rows ----
+  // h_{i-1} rows in (b, i) order: i = 0 -> encoder final state, i >= 1 -> hs[b, i-1]
+  PVCR_CUDA_CHECK(cudaMemcpy2DAsync(w.hprev_dec, sizeof(float) * (size_t)L * H, w.enc + (long long)(N - 1) * H,
+                                    sizeof(float) * (size_t)N * H, sizeof(float) * H, B, cudaMemcpyDeviceToDevice, st));
+  if (L > 1)
+    PVCR_CUDA_CHECK(cudaMemcpy2DAsync(w.hprev_dec + H, sizeof(float) * (size_t)L * H, hs, sizeof(float) * (size_t)L * H,
+                                      sizeof(float) * (size_t)(L - 1) * H, B, cudaMemcpyDeviceToDevice, st));
+  PVCR_TRY(grad_w(a, w.d1_all, H4, BL, H, w.hprev_dec, H, H, nullptr, nullptr, g.att_wq, H, 0, ns, st));
+  PVCR_TRY(grad_w(a, w.d1_all + H, H4, BL, H3, w.hprev_dec, H, H, nullptr, nullptr, g.dec_w_hh, H, 0, ns, st));
+  PVCR_TRY(colsum(w.d1_all + H, H4, BL, H3, g.dec_b_hh, 0, st));
+  PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, w.ctx_all, H, H, nullptr, nullptr, g.dec_w_ih, H + E, 0, ns, st));
+  PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, p.emb, E, E, s_in, nullptr, g.dec_w_ih + H, H + E, 0, ns, st));
+  PVCR_TRY(colsum(w.dgi_all, H3, BL, H3, g.dec_b_ih, 0, st));
+  PVCR_TRY(grad_x(a, w.dgi_all, H3, BL, H3, w.weT, w.demb_rows, E, 0, st));
+  PVCR_TRY(fill_zero(g.emb, sizeof(float) * (size_t)d.Vc * E, st));
+  PVCR_TRY(scatter_add_rows(w.demb_rows, E, s_in, BL, E, g.emb, NO_DROPOUT, st));
+  PVCR_TRY(colsum(w.dv_part, H, B, H, g.att_v, 0, st));
+  // key projection: dWk = dpk^T enc ; denc += dpk Wk
+  PVCR_TRY(grad_w(a, w.dpk, H, BN, H, w.enc, H, H, nullptr, nullptr, g.att_wk, H, 0, ns, st));
+  PVCR_TRY(grad_x(a, w.dpk, H, BN, H, w.wkT, w.denc, H, 1, st));
+
+  // ---- encoder, reverse time (dh_carry already holds the gradient on the final state) ----
+  GruSeq es = encoder_seq(d, p, w);
+  GruSeqGrad eg{};
+  eg.dh_ext = w.denc; eg.dh_ext_ts = H; eg.dh_ext_ld = (long long)N * H;
+  eg.dh_carry = w.dh_carry;
+  eg.dgi = w.dgi_enc; eg.dgi_ts = H3; eg.dgi_ld = (long long)N * H3;
+  eg.dgh = w.dgh_enc; eg.dgh_ts = H3; eg.dgh_ld = (long long)N * H3;
+  eg.dgh_a = w.dgh_a; eg.whhT = w.whh_encT;
+  PVCR_TRY(gru_seq_bwd(es, eg, st));
+  // h_{t-1} rows in (b, t) order: zero for t = 0
+  PVCR_TRY(fill_zero(w.hprev_enc, sizeof(float) * (size_t)BN * H, st));
+  if (N > 1)
+    PVCR_CUDA_CHECK(cudaMemcpy2DAsync(w.hprev_enc + H, sizeof(float) * (size_t)N * H, w.enc, sizeof(float) * (size_t)N * H,
+                                      sizeof(float) * (size_t)(N - 1) * H, B, cudaMemcpyDeviceToDevice, st));
+  PVCR_TRY(grad_w(a, w.dgh_enc, H3, BN, H3, w.hprev_enc, H, H, nullptr, nullptr, g.enc_w_hh, H, 0, ns, st));
+  PVCR_TRY(colsum(w.dgh_enc, H3, BN, H3, g.enc_b_hh, 0, st));
+  PVCR_TRY(grad_w(a, w.dgi_enc, H3, BN, H3, vid, V, V, nullptr, frame_scale, g.enc_w_ih, V, 0, ns, st));
+  PVCR_TRY(colsum(w.dgi_enc, H3, BN, H3, g.enc_b_ih, 0, st));
+  if (need_frame_grad) {
+    // d(sel) = dgi W_ih ; d frame_scale[b,n] = sum_v vid[b,n,v] * dsel[b,n,v]   (model/RationaleNet.py:52)
+    PVCR_TRY(grad_x(a, w.dgi_enc, H3, BN, H3, w.wih_encT, w.dxsel, V, 0, st));
+    PVCR_TRY(rowdot(vid, w.dxsel, BN, V, d_frame_scale, st));
+  }
+  return PVCR_OK;
+}
+
+}  // namespace pvcr

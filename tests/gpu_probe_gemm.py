@@ -1,5 +1,8 @@
 """Timing probe for the GEMM at the cfg2 shapes (prints TFLOP/s; not a test)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+import pvcr_b200
 from pvcr_b200 import _lib
 from pvcr_b200._lib import lib, ptr, stream_ptr, check
 
