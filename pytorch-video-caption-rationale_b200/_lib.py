@@ -8,7 +8,6 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpvcr_b200.so")
 
-c_f32p = ctypes.c_void_p
 c_i64 = ctypes.c_int64
 c_int = ctypes.c_int
 c_size = ctypes.c_size_t
@@ -23,6 +22,30 @@ class PvcrError(RuntimeError):
     pass
 
 
+class PvcrDims(ctypes.Structure):
+    _fields_ = [("B", c_int), ("N", c_int), ("V", c_int), ("H", c_int), ("E", c_int), ("L", c_int), ("Vc", c_int),
+                ("nsplit", c_int), ("dropout_p", c_f), ("seed", c_u64)]
+
+
+ATT_PARAM_FIELDS = ["enc_w_ih", "enc_w_hh", "enc_b_ih", "enc_b_hh", "emb", "dec_w_ih", "dec_w_hh", "dec_b_ih",
+                    "dec_b_hh", "att_wk", "att_wq", "att_v", "out_w", "out_b"]
+S2VT_PARAM_FIELDS = ["emb", "rnn1_w_ih", "rnn1_w_hh", "rnn1_b_ih", "rnn1_b_hh", "rnn2_w_ih", "rnn2_w_hh", "rnn2_b_ih",
+                     "rnn2_b_hh", "out_w", "out_b"]
+GEN_PARAM_FIELDS = ["w_ih", "w_hh", "b_ih", "b_hh", "w_ih_r", "w_hh_r", "b_ih_r", "b_hh_r", "lin_w", "lin_b"]
+
+
+def _ptr_struct(name, fields):
+    return type(name, (ctypes.Structure,), {"_fields_": [(f, c_vp) for f in fields]})
+
+
+PvcrS2vtAttParams = _ptr_struct("PvcrS2vtAttParams", ATT_PARAM_FIELDS)
+PvcrS2vtAttGrads = _ptr_struct("PvcrS2vtAttGrads", ATT_PARAM_FIELDS)
+PvcrS2vtParams = _ptr_struct("PvcrS2vtParams", S2VT_PARAM_FIELDS)
+PvcrS2vtGrads = _ptr_struct("PvcrS2vtGrads", S2VT_PARAM_FIELDS)
+PvcrGenParams = _ptr_struct("PvcrGenParams", GEN_PARAM_FIELDS)
+PvcrGenGrads = _ptr_struct("PvcrGenGrads", GEN_PARAM_FIELDS)
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -35,18 +58,36 @@ def lib():
     return _lib
 
 
-def _sig(fn, restype, argtypes):
+def _sig(L, name, restype, argtypes):
+    fn = getattr(L, name)
     fn.restype = restype
     fn.argtypes = argtypes
 
 
+# name -> (restype, argtypes); mirrors include/pvcr_b200.h one to one (tests/test_abi.py cross-checks the header)
+P = ctypes.POINTER
+SIGNATURES = {
+    "pvcr_linear_fwd_workspace": (c_size, [c_int, c_int, c_int, c_int]),
+    "pvcr_linear_fwd": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_size,
+                                c_vp]),
+    "pvcr_linear_bwd_workspace": (c_size, [c_int, c_int, c_int, c_int]),
+    "pvcr_linear_bwd": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_int,
+                                c_int, c_int, c_int, c_vp, c_size, c_vp]),
+    "pvcr_s2vtatt_workspace": (c_size, [P(PvcrDims), c_int]),
+    "pvcr_s2vtatt_fwd": (c_int, [P(PvcrDims), P(PvcrS2vtAttParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
+    "pvcr_s2vtatt_bwd": (c_int, [P(PvcrDims), P(PvcrS2vtAttParams), c_vp, c_vp, c_vp, c_vp, c_vp, P(PvcrS2vtAttGrads),
+                                 c_vp, c_vp, c_size, c_vp]),
+    "pvcr_vocab_ce_workspace": (c_size, [c_int, c_int, c_int, c_int, c_int, c_f]),
+    "pvcr_vocab_ce_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_u64, c_vp,
+                                  c_vp, c_vp, c_vp, c_i64, c_vp, c_size, c_vp]),
+    "pvcr_vocab_ce_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_u64, c_vp, c_vp,
+                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
+}
+
+
 def _declare(L):
-    _sig(L.pvcr_linear_fwd_workspace, c_size, [c_int, c_int, c_int, c_int])
-    _sig(L.pvcr_linear_fwd, c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp,
-                                    c_size, c_vp])
-    _sig(L.pvcr_linear_bwd_workspace, c_size, [c_int, c_int, c_int, c_int])
-    _sig(L.pvcr_linear_bwd, c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_int,
-                                    c_int, c_int, c_int, c_int, c_vp, c_size, c_vp])
+    for name, (res, args) in SIGNATURES.items():
+        _sig(L, name, res, args)
 
 
 def check(rc, what):

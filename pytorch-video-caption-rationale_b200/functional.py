@@ -1,0 +1,173 @@
+"""torch.autograd bindings of the model-level C-ABI entry points (include/pvcr_b200.h).
+
+PyTorch supplies device memory, the current stream and the autograd tape; every FLOP runs in
+libpvcr_b200.so.  Nothing here falls back to torch ops: without the library the calls raise.
+"""
+import ctypes
+import itertools
+
+import torch
+
+from . import _lib
+from ._lib import (ATT_PARAM_FIELDS, PvcrDims, PvcrS2vtAttGrads, PvcrS2vtAttParams, check, lib, ptr, stream_ptr)
+
+_seed_counter = itertools.count(1)
+
+
+def next_seed():
+    """Per-call Philox seed derived from torch's global seed (dropout / Gumbel draws inside the kernels)."""
+    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + next(_seed_counter) * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+
+
+def _f32c(t):
+    assert t.is_cuda, "pvcr_b200 runs on CUDA tensors only (no CPU path)"
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _i64c(t):
+    assert t.is_cuda
+    return t.detach().to(torch.int64).contiguous()
+
+
+def _ws(nbytes, device):
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+
+
+def make_dims(B, N, V, H, E, L, Vc, nsplit=1, dropout_p=0.0, seed=0):
+    return PvcrDims(B, N, V, H, E, L, Vc, nsplit, float(dropout_p), seed)
+
+
+def _fill_struct(struct, fields, tensors):
+    for f in fields:
+        t = tensors.get(f)
+        setattr(struct, f, None if t is None else t.data_ptr())
+    return struct
+
+
+ATT_SEQ_FIELDS = [f for f in ATT_PARAM_FIELDS if f not in ("out_w", "out_b")]
+
+
+class S2VTAttSequence(torch.autograd.Function):
+    """Encoder GRU + attention decoder, teacher forced: (vid_feats, frame_scale, s_in, params) -> hs, alphas.
+
+    Replaces Encoder.forward + the Decoder.forward loop of the reference (model/S2VTAttModel.py:80-96,150-196)
+    up to the vocabulary projection."""
+
+    @staticmethod
+    def forward(ctx, cfg, vid, frame_scale, s_in, *params):
+        B, N, V = vid.shape
+        L = s_in.shape[1]
+        tensors = {f: _f32c(p) for f, p in zip(ATT_SEQ_FIELDS, params)}
+        H = tensors["enc_w_hh"].shape[1]
+        Vc, E = tensors["emb"].shape
+        dims = make_dims(B, N, V, H, E, L, Vc, cfg["nsplit"], 0.0, 0)
+        vid_c = _f32c(vid)
+        fs_c = None if frame_scale is None else _f32c(frame_scale)
+        s_c = _i64c(s_in)
+        need_fg = int(frame_scale is not None and frame_scale.requires_grad)
+        Lb = lib()
+        ws = _ws(Lb.pvcr_s2vtatt_workspace(ctypes.byref(dims), need_fg), vid.device)
+        hs = torch.empty((B, L, H), dtype=torch.float32, device=vid.device)
+        alphas = torch.empty((L, B, N), dtype=torch.float32, device=vid.device)
+        ps = _fill_struct(PvcrS2vtAttParams(), ATT_SEQ_FIELDS, tensors)
+        check(Lb.pvcr_s2vtatt_fwd(ctypes.byref(dims), ctypes.byref(ps), ptr(vid_c), ptr(fs_c), ptr(s_c), ptr(hs),
+                                  ptr(alphas), ptr(ws), ws.numel(), stream_ptr()), "pvcr_s2vtatt_fwd")
+        ctx.dims = dims
+        ctx.need_fg = need_fg
+        ctx.keep = (vid_c, fs_c, s_c, hs, ws, tensors)
+        ctx.mark_non_differentiable(alphas)
+        return hs, alphas
+
+    @staticmethod
+    def backward(ctx, d_hs, _d_alphas):
+        vid_c, fs_c, s_c, hs, ws, tensors = ctx.keep
+        d_hs = _f32c(d_hs)
+        grads = {f: torch.empty_like(t) for f, t in tensors.items()}
+        d_fs = torch.empty_like(fs_c) if ctx.need_fg else None
+        ps = _fill_struct(PvcrS2vtAttParams(), ATT_SEQ_FIELDS, tensors)
+        gs = _fill_struct(PvcrS2vtAttGrads(), ATT_SEQ_FIELDS, grads)
+        Lb = lib()
+        check(Lb.pvcr_s2vtatt_bwd(ctypes.byref(ctx.dims), ctypes.byref(ps), ptr(vid_c), ptr(fs_c), ptr(s_c), ptr(hs),
+                                  ptr(d_hs), ctypes.byref(gs), ptr(d_fs), ptr(ws), ws.numel(), stream_ptr()),
+              "pvcr_s2vtatt_bwd")
+        return (None, None, d_fs, None) + tuple(grads[f] for f in ATT_SEQ_FIELDS)
+
+
+class VocabCrossEntropy(torch.autograd.Function):
+    """Dropout + Linear(H -> Vc) fused with calc_masked_loss / calc_masked_accuracy / argmax
+    (model/S2VTAttModel.py:145, train_utils.py:37-71, train.py:38): (hs, W, b, target, s_len) -> loss, stats, pred."""
+
+    @staticmethod
+    def forward(ctx, cfg, hs, out_w, out_b, target, s_len):
+        B, L, H = hs.shape
+        Vc = out_w.shape[0]
+        hs_c, w_c, b_c = _f32c(hs), _f32c(out_w), _f32c(out_b)
+        t_c, l_c = _i64c(target), _i64c(s_len)
+        Lb = lib()
+        nsplit, p, seed = cfg["nsplit"], float(cfg.get("dropout_p", 0.0)), int(cfg.get("seed", 0))
+        ws = _ws(Lb.pvcr_vocab_ce_workspace(B, L, H, Vc, nsplit, p), hs.device)
+        loss3 = torch.empty(3, dtype=torch.float32, device=hs.device)
+        pred = torch.empty((B, L), dtype=torch.int64, device=hs.device)
+        lse = torch.empty((B, L), dtype=torch.float32, device=hs.device)
+        check(Lb.pvcr_vocab_ce_fwd(ptr(hs_c), ptr(w_c), ptr(b_c), ptr(t_c), ptr(l_c), B, L, H, Vc, nsplit, p, seed,
+                                   ptr(loss3), ptr(pred), ptr(lse), None, 0, ptr(ws), ws.numel(), stream_ptr()),
+              "pvcr_vocab_ce_fwd")
+        ctx.cfg = (B, L, H, Vc, nsplit, p, seed)
+        ctx.keep = (hs_c, w_c, t_c, l_c, ws, lse, pred)
+        ctx.mark_non_differentiable(pred)
+        stats = loss3[1:].clone()
+        ctx.mark_non_differentiable(stats)
+        return loss3[0].clone(), stats, pred
+
+    @staticmethod
+    def backward(ctx, d_loss, _d_stats, _d_pred):
+        B, L, H, Vc, nsplit, p, seed = ctx.cfg
+        hs_c, w_c, t_c, l_c, ws, lse, pred = ctx.keep
+        gscale = _f32c(d_loss).reshape(1)
+        d_hs = torch.empty_like(hs_c)
+        d_w = torch.empty_like(w_c)
+        d_b = torch.empty((Vc,), dtype=torch.float32, device=hs_c.device)
+        Lb = lib()
+        check(Lb.pvcr_vocab_ce_bwd(ptr(hs_c), ptr(w_c), ptr(t_c), ptr(l_c), B, L, H, Vc, nsplit, p, seed, ptr(gscale),
+                                   ptr(d_hs), ptr(d_w), ptr(d_b), ptr(lse), ptr(pred), ptr(ws), ws.numel(),
+                                   stream_ptr()), "pvcr_vocab_ce_bwd")
+        return None, d_hs, d_w, d_b, None, None
+
+
+class VocabLogits(torch.autograd.Function):
+    """logits = Dropout(hs) W^T + b, materialised (the reference module API returns the [B,L,Vc] tensor)."""
+
+    @staticmethod
+    def forward(ctx, cfg, hs, out_w, out_b):
+        B, L, H = hs.shape
+        Vc = out_w.shape[0]
+        hs_c, w_c, b_c = _f32c(hs), _f32c(out_w), _f32c(out_b)
+        nsplit, p, seed = cfg["nsplit"], float(cfg.get("dropout_p", 0.0)), int(cfg.get("seed", 0))
+        Lb = lib()
+        ws = _ws(Lb.pvcr_vocab_ce_workspace(B, L, H, Vc, nsplit, p), hs.device)
+        logits = torch.empty((B, L, Vc), dtype=torch.float32, device=hs.device)
+        check(Lb.pvcr_vocab_ce_fwd(ptr(hs_c), ptr(w_c), ptr(b_c), None, None, B, L, H, Vc, nsplit, p, seed, None, None,
+                                   None, ptr(logits), Vc, ptr(ws), ws.numel(), stream_ptr()), "pvcr_vocab_ce_fwd")
+        ctx.cfg = (B, L, H, Vc, nsplit, p, seed)
+        ctx.keep = (hs_c, w_c)
+        return logits
+
+    @staticmethod
+    def backward(ctx, d_logits):
+        B, L, H, Vc, nsplit, p, seed = ctx.cfg
+        hs_c, w_c = ctx.keep
+        d_logits = _f32c(d_logits).view(B * L, Vc)
+        Lb = lib()
+        d_hs = torch.empty_like(hs_c)
+        d_w = torch.empty_like(w_c)
+        d_b = torch.empty((Vc,), dtype=torch.float32, device=hs_c.device)
+        ws = _ws(Lb.pvcr_linear_bwd_workspace(B * L, Vc, H, nsplit), hs_c.device)
+        if p > 0.0:
+            raise _lib.PvcrError("materialised-logits backward with dropout is not supported: use forward_loss()")
+        check(Lb.pvcr_linear_bwd(ptr(d_logits), Vc, ptr(hs_c), H, ptr(w_c), H, ptr(d_hs), H, ptr(d_w), H, ptr(d_b),
+                                 B * L, Vc, H, nsplit, 0, ptr(ws), ws.numel(), stream_ptr()), "pvcr_linear_bwd")
+        return None, d_hs, d_w, d_b
+
+
+def s2vtatt_greedy(vid, frame_scale, sos_id, max_len, seq_params, out_w, out_b):
+    raise _lib.PvcrError("greedy decoding entry point not built yet")

@@ -1,0 +1,117 @@
+"""S2VTAttModel on the B200 kernels.
+
+Same constructor, ``forward(vid_feats, s)`` contract, helper methods and ``state_dict`` keys as the reference
+class (model/S2VTAttModel.py:199-264); the torch.nn layers below are parameter containers only (so reference
+checkpoints load and default initialisation under a seed is identical) — their ``forward`` is never called.
+All arithmetic goes through the C ABI (include/pvcr_b200.h).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import functional as F_
+
+
+class Attention(nn.Module):
+    """Parameter container of the additive attention (model/S2VTAttModel.py:12-23)."""
+
+    def __init__(self, hidden_size):
+        super().__init__()
+        self.key_layer = nn.Linear(hidden_size, hidden_size, bias=False)
+        self.query_layer = nn.Linear(hidden_size, hidden_size, bias=False)
+        self.energy_layer = nn.Linear(hidden_size, 1, bias=False)
+
+
+class Encoder(nn.Module):
+    """model/S2VTAttModel.py:50-61."""
+
+    def __init__(self, vid_feat_size, hidden_size):
+        super().__init__()
+        self.rnn = nn.GRU(vid_feat_size, hidden_size, num_layers=1)
+
+
+class Decoder(nn.Module):
+    """model/S2VTAttModel.py:98-123."""
+
+    def __init__(self, glove_loader, hidden_size, dropout_p, max_len):
+        super().__init__()
+        word_vectors = np.vstack(glove_loader.word_vectors)
+        self.vocab_size, self.embed_size = word_vectors.shape
+        self.max_len = max_len
+        self.sos_id = glove_loader.get_id('<sos>')
+        self.embedding = nn.Embedding(self.vocab_size, self.embed_size)
+        self.embedding.load_state_dict({'weight': torch.Tensor(word_vectors)})
+        self.rnn = nn.GRU(hidden_size + self.embed_size, hidden_size, num_layers=1)
+        self.attention = Attention(hidden_size=hidden_size)
+        self.pred_linear = nn.Sequential(nn.Dropout(p=dropout_p), nn.Linear(hidden_size, self.vocab_size))
+
+
+class S2VTAttModel(nn.Module):
+    """S2VT with Bahdanau temporal attention.
+
+    ``precision``: 'bf16' (one bf16 tcgen05 product per logical product, fp32 accumulation; training default),
+    'bf16x2' or 'bf16x3' (split-bf16 operands; 'bf16x3' reproduces fp32 arithmetic and is always used for greedy
+    decoding so that token ids match the fp32 reference)."""
+
+    NSPLIT = {'bf16': 1, 'bf16x2': 2, 'bf16x3': 3}
+
+    def __init__(self, glove_loader, dropout_p, hidden_size, vid_feat_size, max_len, precision='bf16'):
+        super().__init__()
+        self.encoder = Encoder(vid_feat_size, hidden_size)
+        self.decoder = Decoder(glove_loader, hidden_size, dropout_p, max_len)
+        self.hidden_size = hidden_size
+        self.precision = precision
+        self.teacher_force_prob = 1.0      # set by train.py:145 on every arch; unused here as in the reference
+        self.last_alphas = None            # [L,B,N] attention weights of the latest forward (reference never exposes them)
+
+    # ---- plumbing -------------------------------------------------------------------------------------------
+    def _seq_params(self):
+        e, d = self.encoder.rnn, self.decoder
+        return (e.weight_ih_l0, e.weight_hh_l0, e.bias_ih_l0, e.bias_hh_l0, d.embedding.weight, d.rnn.weight_ih_l0,
+                d.rnn.weight_hh_l0, d.rnn.bias_ih_l0, d.rnn.bias_hh_l0, d.attention.key_layer.weight,
+                d.attention.query_layer.weight, d.attention.energy_layer.weight)
+
+    def _cfg(self, train):
+        p = float(self.decoder.pred_linear[0].p) if train else 0.0
+        return {"nsplit": self.NSPLIT[self.precision] if train else 3, "dropout_p": p,
+                "seed": F_.next_seed() if p > 0 else 0}
+
+    def _shifted(self, s, B):
+        sos = torch.full((B, 1), self.decoder.sos_id, dtype=torch.long, device=s.device)
+        return torch.cat((sos, s[:, :self.decoder.max_len - 1]), dim=1)
+
+    def _hidden_states(self, vid_feats, s, frame_scale=None):
+        cfg = self._cfg(True)
+        hs, alphas = F_.S2VTAttSequence.apply(cfg, vid_feats, frame_scale, self._shifted(s, vid_feats.shape[0]),
+                                              *self._seq_params())
+        self.last_alphas = alphas
+        return hs, cfg
+
+    # ---- reference API --------------------------------------------------------------------------------------
+    def forward(self, vid_feats, s=None, frame_scale=None):
+        """vid_feats [B,N,V], s [B,L] (required in training) -> logits [B,L,Vc] (model/S2VTAttModel.py:245-264)."""
+        lin = self.decoder.pred_linear[1]
+        if self.training:
+            assert s is not None
+            hs, cfg = self._hidden_states(vid_feats, s, frame_scale)
+            return F_.VocabLogits.apply(cfg, hs, lin.weight, lin.bias)
+        return self.greedy(vid_feats, frame_scale)[1]
+
+    def forward_loss(self, vid_feats, s, s_len, frame_scale=None):
+        """Fused run_iter (train.py:37-40): returns (loss, acc, pred) without materialising logits for the caller.
+        loss == calc_masked_loss(model(vid_feats, s), s, s_len, CrossEntropyLoss(reduction='none'))."""
+        assert self.training and s is not None
+        lin = self.decoder.pred_linear[1]
+        hs, cfg = self._hidden_states(vid_feats, s, frame_scale)
+        loss, stats, pred = F_.VocabCrossEntropy.apply(cfg, hs, lin.weight, lin.bias, s, s_len)
+        return loss, stats[0] / stats[1], pred
+
+    @torch.no_grad()
+    def greedy(self, vid_feats, frame_scale=None):
+        """Fixed-length greedy decoding (eval branch, model/S2VTAttModel.py:172-191): -> (ids [B,L], logits [B,L,Vc])."""
+        d = self.decoder
+        lin = d.pred_linear[1]
+        ids, logits, alphas = F_.s2vtatt_greedy(vid_feats, frame_scale, d.sos_id, d.max_len, self._seq_params(),
+                                                lin.weight, lin.bias)
+        self.last_alphas = alphas
+        return ids, logits
