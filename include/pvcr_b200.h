@@ -28,6 +28,16 @@ extern "C" {
 const char* pvcr_last_error(void);
 int pvcr_version(void);
 
+/* Launch accounting used by bench.py: every kernel launch of the library is counted per kernel class; with
+ * pvcr_prof_enable(1) each launch is additionally bracketed by a CUDA-event pair on its stream.
+ * pvcr_prof_read fills launches[], ms[] (summed event durations; synchronises) and work[] (executed tensor-core
+ * FLOPs for the GEMM class) for pvcr_prof_num_classes() classes, all since the last pvcr_prof_reset(). */
+int pvcr_prof_num_classes(void);
+const char* pvcr_prof_class_name(int cls);
+void pvcr_prof_enable(int on);
+void pvcr_prof_reset(void);
+int pvcr_prof_read(uint64_t* launches, double* ms, double* work);
+
 /* y[M,N] = x[M,K] w[N,K]^T + bias[N]      (torch.nn.Linear / F.linear; bias may be NULL) */
 size_t pvcr_linear_fwd_workspace(int M, int N, int K, int nsplit);
 int pvcr_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,

@@ -67,6 +67,11 @@ def _sig(L, name, restype, argtypes):
 # name -> (restype, argtypes); mirrors include/pvcr_b200.h one to one (tests/test_abi.py cross-checks the header)
 P = ctypes.POINTER
 SIGNATURES = {
+    "pvcr_prof_num_classes": (c_int, []),
+    "pvcr_prof_class_name": (ctypes.c_char_p, [c_int]),
+    "pvcr_prof_enable": (None, [c_int]),
+    "pvcr_prof_reset": (None, []),
+    "pvcr_prof_read": (c_int, [P(c_u64), P(ctypes.c_double), P(ctypes.c_double)]),
     "pvcr_linear_fwd_workspace": (c_size, [c_int, c_int, c_int, c_int]),
     "pvcr_linear_fwd": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_size,
                                 c_vp]),
@@ -103,3 +108,14 @@ def ptr(t):
 def stream_ptr():
     import torch
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def prof_read():
+    """{class name: (launches, summed event ms, work)} since the last pvcr_prof_reset()."""
+    L = lib()
+    n = L.pvcr_prof_num_classes()
+    launches = (c_u64 * n)()
+    ms = (ctypes.c_double * n)()
+    work = (ctypes.c_double * n)()
+    check(L.pvcr_prof_read(launches, ms, work), "pvcr_prof_read")
+    return {L.pvcr_prof_class_name(i).decode(): (int(launches[i]), float(ms[i]), float(work[i])) for i in range(n)}

@@ -41,6 +41,16 @@ void set_last_error(const char* fmt, ...);
     if (_r != PVCR_OK) return _r; \
   } while (0)
 
+// ---- launch accounting (pvcr_prof_* in include/pvcr_b200.h) ---------------------------------------
+// Every kernel launcher opens a LaunchScope: it counts the launch per kernel class and, when timing is
+// enabled (bench.py's roofline leg), brackets it with a CUDA-event pair on the launching stream.
+enum KernelClass { KC_GEMM = 0, KC_STAGE, KC_GATE, KC_ATTN, KC_LOSS, KC_RECURRENT, KC_MISC, KC_COUNT };
+struct LaunchScope {
+  int cls; cudaStream_t st; void* rec;
+  LaunchScope(int cls, cudaStream_t st, double work = 0.0);
+  ~LaunchScope();
+};
+
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

@@ -80,7 +80,9 @@ int cast_split(const float* in, long long ld_in, int R, int C, bf16* out, long l
   if (R == 0) return PVCR_OK;
   const long long total = (long long)R * (Cp / 8);
   const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  { LaunchScope ls_(KC_STAGE, st);
   cast_split_kernel<<<blocks, 256, 0, st>>>(in, ld_in, R, C, out, ld_out, Cp, nsplit, role_b, row_scale, drop);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
 }
@@ -116,8 +118,10 @@ int transpose_split(const float* in, long long ld_in, int R, int C, bf16* out, l
   const int r_end = zero_pad ? Rp - r_off : R;       // rows >= R read as zero
   if (r_end == 0) return PVCR_OK;
   dim3 grid(cdiv(r_end, 32), cdiv(C, 32));
+  { LaunchScope ls_(KC_STAGE, st);
   transpose_split_kernel<<<grid, dim3(32, 8), 0, st>>>(in, ld_in, R, C, out, ld_out, Rp, r_off, r_end, nsplit, role_b,
                                                        row_ids, row_scale);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
 }
@@ -142,7 +146,9 @@ int gather_split(const float* table, int E, const long long* ids, int n_ids, bf1
   if (n_ids == 0) return PVCR_OK;
   const long long total = (long long)n_ids * Ep;
   const int blocks = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
+  { LaunchScope ls_(KC_STAGE, st);
   gather_split_kernel<<<blocks, 256, 0, st>>>(table, E, ids, n_ids, out, ld_out, Ep, nsplit, drop);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
 }
@@ -163,7 +169,9 @@ int scatter_add_rows(const float* rows, long long ld, const long long* ids, int 
   if (n_ids == 0) return PVCR_OK;
   const long long total = (long long)n_ids * E;
   const int blocks = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
+  { LaunchScope ls_(KC_MISC, st);
   scatter_add_rows_kernel<<<blocks, 256, 0, st>>>(rows, ld, ids, n_ids, E, table_grad, drop);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
 }
@@ -187,7 +195,9 @@ __global__ void colsum_kernel(const float* __restrict__ in, long long ld, int R,
 }
 int colsum(const float* in, long long ld, int R, int C, float* out, int accumulate, cudaStream_t st) {
   if (C == 0) return PVCR_OK;
+  { LaunchScope ls_(KC_MISC, st);
   colsum_kernel<<<cdiv(C, 32), dim3(32, 32), 0, st>>>(in, ld, R, C, out, accumulate);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
 }
@@ -199,7 +209,9 @@ __global__ void dropout_apply_kernel(const float* __restrict__ in, float* __rest
 int dropout_apply(const float* in, float* out, long long n, Dropout drop, cudaStream_t st) {
   if (n == 0) return PVCR_OK;
   const int blocks = (int)((n + 255) / 256 > 148 * 8 ? 148 * 8 : (n + 255) / 256);
+  { LaunchScope ls_(KC_MISC, st);
   dropout_apply_kernel<<<blocks, 256, 0, st>>>(in, out, n, drop);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
 }
@@ -239,7 +251,9 @@ __global__ void gru_gate_fwd_kernel(GruFwdArgs a) {
 int gru_gate_fwd(const GruFwdArgs& a, cudaStream_t st) {
   const int total = a.B * a.H;
   if (total == 0) return PVCR_OK;
+  { LaunchScope ls_(KC_GATE, st);
   gru_gate_fwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(a);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
 }
@@ -279,7 +293,9 @@ __global__ void gru_gate_bwd_kernel(GruBwdArgs a) {
 int gru_gate_bwd(const GruBwdArgs& a, cudaStream_t st) {
   const int total = a.B * a.H;
   if (total == 0) return PVCR_OK;
+  { LaunchScope ls_(KC_GATE, st);
   gru_gate_bwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(a);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
 }
@@ -308,7 +324,9 @@ __global__ void lstm_gate_fwd_kernel(LstmFwdArgs a) {
 int lstm_gate_fwd(const LstmFwdArgs& a, cudaStream_t st) {
   const int total = a.B * a.H;
   if (total == 0) return PVCR_OK;
+  { LaunchScope ls_(KC_GATE, st);
   lstm_gate_fwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(a);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
 }
@@ -341,7 +359,9 @@ __global__ void lstm_gate_bwd_kernel(LstmBwdArgs a) {
 int lstm_gate_bwd(const LstmBwdArgs& a, cudaStream_t st) {
   const int total = a.B * a.H;
   if (total == 0) return PVCR_OK;
+  { LaunchScope ls_(KC_GATE, st);
   lstm_gate_bwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(a);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
 }
@@ -400,7 +420,9 @@ int attn_fwd(const AttnFwdArgs& a, cudaStream_t st) {
   if (a.B == 0) return PVCR_OK;
   const size_t smem = (size_t)(2 * a.H + a.N) * sizeof(float);
   PVCR_REQUIRE(smem <= 48 * 1024, "attn_fwd: H=%d N=%d needs %zu B of shared memory", a.H, a.N, smem);
+  { LaunchScope ls_(KC_ATTN, st);
   attn_fwd_kernel<<<a.B, 256, smem, st>>>(a);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
 }
@@ -462,7 +484,9 @@ int attn_bwd(const AttnBwdArgs& a, cudaStream_t st) {
   if (a.B == 0) return PVCR_OK;
   const size_t smem = (size_t)(3 * a.H + 2 * a.N) * sizeof(float);
   PVCR_REQUIRE(smem <= 48 * 1024, "attn_bwd: H=%d N=%d needs %zu B of shared memory", a.H, a.N, smem);
+  { LaunchScope ls_(KC_ATTN, st);
   attn_bwd_kernel<<<a.B, 256, smem, st>>>(a);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
 }
@@ -531,7 +555,9 @@ int ce_rows(const float* logits, long long ld, int B, int L, int Vc, const long 
             float* lse, float* nll, long long* pred, float* dlogits, long long ld_d, const float* gscale,
             cudaStream_t st) {
   if (B * L == 0) return PVCR_OK;
+  { LaunchScope ls_(KC_LOSS, st);
   ce_rows_kernel<<<B * L, 256, 0, st>>>(logits, ld, B, L, Vc, target, s_len, lse, nll, pred, dlogits, ld_d, gscale);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
 }
@@ -566,7 +592,9 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(const float* nll, co
 }
 int loss_finalize(const float* nll, const long long* pred, const long long* target, const long long* s_len, int B,
                   int L, float* out3, cudaStream_t st) {
+  { LaunchScope ls_(KC_LOSS, st);
   loss_finalize_kernel<<<1, 256, 0, st>>>(nll, pred, target, s_len, B, L, out3);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
 }
@@ -634,10 +662,14 @@ __global__ void __launch_bounds__(256) penalties_kernel(const float* probs, int 
 int gumbel_select_fwd(const GumbelArgs& a, cudaStream_t st) {
   const int rows = a.B * a.N;
   if (rows == 0) return PVCR_OK;
+  { LaunchScope ls_(KC_MISC, st);
   gumbel_fwd_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, st>>>(a);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   if (a.pen) {
+    { LaunchScope ls_(KC_MISC, st);
     penalties_kernel<<<1, 256, 0, st>>>(a.probs, a.B, a.N, a.pen);
+    }
     PVCR_CUDA_CHECK(cudaGetLastError());
   }
   return PVCR_OK;
@@ -694,9 +726,13 @@ __global__ void __launch_bounds__(256) gumbel_bwd_w_kernel(GumbelBwdArgs a) {
 int gumbel_select_bwd(const GumbelBwdArgs& a, cudaStream_t st) {
   const int rows = a.B * a.N;
   if (rows == 0) return PVCR_OK;
+  { LaunchScope ls_(KC_MISC, st);
   gumbel_bwd_rows_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, st>>>(a);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
+  { LaunchScope ls_(KC_MISC, st);
   gumbel_bwd_w_kernel<<<cdiv(2 * a.H, 256), 256, 0, st>>>(a);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
 }
@@ -714,7 +750,9 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ x
 }
 int rowdot(const float* x, const float* dsel, int R, int C, float* out, cudaStream_t st) {
   if (R == 0) return PVCR_OK;
+  { LaunchScope ls_(KC_MISC, st);
   rowdot_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(x, dsel, R, C, out);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
 }

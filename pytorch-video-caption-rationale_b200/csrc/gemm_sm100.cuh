@@ -195,7 +195,10 @@ int launch_gemm_tn(const OperandView& a, const OperandView& b, const GemmCoords&
     attr_set = true;
   }
   dim3 grid(cdiv(gc.N, BN), cdiv(gc.M, GEMM_BM), grid_z);
-  kern<<<grid, GEMM_THREADS, SM::TOTAL, stream>>>(ta, tb, gc, epi);
+  {
+    LaunchScope ls_(KC_GEMM, stream, 2.0 * gc.M * gc.N * (double)gc.K * grid_z);
+    kern<<<grid, GEMM_THREADS, SM::TOTAL, stream>>>(ta, tb, gc, epi);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
 }

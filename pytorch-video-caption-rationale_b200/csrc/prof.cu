@@ -1,0 +1,73 @@
+// Launch accounting: per-class launch counters (always on) and optional CUDA-event timing of every launch.
+#include <mutex>
+#include <vector>
+
+#include "../../include/pvcr_b200.h"
+#include "common.cuh"
+
+namespace pvcr {
+
+struct EventPair { cudaEvent_t a, b; int cls; };
+static std::mutex g_mu;
+static unsigned long long g_launches[KC_COUNT];
+static double g_work[KC_COUNT];
+static bool g_timing = false;
+static std::vector<EventPair> g_pending;
+static std::vector<EventPair> g_pool;
+static const char* const g_names[KC_COUNT] = {"gemm_tcgen05", "operand_staging", "rnn_gates", "attention",
+                                              "loss", "recurrent_persistent", "misc"};
+
+LaunchScope::LaunchScope(int c, cudaStream_t s, double work) : cls(c), st(s), rec(nullptr) {
+  std::lock_guard<std::mutex> g(g_mu);
+  g_launches[c]++;
+  g_work[c] += work;
+  if (!g_timing) return;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+  EventPair ep;
+  if (!g_pool.empty()) { ep = g_pool.back(); g_pool.pop_back(); }
+  else if (cudaEventCreate(&ep.a) != cudaSuccess || cudaEventCreate(&ep.b) != cudaSuccess) return;
+  ep.cls = c;
+  cudaEventRecord(ep.a, s);
+  g_pending.push_back(ep);
+  rec = reinterpret_cast<void*>(g_pending.size());     // 1-based index
+}
+LaunchScope::~LaunchScope() {
+  if (!rec) return;
+  std::lock_guard<std::mutex> g(g_mu);
+  const size_t i = reinterpret_cast<size_t>(rec) - 1;
+  if (i < g_pending.size()) cudaEventRecord(g_pending[i].b, st);
+}
+
+}  // namespace pvcr
+
+using namespace pvcr;
+
+extern "C" {
+
+int pvcr_prof_num_classes(void) { return KC_COUNT; }
+const char* pvcr_prof_class_name(int cls) { return (cls >= 0 && cls < KC_COUNT) ? g_names[cls] : ""; }
+void pvcr_prof_enable(int on) {
+  std::lock_guard<std::mutex> g(g_mu);
+  g_timing = on != 0;
+}
+void pvcr_prof_reset(void) {
+  std::lock_guard<std::mutex> g(g_mu);
+  for (int i = 0; i < KC_COUNT; ++i) { g_launches[i] = 0; g_work[i] = 0.0; }
+  for (auto& e : g_pending) g_pool.push_back(e);
+  g_pending.clear();
+}
+// launches[cls], ms[cls] (sum of event-timed durations since the last reset; 0 when timing is off), work[cls]
+int pvcr_prof_read(uint64_t* launches, double* ms, double* work) {
+  std::lock_guard<std::mutex> g(g_mu);
+  for (int i = 0; i < KC_COUNT; ++i) { launches[i] = g_launches[i]; ms[i] = 0.0; work[i] = g_work[i]; }
+  for (auto& e : g_pending) {
+    if (cudaEventSynchronize(e.b) != cudaSuccess) return PVCR_ERR_CUDA;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, e.a, e.b) != cudaSuccess) return PVCR_ERR_CUDA;
+    ms[e.cls] += t;
+  }
+  return PVCR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+"""Data-parallel training over the videos of a batch: one process per GPU, parameters replicated, gradients
+averaged with one all-reduce per bucket (NCCL over NVLink on GPUs; gloo in the CPU tests).
+
+The reference is single-process; the contract here is that after ``reduce()`` every rank holds
+the gradient of the mean loss over the concatenated global batch (equal shards: mean of per-rank means).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_batch(tensors, rank, world):
+    """Rank's contiguous slice of each [B, ...] tensor (B must divide evenly: videos are independent units)."""
+    out = []
+    for t in tensors:
+        B = t.shape[0]
+        assert B % world == 0, "global batch %d not divisible by world size %d" % (B, world)
+        n = B // world
+        out.append(t[rank * n:(rank + 1) * n])
+    return out
+
+
+class GradAllReducer:
+    """Flat-bucket gradient averaging.  Buckets follow reverse parameter order (the order in which backward
+    produces gradients: vocabulary projection and embedding first), so ``reduce()`` can be issued per bucket on a
+    side stream while later buckets are still being computed."""
+
+    def __init__(self, module, bucket_mb=64, group=None):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.buckets = []
+        cur, cur_bytes = [], 0
+        for p in reversed(self.params):
+            cur.append(p)
+            cur_bytes += p.numel() * 4
+            if cur_bytes >= bucket_mb * (1 << 20):
+                self.buckets.append(cur)
+                cur, cur_bytes = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self._flat = [None] * len(self.buckets)
+
+    def reduce(self):
+        if self.world == 1:
+            return
+        handles = []
+        for i, bucket in enumerate(self.buckets):
+            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
+            flat = torch.cat([g.reshape(-1).float() for g in grads])
+            self._flat[i] = flat
+            handles.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        for i, (bucket, h) in enumerate(zip(self.buckets, handles)):
+            h.wait()
+            flat = self._flat[i]
+            flat.div_(self.world)
+            off = 0
+            for p in bucket:
+                n = p.numel()
+                g = flat[off:off + n].view_as(p)
+                if p.grad is None:
+                    p.grad = g.clone()
+                else:
+                    p.grad.copy_(g)
+                off += n
+
+
+def reduce_metrics(loss, correct, count, group=None):
+    """Global loss mean and token accuracy from per-rank values (train_utils.py:37-71 semantics on the global batch)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return loss, correct / count
+    v = torch.stack([loss.detach().float(), correct.float(), count.float()])
+    dist.all_reduce(v, op=dist.ReduceOp.SUM, group=group)
+    return v[0] / dist.get_world_size(group), v[1] / v[2]
