@@ -1,0 +1,393 @@
+// Persistent GRU sequence kernels (forward and reverse-time backward): one cooperative launch runs all T
+// timesteps with the CTA's slice of W_hh (forward) / W_hh^T (backward) resident in shared memory.
+// Reference semantics: torch.nn.GRU over a sequence (model/S2VTAttModel.py:88-93, model/S2VTModel.py:84,107);
+// gate order r,z,n;  n = tanh(gi_n + r * (W_hn h + b_hn));  h' = (1-z) n + z h.
+//
+// Work split (persist.cuh): groups of `bs` videos x C CTAs; CTA c of a group owns hidden units [c*u, (c+1)*u).
+//   forward : rows {r,z,n} x u of W_hh (3u x H bf16) resident; per step D[3u, bs] = W_slice * h_{t-1}^T, then
+//             the gate math for its (unit, video) pairs with h kept in fp32 registers across steps.
+//   backward: rows u of W_hh^T (u x 3H bf16) resident; per step the gate gradients of its (unit, video) pairs,
+//             exchange of dgh (bf16), then D[u, bs] = W_hh^T slice * dgh^T added into the fp32 dh carry registers.
+#include <mutex>
+
+#include "host.h"
+#include "persist.cuh"
+
+namespace pvcr {
+
+constexpr int MAX_ITEMS = 8;    // (unit, video) pairs per thread: u * bs <= MAX_ITEMS * PERSIST_THREADS
+
+struct GruPersistFwd {
+  int T, B, H, bs, C, u;
+  const bf16* whh; long long whh_ld;        // [3H, ld] bf16
+  const float* b_hh;
+  const float* gi; long long gi_ts, gi_ld;  // step t rows: gi + t*gi_ts + b*gi_ld  (includes b_ih)
+  const float* gi_b; long long gi_b_ts, gi_b_ld; int gi_b_from;
+  const float* gi_bias;
+  const float* h0; long long h0_ld;         // nullable
+  const bf16* h0p; long long h0p_ld;
+  float* h; long long h_ts, h_ld;
+  bf16* hp; long long hp_ts, hp_ld;
+  float *r, *z, *n, *ghn;                   // [T][B,H]
+  unsigned* counters;
+};
+
+__global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_fwd_kernel(const GruPersistFwd p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int H = p.H, u = p.u, bs = p.bs, KB = H >> 6, Rw = 3 * u;
+  uint8_t* sW = smem;
+  uint8_t* sX = sW + (size_t)KB * Rw * 128;
+  float* sS = reinterpret_cast<float*>(sX + (size_t)KB * bs * 128);
+  const int s_ld = Rw + 1;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sS + (size_t)bs * s_ld + 2);
+  bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bar) + 7) & ~uintptr_t(7));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int g = blockIdx.x / p.C, c = blockIdx.x % p.C;
+  const int b0 = g * bs, j0 = c * u;
+  unsigned* ctr = p.counters + g;
+
+  // resident weights: local row q*u + jj  <-  W_hh row q*H + j0 + jj
+  for (int q = 0; q < 3; ++q)
+    load_operand_rows(sW, Rw, q * u, p.whh, p.whh_ld, (long long)q * H + j0, u, (long long)3 * H, H);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  const uint32_t ncols = bs <= 32 ? 32u : (bs <= 64 ? 64u : 128u);
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, ncols);
+    tmem_relinquish();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = umma_idesc_bf16(128, bs);
+
+  // this thread's (unit, video) pairs
+  const int n_items = (u * bs + PERSIST_THREADS - 1) / PERSIST_THREADS;
+  float hreg[MAX_ITEMS], bhr[MAX_ITEMS], bhz[MAX_ITEMS], bhn[MAX_ITEMS];
+#pragma unroll
+  for (int k = 0; k < MAX_ITEMS; ++k) {
+    hreg[k] = 0.f; bhr[k] = 0.f; bhz[k] = 0.f; bhn[k] = 0.f;
+    if (k < n_items) {
+      const int idx = tid + k * PERSIST_THREADS, jj = idx % u, lb = idx / u;
+      if (lb < bs) {
+        const int j = j0 + jj, b = b0 + lb;
+        bhr[k] = p.b_hh[j]; bhz[k] = p.b_hh[H + j]; bhn[k] = p.b_hh[2 * H + j];
+        if (p.h0 && b < p.B) hreg[k] = p.h0[(long long)b * p.h0_ld + j];
+      }
+    }
+  }
+  uint32_t phase = 0;
+
+  for (int t = 0; t < p.T; ++t) {
+    // prefetch this step's input projections (independent of the group barrier)
+    float gir[MAX_ITEMS], giz[MAX_ITEMS], gin[MAX_ITEMS];
+#pragma unroll
+    for (int k = 0; k < MAX_ITEMS; ++k) {
+      gir[k] = giz[k] = gin[k] = 0.f;
+      if (k < n_items) {
+        const int idx = tid + k * PERSIST_THREADS, jj = idx % u, lb = idx / u;
+        const int j = j0 + jj, b = b0 + lb;
+        if (lb < bs && b < p.B) {
+          const float* gp = p.gi + (long long)t * p.gi_ts + (long long)b * p.gi_ld;
+          gir[k] = __ldg(gp + j); giz[k] = __ldg(gp + H + j); gin[k] = __ldg(gp + 2 * H + j);
+          if (p.gi_b && t >= p.gi_b_from) {
+            const float* gq = p.gi_b + (long long)(t - p.gi_b_from) * p.gi_b_ts + (long long)b * p.gi_b_ld;
+            gir[k] += __ldg(gq + j); giz[k] += __ldg(gq + H + j); gin[k] += __ldg(gq + 2 * H + j);
+          }
+          if (p.gi_bias) { gir[k] += p.gi_bias[j]; giz[k] += p.gi_bias[H + j]; gin[k] += p.gi_bias[2 * H + j]; }
+        }
+      }
+    }
+    const bool has_prev = (t > 0) || (p.h0p != nullptr);
+    if (has_prev) {
+      if (t > 0) {
+        group_wait(ctr, (unsigned)(p.C * t));
+        load_operand_rows(sX, bs, 0, p.hp + (long long)(t - 1) * p.hp_ts, p.hp_ld, b0, bs, p.B, H);
+      } else {
+        load_operand_rows(sX, bs, 0, p.h0p, p.h0p_ld, b0, bs, p.B, H);
+      }
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        issue_swapped_mma(tmem_base, smem_u32(sW), Rw, smem_u32(sX), bs, H, idesc, bar);
+      }
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      tmem_to_smem_cols(tmem_base, sS, s_ld, Rw, bs);
+      tc_fence_before();
+      __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < MAX_ITEMS; ++k) {
+      if (k < n_items) {
+        const int idx = tid + k * PERSIST_THREADS, jj = idx % u, lb = idx / u;
+        const int j = j0 + jj, b = b0 + lb;
+        if (lb < bs && b < p.B) {
+          float ghr = bhr[k], ghz = bhz[k], ghn = bhn[k];
+          if (has_prev) {
+            ghr += sS[lb * s_ld + jj]; ghz += sS[lb * s_ld + u + jj]; ghn += sS[lb * s_ld + 2 * u + jj];
+          }
+          const float r = 1.f / (1.f + expf(-(gir[k] + ghr)));
+          const float z = 1.f / (1.f + expf(-(giz[k] + ghz)));
+          const float n = tanhf(gin[k] + r * ghn);
+          const float hn = (1.f - z) * n + z * hreg[k];
+          hreg[k] = hn;
+          p.h[(long long)t * p.h_ts + (long long)b * p.h_ld + j] = hn;
+          p.hp[(long long)t * p.hp_ts + (long long)b * p.hp_ld + j] = __float2bfloat16_rn(hn);
+          const long long o = ((long long)t * p.B + b) * H + j;
+          p.r[o] = r; p.z[o] = z; p.n[o] = n; p.ghn[o] = ghn;
+        }
+      }
+    }
+    group_arrive(ctr);      // also protects sS / sX reuse by the next step
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ncols);
+  }
+}
+
+struct GruPersistBwd {
+  int T, B, H, bs, C, u;
+  const bf16* whhT; long long whhT_ld;      // [H, ld] bf16: element (j, k) = W_hh[k, j], k in [0, 3H)
+  const float* dh_ext; long long dh_ext_ts, dh_ext_ld;   // nullable
+  float* dh_carry;                          // [B,H] in: gradient on the final state; out: gradient on h0
+  const float *r, *z, *n, *ghn;             // [T][B,H]
+  const float* h; long long h_ts, h_ld;     // forward states (h_{t-1} = h + (t-1)*h_ts)
+  const float* h0; long long h0_ld;         // nullable
+  float* dgi; long long dgi_ts, dgi_ld;
+  float* dgh; long long dgh_ts, dgh_ld;
+  bf16* xch;                                // exchange [2][B][3H] bf16
+  unsigned* counters;
+};
+
+__global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_bwd_kernel(const GruPersistBwd p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int H = p.H, u = p.u, bs = p.bs, K = 3 * H, KB = K >> 6;
+  uint8_t* sW = smem;                                        // KB x (u rows x 128 B)
+  uint8_t* sX = sW + (size_t)KB * u * 128;                   // KB x (bs rows x 128 B)
+  float* sS = reinterpret_cast<float*>(sX + (size_t)KB * bs * 128);
+  const int s_ld = u + 1;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sS + (size_t)bs * s_ld + 2);
+  bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bar) + 7) & ~uintptr_t(7));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int g = blockIdx.x / p.C, c = blockIdx.x % p.C;
+  const int b0 = g * bs, j0 = c * u;
+  unsigned* ctr = p.counters + g;
+
+  load_operand_rows(sW, u, 0, p.whhT, p.whhT_ld, j0, u, H, K);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  const uint32_t ncols = bs <= 32 ? 32u : (bs <= 64 ? 64u : 128u);
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, ncols);
+    tmem_relinquish();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = umma_idesc_bf16(128, bs);
+
+  const int n_items = (u * bs + PERSIST_THREADS - 1) / PERSIST_THREADS;
+  float dhc[MAX_ITEMS];
+#pragma unroll
+  for (int k = 0; k < MAX_ITEMS; ++k) {
+    dhc[k] = 0.f;
+    if (k < n_items) {
+      const int idx = tid + k * PERSIST_THREADS, jj = idx % u, lb = idx / u;
+      if (lb < bs && b0 + lb < p.B) dhc[k] = p.dh_carry[(long long)(b0 + lb) * H + j0 + jj];
+    }
+  }
+  uint32_t phase = 0;
+  unsigned arrivals = 0;
+
+  for (int t = p.T - 1; t >= 0; --t) {
+    const bool has_prev = (t > 0) || (p.h0 != nullptr);
+    bf16* xw = p.xch + (size_t)(t & 1) * p.B * K;
+    float zreg[MAX_ITEMS];
+#pragma unroll
+    for (int k = 0; k < MAX_ITEMS; ++k) {
+      zreg[k] = 0.f;
+      if (k < n_items) {
+        const int idx = tid + k * PERSIST_THREADS, jj = idx % u, lb = idx / u;
+        const int j = j0 + jj, b = b0 + lb;
+        if (lb < bs && b < p.B) {
+          float dh = dhc[k];
+          if (p.dh_ext) dh += p.dh_ext[(long long)t * p.dh_ext_ts + (long long)b * p.dh_ext_ld + j];
+          const long long o = ((long long)t * p.B + b) * H + j;
+          const float r = p.r[o], z = p.z[o], n = p.n[o], ghn = p.ghn[o];
+          float hp = 0.f;
+          if (t > 0) hp = p.h[(long long)(t - 1) * p.h_ts + (long long)b * p.h_ld + j];
+          else if (p.h0) hp = p.h0[(long long)b * p.h0_ld + j];
+          const float dn = dh * (1.f - z), dz = dh * (hp - n);
+          const float dnp = dn * (1.f - n * n);
+          const float dzp = dz * z * (1.f - z);
+          const float drp = dnp * ghn * r * (1.f - r);
+          const float dghn = dnp * r;
+          float* dgi = p.dgi + (long long)t * p.dgi_ts + (long long)b * p.dgi_ld;
+          float* dgh = p.dgh + (long long)t * p.dgh_ts + (long long)b * p.dgh_ld;
+          dgi[j] = drp; dgi[H + j] = dzp; dgi[2 * H + j] = dnp;
+          dgh[j] = drp; dgh[H + j] = dzp; dgh[2 * H + j] = dghn;
+          if (has_prev) {
+            bf16* x = xw + (long long)b * K;
+            x[j] = __float2bfloat16_rn(drp); x[H + j] = __float2bfloat16_rn(dzp); x[2 * H + j] = __float2bfloat16_rn(dghn);
+          }
+          dhc[k] = dh * z;
+          zreg[k] = 1.f;
+        }
+      }
+    }
+    if (has_prev) {
+      group_arrive(ctr);
+      ++arrivals;
+      group_wait(ctr, (unsigned)p.C * arrivals);
+      load_operand_rows(sX, bs, 0, xw, K, b0, bs, p.B, K);
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        issue_swapped_mma(tmem_base, smem_u32(sW), u, smem_u32(sX), bs, K, idesc, bar);
+      }
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      tmem_to_smem_cols(tmem_base, sS, s_ld, u, bs);
+      tc_fence_before();
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < MAX_ITEMS; ++k) {
+        if (k < n_items && zreg[k] != 0.f) {
+          const int idx = tid + k * PERSIST_THREADS, jj = idx % u, lb = idx / u;
+          dhc[k] += sS[lb * s_ld + jj];
+        }
+      }
+      __syncthreads();     // sS is rewritten by the next step
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < MAX_ITEMS; ++k) {
+    if (k < n_items) {
+      const int idx = tid + k * PERSIST_THREADS, jj = idx % u, lb = idx / u;
+      if (lb < bs && b0 + lb < p.B) p.dh_carry[(long long)(b0 + lb) * H + j0 + jj] = dhc[k];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ncols);
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------
+struct PersistPlan { int bs, C, u, G; size_t smem; };
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+// units per CTA: largest u <= 32 dividing H with u % 8 == 0; videos per group: 16.
+static bool plan_gru(int B, int H, int k_rows_fwd, PersistPlan& pl, bool backward) {
+  if (H % 64 != 0 || H < 64) return false;
+  int u = 32;
+  while (u >= 8 && H % u != 0) u -= 8;
+  if (u < 8) return false;
+  pl.u = u; pl.C = H / u; pl.bs = 16; pl.G = (B + pl.bs - 1) / pl.bs;
+  if (pl.u * pl.bs > MAX_ITEMS * PERSIST_THREADS) return false;
+  if ((long long)pl.G * pl.C > num_sms()) return false;
+  const size_t K = backward ? (size_t)3 * H : (size_t)H;
+  const size_t rows = backward ? (size_t)u : (size_t)3 * u;
+  const size_t w = (K / 64) * rows * 128, x = (K / 64) * pl.bs * 128;
+  const size_t s = (size_t)pl.bs * (rows + 1) * 4 + 64;
+  size_t total = w + x + s;
+  // the 128-row MMA tile of the last k-block over-reads (128 - rows) * 128 bytes past the weight slice
+  const size_t need_tail = (128 - rows) * 128;
+  if (x + s < need_tail) total += need_tail - (x + s);
+  pl.smem = total + 1024;
+  (void)k_rows_fwd;
+  return pl.smem <= 227 * 1024;
+}
+
+static int coop_launch(const void* kern, int grid, size_t smem, void* param, cudaStream_t st, const char* what) {
+  static std::mutex mu;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  int per_sm = 0;
+  PVCR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PERSIST_THREADS, smem));
+  PVCR_REQUIRE(per_sm * num_sms() >= grid, "%s: %d CTAs cannot be co-resident (%d per SM)", what, grid, per_sm);
+  void* args[] = {param};
+  LaunchScope ls_(KC_RECURRENT, st);
+  PVCR_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(PERSIST_THREADS), args, smem, st));
+  return PVCR_OK;
+}
+
+bool gru_persist_eligible(const GruSeq& s) {
+  PersistPlan pl;
+  return s.nsplit == 1 && s.sync != nullptr && s.hp != nullptr && s.Hp == s.H && plan_gru(s.B, s.H, 0, pl, false) &&
+         plan_gru(s.B, s.H, 0, pl, true) && (s.h0 == nullptr || s.h0_planes != nullptr);
+}
+
+int gru_persist_fwd(const GruSeq& s, cudaStream_t st) {
+  PersistPlan pl;
+  PVCR_REQUIRE(plan_gru(s.B, s.H, 0, pl, false), "gru_persist_fwd: shape B=%d H=%d not supported", s.B, s.H);
+  GruPersistFwd p{};
+  p.T = s.T; p.B = s.B; p.H = s.H; p.bs = pl.bs; p.C = pl.C; p.u = pl.u;
+  p.whh = s.whh.ptr; p.whh_ld = s.whh.ld; p.b_hh = s.b_hh;
+  p.gi = s.gi_a; p.gi_ts = s.gi_a_ts; p.gi_ld = s.gi_a_ld;
+  p.gi_b = s.gi_b; p.gi_b_ts = s.gi_b_ts; p.gi_b_ld = s.gi_b_ld; p.gi_b_from = s.gi_b_from;
+  p.gi_bias = s.gi_bias;
+  p.h0 = s.h0; p.h0_ld = s.h0_ld; p.h0p = s.h0 ? s.h0_planes : nullptr; p.h0p_ld = s.h0_planes_ld;
+  p.h = s.h; p.h_ts = s.h_ts; p.h_ld = s.h_ld;
+  p.hp = s.hp; p.hp_ts = s.hp_ts; p.hp_ld = s.hp_ld;
+  p.r = s.r; p.z = s.z; p.n = s.n; p.ghn = s.ghn;
+  p.counters = s.sync;
+  PVCR_TRY(fill_zero(s.sync, sizeof(unsigned) * pl.G, st));
+  return coop_launch((const void*)gru_persist_fwd_kernel, pl.G * pl.C, pl.smem, &p, st, "gru_persist_fwd");
+}
+
+int gru_persist_bwd(const GruSeq& s, const GruSeqGrad& g, cudaStream_t st) {
+  PersistPlan pl;
+  PVCR_REQUIRE(plan_gru(s.B, s.H, 0, pl, true), "gru_persist_bwd: shape B=%d H=%d not supported", s.B, s.H);
+  GruPersistBwd p{};
+  p.T = s.T; p.B = s.B; p.H = s.H; p.bs = pl.bs; p.C = pl.C; p.u = pl.u;
+  p.whhT = g.whhT.ptr; p.whhT_ld = g.whhT.ld;
+  p.dh_ext = g.dh_ext; p.dh_ext_ts = g.dh_ext_ts; p.dh_ext_ld = g.dh_ext_ld;
+  p.dh_carry = g.dh_carry;
+  p.r = s.r; p.z = s.z; p.n = s.n; p.ghn = s.ghn;
+  p.h = s.h; p.h_ts = s.h_ts; p.h_ld = s.h_ld;
+  p.h0 = s.h0; p.h0_ld = s.h0_ld;
+  p.dgi = g.dgi; p.dgi_ts = g.dgi_ts; p.dgi_ld = g.dgi_ld;
+  p.dgh = g.dgh; p.dgh_ts = g.dgh_ts; p.dgh_ld = g.dgh_ld;
+  p.xch = g.xch;
+  p.counters = s.sync;
+  PVCR_TRY(fill_zero(s.sync, sizeof(unsigned) * pl.G, st));
+  return coop_launch((const void*)gru_persist_bwd_kernel, pl.G * pl.C, pl.smem, &p, st, "gru_persist_bwd");
+}
+
+}  // namespace pvcr

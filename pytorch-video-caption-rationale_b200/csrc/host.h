@@ -98,6 +98,7 @@ struct GruSeq {
   bf16* hp; long long hp_ts, hp_ld; int Hp;   // A-role planes of h_t
   float* gh;                               // scratch [B,3H]
   float *r, *z, *n, *ghn;                  // saved [T][B,H]
+  unsigned* sync;                          // >= ceil(B/16) counters for the persistent kernels (null: per-step path)
 };
 int gru_seq_fwd(const GruSeq& s, cudaStream_t st);
 
@@ -108,7 +109,12 @@ struct GruSeqGrad {
   float* dgh; long long dgh_ts, dgh_ld;
   Planes dgh_a;                            // scratch A-role planes [B, P*(3H)p]
   Planes whhT;                             // transposed B-role planes of W_hh [H, P*(3H)p]
+  bf16* xch;                               // [2][B][3H] bf16 exchange buffer of the persistent kernel (nullable)
 };
+// Persistent single-launch implementations (gru_persist.cu); used by gru_seq_* when eligible.
+bool gru_persist_eligible(const GruSeq& s);
+int gru_persist_fwd(const GruSeq& s, cudaStream_t st);
+int gru_persist_bwd(const GruSeq& s, const GruSeqGrad& g, cudaStream_t st);
 int gru_seq_bwd(const GruSeq& s, const GruSeqGrad& g, cudaStream_t st);
 
 }  // namespace pvcr

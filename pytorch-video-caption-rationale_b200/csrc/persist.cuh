@@ -1,0 +1,112 @@
+// Building blocks of the persistent recurrent kernels (sm_100a).
+//
+// A persistent kernel owns a slice of the recurrent weight matrices in shared memory for the whole sequence
+// and loops over the timesteps inside one cooperative launch.  The batch is cut into independent groups of
+// `bs` videos; a group is served by C CTAs, each owning the weight rows of `u` hidden units, so the only
+// inter-CTA communication is the per-step exchange of the group's activation vectors through global memory
+// (L2-resident), guarded by a monotonic arrive counter per group.
+//
+// The per-step product is a "swapped" tcgen05 MMA:  D[row, video] = sum_k W[row, k] * X[video, k]
+//   A = weight slice (rows x K, K-major, 128-byte swizzle, resident in shared memory),
+//   B = the group's activations (bs x K, K-major, 128-byte swizzle, refreshed every step),
+//   D in TMEM: lane = weight row, column = video of the group.
+#pragma once
+#include "common.cuh"
+
+namespace pvcr {
+
+constexpr int PERSIST_THREADS = 128;
+
+#ifdef __CUDACC__
+
+// Byte offset of element (row, k) inside a K-major SWIZZLE_128B operand whose 64-column k-blocks hold
+// `rows_alloc` rows each (rows at 128 B pitch; 16-byte chunk index XORed with row & 7), for k % 8 == 0.
+__device__ __forceinline__ uint32_t sw128_offset(int row, int k, int rows_alloc) {
+  const int kb = k >> 6, c = (k >> 3) & 7;
+  return (uint32_t)kb * (uint32_t)rows_alloc * 128u + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4);
+}
+
+// Copy rows [row0, row0+nrows) x K bf16 from global (row stride ld elements, rows >= row_limit read as zero) into a
+// SW128 operand at local rows [lrow0, lrow0+nrows).  All threads of the CTA participate; 16-byte L2 loads (.cg).
+__device__ __forceinline__ void load_operand_rows(uint8_t* dst, int rows_alloc, int lrow0, const bf16* src,
+                                                  long long ld, long long row0, int nrows, long long row_limit,
+                                                  int K) {
+  const int chunks = K >> 3;
+  for (int i = threadIdx.x; i < nrows * chunks; i += blockDim.x) {
+    const int lr = i / chunks, ch = i - lr * chunks;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (row0 + lr < row_limit) v = __ldcg(reinterpret_cast<const uint4*>(src + (row0 + lr) * ld + ch * 8));
+    *reinterpret_cast<uint4*>(dst + sw128_offset(lrow0 + lr, ch * 8, rows_alloc)) = v;
+  }
+}
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Group barrier on a monotonic counter.  arrive: all of this CTA's global writes of the step are published;
+// wait: the counter has reached `target` arrivals.  Bounded spin: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void group_arrive(unsigned* ctr) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+  }
+}
+__device__ __forceinline__ void group_wait(const unsigned* ctr, unsigned target) {
+  if (threadIdx.x == 0) {
+    if (ld_acquire_u32(ctr) < target) {
+      const long long t0 = clock64();
+      while (ld_acquire_u32(ctr) < target) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// D[128 x N] (TMEM, fp32) = A[128 x K] * B[N x K]^T, both SW128 K-major in shared memory; issued by one thread.
+__device__ __forceinline__ void issue_swapped_mma(uint32_t tmem_d, uint32_t a_base, int a_rows_alloc, uint32_t b_base,
+                                                  int b_rows_alloc, int K, uint32_t idesc, uint64_t* done_bar) {
+  const int KB = K >> 6;
+  for (int kb = 0; kb < KB; ++kb) {
+    const uint64_t da = umma_desc_k128(a_base + (uint32_t)kb * (uint32_t)a_rows_alloc * 128u);
+    const uint64_t db = umma_desc_k128(b_base + (uint32_t)kb * (uint32_t)b_rows_alloc * 128u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+  }
+  umma_commit(done_bar);
+}
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Move the accumulator D[row = TMEM lane, col < ncols] to shared memory as S[col * s_ld + row] for rows < nrows.
+// Executed by all 128 threads (thread == lane).  ncols is a multiple of 16.
+__device__ __forceinline__ void tmem_to_smem_cols(uint32_t tmem_base, float* S, int s_ld, int nrows, int ncols) {
+  const int warp = threadIdx.x >> 5, row = threadIdx.x;
+  float v[16];
+  for (int c0 = 0; c0 < ncols; c0 += 16) {
+    tmem_ld_32x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+    if (row < nrows) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) S[(c0 + j) * s_ld + row] = v[j];
+    }
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace pvcr

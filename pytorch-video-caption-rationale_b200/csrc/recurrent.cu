@@ -37,6 +37,7 @@ int grad_x(Arena& a, const float* dy, long long lddy, int R, int N, const Planes
 }
 
 int gru_seq_fwd(const GruSeq& s, cudaStream_t st) {
+  if (gru_persist_eligible(s)) return gru_persist_fwd(s, st);
   const int H3 = 3 * s.H;
   for (int t = 0; t < s.T; ++t) {
     const bool has_prev = (t > 0) || (s.h0 != nullptr);
@@ -64,6 +65,7 @@ int gru_seq_fwd(const GruSeq& s, cudaStream_t st) {
 }
 
 int gru_seq_bwd(const GruSeq& s, const GruSeqGrad& g, cudaStream_t st) {
+  if (g.xch && gru_persist_eligible(s)) return gru_persist_bwd(s, g, st);
   for (int t = s.T - 1; t >= 0; --t) {
     const bool has_prev = (t > 0) || (s.h0 != nullptr);
     GruBwdArgs b{};

@@ -23,6 +23,8 @@ struct AttWs {
   Planes wcT, wcatT, wkT, weT, whh_encT, wih_encT, dgi_a, d1_a, dgh_a;
   float *dh_carry, *dgi_all, *d1_all, *dctx, *dpk, *denc, *dv_part, *dgi_enc, *dgh_enc, *hprev_dec, *hprev_enc,
       *demb_rows, *dxsel;
+  unsigned* sync;
+  bf16* xch;
 };
 
 static size_t scratch_need(const PvcrDims& d, int need_frame_grad) {
@@ -96,6 +98,8 @@ static void carve(Arena& a, const PvcrDims& d, int need_frame_grad, AttWs& w) {
   w.hprev_enc = a.alloc<float>(BN * H);
   w.demb_rows = a.alloc<float>(BL * E);
   w.dxsel = need_frame_grad ? a.alloc<float>(BN * V) : nullptr;
+  w.sync = a.alloc<unsigned>(256);
+  w.xch = a.alloc<bf16>((size_t)2 * B * 4 * H);
 }
 
 size_t s2vtatt_workspace(const PvcrDims& d, int need_frame_grad) {
@@ -123,6 +127,7 @@ static GruSeq encoder_seq(const PvcrDims& d, const PvcrS2vtAttParams& p, const A
   s.hp = w.enc_a.ptr; s.hp_ts = w.enc_a.ld; s.hp_ld = (long long)N * w.enc_a.ld; s.Hp = w.enc_a.Kp;
   s.gh = w.gh;
   s.r = w.er; s.z = w.ez; s.n = w.en; s.ghn = w.eghn;
+  s.sync = w.sync;
   return s;
 }
 
@@ -288,7 +293,7 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   eg.dh_carry = w.dh_carry;
   eg.dgi = w.dgi_enc; eg.dgi_ts = H3; eg.dgi_ld = (long long)N * H3;
   eg.dgh = w.dgh_enc; eg.dgh_ts = H3; eg.dgh_ld = (long long)N * H3;
-  eg.dgh_a = w.dgh_a; eg.whhT = w.whh_encT;
+  eg.dgh_a = w.dgh_a; eg.whhT = w.whh_encT; eg.xch = w.xch;
   PVCR_TRY(gru_seq_bwd(es, eg, st));
   // h_{t-1} rows in (b, t) order: zero for t = 0
   PVCR_TRY(fill_zero(w.hprev_enc, sizeof(float) * (size_t)BN * H, st));

@@ -64,3 +64,37 @@ def test_module_forward_returns_reference_logits(tag, precision):
     got = grads_of(m)
     for k in g:
         assert relerr(got[k], g[k]) < t_grad, (k, relerr(got[k], g[k]))
+
+
+def _oracle_case(B, N, V, H, E, L, Vc, seed):
+    from oracle import captioning_oracle as O
+    from oracle import workloads as W
+    p = W.s2vtatt_params(V, H, E, Vc, seed)
+    vid, s, s_len = W.make_batch(B, N, V, L, Vc, seed + 1)
+    ref = O.train_iter_s2vtatt({k: v.astype(np.float64) for k, v in p.items()}, vid.astype(np.float64), s, s_len,
+                               Vc - 4, L)
+    return p, vid, s, s_len, ref
+
+
+@pytest.mark.parametrize("precision,B", [("bf16", 24), ("bf16", 128), ("bf16x3", 24)])
+def test_msrvtt_shape_vs_oracle(precision, B):
+    """cfg2 dims (N=40, V=2048, H=512, E=300, L=30) with a reduced vocabulary so the float64 oracle stays fast:
+    exercises the persistent recurrent kernels (bf16) incl. a partially filled batch group (B=24)."""
+    from pvcr_b200.model import S2VTAttModel
+    N, V, H, E, L, Vc = 40, 2048, 512, 300, 30, 3000
+    p, vid, s, s_len, ref = _oracle_case(B, N, V, H, E, L, Vc, 77)
+    m = S2VTAttModel(FixtureGlove(Vc, E), 0.0, H, V, L, precision=precision)
+    m = to_cuda(m, p).train()
+    loss, acc, pred = m.forward_loss(torch.from_numpy(vid).cuda(), torch.from_numpy(s).cuda(),
+                                     torch.from_numpy(s_len).cuda())
+    loss.backward()
+    t_loss, _, t_grad, t_alpha = TOL[precision]
+    errs = {k: relerr(v, ref["grads"][k]) for k, v in grads_of(m).items()}
+    a_err = float(np.abs(m.last_alphas.cpu().numpy() - ref["alphas"]).max())
+    l_err = abs(loss.item() - ref["loss"]) / abs(ref["loss"])
+    print("\n[%s B=%d] loss rel %.2e  alphas abs %.2e  grads rel max %.2e (%s)" % (
+        precision, B, l_err, a_err, max(errs.values()), max(errs, key=errs.get)))
+    assert l_err < t_loss
+    assert a_err < t_alpha
+    for k, e in errs.items():
+        assert e < t_grad, (k, e)
