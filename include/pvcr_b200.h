@@ -38,6 +38,10 @@ void pvcr_prof_enable(int on);
 void pvcr_prof_reset(void);
 int pvcr_prof_read(uint64_t* launches, double* ms, double* work);
 
+/* Tuning aid: in-kernel phase timestamps (clock64 of CTA 0, [step][8]) of the last persistent-kernel launch. */
+int pvcr_debug_phase_timing(int on);
+int pvcr_debug_phase_read(long long* out, int steps);
+
 /* y[M,N] = x[M,K] w[N,K]^T + bias[N]      (torch.nn.Linear / F.linear; bias may be NULL) */
 size_t pvcr_linear_fwd_workspace(int M, int N, int K, int nsplit);
 int pvcr_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,

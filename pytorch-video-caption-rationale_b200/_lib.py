@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpvcr_b200.so")
+LIB_PATH = os.environ.get("PVCR_LIB", os.path.join(_HERE, "libpvcr_b200.so"))
 
 c_i64 = ctypes.c_int64
 c_int = ctypes.c_int
@@ -67,6 +67,8 @@ def _sig(L, name, restype, argtypes):
 # name -> (restype, argtypes); mirrors include/pvcr_b200.h one to one (tests/test_abi.py cross-checks the header)
 P = ctypes.POINTER
 SIGNATURES = {
+    "pvcr_debug_phase_timing": (c_int, [c_int]),
+    "pvcr_debug_phase_read": (c_int, [P(ctypes.c_longlong), c_int]),
     "pvcr_prof_num_classes": (c_int, []),
     "pvcr_prof_class_name": (ctypes.c_char_p, [c_int]),
     "pvcr_prof_enable": (None, [c_int]),

@@ -1,0 +1,706 @@
+// Persistent attention-decoder kernels of S2VTAtt (teacher forced): one cooperative launch runs all L decoder
+// steps.  Reference: Decoder.forward / forward_step and Attention.forward, model/S2VTAttModel.py:25-48,125-196.
+//
+// Work split: groups of bs = C videos served by C CTAs; CTA c of a group
+//   * owns hidden units [c*u, (c+1)*u): rows {W_q; W_hh r,z,n} (4u x H) and rows {W_c r,z,n} (3u x H) of the
+//     step's two weight matrices stay resident in shared memory (bf16, 128-byte swizzle) for all steps;
+//   * owns video c of the group for the attention: the video's proj_key (fp16) and encoder outputs (bf16),
+//     N x H each, stay resident in REGISTERS for all steps, so the attention phase touches no HBM/L2 data
+//     besides q (in) and ctx / alpha (out).
+// Per step:  P1  [q | gh] = [W_q; W_hh] h_{i-1}           (swapped tcgen05 MMA, D1 in TMEM)   -> q exchanged
+//            P2  alpha = softmax_n(v . tanh(q + pk_n)),  ctx = sum_n alpha_n enc_n            -> ctx exchanged
+//            P3  gi_c = W_c ctx                           (swapped tcgen05 MMA, D2 in TMEM)
+//            P4  GRU gates with gi = gi_c + (E W_e^T + b_ih)[i] (hoisted), h kept in fp32 registers -> h exchanged
+// Three group barriers per step on one monotonic counter per group.
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+#include <mutex>
+
+#include "host.h"
+#include "persist.cuh"
+
+namespace pvcr {
+
+constexpr int DEC_THREADS = 256;
+constexpr int DEC_ITEMS = 4;      // (unit, video) pairs per thread: u * bs <= DEC_ITEMS * DEC_THREADS
+
+
+template <int NF>
+__global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const DecPersistFwd p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int H = p.H, u = p.u, C = p.C, bsp = p.bsp, N = p.N, L = p.L, B = p.B, KB = H >> 6;
+  const int R1 = 4 * u, R3 = 3 * u;
+  uint8_t* sW1 = smem;
+  uint8_t* sW3 = sW1 + (size_t)KB * R1 * 128;
+  uint8_t* sX = sW3 + (size_t)KB * R3 * 128;
+  float* sS1 = reinterpret_cast<float*>(sX + (size_t)KB * bsp * 128);
+  const int s1_ld = R1 + 1, s3_ld = R3 + 1;
+  float* sS3 = sS1 + (size_t)bsp * s1_ld;
+  const int DG = H >> 3, FG = DEC_THREADS / DG, PW = DG >= 32 ? DG / 32 : 1;
+  float* sP = sS3 + (size_t)bsp * s3_ld;    // [N][PW]
+  float* sScore = sP + (size_t)N * PW;      // [N]
+  float* sC = sScore + N;                   // [FG][H]
+  uint64_t* bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sC + (size_t)FG * H) + 15) & ~uintptr_t(7));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int g = blockIdx.x / C, c = blockIdx.x % C;
+  const int b0 = g * C, j0 = c * u;
+  const int bs = min(C, B - b0);            // valid videos of this group
+  unsigned* ctr = p.counters + g * 32;
+
+  load_operand_rows(sW1, R1, 0, p.w1, p.w1_ld, j0, u, (long long)4 * H, H);
+  for (int q = 0; q < 3; ++q) {
+    load_operand_rows(sW1, R1, (q + 1) * u, p.w1, p.w1_ld, (long long)(q + 1) * H + j0, u, (long long)4 * H, H);
+    load_operand_rows(sW3, R3, q * u, p.w3, p.w3_ld, (long long)q * H + j0, u, (long long)3 * H, H);
+  }
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  const uint32_t ncols = 2 * bsp <= 32 ? 32u : (2 * bsp <= 64 ? 64u : (2 * bsp <= 128 ? 128u : 256u));
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, ncols);
+    tmem_relinquish();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d1 = *tmem_slot, tmem_d2 = tmem_d1 + (uint32_t)bsp;
+  const uint32_t idesc = umma_idesc_bf16(128, bsp);
+
+  // ---- attention residency: video vb, dims [d0, d0+8), frames fg + FG*m --------------------------------
+  const int vb = min(b0 + c, B - 1);
+  const bool video_ok = (c < bs);
+  const int dg = tid % DG, fg = tid / DG, d0 = dg * 8;
+  __half2 pkr[NF][4];
+  __nv_bfloat162 enr[NF][4];
+  float v8[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v8[e] = p.v[d0 + e];
+#pragma unroll
+  for (int m = 0; m < NF; ++m) {
+    const int n = fg + FG * m;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { pkr[m][e] = __floats2half2_rn(0.f, 0.f); enr[m][e] = __floats2bfloat162_rn(0.f, 0.f); }
+    if (n < N) {
+      const float4* s4 = reinterpret_cast<const float4*>(p.pk + ((long long)vb * N + n) * H + d0);
+      const float4 a = __ldg(s4), bq = __ldg(s4 + 1);
+      const float lim = 60000.f;
+      pkr[m][0] = __floats2half2_rn(fminf(fmaxf(a.x, -lim), lim), fminf(fmaxf(a.y, -lim), lim));
+      pkr[m][1] = __floats2half2_rn(fminf(fmaxf(a.z, -lim), lim), fminf(fmaxf(a.w, -lim), lim));
+      pkr[m][2] = __floats2half2_rn(fminf(fmaxf(bq.x, -lim), lim), fminf(fmaxf(bq.y, -lim), lim));
+      pkr[m][3] = __floats2half2_rn(fminf(fmaxf(bq.z, -lim), lim), fminf(fmaxf(bq.w, -lim), lim));
+      const uint4 ev = __ldg(reinterpret_cast<const uint4*>(p.enc_a + ((long long)vb * N + n) * p.enc_ld + d0));
+      enr[m][0] = *reinterpret_cast<const __nv_bfloat162*>(&ev.x);
+      enr[m][1] = *reinterpret_cast<const __nv_bfloat162*>(&ev.y);
+      enr[m][2] = *reinterpret_cast<const __nv_bfloat162*>(&ev.z);
+      enr[m][3] = *reinterpret_cast<const __nv_bfloat162*>(&ev.w);
+    }
+  }
+
+  // ---- GRU state of this thread's (unit, video) pairs ---------------------------------------------------
+  const int n_items = (u * C + DEC_THREADS - 1) / DEC_THREADS;
+  float hreg[DEC_ITEMS], bhr[DEC_ITEMS], bhz[DEC_ITEMS], bhn[DEC_ITEMS];
+#pragma unroll
+  for (int k = 0; k < DEC_ITEMS; ++k) {
+    hreg[k] = bhr[k] = bhz[k] = bhn[k] = 0.f;
+    if (k < n_items) {
+      const int idx = tid + k * DEC_THREADS, jj = idx % u, lb = idx / u;
+      if (lb < bs) {
+        const int j = j0 + jj, b = b0 + lb;
+        bhr[k] = p.b_hh[j]; bhz[k] = p.b_hh[H + j]; bhn[k] = p.b_hh[2 * H + j];
+        hreg[k] = p.enc[((long long)b * N + (N - 1)) * H + j];
+      }
+    }
+  }
+  uint32_t phase = 0;
+  unsigned target = 0;
+
+  for (int i = 0; i < L; ++i) {
+    // prefetch the hoisted embedding projection of this step
+    float epr[DEC_ITEMS], epz[DEC_ITEMS], epn[DEC_ITEMS];
+#pragma unroll
+    for (int k = 0; k < DEC_ITEMS; ++k) {
+      epr[k] = epz[k] = epn[k] = 0.f;
+      if (k < n_items) {
+        const int idx = tid + k * DEC_THREADS, jj = idx % u, lb = idx / u;
+        if (lb < bs) {
+          const float* e = p.ep + ((long long)(b0 + lb) * L + i) * 3 * H + j0 + jj;
+          epr[k] = __ldg(e); epz[k] = __ldg(e + H); epn[k] = __ldg(e + 2 * H);
+        }
+      }
+    }
+    // ---- P1: [q | gh] = [W_q; W_hh] h_{i-1} -------------------------------------------------------------
+    if (i > 0) {
+      group_wait(ctr, target);
+      load_operand_rows(sX, bsp, 0, p.hs_a + (long long)(i - 1) * p.hs_a_ld, (long long)L * p.hs_a_ld, b0, bsp,
+                        b0 + bs, H);
+    } else {
+      load_operand_rows(sX, bsp, 0, p.enc_a + (long long)(N - 1) * p.enc_ld, (long long)N * p.enc_ld, b0, bsp,
+                        b0 + bs, H);
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_swapped_mma(tmem_d1, smem_u32(sW1), R1, smem_u32(sX), bsp, H, idesc, bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    if (tid < 128) tmem_to_smem_cols(tmem_d1, sS1, s1_ld, R1, bsp);
+    tc_fence_before();
+    __syncthreads();
+    {
+      float* qout = p.q_all + (long long)i * B * p.q_ld;
+      for (int idx = tid; idx < u * bs; idx += DEC_THREADS) {
+        const int jj = idx % u, lb = idx / u;
+        qout[(long long)(b0 + lb) * p.q_ld + j0 + jj] = sS1[lb * s1_ld + jj];
+      }
+    }
+    group_arrive(ctr);
+    target += (unsigned)C;
+    // ---- P2: attention of video vb ---------------------------------------------------------------------
+    group_wait(ctr, target);
+    {
+      const float4* q4 = reinterpret_cast<const float4*>(p.q_all + (long long)i * B * p.q_ld + (long long)vb * p.q_ld + d0);
+      const float4 qa = __ldcg(q4), qb = __ldcg(q4 + 1);
+      const float q8[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+      const int W = DG < 32 ? DG : 32;
+#pragma unroll
+      for (int m = 0; m < NF; ++m) {
+        float s = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 pf = __half22float2(pkr[m][e]);
+          s += v8[2 * e] * fast_tanh(q8[2 * e] + pf.x) + v8[2 * e + 1] * fast_tanh(q8[2 * e + 1] + pf.y);
+        }
+        for (int o = W >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const int n = fg + FG * m;
+        if ((tid % W) == 0 && n < N) sP[n * PW + dg / 32] = s;
+      }
+      __syncthreads();
+      if (tid < N) {
+        float s = 0.f;
+        for (int w = 0; w < PW; ++w) s += sP[tid * PW + w];
+        sScore[tid] = s;
+      }
+      __syncthreads();
+      float mx = -INFINITY;
+      for (int n = 0; n < N; ++n) mx = fmaxf(mx, sScore[n]);
+      float den = 0.f;
+      for (int n = 0; n < N; ++n) den += __expf(sScore[n] - mx);
+      const float inv = 1.f / den;
+      float c8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int m = 0; m < NF; ++m) {
+        const int n = fg + FG * m;
+        if (n < N) {
+          const float a = __expf(sScore[n] - mx) * inv;
+          if (dg == 0 && video_ok) p.alpha[((long long)i * B + vb) * N + n] = a;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 ef = __bfloat1622float2(enr[m][e]);
+            c8[2 * e] += a * ef.x; c8[2 * e + 1] += a * ef.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sC[fg * H + d0 + e] = c8[e];
+      __syncthreads();
+      if (video_ok) {
+        for (int d = tid; d < H; d += DEC_THREADS) {
+          float cx = 0.f;
+          for (int f = 0; f < FG; ++f) cx += sC[f * H + d];
+          p.ctx_all[((long long)vb * L + i) * H + d] = cx;
+          p.ctx_x[((long long)i * B + vb) * H + d] = __float2bfloat16_rn(cx);
+        }
+      }
+    }
+    group_arrive(ctr);
+    target += (unsigned)C;
+    // ---- P3: gi_c = W_c ctx -----------------------------------------------------------------------------
+    group_wait(ctr, target);
+    load_operand_rows(sX, bsp, 0, p.ctx_x + (long long)i * B * H, H, b0, bsp, b0 + bs, H);
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_swapped_mma(tmem_d2, smem_u32(sW3), R3, smem_u32(sX), bsp, H, idesc, bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    if (tid < 128) tmem_to_smem_cols(tmem_d2, sS3, s3_ld, R3, bsp);
+    tc_fence_before();
+    __syncthreads();
+    // ---- P4: gates ----------------------------------------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < DEC_ITEMS; ++k) {
+      if (k < n_items) {
+        const int idx = tid + k * DEC_THREADS, jj = idx % u, lb = idx / u;
+        if (lb < bs) {
+          const int j = j0 + jj, b = b0 + lb;
+          const float gir = sS3[lb * s3_ld + jj] + epr[k];
+          const float giz = sS3[lb * s3_ld + u + jj] + epz[k];
+          const float gin = sS3[lb * s3_ld + 2 * u + jj] + epn[k];
+          const float ghr = sS1[lb * s1_ld + u + jj] + bhr[k];
+          const float ghz = sS1[lb * s1_ld + 2 * u + jj] + bhz[k];
+          const float ghn = sS1[lb * s1_ld + 3 * u + jj] + bhn[k];
+          const float r = sigmoidf_(gir + ghr);
+          const float z = sigmoidf_(giz + ghz);
+          const float n = fast_tanh(gin + r * ghn);
+          const float hn = (1.f - z) * n + z * hreg[k];
+          hreg[k] = hn;
+          p.hs[((long long)b * L + i) * H + j] = hn;
+          p.hs_a[((long long)b * L + i) * p.hs_a_ld + j] = __float2bfloat16_rn(hn);
+          const long long o = ((long long)i * B + b) * H + j;
+          p.r[o] = r; p.z[o] = z; p.n[o] = n; p.ghn[o] = ghn;
+        }
+      }
+    }
+    group_arrive(ctr);
+    target += (unsigned)C;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_d1, ncols);
+  }
+}
+
+// ---- backward sweep -----------------------------------------------------------------------------------------
+// Per step i (reverse):  B1  gate gradients of this CTA's (unit, video) pairs            -> [drp|dzp|dghn|dnp] exchanged
+//                        B2  dctx = W_c^T dgi  and the W_hh^T dgh part of dh_{i-1}       (tcgen05, K in chunks of H)
+//                        B3  attention gradient of video vb: d alpha, d score, dq         -> dq exchanged
+//                        B4  dh_{i-1} += W_q^T dq                                         (tcgen05), carry in registers
+// d enc / d proj_key / d v do not feed back into the recurrence and are accumulated after the sweep by
+// attn_grad_hoisted from the saved alpha, d score, dctx and q.
+template <int NF>
+__global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_bwd_kernel(const DecPersistBwd p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int H = p.H, u = p.u, C = p.C, bsp = p.bsp, N = p.N, L = p.L, B = p.B, KBH = H >> 6;
+  uint8_t* sWA = smem;                                         // 3*KBH k-blocks x (u rows x 128 B)
+  uint8_t* sWB = sWA + (size_t)3 * KBH * u * 128;              // 4*KBH k-blocks
+  uint8_t* sX0 = sWB + (size_t)4 * KBH * u * 128;              // chunk buffers: KBH x (bsp x 128 B) each
+  uint8_t* sX1 = sX0 + (size_t)KBH * bsp * 128;
+  float* sSA = reinterpret_cast<float*>(sX1 + (size_t)KBH * bsp * 128);
+  const int s_ld = u + 1;
+  float* sSB = sSA + (size_t)bsp * s_ld;
+  const int DG = H >> 3, FG = DEC_THREADS / DG, PW = DG >= 32 ? DG / 32 : 1;
+  float* sP = sSB + (size_t)bsp * s_ld;     // [N][PW]
+  float* sDa = sP + (size_t)N * PW;         // [N] d alpha -> d score
+  float* sAl = sDa + N;                     // [N] alpha
+  float* sC = sAl + N;                      // [FG][H]
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sC + (size_t)FG * H) + 15) & ~uintptr_t(7));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int g = blockIdx.x / C, c = blockIdx.x % C;
+  const int b0 = g * C, j0 = c * u;
+  const int bs = min(C, B - b0);
+  unsigned* ctr = p.counters + g * 32;
+
+  load_operand_rows(sWA, u, 0, p.wcT, p.wcT_ld, j0, u, H, 3 * H);
+  load_operand_rows(sWB, u, 0, p.wcatT, p.wcatT_ld, j0, u, H, 4 * H);
+  if (tid == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    fence_barrier_init();
+  }
+  const uint32_t ncols = 2 * bsp <= 32 ? 32u : (2 * bsp <= 64 ? 64u : (2 * bsp <= 128 ? 128u : 256u));
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, ncols);
+    tmem_relinquish();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_a = *tmem_slot, tmem_b = tmem_a + (uint32_t)bsp;
+  const uint32_t idesc = umma_idesc_bf16(128, bsp);
+  const uint32_t aWA = smem_u32(sWA), aWB = smem_u32(sWB), aX0 = smem_u32(sX0), aX1 = smem_u32(sX1);
+
+  // attention residency (as in the forward kernel)
+  const int vb = min(b0 + c, B - 1);
+  const bool video_ok = (c < bs);
+  const int dg = tid % DG, fg = tid / DG, d0 = dg * 8;
+  __half2 pkr[NF][4];
+  __nv_bfloat162 enr[NF][4];
+  float v8[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v8[e] = p.v[d0 + e];
+#pragma unroll
+  for (int m = 0; m < NF; ++m) {
+    const int n = fg + FG * m;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { pkr[m][e] = __floats2half2_rn(0.f, 0.f); enr[m][e] = __floats2bfloat162_rn(0.f, 0.f); }
+    if (n < N) {
+      const float4* s4 = reinterpret_cast<const float4*>(p.pk + ((long long)vb * N + n) * H + d0);
+      const float4 a = __ldg(s4), bq = __ldg(s4 + 1);
+      const float lim = 60000.f;
+      pkr[m][0] = __floats2half2_rn(fminf(fmaxf(a.x, -lim), lim), fminf(fmaxf(a.y, -lim), lim));
+      pkr[m][1] = __floats2half2_rn(fminf(fmaxf(a.z, -lim), lim), fminf(fmaxf(a.w, -lim), lim));
+      pkr[m][2] = __floats2half2_rn(fminf(fmaxf(bq.x, -lim), lim), fminf(fmaxf(bq.y, -lim), lim));
+      pkr[m][3] = __floats2half2_rn(fminf(fmaxf(bq.z, -lim), lim), fminf(fmaxf(bq.w, -lim), lim));
+      const uint4 ev = __ldg(reinterpret_cast<const uint4*>(p.enc_a + ((long long)vb * N + n) * p.enc_ld + d0));
+      enr[m][0] = *reinterpret_cast<const __nv_bfloat162*>(&ev.x);
+      enr[m][1] = *reinterpret_cast<const __nv_bfloat162*>(&ev.y);
+      enr[m][2] = *reinterpret_cast<const __nv_bfloat162*>(&ev.z);
+      enr[m][3] = *reinterpret_cast<const __nv_bfloat162*>(&ev.w);
+    }
+  }
+
+  const int n_items = (u * C + DEC_THREADS - 1) / DEC_THREADS;
+  float dhc[DEC_ITEMS];
+#pragma unroll
+  for (int k = 0; k < DEC_ITEMS; ++k) dhc[k] = 0.f;
+  uint32_t ph0 = 0, ph1 = 0, phA = 0;
+  unsigned target = 0;
+  const long long xrow = (long long)5 * H;
+
+  for (int i = L - 1; i >= 0; --i) {
+    bf16* xg = p.xg + (size_t)(i & 1) * B * xrow;
+    // ---- B1: gate gradients ---------------------------------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < DEC_ITEMS; ++k) {
+      if (k < n_items) {
+        const int idx = tid + k * DEC_THREADS, jj = idx % u, lb = idx / u;
+        if (lb < bs) {
+          const int j = j0 + jj, b = b0 + lb;
+          const float dh = dhc[k] + p.d_hs[((long long)b * L + i) * H + j];
+          const long long o = ((long long)i * B + b) * H + j;
+          const float r = p.r[o], z = p.z[o], n = p.n[o], ghn = p.ghn[o];
+          const float hp = i > 0 ? p.hs[((long long)b * L + (i - 1)) * H + j] : p.enc[((long long)b * N + (N - 1)) * H + j];
+          const float dn = dh * (1.f - z), dz = dh * (hp - n);
+          const float dnp = dn * (1.f - n * n);
+          const float dzp = dz * z * (1.f - z);
+          const float drp = dnp * ghn * r * (1.f - r);
+          const float dghn = dnp * r;
+          float* dgi = p.dgi_all + ((long long)b * L + i) * 3 * H;
+          float* d1 = p.d1_all + ((long long)b * L + i) * 4 * H + H;
+          dgi[j] = drp; dgi[H + j] = dzp; dgi[2 * H + j] = dnp;
+          d1[j] = drp; d1[H + j] = dzp; d1[2 * H + j] = dghn;
+          bf16* x = xg + (long long)b * xrow;
+          x[H + j] = __float2bfloat16_rn(drp); x[2 * H + j] = __float2bfloat16_rn(dzp);
+          x[3 * H + j] = __float2bfloat16_rn(dghn); x[4 * H + j] = __float2bfloat16_rn(dnp);
+          dhc[k] = dh * z;
+        }
+      }
+    }
+    group_arrive(ctr);
+    target += (unsigned)C;
+    // ---- B2: dctx = W_c^T [drp|dzp|dnp] ; dh part = W_hh^T [drp|dzp|dghn] -------------------------------------
+    group_wait(ctr, target);
+    // chunk drp -> X0 : A k-chunk 0, B k-chunk 1
+    load_operand_rows(sX0, bsp, 0, xg + H, xrow, b0, bsp, b0 + bs, H);
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_mma_chunk(tmem_a, aWA, u, 0, aX0, bsp, H, idesc, false);
+      issue_mma_chunk(tmem_b, aWB, u, KBH, aX0, bsp, H, idesc, false);
+      umma_commit(&bars[0]);
+    }
+    // chunk dzp -> X1 : A k-chunk 1, B k-chunk 2
+    load_operand_rows(sX1, bsp, 0, xg + 2 * H, xrow, b0, bsp, b0 + bs, H);
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_mma_chunk(tmem_a, aWA, u, KBH, aX1, bsp, H, idesc, true);
+      issue_mma_chunk(tmem_b, aWB, u, 2 * KBH, aX1, bsp, H, idesc, true);
+      umma_commit(&bars[1]);
+    }
+    // chunk dnp -> X0 (after its MMAs retired) : A k-chunk 2, completes dctx
+    mbar_wait(&bars[0], ph0); ph0 ^= 1;
+    load_operand_rows(sX0, bsp, 0, xg + 4 * H, xrow, b0, bsp, b0 + bs, H);
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_mma_chunk(tmem_a, aWA, u, 2 * KBH, aX0, bsp, H, idesc, true);
+      umma_commit(&bars[2]);
+    }
+    // chunk dghn -> X1 : B k-chunk 3
+    mbar_wait(&bars[1], ph1); ph1 ^= 1;
+    load_operand_rows(sX1, bsp, 0, xg + 3 * H, xrow, b0, bsp, b0 + bs, H);
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_mma_chunk(tmem_b, aWB, u, 3 * KBH, aX1, bsp, H, idesc, true);
+      umma_commit(&bars[1]);
+    }
+    mbar_wait(&bars[2], phA); phA ^= 1;
+    tc_fence_after();
+    if (tid < 128) tmem_to_smem_cols(tmem_a, sSA, s_ld, u, bsp);
+    tc_fence_before();
+    __syncthreads();
+    {
+      float* dc = p.dctx_all + (long long)i * B * H;
+      for (int idx = tid; idx < u * bs; idx += DEC_THREADS) {
+        const int jj = idx % u, lb = idx / u;
+        dc[(long long)(b0 + lb) * H + j0 + jj] = sSA[lb * s_ld + jj];
+      }
+    }
+    group_arrive(ctr);
+    target += (unsigned)C;
+    // ---- B3: attention gradient of video vb ------------------------------------------------------------------
+    group_wait(ctr, target);
+    {
+      const float4* c4 = reinterpret_cast<const float4*>(p.dctx_all + ((long long)i * B + vb) * H + d0);
+      const float4 ca = __ldcg(c4), cb = __ldcg(c4 + 1);
+      const float dc8[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+      const float4* q4 = reinterpret_cast<const float4*>(p.q_all + (long long)i * B * p.q_ld + (long long)vb * p.q_ld + d0);
+      const float4 qa = __ldg(q4), qb = __ldg(q4 + 1);
+      const float q8[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+      if (tid < N) sAl[tid] = __ldg(p.alpha + ((long long)i * B + vb) * N + tid);
+      const int W = DG < 32 ? DG : 32;
+#pragma unroll
+      for (int m = 0; m < NF; ++m) {
+        float s = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 ef = __bfloat1622float2(enr[m][e]);
+          s += dc8[2 * e] * ef.x + dc8[2 * e + 1] * ef.y;
+        }
+        for (int o = W >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const int n = fg + FG * m;
+        if ((tid % W) == 0 && n < N) sP[n * PW + dg / 32] = s;
+      }
+      __syncthreads();
+      if (tid < N) {
+        float s = 0.f;
+        for (int w = 0; w < PW; ++w) s += sP[tid * PW + w];
+        sDa[tid] = s;                       // d alpha_n = dctx . enc_n
+      }
+      __syncthreads();
+      float dot = 0.f;
+      for (int n = 0; n < N; ++n) dot += sAl[n] * sDa[n];
+      float dq8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int m = 0; m < NF; ++m) {
+        const int n = fg + FG * m;
+        if (n < N) {
+          const float ds = sAl[n] * (sDa[n] - dot);          // d score_n
+          if (dg == 0 && video_ok) p.ds_all[((long long)i * B + vb) * N + n] = ds;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 pf = __half22float2(pkr[m][e]);
+            const float e0 = fast_tanh(q8[2 * e] + pf.x), e1 = fast_tanh(q8[2 * e + 1] + pf.y);
+            dq8[2 * e] += ds * (1.f - e0 * e0);
+            dq8[2 * e + 1] += ds * (1.f - e1 * e1);
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sC[fg * H + d0 + e] = dq8[e] * v8[e];
+      __syncthreads();
+      if (video_ok) {
+        for (int d = tid; d < H; d += DEC_THREADS) {
+          float dq = 0.f;
+          for (int f = 0; f < FG; ++f) dq += sC[f * H + d];
+          p.d1_all[((long long)vb * L + i) * 4 * H + d] = dq;
+          xg[(long long)vb * xrow + d] = __float2bfloat16_rn(dq);
+        }
+      }
+    }
+    group_arrive(ctr);
+    target += (unsigned)C;
+    // ---- B4: dh_{i-1} = dh z + W_hh^T dgh + W_q^T dq -----------------------------------------------------------
+    group_wait(ctr, target);
+    load_operand_rows(sX0, bsp, 0, xg, xrow, b0, bsp, b0 + bs, H);
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_mma_chunk(tmem_b, aWB, u, 0, aX0, bsp, H, idesc, true);
+      umma_commit(&bars[0]);
+    }
+    mbar_wait(&bars[1], ph1); ph1 ^= 1;      // chunk dghn retired (X1 free for the next step)
+    mbar_wait(&bars[0], ph0); ph0 ^= 1;
+    tc_fence_after();
+    if (tid < 128) tmem_to_smem_cols(tmem_b, sSB, s_ld, u, bsp);
+    tc_fence_before();
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < DEC_ITEMS; ++k) {
+      if (k < n_items) {
+        const int idx = tid + k * DEC_THREADS, jj = idx % u, lb = idx / u;
+        if (lb < bs) dhc[k] += sSB[lb * s_ld + jj];
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < DEC_ITEMS; ++k) {
+    if (k < n_items) {
+      const int idx = tid + k * DEC_THREADS, jj = idx % u, lb = idx / u;
+      if (lb < bs) p.dh_carry[(long long)(b0 + lb) * H + j0 + jj] = dhc[k];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_a, ncols);
+  }
+}
+
+// One CTA per (video, 64-dim tile): thread = (dim, frame group); frames fg + 4m.
+constexpr int AG_DIMS = 64, AG_FG = 4, AG_NF = 20;
+__global__ void __launch_bounds__(AG_DIMS * AG_FG) attn_grad_hoisted_kernel(const AttnGradArgs a) {
+  extern __shared__ float ag_sm[];
+  const int L = a.L, B = a.B, N = a.N, H = a.H;
+  float* sAl = ag_sm;                 // [L][N]
+  float* sDs = sAl + L * N;           // [L][N]
+  float* sV = sDs + L * N;            // [AG_FG][AG_DIMS]
+  const int b = blockIdx.x, d = blockIdx.y * AG_DIMS + (threadIdx.x % AG_DIMS), fg = threadIdx.x / AG_DIMS;
+  for (int i = threadIdx.x; i < L * N; i += blockDim.x) {
+    const int l = i / N, n = i - l * N;
+    sAl[i] = a.alpha[((long long)l * B + b) * N + n];
+    sDs[i] = a.ds[((long long)l * B + b) * N + n];
+  }
+  __syncthreads();
+  const bool ok = d < H;
+  float pk[AG_NF], acc_pk[AG_NF], acc_en[AG_NF];
+#pragma unroll
+  for (int m = 0; m < AG_NF; ++m) {
+    const int n = fg + AG_FG * m;
+    pk[m] = (ok && n < N) ? a.pk[((long long)b * N + n) * H + d] : 0.f;
+    acc_pk[m] = 0.f; acc_en[m] = 0.f;
+  }
+  float dv = 0.f;
+  for (int l = 0; l < L; ++l) {
+    const float q = ok ? a.q[(long long)l * B * a.q_ld + (long long)b * a.q_ld + d] : 0.f;
+    const float dc = ok ? a.dctx[((long long)l * B + b) * H + d] : 0.f;
+#pragma unroll
+    for (int m = 0; m < AG_NF; ++m) {
+      const int n = fg + AG_FG * m;
+      if (n < N) {
+        const float ds = sDs[l * N + n];
+        const float e = fast_tanh(q + pk[m]);
+        acc_pk[m] += ds * (1.f - e * e);
+        acc_en[m] += sAl[l * N + n] * dc;
+        dv += ds * e;
+      }
+    }
+  }
+  const float vd = ok ? a.v[d] : 0.f;
+#pragma unroll
+  for (int m = 0; m < AG_NF; ++m) {
+    const int n = fg + AG_FG * m;
+    if (ok && n < N) {
+      a.dpk[((long long)b * N + n) * H + d] = acc_pk[m] * vd;
+      a.denc[((long long)b * N + n) * H + d] = acc_en[m];
+    }
+  }
+  sV[fg * AG_DIMS + (threadIdx.x % AG_DIMS)] = dv;
+  __syncthreads();
+  if (fg == 0 && ok) {
+    float s = 0.f;
+    for (int f = 0; f < AG_FG; ++f) s += sV[f * AG_DIMS + threadIdx.x];
+    a.dv_part[(long long)b * H + d] = s;
+  }
+}
+
+int attn_grad_hoisted(const AttnGradArgs& a, cudaStream_t st) {
+  PVCR_REQUIRE(a.N <= AG_FG * AG_NF, "attn_grad_hoisted: N=%d > %d frames", a.N, AG_FG * AG_NF);
+  const size_t smem = ((size_t)2 * a.L * a.N + AG_FG * AG_DIMS) * sizeof(float);
+  PVCR_REQUIRE(smem <= 48 * 1024, "attn_grad_hoisted: L=%d N=%d needs %zu B of shared memory", a.L, a.N, smem);
+  LaunchScope ls_(KC_ATTN, st);
+  attn_grad_hoisted_kernel<<<dim3(a.B, cdiv(a.H, AG_DIMS)), AG_DIMS * AG_FG, smem, st>>>(a);
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  return PVCR_OK;
+}
+
+// ---- host side -------------------------------------------------------------------------------------------
+struct DecPlan { int C, u, bsp, G, NF; size_t smem; };
+
+static int dec_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+static bool plan_dec(int B, int N, int H, DecPlan& pl) {
+  if (H < 64 || H > 512 || (H & (H - 1)) != 0) return false;
+  pl.C = H / 8 < 32 ? H / 8 : 32;
+  pl.u = H / pl.C;
+  if (pl.u % 8 != 0 || 4 * pl.u > 128) return false;
+  pl.bsp = (pl.C + 15) / 16 * 16;
+  pl.G = (B + pl.C - 1) / pl.C;
+  if ((long long)pl.G * pl.C > dec_num_sms()) return false;
+  if (pl.u * pl.C > DEC_ITEMS * DEC_THREADS) return false;
+  const int DG = H / 8, FG = DEC_THREADS / DG, PW = DG >= 32 ? DG / 32 : 1;
+  const int nf = (N + FG - 1) / FG;
+  if (nf > 10) return false;
+  pl.NF = nf <= 2 ? 2 : (nf <= 5 ? 5 : 10);
+  const size_t KB = H / 64;
+  size_t s = KB * 4 * pl.u * 128 + KB * 3 * pl.u * 128 + KB * pl.bsp * 128;
+  s += ((size_t)pl.bsp * (4 * pl.u + 1) + (size_t)pl.bsp * (3 * pl.u + 1) + (size_t)N * PW + N + (size_t)FG * H) * 4;
+  s += 64 + 16 * 1024 + 1024;      // barrier/slot, over-read tail of the last W3 k-block, alignment slack
+  pl.smem = s;
+  return s <= 227 * 1024;
+}
+
+bool dec_persist_eligible(int B, int N, int H, int nsplit, int Hp) {
+  DecPlan pl;
+  static const bool off = getenv("PVCR_NO_PERSIST_DEC") != nullptr;     // A/B knob for profiling
+  return !off && nsplit == 1 && Hp == H && plan_dec(B, N, H, pl);
+}
+
+int dec_persist_fwd(const DecPersistFwd& p0, cudaStream_t st) {
+  DecPlan pl;
+  PVCR_REQUIRE(plan_dec(p0.B, p0.N, p0.H, pl), "dec_persist_fwd: shape B=%d N=%d H=%d not supported", p0.B, p0.N, p0.H);
+  DecPersistFwd p = p0;
+  p.C = pl.C; p.u = pl.u; p.bsp = pl.bsp;
+  const void* kern = pl.NF == 2 ? (const void*)dec_persist_fwd_kernel<2>
+                     : (pl.NF == 5 ? (const void*)dec_persist_fwd_kernel<5> : (const void*)dec_persist_fwd_kernel<10>);
+  PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  int per_sm = 0;
+  PVCR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DEC_THREADS, pl.smem));
+  const int grid = pl.G * pl.C;
+  PVCR_REQUIRE(per_sm * dec_num_sms() >= grid, "dec_persist_fwd: %d CTAs cannot be co-resident", grid);
+  PVCR_TRY(fill_zero(p.counters, sizeof(unsigned) * 32 * pl.G, st));
+  void* args[] = {&p};
+  LaunchScope ls_(KC_RECURRENT, st);
+  PVCR_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(DEC_THREADS), args, pl.smem, st));
+  return PVCR_OK;
+}
+
+int dec_persist_bwd(const DecPersistBwd& p0, cudaStream_t st) {
+  DecPlan pl;
+  PVCR_REQUIRE(plan_dec(p0.B, p0.N, p0.H, pl), "dec_persist_bwd: shape B=%d N=%d H=%d not supported", p0.B, p0.N, p0.H);
+  DecPersistBwd p = p0;
+  p.C = pl.C; p.u = pl.u; p.bsp = pl.bsp;
+  const int H = p.H, KBH = H / 64, DG = H / 8, FG = DEC_THREADS / DG, PW = DG >= 32 ? DG / 32 : 1;
+  size_t smem = (size_t)7 * KBH * pl.u * 128 + (size_t)2 * KBH * pl.bsp * 128;
+  smem += ((size_t)2 * pl.bsp * (pl.u + 1) + (size_t)p.N * PW + 2 * p.N + (size_t)FG * H) * 4 + 64 + 1024;
+  smem += 16 * 1024;     // the 128-row MMA tile of the last weight k-blocks over-reads up to 16 KB past the slices
+  PVCR_REQUIRE(smem <= 227 * 1024, "dec_persist_bwd: needs %zu B of shared memory", smem);
+  const void* kern = pl.NF == 2 ? (const void*)dec_persist_bwd_kernel<2>
+                     : (pl.NF == 5 ? (const void*)dec_persist_bwd_kernel<5> : (const void*)dec_persist_bwd_kernel<10>);
+  PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  PVCR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DEC_THREADS, smem));
+  const int grid = pl.G * pl.C;
+  PVCR_REQUIRE(per_sm * dec_num_sms() >= grid, "dec_persist_bwd: %d CTAs cannot be co-resident", grid);
+  PVCR_TRY(fill_zero(p.counters, sizeof(unsigned) * 32 * pl.G, st));
+  void* args[] = {&p};
+  LaunchScope ls_(KC_RECURRENT, st);
+  PVCR_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(DEC_THREADS), args, smem, st));
+  return PVCR_OK;
+}
+
+}  // namespace pvcr

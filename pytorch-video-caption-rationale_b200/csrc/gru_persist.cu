@@ -8,6 +8,7 @@
 //             the gate math for its (unit, video) pairs with h kept in fp32 registers across steps.
 //   backward: rows u of W_hh^T (u x 3H bf16) resident; per step the gate gradients of its (unit, video) pairs,
 //             exchange of dgh (bf16), then D[u, bs] = W_hh^T slice * dgh^T added into the fp32 dh carry registers.
+#include <cstdlib>
 #include <mutex>
 
 #include "host.h"
@@ -15,6 +16,12 @@
 
 namespace pvcr {
 
+#ifndef DBG_STALE_X
+#define DBG_STALE_X 0       // experiment knob: read step 0's h every step (stale data) to isolate the load latency
+#endif
+#ifndef DBG_NO_GI_PREFETCH
+#define DBG_NO_GI_PREFETCH 0
+#endif
 constexpr int MAX_ITEMS = 8;    // (unit, video) pairs per thread: u * bs <= MAX_ITEMS * PERSIST_THREADS
 
 struct GruPersistFwd {
@@ -30,6 +37,7 @@ struct GruPersistFwd {
   bf16* hp; long long hp_ts, hp_ld;
   float *r, *z, *n, *ghn;                   // [T][B,H]
   unsigned* counters;
+  long long* dbg;
 };
 
 __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_fwd_kernel(const GruPersistFwd p) {
@@ -47,7 +55,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_fwd_kernel(con
   const int tid = threadIdx.x, warp = tid >> 5;
   const int g = blockIdx.x / p.C, c = blockIdx.x % p.C;
   const int b0 = g * bs, j0 = c * u;
-  unsigned* ctr = p.counters + g;
+  unsigned* ctr = p.counters + g * 32;
 
   // resident weights: local row q*u + jj  <-  W_hh row q*H + j0 + jj
   for (int q = 0; q < 3; ++q)
@@ -94,7 +102,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_fwd_kernel(con
       if (k < n_items) {
         const int idx = tid + k * PERSIST_THREADS, jj = idx % u, lb = idx / u;
         const int j = j0 + jj, b = b0 + lb;
-        if (lb < bs && b < p.B) {
+        if (!DBG_NO_GI_PREFETCH && lb < bs && b < p.B) {
           const float* gp = p.gi + (long long)t * p.gi_ts + (long long)b * p.gi_ld;
           gir[k] = __ldg(gp + j); giz[k] = __ldg(gp + H + j); gin[k] = __ldg(gp + 2 * H + j);
           if (p.gi_b && t >= p.gi_b_from) {
@@ -106,15 +114,19 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_fwd_kernel(con
       }
     }
     const bool has_prev = (t > 0) || (p.h0p != nullptr);
+    phase_stamp(p.dbg, t, 0);
     if (has_prev) {
       if (t > 0) {
         group_wait(ctr, (unsigned)(p.C * t));
-        load_operand_rows(sX, bs, 0, p.hp + (long long)(t - 1) * p.hp_ts, p.hp_ld, b0, bs, p.B, H);
+        phase_stamp(p.dbg, t, 1);
+        load_operand_rows(sX, bs, 0, p.hp + (long long)(DBG_STALE_X ? 0 : t - 1) * p.hp_ts, p.hp_ld, b0, bs, p.B, H);
+        phase_stamp(p.dbg, t, 7);
       } else {
         load_operand_rows(sX, bs, 0, p.h0p, p.h0p_ld, b0, bs, p.B, H);
       }
       fence_proxy_async();
       __syncthreads();
+      phase_stamp(p.dbg, t, 2);
       if (tid == 0) {
         tc_fence_after();
         issue_swapped_mma(tmem_base, smem_u32(sW), Rw, smem_u32(sX), bs, H, idesc, bar);
@@ -122,9 +134,11 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_fwd_kernel(con
       mbar_wait(bar, phase);
       phase ^= 1;
       tc_fence_after();
-      tmem_to_smem_cols(tmem_base, sS, s_ld, Rw, bs);
+      phase_stamp(p.dbg, t, 3);
+      if (tid < 128) tmem_to_smem_cols(tmem_base, sS, s_ld, Rw, bs);
       tc_fence_before();
       __syncthreads();
+      phase_stamp(p.dbg, t, 4);
     }
 #pragma unroll
     for (int k = 0; k < MAX_ITEMS; ++k) {
@@ -136,9 +150,9 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_fwd_kernel(con
           if (has_prev) {
             ghr += sS[lb * s_ld + jj]; ghz += sS[lb * s_ld + u + jj]; ghn += sS[lb * s_ld + 2 * u + jj];
           }
-          const float r = 1.f / (1.f + expf(-(gir[k] + ghr)));
-          const float z = 1.f / (1.f + expf(-(giz[k] + ghz)));
-          const float n = tanhf(gin[k] + r * ghn);
+          const float r = sigmoidf_(gir[k] + ghr);
+          const float z = sigmoidf_(giz[k] + ghz);
+          const float n = fast_tanh(gin[k] + r * ghn);
           const float hn = (1.f - z) * n + z * hreg[k];
           hreg[k] = hn;
           p.h[(long long)t * p.h_ts + (long long)b * p.h_ld + j] = hn;
@@ -148,7 +162,9 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_fwd_kernel(con
         }
       }
     }
+    phase_stamp(p.dbg, t, 5);
     group_arrive(ctr);      // also protects sS / sX reuse by the next step
+    phase_stamp(p.dbg, t, 6);
   }
   tc_fence_before();
   __syncthreads();
@@ -187,7 +203,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_bwd_kernel(con
   const int tid = threadIdx.x, warp = tid >> 5;
   const int g = blockIdx.x / p.C, c = blockIdx.x % p.C;
   const int b0 = g * bs, j0 = c * u;
-  unsigned* ctr = p.counters + g;
+  unsigned* ctr = p.counters + g * 32;
 
   load_operand_rows(sW, u, 0, p.whhT, p.whhT_ld, j0, u, H, K);
   if (tid == 0) {
@@ -269,7 +285,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_bwd_kernel(con
       mbar_wait(bar, phase);
       phase ^= 1;
       tc_fence_after();
-      tmem_to_smem_cols(tmem_base, sS, s_ld, u, bs);
+      if (tid < 128) tmem_to_smem_cols(tmem_base, sS, s_ld, u, bs);
       tc_fence_before();
       __syncthreads();
 #pragma unroll
@@ -349,7 +365,8 @@ static int coop_launch(const void* kern, int grid, size_t smem, void* param, cud
 
 bool gru_persist_eligible(const GruSeq& s) {
   PersistPlan pl;
-  return s.nsplit == 1 && s.sync != nullptr && s.hp != nullptr && s.Hp == s.H && plan_gru(s.B, s.H, 0, pl, false) &&
+  static const bool off = getenv("PVCR_NO_PERSIST_GRU") != nullptr;     // A/B knob for profiling
+  return !off && s.nsplit == 1 && s.sync != nullptr && s.hp != nullptr && s.Hp == s.H && plan_gru(s.B, s.H, 0, pl, false) &&
          plan_gru(s.B, s.H, 0, pl, true) && (s.h0 == nullptr || s.h0_planes != nullptr);
 }
 
@@ -367,7 +384,8 @@ int gru_persist_fwd(const GruSeq& s, cudaStream_t st) {
   p.hp = s.hp; p.hp_ts = s.hp_ts; p.hp_ld = s.hp_ld;
   p.r = s.r; p.z = s.z; p.n = s.n; p.ghn = s.ghn;
   p.counters = s.sync;
-  PVCR_TRY(fill_zero(s.sync, sizeof(unsigned) * pl.G, st));
+  p.dbg = debug_phase_buffer();
+  PVCR_TRY(fill_zero(s.sync, sizeof(unsigned) * 32 * pl.G, st));
   return coop_launch((const void*)gru_persist_fwd_kernel, pl.G * pl.C, pl.smem, &p, st, "gru_persist_fwd");
 }
 
@@ -386,7 +404,7 @@ int gru_persist_bwd(const GruSeq& s, const GruSeqGrad& g, cudaStream_t st) {
   p.dgh = g.dgh; p.dgh_ts = g.dgh_ts; p.dgh_ld = g.dgh_ld;
   p.xch = g.xch;
   p.counters = s.sync;
-  PVCR_TRY(fill_zero(s.sync, sizeof(unsigned) * pl.G, st));
+  PVCR_TRY(fill_zero(s.sync, sizeof(unsigned) * 32 * pl.G, st));
   return coop_launch((const void*)gru_persist_bwd_kernel, pl.G * pl.C, pl.smem, &p, st, "gru_persist_bwd");
 }
 

@@ -117,4 +117,58 @@ int gru_persist_fwd(const GruSeq& s, cudaStream_t st);
 int gru_persist_bwd(const GruSeq& s, const GruSeqGrad& g, cudaStream_t st);
 int gru_seq_bwd(const GruSeq& s, const GruSeqGrad& g, cudaStream_t st);
 
+// ---- persistent attention decoder (dec_persist.cu) ---------------------------------------------------------
+struct DecPersistFwd {
+  int L, B, N, H, C, u, bsp;                // bsp = videos per group rounded up to 16 (MMA N)
+  const bf16* w1; long long w1_ld;          // [4H, ld]: rows [0,H) = W_q, [H,4H) = W_hh
+  const bf16* w3; long long w3_ld;          // [3H, ld]: W_c = W_ih[:, :H]
+  const float* b_hh;
+  const float* v;                           // [H]
+  const float* pk;                          // [B,N,H] fp32
+  const bf16* enc_a; long long enc_ld;      // rows b*N + n
+  const float* enc;                         // [B,N,H] fp32 (initial state = frame N-1)
+  const float* ep;                          // [B,L,3H] hoisted embedding projection (+ b_ih)
+  float* q_all; long long q_ld;             // step i: q_all + i*B*q_ld, rows b
+  bf16* ctx_x;                              // [L][B][H]
+  float* ctx_all;                           // rows b*L + i, H
+  float* alpha;                             // [L][B][N]
+  float* hs;                                // [B,L,H]
+  bf16* hs_a; long long hs_a_ld;            // rows b*L + i
+  float *r, *z, *n, *ghn;                   // [L][B,H]
+  unsigned* counters;
+};
+struct DecPersistBwd {
+  int L, B, N, H, C, u, bsp;
+  const bf16* wcT; long long wcT_ld;        // [H, ld]: element (j, k) = W_c[k, j],            k in [0, 3H)
+  const bf16* wcatT; long long wcatT_ld;    // [H, ld]: element (j, k) = [W_q; W_hh][k, j],    k in [0, 4H)
+  const float* v;                           // [H]
+  const float* pk;                          // [B,N,H]
+  const bf16* enc_a; long long enc_ld;
+  const float* enc;                         // [B,N,H] (h_prev of step 0 = frame N-1)
+  const float* hs;                          // [B,L,H] forward states
+  const float* d_hs;                        // [B,L,H] incoming gradient
+  const float* q_all; long long q_ld;       // saved q (step i: q_all + i*B*q_ld)
+  const float* alpha;                       // [L][B][N]
+  const float *r, *z, *n, *ghn;             // [L][B,H]
+  float* dgi_all;                           // rows b*L + i, 3H   (d gi = d(ctx W_c^T + ep))
+  float* d1_all;                            // rows b*L + i, 4H   ([dq | d gh])
+  float* dctx_all;                          // [L][B][H]
+  float* ds_all;                            // [L][B][N] d(score)
+  float* dh_carry;                          // [B,H] out: gradient on the initial state (encoder final)
+  bf16* xg;                                 // exchange [2][B][5H]: [dq | drp | dzp | dghn | dnp]
+  unsigned* counters;
+};
+// dpk / denc / dv from the per-step quantities saved by the backward sweep (hoisted out of the time loop)
+struct AttnGradArgs {
+  int L, B, N, H;
+  const float *alpha, *ds, *dctx;           // [L][B][N], [L][B][N], [L][B][H]
+  const float* q; long long q_ld;           // step i: q + i*B*q_ld
+  const float *pk, *v;
+  float *dpk, *denc, *dv_part;              // [B,N,H], [B,N,H], [B,H]  (all overwritten)
+};
+int attn_grad_hoisted(const AttnGradArgs& a, cudaStream_t st);
+int dec_persist_bwd(const DecPersistBwd& p, cudaStream_t st);
+bool dec_persist_eligible(int B, int N, int H, int nsplit, int Hp);
+int dec_persist_fwd(const DecPersistFwd& p, cudaStream_t st);
+
 }  // namespace pvcr

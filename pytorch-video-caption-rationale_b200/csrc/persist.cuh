@@ -15,9 +15,18 @@
 
 namespace pvcr {
 
-constexpr int PERSIST_THREADS = 128;
+constexpr int PERSIST_THREADS = 256;
+
+// Optional in-kernel phase timing (tuning aid): when non-null, CTA 0 / thread 0 of a persistent kernel stores
+// clock64() at up to PHASE_SLOTS points of every step into this device buffer ([step][slot]).
+constexpr int PHASE_SLOTS = 8;
+long long* debug_phase_buffer();       // null unless pvcr_debug_phase_timing(1) was called
 
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void phase_stamp(long long* dbg, int step, int slot) {
+  if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[step * PHASE_SLOTS + slot] = clock64();
+}
 
 // Byte offset of element (row, k) inside a K-major SWIZZLE_128B operand whose 64-column k-blocks hold
 // `rows_alloc` rows each (rows at 128 B pitch; 16-byte chunk index XORed with row & 7), for k % 8 == 0.
@@ -31,12 +40,29 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int k, int rows_alloc)
 __device__ __forceinline__ void load_operand_rows(uint8_t* dst, int rows_alloc, int lrow0, const bf16* src,
                                                   long long ld, long long row0, int nrows, long long row_limit,
                                                   int K) {
-  const int chunks = K >> 3;
-  for (int i = threadIdx.x; i < nrows * chunks; i += blockDim.x) {
-    const int lr = i / chunks, ch = i - lr * chunks;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (row0 + lr < row_limit) v = __ldcg(reinterpret_cast<const uint4*>(src + (row0 + lr) * ld + ch * 8));
-    *reinterpret_cast<uint4*>(dst + sw128_offset(lrow0 + lr, ch * 8, rows_alloc)) = v;
+  const int chunks = K >> 3, total = nrows * chunks, step = blockDim.x;
+  // (row, chunk) of element i = threadIdx.x + j*step advanced incrementally: no divisions inside the loops.
+  const int dlr = step / chunks, dch = step - dlr * chunks;
+  int lr = threadIdx.x / chunks, ch = threadIdx.x - lr * chunks;
+  // batches of 8 independent 16-byte loads per thread: one L2 round trip per batch instead of one per chunk
+  for (int base = threadIdx.x; base < total; base += 8 * step) {
+    uint4 v[8];
+    int lr_j = lr, ch_j = ch;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (base + j * step < total && row0 + lr_j < row_limit)
+        v[j] = __ldcg(reinterpret_cast<const uint4*>(src + (row0 + lr_j) * ld + ch_j * 8));
+      lr_j += dlr; ch_j += dch;
+      if (ch_j >= chunks) { ch_j -= chunks; ++lr_j; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (base + j * step < total)
+        *reinterpret_cast<uint4*>(dst + sw128_offset(lrow0 + lr, ch * 8, rows_alloc)) = v[j];
+      lr += dlr; ch += dch;
+      if (ch >= chunks) { ch -= chunks; ++lr; }
+    }
   }
 }
 
@@ -63,9 +89,8 @@ __device__ __forceinline__ void group_wait(const unsigned* ctr, unsigned target)
         if (clock64() - t0 > 4000000000LL) __trap();
       }
     }
-    __threadfence();
   }
-  __syncthreads();
+  __syncthreads();      // orders every thread's later loads after thread 0's acquire
 }
 
 // D[128 x N] (TMEM, fp32) = A[128 x K] * B[N x K]^T, both SW128 K-major in shared memory; issued by one thread.
@@ -81,6 +106,20 @@ __device__ __forceinline__ void issue_swapped_mma(uint32_t tmem_d, uint32_t a_ba
   umma_commit(done_bar);
 }
 
+// Same product over one K-chunk, without the commit: A k-blocks [a_kb0, a_kb0 + Kc/64), B k-blocks [0, Kc/64).
+__device__ __forceinline__ void issue_mma_chunk(uint32_t tmem_d, uint32_t a_base, int a_rows_alloc, int a_kb0,
+                                                uint32_t b_base, int b_rows_alloc, int Kc, uint32_t idesc,
+                                                bool accumulate) {
+  const int KB = Kc >> 6;
+  for (int kb = 0; kb < KB; ++kb) {
+    const uint64_t da = umma_desc_k128(a_base + (uint32_t)(a_kb0 + kb) * (uint32_t)a_rows_alloc * 128u);
+    const uint64_t db = umma_desc_k128(b_base + (uint32_t)kb * (uint32_t)b_rows_alloc * 128u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, accumulate || (kb | k) != 0);
+  }
+}
+
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
@@ -94,7 +133,7 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
 }
 
 // Move the accumulator D[row = TMEM lane, col < ncols] to shared memory as S[col * s_ld + row] for rows < nrows.
-// Executed by all 128 threads (thread == lane).  ncols is a multiple of 16.
+// Executed by warps 0..3 (thread == lane).  ncols is a multiple of 16.
 __device__ __forceinline__ void tmem_to_smem_cols(uint32_t tmem_base, float* S, int s_ld, int nrows, int ncols) {
   const int warp = threadIdx.x >> 5, row = threadIdx.x;
   float v[16];

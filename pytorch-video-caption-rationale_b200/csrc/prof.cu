@@ -4,6 +4,7 @@
 
 #include "../../include/pvcr_b200.h"
 #include "common.cuh"
+#include "persist.cuh"
 
 namespace pvcr {
 
@@ -39,6 +40,11 @@ LaunchScope::~LaunchScope() {
   if (i < g_pending.size()) cudaEventRecord(g_pending[i].b, st);
 }
 
+static long long* g_phase_buf = nullptr;
+static bool g_phase_on = false;
+constexpr int PHASE_STEPS = 256;
+long long* debug_phase_buffer() { return g_phase_on ? g_phase_buf : nullptr; }
+
 }  // namespace pvcr
 
 using namespace pvcr;
@@ -67,6 +73,23 @@ int pvcr_prof_read(uint64_t* launches, double* ms, double* work) {
     if (cudaEventElapsedTime(&t, e.a, e.b) != cudaSuccess) return PVCR_ERR_CUDA;
     ms[e.cls] += t;
   }
+  return PVCR_OK;
+}
+
+// Tuning aid: in-kernel phase timestamps of the persistent kernels (CTA 0).  enable allocates a small device
+// buffer; read copies [steps][8] clock64 stamps of the LAST persistent launch to the host (synchronises).
+int pvcr_debug_phase_timing(int on) {
+  if (on && !g_phase_buf) {
+    if (cudaMalloc(&g_phase_buf, sizeof(long long) * PHASE_STEPS * PHASE_SLOTS) != cudaSuccess) return PVCR_ERR_CUDA;
+  }
+  g_phase_on = on != 0;
+  return PVCR_OK;
+}
+int pvcr_debug_phase_read(long long* out, int steps) {
+  if (!g_phase_buf || steps > PHASE_STEPS) return PVCR_ERR_ARG;
+  if (cudaDeviceSynchronize() != cudaSuccess) return PVCR_ERR_CUDA;
+  if (cudaMemcpy(out, g_phase_buf, sizeof(long long) * steps * PHASE_SLOTS, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return PVCR_ERR_CUDA;
   return PVCR_OK;
 }
 

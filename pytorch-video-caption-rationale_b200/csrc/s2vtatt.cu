@@ -25,6 +25,9 @@ struct AttWs {
       *demb_rows, *dxsel;
   unsigned* sync;
   bf16* xch;
+  bf16* ctx_x;
+  float *dctx_all, *ds_all;
+  bf16* xg;
 };
 
 static size_t scratch_need(const PvcrDims& d, int need_frame_grad) {
@@ -98,8 +101,12 @@ static void carve(Arena& a, const PvcrDims& d, int need_frame_grad, AttWs& w) {
   w.hprev_enc = a.alloc<float>(BN * H);
   w.demb_rows = a.alloc<float>(BL * E);
   w.dxsel = need_frame_grad ? a.alloc<float>(BN * V) : nullptr;
-  w.sync = a.alloc<unsigned>(256);
+  w.sync = a.alloc<unsigned>(32 * 160);
+  w.dctx_all = a.alloc<float>(BL * H);
+  w.ds_all = a.alloc<float>(BL * N);
+  w.xg = a.alloc<bf16>((size_t)2 * B * 5 * H);
   w.xch = a.alloc<bf16>((size_t)2 * B * 4 * H);
+  w.ctx_x = a.alloc<bf16>(BL * H);
 }
 
 size_t s2vtatt_workspace(const PvcrDims& d, int need_frame_grad) {
@@ -165,7 +172,17 @@ int s2vtatt_fwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   PVCR_TRY(gather_split(p.emb, E, s_in, BL, w.emb_a.ptr, w.emb_a.ld, w.emb_a.Kp, d.nsplit, NO_DROPOUT, st));
   PVCR_TRY(gemm_planes(w.emb_a.view(), w.we.view(), BL, H3, (int)w.emb_a.ld, w.ep, H3, p.dec_b_ih, 0, st));
 
-  // decoder steps
+  // decoder steps: one persistent cooperative kernel when the shape allows, else per-step launches
+  if (dec_persist_eligible(B, N, H, d.nsplit, w.enc_a.Kp)) {
+    DecPersistFwd q{};
+    q.L = L; q.B = B; q.N = N; q.H = H;
+    q.w1 = w.wcat.ptr; q.w1_ld = w.wcat.ld; q.w3 = w.wc.ptr; q.w3_ld = w.wc.ld;
+    q.b_hh = p.dec_b_hh; q.v = p.att_v; q.pk = w.pk; q.enc_a = w.enc_a.ptr; q.enc_ld = w.enc_a.ld; q.enc = w.enc;
+    q.ep = w.ep; q.q_all = w.g1_all; q.q_ld = H4; q.ctx_x = w.ctx_x; q.ctx_all = w.ctx_all; q.alpha = w.alpha_all;
+    q.hs = hs; q.hs_a = w.hs_a.ptr; q.hs_a_ld = w.hs_a.ld;
+    q.r = w.dr; q.z = w.dz; q.n = w.dn; q.ghn = w.dghn; q.counters = w.sync;
+    PVCR_TRY(dec_persist_fwd(q, st));
+  } else
   for (int i = 0; i < L; ++i) {
     OperandView hprev_a = (i == 0)
         ? OperandView{w.enc_a.ptr + (long long)(N - 1) * w.enc_a.ld, (long long)N * w.enc_a.ld, 0, B, 1}
@@ -223,6 +240,23 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   PVCR_TRY(prep_weight_T(p.enc_w_hh, H, H3, H, w.whh_encT, 0, 1, st));
   if (need_frame_grad) PVCR_TRY(prep_weight_T(p.enc_w_ih, V, H3, V, w.wih_encT, 0, 1, st));
 
+  const bool persist_dec = dec_persist_eligible(B, N, H, ns, w.enc_a.Kp);
+  if (persist_dec) {
+    DecPersistBwd q{};
+    q.L = L; q.B = B; q.N = N; q.H = H;
+    q.wcT = w.wcT.ptr; q.wcT_ld = w.wcT.ld; q.wcatT = w.wcatT.ptr; q.wcatT_ld = w.wcatT.ld;
+    q.v = p.att_v; q.pk = w.pk; q.enc_a = w.enc_a.ptr; q.enc_ld = w.enc_a.ld; q.enc = w.enc; q.hs = hs; q.d_hs = d_hs;
+    q.q_all = w.g1_all; q.q_ld = H4; q.alpha = w.alpha_all;
+    q.r = w.dr; q.z = w.dz; q.n = w.dn; q.ghn = w.dghn;
+    q.dgi_all = w.dgi_all; q.d1_all = w.d1_all; q.dctx_all = w.dctx_all; q.ds_all = w.ds_all;
+    q.dh_carry = w.dh_carry; q.xg = w.xg; q.counters = w.sync;
+    PVCR_TRY(dec_persist_bwd(q, st));
+    AttnGradArgs ag{};
+    ag.L = L; ag.B = B; ag.N = N; ag.H = H;
+    ag.alpha = w.alpha_all; ag.ds = w.ds_all; ag.dctx = w.dctx_all; ag.q = w.g1_all; ag.q_ld = H4;
+    ag.pk = w.pk; ag.v = p.att_v; ag.dpk = w.dpk; ag.denc = w.denc; ag.dv_part = w.dv_part;
+    PVCR_TRY(attn_grad_hoisted(ag, st));
+  } else {
   PVCR_TRY(fill_zero(w.dh_carry, sizeof(float) * (size_t)B * H, st));
   PVCR_TRY(fill_zero(w.dpk, sizeof(float) * (size_t)BN * H, st));
   PVCR_TRY(fill_zero(w.denc, sizeof(float) * (size_t)BN * H, st));
@@ -232,7 +266,6 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
     PVCR_TRY(fill_zero(w.dgi_a.ptr, sizeof(bf16) * (size_t)B * w.dgi_a.ld, st));
     PVCR_TRY(fill_zero(w.dgh_a.ptr, sizeof(bf16) * (size_t)B * w.dgh_a.ld, st));
   }
-
   // ---- decoder, reverse time ----
   for (int i = L - 1; i >= 0; --i) {
     GruBwdArgs b{};
@@ -263,6 +296,7 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
     PVCR_TRY(attn_bwd(at, st));
     // dh_{i-1} = dh*z + [dq | dgh] [Wq ; Whh]
     PVCR_TRY(gemm_planes(w.d1_a.view(), w.wcatT.view(), B, H, (int)w.d1_a.ld, w.dh_carry, H, nullptr, 1, st));
+  }
   }
 
   // ---- decoder weight gradients, hoisted over all (b, i) rows ----

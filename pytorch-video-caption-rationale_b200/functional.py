@@ -44,6 +44,13 @@ def _fill_struct(struct, fields, tensors):
     return struct
 
 
+class ManualCtx:
+    """Stand-in for the autograd context when the Functions below are chained by hand (tape-free train step)."""
+
+    def mark_non_differentiable(self, *a):
+        pass
+
+
 ATT_SEQ_FIELDS = [f for f in ATT_PARAM_FIELDS if f not in ("out_w", "out_b")]
 
 

@@ -1,0 +1,34 @@
+"""CUDA-graph capture of a whole training step (forward + backward) of a drop-in module.
+
+Every kernel of the library is stream-ordered and allocation-free (include/pvcr_b200.h), so one fwd+bwd step is
+captured once and replayed with a single graph launch: host launch latency and jitter leave the critical path.
+The step is the module's tape-free ``train_step_grads`` (no autograd state inside the capture).  Inputs are copied
+into static device buffers (directly from pinned host memory when given CPU tensors); the gradients appear in
+``param.grad`` (static buffers rewritten by every replay), ready for the all-reduce / optimizer.
+"""
+import torch
+
+
+class GraphedTrainStep:
+    def __init__(self, model, example_inputs, warmup=3):
+        """example_inputs: tuple of CUDA tensors, the arguments of model.train_step_grads (fixes shapes/dtypes)."""
+        self.model = model
+        self.static_in = tuple(t.clone() for t in example_inputs)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                model.train_step_grads(*self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            out = model.train_step_grads(*self.static_in)
+        self.static_out = tuple(o.detach() if torch.is_tensor(o) else o for o in out)
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.static_in, inputs):
+            if src is not dst:
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.static_out

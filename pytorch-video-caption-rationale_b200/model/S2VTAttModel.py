@@ -107,6 +107,29 @@ class S2VTAttModel(nn.Module):
         return loss, stats[0] / stats[1], pred
 
     @torch.no_grad()
+    def train_step_grads(self, vid_feats, s, s_len, frame_scale=None):
+        """Tape-free fwd+bwd of run_iter (train.py:37-40 + loss.backward()): chains the C-ABI forward and backward
+        entry points by hand and (over)writes ``param.grad`` of every parameter.  Stream-ordered and free of autograd
+        state, hence capturable in a CUDA graph (pvcr_b200.graphs.GraphedTrainStep).  Returns (loss, acc, pred)."""
+        assert self.training and s is not None
+        cfg = self._cfg(True)
+        params = self._seq_params()
+        lin = self.decoder.pred_linear[1]
+        c1, c2 = F_.ManualCtx(), F_.ManualCtx()
+        hs, alphas = F_.S2VTAttSequence.forward(c1, cfg, vid_feats, frame_scale, self._shifted(s, vid_feats.shape[0]),
+                                                *params)
+        self.last_alphas = alphas
+        loss, stats, pred = F_.VocabCrossEntropy.forward(c2, cfg, hs, lin.weight, lin.bias, s, s_len)
+        one = torch.ones((), dtype=torch.float32, device=hs.device)
+        _, d_hs, d_w, d_b, _, _ = F_.VocabCrossEntropy.backward(c2, one, None, None)
+        grads = F_.S2VTAttSequence.backward(c1, d_hs, None)
+        for p, g in zip(params, grads[4:]):
+            p.grad = g
+        lin.weight.grad, lin.bias.grad = d_w, d_b
+        self.last_frame_scale_grad = grads[2]
+        return loss, stats[0] / stats[1], pred
+
+    @torch.no_grad()
     def greedy(self, vid_feats, frame_scale=None):
         """Fixed-length greedy decoding (eval branch, model/S2VTAttModel.py:172-191): -> (ids [B,L], logits [B,L,Vc])."""
         d = self.decoder

@@ -1,0 +1,37 @@
+"""Tuning aid: per-phase clock64 breakdown of the persistent GRU forward kernel (CTA 0), cfg2 encoder shape."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import pvcr_b200
+from pvcr_b200 import _lib
+from pvcr_b200.model import S2VTAttModel
+from tests.gpu_util import FixtureGlove
+
+B, N, V, H, E, L, Vc = 128, 40, 2048, 512, 300, 30, 23000
+m = S2VTAttModel(FixtureGlove(Vc, E), 0.0, H, V, L).cuda().train()
+vid = torch.randn(B, N, V, device="cuda"); s = torch.randint(0, Vc - 4, (B, L), device="cuda")
+s_len = torch.randint(1, L + 1, (B,), device="cuda")
+Lb = _lib.lib()
+os.environ.setdefault("X", "1")
+for _ in range(3): m.train_step_grads(vid, s, s_len)
+torch.cuda.synchronize()
+Lb.pvcr_debug_phase_timing(1)
+which = sys.argv[1] if len(sys.argv) > 1 else "enc_fwd"
+# the debug buffer is overwritten by every persistent launch that stamps: run only the forward sequence
+from pvcr_b200 import functional as F_
+with torch.no_grad():
+    F_.S2VTAttSequence.forward(F_.ManualCtx(), m._cfg(True), vid, None, m._shifted(s, B), *m._seq_params())
+steps = N
+buf = (ctypes.c_longlong * (steps * 8))()
+_lib.check(Lb.pvcr_debug_phase_read(buf, steps), "read")
+a = np.array(buf[:]).reshape(steps, 8)
+a2 = a[:, [0, 1, 7, 2, 3, 4, 5, 6]]
+d = np.diff(a2, axis=1)[5:]           # skip the first steps
+names = ["wait", "load X (ld+st)", "fence+sync", "mma", "tmem->smem", "gates+stores", "arrive"]
+clk = 1.965e3  # cycles per us at max clock
+print("per-step cycles (median over steps 5..):")
+for i, n in enumerate(names):
+    print("  %-14s %8.0f cyc  %.2f us" % (n, np.median(d[:, i]), np.median(d[:, i]) / clk))
+tot = np.median(a[6:, 6] - a[5:-1, 6])
+print("  step total     %8.0f cyc  %.2f us" % (tot, tot / clk))

@@ -29,4 +29,13 @@ t0 = time.time(); e0.record()
 for _ in range(10): step()
 e1.record(); torch.cuda.synchronize()
 print("%s: %.3f ms/iter (device), %.3f ms/iter (wall) -> %.0f videos/s" % (prec, e0.elapsed_time(e1) / 10, (time.time() - t0) * 100, B / (e0.elapsed_time(e1) / 10) * 1e3))
+from pvcr_b200.graphs import GraphedTrainStep
+gs = GraphedTrainStep(m, (vid, s, s_len))
+for _ in range(3): out = gs(vid, s, s_len)
+torch.cuda.synchronize()
+print("graphed loss", out[0].item())
+t0 = time.time(); e0.record()
+for _ in range(10): gs(vid, s, s_len)
+e1.record(); torch.cuda.synchronize()
+print("%s graphed: %.3f ms/iter (device), %.3f ms/iter (wall) -> %.0f videos/s" % (prec, e0.elapsed_time(e1) / 10, (time.time() - t0) * 100, B / (e0.elapsed_time(e1) / 10) * 1e3))
 print("max mem MB", torch.cuda.max_memory_allocated() / 1e6)
