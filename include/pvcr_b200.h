@@ -105,6 +105,38 @@ int pvcr_s2vtatt_bwd(const PvcrDims* d, const PvcrS2vtAttParams* p, const float*
                      const int64_t* s_in, const float* hs, const float* d_hs, PvcrS2vtAttGrads* g,
                      float* d_frame_scale, void* workspace, size_t workspace_bytes, void* stream);
 
+/* S2VTModel parameters (reference state_dict names, model/S2VTModel.py:36-49). */
+typedef struct {
+  const float* emb;       /* embedding.0.weight   [Vc, E]   */
+  const float* rnn1_w_ih; /* rnn1.weight_ih_l0    [3H, V]   */
+  const float* rnn1_w_hh; /* rnn1.weight_hh_l0    [3H, H]   */
+  const float* rnn1_b_ih; /* rnn1.bias_ih_l0      [3H]      */
+  const float* rnn1_b_hh; /* rnn1.bias_hh_l0      [3H]      */
+  const float* rnn2_w_ih; /* rnn2.weight_ih_l0    [3H, H+E] */
+  const float* rnn2_w_hh; /* rnn2.weight_hh_l0    [3H, H]   */
+  const float* rnn2_b_ih; /* rnn2.bias_ih_l0      [3H]      */
+  const float* rnn2_b_hh; /* rnn2.bias_hh_l0      [3H]      */
+  const float* out_w;     /* linear.1.weight      [Vc, H]   */
+  const float* out_b;     /* linear.1.bias        [Vc]      */
+} PvcrS2vtParams;
+typedef struct {
+  float *emb, *rnn1_w_ih, *rnn1_w_hh, *rnn1_b_ih, *rnn1_b_hh, *rnn2_w_ih, *rnn2_w_hh, *rnn2_b_ih, *rnn2_b_hh, *out_w,
+      *out_b;
+} PvcrS2vtGrads;
+
+/* S2VTModel.forward with the fed-back words given (model/S2VTModel.py:74-145): encode with rnn1/rnn2, then L
+ * decoding steps whose input words are s_in [B,L] (teacher forcing: [<sos>, s[:, :L-1]]; with scheduled sampling
+ * the caller first obtains the sampled words from pvcr_s2vt_decode_steps).  hs [B,L,H] = rnn2 decoding states
+ * (the input of the vocabulary projection).  dims.dropout_p / seed drive the Dropout on the embedded words
+ * (embedding.1).  _bwd: given d_hs, writes every gradient in g except out_w / out_b, and d_frame_scale [B,N] if
+ * non-NULL.  The workspace carries the activations from _fwd to _bwd. */
+size_t pvcr_s2vt_workspace(const PvcrDims* d, int need_frame_grad);
+int pvcr_s2vt_fwd(const PvcrDims* d, const PvcrS2vtParams* p, const float* vid_feats, const float* frame_scale,
+                  const int64_t* s_in, float* hs, void* workspace, size_t workspace_bytes, void* stream);
+int pvcr_s2vt_bwd(const PvcrDims* d, const PvcrS2vtParams* p, const float* vid_feats, const float* frame_scale,
+                  const int64_t* s_in, float* hs, const float* d_hs, PvcrS2vtGrads* g, float* d_frame_scale,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
 /* Vocabulary projection fused with the loss contract:  logits = Dropout(hs) out_w^T + out_b
  * (model/S2VTAttModel.py:145, model/S2VTModel.py:130), then calc_masked_loss / calc_masked_accuracy /
  * argmax (train_utils.py:37-71, train.py:38).

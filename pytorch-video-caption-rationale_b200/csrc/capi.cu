@@ -14,6 +14,11 @@ int s2vtatt_fwd(const PvcrDims&, const PvcrS2vtAttParams&, const float*, const f
                 void*, size_t, cudaStream_t);
 int s2vtatt_bwd(const PvcrDims&, const PvcrS2vtAttParams&, const float*, const float*, const long long*, const float*,
                 const float*, PvcrS2vtAttGrads&, float*, void*, size_t, cudaStream_t);
+size_t s2vt_workspace(const PvcrDims& d, int need_frame_grad);
+int s2vt_fwd(const PvcrDims&, const PvcrS2vtParams&, const float*, const float*, const long long*, float*, void*, size_t,
+             cudaStream_t);
+int s2vt_bwd(const PvcrDims&, const PvcrS2vtParams&, const float*, const float*, const long long*, const float*, float*,
+             PvcrS2vtGrads&, float*, void*, size_t, cudaStream_t);
 size_t vocab_ce_workspace(int B, int L, int H, int Vc, int nsplit, float dropout_p);
 int vocab_ce_fwd(const float*, const float*, const float*, const long long*, const long long*, int, int, int, int, int,
                  float, unsigned long long, float*, long long*, float*, float*, long long, void*, size_t, cudaStream_t);
@@ -55,6 +60,18 @@ int pvcr_s2vtatt_bwd(const PvcrDims* d, const PvcrS2vtAttParams* p, const float*
                      float* d_frame_scale, void* workspace, size_t workspace_bytes, void* stream) {
   return s2vtatt_bwd(*d, *p, vid_feats, frame_scale, (const long long*)s_in, d_hs, hs, *g, d_frame_scale, workspace,
                      workspace_bytes, (cudaStream_t)stream);
+}
+size_t pvcr_s2vt_workspace(const PvcrDims* d, int need_frame_grad) { return s2vt_workspace(*d, need_frame_grad); }
+int pvcr_s2vt_fwd(const PvcrDims* d, const PvcrS2vtParams* p, const float* vid_feats, const float* frame_scale,
+                  const int64_t* s_in, float* hs, void* workspace, size_t workspace_bytes, void* stream) {
+  return s2vt_fwd(*d, *p, vid_feats, frame_scale, (const long long*)s_in, hs, workspace, workspace_bytes,
+                  (cudaStream_t)stream);
+}
+int pvcr_s2vt_bwd(const PvcrDims* d, const PvcrS2vtParams* p, const float* vid_feats, const float* frame_scale,
+                  const int64_t* s_in, float* hs, const float* d_hs, PvcrS2vtGrads* g, float* d_frame_scale,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+  return s2vt_bwd(*d, *p, vid_feats, frame_scale, (const long long*)s_in, d_hs, hs, *g, d_frame_scale, workspace,
+                  workspace_bytes, (cudaStream_t)stream);
 }
 size_t pvcr_vocab_ce_workspace(int B, int L, int H, int Vc, int nsplit, float dropout_p) {
   return vocab_ce_workspace(B, L, H, Vc, nsplit, dropout_p);

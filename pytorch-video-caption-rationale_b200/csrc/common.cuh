@@ -44,7 +44,8 @@ void set_last_error(const char* fmt, ...);
 // ---- launch accounting (pvcr_prof_* in include/pvcr_b200.h) ---------------------------------------
 // Every kernel launcher opens a LaunchScope: it counts the launch per kernel class and, when timing is
 // enabled (bench.py's roofline leg), brackets it with a CUDA-event pair on the launching stream.
-enum KernelClass { KC_GEMM = 0, KC_STAGE, KC_GATE, KC_ATTN, KC_LOSS, KC_RECURRENT, KC_MISC, KC_COUNT };
+enum KernelClass { KC_GEMM = 0, KC_STAGE, KC_GATE, KC_ATTN, KC_LOSS, KC_GRU_FWD, KC_GRU_BWD, KC_DEC_FWD, KC_DEC_BWD, KC_MISC,
+                   KC_COUNT };
 struct LaunchScope {
   int cls; cudaStream_t st; void* rec;
   LaunchScope(int cls, cudaStream_t st, double work = 0.0);

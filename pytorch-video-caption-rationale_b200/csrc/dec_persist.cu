@@ -674,7 +674,7 @@ int dec_persist_fwd(const DecPersistFwd& p0, cudaStream_t st) {
   PVCR_REQUIRE(per_sm * dec_num_sms() >= grid, "dec_persist_fwd: %d CTAs cannot be co-resident", grid);
   PVCR_TRY(fill_zero(p.counters, sizeof(unsigned) * 32 * pl.G, st));
   void* args[] = {&p};
-  LaunchScope ls_(KC_RECURRENT, st);
+  LaunchScope ls_(KC_DEC_FWD, st);
   PVCR_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(DEC_THREADS), args, pl.smem, st));
   return PVCR_OK;
 }
@@ -698,7 +698,7 @@ int dec_persist_bwd(const DecPersistBwd& p0, cudaStream_t st) {
   PVCR_REQUIRE(per_sm * dec_num_sms() >= grid, "dec_persist_bwd: %d CTAs cannot be co-resident", grid);
   PVCR_TRY(fill_zero(p.counters, sizeof(unsigned) * 32 * pl.G, st));
   void* args[] = {&p};
-  LaunchScope ls_(KC_RECURRENT, st);
+  LaunchScope ls_(KC_DEC_BWD, st);
   PVCR_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(DEC_THREADS), args, smem, st));
   return PVCR_OK;
 }

@@ -90,7 +90,7 @@ int cast_split(const float* in, long long ld_in, int R, int C, bf16* out, long l
 __global__ void transpose_split_kernel(const float* __restrict__ in, long long ld_in, int R, int C,
                                        bf16* __restrict__ out, long long ld_out, int Rp, int r_off, int r_end,
                                        int nsplit, int role_b, const long long* __restrict__ row_ids,
-                                       const float* __restrict__ row_scale) {
+                                       const float* __restrict__ row_scale, Dropout drop) {
   __shared__ float tile[32][33];
   const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -99,7 +99,8 @@ __global__ void transpose_split_kernel(const float* __restrict__ in, long long l
     if (r < R && c < C) {
       const long long src_row = row_ids ? row_ids[r] : r;
       v = __ldg(in + src_row * ld_in + c);
-      if (row_scale) v *= __ldg(row_scale + r);
+      if (row_scale) v *= __ldg(row_scale + src_row);
+      if (drop.p > 0.f) v *= dropout_scale(drop, (unsigned long long)r * C + c);
     }
     tile[i][threadIdx.x] = v;
   }
@@ -112,7 +113,7 @@ __global__ void transpose_split_kernel(const float* __restrict__ in, long long l
 
 int transpose_split(const float* in, long long ld_in, int R, int C, bf16* out, long long ld_out, int Rp, int r_off,
                     int zero_pad, int nsplit, int role_b, const long long* row_ids, const float* row_scale,
-                    cudaStream_t st) {
+                    cudaStream_t st, Dropout drop) {
   PVCR_REQUIRE(r_off + R <= Rp, "transpose_split: r_off=%d R=%d exceed Rp=%d", r_off, R, Rp);
   if (C == 0) return PVCR_OK;
   const int r_end = zero_pad ? Rp - r_off : R;       // rows >= R read as zero
@@ -120,7 +121,7 @@ int transpose_split(const float* in, long long ld_in, int R, int C, bf16* out, l
   dim3 grid(cdiv(r_end, 32), cdiv(C, 32));
   { LaunchScope ls_(KC_STAGE, st);
   transpose_split_kernel<<<grid, dim3(32, 8), 0, st>>>(in, ld_in, R, C, out, ld_out, Rp, r_off, r_end, nsplit, role_b,
-                                                       row_ids, row_scale);
+                                                       row_ids, row_scale, drop);
   }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
@@ -231,7 +232,7 @@ __global__ void gru_gate_fwd_kernel(GruFwdArgs a) {
   float gi[3], gh[3];
 #pragma unroll
   for (int g = 0; g < 3; ++g) {
-    float x = a.gi_a[(long long)b * a.gi_a_ld + g * H + j];
+    float x = a.gi_a ? a.gi_a[(long long)b * a.gi_a_ld + g * H + j] : 0.f;
     if (a.gi_b) x += a.gi_b[(long long)b * a.gi_b_ld + g * H + j];
     if (a.gi_bias) x += a.gi_bias[g * H + j];
     gi[g] = x;

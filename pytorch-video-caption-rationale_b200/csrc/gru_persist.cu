@@ -103,8 +103,10 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_fwd_kernel(con
         const int idx = tid + k * PERSIST_THREADS, jj = idx % u, lb = idx / u;
         const int j = j0 + jj, b = b0 + lb;
         if (!DBG_NO_GI_PREFETCH && lb < bs && b < p.B) {
-          const float* gp = p.gi + (long long)t * p.gi_ts + (long long)b * p.gi_ld;
-          gir[k] = __ldg(gp + j); giz[k] = __ldg(gp + H + j); gin[k] = __ldg(gp + 2 * H + j);
+          if (p.gi) {
+            const float* gp = p.gi + (long long)t * p.gi_ts + (long long)b * p.gi_ld;
+            gir[k] = __ldg(gp + j); giz[k] = __ldg(gp + H + j); gin[k] = __ldg(gp + 2 * H + j);
+          }
           if (p.gi_b && t >= p.gi_b_from) {
             const float* gq = p.gi_b + (long long)(t - p.gi_b_from) * p.gi_b_ts + (long long)b * p.gi_b_ld;
             gir[k] += __ldg(gq + j); giz[k] += __ldg(gq + H + j); gin[k] += __ldg(gq + 2 * H + j);
@@ -348,7 +350,8 @@ static bool plan_gru(int B, int H, int k_rows_fwd, PersistPlan& pl, bool backwar
   return pl.smem <= 227 * 1024;
 }
 
-static int coop_launch(const void* kern, int grid, size_t smem, void* param, cudaStream_t st, const char* what) {
+static int coop_launch(const void* kern, int grid, size_t smem, void* param, cudaStream_t st, const char* what,
+                       int cls) {
   static std::mutex mu;
   {
     std::lock_guard<std::mutex> g(mu);
@@ -358,7 +361,7 @@ static int coop_launch(const void* kern, int grid, size_t smem, void* param, cud
   PVCR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PERSIST_THREADS, smem));
   PVCR_REQUIRE(per_sm * num_sms() >= grid, "%s: %d CTAs cannot be co-resident (%d per SM)", what, grid, per_sm);
   void* args[] = {param};
-  LaunchScope ls_(KC_RECURRENT, st);
+  LaunchScope ls_(cls, st);
   PVCR_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(PERSIST_THREADS), args, smem, st));
   return PVCR_OK;
 }
@@ -386,7 +389,7 @@ int gru_persist_fwd(const GruSeq& s, cudaStream_t st) {
   p.counters = s.sync;
   p.dbg = debug_phase_buffer();
   PVCR_TRY(fill_zero(s.sync, sizeof(unsigned) * 32 * pl.G, st));
-  return coop_launch((const void*)gru_persist_fwd_kernel, pl.G * pl.C, pl.smem, &p, st, "gru_persist_fwd");
+  return coop_launch((const void*)gru_persist_fwd_kernel, pl.G * pl.C, pl.smem, &p, st, "gru_persist_fwd", KC_GRU_FWD);
 }
 
 int gru_persist_bwd(const GruSeq& s, const GruSeqGrad& g, cudaStream_t st) {
@@ -405,7 +408,7 @@ int gru_persist_bwd(const GruSeq& s, const GruSeqGrad& g, cudaStream_t st) {
   p.xch = g.xch;
   p.counters = s.sync;
   PVCR_TRY(fill_zero(s.sync, sizeof(unsigned) * 32 * pl.G, st));
-  return coop_launch((const void*)gru_persist_bwd_kernel, pl.G * pl.C, pl.smem, &p, st, "gru_persist_bwd");
+  return coop_launch((const void*)gru_persist_bwd_kernel, pl.G * pl.C, pl.smem, &p, st, "gru_persist_bwd", KC_GRU_BWD);
 }
 
 }  // namespace pvcr

@@ -56,13 +56,14 @@ inline int gemm_planes(const OperandView& a, const OperandView& b, int M, int N,
   return gemm_store(a, b, gc, 1, C, ldc, 0, bias, 0, accumulate, st);
 }
 
+static const Dropout NO_DROPOUT = {0.f, 0ull, 0ull};
+
 // fp32 [R,C] -> planes (role A or B), optional row scale / dropout
 inline int stage(const float* in, long long ld_in, int R, int C, const Planes& p, int role_b, const float* row_scale,
                  Dropout drop, cudaStream_t st, int row0 = 0) {
   return cast_split(in, ld_in, R, C, p.ptr + (long long)row0 * p.ld, p.ld, p.Kp, p.nsplit, role_b, row_scale, drop, st);
 }
 
-static const Dropout NO_DROPOUT = {0.f, 0ull, 0ull};
 
 // weight [N,K] fp32 -> B-role planes [N, P*Kp]
 inline int prep_weight(const float* w, long long ldw, int N, int K, const Planes& p, cudaStream_t st, int row0 = 0) {
@@ -71,13 +72,13 @@ inline int prep_weight(const float* w, long long ldw, int N, int K, const Planes
 // weight [N,K] fp32 -> transposed B-role planes [K, P*Np] occupying contraction columns n_off .. n_off+N-1
 inline int prep_weight_T(const float* w, long long ldw, int N, int K, const Planes& p, int n_off, int zero_pad,
                          cudaStream_t st) {
-  return transpose_split(w, ldw, N, K, p.ptr, p.ld, p.Kp, n_off, zero_pad, p.nsplit, 1, nullptr, nullptr, st);
+  return transpose_split(w, ldw, N, K, p.ptr, p.ld, p.Kp, n_off, zero_pad, p.nsplit, 1, nullptr, nullptr, st, NO_DROPOUT);
 }
 
 // dw[N,K] (+)= dy^T x over R rows.  Scratch planes come from `a` and are released on return.
 int grad_w(Arena& a, const float* dy, long long lddy, int R, int N, const float* x, long long ldx, int K,
            const long long* x_row_ids, const float* x_row_scale, float* dw, long long lddw, int accumulate,
-           int nsplit, cudaStream_t st);
+           int nsplit, cudaStream_t st, Dropout x_drop = NO_DROPOUT);
 // dx[R,K] (+)= dy wT^T where wT are the transposed B-role planes of w ([K, P*Np]).
 int grad_x(Arena& a, const float* dy, long long lddy, int R, int N, const Planes& wT, float* dx, long long lddx,
            int accumulate, cudaStream_t st);

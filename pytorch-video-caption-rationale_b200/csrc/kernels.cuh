@@ -20,7 +20,7 @@ int cast_split(const float* in, long long ld_in, int R, int C, bf16* out, long l
 // src(r) = in + (row_ids ? row_ids[r] : r) * ld_in.  With zero_pad, columns r_off+R .. Rp-1 are zero-filled.
 int transpose_split(const float* in, long long ld_in, int R, int C, bf16* out, long long ld_out, int Rp, int r_off,
                     int zero_pad, int nsplit, int role_b, const long long* row_ids, const float* row_scale,
-                    cudaStream_t st);
+                    cudaStream_t st, Dropout drop);     // drop: element index r*C + c (as gather_split)
 // out[i][p*Ep + e] = term_{A,p}( table[ids[i]][e] * dropout )     (embedding rows as an A operand)
 int gather_split(const float* table, int E, const long long* ids, int n_ids, bf16* out, long long ld_out, int Ep,
                  int nsplit, Dropout drop, cudaStream_t st);
@@ -36,7 +36,7 @@ int fill_zero(void* p, size_t bytes, cudaStream_t st);
 // ---- GRU gate math ---------------------------------------------------------------------------------
 struct GruFwdArgs {
   int B, H;
-  const float* gi_a; long long gi_a_ld;     // [B,3H] required (includes b_ih)
+  const float* gi_a; long long gi_a_ld;     // [B,3H] (nullable: the step has no input, e.g. S2VT rnn1 while decoding)
   const float* gi_b; long long gi_b_ld;     // optional second addend
   const float* gi_bias;                     // optional [3H] bias addend
   const float* gh; long long gh_ld;         // [B,3H] W_hh h (no bias) or null (h_prev == 0)

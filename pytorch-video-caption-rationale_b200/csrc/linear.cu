@@ -48,12 +48,12 @@ int linear_bwd(const float* dy, long long lddy, const float* x, long long ldx, c
   if (a.failed) { set_last_error("linear_bwd: workspace too small (%zu < %zu)", ws_bytes, a.off); return PVCR_ERR_WORKSPACE; }
   if (dx) {
     PVCR_TRY(stage(dy, lddy, M, N, dya, 0, nullptr, NO_DROPOUT, st));
-    PVCR_TRY(transpose_split(w, ldw, N, K, wtb.ptr, wtb.ld, wtb.Kp, 0, 1, nsplit, 1, nullptr, nullptr, st));
+    PVCR_TRY(transpose_split(w, ldw, N, K, wtb.ptr, wtb.ld, wtb.Kp, 0, 1, nsplit, 1, nullptr, nullptr, st, NO_DROPOUT));
     PVCR_TRY(gemm_planes(dya.view(), wtb.view(), M, K, (int)dya.ld, dx, lddx, nullptr, 0, st));
   }
   if (dw) {
-    PVCR_TRY(transpose_split(dy, lddy, M, N, dyta.ptr, dyta.ld, dyta.Kp, 0, 1, nsplit, 0, nullptr, nullptr, st));
-    PVCR_TRY(transpose_split(x, ldx, M, K, xtb.ptr, xtb.ld, xtb.Kp, 0, 1, nsplit, 1, nullptr, nullptr, st));
+    PVCR_TRY(transpose_split(dy, lddy, M, N, dyta.ptr, dyta.ld, dyta.Kp, 0, 1, nsplit, 0, nullptr, nullptr, st, NO_DROPOUT));
+    PVCR_TRY(transpose_split(x, ldx, M, K, xtb.ptr, xtb.ld, xtb.Kp, 0, 1, nsplit, 1, nullptr, nullptr, st, NO_DROPOUT));
     PVCR_TRY(gemm_planes(dyta.view(), xtb.view(), N, K, (int)dyta.ld, dw, lddw, nullptr, accumulate, st));
   }
   if (db) PVCR_TRY(colsum(dy, lddy, M, N, db, accumulate, st));

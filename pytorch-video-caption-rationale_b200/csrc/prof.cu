@@ -16,7 +16,8 @@ static bool g_timing = false;
 static std::vector<EventPair> g_pending;
 static std::vector<EventPair> g_pool;
 static const char* const g_names[KC_COUNT] = {"gemm_tcgen05", "operand_staging", "rnn_gates", "attention",
-                                              "loss", "recurrent_persistent", "misc"};
+                                              "loss", "gru_persistent_fwd", "gru_persistent_bwd",
+                                              "decoder_persistent_fwd", "decoder_persistent_bwd", "misc"};
 
 LaunchScope::LaunchScope(int c, cudaStream_t s, double work) : cls(c), st(s), rec(nullptr) {
   std::lock_guard<std::mutex> g(g_mu);

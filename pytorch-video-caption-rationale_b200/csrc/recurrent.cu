@@ -7,15 +7,15 @@ namespace pvcr {
 
 int grad_w(Arena& a, const float* dy, long long lddy, int R, int N, const float* x, long long ldx, int K,
            const long long* x_row_ids, const float* x_row_scale, float* dw, long long lddw, int accumulate,
-           int nsplit, cudaStream_t st) {
+           int nsplit, cudaStream_t st, Dropout x_drop) {
   const size_t m = a.mark();
   Planes dyT = alloc_planes(a, N, R, nsplit);
   Planes xT = alloc_planes(a, K, R, nsplit);
   int rc = PVCR_OK;
   if (!a.measuring()) {
     if (a.failed) { set_last_error("grad_w: workspace too small"); return PVCR_ERR_WORKSPACE; }
-    rc = transpose_split(dy, lddy, R, N, dyT.ptr, dyT.ld, dyT.Kp, 0, 1, nsplit, 0, nullptr, nullptr, st);
-    if (rc == PVCR_OK) rc = transpose_split(x, ldx, R, K, xT.ptr, xT.ld, xT.Kp, 0, 1, nsplit, 1, x_row_ids, x_row_scale, st);
+    rc = transpose_split(dy, lddy, R, N, dyT.ptr, dyT.ld, dyT.Kp, 0, 1, nsplit, 0, nullptr, nullptr, st, NO_DROPOUT);
+    if (rc == PVCR_OK) rc = transpose_split(x, ldx, R, K, xT.ptr, xT.ld, xT.Kp, 0, 1, nsplit, 1, x_row_ids, x_row_scale, st, x_drop);
     if (rc == PVCR_OK) rc = gemm_planes(dyT.view(), xT.view(), N, K, (int)dyT.ld, dw, lddw, nullptr, accumulate, st);
   }
   a.release(m);
@@ -48,7 +48,7 @@ int gru_seq_fwd(const GruSeq& s, cudaStream_t st) {
     }
     GruFwdArgs g{};
     g.B = s.B; g.H = s.H;
-    g.gi_a = s.gi_a + t * s.gi_a_ts; g.gi_a_ld = s.gi_a_ld;
+    g.gi_a = s.gi_a ? s.gi_a + t * s.gi_a_ts : nullptr; g.gi_a_ld = s.gi_a_ld;
     if (s.gi_b && t >= s.gi_b_from) { g.gi_b = s.gi_b + (t - s.gi_b_from) * s.gi_b_ts; g.gi_b_ld = s.gi_b_ld; }
     g.gi_bias = s.gi_bias;
     g.gh = has_prev ? s.gh : nullptr; g.gh_ld = H3;

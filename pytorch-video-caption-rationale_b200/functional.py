@@ -9,7 +9,8 @@ import itertools
 import torch
 
 from . import _lib
-from ._lib import (ATT_PARAM_FIELDS, PvcrDims, PvcrS2vtAttGrads, PvcrS2vtAttParams, check, lib, ptr, stream_ptr)
+from ._lib import (ATT_PARAM_FIELDS, S2VT_PARAM_FIELDS, PvcrDims, PvcrS2vtAttGrads, PvcrS2vtAttParams, PvcrS2vtGrads,
+                   PvcrS2vtParams, check, lib, ptr, stream_ptr)
 
 _seed_counter = itertools.count(1)
 
@@ -100,6 +101,51 @@ class S2VTAttSequence(torch.autograd.Function):
         return (None, None, d_fs, None) + tuple(grads[f] for f in ATT_SEQ_FIELDS)
 
 
+S2VT_SEQ_FIELDS = [f for f in S2VT_PARAM_FIELDS if f not in ("out_w", "out_b")]
+
+
+class S2VTSequence(torch.autograd.Function):
+    """S2VT encode + decode with given input words: (vid_feats, frame_scale, s_in, params) -> hs [B,L,H]
+    (model/S2VTModel.py:74-145 up to, but excluding, the vocabulary projection)."""
+
+    @staticmethod
+    def forward(ctx, cfg, vid, frame_scale, s_in, *params):
+        B, N, V = vid.shape
+        L = s_in.shape[1]
+        tensors = {f: _f32c(p) for f, p in zip(S2VT_SEQ_FIELDS, params)}
+        H = tensors["rnn1_w_hh"].shape[1]
+        Vc, E = tensors["emb"].shape
+        dims = make_dims(B, N, V, H, E, L, Vc, cfg["nsplit"], cfg.get("emb_dropout_p", 0.0), cfg.get("seed", 0))
+        vid_c = _f32c(vid)
+        fs_c = None if frame_scale is None else _f32c(frame_scale)
+        s_c = _i64c(s_in)
+        need_fg = int(frame_scale is not None and frame_scale.requires_grad)
+        Lb = lib()
+        ws = _ws(Lb.pvcr_s2vt_workspace(ctypes.byref(dims), need_fg), vid.device)
+        hs = torch.empty((B, L, H), dtype=torch.float32, device=vid.device)
+        ps = _fill_struct(PvcrS2vtParams(), S2VT_SEQ_FIELDS, tensors)
+        check(Lb.pvcr_s2vt_fwd(ctypes.byref(dims), ctypes.byref(ps), ptr(vid_c), ptr(fs_c), ptr(s_c), ptr(hs), ptr(ws),
+                               ws.numel(), stream_ptr()), "pvcr_s2vt_fwd")
+        ctx.dims = dims
+        ctx.need_fg = need_fg
+        ctx.keep = (vid_c, fs_c, s_c, hs, ws, tensors)
+        return hs
+
+    @staticmethod
+    def backward(ctx, d_hs):
+        vid_c, fs_c, s_c, hs, ws, tensors = ctx.keep
+        d_hs = _f32c(d_hs)
+        grads = {f: torch.empty_like(t) for f, t in tensors.items()}
+        d_fs = torch.empty_like(fs_c) if ctx.need_fg else None
+        ps = _fill_struct(PvcrS2vtParams(), S2VT_SEQ_FIELDS, tensors)
+        gs = _fill_struct(PvcrS2vtGrads(), S2VT_SEQ_FIELDS, grads)
+        Lb = lib()
+        check(Lb.pvcr_s2vt_bwd(ctypes.byref(ctx.dims), ctypes.byref(ps), ptr(vid_c), ptr(fs_c), ptr(s_c), ptr(hs),
+                               ptr(d_hs), ctypes.byref(gs), ptr(d_fs), ptr(ws), ws.numel(), stream_ptr()),
+              "pvcr_s2vt_bwd")
+        return (None, None, d_fs, None) + tuple(grads[f] for f in S2VT_SEQ_FIELDS)
+
+
 class VocabCrossEntropy(torch.autograd.Function):
     """Dropout + Linear(H -> Vc) fused with calc_masked_loss / calc_masked_accuracy / argmax
     (model/S2VTAttModel.py:145, train_utils.py:37-71, train.py:38): (hs, W, b, target, s_len) -> loss, stats, pred."""
@@ -178,3 +224,8 @@ class VocabLogits(torch.autograd.Function):
 
 def s2vtatt_greedy(vid, frame_scale, sos_id, max_len, seq_params, out_w, out_b):
     raise _lib.PvcrError("greedy decoding entry point not built yet")
+
+
+def s2vt_decode_steps(vid, frame_scale, sos_id, max_len, seq_params, out_w, out_b, cfg, teacher_words=None,
+                      teacher_mask=None, want_logits=True):
+    raise _lib.PvcrError("step-wise S2VT decoding entry point not built yet")
