@@ -137,6 +137,25 @@ int pvcr_s2vt_bwd(const PvcrDims* d, const PvcrS2vtParams* p, const float* vid_f
                   const int64_t* s_in, float* hs, const float* d_hs, PvcrS2vtGrads* g, float* d_frame_scale,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* Step-wise decoding with word feedback.
+ * pvcr_s2vtatt_greedy: eval branch of S2VTAttModel (model/S2VTAttModel.py:172-191): fixed L steps, arg-max fed back,
+ *   no early stop.  ids [B,L] int64; logits [B,L,Vc] (NULL: not materialised); alphas [L,B,N] (NULL ok).
+ *   p->out_w / p->out_b are used.  dims->nsplit = 3 reproduces fp32 arithmetic (token ids match the reference).
+ * pvcr_s2vt_decode_steps: eval branch of S2VTModel (model/S2VTModel.py:147-177) when teacher_mask == NULL, and
+ *   its scheduled-sampling training branch (:121-141) otherwise: teacher_mask is a HOST array of L ints, entry i
+ *   being the outcome of the reference's per-step coin `random.random() < teacher_force_prob`; the word fed to step
+ *   i+1 is teacher_words[:, i+1] if teacher_mask[i] else argmax(logits_i).  fed [B,L] receives the fed words
+ *   (NULL ok).  dims->dropout_p / seed and out_dropout_p reproduce the masks of pvcr_s2vt_fwd / pvcr_vocab_ce_fwd. */
+size_t pvcr_s2vtatt_greedy_workspace(const PvcrDims* d);
+int pvcr_s2vtatt_greedy(const PvcrDims* d, const PvcrS2vtAttParams* p, const float* vid_feats, const float* frame_scale,
+                        int64_t sos_id, int64_t* ids, float* logits, float* alphas, void* workspace,
+                        size_t workspace_bytes, void* stream);
+size_t pvcr_s2vt_decode_steps_workspace(const PvcrDims* d);
+int pvcr_s2vt_decode_steps(const PvcrDims* d, const PvcrS2vtParams* p, const float* vid_feats, const float* frame_scale,
+                           int64_t sos_id, const int64_t* teacher_words, const int32_t* teacher_mask,
+                           float out_dropout_p, int64_t* ids, int64_t* fed, float* logits, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 /* Vocabulary projection fused with the loss contract:  logits = Dropout(hs) out_w^T + out_b
  * (model/S2VTAttModel.py:145, model/S2VTModel.py:130), then calc_masked_loss / calc_masked_accuracy /
  * argmax (train_utils.py:37-71, train.py:38).

@@ -19,6 +19,12 @@ int s2vt_fwd(const PvcrDims&, const PvcrS2vtParams&, const float*, const float*,
              cudaStream_t);
 int s2vt_bwd(const PvcrDims&, const PvcrS2vtParams&, const float*, const float*, const long long*, const float*, float*,
              PvcrS2vtGrads&, float*, void*, size_t, cudaStream_t);
+size_t s2vtatt_greedy_workspace(const PvcrDims& d);
+int s2vtatt_greedy(const PvcrDims&, const PvcrS2vtAttParams&, const float*, const float*, long long, long long*, float*,
+                   float*, void*, size_t, cudaStream_t);
+size_t s2vt_decode_steps_workspace(const PvcrDims& d);
+int s2vt_decode_steps(const PvcrDims&, const PvcrS2vtParams&, const float*, const float*, long long, const long long*,
+                      const int*, float, long long*, long long*, float*, void*, size_t, cudaStream_t);
 size_t vocab_ce_workspace(int B, int L, int H, int Vc, int nsplit, float dropout_p);
 int vocab_ce_fwd(const float*, const float*, const float*, const long long*, const long long*, int, int, int, int, int,
                  float, unsigned long long, float*, long long*, float*, float*, long long, void*, size_t, cudaStream_t);
@@ -72,6 +78,22 @@ int pvcr_s2vt_bwd(const PvcrDims* d, const PvcrS2vtParams* p, const float* vid_f
                   void* workspace, size_t workspace_bytes, void* stream) {
   return s2vt_bwd(*d, *p, vid_feats, frame_scale, (const long long*)s_in, d_hs, hs, *g, d_frame_scale, workspace,
                   workspace_bytes, (cudaStream_t)stream);
+}
+size_t pvcr_s2vtatt_greedy_workspace(const PvcrDims* d) { return s2vtatt_greedy_workspace(*d); }
+int pvcr_s2vtatt_greedy(const PvcrDims* d, const PvcrS2vtAttParams* p, const float* vid_feats, const float* frame_scale,
+                        int64_t sos_id, int64_t* ids, float* logits, float* alphas, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  return s2vtatt_greedy(*d, *p, vid_feats, frame_scale, sos_id, (long long*)ids, logits, alphas, workspace,
+                        workspace_bytes, (cudaStream_t)stream);
+}
+size_t pvcr_s2vt_decode_steps_workspace(const PvcrDims* d) { return s2vt_decode_steps_workspace(*d); }
+int pvcr_s2vt_decode_steps(const PvcrDims* d, const PvcrS2vtParams* p, const float* vid_feats, const float* frame_scale,
+                           int64_t sos_id, const int64_t* teacher_words, const int32_t* teacher_mask,
+                           float out_dropout_p, int64_t* ids, int64_t* fed, float* logits, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  return s2vt_decode_steps(*d, *p, vid_feats, frame_scale, sos_id, (const long long*)teacher_words, teacher_mask,
+                           out_dropout_p, (long long*)ids, (long long*)fed, logits, workspace, workspace_bytes,
+                           (cudaStream_t)stream);
 }
 size_t pvcr_vocab_ce_workspace(int B, int L, int H, int Vc, int nsplit, float dropout_p) {
   return vocab_ce_workspace(B, L, H, Vc, nsplit, dropout_p);

@@ -29,6 +29,10 @@ __device__ __forceinline__ float dropout_scale(const Dropout& d, unsigned long l
   return philox_uniform(d.seed, d.offset + idx) >= d.p ? 1.f / (1.f - d.p) : 0.f;
 }
 
+__device__ __forceinline__ unsigned long long drop_index(const Dropout& d, long long r, int C, int c) {
+  return (unsigned long long)((r * d.row_mul + d.row_add) * C + c);
+}
+
 __device__ __forceinline__ void write_split(bf16* row_out, int Kp, int k, int nsplit, int role_b, float x) {
   bf16 t[3];
   split3(x, t[0], t[1], t[2]);
@@ -63,7 +67,7 @@ __global__ void cast_split_kernel(const float* __restrict__ in, long long ld_in,
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float val = x[j] * rs;
-      if (drop.p > 0.f) val *= dropout_scale(drop, (unsigned long long)r * C + c0 + j);
+      if (drop.p > 0.f) val *= dropout_scale(drop, drop_index(drop, r, C, c0 + j));
       split3(val, t[0][j], t[1][j], t[2][j]);
     }
     bf16* dst = out + (long long)r * ld_out + c0;
@@ -100,7 +104,7 @@ __global__ void transpose_split_kernel(const float* __restrict__ in, long long l
       const long long src_row = row_ids ? row_ids[r] : r;
       v = __ldg(in + src_row * ld_in + c);
       if (row_scale) v *= __ldg(row_scale + src_row);
-      if (drop.p > 0.f) v *= dropout_scale(drop, (unsigned long long)r * C + c);
+      if (drop.p > 0.f) v *= dropout_scale(drop, drop_index(drop, r, C, c));
     }
     tile[i][threadIdx.x] = v;
   }
@@ -137,7 +141,7 @@ __global__ void gather_split_kernel(const float* __restrict__ table, int E, cons
     float val = 0.f;
     if (e < E) {
       val = __ldg(table + ids[r] * E + e);
-      if (drop.p > 0.f) val *= dropout_scale(drop, (unsigned long long)r * E + e);
+      if (drop.p > 0.f) val *= dropout_scale(drop, drop_index(drop, r, E, e));
     }
     write_split(out + (long long)r * ld_out, Ep, e, nsplit, 0, val);
   }
@@ -161,7 +165,7 @@ __global__ void scatter_add_rows_kernel(const float* __restrict__ rows, long lon
        i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / E), e = (int)(i % E);
     float v = rows[(long long)r * ld + e];
-    if (drop.p > 0.f) v *= dropout_scale(drop, (unsigned long long)r * E + e);
+    if (drop.p > 0.f) v *= dropout_scale(drop, drop_index(drop, r, E, e));
     atomicAdd(grad + ids[r] * E + e, v);
   }
 }
@@ -212,6 +216,57 @@ int dropout_apply(const float* in, float* out, long long n, Dropout drop, cudaSt
   const int blocks = (int)((n + 255) / 256 > 148 * 8 ? 148 * 8 : (n + 255) / 256);
   { LaunchScope ls_(KC_MISC, st);
   dropout_apply_kernel<<<blocks, 256, 0, st>>>(in, out, n, drop);
+  }
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  return PVCR_OK;
+}
+__global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restrict__ in, long long ld, int C,
+                                                         long long* out, long long out_stride, long long* next,
+                                                         const long long* teacher, long long teacher_stride,
+                                                         int use_teacher) {
+  __shared__ float s_val[8];
+  __shared__ int s_idx[8];
+  const int row = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* x = in + (long long)row * ld;
+  float m = -INFINITY;
+  int mi = 0x7fffffff;
+  for (int j = tid; j < C; j += 256) {
+    const float v = x[j];
+    if (v > m) { m = v; mi = j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+  }
+  if (lane == 0) { s_val[warp] = m; s_idx[warp] = mi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (s_val[w] > m || (s_val[w] == m && s_idx[w] < mi)) { m = s_val[w]; mi = s_idx[w]; }
+    if (mi == 0x7fffffff) mi = 0;                      // all-NaN row: torch.argmax returns an index too
+    out[(long long)row * out_stride] = mi;
+    if (next) next[row] = use_teacher ? teacher[(long long)row * teacher_stride] : (long long)mi;
+  }
+}
+int argmax_rows(const float* in, long long ld, int R, int C, long long* out, long long out_stride, long long* next,
+                const long long* teacher, long long teacher_stride, int use_teacher, cudaStream_t st) {
+  if (R == 0) return PVCR_OK;
+  { LaunchScope ls_(KC_LOSS, st);
+  argmax_rows_kernel<<<R, 256, 0, st>>>(in, ld, C, out, out_stride, next, teacher, teacher_stride, use_teacher);
+  }
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  return PVCR_OK;
+}
+__global__ void fill_i64_kernel(long long* p, long long v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+int fill_i64(long long* p, long long v, int n, cudaStream_t st) {
+  if (n == 0) return PVCR_OK;
+  { LaunchScope ls_(KC_MISC, st);
+  fill_i64_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, v, n);
   }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;

@@ -10,6 +10,9 @@ struct Dropout {
   float p;                  // 0 = disabled
   unsigned long long seed;
   unsigned long long offset;   // added to the element index (distinct per tensor / per step)
+  // element (r, c) of a [R, C] call maps to index ((r * row_mul + row_add) * C + c): lets a step-wise call on
+  // B rows reproduce the mask of row b*L + i of the all-steps call (row_mul = L, row_add = i)
+  int row_mul = 1, row_add = 0;
 };
 
 // ---- operand staging: fp32 -> bf16 split planes -------------------------------------------------
@@ -32,6 +35,11 @@ int colsum(const float* in, long long ld, int R, int C, float* out, int accumula
 // y[i] = a[i] * mask_i/(1-p)  (dropout backward / forward on fp32 data), in place allowed
 int dropout_apply(const float* in, float* out, long long n, Dropout drop, cudaStream_t st);
 int fill_zero(void* p, size_t bytes, cudaStream_t st);
+// out[r * out_stride] = argmax_c in[r*ld + c] (first maximal index), and optionally
+// next[r] = use_teacher ? teacher[r * teacher_stride] : argmax   (the word fed to the next decoding step)
+int argmax_rows(const float* in, long long ld, int R, int C, long long* out, long long out_stride, long long* next,
+                const long long* teacher, long long teacher_stride, int use_teacher, cudaStream_t st);
+int fill_i64(long long* p, long long v, int n, cudaStream_t st);
 
 // ---- GRU gate math ---------------------------------------------------------------------------------
 struct GruFwdArgs {

@@ -129,15 +129,11 @@ static int check_s2vt_dims(const PvcrDims& d) {
 
 static Dropout emb_dropout(const PvcrDims& d) { return Dropout{d.dropout_p, d.seed, 0x3000000000ull}; }
 
-int s2vt_fwd(const PvcrDims& d, const PvcrS2vtParams& p, const float* vid, const float* frame_scale,
-             const long long* s_in, float* hs, void* ws, size_t ws_bytes, cudaStream_t st) {
-  PVCR_TRY(check_s2vt_dims(d));
-  const int B = d.B, N = d.N, V = d.V, H = d.H, E = d.E, L = d.L;
-  const int BN = B * N, BL = B * L, H3 = 3 * H;
-  Arena a(ws, ws_bytes);
-  S2vtWs w;
-  carve_s2vt(a, d, 0, w);
-  if (a.failed) { set_last_error("s2vt_fwd: workspace too small (%zu < %zu)", ws_bytes, a.off); return PVCR_ERR_WORKSPACE; }
+// weights -> planes, rnn1 over the frames, rnn2 encoding stage
+static int s2vt_encode(const PvcrDims& d, const PvcrS2vtParams& p, S2vtWs& w, const S2vtSeqs& q, const float* vid,
+                       const float* frame_scale, cudaStream_t st) {
+  const int B = d.B, N = d.N, V = d.V, H = d.H, E = d.E;
+  const int BN = B * N, H3 = 3 * H;
   PVCR_TRY(prep_weight(p.rnn1_w_ih, V, H3, V, w.w1i, st));
   PVCR_TRY(prep_weight(p.rnn1_w_hh, H, H3, H, w.w1h, st));
   PVCR_TRY(prep_weight(p.rnn2_w_ih, H + E, H3, H, w.w2o, st));
@@ -147,15 +143,27 @@ int s2vt_fwd(const PvcrDims& d, const PvcrS2vtParams& p, const float* vid, const
     for (SeqBuf* s : {&w.e1, &w.d1, &w.e2, &w.d2})
       PVCR_TRY(fill_zero(s->hp.ptr, sizeof(bf16) * (size_t)s->hp.rows * s->hp.ld, st));
   }
-  S2vtSeqs q = make_seqs(d, p, w, hs);
-  // rnn1: encode the frames, then L input-free steps
   PVCR_TRY(stage(vid, V, BN, V, w.x_a, 0, frame_scale, NO_DROPOUT, st));
   PVCR_TRY(gemm_planes(w.x_a.view(), w.w1i.view(), BN, H3, (int)w.x_a.ld, w.gi1, H3, p.rnn1_b_ih, 0, st));
   PVCR_TRY(gru_seq_fwd(q.e1, st));
-  PVCR_TRY(gru_seq_fwd(q.d1, st));
   // rnn2 encoding stage: [out1 ; 0] -> only the out1 half of W_ih contributes
   PVCR_TRY(gemm_planes(w.e1.hp.view(), w.w2o.view(), BN, H3, (int)w.e1.hp.ld, w.gi2e, H3, p.rnn2_b_ih, 0, st));
   PVCR_TRY(gru_seq_fwd(q.e2, st));
+  return PVCR_OK;
+}
+
+int s2vt_fwd(const PvcrDims& d, const PvcrS2vtParams& p, const float* vid, const float* frame_scale,
+             const long long* s_in, float* hs, void* ws, size_t ws_bytes, cudaStream_t st) {
+  PVCR_TRY(check_s2vt_dims(d));
+  const int B = d.B, H = d.H, E = d.E, L = d.L;
+  const int BL = B * L, H3 = 3 * H;
+  Arena a(ws, ws_bytes);
+  S2vtWs w;
+  carve_s2vt(a, d, 0, w);
+  if (a.failed) { set_last_error("s2vt_fwd: workspace too small (%zu < %zu)", ws_bytes, a.off); return PVCR_ERR_WORKSPACE; }
+  S2vtSeqs q = make_seqs(d, p, w, hs);
+  PVCR_TRY(s2vt_encode(d, p, w, q, vid, frame_scale, st));
+  PVCR_TRY(gru_seq_fwd(q.d1, st));
   // rnn2 decoding stage: [h1_dec ; Dropout(Emb[w])]
   PVCR_TRY(gemm_planes(w.d1.hp.view(), w.w2o.view(), BL, H3, (int)w.d1.hp.ld, w.gi2d, H3, p.rnn2_b_ih, 0, st));
   PVCR_TRY(gather_split(p.emb, E, s_in, BL, w.emb_a.ptr, w.emb_a.ld, w.emb_a.Kp, d.nsplit, emb_dropout(d), st));
@@ -163,6 +171,7 @@ int s2vt_fwd(const PvcrDims& d, const PvcrS2vtParams& p, const float* vid, const
   PVCR_TRY(gru_seq_fwd(q.d2, st));
   return PVCR_OK;
 }
+
 
 // rows (b, t) of h_{t-1}: step 0 takes `first` (row stride first_ld; null = zeros), steps >= 1 the sequence itself
 static int build_hprev(const SeqBuf& s, int B, int H, const float* first, long long first_ld, cudaStream_t st) {
@@ -250,6 +259,92 @@ int s2vt_bwd(const PvcrDims& d, const PvcrS2vtParams& p, const float* vid, const
   if (need_frame_grad) {
     PVCR_TRY(grad_x(a, w.e1.dgi, H3, BN, H3, w.w1iT, w.dxsel, V, 0, st));
     PVCR_TRY(rowdot(vid, w.dxsel, BN, V, d_frame_scale, st));
+  }
+  return PVCR_OK;
+}
+
+// ---- step-wise decoding with word feedback -----------------------------------------------------------------------
+// Eval branch (model/S2VTModel.py:147-177: arg-max always fed back) and the scheduled-sampling training branch
+// (:121-141: per step, the teacher word or the arg-max according to a host-drawn coin).
+struct S2vtStepWs {
+  S2vtWs w;
+  Planes wv, emb_step, hdrop;
+  float *logits_step, *hs, *g2;
+  long long* words;
+};
+static void carve_steps(Arena& a, const PvcrDims& d, S2vtStepWs& g) {
+  carve_s2vt(a, d, 0, g.w);
+  g.wv = alloc_planes(a, d.Vc, d.H, d.nsplit);
+  g.emb_step = alloc_planes(a, d.B, d.E, d.nsplit);
+  g.hdrop = alloc_planes(a, d.B, d.H, d.nsplit);
+  g.logits_step = a.alloc<float>((size_t)d.B * round_up(d.Vc, 4));
+  g.hs = a.alloc<float>((size_t)d.B * d.L * d.H);
+  g.g2 = a.alloc<float>((size_t)d.B * 3 * d.H);
+  g.words = a.alloc<long long>(d.B);
+}
+size_t s2vt_decode_steps_workspace(const PvcrDims& d) {
+  Arena a(nullptr, 0);
+  S2vtStepWs g;
+  carve_steps(a, d, g);
+  return a.off + 4096;
+}
+
+static int gru_single_step(const PvcrDims& d, const SeqBuf& s, int i, const SeqBuf& prev_stage, const Planes& whh,
+                           const float* gi, const float* gi_bias, const float* b_hh, float* gh, cudaStream_t st) {
+  const int B = d.B, H = d.H, T = s.T, H3 = 3 * H;
+  OperandView hprev_a = (i == 0)
+      ? OperandView{prev_stage.hp.ptr + (long long)(prev_stage.T - 1) * prev_stage.hp.ld,
+                    (long long)prev_stage.T * prev_stage.hp.ld, 0, B, 1}
+      : OperandView{s.hp.ptr + (long long)(i - 1) * s.hp.ld, (long long)T * s.hp.ld, 0, B, 1};
+  PVCR_TRY(gemm_planes(hprev_a, whh.view(), B, H3, (int)whh.ld, gh, H3, nullptr, 0, st));
+  GruFwdArgs g{};
+  g.B = B; g.H = H;
+  g.gi_a = gi; g.gi_a_ld = H3; g.gi_bias = gi_bias;
+  g.gh = gh; g.gh_ld = H3; g.b_hh = b_hh;
+  if (i == 0) { g.h_prev = prev_stage.h + (long long)(prev_stage.T - 1) * H; g.h_prev_ld = (long long)prev_stage.T * H; }
+  else { g.h_prev = s.h + (long long)(i - 1) * H; g.h_prev_ld = (long long)T * H; }
+  g.h_out = s.h + (long long)i * H; g.h_out_ld = (long long)T * H;
+  g.h_planes = s.hp.ptr + (long long)i * s.hp.ld; g.h_planes_ld = (long long)T * s.hp.ld;
+  g.Hp = s.hp.Kp; g.nsplit = d.nsplit;
+  return gru_gate_fwd(g, st);
+}
+
+// teacher_mask: HOST array of L ints (coin of step i decides the word fed to step i+1); null = always feed back.
+int s2vt_decode_steps(const PvcrDims& d, const PvcrS2vtParams& p, const float* vid, const float* frame_scale,
+                      long long sos_id, const long long* teacher_words, const int* teacher_mask, float out_dropout_p,
+                      long long* ids, long long* fed, float* logits, void* ws, size_t ws_bytes, cudaStream_t st) {
+  PVCR_TRY(check_s2vt_dims(d));
+  const int B = d.B, H = d.H, E = d.E, L = d.L, Vc = d.Vc, H3 = 3 * H;
+  Arena a(ws, ws_bytes);
+  S2vtStepWs gw;
+  carve_steps(a, d, gw);
+  if (a.failed) { set_last_error("s2vt_decode_steps: workspace too small (%zu < %zu)", ws_bytes, a.off); return PVCR_ERR_WORKSPACE; }
+  S2vtWs& w = gw.w;
+  S2vtSeqs q = make_seqs(d, p, w, gw.hs);
+  PVCR_TRY(s2vt_encode(d, p, w, q, vid, frame_scale, st));
+  PVCR_TRY(prep_weight(p.out_w, H, Vc, H, gw.wv, st));
+  if (gw.hdrop.Kp != H) PVCR_TRY(fill_zero(gw.hdrop.ptr, sizeof(bf16) * (size_t)B * gw.hdrop.ld, st));
+  PVCR_TRY(fill_i64(gw.words, sos_id, B, st));
+  for (int i = 0; i < L; ++i) {
+    if (fed) PVCR_CUDA_CHECK(cudaMemcpy2DAsync(fed + i, sizeof(long long) * L, gw.words, sizeof(long long),
+                                               sizeof(long long), B, cudaMemcpyDeviceToDevice, st));
+    PVCR_TRY(gru_single_step(d, w.d1, i, w.e1, w.w1h, nullptr, p.rnn1_b_ih, p.rnn1_b_hh, w.gh, st));
+    OperandView h1_a{w.d1.hp.ptr + (long long)i * w.d1.hp.ld, (long long)L * w.d1.hp.ld, 0, B, 1};
+    PVCR_TRY(gemm_planes(h1_a, w.w2o.view(), B, H3, (int)w.w2o.ld, gw.g2, H3, p.rnn2_b_ih, 0, st));
+    Dropout ed = emb_dropout(d);
+    ed.row_mul = L; ed.row_add = i;
+    PVCR_TRY(gather_split(p.emb, E, gw.words, B, gw.emb_step.ptr, gw.emb_step.ld, gw.emb_step.Kp, d.nsplit, ed, st));
+    PVCR_TRY(gemm_planes(gw.emb_step.view(), w.w2e.view(), B, H3, (int)gw.emb_step.ld, gw.g2, H3, nullptr, 1, st));
+    PVCR_TRY(gru_single_step(d, w.d2, i, w.e2, w.w2h, gw.g2, nullptr, p.rnn2_b_hh, w.gh, st));
+    Dropout od{out_dropout_p, d.seed, 0x5000000000ull, L, i};
+    PVCR_TRY(cast_split(gw.hs + (long long)i * H, (long long)L * H, B, H, gw.hdrop.ptr, gw.hdrop.ld, gw.hdrop.Kp,
+                        d.nsplit, 0, nullptr, od, st));
+    float* lg = logits ? logits + (long long)i * Vc : gw.logits_step;
+    const long long ldl = logits ? (long long)L * Vc : round_up(Vc, 4);
+    PVCR_TRY(gemm_planes(gw.hdrop.view(), gw.wv.view(), B, Vc, (int)gw.wv.ld, lg, ldl, p.out_b, 0, st));
+    const int use_teacher = (teacher_mask && teacher_words && i + 1 < L) ? teacher_mask[i] : 0;
+    PVCR_TRY(argmax_rows(lg, ldl, B, Vc, ids + i, L, gw.words, teacher_words ? teacher_words + i + 1 : nullptr, L,
+                         use_teacher, st));
   }
   return PVCR_OK;
 }

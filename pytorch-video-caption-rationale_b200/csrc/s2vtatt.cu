@@ -346,4 +346,91 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   return PVCR_OK;
 }
 
+// ---- fixed-length greedy decoding (eval branch, model/S2VTAttModel.py:172-191) ---------------------------------
+struct GreedyWs {
+  AttWs w;
+  Planes wv, emb_step;
+  float *logits_step, *hs;
+  long long* words;
+};
+static void carve_greedy(Arena& a, const PvcrDims& d, GreedyWs& g) {
+  carve(a, d, 0, g.w);
+  g.wv = alloc_planes(a, d.Vc, d.H, d.nsplit);
+  g.emb_step = alloc_planes(a, d.B, d.E, d.nsplit);
+  g.logits_step = a.alloc<float>((size_t)d.B * round_up(d.Vc, 4));
+  g.hs = a.alloc<float>((size_t)d.B * d.L * d.H);
+  g.words = a.alloc<long long>(d.B);
+}
+size_t s2vtatt_greedy_workspace(const PvcrDims& d) {
+  Arena a(nullptr, 0);
+  GreedyWs g;
+  carve_greedy(a, d, g);
+  return a.off + 4096;
+}
+
+int s2vtatt_greedy(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid, const float* frame_scale,
+                   long long sos_id, long long* ids, float* logits, float* alphas, void* ws, size_t ws_bytes,
+                   cudaStream_t st) {
+  PVCR_TRY(check_dims(d));
+  const int B = d.B, N = d.N, V = d.V, H = d.H, E = d.E, L = d.L, Vc = d.Vc;
+  const int BN = B * N, BL = B * L, H3 = 3 * H, H4 = 4 * H;
+  Arena a(ws, ws_bytes);
+  GreedyWs gw;
+  carve_greedy(a, d, gw);
+  if (a.failed) { set_last_error("s2vtatt_greedy: workspace too small (%zu < %zu)", ws_bytes, a.off); return PVCR_ERR_WORKSPACE; }
+  AttWs& w = gw.w;
+  PVCR_TRY(prep_weight(p.enc_w_ih, V, H3, V, w.wih_enc, st));
+  PVCR_TRY(prep_weight(p.enc_w_hh, H, H3, H, w.whh_enc, st));
+  PVCR_TRY(prep_weight(p.att_wk, H, H, H, w.wk, st));
+  PVCR_TRY(prep_weight(p.att_wq, H, H, H, w.wcat, st, 0));
+  PVCR_TRY(prep_weight(p.dec_w_hh, H, H3, H, w.wcat, st, H));
+  PVCR_TRY(prep_weight(p.dec_w_ih, H + E, H3, H, w.wc, st));
+  PVCR_TRY(prep_weight(p.dec_w_ih + H, H + E, H3, E, w.we, st));
+  PVCR_TRY(prep_weight(p.out_w, H, Vc, H, gw.wv, st));
+  if (w.enc_a.Kp != H) {
+    PVCR_TRY(fill_zero(w.enc_a.ptr, sizeof(bf16) * (size_t)BN * w.enc_a.ld, st));
+    PVCR_TRY(fill_zero(w.hs_a.ptr, sizeof(bf16) * (size_t)BL * w.hs_a.ld, st));
+    PVCR_TRY(fill_zero(w.ctx_a.ptr, sizeof(bf16) * (size_t)B * w.ctx_a.ld, st));
+  }
+  PVCR_TRY(stage(vid, V, BN, V, w.x_a, 0, frame_scale, NO_DROPOUT, st));
+  PVCR_TRY(gemm_planes(w.x_a.view(), w.wih_enc.view(), BN, H3, (int)w.x_a.ld, w.gi_enc, H3, p.enc_b_ih, 0, st));
+  PVCR_TRY(gru_seq_fwd(encoder_seq(d, p, w), st));
+  PVCR_TRY(gemm_planes(w.enc_a.view(), w.wk.view(), BN, H, (int)w.enc_a.ld, w.pk, H, nullptr, 0, st));
+  PVCR_TRY(fill_i64(gw.words, sos_id, B, st));
+  float* hs = gw.hs;
+  for (int i = 0; i < L; ++i) {
+    OperandView hprev_a = (i == 0)
+        ? OperandView{w.enc_a.ptr + (long long)(N - 1) * w.enc_a.ld, (long long)N * w.enc_a.ld, 0, B, 1}
+        : OperandView{w.hs_a.ptr + (long long)(i - 1) * w.hs_a.ld, (long long)L * w.hs_a.ld, 0, B, 1};
+    float* g1 = w.g1_all;
+    PVCR_TRY(gemm_planes(hprev_a, w.wcat.view(), B, H4, (int)w.wcat.ld, g1, H4, nullptr, 0, st));
+    AttnFwdArgs at{};
+    at.B = B; at.N = N; at.H = H;
+    at.q = g1; at.q_ld = H4; at.pk = w.pk; at.enc = w.enc; at.v = p.att_v;
+    at.alpha = alphas ? alphas + (long long)i * B * N : w.alpha_all;
+    at.ctx = w.ctx_all; at.ctx_ld = H;
+    at.ctx_planes = w.ctx_a.ptr; at.ctx_planes_ld = w.ctx_a.ld; at.Hp = w.ctx_a.Kp; at.nsplit = d.nsplit;
+    PVCR_TRY(attn_fwd(at, st));
+    PVCR_TRY(gemm_planes(w.ctx_a.view(), w.wc.view(), B, H3, (int)w.ctx_a.ld, w.g2, H3, nullptr, 0, st));
+    PVCR_TRY(gather_split(p.emb, E, gw.words, B, gw.emb_step.ptr, gw.emb_step.ld, gw.emb_step.Kp, d.nsplit, NO_DROPOUT, st));
+    PVCR_TRY(gemm_planes(gw.emb_step.view(), w.we.view(), B, H3, (int)gw.emb_step.ld, w.g2, H3, p.dec_b_ih, 1, st));
+    GruFwdArgs g{};
+    g.B = B; g.H = H;
+    g.gi_a = w.g2; g.gi_a_ld = H3;
+    g.gh = g1 + H; g.gh_ld = H4; g.b_hh = p.dec_b_hh;
+    if (i == 0) { g.h_prev = w.enc + (long long)(N - 1) * H; g.h_prev_ld = (long long)N * H; }
+    else { g.h_prev = hs + (long long)(i - 1) * H; g.h_prev_ld = (long long)L * H; }
+    g.h_out = hs + (long long)i * H; g.h_out_ld = (long long)L * H;
+    g.h_planes = w.hs_a.ptr + (long long)i * w.hs_a.ld; g.h_planes_ld = (long long)L * w.hs_a.ld;
+    g.Hp = w.hs_a.Kp; g.nsplit = d.nsplit;
+    PVCR_TRY(gru_gate_fwd(g, st));
+    OperandView h_a{w.hs_a.ptr + (long long)i * w.hs_a.ld, (long long)L * w.hs_a.ld, 0, B, 1};
+    float* lg = logits ? logits + (long long)i * Vc : gw.logits_step;
+    const long long ldl = logits ? (long long)L * Vc : round_up(Vc, 4);
+    PVCR_TRY(gemm_planes(h_a, gw.wv.view(), B, Vc, (int)gw.wv.ld, lg, ldl, p.out_b, 0, st));
+    PVCR_TRY(argmax_rows(lg, ldl, B, Vc, ids + i, L, gw.words, nullptr, 0, 0, st));
+  }
+  return PVCR_OK;
+}
+
 }  // namespace pvcr

@@ -222,10 +222,47 @@ class VocabLogits(torch.autograd.Function):
         return None, d_hs, d_w, d_b
 
 
-def s2vtatt_greedy(vid, frame_scale, sos_id, max_len, seq_params, out_w, out_b):
-    raise _lib.PvcrError("greedy decoding entry point not built yet")
+def s2vtatt_greedy(vid, frame_scale, sos_id, max_len, seq_params, out_w, out_b, nsplit=3):
+    """-> (ids [B,L] int64, logits [B,L,Vc], alphas [L,B,N]); eval branch of S2VTAttModel."""
+    B, N, V = vid.shape
+    tensors = {f: _f32c(p) for f, p in zip(ATT_SEQ_FIELDS, seq_params)}
+    tensors["out_w"], tensors["out_b"] = _f32c(out_w), _f32c(out_b)
+    H = tensors["enc_w_hh"].shape[1]
+    Vc, E = tensors["emb"].shape
+    dims = make_dims(B, N, V, H, E, max_len, Vc, nsplit, 0.0, 0)
+    vid_c = _f32c(vid)
+    fs_c = None if frame_scale is None else _f32c(frame_scale)
+    Lb = lib()
+    ws = _ws(Lb.pvcr_s2vtatt_greedy_workspace(ctypes.byref(dims)), vid.device)
+    ids = torch.empty((B, max_len), dtype=torch.int64, device=vid.device)
+    logits = torch.empty((B, max_len, Vc), dtype=torch.float32, device=vid.device)
+    alphas = torch.empty((max_len, B, N), dtype=torch.float32, device=vid.device)
+    ps = _fill_struct(PvcrS2vtAttParams(), ATT_PARAM_FIELDS, tensors)
+    check(Lb.pvcr_s2vtatt_greedy(ctypes.byref(dims), ctypes.byref(ps), ptr(vid_c), ptr(fs_c), int(sos_id), ptr(ids),
+                                 ptr(logits), ptr(alphas), ptr(ws), ws.numel(), stream_ptr()), "pvcr_s2vtatt_greedy")
+    return ids, logits, alphas
 
 
 def s2vt_decode_steps(vid, frame_scale, sos_id, max_len, seq_params, out_w, out_b, cfg, teacher_words=None,
                       teacher_mask=None, want_logits=True):
-    raise _lib.PvcrError("step-wise S2VT decoding entry point not built yet")
+    """-> (ids [B,L] arg-max of every step, logits [B,L,Vc] or None, fed [B,L] words fed to every step)."""
+    B, N, V = vid.shape
+    tensors = {f: _f32c(p) for f, p in zip(S2VT_SEQ_FIELDS, seq_params)}
+    tensors["out_w"], tensors["out_b"] = _f32c(out_w), _f32c(out_b)
+    H = tensors["rnn1_w_hh"].shape[1]
+    Vc, E = tensors["emb"].shape
+    dims = make_dims(B, N, V, H, E, max_len, Vc, cfg["nsplit"], cfg.get("emb_dropout_p", 0.0), cfg.get("seed", 0))
+    vid_c = _f32c(vid)
+    fs_c = None if frame_scale is None else _f32c(frame_scale)
+    tw = None if teacher_words is None else _i64c(teacher_words)
+    mask = None if teacher_mask is None else (ctypes.c_int32 * max_len)(*[int(bool(t)) for t in teacher_mask])
+    Lb = lib()
+    ws = _ws(Lb.pvcr_s2vt_decode_steps_workspace(ctypes.byref(dims)), vid.device)
+    ids = torch.empty((B, max_len), dtype=torch.int64, device=vid.device)
+    fed = torch.empty((B, max_len), dtype=torch.int64, device=vid.device)
+    logits = torch.empty((B, max_len, Vc), dtype=torch.float32, device=vid.device) if want_logits else None
+    ps = _fill_struct(PvcrS2vtParams(), S2VT_PARAM_FIELDS, tensors)
+    check(Lb.pvcr_s2vt_decode_steps(ctypes.byref(dims), ctypes.byref(ps), ptr(vid_c), ptr(fs_c), int(sos_id), ptr(tw),
+                                    mask, float(cfg.get("dropout_p", 0.0)), ptr(ids), ptr(fed), ptr(logits), ptr(ws),
+                                    ws.numel(), stream_ptr()), "pvcr_s2vt_decode_steps")
+    return ids, logits, fed

@@ -1,0 +1,71 @@
+"""GPU parity of the eval / feedback decoding paths: greedy token ids must match the reference bit for bit."""
+import numpy as np
+import pytest
+import torch
+
+from tests.golden_util import relerr
+from tests.gpu_util import FixtureGlove, grads_of, load_case, to_cuda
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("tag", ["s2vtatt_tiny", "s2vtatt_mid"])
+def test_s2vtatt_greedy_ids_bit_exact(tag):
+    from pvcr_b200.model import S2VTAttModel
+    d, params, _, (B, N, V, H, E, L, Vc) = load_case(tag)
+    m = to_cuda(S2VTAttModel(FixtureGlove(Vc, E), 0.0, H, V, L), params).eval()
+    vid = torch.from_numpy(d["vid"]).cuda()
+    logits = m(vid, None)                                   # reference API: eval forward returns logits
+    assert np.array_equal(torch.argmax(logits, dim=2).cpu().numpy(), d["greedy_ids"])
+    ids, _ = m.greedy(vid)
+    assert np.array_equal(ids.cpu().numpy(), d["greedy_ids"])
+    assert relerr(logits.cpu().numpy(), d["greedy_logits"]) < 2e-5
+    assert np.abs(m.last_alphas.cpu().numpy() - d["greedy_alphas"]).max() < 1e-5
+
+
+@pytest.mark.parametrize("tag", ["s2vt_tiny", "s2vt_mid", "s2vt_sched"])
+def test_s2vt_greedy_ids_bit_exact(tag):
+    from pvcr_b200.model import S2VTModel
+    d, params, _, (B, N, V, H, E, L, Vc) = load_case(tag)
+    m = to_cuda(S2VTModel(FixtureGlove(Vc, E), 0.0, H, V, L), params).eval()
+    logits = m(torch.from_numpy(d["vid"]).cuda(), None)
+    assert np.array_equal(torch.argmax(logits, dim=2).cpu().numpy(), d["greedy_ids"])
+    assert relerr(logits.cpu().numpy(), d["greedy_logits"]) < 2e-5
+
+
+def test_s2vt_scheduled_sampling(monkeypatch):
+    """teacher_force_prob < 1: the per-step coin (Python RNG, as in the reference) is scripted to the golden sequence."""
+    from pvcr_b200.model import S2VTModel
+    import sys
+    mod = sys.modules["pvcr_b200.model.S2VTModel"]
+    d, params, g, (B, N, V, H, E, L, Vc) = load_case("s2vt_sched")
+    m = to_cuda(S2VTModel(FixtureGlove(Vc, E), 0.0, H, V, L, precision="bf16x3"), params).train()
+    m.teacher_force_prob = 0.5
+    seq = iter([0.0 if t else 1.0 for t in d["teacher"]])
+    monkeypatch.setattr(mod.random, "random", lambda: next(seq))
+    vid = torch.from_numpy(d["vid"]).cuda()
+    s = torch.from_numpy(d["s"]).cuda()
+    s_len = torch.from_numpy(d["s_len"]).cuda()
+    loss, acc, pred = m.forward_loss(vid, s, s_len)
+    loss.backward()
+    assert abs(loss.item() - float(d["loss"])) < 2e-6 * abs(float(d["loss"]))
+    assert np.array_equal(pred.cpu().numpy(), d["pred"])
+    got = grads_of(m)
+    for k in g:
+        assert relerr(got[k], g[k]) < 1e-4, (k, relerr(got[k], g[k]))
+
+
+def test_greedy_msrvtt_shape_vs_oracle():
+    """cfg5 dims at B=16 with a reduced vocabulary: ids vs the float64 oracle (bit exact up to near-ties)."""
+    from oracle import captioning_oracle as O
+    from oracle import workloads as W
+    from pvcr_b200.model import S2VTAttModel
+    B, N, V, H, E, L, Vc = 16, 40, 2048, 512, 300, 30, 3000
+    p = W.s2vtatt_params(V, H, E, Vc, 91)
+    vid, _, _ = W.make_batch(B, N, V, L, Vc, 92)
+    ids_ref, logits_ref, _ = O.s2vtatt_greedy({k: v.astype(np.float64) for k, v in p.items()}, vid.astype(np.float64),
+                                              Vc - 4, L)
+    m = to_cuda(S2VTAttModel(FixtureGlove(Vc, E), 0.0, H, V, L), p).eval()
+    ids, logits = m.greedy(torch.from_numpy(vid).cuda())
+    assert np.array_equal(ids.cpu().numpy(), ids_ref)
+    assert relerr(logits.cpu().numpy(), logits_ref) < 2e-5
