@@ -137,6 +137,39 @@ int pvcr_s2vt_bwd(const PvcrDims* d, const PvcrS2vtParams* p, const float* vid_f
                   const int64_t* s_in, float* hs, const float* d_hs, PvcrS2vtGrads* g, float* d_frame_scale,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* RationaleNet generator parameters (reference state_dict names under `gen.`, model/RationaleNet.py:26-30). */
+typedef struct {
+  const float* w_ih;   /* rnn.weight_ih_l0          [4H, V] */
+  const float* w_hh;   /* rnn.weight_hh_l0          [4H, H] */
+  const float* b_ih;   /* rnn.bias_ih_l0            [4H]    */
+  const float* b_hh;   /* rnn.bias_hh_l0            [4H]    */
+  const float* w_ih_r; /* rnn.weight_ih_l0_reverse  [4H, V] */
+  const float* w_hh_r; /* rnn.weight_hh_l0_reverse  [4H, H] */
+  const float* b_ih_r; /* rnn.bias_ih_l0_reverse    [4H]    */
+  const float* b_hh_r; /* rnn.bias_hh_l0_reverse    [4H]    */
+  const float* lin_w;  /* linear.weight             [2, 2H] */
+  const float* lin_b;  /* linear.bias               [2]     */
+} PvcrGenParams;
+typedef struct {
+  float *w_ih, *w_hh, *b_ih, *b_hh, *w_ih_r, *w_hh_r, *b_ih_r, *b_hh_r, *lin_w, *lin_b;
+} PvcrGenGrads;
+
+/* Generator.forward (model/RationaleNet.py:32-54) without materialising sel_vid_feats: writes probs [B,N,2],
+ * p1 [B,N] = probs[:,:,1] (pass it as `frame_scale` to pvcr_s2vt(att)_fwd, which computes on vid_feats * p1), and
+ * pen [2] = { calc_brevity_loss(probs), calc_cont_loss(probs) } (train_utils.py:73-95).  noise: [B*N,2] Exp(1) draws
+ * of F.gumbel_softmax (row b*N+n) or NULL to draw them in-kernel from dims->seed; hard != 0 selects the
+ * straight-through one-hot of eval mode.  dims: B, N, V, H, nsplit, dropout_p (Dropout on the LSTM outputs), seed.
+ * _bwd: d_p1 [B,N] (the d_frame_scale output of the caption network's _bwd), d_probs [B,N,2] and g_pen (device [2],
+ * d loss / d pen) are each optional; writes every gradient in g (w_ih and w_ih_r may be the two halves of one
+ * contiguous [8H,V] buffer, which saves a GEMM). */
+size_t pvcr_generator_workspace(const PvcrDims* d);
+int pvcr_generator_fwd(const PvcrDims* d, const PvcrGenParams* p, const float* vid_feats, const float* noise, float tau,
+                       int hard, float* probs, float* p1, float* pen, void* workspace, size_t workspace_bytes,
+                       void* stream);
+int pvcr_generator_bwd(const PvcrDims* d, const PvcrGenParams* p, const float* vid_feats, float tau, const float* d_p1,
+                       const float* d_probs, const float* g_pen, PvcrGenGrads* g, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* Step-wise decoding with word feedback.
  * pvcr_s2vtatt_greedy: eval branch of S2VTAttModel (model/S2VTAttModel.py:172-191): fixed L steps, arg-max fed back,
  *   no early stop.  ids [B,L] int64; logits [B,L,Vc] (NULL: not materialised); alphas [L,B,N] (NULL ok).

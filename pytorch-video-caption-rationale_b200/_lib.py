@@ -94,6 +94,11 @@ SIGNATURES = {
     "pvcr_s2vt_decode_steps_workspace": (c_size, [P(PvcrDims)]),
     "pvcr_s2vt_decode_steps": (c_int, [P(PvcrDims), P(PvcrS2vtParams), c_vp, c_vp, c_i64, c_vp, P(ctypes.c_int32), c_f,
                                        c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
+    "pvcr_generator_workspace": (c_size, [P(PvcrDims)]),
+    "pvcr_generator_fwd": (c_int, [P(PvcrDims), P(PvcrGenParams), c_vp, c_vp, c_f, c_int, c_vp, c_vp, c_vp, c_vp, c_size,
+                                   c_vp]),
+    "pvcr_generator_bwd": (c_int, [P(PvcrDims), P(PvcrGenParams), c_vp, c_f, c_vp, c_vp, c_vp, P(PvcrGenGrads), c_vp,
+                                   c_size, c_vp]),
     "pvcr_vocab_ce_workspace": (c_size, [c_int, c_int, c_int, c_int, c_int, c_f]),
     "pvcr_vocab_ce_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_u64, c_vp,
                                   c_vp, c_vp, c_vp, c_i64, c_vp, c_size, c_vp]),

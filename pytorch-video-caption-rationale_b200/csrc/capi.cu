@@ -25,6 +25,11 @@ int s2vtatt_greedy(const PvcrDims&, const PvcrS2vtAttParams&, const float*, cons
 size_t s2vt_decode_steps_workspace(const PvcrDims& d);
 int s2vt_decode_steps(const PvcrDims&, const PvcrS2vtParams&, const float*, const float*, long long, const long long*,
                       const int*, float, long long*, long long*, float*, void*, size_t, cudaStream_t);
+size_t generator_workspace(const PvcrDims& d);
+int generator_fwd(const PvcrDims&, const PvcrGenParams&, const float*, const float*, float, int, float*, float*, float*,
+                  void*, size_t, cudaStream_t);
+int generator_bwd(const PvcrDims&, const PvcrGenParams&, const float*, float, const float*, const float*, const float*,
+                  PvcrGenGrads&, void*, size_t, cudaStream_t);
 size_t vocab_ce_workspace(int B, int L, int H, int Vc, int nsplit, float dropout_p);
 int vocab_ce_fwd(const float*, const float*, const float*, const long long*, const long long*, int, int, int, int, int,
                  float, unsigned long long, float*, long long*, float*, float*, long long, void*, size_t, cudaStream_t);
@@ -94,6 +99,19 @@ int pvcr_s2vt_decode_steps(const PvcrDims* d, const PvcrS2vtParams* p, const flo
   return s2vt_decode_steps(*d, *p, vid_feats, frame_scale, sos_id, (const long long*)teacher_words, teacher_mask,
                            out_dropout_p, (long long*)ids, (long long*)fed, logits, workspace, workspace_bytes,
                            (cudaStream_t)stream);
+}
+size_t pvcr_generator_workspace(const PvcrDims* d) { return generator_workspace(*d); }
+int pvcr_generator_fwd(const PvcrDims* d, const PvcrGenParams* p, const float* vid_feats, const float* noise, float tau,
+                       int hard, float* probs, float* p1, float* pen, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  return generator_fwd(*d, *p, vid_feats, noise, tau, hard, probs, p1, pen, workspace, workspace_bytes,
+                       (cudaStream_t)stream);
+}
+int pvcr_generator_bwd(const PvcrDims* d, const PvcrGenParams* p, const float* vid_feats, float tau, const float* d_p1,
+                       const float* d_probs, const float* g_pen, PvcrGenGrads* g, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  return generator_bwd(*d, *p, vid_feats, tau, d_p1, d_probs, g_pen, *g, workspace, workspace_bytes,
+                       (cudaStream_t)stream);
 }
 size_t pvcr_vocab_ce_workspace(int B, int L, int H, int Vc, int nsplit, float dropout_p) {
   return vocab_ce_workspace(B, L, H, Vc, nsplit, dropout_p);

@@ -663,8 +663,8 @@ __global__ void __launch_bounds__(256) gumbel_fwd_kernel(GumbelArgs a) {
   const int B = a.B, N = a.N, H = a.H;
   if (warp >= B * N) return;
   const int b = warp / N, n = warp % N;
-  const float* hf = a.hf + ((long long)n * B + b) * H;
-  const float* hb = a.hb + ((long long)n * B + b) * H;
+  const float* hf = a.hf + (long long)n * a.h_ts + (long long)b * a.h_bs;
+  const float* hb = a.hb + (long long)n * a.h_ts + (long long)b * a.h_bs;
   float l0 = 0.f, l1 = 0.f;
   const unsigned long long e0 = (unsigned long long)warp * 2 * H;
   for (int k = lane; k < 2 * H; k += 32) {
@@ -694,6 +694,7 @@ __global__ void __launch_bounds__(256) gumbel_fwd_kernel(GumbelArgs a) {
     } else {
       a.probs[warp * 2] = s0; a.probs[warp * 2 + 1] = s1;
     }
+    if (a.p1) a.p1[warp] = a.probs[warp * 2 + 1];
   }
 }
 __global__ void __launch_bounds__(256) penalties_kernel(const float* probs, int B, int N, float* pen) {
@@ -740,17 +741,18 @@ __global__ void __launch_bounds__(256) gumbel_bwd_rows_kernel(GumbelBwdArgs a) {
   float d0 = a.dprobs ? a.dprobs[warp * 2] : 0.f;
   float d1 = a.dprobs ? a.dprobs[warp * 2 + 1] : 0.f;
   if (a.dp1_sel) d1 += a.dp1_sel[warp];
-  d1 += a.g_brev / (float)B;
-  if (N > 1 && a.g_cont != 0.f) {
-    const float sc = a.g_cont / ((float)B * (float)(N - 1));
+  const float g_brev = a.g_pen ? a.g_pen[0] : 0.f, g_cont = a.g_pen ? a.g_pen[1] : 0.f;
+  d1 += g_brev / (float)B;
+  if (N > 1 && g_cont != 0.f) {
+    const float sc = g_cont / ((float)B * (float)(N - 1));
     if (n > 0) { const float df = y1 - a.y[(warp - 1) * 2 + 1]; d1 += sc * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f)); }
     if (n < N - 1) { const float df = a.y[(warp + 1) * 2 + 1] - y1; d1 -= sc * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f)); }
   }
   const float dot = y0 * d0 + y1 * d1;
   const float dl0 = y0 * (d0 - dot) / a.tau, dl1 = y1 * (d1 - dot) / a.tau;
   if (lane == 0) { a.scratch[warp * 2] = dl0; a.scratch[warp * 2 + 1] = dl1; }
-  float* dhf = a.dhf + ((long long)n * B + b) * H;
-  float* dhb = a.dhb + ((long long)n * B + b) * H;
+  float* dhf = a.dhf + (long long)n * a.h_ts + (long long)b * a.h_bs;
+  float* dhb = a.dhb + (long long)n * a.h_ts + (long long)b * a.h_bs;
   const unsigned long long e0 = (unsigned long long)warp * 2 * H;
   for (int k = lane; k < 2 * H; k += 32) {
     float g = dl0 * a.w[k] + dl1 * a.w[2 * H + k];
@@ -765,7 +767,8 @@ __global__ void __launch_bounds__(256) gumbel_bwd_w_kernel(GumbelBwdArgs a) {
     float g0 = 0.f, g1 = 0.f;
     for (int row = 0; row < B * N; ++row) {
       const int b = row / N, n = row % N;
-      float x = k < H ? a.hf[((long long)n * B + b) * H + k] : a.hb[((long long)n * B + b) * H + k - H];
+      const long long o = (long long)n * a.h_ts + (long long)b * a.h_bs;
+      float x = k < H ? a.hf[o + k] : a.hb[o + k - H];
       if (a.drop.p > 0.f) x *= dropout_scale(a.drop, (unsigned long long)row * 2 * H + k);
       g0 += a.scratch[row * 2] * x;
       g1 += a.scratch[row * 2 + 1] * x;

@@ -133,8 +133,9 @@ int loss_finalize(const float* nll, const long long* pred, const long long* targ
 // ---- RationaleNet generator head ------------------------------------------------------------------------
 // logits = [hf;hb] W^T + b (2 classes) ; y = softmax((logits - log(noise)) / tau) ; probs = hard ? onehot-st : y
 struct GumbelArgs {
-  int B, N, H;                               // hf/hb: [N,B,H] (seq-first, fwd and bwd direction outputs)
-  const float *hf, *hb;
+  int B, N, H;                               // hf/hb: forward / reverse direction LSTM outputs, element (b, n) at
+  const float *hf, *hb;                      //        n*h_ts + b*h_bs
+  long long h_ts, h_bs;
   const float* w;                            // [2, 2H]
   const float* bias;                         // [2]
   const float* noise;                        // [B*N, 2] Exp(1) draws (row = b*N + n), or null => philox
@@ -142,6 +143,7 @@ struct GumbelArgs {
   float tau; int hard;
   Dropout drop;                              // dropout on the LSTM outputs
   float* probs;                              // [B,N,2]
+  float* p1;                                 // [B,N] = probs[:,:,1] (the frame scale; nullable)
   float* y;                                  // [B,N,2] soft sample (saved for backward)
   float* pen;                                // [2]: brevity, continuity losses (unscaled)
 };
@@ -149,11 +151,12 @@ int gumbel_select_fwd(const GumbelArgs& a, cudaStream_t st);
 struct GumbelBwdArgs {
   int B, N, H;
   const float *hf, *hb, *w, *y;
+  long long h_ts, h_bs;
   float tau;
   Dropout drop;
   const float* dp1_sel;                      // [B,N] d(loss)/d(p1) through the feature scaling (nullable)
   const float* dprobs;                       // [B,N,2] external gradient on probs (nullable)
-  float g_brev, g_cont;                      // d(loss)/d(brevity), d(loss)/d(continuity)
+  const float* g_pen;                        // device [2]: d(loss)/d(brevity), d(loss)/d(continuity) (nullable = 0)
   float* dhf; float* dhb;                    // [N,B,H] each
   float* dw;                                 // [2,2H]  (overwritten)
   float* dbias;                              // [2]

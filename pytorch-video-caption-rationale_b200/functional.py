@@ -9,8 +9,8 @@ import itertools
 import torch
 
 from . import _lib
-from ._lib import (ATT_PARAM_FIELDS, S2VT_PARAM_FIELDS, PvcrDims, PvcrS2vtAttGrads, PvcrS2vtAttParams, PvcrS2vtGrads,
-                   PvcrS2vtParams, check, lib, ptr, stream_ptr)
+from ._lib import (ATT_PARAM_FIELDS, GEN_PARAM_FIELDS, S2VT_PARAM_FIELDS, PvcrDims, PvcrGenGrads, PvcrGenParams,
+                   PvcrS2vtAttGrads, PvcrS2vtAttParams, PvcrS2vtGrads, PvcrS2vtParams, check, lib, ptr, stream_ptr)
 
 _seed_counter = itertools.count(1)
 
@@ -144,6 +144,52 @@ class S2VTSequence(torch.autograd.Function):
                                ptr(d_hs), ctypes.byref(gs), ptr(d_fs), ptr(ws), ws.numel(), stream_ptr()),
               "pvcr_s2vt_bwd")
         return (None, None, d_fs, None) + tuple(grads[f] for f in S2VT_SEQ_FIELDS)
+
+
+class GeneratorSelect(torch.autograd.Function):
+    """RationaleNet Generator (model/RationaleNet.py:32-54): (vid_feats, noise?, params) -> probs [B,N,2],
+    p1 [B,N] (the frame scale handed to the caption network instead of materialising vid_feats * p1) and
+    pen [2] = (calc_brevity_loss(probs), calc_cont_loss(probs))."""
+
+    @staticmethod
+    def forward(ctx, cfg, vid, noise, *params):
+        B, N, V = vid.shape
+        tensors = {f: _f32c(p) for f, p in zip(GEN_PARAM_FIELDS, params)}
+        H = tensors["w_hh"].shape[1]
+        dims = make_dims(B, N, V, H, 1, 1, 1, cfg["nsplit"], cfg.get("dropout_p", 0.0), cfg.get("seed", 0))
+        vid_c = _f32c(vid)
+        noise_c = None if noise is None else _f32c(noise)
+        Lb = lib()
+        ws = _ws(Lb.pvcr_generator_workspace(ctypes.byref(dims)), vid.device)
+        probs = torch.empty((B, N, 2), dtype=torch.float32, device=vid.device)
+        p1 = torch.empty((B, N), dtype=torch.float32, device=vid.device)
+        pen = torch.empty((2,), dtype=torch.float32, device=vid.device)
+        ps = _fill_struct(PvcrGenParams(), GEN_PARAM_FIELDS, tensors)
+        check(Lb.pvcr_generator_fwd(ctypes.byref(dims), ctypes.byref(ps), ptr(vid_c), ptr(noise_c), float(cfg["tau"]),
+                                    int(cfg["hard"]), ptr(probs), ptr(p1), ptr(pen), ptr(ws), ws.numel(), stream_ptr()),
+              "pvcr_generator_fwd")
+        ctx.dims, ctx.tau = dims, float(cfg["tau"])
+        ctx.keep = (vid_c, ws, tensors)
+        return probs, p1, pen
+
+    @staticmethod
+    def backward(ctx, d_probs, d_p1, d_pen):
+        vid_c, ws, tensors = ctx.keep
+        dev = vid_c.device
+        H4, V = tensors["w_ih"].shape
+        wih_cat = torch.empty((2 * H4, V), dtype=torch.float32, device=dev)       # both directions: one GEMM
+        grads = {f: torch.empty_like(t) for f, t in tensors.items() if f not in ("w_ih", "w_ih_r")}
+        grads["w_ih"], grads["w_ih_r"] = wih_cat[:H4], wih_cat[H4:]
+        ps = _fill_struct(PvcrGenParams(), GEN_PARAM_FIELDS, tensors)
+        gs = _fill_struct(PvcrGenGrads(), GEN_PARAM_FIELDS, grads)
+        d_probs = None if d_probs is None else _f32c(d_probs)
+        d_p1 = None if d_p1 is None else _f32c(d_p1)
+        d_pen = None if d_pen is None else _f32c(d_pen)
+        Lb = lib()
+        check(Lb.pvcr_generator_bwd(ctypes.byref(ctx.dims), ctypes.byref(ps), ptr(vid_c), ctx.tau, ptr(d_p1),
+                                    ptr(d_probs), ptr(d_pen), ctypes.byref(gs), ptr(ws), ws.numel(), stream_ptr()),
+              "pvcr_generator_bwd")
+        return (None, None, None) + tuple(grads[f] for f in GEN_PARAM_FIELDS)
 
 
 class VocabCrossEntropy(torch.autograd.Function):
