@@ -207,6 +207,18 @@ int pvcr_vocab_ce_bwd(const float* hs, const float* out_w, const int64_t* target
                       float* d_out_w, float* d_out_b, float* lse, int64_t* pred, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* The loss contract on a materialised logits tensor (callers that use the reference's module API and then its
+ * train_utils functions).  pvcr_masked_ce: calc_masked_loss / calc_masked_accuracy / argmax (train_utils.py:37-71,
+ * train.py:38) on logits [B*L, Vc] (row stride ld).  Writes loss3 (as pvcr_vocab_ce_fwd), pred, lse, nll [B*L]; if
+ * dlogits != NULL also dlogits = d loss / d logits * gscale[0] (gscale NULL = 1; in-place on logits is allowed).
+ * pvcr_rationale_penalties(_bwd): calc_brevity_loss / calc_cont_loss (train_utils.py:73-95) on probs [B,N,2] and their
+ * gradient for g_pen = device [2] upstream gradients. */
+int pvcr_masked_ce(const float* logits, int64_t ld, int B, int L, int Vc, const int64_t* target, const int64_t* s_len,
+                   const float* gscale, float* loss3, int64_t* pred, float* lse, float* nll, float* dlogits,
+                   int64_t ld_d, void* stream);
+int pvcr_rationale_penalties(const float* probs, int B, int N, float* pen, void* stream);
+int pvcr_rationale_penalties_bwd(const float* probs, int B, int N, const float* g_pen, float* dprobs, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

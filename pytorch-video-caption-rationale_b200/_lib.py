@@ -99,6 +99,10 @@ SIGNATURES = {
                                    c_vp]),
     "pvcr_generator_bwd": (c_int, [P(PvcrDims), P(PvcrGenParams), c_vp, c_f, c_vp, c_vp, c_vp, P(PvcrGenGrads), c_vp,
                                    c_size, c_vp]),
+    "pvcr_masked_ce": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64,
+                               c_vp]),
+    "pvcr_rationale_penalties": (c_int, [c_vp, c_int, c_int, c_vp, c_vp]),
+    "pvcr_rationale_penalties_bwd": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
     "pvcr_vocab_ce_workspace": (c_size, [c_int, c_int, c_int, c_int, c_int, c_f]),
     "pvcr_vocab_ce_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_u64, c_vp,
                                   c_vp, c_vp, c_vp, c_i64, c_vp, c_size, c_vp]),

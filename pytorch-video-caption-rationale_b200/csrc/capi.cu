@@ -113,6 +113,21 @@ int pvcr_generator_bwd(const PvcrDims* d, const PvcrGenParams* p, const float* v
   return generator_bwd(*d, *p, vid_feats, tau, d_p1, d_probs, g_pen, *g, workspace, workspace_bytes,
                        (cudaStream_t)stream);
 }
+int pvcr_masked_ce(const float* logits, int64_t ld, int B, int L, int Vc, const int64_t* target, const int64_t* s_len,
+                   const float* gscale, float* loss3, int64_t* pred, float* lse, float* nll, float* dlogits,
+                   int64_t ld_d, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  PVCR_TRY(ce_rows(logits, ld, B, L, Vc, (const long long*)target, (const long long*)s_len, lse, nll, (long long*)pred,
+                   dlogits, ld_d, gscale, st));
+  if (loss3) PVCR_TRY(loss_finalize(nll, (const long long*)pred, (const long long*)target, (const long long*)s_len, B, L, loss3, st));
+  return PVCR_OK;
+}
+int pvcr_rationale_penalties(const float* probs, int B, int N, float* pen, void* stream) {
+  return penalties_fwd(probs, B, N, pen, (cudaStream_t)stream);
+}
+int pvcr_rationale_penalties_bwd(const float* probs, int B, int N, const float* g_pen, float* dprobs, void* stream) {
+  return penalties_bwd(probs, B, N, g_pen, dprobs, (cudaStream_t)stream);
+}
 size_t pvcr_vocab_ce_workspace(int B, int L, int H, int Vc, int nsplit, float dropout_p) {
   return vocab_ce_workspace(B, L, H, Vc, nsplit, dropout_p);
 }

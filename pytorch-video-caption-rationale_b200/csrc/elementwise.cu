@@ -716,6 +716,37 @@ __global__ void __launch_bounds__(256) penalties_kernel(const float* probs, int 
     pen[1] = N > 1 ? red[1][0] / ((float)B * (float)(N - 1)) : nanf("");
   }
 }
+__global__ void __launch_bounds__(256) penalties_bwd_kernel(const float* probs, int B, int N, const float* g_pen,
+                                                            float* dprobs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * N) return;
+  const int n = i % N;
+  const float p = probs[i * 2 + 1];
+  float d1 = g_pen[0] / (float)B;
+  if (N > 1) {
+    const float sc = g_pen[1] / ((float)B * (float)(N - 1));
+    if (n > 0) { const float df = p - probs[(i - 1) * 2 + 1]; d1 += sc * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f)); }
+    if (n < N - 1) { const float df = probs[(i + 1) * 2 + 1] - p; d1 -= sc * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f)); }
+  }
+  dprobs[i * 2] = 0.f;
+  dprobs[i * 2 + 1] = d1;
+}
+int penalties_fwd(const float* probs, int B, int N, float* pen, cudaStream_t st) {
+  { LaunchScope ls_(KC_MISC, st);
+  penalties_kernel<<<1, 256, 0, st>>>(probs, B, N, pen);
+  }
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  return PVCR_OK;
+}
+int penalties_bwd(const float* probs, int B, int N, const float* g_pen, float* dprobs, cudaStream_t st) {
+  if (B * N == 0) return PVCR_OK;
+  { LaunchScope ls_(KC_MISC, st);
+  penalties_bwd_kernel<<<cdiv(B * N, 256), 256, 0, st>>>(probs, B, N, g_pen, dprobs);
+  }
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  return PVCR_OK;
+}
+
 int gumbel_select_fwd(const GumbelArgs& a, cudaStream_t st) {
   const int rows = a.B * a.N;
   if (rows == 0) return PVCR_OK;

@@ -163,6 +163,9 @@ struct GumbelBwdArgs {
   float* scratch;                            // [B*N*2] dlogits
 };
 int gumbel_select_bwd(const GumbelBwdArgs& a, cudaStream_t st);
+// pen[2] = { mean_b sum_n p1, mean_{b, n>=1} |p1[b,n] - p1[b,n-1]| } with p1 = probs[:,:,1]; and its gradient
+int penalties_fwd(const float* probs, int B, int N, float* pen, cudaStream_t st);
+int penalties_bwd(const float* probs, int B, int N, const float* g_pen, float* dprobs, cudaStream_t st);
 // dp1[b,n] = sum_v x[b,n,v] * dsel[b,n,v]
 int rowdot(const float* x, const float* dsel, int R, int C, float* out, cudaStream_t st);
 
