@@ -196,13 +196,16 @@ int pvcr_s2vt_decode_steps(const PvcrDims* d, const PvcrS2vtParams* p, const flo
  *   loss3 [3] = { mean_b( sum_l nll*mask / s_len ), #correct under mask, #mask };  pred [B*L] int64 argmax
  *   (first max index);  lse [B*L] log-sum-exp per token.  logits_out (optional, ld elements) receives the
  *   fp32 logits for callers that need the reference's logits tensor; pass target = NULL to only project.
+ * With nsplit = 1 and logits_out = NULL the logits are never materialised: the GEMM epilogue reduces them per tile
+ * (forward) and re-creates them to emit bf16 d logits (backward).
  * _bwd needs the workspace of the matching _fwd untouched; gscale is a device scalar d total / d loss (NULL = 1). */
 size_t pvcr_vocab_ce_workspace(int B, int L, int H, int Vc, int nsplit, float dropout_p);
 int pvcr_vocab_ce_fwd(const float* hs, const float* out_w, const float* out_b, const int64_t* target,
                       const int64_t* s_len, int B, int L, int H, int Vc, int nsplit, float dropout_p, uint64_t seed,
                       float* loss3, int64_t* pred, float* lse, float* logits_out, int64_t ld_logits_out,
                       void* workspace, size_t workspace_bytes, void* stream);
-int pvcr_vocab_ce_bwd(const float* hs, const float* out_w, const int64_t* target, const int64_t* s_len, int B, int L,
+int pvcr_vocab_ce_bwd(const float* hs, const float* out_w, const float* out_b, const int64_t* target,
+                      const int64_t* s_len, int B, int L,
                       int H, int Vc, int nsplit, float dropout_p, uint64_t seed, const float* gscale, float* d_hs,
                       float* d_out_w, float* d_out_b, float* lse, int64_t* pred, void* workspace,
                       size_t workspace_bytes, void* stream);

@@ -33,7 +33,7 @@ int generator_bwd(const PvcrDims&, const PvcrGenParams&, const float*, float, co
 size_t vocab_ce_workspace(int B, int L, int H, int Vc, int nsplit, float dropout_p);
 int vocab_ce_fwd(const float*, const float*, const float*, const long long*, const long long*, int, int, int, int, int,
                  float, unsigned long long, float*, long long*, float*, float*, long long, void*, size_t, cudaStream_t);
-int vocab_ce_bwd(const float*, const float*, const long long*, const long long*, int, int, int, int, int, float,
+int vocab_ce_bwd(const float*, const float*, const float*, const long long*, const long long*, int, int, int, int, int, float,
                  unsigned long long, const float*, float*, float*, float*, float*, long long*, void*, size_t,
                  cudaStream_t);
 }  // namespace pvcr
@@ -139,11 +139,12 @@ int pvcr_vocab_ce_fwd(const float* hs, const float* out_w, const float* out_b, c
                       dropout_p, seed, loss3, (long long*)pred, lse, logits_out, ld_logits_out, workspace,
                       workspace_bytes, (cudaStream_t)stream);
 }
-int pvcr_vocab_ce_bwd(const float* hs, const float* out_w, const int64_t* target, const int64_t* s_len, int B, int L,
+int pvcr_vocab_ce_bwd(const float* hs, const float* out_w, const float* out_b, const int64_t* target,
+                      const int64_t* s_len, int B, int L,
                       int H, int Vc, int nsplit, float dropout_p, uint64_t seed, const float* gscale, float* d_hs,
                       float* d_out_w, float* d_out_b, float* lse, int64_t* pred, void* workspace,
                       size_t workspace_bytes, void* stream) {
-  return vocab_ce_bwd(hs, out_w, (const long long*)target, (const long long*)s_len, B, L, H, Vc, nsplit, dropout_p,
+  return vocab_ce_bwd(hs, out_w, out_b, (const long long*)target, (const long long*)s_len, B, L, H, Vc, nsplit, dropout_p,
                       seed, gscale, d_hs, d_out_w, d_out_b, lse, (long long*)pred, workspace, workspace_bytes,
                       (cudaStream_t)stream);
 }

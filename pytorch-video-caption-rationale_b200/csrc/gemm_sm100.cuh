@@ -108,7 +108,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     const int q = warp & 3;             // TMEM lane quadrant of this warp
     const int row = m0 + q * 32 + lane;
-    epi.begin(row, z);
+    Epi e = epi;                        // per-thread copy: functors may keep running state across chunks
+    e.begin(row, z);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     float v[32];
@@ -116,9 +117,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int c = 0; c < BN; c += 32) {
       if (n0 + c >= gc.N) break;        // warp-uniform
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      epi.chunk(row, n0 + c, z, v);
+      e.chunk(row, n0 + c, z, v);
     }
-    epi.end(row, blockIdx.x, z);
+    e.end(row, blockIdx.x, z);
     tc_fence_before();
   }
   __syncthreads();

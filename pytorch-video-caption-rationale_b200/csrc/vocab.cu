@@ -4,9 +4,19 @@
 // Generic-precision path (any nsplit): logits are materialised once in the workspace (fp32), reduced
 // row-wise, and overwritten in place by d(loss)/d(logits) for the gradient GEMMs.
 #include "../../include/pvcr_b200.h"
+#include <cstdlib>
+
 #include "host.h"
 
 namespace pvcr {
+
+size_t vocab_fused_workspace(int M, int H, int Vc);
+int vocab_fused_fwd(const float*, const float*, const float*, const long long*, const long long*, int, int, int, int,
+                    float, unsigned long long, float*, long long*, float*, void*, size_t, cudaStream_t);
+int vocab_fused_bwd(const float*, const float*, const float*, const long long*, const long long*, int, int, int, int,
+                    float, unsigned long long, const float*, float*, float*, float*, const float*, void*, size_t,
+                    cudaStream_t);
+static bool fused_off() { static const bool off = getenv("PVCR_NO_FUSED_CE") != nullptr; return off; }
 
 struct VocabWs {
   Planes hs_a, wv;
@@ -32,7 +42,8 @@ size_t vocab_ce_workspace(int B, int L, int H, int Vc, int nsplit, float dropout
   size_t peak = 0;
   { size_t m = a.mark(); alloc_planes(a, H, Vc, nsplit); alloc_planes(a, M, Vc, nsplit); peak = a.off; a.release(m); }
   { size_t m = a.mark(); alloc_planes(a, Vc, M, nsplit); alloc_planes(a, H, M, nsplit); if (a.off > peak) peak = a.off; a.release(m); }
-  return peak + 4096;
+  const size_t fused = nsplit == 1 ? vocab_fused_workspace(M, H, Vc) : 0;
+  return (peak > fused ? peak : fused) + 4096;
 }
 
 static Dropout out_dropout(float p, unsigned long long seed) { return Dropout{p, seed, 0x5000000000ull}; }
@@ -43,6 +54,8 @@ int vocab_ce_fwd(const float* hs, const float* wv, const float* bv, const long l
                  long long* pred, float* lse, float* logits_out, long long ld_logits_out, void* ws, size_t ws_bytes,
                  cudaStream_t st) {
   PVCR_REQUIRE(nsplit >= 1 && nsplit <= 3, "vocab_ce_fwd: nsplit=%d", nsplit);
+  if (nsplit == 1 && !logits_out && target && !fused_off())
+    return vocab_fused_fwd(hs, wv, bv, target, s_len, B, L, H, Vc, dropout_p, seed, loss3, pred, lse, ws, ws_bytes, st);
   const int M = B * L;
   Arena a(ws, ws_bytes);
   VocabWs w;
@@ -63,9 +76,12 @@ int vocab_ce_fwd(const float* hs, const float* wv, const float* bv, const long l
 }
 
 // Requires the workspace of the preceding vocab_ce_fwd (logits inside).  gscale: device scalar d(total)/d(loss) or null.
-int vocab_ce_bwd(const float* hs, const float* wv, const long long* target, const long long* s_len, int B, int L, int H,
+int vocab_ce_bwd(const float* hs, const float* wv, const float* bv, const long long* target, const long long* s_len, int B, int L, int H,
                  int Vc, int nsplit, float dropout_p, unsigned long long seed, const float* gscale, float* d_hs,
                  float* d_wv, float* d_bv, float* lse, long long* pred, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (nsplit == 1 && !fused_off())
+    return vocab_fused_bwd(hs, wv, bv, target, s_len, B, L, H, Vc, dropout_p, seed, gscale, d_hs, d_wv, d_bv, lse, ws,
+                           ws_bytes, st);
   const int M = B * L;
   Arena a(ws, ws_bytes);
   VocabWs w;

@@ -212,7 +212,7 @@ class VocabCrossEntropy(torch.autograd.Function):
                                    ptr(loss3), ptr(pred), ptr(lse), None, 0, ptr(ws), ws.numel(), stream_ptr()),
               "pvcr_vocab_ce_fwd")
         ctx.cfg = (B, L, H, Vc, nsplit, p, seed)
-        ctx.keep = (hs_c, w_c, t_c, l_c, ws, lse, pred)
+        ctx.keep = (hs_c, w_c, b_c, t_c, l_c, ws, lse, pred)
         ctx.mark_non_differentiable(pred)
         stats = loss3[1:].clone()
         ctx.mark_non_differentiable(stats)
@@ -221,13 +221,13 @@ class VocabCrossEntropy(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_loss, _d_stats, _d_pred):
         B, L, H, Vc, nsplit, p, seed = ctx.cfg
-        hs_c, w_c, t_c, l_c, ws, lse, pred = ctx.keep
+        hs_c, w_c, b_c, t_c, l_c, ws, lse, pred = ctx.keep
         gscale = _f32c(d_loss).reshape(1)
         d_hs = torch.empty_like(hs_c)
         d_w = torch.empty_like(w_c)
         d_b = torch.empty((Vc,), dtype=torch.float32, device=hs_c.device)
         Lb = lib()
-        check(Lb.pvcr_vocab_ce_bwd(ptr(hs_c), ptr(w_c), ptr(t_c), ptr(l_c), B, L, H, Vc, nsplit, p, seed, ptr(gscale),
+        check(Lb.pvcr_vocab_ce_bwd(ptr(hs_c), ptr(w_c), ptr(b_c), ptr(t_c), ptr(l_c), B, L, H, Vc, nsplit, p, seed, ptr(gscale),
                                    ptr(d_hs), ptr(d_w), ptr(d_b), ptr(lse), ptr(pred), ptr(ws), ws.numel(),
                                    stream_ptr()), "pvcr_vocab_ce_bwd")
         return None, d_hs, d_w, d_b, None, None
