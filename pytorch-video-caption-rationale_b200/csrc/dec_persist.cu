@@ -135,8 +135,10 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
       }
     }
     // ---- P1: [q | gh] = [W_q; W_hh] h_{i-1} -------------------------------------------------------------
+    phase_stamp(p.dbg, i, 0);
     if (i > 0) {
       group_wait(ctr, target);
+      phase_stamp(p.dbg, i, 1);
       load_operand_rows(sX, bsp, 0, p.hs_a + (long long)(i - 1) * p.hs_a_ld, (long long)L * p.hs_a_ld, b0, bsp,
                         b0 + bs, H);
     } else {
@@ -145,6 +147,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
     }
     fence_proxy_async();
     __syncthreads();
+    phase_stamp(p.dbg, i, 2);
     if (tid == 0) {
       tc_fence_after();
       issue_swapped_mma(tmem_d1, smem_u32(sW1), R1, smem_u32(sX), bsp, H, idesc, bar);
@@ -152,6 +155,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
     mbar_wait(bar, phase);
     phase ^= 1;
     tc_fence_after();
+    phase_stamp(p.dbg, i, 3);
     if (tid < 128) tmem_to_smem_cols(tmem_d1, sS1, s1_ld, R1, bsp);
     tc_fence_before();
     __syncthreads();
@@ -164,44 +168,80 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
     }
     group_arrive(ctr);
     target += (unsigned)C;
+    phase_stamp(p.dbg, i, 4);
     // ---- P2: attention of video vb ---------------------------------------------------------------------
     group_wait(ctr, target);
+    phase_stamp(p.dbg, i, 5);
     {
       const float4* q4 = reinterpret_cast<const float4*>(p.q_all + (long long)i * B * p.q_ld + (long long)vb * p.q_ld + d0);
       const float4 qa = __ldcg(q4), qb = __ldcg(q4 + 1);
       const float q8[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+      if (p.dbg && tid == 0 && blockIdx.x == 0 && q8[0] == 123.456f) p.dbg[0] = 0;   // force the load to complete
+      phase_stamp(p.dbg, i, 8);
       const int W = DG < 32 ? DG : 32;
+      float sc[NF];
 #pragma unroll
       for (int m = 0; m < NF; ++m) {
         float s = 0.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 pf = __half22float2(pkr[m][e]);
-          s += v8[2 * e] * fast_tanh(q8[2 * e] + pf.x) + v8[2 * e + 1] * fast_tanh(q8[2 * e + 1] + pf.y);
+          s += v8[2 * e] * tanh_approx(q8[2 * e] + pf.x) + v8[2 * e + 1] * tanh_approx(q8[2 * e + 1] + pf.y);
         }
-        for (int o = W >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        sc[m] = s;
+      }
+      // reduce every frame's partial score over the dims held by the other lanes (levels interleaved over frames)
+      if (W == 32) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int m = 0; m < NF; ++m) sc[m] += __shfl_xor_sync(0xffffffffu, sc[m], o);
+        }
+      } else {
+        for (int o = W >> 1; o > 0; o >>= 1) {
+#pragma unroll
+          for (int m = 0; m < NF; ++m) sc[m] += __shfl_xor_sync(0xffffffffu, sc[m], o);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < NF; ++m) {
         const int n = fg + FG * m;
-        if ((tid % W) == 0 && n < N) sP[n * PW + dg / 32] = s;
+        if ((tid % W) == 0 && n < N) sP[n * PW + dg / 32] = sc[m];
+      }
+      phase_stamp(p.dbg, i, 9);
+      __syncthreads();
+      // softmax over the N frames by warp 0 (lanes over frames), alpha broadcast through shared memory
+      if (warp == 0) {
+        float mx = -INFINITY;
+        for (int n = tid; n < N; n += 32) {
+          float s = 0.f;
+          for (int w = 0; w < PW; ++w) s += sP[n * PW + w];
+          sScore[n] = s;
+          mx = fmaxf(mx, s);
+        }
+        mx = warp_max(mx);
+        float den = 0.f;
+        for (int n = tid; n < N; n += 32) {
+          const float e = __expf(sScore[n] - mx);
+          sScore[n] = e;
+          den += e;
+        }
+        den = warp_sum(den);
+        const float inv = 1.f / den;
+        for (int n = tid; n < N; n += 32) {
+          const float al = sScore[n] * inv;
+          sScore[n] = al;
+          if (video_ok) p.alpha[((long long)i * B + vb) * N + n] = al;
+        }
       }
       __syncthreads();
-      if (tid < N) {
-        float s = 0.f;
-        for (int w = 0; w < PW; ++w) s += sP[tid * PW + w];
-        sScore[tid] = s;
-      }
-      __syncthreads();
-      float mx = -INFINITY;
-      for (int n = 0; n < N; ++n) mx = fmaxf(mx, sScore[n]);
-      float den = 0.f;
-      for (int n = 0; n < N; ++n) den += __expf(sScore[n] - mx);
-      const float inv = 1.f / den;
+      phase_stamp(p.dbg, i, 10);
       float c8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int m = 0; m < NF; ++m) {
         const int n = fg + FG * m;
         if (n < N) {
-          const float a = __expf(sScore[n] - mx) * inv;
-          if (dg == 0 && video_ok) p.alpha[((long long)i * B + vb) * N + n] = a;
+          const float a = sScore[n];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float2 ef = __bfloat1622float2(enr[m][e]);
@@ -211,7 +251,9 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) sC[fg * H + d0 + e] = c8[e];
+      phase_stamp(p.dbg, i, 11);
       __syncthreads();
+      phase_stamp(p.dbg, i, 12);
       if (video_ok) {
         for (int d = tid; d < H; d += DEC_THREADS) {
           float cx = 0.f;
@@ -220,11 +262,14 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
           p.ctx_x[((long long)i * B + vb) * H + d] = __float2bfloat16_rn(cx);
         }
       }
+      phase_stamp(p.dbg, i, 13);
     }
     group_arrive(ctr);
     target += (unsigned)C;
+    phase_stamp(p.dbg, i, 6);
     // ---- P3: gi_c = W_c ctx -----------------------------------------------------------------------------
     group_wait(ctr, target);
+    phase_stamp(p.dbg, i, 7);
     load_operand_rows(sX, bsp, 0, p.ctx_x + (long long)i * B * H, H, b0, bsp, b0 + bs, H);
     fence_proxy_async();
     __syncthreads();
@@ -460,8 +505,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_bwd_kernel(const D
       const float4* q4 = reinterpret_cast<const float4*>(p.q_all + (long long)i * B * p.q_ld + (long long)vb * p.q_ld + d0);
       const float4 qa = __ldg(q4), qb = __ldg(q4 + 1);
       const float q8[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-      if (tid < N) sAl[tid] = __ldg(p.alpha + ((long long)i * B + vb) * N + tid);
       const int W = DG < 32 ? DG : 32;
+      float da[NF];
 #pragma unroll
       for (int m = 0; m < NF; ++m) {
         float s = 0.f;
@@ -470,30 +515,54 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_bwd_kernel(const D
           const float2 ef = __bfloat1622float2(enr[m][e]);
           s += dc8[2 * e] * ef.x + dc8[2 * e + 1] * ef.y;
         }
-        for (int o = W >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        da[m] = s;
+      }
+      if (W == 32) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int m = 0; m < NF; ++m) da[m] += __shfl_xor_sync(0xffffffffu, da[m], o);
+        }
+      } else {
+        for (int o = W >> 1; o > 0; o >>= 1) {
+#pragma unroll
+          for (int m = 0; m < NF; ++m) da[m] += __shfl_xor_sync(0xffffffffu, da[m], o);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < NF; ++m) {
         const int n = fg + FG * m;
-        if ((tid % W) == 0 && n < N) sP[n * PW + dg / 32] = s;
+        if ((tid % W) == 0 && n < N) sP[n * PW + dg / 32] = da[m];
       }
       __syncthreads();
-      if (tid < N) {
-        float s = 0.f;
-        for (int w = 0; w < PW; ++w) s += sP[tid * PW + w];
-        sDa[tid] = s;                       // d alpha_n = dctx . enc_n
+      // d score_n = alpha_n (d alpha_n - sum_m alpha_m d alpha_m): warp 0, lanes over frames
+      if (warp == 0) {
+        float dot = 0.f;
+        for (int n = tid; n < N; n += 32) {
+          float s = 0.f;
+          for (int w = 0; w < PW; ++w) s += sP[n * PW + w];
+          const float al = __ldg(p.alpha + ((long long)i * B + vb) * N + n);
+          sAl[n] = al; sDa[n] = s;
+          dot += al * s;
+        }
+        dot = warp_sum(dot);
+        for (int n = tid; n < N; n += 32) {
+          const float ds = sAl[n] * (sDa[n] - dot);
+          sDa[n] = ds;
+          if (video_ok) p.ds_all[((long long)i * B + vb) * N + n] = ds;
+        }
       }
       __syncthreads();
-      float dot = 0.f;
-      for (int n = 0; n < N; ++n) dot += sAl[n] * sDa[n];
       float dq8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int m = 0; m < NF; ++m) {
         const int n = fg + FG * m;
         if (n < N) {
-          const float ds = sAl[n] * (sDa[n] - dot);          // d score_n
-          if (dg == 0 && video_ok) p.ds_all[((long long)i * B + vb) * N + n] = ds;
+          const float ds = sDa[n];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float2 pf = __half22float2(pkr[m][e]);
-            const float e0 = fast_tanh(q8[2 * e] + pf.x), e1 = fast_tanh(q8[2 * e + 1] + pf.y);
+            const float e0 = tanh_approx(q8[2 * e] + pf.x), e1 = tanh_approx(q8[2 * e + 1] + pf.y);
             dq8[2 * e] += ds * (1.f - e0 * e0);
             dq8[2 * e + 1] += ds * (1.f - e1 * e1);
           }
@@ -585,7 +654,7 @@ __global__ void __launch_bounds__(AG_DIMS * AG_FG) attn_grad_hoisted_kernel(cons
       const int n = fg + AG_FG * m;
       if (n < N) {
         const float ds = sDs[l * N + n];
-        const float e = fast_tanh(q + pk[m]);
+        const float e = tanh_approx(q + pk[m]);
         acc_pk[m] += ds * (1.f - e * e);
         acc_en[m] += sAl[l * N + n] * dc;
         dv += ds * e;
@@ -665,6 +734,7 @@ int dec_persist_fwd(const DecPersistFwd& p0, cudaStream_t st) {
   PVCR_REQUIRE(plan_dec(p0.B, p0.N, p0.H, pl), "dec_persist_fwd: shape B=%d N=%d H=%d not supported", p0.B, p0.N, p0.H);
   DecPersistFwd p = p0;
   p.C = pl.C; p.u = pl.u; p.bsp = pl.bsp;
+  p.dbg = debug_phase_buffer();
   const void* kern = pl.NF == 2 ? (const void*)dec_persist_fwd_kernel<2>
                      : (pl.NF == 5 ? (const void*)dec_persist_fwd_kernel<5> : (const void*)dec_persist_fwd_kernel<10>);
   PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));

@@ -387,7 +387,7 @@ int gru_persist_fwd(const GruSeq& s, cudaStream_t st) {
   p.hp = s.hp; p.hp_ts = s.hp_ts; p.hp_ld = s.hp_ld;
   p.r = s.r; p.z = s.z; p.n = s.n; p.ghn = s.ghn;
   p.counters = s.sync;
-  p.dbg = debug_phase_buffer();
+  p.dbg = getenv("PVCR_PHASE_GRU") ? debug_phase_buffer() : nullptr;
   PVCR_TRY(fill_zero(s.sync, sizeof(unsigned) * 32 * pl.G, st));
   return coop_launch((const void*)gru_persist_fwd_kernel, pl.G * pl.C, pl.smem, &p, st, "gru_persist_fwd", KC_GRU_FWD);
 }

@@ -137,6 +137,7 @@ struct DecPersistFwd {
   bf16* hs_a; long long hs_a_ld;            // rows b*L + i
   float *r, *z, *n, *ghn;                   // [L][B,H]
   unsigned* counters;
+  long long* dbg;                           // phase timestamps (tuning aid, nullable)
 };
 struct DecPersistBwd {
   int L, B, N, H, C, u, bsp;

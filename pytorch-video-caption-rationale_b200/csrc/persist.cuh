@@ -19,7 +19,7 @@ constexpr int PERSIST_THREADS = 256;
 
 // Optional in-kernel phase timing (tuning aid): when non-null, CTA 0 / thread 0 of a persistent kernel stores
 // clock64() at up to PHASE_SLOTS points of every step into this device buffer ([step][slot]).
-constexpr int PHASE_SLOTS = 8;
+constexpr int PHASE_SLOTS = 16;
 long long* debug_phase_buffer();       // null unless pvcr_debug_phase_timing(1) was called
 
 #ifdef __CUDACC__

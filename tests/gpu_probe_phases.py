@@ -22,16 +22,23 @@ which = sys.argv[1] if len(sys.argv) > 1 else "enc_fwd"
 from pvcr_b200 import functional as F_
 with torch.no_grad():
     F_.S2VTAttSequence.forward(F_.ManualCtx(), m._cfg(True), vid, None, m._shifted(s, B), *m._seq_params())
-steps = N
-buf = (ctypes.c_longlong * (steps * 8))()
+gru = os.environ.get("PVCR_PHASE_GRU") is not None
+steps = N if gru else L
+buf = (ctypes.c_longlong * (steps * 16))()
 _lib.check(Lb.pvcr_debug_phase_read(buf, steps), "read")
-a = np.array(buf[:]).reshape(steps, 8)
-a2 = a[:, [0, 1, 7, 2, 3, 4, 5, 6]]
+a = np.array(buf[:]).reshape(steps, 16)
+if gru:
+    a2 = a[:, [0, 1, 7, 2, 3, 4, 5, 6]]
+    names = ["wait", "load X (ld+st)", "fence+sync", "mma", "tmem->smem", "gates+stores", "arrive"]
+else:
+    a2 = np.concatenate([a[:, [0, 1, 2, 3, 4, 5, 8, 9, 10, 11, 12, 13, 6, 7]], np.roll(a[:, 0:1], -1, axis=0)], axis=1)[:-1]
+    names = ["P1 wait h", "P1 load X", "P1 mma", "P1 t2s+q write+arrive", "P2 wait q", "P2 q load", "P2 tanh+shfl",
+             "P2 sync+score+sync", "P2 softmax+ctx partial", "P2 sync", "P2 ctx reduce+write", "P2 arrive",
+             "P3 wait ctx", "P3 load+mma+P4 gates+arrive"]
 d = np.diff(a2, axis=1)[5:]           # skip the first steps
-names = ["wait", "load X (ld+st)", "fence+sync", "mma", "tmem->smem", "gates+stores", "arrive"]
 clk = 1.965e3  # cycles per us at max clock
 print("per-step cycles (median over steps 5..):")
 for i, n in enumerate(names):
     print("  %-14s %8.0f cyc  %.2f us" % (n, np.median(d[:, i]), np.median(d[:, i]) / clk))
-tot = np.median(a[6:, 6] - a[5:-1, 6])
+tot = np.median(a[6:, 0] - a[5:-1, 0])
 print("  step total     %8.0f cyc  %.2f us" % (tot, tot / clk))
