@@ -224,15 +224,19 @@ def run_ours(args):
     ms_step = ms_total / args.steps
 
     # end to end through the public API: pinned host inputs copied in, loss read back, every step
+    # Every step copies ITS inputs from pinned host memory and reads ITS loss back; the copy of step k+1 is issued
+    # before step k's loss is read (input prefetch on a copy stream), as a pinned-memory DataLoader would do.
     def e2e_step():
-        v = vid_h.to(dev, non_blocking=True)
-        t = s_h.to(dev, non_blocking=True)
-        tl = s_len_h.to(dev, non_blocking=True)
-        return step(v, t, tl).item()
+        graphed.step_prefetched()
+        reducer.reduce()
+        graphed.prefetch(vid_h, s_h, s_len_h)
+        return graphed.static_out[0].item()
 
+    graphed.prefetch(vid_h, s_h, s_len_h)
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps) / args.steps
+    torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     h2d = vid_h.numel() * 4 + s_h.numel() * 8 + s_len_h.numel() * 8
 

@@ -25,10 +25,39 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             out = model.train_step_grads(*self.static_in)
         self.static_out = tuple(o.detach() if torch.is_tensor(o) else o for o in out)
+        # input pipeline: the next batch is copied host -> device into staging buffers on a side stream while the
+        # current step computes (what a pinned-memory DataLoader with non_blocking copies gives the reference loop)
+        self._copy_stream = torch.cuda.Stream()
+        self._staging = tuple(torch.empty_like(t) for t in self.static_in)
+        self._staged = None
+        self._handover = None
 
     def __call__(self, *inputs):
         for dst, src in zip(self.static_in, inputs):
             if src is not dst:
                 dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
+
+    def prefetch(self, *inputs):
+        """Start copying the NEXT step's inputs (pinned host tensors) to the device; returns immediately."""
+        cs = self._copy_stream
+        if self._handover is not None:
+            cs.wait_event(self._handover)                 # staging buffers must have been handed over, nothing more
+        with torch.cuda.stream(cs):
+            for dst, src in zip(self._staging, inputs):
+                dst.copy_(src, non_blocking=True)
+            self._staged = torch.cuda.Event()
+            self._staged.record(cs)
+
+    def step_prefetched(self):
+        """Run one step on the inputs handed to the latest prefetch()."""
+        assert self._staged is not None, "call prefetch() first"
+        torch.cuda.current_stream().wait_event(self._staged)
+        for dst, src in zip(self.static_in, self._staging):
+            dst.copy_(src, non_blocking=True)              # device-to-device hand-over (tens of microseconds)
+        self._handover = torch.cuda.Event()
+        self._handover.record(torch.cuda.current_stream())
+        self._staged = None
         self.graph.replay()
         return self.static_out
