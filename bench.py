@@ -164,7 +164,7 @@ def run_ours(args):
     with torch.no_grad():
         model.decoder.embedding.weight.normal_(0.0, 0.4)
     model = model.to(dev).train()
-    reducer = GradAllReducer(model)
+    reducer = GradAllReducer(model, flat=True, early=model.early_grad_params())   # grads land in the buckets
 
     gen = torch.Generator().manual_seed(1000 + rank)
     vid_h = torch.randn(B, N, V, generator=gen)
@@ -185,13 +185,12 @@ def run_ours(args):
     for _ in range(2):                      # eager warm-up (module load, attribute setup) before the capture
         model.train_step_grads(vid, s, s_len)
     L_.pvcr_prof_reset()
-    graphed = GraphedTrainStep(model, (vid, s, s_len), warmup=0)      # one fwd+bwd captured into a CUDA graph
+    # one fwd+bwd captured as CUDA graph(s); with N > 1 the vocabulary gradients' all-reduce overlaps the backward
+    graphed = GraphedTrainStep(model, (vid, s, s_len), warmup=0, reducer=reducer if world > 1 else None)
     launches_per_step = sum(v[0] for v in _lib.prof_read().values())
 
     def step(v, t, tl):
-        loss = graphed(v, t, tl)[0]         # copies inputs into the static buffers, replays the graph
-        reducer.reduce()                    # NCCL all-reduce of the gradients (no-op at world size 1)
-        return loss
+        return graphed(v, t, tl)[0]         # copies inputs, replays the graph(s), all-reduces the gradients
 
     def barrier():
         if world > 1:
@@ -228,7 +227,6 @@ def run_ours(args):
     # before step k's loss is read (input prefetch on a copy stream), as a pinned-memory DataLoader would do.
     def e2e_step():
         graphed.step_prefetched()
-        reducer.reduce()
         graphed.prefetch(vid_h, s_h, s_len_h)
         return graphed.static_out[0].item()
 

@@ -45,6 +45,18 @@ def _fill_struct(struct, fields, tensors):
     return struct
 
 
+def _grad_buffers(cfg, key, fields, tensors):
+    """Gradient output buffers: caller-provided (cfg[key][field], e.g. views into a flat all-reduce bucket) or fresh."""
+    given = cfg.get(key) or {}
+    out = {}
+    for f in fields:
+        t = tensors[f]
+        g = given.get(f)
+        ok = g is not None and g.shape == t.shape and g.dtype == torch.float32 and g.is_contiguous() and g.device == t.device
+        out[f] = g if ok else torch.empty_like(t)
+    return out
+
+
 class ManualCtx:
     """Stand-in for the autograd context when the Functions below are chained by hand (tape-free train step)."""
 
@@ -82,6 +94,7 @@ class S2VTAttSequence(torch.autograd.Function):
                                   ptr(alphas), ptr(ws), ws.numel(), stream_ptr()), "pvcr_s2vtatt_fwd")
         ctx.dims = dims
         ctx.need_fg = need_fg
+        ctx.cfg = cfg
         ctx.keep = (vid_c, fs_c, s_c, hs, ws, tensors)
         ctx.mark_non_differentiable(alphas)
         return hs, alphas
@@ -90,7 +103,7 @@ class S2VTAttSequence(torch.autograd.Function):
     def backward(ctx, d_hs, _d_alphas):
         vid_c, fs_c, s_c, hs, ws, tensors = ctx.keep
         d_hs = _f32c(d_hs)
-        grads = {f: torch.empty_like(t) for f, t in tensors.items()}
+        grads = _grad_buffers(ctx.cfg, "grad_out", ATT_SEQ_FIELDS, tensors)
         d_fs = torch.empty_like(fs_c) if ctx.need_fg else None
         ps = _fill_struct(PvcrS2vtAttParams(), ATT_SEQ_FIELDS, tensors)
         gs = _fill_struct(PvcrS2vtAttGrads(), ATT_SEQ_FIELDS, grads)
@@ -128,6 +141,7 @@ class S2VTSequence(torch.autograd.Function):
                                ws.numel(), stream_ptr()), "pvcr_s2vt_fwd")
         ctx.dims = dims
         ctx.need_fg = need_fg
+        ctx.cfg = cfg
         ctx.keep = (vid_c, fs_c, s_c, hs, ws, tensors)
         return hs
 
@@ -135,7 +149,7 @@ class S2VTSequence(torch.autograd.Function):
     def backward(ctx, d_hs):
         vid_c, fs_c, s_c, hs, ws, tensors = ctx.keep
         d_hs = _f32c(d_hs)
-        grads = {f: torch.empty_like(t) for f, t in tensors.items()}
+        grads = _grad_buffers(ctx.cfg, "grad_out", S2VT_SEQ_FIELDS, tensors)
         d_fs = torch.empty_like(fs_c) if ctx.need_fg else None
         ps = _fill_struct(PvcrS2vtParams(), S2VT_SEQ_FIELDS, tensors)
         gs = _fill_struct(PvcrS2vtGrads(), S2VT_SEQ_FIELDS, grads)
@@ -212,6 +226,7 @@ class VocabCrossEntropy(torch.autograd.Function):
                                    ptr(loss3), ptr(pred), ptr(lse), None, 0, ptr(ws), ws.numel(), stream_ptr()),
               "pvcr_vocab_ce_fwd")
         ctx.cfg = (B, L, H, Vc, nsplit, p, seed)
+        ctx.grad_out = cfg.get("vocab_grad_out") or {}
         ctx.keep = (hs_c, w_c, b_c, t_c, l_c, ws, lse, pred)
         ctx.mark_non_differentiable(pred)
         stats = loss3[1:].clone()
@@ -224,8 +239,8 @@ class VocabCrossEntropy(torch.autograd.Function):
         hs_c, w_c, b_c, t_c, l_c, ws, lse, pred = ctx.keep
         gscale = _f32c(d_loss).reshape(1)
         d_hs = torch.empty_like(hs_c)
-        d_w = torch.empty_like(w_c)
-        d_b = torch.empty((Vc,), dtype=torch.float32, device=hs_c.device)
+        gb = _grad_buffers({"g": ctx.grad_out}, "g", ("out_w", "out_b"), {"out_w": w_c, "out_b": b_c})
+        d_w, d_b = gb["out_w"], gb["out_b"]
         Lb = lib()
         check(Lb.pvcr_vocab_ce_bwd(ptr(hs_c), ptr(w_c), ptr(b_c), ptr(t_c), ptr(l_c), B, L, H, Vc, nsplit, p, seed, ptr(gscale),
                                    ptr(d_hs), ptr(d_w), ptr(d_b), ptr(lse), ptr(pred), ptr(ws), ws.numel(),

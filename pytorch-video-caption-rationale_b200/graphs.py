@@ -10,9 +10,12 @@ import torch
 
 
 class GraphedTrainStep:
-    def __init__(self, model, example_inputs, warmup=3):
-        """example_inputs: tuple of CUDA tensors, the arguments of model.train_step_grads (fixes shapes/dtypes)."""
+    def __init__(self, model, example_inputs, warmup=3, reducer=None):
+        """example_inputs: tuple of CUDA tensors, the arguments of model.train_step_grads (fixes shapes/dtypes).
+        reducer: a parallel.GradAllReducer(flat=True, early=model.early_grad_params()); the step is then captured as
+        two graphs split where the early gradients are final, and their all-reduce overlaps the second graph."""
         self.model = model
+        self.reducer = reducer
         self.static_in = tuple(t.clone() for t in example_inputs)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -22,8 +25,22 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            out = model.train_step_grads(*self.static_in)
+        self.graph2 = None
+        if reducer is not None and hasattr(model, "train_step_stages"):
+            with torch.no_grad():
+                gen = model.train_step_stages(*self.static_in)
+                with torch.cuda.graph(self.graph):
+                    next(gen)
+                self.graph2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph2, pool=self.graph.pool()):
+                    try:
+                        next(gen)
+                        raise RuntimeError("train_step_stages must yield exactly once")
+                    except StopIteration as done:
+                        out = done.value
+        else:
+            with torch.cuda.graph(self.graph):
+                out = model.train_step_grads(*self.static_in)
         self.static_out = tuple(o.detach() if torch.is_tensor(o) else o for o in out)
         # input pipeline: the next batch is copied host -> device into staging buffers on a side stream while the
         # current step computes (what a pinned-memory DataLoader with non_blocking copies gives the reference loop)
@@ -36,8 +53,19 @@ class GraphedTrainStep:
         for dst, src in zip(self.static_in, inputs):
             if src is not dst:
                 dst.copy_(src, non_blocking=True)
-        self.graph.replay()
+        self._replay()
         return self.static_out
+
+    def _replay(self):
+        self.graph.replay()
+        if self.graph2 is not None:
+            self.reducer.begin(0)              # all-reduce of the early bucket overlaps the rest of the backward
+            self.graph2.replay()
+            for i in range(1, len(self.reducer.buckets)):
+                self.reducer.begin(i)
+            self.reducer.finish()
+        elif self.reducer is not None:
+            self.reducer.reduce()
 
     def prefetch(self, *inputs):
         """Start copying the NEXT step's inputs (pinned host tensors) to the device; returns immediately."""
@@ -59,5 +87,5 @@ class GraphedTrainStep:
         self._handover = torch.cuda.Event()
         self._handover.record(torch.cuda.current_stream())
         self._staged = None
-        self.graph.replay()
+        self._replay()
         return self.static_out

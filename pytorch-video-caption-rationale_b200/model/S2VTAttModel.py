@@ -106,15 +106,17 @@ class S2VTAttModel(nn.Module):
         loss, stats, pred = F_.VocabCrossEntropy.apply(cfg, hs, lin.weight, lin.bias, s, s_len)
         return loss, stats[0] / stats[1], pred
 
-    @torch.no_grad()
-    def train_step_grads(self, vid_feats, s, s_len, frame_scale=None):
-        """Tape-free fwd+bwd of run_iter (train.py:37-40 + loss.backward()): chains the C-ABI forward and backward
-        entry points by hand and (over)writes ``param.grad`` of every parameter.  Stream-ordered and free of autograd
-        state, hence capturable in a CUDA graph (pvcr_b200.graphs.GraphedTrainStep).  Returns (loss, acc, pred)."""
+    def train_step_stages(self, vid_feats, s, s_len, frame_scale=None):
+        """Generator form of the tape-free fwd+bwd: yields once when the vocabulary-projection gradients (out_w, out_b:
+        ~47 % of all gradient bytes) are final, so a data-parallel caller can start their all-reduce while the rest of
+        the backward runs; returns (loss, acc, pred)."""
         assert self.training and s is not None
         cfg = self._cfg(True)
         params = self._seq_params()
         lin = self.decoder.pred_linear[1]
+        # existing .grad tensors (e.g. views into the all-reduce buckets of parallel.GradAllReducer) are written in place
+        cfg["grad_out"] = {f: p.grad for f, p in zip(F_.ATT_SEQ_FIELDS, params) if p.grad is not None}
+        cfg["vocab_grad_out"] = {"out_w": lin.weight.grad, "out_b": lin.bias.grad}
         c1, c2 = F_.ManualCtx(), F_.ManualCtx()
         hs, alphas = F_.S2VTAttSequence.forward(c1, cfg, vid_feats, frame_scale, self._shifted(s, vid_feats.shape[0]),
                                                 *params)
@@ -122,12 +124,30 @@ class S2VTAttModel(nn.Module):
         loss, stats, pred = F_.VocabCrossEntropy.forward(c2, cfg, hs, lin.weight, lin.bias, s, s_len)
         one = torch.ones((), dtype=torch.float32, device=hs.device)
         _, d_hs, d_w, d_b, _, _ = F_.VocabCrossEntropy.backward(c2, one, None, None)
+        lin.weight.grad, lin.bias.grad = d_w, d_b
+        yield "vocab_grads"
         grads = F_.S2VTAttSequence.backward(c1, d_hs, None)
         for p, g in zip(params, grads[4:]):
             p.grad = g
-        lin.weight.grad, lin.bias.grad = d_w, d_b
         self.last_frame_scale_grad = grads[2]
         return loss, stats[0] / stats[1], pred
+
+    def early_grad_params(self):
+        """Parameters whose gradients are complete at the first yield of train_step_stages."""
+        lin = self.decoder.pred_linear[1]
+        return [lin.bias, lin.weight]
+
+    @torch.no_grad()
+    def train_step_grads(self, vid_feats, s, s_len, frame_scale=None):
+        """Tape-free fwd+bwd of run_iter (train.py:37-40 + loss.backward()): chains the C-ABI forward and backward
+        entry points by hand and (over)writes ``param.grad`` of every parameter.  Stream-ordered and free of autograd
+        state, hence capturable in a CUDA graph (pvcr_b200.graphs.GraphedTrainStep).  Returns (loss, acc, pred)."""
+        gen = self.train_step_stages(vid_feats, s, s_len, frame_scale)
+        try:
+            while True:
+                next(gen)
+        except StopIteration as done:
+            return done.value
 
     @torch.no_grad()
     def greedy(self, vid_feats, frame_scale=None):

@@ -99,6 +99,8 @@ class S2VTModel(nn.Module):
         cfg = self._cfg(True)
         params = self._seq_params()
         lin = self.linear[1]
+        cfg["grad_out"] = {f: p.grad for f, p in zip(F_.S2VT_SEQ_FIELDS, params) if p.grad is not None}
+        cfg["vocab_grad_out"] = {"out_w": lin.weight.grad, "out_b": lin.bias.grad}
         s_in = self._fed_words(vid_feats, s, frame_scale, cfg)
         c1, c2 = F_.ManualCtx(), F_.ManualCtx()
         hs = F_.S2VTSequence.forward(c1, cfg, vid_feats, frame_scale, s_in, *params)

@@ -24,13 +24,20 @@ class GradAllReducer:
     produces gradients: vocabulary projection and embedding first), so ``reduce()`` can be issued per bucket on a
     side stream while later buckets are still being computed."""
 
-    def __init__(self, module, bucket_mb=64, group=None):
+    def __init__(self, module, bucket_mb=64, group=None, flat=False, early=None):
+        """flat=True pre-allocates one flat fp32 buffer per bucket and installs views of it as ``param.grad``; the
+        tape-free train steps write gradients straight into those views, so ``reduce()`` all-reduces in place
+        without gather / scatter copies."""
         self.params = [p for p in module.parameters() if p.requires_grad]
         self.group = group
+        early = list(early or [])           # parameters whose gradients are complete first: bucket 0 on its own
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.buckets = []
+        self.buckets = [early] if early else []
+        early_ids = {id(p) for p in early}
         cur, cur_bytes = [], 0
         for p in reversed(self.params):
+            if id(p) in early_ids:
+                continue
             cur.append(p)
             cur_bytes += p.numel() * 4
             if cur_bytes >= bucket_mb * (1 << 20):
@@ -39,20 +46,57 @@ class GradAllReducer:
         if cur:
             self.buckets.append(cur)
         self._flat = [None] * len(self.buckets)
+        self._views = None
+        self._pending = []
+        if flat:
+            self._views = []
+            for i, bucket in enumerate(self.buckets):
+                buf = torch.zeros(sum(p.numel() for p in bucket), dtype=torch.float32, device=bucket[0].device)
+                self._flat[i] = buf
+                off, views = 0, []
+                for p in bucket:
+                    v = buf[off:off + p.numel()].view_as(p)
+                    p.grad = v
+                    views.append(v)
+                    off += p.numel()
+                self._views.append(views)
+
+    def _in_place(self, i):
+        return self._views is not None and all(p.grad is not None and p.grad.data_ptr() == v.data_ptr()
+                                               for p, v in zip(self.buckets[i], self._views[i]))
+
+    def begin(self, i):
+        """Start the all-reduce of bucket i (asynchronous: later kernels on the current stream overlap with it)."""
+        if self.world == 1:
+            return
+        assert self._in_place(i), "begin()/finish() need flat=True buckets written in place"
+        self._pending.append((i, dist.all_reduce(self._flat[i], op=dist.ReduceOp.SUM, group=self.group, async_op=True)))
+
+    def finish(self):
+        for i, h in self._pending:
+            h.wait()
+            self._flat[i].div_(self.world)
+        self._pending = []
 
     def reduce(self):
         if self.world == 1:
             return
-        handles = []
+        handles, in_place = [], []
         for i, bucket in enumerate(self.buckets):
-            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
-            flat = torch.cat([g.reshape(-1).float() for g in grads])
-            self._flat[i] = flat
+            in_place.append(self._in_place(i))
+            if in_place[i]:
+                flat = self._flat[i]
+            else:
+                grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
+                flat = torch.cat([g.reshape(-1).float() for g in grads])
+                self._flat[i] = flat
             handles.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         for i, (bucket, h) in enumerate(zip(self.buckets, handles)):
             h.wait()
             flat = self._flat[i]
             flat.div_(self.world)
+            if in_place[i]:
+                continue
             off = 0
             for p in bucket:
                 n = p.numel()
