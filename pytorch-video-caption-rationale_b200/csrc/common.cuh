@@ -175,6 +175,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 // tanh via one fast exponential: absolute error ~1e-7 (used inside the attention score, where only the absolute
 // error matters); saturates correctly for |x| large.
 __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+// 2^x on the special-function unit (ex2.approx: 2 ulp; ex2(-inf) = 0)
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // single-MUFU hardware tanh (max relative error ~2^-11)
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;

@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "gemm_sm100.cuh"
 
@@ -95,6 +96,9 @@ int gemm_store(const OperandView& a, const OperandView& b, const GemmCoords& gc,
                cudaStream_t stream) {
   EpiStore epi{C, ldc, c_zstride, bias, bias_zstride, accumulate, gc.M, gc.N};
   const long long tiles256 = (long long)cdiv(gc.N, 256) * cdiv(gc.M, GEMM_BM) * grid_z;
+  static const bool no_persist = getenv("PVCR_NO_PERSIST_GEMM") != nullptr;
+  if (gc.N >= 256 && tiles256 >= 64 && !no_persist)
+    return launch_gemm_tn_persistent<256, 4, EpiStore>(a, b, gc, grid_z, epi, stream);
   if (gc.N >= 256 && tiles256 >= 148) return launch_gemm_tn<256, 4, EpiStore>(a, b, gc, grid_z, epi, stream);
   return launch_gemm_tn<128, 3, EpiStore>(a, b, gc, grid_z, epi, stream);
 }

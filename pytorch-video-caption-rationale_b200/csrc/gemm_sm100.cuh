@@ -16,6 +16,7 @@ namespace pvcr {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;   // 64 bf16 = 128 bytes = one swizzle row
 constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_PERSIST_THREADS = 320;   // TMA warp + MMA warp + 8 epilogue warps (two per TMEM lane quadrant)
 
 template <int BN, int STAGES>
 struct GemmSmem {
@@ -129,6 +130,130 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// Persistent variant: one CTA per SM loops over output tiles (m fastest, so CTAs running side by side share the
+// B tile in L2); the TMA producer runs ahead across tile boundaries through the same shared-memory ring, the
+// accumulator is double-buffered in TMEM (2 x BN columns), and the four epilogue warps drain tile i while the
+// MMA warp already accumulates tile i+1.
+template <int BN, int STAGES, class Epi>
+__global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1)
+gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                          GemmCoords gc, int tiles_m, int tiles_n, int num_tiles, Epi epi) {
+  using SM = GemmSmem<BN, STAGES>;
+  static_assert(2 * BN <= 512, "two accumulators must fit the 512 TMEM columns");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = gc.K / GEMM_BK;
+  const int per_z = tiles_m * tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 8);              // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;                                    // running k-block counter across tiles
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int z = t / per_z, r = t - z * per_z;
+        const int m0 = (r % tiles_m) * GEMM_BM, n0 = (r / tiles_m) * BN;
+        const int az = gc.a_z0 + z * gc.a_zmul, bz = gc.b_z0 + z * gc.b_zmul;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], SM::STAGE_BYTES);
+          uint8_t* sa = smem + s * SM::STAGE_BYTES;
+          tma_load_3d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m0, az);
+          tma_load_3d(sa + SM::A_BYTES, &tmB, &full_bar[s], kb * GEMM_BK, n0, bz);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+      int it = 0, ti = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+        const int acc = ti & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((ti >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
+          const uint64_t da = umma_desc_k128(sa);
+          const uint64_t db = umma_desc_k128(sa + SM::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k)
+            umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    // warp w drains TMEM lanes 32*(w%4).. of the column half (w-2)/4: two warps per SM sub-partition hide each
+    // other's dependency stalls in the epilogue arithmetic
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    constexpr int HALF = BN / 2;
+    int ti = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+      const int z = t / per_z, r = t - z * per_z;
+      const int m0 = (r % tiles_m) * GEMM_BM, n0 = (r / tiles_m) * BN;
+      const int acc = ti & 1;
+      const int row = m0 + q * 32 + lane;
+      Epi e = epi;
+      e.begin(row, z);
+      mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);
+      tc_fence_after();
+      float v[32];
+#pragma unroll 1
+      for (int c = half * HALF; c < (half + 1) * HALF; c += 32) {
+        if (n0 + c >= gc.N) break;
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
+        e.chunk(row, n0 + c, z, v);
+      }
+      e.end(row, (r / tiles_m) * 2 + half, z);      // part index: (N tile, column half)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
 // Plain store epilogue: C = acc (+ bias[n]) (+ C).  fp32 output, arbitrary ldc.
 struct EpiStore {
   float* C;
@@ -199,6 +324,36 @@ int launch_gemm_tn(const OperandView& a, const OperandView& b, const GemmCoords&
   {
     LaunchScope ls_(KC_GEMM, stream, 2.0 * gc.M * gc.N * (double)gc.K * grid_z);
     kern<<<grid, GEMM_THREADS, SM::TOTAL, stream>>>(ta, tb, gc, epi);
+  }
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  return PVCR_OK;
+}
+
+template <int BN, int STAGES, class Epi>
+int launch_gemm_tn_persistent(const OperandView& a, const OperandView& b, const GemmCoords& gc, int grid_z,
+                              const Epi& epi, cudaStream_t stream) {
+  using SM = GemmSmem<BN, STAGES>;
+  PVCR_REQUIRE(gc.K > 0 && gc.K % GEMM_BK == 0, "gemm: K=%d must be a positive multiple of %d", gc.K, GEMM_BK);
+  PVCR_REQUIRE(gc.M > 0 && gc.N > 0 && grid_z > 0, "gemm: empty problem M=%d N=%d z=%d", gc.M, gc.N, grid_z);
+  CUtensorMap ta, tb;
+  PVCR_TRY(make_tensor_map(&ta, a, gc.K, GEMM_BM));
+  PVCR_TRY(make_tensor_map(&tb, b, gc.K, BN));
+  auto kern = gemm_tn_persistent_kernel<BN, STAGES, Epi>;
+  static bool attr_set = false;
+  static int sms = 0;
+  if (!attr_set) {
+    PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL + 64));
+    int dev = 0;
+    PVCR_CUDA_CHECK(cudaGetDevice(&dev));
+    PVCR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    attr_set = true;
+  }
+  const int tiles_m = cdiv(gc.M, GEMM_BM), tiles_n = cdiv(gc.N, BN);
+  const long long num_tiles = (long long)tiles_m * tiles_n * grid_z;
+  const int grid = (int)(num_tiles < sms ? num_tiles : sms);
+  {
+    LaunchScope ls_(KC_GEMM, stream, 2.0 * gc.M * gc.N * (double)gc.K * grid_z);
+    kern<<<grid, GEMM_PERSIST_THREADS, SM::TOTAL + 64, stream>>>(ta, tb, gc, tiles_m, tiles_n, (int)num_tiles, epi);
   }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;

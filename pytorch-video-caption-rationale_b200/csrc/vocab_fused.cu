@@ -11,61 +11,99 @@
 
 namespace pvcr {
 
-constexpr int CE_BN = 128;
+constexpr int CE_BN = 256;
+
+// Work in the log2 domain: y = (acc + bias) * log2(e), so that exp(x - m) = ex2(y - m2) costs FADD + MUFU.
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
 
 struct EpiCeFwd {
-  const float* bias; const long long* target;
-  float *pmax, *psum, *tgt; int* pidx;
-  int M, N, ntiles;
-  float m_run, s_run; int i_run; long long t;
-  __device__ __forceinline__ void begin(int row, int) {
-    m_run = -INFINITY; s_run = 0.f; i_run = 0x7fffffff;
-    t = row < M ? target[row] : -1;
-  }
+  const float* bias;
+  float *pmax, *psum; int* pidx;
+  int M, N, nparts;
+  float m_run, s_run; int i_run;
+  __device__ __forceinline__ void begin(int, int) { m_run = -INFINITY; s_run = 0.f; i_run = 0x7fffffff; }
   __device__ __forceinline__ void chunk(int row, int col0, int, float (&v)[32]) {
-    float cm = -INFINITY; int ci = 0x7fffffff;
+    const bool full = col0 + 32 <= N;
+    float cm = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int col = col0 + j;
-      float x = -INFINITY;
-      if (col < N) {
-        x = v[j] + __ldg(bias + col);
-        if (col == t) tgt[row] = x;
+    for (int j4 = 0; j4 < 8; ++j4) {
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (full) b4 = __ldg(reinterpret_cast<const float4*>(bias + col0) + j4);
+      else {
+        const int c = col0 + j4 * 4;
+        if (c < N) b4.x = __ldg(bias + c);
+        if (c + 1 < N) b4.y = __ldg(bias + c + 1);
+        if (c + 2 < N) b4.z = __ldg(bias + c + 2);
+        if (c + 3 < N) b4.w = __ldg(bias + c + 3);
       }
-      v[j] = x;
-      if (x > cm) { cm = x; ci = col; }
-    }
-    if (cm > m_run) { s_run *= __expf(m_run - cm); m_run = cm; i_run = ci; }
-    float s = 0.f;
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-    for (int j = 0; j < 32; ++j) s += __expf(v[j] - m_run);       // exp(-inf) = 0 for the padding columns
-    s_run += s;
+      for (int k = 0; k < 4; ++k) {
+        const int j = j4 * 4 + k;
+        float y = (v[j] + bb[k]) * LOG2E;
+        if (!full && col0 + j >= N) y = -INFINITY;
+        v[j] = y;
+        cm = fmaxf(cm, y);
+      }
+    }
+    if (cm > m_run) {                       // new running maximum (rare after the first chunks): locate its column
+      int ci = 0;
+#pragma unroll
+      for (int j = 31; j >= 0; --j)
+        if (v[j] == cm) ci = j;             // smallest index among ties
+      s_run *= fast_ex2(m_run - cm);
+      m_run = cm; i_run = col0 + ci;
+    }
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) { s0 += fast_ex2(v[j] - m_run); s1 += fast_ex2(v[j + 1] - m_run); }
+    s_run += s0 + s1;
   }
-  __device__ __forceinline__ void end(int row, int tile, int) {
+  __device__ __forceinline__ void end(int row, int part, int) {
     if (row < M) {
-      const long long o = (long long)row * ntiles + tile;
+      const long long o = (long long)row * nparts + part;
       pmax[o] = m_run; psum[o] = s_run; pidx[o] = i_run;
     }
   }
 };
 
 struct EpiCeBwd {
-  const float* bias; const long long* target; const float *lse, *roww;
+  const float* bias; const long long* target; const float *lse2, *roww;      // lse2 = lse * log2(e)
   bf16* D; long long ldD; bf16* DT; long long ldDT;
   int M, N, Mp;
-  float l, w; long long t;
+  float l2, w; int t;
   __device__ __forceinline__ void begin(int row, int) {
-    l = 0.f; w = 0.f; t = -1;
-    if (row < M) { l = lse[row]; w = roww[row]; t = target[row]; }
+    l2 = 0.f; w = 0.f; t = -1;
+    if (row < M) { l2 = lse2[row]; w = roww[row]; t = (int)target[row]; }
   }
   __device__ __forceinline__ void chunk(int row, int col0, int, float (&v)[32]) {
-    __align__(16) bf16 o[32];
+    const bool full = col0 + 32 <= N;
+    const int tj = t - col0;
+    __align__(16) __nv_bfloat162 o[16];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int col = col0 + j;
-      float d = 0.f;
-      if (col < N && w != 0.f) d = (__expf(v[j] + __ldg(bias + col) - l) - (col == t ? 1.f : 0.f)) * w;
-      o[j] = __float2bfloat16_rn(d);
+    for (int j4 = 0; j4 < 8; ++j4) {
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (full) b4 = __ldg(reinterpret_cast<const float4*>(bias + col0) + j4);
+      else {
+        const int c = col0 + j4 * 4;
+        if (c < N) b4.x = __ldg(bias + c);
+        if (c + 1 < N) b4.y = __ldg(bias + c + 1);
+        if (c + 2 < N) b4.z = __ldg(bias + c + 2);
+        if (c + 3 < N) b4.w = __ldg(bias + c + 3);
+      }
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+      float d[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = j4 * 4 + k;
+        float pr = fast_ex2((v[j] + bb[k]) * LOG2E - l2);
+        if (j == tj) pr -= 1.f;
+        d[k] = pr * w;
+        if (!full && col0 + j >= N) d[k] = 0.f;
+      }
+      o[j4 * 2] = __floats2bfloat162_rn(d[0], d[1]);
+      o[j4 * 2 + 1] = __floats2bfloat162_rn(d[2], d[3]);
     }
     if (row < M) {
       uint4* dst = reinterpret_cast<uint4*>(D + (long long)row * ldD + col0);
@@ -73,13 +111,39 @@ struct EpiCeBwd {
       for (int j = 0; j < 4; ++j) dst[j] = reinterpret_cast<const uint4*>(o)[j];
     }
     if (row < Mp) {
+      const bf16* ob = reinterpret_cast<const bf16*>(o);
+      bf16* dt = DT + (long long)col0 * ldDT + row;
+      if (full) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < N) DT[(long long)(col0 + j) * ldDT + row] = o[j];
+        for (int j = 0; j < 32; ++j) dt[(long long)j * ldDT] = ob[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < N) dt[(long long)j * ldDT] = ob[j];
+      }
     }
   }
   __device__ __forceinline__ void end(int, int, int) {}
 };
+
+// target logit per row (log2 domain): tgt2[row] = (hs_bf16[row] . W_bf16[target[row]] + b[target[row]]) * log2(e)
+__global__ void __launch_bounds__(256) target_logit_kernel(const bf16* hs, long long ld_hs, const bf16* wv, long long ld_w,
+                                                           const float* bias, const long long* target, int M, int H,
+                                                           float* tgt2) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const long long t = target[row];
+  const bf16* a = hs + (long long)row * ld_hs;
+  const bf16* b = wv + t * ld_w;
+  float s = 0.f;
+  for (int k = lane * 2; k < H; k += 64) {
+    const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + k));
+    const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(b + k));
+    s += x.x * y.x + x.y * y.y;
+  }
+  s = warp_sum(s);
+  if (lane == 0) tgt2[row] = (s + bias[t]) * LOG2E;
+}
 
 // one warp per row: combine the per-tile partials
 __global__ void __launch_bounds__(256) ce_finalize_rows_kernel(const float* pmax, const float* psum, const int* pidx,
@@ -101,20 +165,22 @@ __global__ void __launch_bounds__(256) ce_finalize_rows_kernel(const float* pmax
   }
   float s = 0.f;
   for (int k = lane; k < ntiles; k += 32)
-    s += psum[(long long)row * ntiles + k] * expf(pmax[(long long)row * ntiles + k] - m);
+    s += psum[(long long)row * ntiles + k] * exp2f(pmax[(long long)row * ntiles + k] - m);
   s = warp_sum(s);
   if (lane == 0) {
-    const float lse = m + logf(s);
-    lse_out[row] = lse;
-    nll_out[row] = lse - tgt[row];
+    const float lse2 = m + log2f(s);              // log2 domain (see EpiCeFwd)
+    lse_out[row] = lse2 * LN2;
+    nll_out[row] = (lse2 - tgt[row]) * LN2;
     pred_out[row] = mi == 0x7fffffff ? 0 : mi;
   }
 }
 
 // w[row] = (l < s_len[b]) / (s_len[b] * B) * gscale
-__global__ void row_weights_kernel(const long long* s_len, int B, int L, const float* gscale, float* w) {
+__global__ void row_weights_kernel(const long long* s_len, int B, int L, const float* gscale, float* w,
+                                   const float* lse, float* lse2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * L) return;
+  lse2[i] = lse[i] * LOG2E;
   const int b = i / L, l = i % L;
   const long long len = s_len[b];
   w[i] = (l < len ? 1.f / ((float)len * (float)B) : 0.f) * (gscale ? gscale[0] : 1.f);
@@ -147,7 +213,7 @@ struct FusedWs {
   int ntiles;
 };
 static void carve_fused(Arena& a, int M, int H, int Vc, FusedWs& w) {
-  w.ntiles = cdiv(Vc, CE_BN);
+  w.ntiles = 2 * cdiv(Vc, CE_BN);        // partials per (N tile, column half) of the persistent GEMM epilogue
   w.hs_a = alloc_planes(a, M, H, 1);
   w.wv = alloc_planes(a, Vc, H, 1);
   w.pmax = a.alloc<float>((size_t)M * w.ntiles); w.psum = a.alloc<float>((size_t)M * w.ntiles);
@@ -155,7 +221,7 @@ static void carve_fused(Arena& a, int M, int H, int Vc, FusedWs& w) {
   w.tgt = a.alloc<float>(M); w.nll = a.alloc<float>(M); w.roww = a.alloc<float>(M);
   w.wvT = alloc_planes(a, H, Vc, 1);
   w.hsT = alloc_planes(a, H, M, 1);
-  w.ldD = (long long)w.ntiles * CE_BN;
+  w.ldD = (long long)cdiv(Vc, CE_BN) * CE_BN;
   w.ldDT = w.hsT.Kp;
   w.D = a.alloc<bf16>((size_t)M * w.ldD);
   w.DT = a.alloc<bf16>((size_t)Vc * w.ldDT);
@@ -179,11 +245,17 @@ int vocab_fused_fwd(const float* hs, const float* wv, const float* bv, const lon
   if (a.failed) { set_last_error("vocab_fused_fwd: workspace too small (%zu < %zu)", ws_bytes, a.off); return PVCR_ERR_WORKSPACE; }
   PVCR_TRY(stage(hs, H, M, H, w.hs_a, 0, nullptr, fused_out_dropout(dropout_p, seed), st));
   PVCR_TRY(prep_weight(wv, H, Vc, H, w.wv, st));
+  {
+    LaunchScope ls_(KC_LOSS, st);
+    target_logit_kernel<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(w.hs_a.ptr, w.hs_a.ld, w.wv.ptr, w.wv.ld, bv, target,
+                                                                      M, H, w.tgt);
+  }
+  PVCR_CUDA_CHECK(cudaGetLastError());
   EpiCeFwd epi{};
-  epi.bias = bv; epi.target = target; epi.pmax = w.pmax; epi.psum = w.psum; epi.tgt = w.tgt; epi.pidx = w.pidx;
-  epi.M = M; epi.N = Vc; epi.ntiles = w.ntiles;
+  epi.bias = bv; epi.pmax = w.pmax; epi.psum = w.psum; epi.pidx = w.pidx;
+  epi.M = M; epi.N = Vc; epi.nparts = w.ntiles;
   GemmCoords gc{M, Vc, (int)w.hs_a.ld, 0, 0, 0, 0};
-  PVCR_TRY((launch_gemm_tn<CE_BN, 3, EpiCeFwd>(w.hs_a.view(), w.wv.view(), gc, 1, epi, st)));
+  PVCR_TRY((launch_gemm_tn_persistent<CE_BN, 4, EpiCeFwd>(w.hs_a.view(), w.wv.view(), gc, 1, epi, st)));
   {
     LaunchScope ls_(KC_LOSS, st);
     ce_finalize_rows_kernel<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(w.pmax, w.psum, w.pidx, w.tgt, M, w.ntiles, lse,
@@ -204,17 +276,17 @@ int vocab_fused_bwd(const float* hs, const float* wv, const float* bv, const lon
   const Dropout dr = fused_out_dropout(dropout_p, seed);
   {
     LaunchScope ls_(KC_LOSS, st);
-    row_weights_kernel<<<cdiv(M, 256), 256, 0, st>>>(s_len, B, L, gscale, w.roww);
+    row_weights_kernel<<<cdiv(M, 256), 256, 0, st>>>(s_len, B, L, gscale, w.roww, lse, w.nll);
   }
   PVCR_CUDA_CHECK(cudaGetLastError());
   // recompute the logits tile by tile; the epilogue emits bf16 dlogits (row-major and transposed)
   EpiCeBwd epi{};
-  epi.bias = bv; epi.target = target; epi.lse = lse; epi.roww = w.roww;
+  epi.bias = bv; epi.target = target; epi.lse2 = w.nll; epi.roww = w.roww;     // w.nll reused: lse * log2(e)
   epi.D = w.D; epi.ldD = w.ldD; epi.DT = w.DT; epi.ldDT = w.ldDT; epi.M = M; epi.N = Vc; epi.Mp = (int)w.ldDT;
   if (w.ldD > Vc)      // chunks lying entirely past Vc are skipped by the GEMM epilogue: their K-padding must read 0
     PVCR_CUDA_CHECK(cudaMemset2DAsync(w.D + Vc, sizeof(bf16) * w.ldD, 0, sizeof(bf16) * (w.ldD - Vc), M, st));
   GemmCoords gc{M, Vc, (int)w.hs_a.ld, 0, 0, 0, 0};
-  PVCR_TRY((launch_gemm_tn<CE_BN, 3, EpiCeBwd>(w.hs_a.view(), w.wv.view(), gc, 1, epi, st)));
+  PVCR_TRY((launch_gemm_tn_persistent<CE_BN, 4, EpiCeBwd>(w.hs_a.view(), w.wv.view(), gc, 1, epi, st)));
   // d hs = dlogits W  (K = Vc padded to 64; the padding columns of D are zeros, of W^T planes too)
   PVCR_TRY(prep_weight_T(wv, H, Vc, H, w.wvT, 0, 1, st));
   {
