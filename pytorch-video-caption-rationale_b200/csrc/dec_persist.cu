@@ -622,69 +622,80 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_bwd_kernel(const D
   }
 }
 
-// One CTA per (video, 64-dim tile): thread = (dim, frame group); frames fg + 4m.
-constexpr int AG_DIMS = 64, AG_FG = 4, AG_NF = 20;
+// One CTA per (video, 64-dim tile): thread = (dim, frame group); frames fg + 4m.  alpha, d score, q and dctx of all L
+// steps are staged in shared memory first, so the L x frames inner loops run without global-memory latency.
+constexpr int AG_DIMS = 64, AG_FG = 4;
+template <int NF>
 __global__ void __launch_bounds__(AG_DIMS * AG_FG) attn_grad_hoisted_kernel(const AttnGradArgs a) {
   extern __shared__ float ag_sm[];
   const int L = a.L, B = a.B, N = a.N, H = a.H;
-  float* sAl = ag_sm;                 // [L][N]
-  float* sDs = sAl + L * N;           // [L][N]
-  float* sV = sDs + L * N;            // [AG_FG][AG_DIMS]
-  const int b = blockIdx.x, d = blockIdx.y * AG_DIMS + (threadIdx.x % AG_DIMS), fg = threadIdx.x / AG_DIMS;
+  float* sAl = ag_sm;                       // [L][N]
+  float* sDs = sAl + L * N;                 // [L][N]
+  float* sQ = sDs + L * N;                  // [L][AG_DIMS]
+  float* sDc = sQ + L * AG_DIMS;            // [L][AG_DIMS]
+  float* sV = sDc + L * AG_DIMS;            // [AG_FG][AG_DIMS]
+  const int b = blockIdx.x, dl = threadIdx.x % AG_DIMS, d = blockIdx.y * AG_DIMS + dl, fg = threadIdx.x / AG_DIMS;
   for (int i = threadIdx.x; i < L * N; i += blockDim.x) {
     const int l = i / N, n = i - l * N;
     sAl[i] = a.alpha[((long long)l * B + b) * N + n];
     sDs[i] = a.ds[((long long)l * B + b) * N + n];
   }
-  __syncthreads();
+  for (int i = threadIdx.x; i < L * AG_DIMS; i += blockDim.x) {
+    const int l = i / AG_DIMS, dd = blockIdx.y * AG_DIMS + (i - l * AG_DIMS);
+    sQ[i] = dd < H ? a.q[(long long)l * B * a.q_ld + (long long)b * a.q_ld + dd] : 0.f;
+    sDc[i] = dd < H ? a.dctx[((long long)l * B + b) * H + dd] : 0.f;
+  }
   const bool ok = d < H;
-  float pk[AG_NF], acc_pk[AG_NF], acc_en[AG_NF];
+  float pk[NF], acc_pk[NF], acc_en[NF];
 #pragma unroll
-  for (int m = 0; m < AG_NF; ++m) {
+  for (int m = 0; m < NF; ++m) {
     const int n = fg + AG_FG * m;
     pk[m] = (ok && n < N) ? a.pk[((long long)b * N + n) * H + d] : 0.f;
     acc_pk[m] = 0.f; acc_en[m] = 0.f;
   }
+  __syncthreads();
   float dv = 0.f;
   for (int l = 0; l < L; ++l) {
-    const float q = ok ? a.q[(long long)l * B * a.q_ld + (long long)b * a.q_ld + d] : 0.f;
-    const float dc = ok ? a.dctx[((long long)l * B + b) * H + d] : 0.f;
+    const float q = sQ[l * AG_DIMS + dl], dc = sDc[l * AG_DIMS + dl];
+    const float* dsl = sDs + l * N + fg;
+    const float* all = sAl + l * N + fg;
 #pragma unroll
-    for (int m = 0; m < AG_NF; ++m) {
-      const int n = fg + AG_FG * m;
-      if (n < N) {
-        const float ds = sDs[l * N + n];
+    for (int m = 0; m < NF; ++m) {
+      if (fg + AG_FG * m < N) {
+        const float ds = dsl[AG_FG * m];
         const float e = tanh_approx(q + pk[m]);
         acc_pk[m] += ds * (1.f - e * e);
-        acc_en[m] += sAl[l * N + n] * dc;
+        acc_en[m] += all[AG_FG * m] * dc;
         dv += ds * e;
       }
     }
   }
   const float vd = ok ? a.v[d] : 0.f;
 #pragma unroll
-  for (int m = 0; m < AG_NF; ++m) {
+  for (int m = 0; m < NF; ++m) {
     const int n = fg + AG_FG * m;
     if (ok && n < N) {
       a.dpk[((long long)b * N + n) * H + d] = acc_pk[m] * vd;
       a.denc[((long long)b * N + n) * H + d] = acc_en[m];
     }
   }
-  sV[fg * AG_DIMS + (threadIdx.x % AG_DIMS)] = dv;
+  sV[fg * AG_DIMS + dl] = dv;
   __syncthreads();
   if (fg == 0 && ok) {
     float s = 0.f;
-    for (int f = 0; f < AG_FG; ++f) s += sV[f * AG_DIMS + threadIdx.x];
+    for (int f = 0; f < AG_FG; ++f) s += sV[f * AG_DIMS + dl];
     a.dv_part[(long long)b * H + d] = s;
   }
 }
 
 int attn_grad_hoisted(const AttnGradArgs& a, cudaStream_t st) {
-  PVCR_REQUIRE(a.N <= AG_FG * AG_NF, "attn_grad_hoisted: N=%d > %d frames", a.N, AG_FG * AG_NF);
-  const size_t smem = ((size_t)2 * a.L * a.N + AG_FG * AG_DIMS) * sizeof(float);
+  PVCR_REQUIRE(a.N <= AG_FG * 20, "attn_grad_hoisted: N=%d > %d frames", a.N, AG_FG * 20);
+  const size_t smem = ((size_t)2 * a.L * a.N + (size_t)2 * a.L * AG_DIMS + AG_FG * AG_DIMS) * sizeof(float);
   PVCR_REQUIRE(smem <= 48 * 1024, "attn_grad_hoisted: L=%d N=%d needs %zu B of shared memory", a.L, a.N, smem);
+  const dim3 grid(a.B, cdiv(a.H, AG_DIMS));
   LaunchScope ls_(KC_ATTN, st);
-  attn_grad_hoisted_kernel<<<dim3(a.B, cdiv(a.H, AG_DIMS)), AG_DIMS * AG_FG, smem, st>>>(a);
+  if (a.N <= AG_FG * 10) attn_grad_hoisted_kernel<10><<<grid, AG_DIMS * AG_FG, smem, st>>>(a);
+  else attn_grad_hoisted_kernel<20><<<grid, AG_DIMS * AG_FG, smem, st>>>(a);
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
 }

@@ -115,6 +115,49 @@ __global__ void transpose_split_kernel(const float* __restrict__ in, long long l
   }
 }
 
+// Fast path (single plane, no gather / dropout): 64 x 64 tiles, 16-byte loads along the input rows, fp32 tile in
+// shared memory, 16-byte bf16 stores along the output rows.
+__global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __restrict__ in, long long ld_in, int R, int C,
+                                                             bf16* __restrict__ out, long long ld_out, int r_off,
+                                                             int r_end, const float* __restrict__ row_scale) {
+  __shared__ float tile[64][65];
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64, t = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + (t >> 4) + 16 * i, c = c0 + (t & 15) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < R) {
+      const float* src = in + (long long)r * ld_in + c;
+      if (c + 3 < C) v = __ldg(reinterpret_cast<const float4*>(src));
+      else {
+        if (c < C) v.x = __ldg(src);
+        if (c + 1 < C) v.y = __ldg(src + 1);
+        if (c + 2 < C) v.z = __ldg(src + 2);
+      }
+      if (row_scale) { const float s = __ldg(row_scale + r); v.x *= s; v.y *= s; v.z *= s; v.w *= s; }
+    }
+    float* d = &tile[(t >> 4) + 16 * i][(t & 15) * 4];
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int cl = (t >> 3) + 32 * i, rl = (t & 7) * 8;
+    const int c = c0 + cl, r = r0 + rl;
+    if (c < C && r < r_end) {
+      __align__(16) __nv_bfloat162 o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = __floats2bfloat162_rn(tile[rl + 2 * k][cl], tile[rl + 2 * k + 1][cl]);
+      bf16* dst = out + (long long)c * ld_out + r_off + r;
+      if (r + 8 <= r_end) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
+      else {
+        const bf16* ob = reinterpret_cast<const bf16*>(o);
+        for (int k = 0; k < 8 && r + k < r_end; ++k) dst[k] = ob[k];
+      }
+    }
+  }
+}
+
 int transpose_split(const float* in, long long ld_in, int R, int C, bf16* out, long long ld_out, int Rp, int r_off,
                     int zero_pad, int nsplit, int role_b, const long long* row_ids, const float* row_scale,
                     cudaStream_t st, Dropout drop) {
@@ -122,6 +165,16 @@ int transpose_split(const float* in, long long ld_in, int R, int C, bf16* out, l
   if (C == 0) return PVCR_OK;
   const int r_end = zero_pad ? Rp - r_off : R;       // rows >= R read as zero
   if (r_end == 0) return PVCR_OK;
+  const bool fast = nsplit == 1 && !row_ids && drop.p <= 0.f && ld_in % 4 == 0 && r_off % 8 == 0 && ld_out % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (fast) {
+    dim3 grid(cdiv(r_end, 64), cdiv(C, 64));
+    { LaunchScope ls_(KC_STAGE, st);
+    transpose_cast_kernel<<<grid, 256, 0, st>>>(in, ld_in, R, C, out, ld_out, r_off, r_end, row_scale);
+    }
+    PVCR_CUDA_CHECK(cudaGetLastError());
+    return PVCR_OK;
+  }
   dim3 grid(cdiv(r_end, 32), cdiv(C, 32));
   { LaunchScope ls_(KC_STAGE, st);
   transpose_split_kernel<<<grid, dim3(32, 8), 0, st>>>(in, ld_in, R, C, out, ld_out, Rp, r_off, r_end, nsplit, role_b,
