@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_bwd_kernel(const D
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_a = *tmem_slot, tmem_b = tmem_a + (uint32_t)bsp;
-  const uint32_t idesc = umma_idesc_bf16(128, bsp);
+  const uint32_t idesc = umma_idesc_bf16(64, bsp);      // 64-row A tiles: the slices hold u <= 32 useful rows
   const uint32_t aWA = smem_u32(sWA), aWB = smem_u32(sWB), aX0 = smem_u32(sX0), aX1 = smem_u32(sX1);
 
   // attention residency (as in the forward kernel)
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_bwd_kernel(const D
     }
     mbar_wait(&bars[2], phA); phA ^= 1;
     tc_fence_after();
-    if (tid < 128) tmem_to_smem_cols(tmem_a, sSA, s_ld, u, bsp);
+    if (tid < 128) tmem64_to_smem_cols(tmem_a, sSA, s_ld, u, bsp);
     tc_fence_before();
     __syncthreads();
     {
@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_bwd_kernel(const D
     mbar_wait(&bars[1], ph1); ph1 ^= 1;      // chunk dghn retired (X1 free for the next step)
     mbar_wait(&bars[0], ph0); ph0 ^= 1;
     tc_fence_after();
-    if (tid < 128) tmem_to_smem_cols(tmem_b, sSB, s_ld, u, bsp);
+    if (tid < 128) tmem64_to_smem_cols(tmem_b, sSB, s_ld, u, bsp);
     tc_fence_before();
     __syncthreads();
 #pragma unroll

@@ -132,6 +132,20 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// M = 64 variant (tcgen05.mma with a 64-row A tile, cta_group::1): the accumulator row r lives in TMEM lane
+// 32*(r/16) + r%16, i.e. every warp quadrant holds 16 rows in its first 16 lanes.
+__device__ __forceinline__ void tmem64_to_smem_cols(uint32_t tmem_base, float* S, int s_ld, int nrows, int ncols) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, row = warp * 16 + lane;
+  float v[16];
+  for (int c0 = 0; c0 < ncols; c0 += 16) {
+    tmem_ld_32x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+    if (lane < 16 && row < nrows) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) S[(c0 + j) * s_ld + row] = v[j];
+    }
+  }
+}
+
 // Move the accumulator D[row = TMEM lane, col < ncols] to shared memory as S[col * s_ld + row] for rows < nrows.
 // Executed by warps 0..3 (thread == lane).  ncols is a multiple of 16.
 __device__ __forceinline__ void tmem_to_smem_cols(uint32_t tmem_base, float* S, int s_ld, int nrows, int ncols) {
