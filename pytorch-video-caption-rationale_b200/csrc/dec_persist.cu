@@ -139,12 +139,14 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
     if (i > 0) {
       group_wait(ctr, target);
       phase_stamp(p.dbg, i, 1);
-      load_operand_rows(sX, bsp, 0, p.hs_a + (long long)(i - 1) * p.hs_a_ld, (long long)L * p.hs_a_ld, b0, bsp,
-                        b0 + bs, H);
+      load_operand_rows_async(sX, bsp, 0, p.hs_a + (long long)(i - 1) * p.hs_a_ld, (long long)L * p.hs_a_ld, b0, bsp,
+                              b0 + bs, H);
     } else {
-      load_operand_rows(sX, bsp, 0, p.enc_a + (long long)(N - 1) * p.enc_ld, (long long)N * p.enc_ld, b0, bsp,
-                        b0 + bs, H);
+      load_operand_rows_async(sX, bsp, 0, p.enc_a + (long long)(N - 1) * p.enc_ld, (long long)N * p.enc_ld, b0, bsp,
+                              b0 + bs, H);
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     fence_proxy_async();
     __syncthreads();
     phase_stamp(p.dbg, i, 2);
@@ -270,7 +272,9 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
     // ---- P3: gi_c = W_c ctx -----------------------------------------------------------------------------
     group_wait(ctr, target);
     phase_stamp(p.dbg, i, 7);
-    load_operand_rows(sX, bsp, 0, p.ctx_x + (long long)i * B * H, H, b0, bsp, b0 + bs, H);
+    load_operand_rows_async(sX, bsp, 0, p.ctx_x + (long long)i * B * H, H, b0, bsp, b0 + bs, H);
+    cp_async_commit();
+    cp_async_wait<0>();
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
@@ -326,8 +330,13 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
 //                        B4  dh_{i-1} += W_q^T dq                                         (tcgen05), carry in registers
 // d enc / d proj_key / d v do not feed back into the recurrence and are accumulated after the sweep by
 // attn_grad_hoisted from the saved alpha, d score, dctx and q.
+// In the two MMA phases (B2, B4) warp 7 switches to the MMA-issue role while warps 0..6 stream the K-chunks of the
+// exchange buffer into shared memory, so the next chunk's load overlaps the tcgen05 issue of the current one (chunk
+// hand-over through the mbarriers xready[] / xfree[]); in all other phases the 8 warps work alike.
+constexpr int DEC_BWD_THREADS = DEC_THREADS;
+constexpr int DEC_LOADERS = DEC_THREADS - 32;
 template <int NF>
-__global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_bwd_kernel(const DecPersistBwd p) {
+__global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(const DecPersistBwd p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int H = p.H, u = p.u, C = p.C, bsp = p.bsp, N = p.N, L = p.L, B = p.B, KBH = H >> 6;
@@ -344,7 +353,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_bwd_kernel(const D
   float* sAl = sDa + N;                     // [N] alpha
   float* sC = sAl + N;                      // [FG][H]
   uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sC + (size_t)FG * H) + 15) & ~uintptr_t(7));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int g = blockIdx.x / C, c = blockIdx.x % C;
@@ -356,6 +365,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_bwd_kernel(const D
   load_operand_rows(sWB, u, 0, p.wcatT, p.wcatT_ld, j0, u, H, 4 * H);
   if (tid == 0) {
     mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    mbar_init(&bars[3], DEC_LOADERS); mbar_init(&bars[4], DEC_LOADERS);      // xready[0], xready[1]
     fence_barrier_init();
   }
   const uint32_t ncols = 2 * bsp <= 32 ? 32u : (2 * bsp <= 64 ? 64u : (2 * bsp <= 128 ? 128u : 256u));
@@ -405,12 +415,15 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_bwd_kernel(const D
   float dhc[DEC_ITEMS];
 #pragma unroll
   for (int k = 0; k < DEC_ITEMS; ++k) dhc[k] = 0.f;
-  uint32_t ph0 = 0, ph1 = 0, phA = 0;
+  uint32_t n0 = 0, n1 = 0, phA = 0;       // completions of xfree[0] / xfree[1] consumed so far
+  uint32_t r0 = 0, r1 = 0;                 // completions of xready[0] / xready[1] consumed (MMA role)
+  const bool mma_role = (warp == 7);
   unsigned target = 0;
   const long long xrow = (long long)5 * H;
 
   for (int i = L - 1; i >= 0; --i) {
     bf16* xg = p.xg + (size_t)(i & 1) * B * xrow;
+    phase_stamp(p.dbg, L - 1 - i, 0);
     // ---- B1: gate gradients ---------------------------------------------------------------------------------
 #pragma unroll
     for (int k = 0; k < DEC_ITEMS; ++k) {
@@ -438,52 +451,53 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_bwd_kernel(const D
         }
       }
     }
+    phase_stamp(p.dbg, L - 1 - i, 1);
     group_arrive(ctr);
     target += (unsigned)C;
     // ---- B2: dctx = W_c^T [drp|dzp|dnp] ; dh part = W_hh^T [drp|dzp|dghn] -------------------------------------
     group_wait(ctr, target);
-    // chunk drp -> X0 : A k-chunk 0, B k-chunk 1
-    load_operand_rows(sX0, bsp, 0, xg + H, xrow, b0, bsp, b0 + bs, H);
-    fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_mma_chunk(tmem_a, aWA, u, 0, aX0, bsp, H, idesc, false);
-      issue_mma_chunk(tmem_b, aWB, u, KBH, aX0, bsp, H, idesc, false);
-      umma_commit(&bars[0]);
+    phase_stamp(p.dbg, L - 1 - i, 2);
+    if (mma_role) {
+      if ((tid & 31) == 0) {
+        mbar_wait(&bars[3], r0 & 1); ++r0; tc_fence_after();                  // drp  -> X0
+        issue_mma_chunk(tmem_a, aWA, u, 0, aX0, bsp, H, idesc, false);
+        issue_mma_chunk(tmem_b, aWB, u, KBH, aX0, bsp, H, idesc, false);
+        umma_commit(&bars[0]);
+        mbar_wait(&bars[4], r1 & 1); ++r1; tc_fence_after();                  // dzp  -> X1
+        issue_mma_chunk(tmem_a, aWA, u, KBH, aX1, bsp, H, idesc, true);
+        issue_mma_chunk(tmem_b, aWB, u, 2 * KBH, aX1, bsp, H, idesc, true);
+        umma_commit(&bars[1]);
+        mbar_wait(&bars[3], r0 & 1); ++r0; tc_fence_after();                  // dnp  -> X0, completes dctx
+        issue_mma_chunk(tmem_a, aWA, u, 2 * KBH, aX0, bsp, H, idesc, true);
+        umma_commit(&bars[0]);
+        umma_commit(&bars[2]);
+        mbar_wait(&bars[4], r1 & 1); ++r1; tc_fence_after();                  // dghn -> X1
+        issue_mma_chunk(tmem_b, aWB, u, 3 * KBH, aX1, bsp, H, idesc, true);
+        umma_commit(&bars[1]);
+      }
+      __syncwarp();
+      n0 += 1; n1 += 1;                      // the loaders consumed one completion of each xfree barrier here
+    } else {
+      // two chunks in flight at a time (cp.async): drp -> X0, dzp -> X1, then dnp -> X0, dghn -> X1
+      load_operand_rows_async(sX0, bsp, 0, xg + H, xrow, b0, bsp, b0 + bs, H, DEC_LOADERS);
+      cp_async_commit();
+      load_operand_rows_async(sX1, bsp, 0, xg + 2 * H, xrow, b0, bsp, b0 + bs, H, DEC_LOADERS);
+      cp_async_commit();
+      cp_async_wait<1>(); fence_proxy_async(); mbar_arrive(&bars[3]);
+      cp_async_wait<0>(); fence_proxy_async(); mbar_arrive(&bars[4]);
+      mbar_wait(&bars[0], n0 & 1); ++n0;
+      load_operand_rows_async(sX0, bsp, 0, xg + 4 * H, xrow, b0, bsp, b0 + bs, H, DEC_LOADERS);
+      cp_async_commit();
+      mbar_wait(&bars[1], n1 & 1); ++n1;
+      load_operand_rows_async(sX1, bsp, 0, xg + 3 * H, xrow, b0, bsp, b0 + bs, H, DEC_LOADERS);
+      cp_async_commit();
+      cp_async_wait<1>(); fence_proxy_async(); mbar_arrive(&bars[3]);
+      cp_async_wait<0>(); fence_proxy_async(); mbar_arrive(&bars[4]);
     }
-    // chunk dzp -> X1 : A k-chunk 1, B k-chunk 2
-    load_operand_rows(sX1, bsp, 0, xg + 2 * H, xrow, b0, bsp, b0 + bs, H);
-    fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_mma_chunk(tmem_a, aWA, u, KBH, aX1, bsp, H, idesc, true);
-      issue_mma_chunk(tmem_b, aWB, u, 2 * KBH, aX1, bsp, H, idesc, true);
-      umma_commit(&bars[1]);
-    }
-    // chunk dnp -> X0 (after its MMAs retired) : A k-chunk 2, completes dctx
-    mbar_wait(&bars[0], ph0); ph0 ^= 1;
-    load_operand_rows(sX0, bsp, 0, xg + 4 * H, xrow, b0, bsp, b0 + bs, H);
-    fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_mma_chunk(tmem_a, aWA, u, 2 * KBH, aX0, bsp, H, idesc, true);
-      umma_commit(&bars[2]);
-    }
-    // chunk dghn -> X1 : B k-chunk 3
-    mbar_wait(&bars[1], ph1); ph1 ^= 1;
-    load_operand_rows(sX1, bsp, 0, xg + 3 * H, xrow, b0, bsp, b0 + bs, H);
-    fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_mma_chunk(tmem_b, aWB, u, 3 * KBH, aX1, bsp, H, idesc, true);
-      umma_commit(&bars[1]);
-    }
+    phase_stamp(p.dbg, L - 1 - i, 3);
     mbar_wait(&bars[2], phA); phA ^= 1;
     tc_fence_after();
+    phase_stamp(p.dbg, L - 1 - i, 4);
     if (tid < 128) tmem64_to_smem_cols(tmem_a, sSA, s_ld, u, bsp);
     tc_fence_before();
     __syncthreads();
@@ -496,8 +510,10 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_bwd_kernel(const D
     }
     group_arrive(ctr);
     target += (unsigned)C;
+    phase_stamp(p.dbg, L - 1 - i, 5);
     // ---- B3: attention gradient of video vb ------------------------------------------------------------------
     group_wait(ctr, target);
+    phase_stamp(p.dbg, L - 1 - i, 6);
     {
       const float4* c4 = reinterpret_cast<const float4*>(p.dctx_all + ((long long)i * B + vb) * H + d0);
       const float4 ca = __ldcg(c4), cb = __ldcg(c4 + 1);
@@ -580,20 +596,30 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_bwd_kernel(const D
         }
       }
     }
+    phase_stamp(p.dbg, L - 1 - i, 7);
     group_arrive(ctr);
     target += (unsigned)C;
     // ---- B4: dh_{i-1} = dh z + W_hh^T dgh + W_q^T dq -----------------------------------------------------------
     group_wait(ctr, target);
-    load_operand_rows(sX0, bsp, 0, xg, xrow, b0, bsp, b0 + bs, H);
-    fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_mma_chunk(tmem_b, aWB, u, 0, aX0, bsp, H, idesc, true);
-      umma_commit(&bars[0]);
+    phase_stamp(p.dbg, L - 1 - i, 8);
+    if (mma_role) {
+      if ((tid & 31) == 0) {
+        mbar_wait(&bars[3], r0 & 1); ++r0; tc_fence_after();                  // dq   -> X0, completes dh
+        issue_mma_chunk(tmem_b, aWB, u, 0, aX0, bsp, H, idesc, true);
+        umma_commit(&bars[0]);
+      }
+      __syncwarp();
+      n0 += 1;
+    } else {
+      mbar_wait(&bars[0], n0 & 1); ++n0;     // chunk dnp retired: X0 is free
+      load_operand_rows_async(sX0, bsp, 0, xg, xrow, b0, bsp, b0 + bs, H, DEC_LOADERS);
+      cp_async_commit();
+      cp_async_wait<0>(); fence_proxy_async(); mbar_arrive(&bars[3]);
     }
-    mbar_wait(&bars[1], ph1); ph1 ^= 1;      // chunk dghn retired (X1 free for the next step)
-    mbar_wait(&bars[0], ph0); ph0 ^= 1;
+    phase_stamp(p.dbg, L - 1 - i, 9);
+    mbar_wait(&bars[1], n1 & 1); ++n1;       // chunk dghn retired (X1 free for the next step)
+    mbar_wait(&bars[0], n0 & 1); ++n0;
+    phase_stamp(p.dbg, L - 1 - i, 10);
     tc_fence_after();
     if (tid < 128) tmem64_to_smem_cols(tmem_b, sSB, s_ld, u, bsp);
     tc_fence_before();
@@ -745,7 +771,7 @@ int dec_persist_fwd(const DecPersistFwd& p0, cudaStream_t st) {
   PVCR_REQUIRE(plan_dec(p0.B, p0.N, p0.H, pl), "dec_persist_fwd: shape B=%d N=%d H=%d not supported", p0.B, p0.N, p0.H);
   DecPersistFwd p = p0;
   p.C = pl.C; p.u = pl.u; p.bsp = pl.bsp;
-  p.dbg = debug_phase_buffer();
+  p.dbg = getenv("PVCR_PHASE_DEC_BWD") || getenv("PVCR_PHASE_GRU") ? nullptr : debug_phase_buffer();
   const void* kern = pl.NF == 2 ? (const void*)dec_persist_fwd_kernel<2>
                      : (pl.NF == 5 ? (const void*)dec_persist_fwd_kernel<5> : (const void*)dec_persist_fwd_kernel<10>);
   PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
@@ -765,6 +791,7 @@ int dec_persist_bwd(const DecPersistBwd& p0, cudaStream_t st) {
   PVCR_REQUIRE(plan_dec(p0.B, p0.N, p0.H, pl), "dec_persist_bwd: shape B=%d N=%d H=%d not supported", p0.B, p0.N, p0.H);
   DecPersistBwd p = p0;
   p.C = pl.C; p.u = pl.u; p.bsp = pl.bsp;
+  p.dbg = getenv("PVCR_PHASE_DEC_BWD") ? debug_phase_buffer() : nullptr;
   const int H = p.H, KBH = H / 64, DG = H / 8, FG = DEC_THREADS / DG, PW = DG >= 32 ? DG / 32 : 1;
   size_t smem = (size_t)7 * KBH * pl.u * 128 + (size_t)2 * KBH * pl.bsp * 128;
   smem += ((size_t)2 * pl.bsp * (pl.u + 1) + (size_t)p.N * PW + 2 * p.N + (size_t)FG * H) * 4 + 64 + 1024;
@@ -774,13 +801,13 @@ int dec_persist_bwd(const DecPersistBwd& p0, cudaStream_t st) {
                      : (pl.NF == 5 ? (const void*)dec_persist_bwd_kernel<5> : (const void*)dec_persist_bwd_kernel<10>);
   PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  PVCR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DEC_THREADS, smem));
+  PVCR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DEC_BWD_THREADS, smem));
   const int grid = pl.G * pl.C;
   PVCR_REQUIRE(per_sm * dec_num_sms() >= grid, "dec_persist_bwd: %d CTAs cannot be co-resident", grid);
   PVCR_TRY(fill_zero(p.counters, sizeof(unsigned) * 32 * pl.G, st));
   void* args[] = {&p};
   LaunchScope ls_(KC_DEC_BWD, st);
-  PVCR_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(DEC_THREADS), args, smem, st));
+  PVCR_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(DEC_BWD_THREADS), args, smem, st));
   return PVCR_OK;
 }
 

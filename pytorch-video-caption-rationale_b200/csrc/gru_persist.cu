@@ -121,11 +121,13 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_fwd_kernel(con
       if (t > 0) {
         group_wait(ctr, (unsigned)(p.C * t));
         phase_stamp(p.dbg, t, 1);
-        load_operand_rows(sX, bs, 0, p.hp + (long long)(DBG_STALE_X ? 0 : t - 1) * p.hp_ts, p.hp_ld, b0, bs, p.B, H);
-        phase_stamp(p.dbg, t, 7);
+        load_operand_rows_async(sX, bs, 0, p.hp + (long long)(DBG_STALE_X ? 0 : t - 1) * p.hp_ts, p.hp_ld, b0, bs, p.B, H);
       } else {
-        load_operand_rows(sX, bs, 0, p.h0p, p.h0p_ld, b0, bs, p.B, H);
+        load_operand_rows_async(sX, bs, 0, p.h0p, p.h0p_ld, b0, bs, p.B, H);
       }
+      cp_async_commit();
+      cp_async_wait<0>();
+      phase_stamp(p.dbg, t, 7);
       fence_proxy_async();
       __syncthreads();
       phase_stamp(p.dbg, t, 2);
@@ -277,7 +279,9 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_bwd_kernel(con
       group_arrive(ctr);
       ++arrivals;
       group_wait(ctr, (unsigned)p.C * arrivals);
-      load_operand_rows(sX, bs, 0, xw, K, b0, bs, p.B, K);
+      load_operand_rows_async(sX, bs, 0, xw, K, b0, bs, p.B, K);
+      cp_async_commit();
+      cp_async_wait<0>();
       fence_proxy_async();
       __syncthreads();
       if (tid == 0) {

@@ -159,6 +159,7 @@ struct DecPersistBwd {
   float* dh_carry;                          // [B,H] out: gradient on the initial state (encoder final)
   bf16* xg;                                 // exchange [2][B][5H]: [dq | drp | dzp | dghn | dnp]
   unsigned* counters;
+  long long* dbg;
 };
 // dpk / denc / dv from the per-step quantities saved by the backward sweep (hoisted out of the time loop)
 struct AttnGradArgs {

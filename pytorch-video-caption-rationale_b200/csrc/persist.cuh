@@ -39,8 +39,8 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int k, int rows_alloc)
 // SW128 operand at local rows [lrow0, lrow0+nrows).  All threads of the CTA participate; 16-byte L2 loads (.cg).
 __device__ __forceinline__ void load_operand_rows(uint8_t* dst, int rows_alloc, int lrow0, const bf16* src,
                                                   long long ld, long long row0, int nrows, long long row_limit,
-                                                  int K) {
-  const int chunks = K >> 3, total = nrows * chunks, step = blockDim.x;
+                                                  int K, int nthr = 0) {
+  const int chunks = K >> 3, total = nrows * chunks, step = nthr ? nthr : (int)blockDim.x;
   // (row, chunk) of element i = threadIdx.x + j*step advanced incrementally: no divisions inside the loops.
   const int dlr = step / chunks, dch = step - dlr * chunks;
   int lr = threadIdx.x / chunks, ch = threadIdx.x - lr * chunks;
@@ -66,6 +66,29 @@ __device__ __forceinline__ void load_operand_rows(uint8_t* dst, int rows_alloc, 
   }
 }
 
+// Same copy with cp.async (LDGSTS): no register staging, every 16-byte chunk of the operand in flight at once, so a
+// whole operand (or several K-chunks of it) costs one L2 round trip.  Rows >= row_limit are zero-filled (src-size 0).
+// Completion: cp_async_commit() + cp_async_wait<N>() by the issuing thread, then fence.proxy.async before the MMA.
+__device__ __forceinline__ void load_operand_rows_async(uint8_t* dst, int rows_alloc, int lrow0, const bf16* src,
+                                                        long long ld, long long row0, int nrows, long long row_limit,
+                                                        int K, int nthr = 0) {
+  const int chunks = K >> 3, total = nrows * chunks, step = nthr ? nthr : (int)blockDim.x;
+  const int dlr = step / chunks, dch = step - dlr * chunks;
+  int lr = threadIdx.x / chunks, ch = threadIdx.x - lr * chunks;
+  const uint32_t dbase = smem_u32(dst);
+  for (int i = threadIdx.x; i < total; i += step) {
+    const bool ok = row0 + lr < row_limit;
+    const bf16* g = src + (ok ? (row0 + lr) * ld + ch * 8 : 0);
+    const uint32_t d = dbase + sw128_offset(lrow0 + lr, ch * 8, rows_alloc);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(g), "r"(ok ? 16 : 0) : "memory");
+    lr += dlr; ch += dch;
+    if (ch >= chunks) { ch -= chunks; ++lr; }
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -74,6 +97,30 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 
 // Group barrier on a monotonic counter.  arrive: all of this CTA's global writes of the step are published;
 // wait: the counter has reached `target` arrivals.  Bounded spin: a protocol bug traps instead of hanging the GPU.
+// worker-only CTA barrier (named barrier 1) for kernels that keep a dedicated MMA-issue warp out of the step loop
+template <int NWORKERS>
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NWORKERS) : "memory"); }
+template <int NWORKERS>
+__device__ __forceinline__ void group_arrive_w(unsigned* ctr) {
+  worker_sync<NWORKERS>();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+  }
+}
+template <int NWORKERS>
+__device__ __forceinline__ void group_wait_w(const unsigned* ctr, unsigned target) {
+  if (threadIdx.x == 0) {
+    if (ld_acquire_u32(ctr) < target) {
+      const long long t0 = clock64();
+      while (ld_acquire_u32(ctr) < target) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+      }
+    }
+  }
+  worker_sync<NWORKERS>();
+}
+
 __device__ __forceinline__ void group_arrive(unsigned* ctr) {
   __syncthreads();
   if (threadIdx.x == 0) {

@@ -20,14 +20,22 @@ Lb.pvcr_debug_phase_timing(1)
 which = sys.argv[1] if len(sys.argv) > 1 else "enc_fwd"
 # the debug buffer is overwritten by every persistent launch that stamps: run only the forward sequence
 from pvcr_b200 import functional as F_
+bwd = os.environ.get("PVCR_PHASE_DEC_BWD") is not None
 with torch.no_grad():
-    F_.S2VTAttSequence.forward(F_.ManualCtx(), m._cfg(True), vid, None, m._shifted(s, B), *m._seq_params())
+    if bwd:
+        m.train_step_grads(vid, s, s_len)
+    else:
+        F_.S2VTAttSequence.forward(F_.ManualCtx(), m._cfg(True), vid, None, m._shifted(s, B), *m._seq_params())
 gru = os.environ.get("PVCR_PHASE_GRU") is not None
 steps = N if gru else L
 buf = (ctypes.c_longlong * (steps * 16))()
 _lib.check(Lb.pvcr_debug_phase_read(buf, steps), "read")
 a = np.array(buf[:]).reshape(steps, 16)
-if gru:
+if bwd:
+    a2 = np.concatenate([a[:, :11], np.roll(a[:, 0:1], -1, axis=0)], axis=1)[:-1]
+    names = ["B1 gate grads", "B1 arrive+wait", "B2 4 chunks load+mma issue", "B2 wait mma A", "B2 t2s+dctx write+arrive",
+             "B3 wait dctx", "B3 attention grad", "B3 arrive+wait", "B4 load+mma issue", "B4 wait mma", "B4 t2s+carry"]
+elif gru:
     a2 = a[:, [0, 1, 7, 2, 3, 4, 5, 6]]
     names = ["wait", "load X (ld+st)", "fence+sync", "mma", "tmem->smem", "gates+stores", "arrive"]
 else:
