@@ -94,12 +94,30 @@ int make_tensor_map(CUtensorMap* out, const OperandView& v, int K, int box_rows)
 int gemm_store(const OperandView& a, const OperandView& b, const GemmCoords& gc, int grid_z, float* C, long long ldc,
                long long c_zstride, const float* bias, long long bias_zstride, int accumulate,
                cudaStream_t stream) {
-  EpiStore epi{C, ldc, c_zstride, bias, bias_zstride, accumulate, gc.M, gc.N};
+  EpiStore epi{C, ldc, c_zstride, bias, bias_zstride, accumulate, gc.M, gc.N, 0, 1};
   const long long tiles256 = (long long)cdiv(gc.N, 256) * cdiv(gc.M, GEMM_BM) * grid_z;
   static const bool no_persist = getenv("PVCR_NO_PERSIST_GEMM") != nullptr;
   if (gc.N >= 256 && tiles256 >= 64 && !no_persist)
     return launch_gemm_tn_persistent<256, 4, EpiStore>(a, b, gc, grid_z, epi, stream);
   if (gc.N >= 256 && tiles256 >= 148) return launch_gemm_tn<256, 4, EpiStore>(a, b, gc, grid_z, epi, stream);
+  // few output tiles but a long contraction (weight / data gradients over all timesteps): split K across CTAs
+  const long long tiles128 = (long long)cdiv(gc.N, 128) * cdiv(gc.M, GEMM_BM);
+  const int total_kb = gc.K / GEMM_BK;
+  static const bool no_split = getenv("PVCR_NO_SPLITK") != nullptr;
+  if (grid_z == 1 && tiles128 <= 24 && total_kb >= 32 && !no_split) {     // measured: atomics lose beyond ~24 tiles
+    int splits = (int)((296 + tiles128 - 1) / tiles128);
+    if (splits > total_kb / 8) splits = total_kb / 8;
+    if (splits > 1) {
+      const int kb_per = (total_kb + splits - 1) / splits;
+      splits = (total_kb + kb_per - 1) / kb_per;          // no empty K range
+      if (!accumulate)
+        PVCR_CUDA_CHECK(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * gc.N, gc.M, stream));
+      GemmCoords g2 = gc;
+      g2.k_splits = splits;
+      epi.atomic = 1;
+      return launch_gemm_tn<128, 3, EpiStore>(a, b, g2, 1, epi, stream);
+    }
+  }
   return launch_gemm_tn<128, 3, EpiStore>(a, b, gc, grid_z, epi, stream);
 }
 

@@ -31,6 +31,7 @@ struct GemmCoords {
   int M, N, K;          // K = concatenated (all split planes), multiple of GEMM_BK
   int a_z0, a_zmul;     // slab coordinate of A for grid z:  a_z0 + z * a_zmul
   int b_z0, b_zmul;
+  int k_splits;         // > 1: grid z enumerates K ranges instead of slabs (epilogue must accumulate atomically)
 };
 
 #ifdef __CUDACC__
@@ -51,8 +52,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
   const int m0 = blockIdx.y * GEMM_BM;
-  const int z = blockIdx.z;
-  const int num_kb = gc.K / GEMM_BK;
+  const bool split = gc.k_splits > 1;
+  const int z = split ? 0 : blockIdx.z;
+  const int total_kb = gc.K / GEMM_BK;
+  const int kb_per = split ? (total_kb + gc.k_splits - 1) / gc.k_splits : total_kb;
+  const int kb0 = split ? blockIdx.z * kb_per : 0;
+  const int num_kb = min(kb_per, total_kb - kb0);      // >= 1 by construction of k_splits on the host
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -82,8 +87,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_arrive_expect_tx(&full_bar[s], SM::STAGE_BYTES);
         uint8_t* sa = smem + s * SM::STAGE_BYTES;
-        tma_load_3d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m0, az);
-        tma_load_3d(sa + SM::A_BYTES, &tmB, &full_bar[s], kb * GEMM_BK, n0, bz);
+        tma_load_3d(sa, &tmA, &full_bar[s], (kb0 + kb) * GEMM_BK, m0, az);
+        tma_load_3d(sa + SM::A_BYTES, &tmB, &full_bar[s], (kb0 + kb) * GEMM_BK, n0, bz);
       }
     }
   } else if (warp == 1) {
@@ -110,7 +115,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;             // TMEM lane quadrant of this warp
     const int row = m0 + q * 32 + lane;
     Epi e = epi;                        // per-thread copy: functors may keep running state across chunks
-    e.begin(row, z);
+    e.begin(row, split ? (int)blockIdx.z : z);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     float v[32];
@@ -261,9 +266,18 @@ struct EpiStore {
   const float* bias;
   long long bias_zstride;
   int accumulate, M, N;
-  __device__ __forceinline__ void begin(int, int) {}
+  int atomic;             // split-K: every K range adds its partial product with red.global.add (C pre-zeroed)
+  int first;              // set in begin(): this CTA's K range is the first one (adds the bias)
+  __device__ __forceinline__ void begin(int, int zsplit) { first = (zsplit == 0); }
   __device__ __forceinline__ void chunk(int row, int col0, int z, float (&v)[32]) {
     if (row >= M) return;
+    if (atomic) {
+      float* c = C + (long long)row * ldc + col0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < N) atomicAdd(c + j, v[j] + ((bias && first) ? __ldg(bias + col0 + j) : 0.f));
+      return;
+    }
     float* c = C + (long long)z * c_zstride + (long long)row * ldc + col0;
     const float* b = bias ? bias + (long long)z * bias_zstride + col0 : nullptr;
     const bool vec = (col0 + 32 <= N) && ((reinterpret_cast<uintptr_t>(c) & 15) == 0);
@@ -320,7 +334,8 @@ int launch_gemm_tn(const OperandView& a, const OperandView& b, const GemmCoords&
     PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     attr_set = true;
   }
-  dim3 grid(cdiv(gc.N, BN), cdiv(gc.M, GEMM_BM), grid_z);
+  PVCR_REQUIRE(gc.k_splits <= 1 || grid_z == 1, "gemm: split-K and batched slabs are exclusive");
+  dim3 grid(cdiv(gc.N, BN), cdiv(gc.M, GEMM_BM), gc.k_splits > 1 ? gc.k_splits : grid_z);
   {
     LaunchScope ls_(KC_GEMM, stream, 2.0 * gc.M * gc.N * (double)gc.K * grid_z);
     kern<<<grid, GEMM_THREADS, SM::TOTAL, stream>>>(ta, tb, gc, epi);
