@@ -87,7 +87,8 @@ class RationaleNet(nn.Module):
         probs, p1, pen = F_.GeneratorSelect.forward(cg, gen._cfg(), vid_feats, gen.noise, *gparams)
         p1.requires_grad_(True)          # makes the caption network emit d loss / d frame_scale
         loss_ce, acc, pred = cap.train_step_grads(vid_feats, s, s_len, frame_scale=p1)
-        d_pen = torch.tensor([lambda_brev, lambda_cont], dtype=torch.float32, device=vid_feats.device)
+        dev = vid_feats.device         # fill kernels (no host-to-device copy): stays CUDA-graph capturable
+        d_pen = torch.cat([torch.full((1,), float(lambda_brev), device=dev), torch.full((1,), float(lambda_cont), device=dev)])
         grads = F_.GeneratorSelect.backward(cg, None, cap.last_frame_scale_grad, d_pen)
         for p, g in zip(gparams, grads[3:]):
             p.grad = g
