@@ -19,7 +19,23 @@ struct GenWs {
   Planes wih, x_a, da_a;
   DirBuf dir[2];
   float *bias_cat, *gi, *gh, *y, *dgi, *dh_carry, *dc, *dhf, *dhb, *dlogit;
+  unsigned* sync;
+  bf16* xch;
 };
+
+static LstmSeqArgs dir_seq(const PvcrDims& d, const PvcrGenParams& p, const GenWs& w, int k) {
+  const int N = d.N, H = d.H;
+  const DirBuf& r = w.dir[k];
+  LstmSeqArgs s{};
+  s.T = N; s.B = d.B; s.H = H; s.rev = k;
+  s.whh = r.whh; s.b_hh = k ? p.b_hh_r : p.b_hh;
+  s.gi = w.gi + (long long)k * 4 * H; s.gi_ts = 8 * H; s.gi_ld = (long long)N * 8 * H;
+  s.h = r.h; s.h_ts = H; s.h_ld = (long long)N * H;
+  s.hp = r.hp.ptr; s.hp_ts = r.hp.ld; s.hp_ld = (long long)N * r.hp.ld;
+  s.si = r.i; s.sf = r.f; s.sg = r.g; s.so = r.o; s.sc = r.c;
+  s.sync = w.sync;
+  return s;
+}
 
 static void carve_gen(Arena& a, const PvcrDims& d, GenWs& w) {
   const int B = d.B, N = d.N, V = d.V, H = d.H, ns = d.nsplit;
@@ -46,6 +62,8 @@ static void carve_gen(Arena& a, const PvcrDims& d, GenWs& w) {
   w.dc = a.alloc<float>((size_t)B * H);
   w.dhf = a.alloc<float>(BN * H); w.dhb = a.alloc<float>(BN * H);
   w.dlogit = a.alloc<float>(BN * 2);
+  w.sync = a.alloc<unsigned>(32 * 160);
+  w.xch = a.alloc<bf16>((size_t)2 * B * 4 * H);
 }
 
 static size_t gen_scratch(const PvcrDims& d) {
@@ -92,6 +110,10 @@ int generator_fwd(const PvcrDims& d, const PvcrGenParams& p, const float* vid, c
     DirBuf& r = w.dir[k];
     if (r.hp.Kp != H) PVCR_TRY(fill_zero(r.hp.ptr, sizeof(bf16) * (size_t)BN * r.hp.ld, st));
     const float* b_hh = k ? p.b_hh_r : p.b_hh;
+    if (lstm_persist_eligible(B, H, d.nsplit, r.hp.Kp)) {
+      PVCR_TRY(lstm_persist_fwd(dir_seq(d, p, w, k), st));
+      continue;
+    }
     for (int s = 0; s < N; ++s) {
       const int t = k ? N - 1 - s : s, tp = k ? t + 1 : t - 1;
       if (s > 0) {
@@ -148,7 +170,11 @@ int generator_bwd(const PvcrDims& d, const PvcrGenParams& p, const float* vid, f
     PVCR_TRY(fill_zero(w.dh_carry, sizeof(float) * (size_t)B * H, st));
     PVCR_TRY(fill_zero(w.dc, sizeof(float) * (size_t)B * H, st));
     const float* dh_ext = k ? w.dhb : w.dhf;
-    for (int s = N - 1; s >= 0; --s) {
+    const bool persist = lstm_persist_eligible(B, H, ns, r.hp.Kp);
+    if (persist)
+      PVCR_TRY(lstm_persist_bwd(dir_seq(d, p, w, k), r.whhT, dh_ext, H, (long long)N * H, w.dgi + (long long)k * H4, H8,
+                                (long long)N * H8, w.xch, st));
+    for (int s = N - 1; s >= 0 && !persist; --s) {
       const int t = k ? N - 1 - s : s, tp = k ? t + 1 : t - 1;
       LstmBwdArgs b{};
       b.B = B; b.H = H;

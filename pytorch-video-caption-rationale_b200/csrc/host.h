@@ -118,6 +118,22 @@ int gru_persist_fwd(const GruSeq& s, cudaStream_t st);
 int gru_persist_bwd(const GruSeq& s, const GruSeqGrad& g, cudaStream_t st);
 int gru_seq_bwd(const GruSeq& s, const GruSeqGrad& g, cudaStream_t st);
 
+// ---- persistent LSTM sequence (lstm_persist.cu; one direction of the RationaleNet generator) ---------------------
+struct LstmSeqArgs {
+  int T, B, H, rev;                        // rev: walk t = T-1 .. 0
+  Planes whh;                              // [4H, Hp] bf16
+  const float* b_hh;
+  const float* gi; long long gi_ts, gi_ld; // 4H columns per (b, t), includes b_ih
+  float* h; long long h_ts, h_ld;
+  bf16* hp; long long hp_ts, hp_ld;
+  float *si, *sf, *sg, *so, *sc;           // saved gates / cell [T][B,H]
+  unsigned* sync;
+};
+bool lstm_persist_eligible(int B, int H, int nsplit, int Hp);
+int lstm_persist_fwd(const LstmSeqArgs& s, cudaStream_t st);
+int lstm_persist_bwd(const LstmSeqArgs& s, const Planes& whhT, const float* dh_ext, long long dh_ext_ts,
+                     long long dh_ext_ld, float* da, long long da_ts, long long da_ld, bf16* xch, cudaStream_t st);
+
 // ---- persistent attention decoder (dec_persist.cu) ---------------------------------------------------------
 struct DecPersistFwd {
   int L, B, N, H, C, u, bsp;                // bsp = videos per group rounded up to 16 (MMA N)

@@ -89,3 +89,38 @@ def test_tape_free_step_matches_autograd(tag):
     got = grads_of(m)
     for k in g:
         assert relerr(got[k], g[k]) < 2e-4, (k, relerr(got[k], g[k]))
+
+
+@pytest.mark.parametrize("precision,B", [("bf16", 24), ("bf16x3", 8)])
+def test_msrvtt_shape_vs_oracle(precision, B):
+    """cfg3 dims (N=40, V=2048, H=512) with a reduced vocabulary: exercises the persistent LSTM / GRU / decoder kernels
+    of the joint RationaleNet + S2VTAtt objective against the float64 oracle."""
+    from oracle import captioning_oracle as O
+    from oracle import workloads as W
+    from pvcr_b200.model import RationaleNet
+    N, V, H, E, L, Vc, tau = 40, 2048, 512, 300, 30, 3000, 0.8
+    pc = W.s2vtatt_params(V, H, E, Vc, 41)
+    pg = W.generator_params(V, H, 42)
+    p = {"caption_net." + k: v for k, v in pc.items()}
+    p.update({"gen." + k: v for k, v in pg.items()})
+    vid, s, s_len = W.make_batch(B, N, V, L, Vc, 43)
+    noise = np.random.RandomState(44).exponential(size=(B * N, 2)).astype(np.float32)
+    ref = O.train_iter_rationale({k: v.astype(np.float64) for k, v in p.items()}, vid.astype(np.float64), s, s_len,
+                                 Vc - 4, L, tau, noise.astype(np.float64), arch="s2vt-att", lambda_brev=0.05,
+                                 lambda_cont=0.5)
+    m = RationaleNet(FixtureGlove(Vc, E), 0.0, H, V, L, tau, "s2vt-att", precision=precision)
+    m = to_cuda(m, p).train()
+    m.gen.noise = torch.from_numpy(noise).cuda()
+    acc, loss, loss_ce, loss_brev, loss_cont, rlen, pred, probs = m.forward_loss(
+        torch.from_numpy(vid).cuda(), torch.from_numpy(s).cuda(), torch.from_numpy(s_len).cuda(), 0.05, 0.5)
+    loss.backward()
+    t_loss, t_probs, t_grad = TOL[precision]
+    errs = {k: relerr(v, ref["grads"][k]) for k, v in grads_of(m).items()}
+    l_err = abs(loss.item() - ref["loss"]) / abs(ref["loss"])
+    p_err = float(np.abs(probs.detach().cpu().numpy() - ref["probs"]).max())
+    print("\n[%s B=%d] loss rel %.2e  probs abs %.2e  grads rel max %.2e (%s)" % (
+        precision, B, l_err, p_err, max(errs.values()), max(errs, key=errs.get)))
+    assert l_err < t_loss
+    assert p_err < t_probs
+    for k, e in errs.items():
+        assert e < t_grad, (k, e)
