@@ -844,26 +844,35 @@ __global__ void __launch_bounds__(256) gumbel_bwd_rows_kernel(GumbelBwdArgs a) {
     if (k < H) dhf[k] = g; else dhb[k - H] = g;
   }
 }
+// d W[c][k] = sum_rows dlogit[row][c] * Dropout(out)[row][k]: block = (64-row chunk, 256-column tile), partial sums
+// merged with atomics (dw / dbias zeroed by the launcher)
+constexpr int GW_ROWS = 64;
 __global__ void __launch_bounds__(256) gumbel_bwd_w_kernel(GumbelBwdArgs a) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int B = a.B, N = a.N, H = a.H;
+  __shared__ float sdl[GW_ROWS][2];
+  const int B = a.B, N = a.N, H = a.H, R = B * N;
+  const int row0 = blockIdx.x * GW_ROWS, k = blockIdx.y * 256 + threadIdx.x;
+  for (int i = threadIdx.x; i < GW_ROWS * 2; i += 256) {
+    const int row = row0 + (i >> 1);
+    sdl[i >> 1][i & 1] = row < R ? a.scratch[row * 2 + (i & 1)] : 0.f;
+  }
+  __syncthreads();
   if (k < 2 * H) {
     float g0 = 0.f, g1 = 0.f;
-    for (int row = 0; row < B * N; ++row) {
-      const int b = row / N, n = row % N;
+    for (int i = 0; i < GW_ROWS && row0 + i < R; ++i) {
+      const int row = row0 + i, b = row / N, n = row % N;
       const long long o = (long long)n * a.h_ts + (long long)b * a.h_bs;
       float x = k < H ? a.hf[o + k] : a.hb[o + k - H];
       if (a.drop.p > 0.f) x *= dropout_scale(a.drop, (unsigned long long)row * 2 * H + k);
-      g0 += a.scratch[row * 2] * x;
-      g1 += a.scratch[row * 2 + 1] * x;
+      g0 += sdl[i][0] * x;
+      g1 += sdl[i][1] * x;
     }
-    a.dw[k] = g0;
-    a.dw[2 * H + k] = g1;
+    atomicAdd(a.dw + k, g0);
+    atomicAdd(a.dw + 2 * H + k, g1);
   }
-  if (k < 2) {
+  if (blockIdx.y == 0 && threadIdx.x < 2) {
     float s = 0.f;
-    for (int row = 0; row < B * N; ++row) s += a.scratch[row * 2 + k];
-    a.dbias[k] = s;
+    for (int i = 0; i < GW_ROWS; ++i) s += sdl[i][threadIdx.x];
+    atomicAdd(a.dbias + threadIdx.x, s);
   }
 }
 int gumbel_select_bwd(const GumbelBwdArgs& a, cudaStream_t st) {
@@ -873,8 +882,10 @@ int gumbel_select_bwd(const GumbelBwdArgs& a, cudaStream_t st) {
   gumbel_bwd_rows_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, st>>>(a);
   }
   PVCR_CUDA_CHECK(cudaGetLastError());
-  { LaunchScope ls_(KC_MISC, st);
-  gumbel_bwd_w_kernel<<<cdiv(2 * a.H, 256), 256, 0, st>>>(a);
+  PVCR_CUDA_CHECK(cudaMemsetAsync(a.dw, 0, sizeof(float) * 4 * a.H, st));
+  PVCR_CUDA_CHECK(cudaMemsetAsync(a.dbias, 0, sizeof(float) * 2, st));
+  { LaunchScope ls2_(KC_MISC, st);
+  gumbel_bwd_w_kernel<<<dim3(cdiv(rows, GW_ROWS), cdiv(2 * a.H, 256)), 256, 0, st>>>(a);
   }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;

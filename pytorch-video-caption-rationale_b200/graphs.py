@@ -89,3 +89,28 @@ class GraphedTrainStep:
         self._staged = None
         self._replay()
         return self.static_out
+
+
+class GraphedGreedy:
+    """CUDA-graph capture of fixed-length greedy captioning (model.greedy) for one batch shape: at small batches the
+    step-wise decode is launch-latency bound, a single graph launch removes the host from the loop."""
+
+    def __init__(self, model, example_vid):
+        self.model = model
+        self.static_vid = example_vid.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            model.greedy(self.static_vid)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            out = model.greedy(self.static_vid)
+        self.static_out = tuple(o for o in out)
+
+    def __call__(self, vid):
+        if vid is not self.static_vid:
+            self.static_vid.copy_(vid, non_blocking=True)
+        self.graph.replay()
+        return self.static_out

@@ -4,7 +4,7 @@ import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import pvcr_b200
-from pvcr_b200.graphs import GraphedTrainStep
+from pvcr_b200.graphs import GraphedGreedy, GraphedTrainStep
 from pvcr_b200.model import RationaleNet, S2VTAttModel, S2VTModel
 from tests.gpu_util import FixtureGlove
 
@@ -55,6 +55,10 @@ sweep = {}
 for B in (1, 8, 64, 128, 512, 1024):
     vid = torch.randn(B, N, V, device="cuda")
     ms = timed(lambda: m.greedy(vid), 5 if B >= 512 else 10)
-    sweep[B] = {"ms_per_batch": ms, "captions_per_s": B / ms * 1e3}
+    gg = GraphedGreedy(m, vid)
+    ms_g = timed(lambda: gg(vid), 5 if B >= 512 else 10)
+    sweep[B] = {"ms_per_batch": ms, "captions_per_s": B / ms * 1e3, "graph_ms_per_batch": ms_g,
+                "graph_captions_per_s": B / ms_g * 1e3}
+    del gg
 out["cfg5_greedy_s2vtatt"] = sweep
 print(json.dumps(out, indent=1))

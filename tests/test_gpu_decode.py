@@ -69,3 +69,15 @@ def test_greedy_msrvtt_shape_vs_oracle():
     ids, logits = m.greedy(torch.from_numpy(vid).cuda())
     assert np.array_equal(ids.cpu().numpy(), ids_ref)
     assert relerr(logits.cpu().numpy(), logits_ref) < 2e-5
+
+
+def test_graphed_greedy_matches_eager():
+    from pvcr_b200.graphs import GraphedGreedy
+    from pvcr_b200.model import S2VTAttModel
+    d, params, _, (B, N, V, H, E, L, Vc) = load_case("s2vtatt_mid")
+    m = to_cuda(S2VTAttModel(FixtureGlove(Vc, E), 0.0, H, V, L), params).eval()
+    vid = torch.from_numpy(d["vid"]).cuda()
+    g = GraphedGreedy(m, vid)
+    ids, logits = g(vid)
+    torch.cuda.synchronize()
+    assert np.array_equal(ids.cpu().numpy(), d["greedy_ids"])
