@@ -53,6 +53,13 @@ int pvcr_linear_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, 
                     float* dx, int64_t lddx, float* dw, int64_t lddw, float* db, int M, int N, int K, int nsplit,
                     int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
+/* dw[N,K] (+)= dy[R,N]^T x[R,K] in bf16 arithmetic with MN-major tcgen05 operands: the operands are cast to bf16
+ * row-major as they are (no transposed copies), the contraction runs over their rows (autograd of F.linear w.r.t.
+ * the weight; the building block of every hoisted weight gradient). */
+size_t pvcr_wgrad_mn_workspace(int R, int N, int K);
+int pvcr_wgrad_mn(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dw, int64_t lddw, int R, int N,
+                  int K, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Model-level entry points.  Symbols: B batch, N frames, V feature size, H hidden, E embedding size,
  * L = max_len, Vc vocabulary.  dropout_p / seed parameterise the counter-based (Philox) dropout masks of

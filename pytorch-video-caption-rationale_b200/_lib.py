@@ -80,6 +80,8 @@ SIGNATURES = {
     "pvcr_linear_bwd_workspace": (c_size, [c_int, c_int, c_int, c_int]),
     "pvcr_linear_bwd": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_int,
                                 c_int, c_int, c_int, c_vp, c_size, c_vp]),
+    "pvcr_wgrad_mn_workspace": (c_size, [c_int, c_int, c_int]),
+    "pvcr_wgrad_mn": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_size, c_vp]),
     "pvcr_s2vtatt_workspace": (c_size, [P(PvcrDims), c_int]),
     "pvcr_s2vtatt_fwd": (c_int, [P(PvcrDims), P(PvcrS2vtAttParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
     "pvcr_s2vtatt_bwd": (c_int, [P(PvcrDims), P(PvcrS2vtAttParams), c_vp, c_vp, c_vp, c_vp, c_vp, P(PvcrS2vtAttGrads),

@@ -9,6 +9,9 @@ int linear_fwd(const float*, long long, const float*, long long, const float*, f
 size_t linear_bwd_workspace(int M, int N, int K, int nsplit);
 int linear_bwd(const float*, long long, const float*, long long, const float*, long long, float*, long long, float*,
                long long, float*, int, int, int, int, int, void*, size_t, cudaStream_t);
+size_t wgrad_mn_workspace(int R, int N, int K);
+int wgrad_mn(const float*, long long, const float*, long long, float*, long long, int, int, int, int, void*, size_t,
+             cudaStream_t);
 size_t s2vtatt_workspace(const PvcrDims& d, int need_frame_grad);
 int s2vtatt_fwd(const PvcrDims&, const PvcrS2vtAttParams&, const float*, const float*, const long long*, float*, float*,
                 void*, size_t, cudaStream_t);
@@ -59,6 +62,11 @@ int pvcr_linear_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, 
                     workspace_bytes, (cudaStream_t)stream);
 }
 
+size_t pvcr_wgrad_mn_workspace(int R, int N, int K) { return wgrad_mn_workspace(R, N, K); }
+int pvcr_wgrad_mn(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dw, int64_t lddw, int R, int N, int K,
+                  int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  return wgrad_mn(dy, lddy, x, ldx, dw, lddw, R, N, K, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
+}
 size_t pvcr_s2vtatt_workspace(const PvcrDims* d, int need_frame_grad) { return s2vtatt_workspace(*d, need_frame_grad); }
 int pvcr_s2vtatt_fwd(const PvcrDims* d, const PvcrS2vtAttParams* p, const float* vid_feats, const float* frame_scale,
                      const int64_t* s_in, float* hs, float* alphas, void* workspace, size_t workspace_bytes,

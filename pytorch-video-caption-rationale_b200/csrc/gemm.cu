@@ -90,6 +90,52 @@ int make_tensor_map(CUtensorMap* out, const OperandView& v, int K, int box_rows)
   return PVCR_OK;
 }
 
+// 3-D tensor map over (mn, k row, slab) of a row-major [k_rows, mn_cols] bf16 matrix, box = 64 x 64 x 1.
+int make_tensor_map_mn(CUtensorMap* out, const OperandView& v, int mn_cols) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = v.ptr; key.ld = v.ld; key.slab_stride = v.slab_stride; key.rows = v.rows; key.slabs = v.slabs;
+  key.K = mn_cols; key.box_rows = -64;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return PVCR_OK; }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_last_error("cuTensorMapEncodeTiled not available from the driver"); return PVCR_ERR_DRIVER; }
+  PVCR_REQUIRE((reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0, "tensor map (mn): base %p not 16-byte aligned", v.ptr);
+  PVCR_REQUIRE(v.ld % 8 == 0 && v.ld >= mn_cols, "tensor map (mn): ld=%lld must be a multiple of 8 and >= %d", v.ld, mn_cols);
+  const int slabs = v.slabs > 0 ? v.slabs : 1;
+  long long slab_stride = v.slab_stride;
+  if (slabs == 1 && slab_stride <= 0) slab_stride = v.ld * (long long)v.rows;
+  cuuint64_t gdim[3] = {(cuuint64_t)mn_cols, (cuuint64_t)v.rows, (cuuint64_t)slabs};
+  cuuint64_t gstr[2] = {(cuuint64_t)v.ld * 2, (cuuint64_t)slab_stride * 2};
+  cuuint32_t box[3] = {64, 64, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(v.ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled (mn) failed (%d): ptr=%p cols=%d rows=%d ld=%lld", (int)r, v.ptr, mn_cols,
+                   v.rows, v.ld);
+    return PVCR_ERR_DRIVER;
+  }
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 65536) cache.clear();
+  cache[key] = *out;
+  return PVCR_OK;
+}
+
+// C[M,N] (+)= A^T B for row-major bf16 A [K, M], B [K, N] (no transposed copies): weight gradients dW = dY^T X.
+int gemm_mn_store(const OperandView& a, const OperandView& b, int M, int N, int K, float* C, long long ldc,
+                  int accumulate, cudaStream_t stream) {
+  EpiStore epi{C, ldc, 0, nullptr, 0, accumulate, M, N, 0, 1};
+  GemmCoords gc{M, N, (int)round_up(K, GEMM_BK), 0, 0, 0, 0};
+  return launch_gemm_tn_persistent<256, 4, EpiStore, true>(a, b, gc, 1, epi, stream);
+}
+
 // C[z] = A[z] * B[z]^T (+bias) (+C).  Tile choice: 128x256 when N is wide enough to fill the machine, else 128x128.
 int gemm_store(const OperandView& a, const OperandView& b, const GemmCoords& gc, int grid_z, float* C, long long ldc,
                long long c_zstride, const float* bias, long long bias_zstride, int accumulate,

@@ -70,10 +70,8 @@ static size_t gen_scratch(const PvcrDims& d) {
   Arena a(nullptr, 0);
   size_t peak = 0;
   auto gw = [&](int R, int N, int K) {
-    size_t m = a.mark();
-    alloc_planes(a, N, R, d.nsplit); alloc_planes(a, K, R, d.nsplit);
-    if (a.off > peak) peak = a.off;
-    a.release(m);
+    const size_t need = a.mark() + grad_w_scratch(R, N, K, d.nsplit);
+    if (need > peak) peak = need;
   };
   gw(d.B * d.N, 8 * d.H, d.V); gw(d.B * d.N, 4 * d.H, d.H);
   return peak + 4096;

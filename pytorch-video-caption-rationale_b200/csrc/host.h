@@ -49,6 +49,10 @@ inline Planes alloc_planes(Arena& a, int rows, int K, int nsplit) {
 int gemm_store(const OperandView& a, const OperandView& b, const GemmCoords& gc, int grid_z, float* C, long long ldc,
                long long c_zstride, const float* bias, long long bias_zstride, int accumulate, cudaStream_t stream);
 
+// C[M,N] (+)= A^T B for row-major bf16 A [K rows, M cols], B [K rows, N cols] (MN-major tcgen05 operands)
+int gemm_mn_store(const OperandView& a, const OperandView& b, int M, int N, int K, float* C, long long ldc,
+                  int accumulate, cudaStream_t stream);
+
 // C[M,N] (ldc) = A * B^T (+bias) (+C); A = a_view (M rows), B = b_view (N rows), both planes over the same K.
 inline int gemm_planes(const OperandView& a, const OperandView& b, int M, int N, int Kcat, float* C, long long ldc,
                        const float* bias, int accumulate, cudaStream_t st) {
@@ -75,6 +79,14 @@ inline int prep_weight_T(const float* w, long long ldw, int N, int K, const Plan
   return transpose_split(w, ldw, N, K, p.ptr, p.ld, p.Kp, n_off, zero_pad, p.nsplit, 1, nullptr, nullptr, st, NO_DROPOUT);
 }
 
+// scratch bytes grad_w needs for (R, N, K): the larger of its transposed-plane and row-major-plane layouts
+inline size_t grad_w_scratch(int R, int N, int K, int nsplit) {
+  Arena t(nullptr, 0);
+  alloc_planes(t, N, R, nsplit); alloc_planes(t, K, R, nsplit);
+  Arena u(nullptr, 0);
+  alloc_planes(u, R, N, 1); alloc_planes(u, R, K, 1);
+  return (t.off > u.off ? t.off : u.off) + 512;
+}
 // dw[N,K] (+)= dy^T x over R rows.  Scratch planes come from `a` and are released on return.
 int grad_w(Arena& a, const float* dy, long long lddy, int R, int N, const float* x, long long ldx, int K,
            const long long* x_row_ids, const float* x_row_scale, float* dw, long long lddw, int accumulate,

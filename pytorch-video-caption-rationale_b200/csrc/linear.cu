@@ -60,4 +60,24 @@ int linear_bwd(const float* dy, long long lddy, const float* x, long long ldx, c
   return PVCR_OK;
 }
 
+// dw[N,K] (+)= dy^T x with MN-major tensor-core operands: dy [R,N] and x [R,K] are only cast to bf16 (row-major,
+// no transposed copies); the contraction runs over their rows.
+size_t wgrad_mn_workspace(int R, int N, int K) {
+  Arena a(nullptr, 0);
+  alloc_planes(a, R, N, 1);
+  alloc_planes(a, R, K, 1);
+  return a.off + 256;
+}
+int wgrad_mn(const float* dy, long long lddy, const float* x, long long ldx, float* dw, long long lddw, int R, int N,
+             int K, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (R == 0 || N == 0 || K == 0) return PVCR_OK;
+  Arena a(ws, ws_bytes);
+  Planes dya = alloc_planes(a, R, N, 1);
+  Planes xa = alloc_planes(a, R, K, 1);
+  if (a.failed) { set_last_error("wgrad_mn: workspace too small (%zu < %zu)", ws_bytes, a.off); return PVCR_ERR_WORKSPACE; }
+  PVCR_TRY(stage(dy, lddy, R, N, dya, 0, nullptr, NO_DROPOUT, st));
+  PVCR_TRY(stage(x, ldx, R, K, xa, 0, nullptr, NO_DROPOUT, st));
+  return gemm_mn_store(dya.view(), xa.view(), N, K, R, dw, lddw, accumulate, st);
+}
+
 }  // namespace pvcr

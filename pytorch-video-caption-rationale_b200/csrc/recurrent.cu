@@ -1,6 +1,8 @@
 // Recurrent layers as sequences of (tcgen05 GEMM  h_{t-1} W_hh^T) + fused gate kernels, and the shared
 // gradient GEMM helpers.  Reference: torch.nn.GRU call sites model/S2VTAttModel.py:88-93,142 and
 // model/S2VTModel.py:84,107,122,129; torch.nn.LSTM model/RationaleNet.py:43.
+#include <cstdlib>
+
 #include "host.h"
 
 namespace pvcr {
@@ -8,6 +10,26 @@ namespace pvcr {
 int grad_w(Arena& a, const float* dy, long long lddy, int R, int N, const float* x, long long ldx, int K,
            const long long* x_row_ids, const float* x_row_scale, float* dw, long long lddw, int accumulate,
            int nsplit, cudaStream_t st, Dropout x_drop) {
+  static const bool mn_off = getenv("PVCR_NO_MN_WGRAD") != nullptr;
+  if (nsplit == 1 && !mn_off) {
+    // bf16 mode: MN-major tensor-core operands -- dy and x are only cast (gathered / scaled) row-major, the
+    // contraction runs over their rows; no transposed copies
+    const size_t m = a.mark();
+    Planes dyp = alloc_planes(a, R, N, 1);
+    Planes xp = alloc_planes(a, R, K, 1);
+    int rc = PVCR_OK;
+    if (!a.measuring()) {
+      if (a.failed) { set_last_error("grad_w: workspace too small"); return PVCR_ERR_WORKSPACE; }
+      rc = stage(dy, lddy, R, N, dyp, 0, nullptr, NO_DROPOUT, st);
+      if (rc == PVCR_OK) {
+        if (x_row_ids) rc = gather_split(x, K, x_row_ids, R, xp.ptr, xp.ld, xp.Kp, 1, x_drop, st);
+        else rc = cast_split(x, ldx, R, K, xp.ptr, xp.ld, xp.Kp, 1, 0, x_row_scale, x_drop, st);
+      }
+      if (rc == PVCR_OK) rc = gemm_mn_store(dyp.view(), xp.view(), N, K, R, dw, lddw, accumulate, st);
+    }
+    a.release(m);
+    return rc;
+  }
   const size_t m = a.mark();
   Planes dyT = alloc_planes(a, N, R, nsplit);
   Planes xT = alloc_planes(a, K, R, nsplit);

@@ -41,7 +41,7 @@ size_t vocab_ce_workspace(int B, int L, int H, int Vc, int nsplit, float dropout
   // backward scratch: grad_x (dlogits planes + W^T planes) and grad_w (dlogits^T, hs^T planes)
   size_t peak = 0;
   { size_t m = a.mark(); alloc_planes(a, H, Vc, nsplit); alloc_planes(a, M, Vc, nsplit); peak = a.off; a.release(m); }
-  { size_t m = a.mark(); alloc_planes(a, Vc, M, nsplit); alloc_planes(a, H, M, nsplit); if (a.off > peak) peak = a.off; a.release(m); }
+  { const size_t need = a.mark() + grad_w_scratch(M, Vc, H, nsplit); if (need > peak) peak = need; }
   const size_t fused = nsplit == 1 ? vocab_fused_workspace(M, H, Vc) : 0;
   return (peak > fused ? peak : fused) + 4096;
 }

@@ -70,8 +70,8 @@ struct EpiCeFwd {
 
 struct EpiCeBwd {
   const float* bias; const long long* target; const float *lse2, *roww;      // lse2 = lse * log2(e)
-  bf16* D; long long ldD; bf16* DT; long long ldDT;
-  int M, N, Mp;
+  bf16* D; long long ldD;
+  int M, N;
   float l2, w; int t;
   __device__ __forceinline__ void begin(int row, int) {
     l2 = 0.f; w = 0.f; t = -1;
@@ -109,18 +109,6 @@ struct EpiCeBwd {
       uint4* dst = reinterpret_cast<uint4*>(D + (long long)row * ldD + col0);
 #pragma unroll
       for (int j = 0; j < 4; ++j) dst[j] = reinterpret_cast<const uint4*>(o)[j];
-    }
-    if (row < Mp) {
-      const bf16* ob = reinterpret_cast<const bf16*>(o);
-      bf16* dt = DT + (long long)col0 * ldDT + row;
-      if (full) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) dt[(long long)j * ldDT] = ob[j];
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < N) dt[(long long)j * ldDT] = ob[j];
-      }
     }
   }
   __device__ __forceinline__ void end(int, int, int) {}
@@ -186,30 +174,37 @@ __global__ void row_weights_kernel(const long long* s_len, int B, int L, const f
   w[i] = (l < len ? 1.f / ((float)len * (float)B) : 0.f) * (gscale ? gscale[0] : 1.f);
 }
 
-// out[r] = sum_c in[r*ld + c]  (bf16 in, fp32 accumulate): one warp per row
-__global__ void __launch_bounds__(256) rowsum_bf16_kernel(const bf16* in, long long ld, int R, int C, float* out) {
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (row >= R) return;
-  const bf16* x = in + (long long)row * ld;
-  float s = 0.f;
-  const int C8 = C & ~7;
-  for (int c = lane * 8; c < C8; c += 256) {
-    const uint4 u = *reinterpret_cast<const uint4*>(x + c);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h[k]); s += f.x + f.y; }
+// out[c] += sum_r in[r*ld + c]  (bf16 in, fp32 accumulate; out pre-zeroed): block = 64 column pairs x 4 row lanes
+// over a chunk of CS_ROWS rows, chunk partials merged with atomics
+constexpr int CS_ROWS = 256;
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* in, long long ld, int R, int C, float* out) {
+  __shared__ float2 part[4][64];
+  const int cp = blockIdx.x * 64 + (threadIdx.x & 63), rl = threadIdx.x >> 6, c = cp * 2;
+  const int r_begin = blockIdx.y * CS_ROWS, r_end = min(R, r_begin + CS_ROWS);
+  float2 s = make_float2(0.f, 0.f);
+  if (c < C) {
+#pragma unroll 8
+    for (int r = r_begin + rl; r < r_end; r += 4) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(in + (long long)r * ld + c));
+      s.x += f.x; s.y += f.y;
+    }
   }
-  for (int c = C8 + lane; c < C; c += 32) s += __bfloat162float(x[c]);
-  s = warp_sum(s);
-  if (lane == 0) out[row] = s;
+  part[rl][threadIdx.x & 63] = s;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    float2 t = part[0][threadIdx.x];
+    for (int k = 1; k < 4; ++k) { t.x += part[k][threadIdx.x].x; t.y += part[k][threadIdx.x].y; }
+    atomicAdd(out + c, t.x);
+    if (c + 1 < C) atomicAdd(out + c + 1, t.y);
+  }
 }
 
 struct FusedWs {
-  Planes hs_a, wv, wvT, hsT;
+  Planes hs_a, wv, wvT;
   float *pmax, *psum, *tgt, *nll, *roww;
   int* pidx;
-  bf16 *D, *DT;
-  long long ldD, ldDT;
+  bf16* D;
+  long long ldD;
   int ntiles;
 };
 static void carve_fused(Arena& a, int M, int H, int Vc, FusedWs& w) {
@@ -220,11 +215,8 @@ static void carve_fused(Arena& a, int M, int H, int Vc, FusedWs& w) {
   w.pidx = a.alloc<int>((size_t)M * w.ntiles);
   w.tgt = a.alloc<float>(M); w.nll = a.alloc<float>(M); w.roww = a.alloc<float>(M);
   w.wvT = alloc_planes(a, H, Vc, 1);
-  w.hsT = alloc_planes(a, H, M, 1);
   w.ldD = (long long)cdiv(Vc, CE_BN) * CE_BN;
-  w.ldDT = w.hsT.Kp;
   w.D = a.alloc<bf16>((size_t)M * w.ldD);
-  w.DT = a.alloc<bf16>((size_t)Vc * w.ldDT);
 }
 size_t vocab_fused_workspace(int M, int H, int Vc) {
   Arena a(nullptr, 0);
@@ -282,7 +274,7 @@ int vocab_fused_bwd(const float* hs, const float* wv, const float* bv, const lon
   // recompute the logits tile by tile; the epilogue emits bf16 dlogits (row-major and transposed)
   EpiCeBwd epi{};
   epi.bias = bv; epi.target = target; epi.lse2 = w.nll; epi.roww = w.roww;     // w.nll reused: lse * log2(e)
-  epi.D = w.D; epi.ldD = w.ldD; epi.DT = w.DT; epi.ldDT = w.ldDT; epi.M = M; epi.N = Vc; epi.Mp = (int)w.ldDT;
+  epi.D = w.D; epi.ldD = w.ldD; epi.M = M; epi.N = Vc;
   if (w.ldD > Vc)      // chunks lying entirely past Vc are skipped by the GEMM epilogue: their K-padding must read 0
     PVCR_CUDA_CHECK(cudaMemset2DAsync(w.D + Vc, sizeof(bf16) * w.ldD, 0, sizeof(bf16) * (w.ldD - Vc), M, st));
   GemmCoords gc{M, Vc, (int)w.hs_a.ld, 0, 0, 0, 0};
@@ -294,15 +286,16 @@ int vocab_fused_bwd(const float* hs, const float* wv, const float* bv, const lon
     PVCR_TRY(gemm_planes(dv, w.wvT.view(), M, H, w.wvT.Kp, d_hs, H, nullptr, 0, st));
   }
   if (dropout_p > 0.f) PVCR_TRY(dropout_apply(d_hs, d_hs, (long long)M * H, dr, st));
-  // d W = dlogits^T Dropout(hs)
-  PVCR_TRY(transpose_split(hs, H, M, H, w.hsT.ptr, w.hsT.ld, w.hsT.Kp, 0, 1, 1, 1, nullptr, nullptr, st, dr));
+  // d W = dlogits^T Dropout(hs): both operands as they are (row-major bf16, MN-major tcgen05 operands); hs_a are
+  // the planes staged (with the dropout mask) by the forward pass
   {
-    OperandView dt{w.DT, w.ldDT, 0, Vc, 1};
-    PVCR_TRY(gemm_planes(dt, w.hsT.view(), Vc, H, w.hsT.Kp, d_wv, H, nullptr, 0, st));
+    OperandView dv{w.D, w.ldD, 0, M, 1};
+    PVCR_TRY(gemm_mn_store(dv, w.hs_a.view(), Vc, H, M, d_wv, H, 0, st));
   }
+  PVCR_CUDA_CHECK(cudaMemsetAsync(d_bv, 0, sizeof(float) * Vc, st));
   {
     LaunchScope ls_(KC_LOSS, st);
-    rowsum_bf16_kernel<<<cdiv((long long)Vc * 32, 256), 256, 0, st>>>(w.DT, w.ldDT, Vc, M, d_bv);
+    colsum_bf16_kernel<<<dim3(cdiv(cdiv(Vc, 2), 64), cdiv(M, CS_ROWS)), 256, 0, st>>>(w.D, w.ldD, M, Vc, d_bv);
   }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;

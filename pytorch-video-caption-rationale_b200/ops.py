@@ -39,3 +39,16 @@ def linear_bwd(dy, x, w, need_dx=True, need_dw=True, need_db=True, nsplit=1):
     check(L.pvcr_linear_bwd(ptr(dy), dy.stride(0), ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(dx), K, ptr(dw), K,
                             ptr(db), M, N, K, nsplit, 0, ptr(ws), ws.numel(), stream_ptr()), "pvcr_linear_bwd")
     return dx, dw, db
+
+
+def wgrad_mn(dy, x, accumulate_into=None):
+    """dw = dy.T @ x (bf16 operands cast in place, MN-major tcgen05 operands, fp32 accumulation)."""
+    _req(dy); _req(x)
+    R, N = dy.shape
+    K = x.shape[1]
+    dw = accumulate_into if accumulate_into is not None else torch.empty((N, K), dtype=torch.float32, device=x.device)
+    L = lib()
+    ws = _ws(L.pvcr_wgrad_mn_workspace(R, N, K), x.device)
+    check(L.pvcr_wgrad_mn(ptr(dy), dy.stride(0), ptr(x), x.stride(0), ptr(dw), dw.stride(0), R, N, K,
+                          int(accumulate_into is not None), ptr(ws), ws.numel(), stream_ptr()), "pvcr_wgrad_mn")
+    return dw

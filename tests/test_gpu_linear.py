@@ -70,3 +70,19 @@ def test_linear_strided_views():
     y = ops.linear_fwd(x, wide[:, 512:], None, nsplit=3)
     ref = x.double() @ wide[:, 512:].double().T
     assert _rel(y, ref) < 5e-6
+
+
+@pytest.mark.parametrize("R,N,K", [(64, 64, 64), (128, 256, 128), (200, 300, 100), (3840, 1536, 512), (5120, 1536, 2048),
+                                   (1000, 70, 520)])
+def test_wgrad_mn_major_operands(R, N, K):
+    """dW = dY^T X with both tcgen05 operands MN-major (no transposed staging copies)."""
+    from pvcr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(R + N + K)
+    dy = torch.randn(R, N, device="cuda", generator=g)
+    x = torch.randn(R, K, device="cuda", generator=g)
+    dw = ops.wgrad_mn(dy, x)
+    ref = _bf(dy).double().T @ _bf(x).double()
+    assert _rel(dw, ref) < 1e-5, _rel(dw, ref)          # fp32 accumulation over up to 5120 rows
+    assert float((dw.double() - ref).abs().max()) < 5e-3 * float(ref.abs().max())
+    dw2 = ops.wgrad_mn(dy, x, accumulate_into=dw.clone())
+    assert _rel(dw2, 2 * ref) < 1e-5
