@@ -133,6 +133,20 @@ int gemm_mn_store(const OperandView& a, const OperandView& b, int M, int N, int 
                   int accumulate, cudaStream_t stream) {
   EpiStore epi{C, ldc, 0, nullptr, 0, accumulate, M, N, 0, 1};
   GemmCoords gc{M, N, (int)round_up(K, GEMM_BK), 0, 0, 0, 0};
+  // few output tiles, long contraction (the recurrent weight gradients): spread K ranges over the idle SMs
+  const long long tiles = (long long)cdiv(M, GEMM_BM) * cdiv(N, 256);
+  const int total_kb = gc.K / GEMM_BK;
+  static const bool no_split = getenv("PVCR_NO_SPLITK") != nullptr;
+  if (tiles <= 8 && total_kb >= 16 && !no_split) {      // measured: beyond a handful of tiles the atomics cost more than they save
+    int splits = (int)(148 / tiles);
+    if (splits > total_kb / 8) splits = total_kb / 8;
+    if (splits > 1) {
+      const int kb_per = (total_kb + splits - 1) / splits;
+      gc.k_splits = (total_kb + kb_per - 1) / kb_per;
+      if (!accumulate) PVCR_CUDA_CHECK(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, stream));
+      epi.atomic = 1;
+    }
+  }
   return launch_gemm_tn_persistent<256, 4, EpiStore, true>(a, b, gc, 1, epi, stream);
 }
 

@@ -156,7 +156,9 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_kb = gc.K / GEMM_BK;
+  const int splits = gc.k_splits > 1 ? gc.k_splits : 1;       // work item = (tile, K range); num_tiles counts items
+  const int total_kb = gc.K / GEMM_BK;
+  const int kb_per = (total_kb + splits - 1) / splits;
   const int per_z = tiles_m * tiles_n;
 
   if (warp == 0 && lane == 0) {
@@ -184,11 +186,14 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;                                    // running k-block counter across tiles
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int w = blockIdx.x; w < num_tiles; w += gridDim.x) {
+        const int t = w / splits, kb0 = (w - t * splits) * kb_per;
+        const int num_kb = min(kb_per, total_kb - kb0);
         const int z = t / per_z, r = t - z * per_z;
         const int m0 = (r % tiles_m) * GEMM_BM, n0 = (r / tiles_m) * BN;
         const int az = gc.a_z0 + z * gc.a_zmul, bz = gc.b_z0 + z * gc.b_zmul;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kq = 0; kq < num_kb; ++kq, ++it) {
+          const int kb = kb0 + kq;
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
@@ -211,7 +216,9 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, MN ? 1 : 0, MN ? 1 : 0);
       int it = 0, ti = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+      for (int w = blockIdx.x; w < num_tiles; w += gridDim.x, ++ti) {
+        const int kb0 = (w % splits) * kb_per;
+        const int num_kb = min(kb_per, total_kb - kb0);
         const int acc = ti & 1;
         mbar_wait(&tmem_empty_bar[acc], ((ti >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
@@ -248,13 +255,14 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     const int q = warp & 3, half = (warp - 2) >> 2;
     constexpr int HALF = BN / 2;
     int ti = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+    for (int w = blockIdx.x; w < num_tiles; w += gridDim.x, ++ti) {
+      const int t = w / splits;
       const int z = t / per_z, r = t - z * per_z;
       const int m0 = (r % tiles_m) * GEMM_BM, n0 = (r / tiles_m) * BN;
       const int acc = ti & 1;
       const int row = m0 + q * 32 + lane;
       Epi e = epi;
-      e.begin(row, z);
+      e.begin(row, splits > 1 ? w - t * splits : z);
       mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);
       tc_fence_after();
       float v[32];
@@ -392,7 +400,8 @@ int launch_gemm_tn_persistent(const OperandView& a, const OperandView& b, const 
     attr_set = true;
   }
   const int tiles_m = cdiv(gc.M, GEMM_BM), tiles_n = cdiv(gc.N, BN);
-  const long long num_tiles = (long long)tiles_m * tiles_n * grid_z;
+  PVCR_REQUIRE(gc.k_splits <= 1 || grid_z == 1, "gemm: split-K and batched slabs are exclusive");
+  const long long num_tiles = (long long)tiles_m * tiles_n * grid_z * (gc.k_splits > 1 ? gc.k_splits : 1);
   const int grid = (int)(num_tiles < sms ? num_tiles : sms);
   {
     LaunchScope ls_(KC_GEMM, stream, 2.0 * gc.M * gc.N * (double)gc.K * grid_z);
