@@ -123,10 +123,8 @@ __device__ __forceinline__ void group_wait_w(const unsigned* ctr, unsigned targe
 
 __device__ __forceinline__ void group_arrive(unsigned* ctr) {
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(ctr, 1u);
-  }
+  // release-reduction: publishes (cumulatively, through the CTA barrier above) every thread's writes of this phase
+  if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
 }
 __device__ __forceinline__ void group_wait(const unsigned* ctr, unsigned target) {
   if (threadIdx.x == 0) {
