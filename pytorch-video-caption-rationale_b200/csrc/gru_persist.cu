@@ -198,11 +198,8 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_bwd_kernel(con
   const int H = p.H, u = p.u, bs = p.bs, K = 3 * H, KB = K >> 6;
   uint8_t* sW = smem;                                        // KB x (u rows x 128 B)
   uint8_t* sX = sW + (size_t)KB * u * 128;                   // KB x (bs rows x 128 B)
-  float* sS = reinterpret_cast<float*>(sX + (size_t)KB * bs * 128);
-  const int s_ld = u + 1;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sS + (size_t)bs * s_ld + 2);
-  bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bar) + 7) & ~uintptr_t(7));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  float* sR = reinterpret_cast<float*>(sX + (size_t)KB * bs * 128);     // [8 warps][u][bs] K-slice partial products
+  const int nwarps = PERSIST_THREADS / 32;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int g = blockIdx.x / p.C, c = blockIdx.x % p.C;
@@ -210,21 +207,9 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_bwd_kernel(con
   unsigned* ctr = p.counters + g * 32;
 
   load_operand_rows(sW, u, 0, p.whhT, p.whhT_ld, j0, u, H, K);
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    fence_barrier_init();
-  }
-  const uint32_t ncols = bs <= 32 ? 32u : (bs <= 64 ? 64u : 128u);
-  if (warp == 0) {
-    tmem_alloc(tmem_slot, ncols);
-    tmem_relinquish();
-  }
-  fence_proxy_async();
-  tc_fence_before();
   __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t idesc = umma_idesc_bf16(128, bs);
+  const uint32_t aW = smem_u32(sW), aX = smem_u32(sX);
+  const int lane = tid & 31, gid = lane >> 2, tig = lane & 3;
 
   const int n_items = (u * bs + PERSIST_THREADS - 1) / PERSIST_THREADS;
   float dhc[MAX_ITEMS];
@@ -236,7 +221,6 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_bwd_kernel(con
       if (lb < bs && b0 + lb < p.B) dhc[k] = p.dh_carry[(long long)(b0 + lb) * H + j0 + jj];
     }
   }
-  uint32_t phase = 0;
   unsigned arrivals = 0;
 
   for (int t = p.T - 1; t >= 0; --t) {
@@ -282,26 +266,52 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_bwd_kernel(con
       load_operand_rows_async(sX, bs, 0, xw, K, b0, bs, p.B, K);
       cp_async_commit();
       cp_async_wait<0>();
-      fence_proxy_async();
       __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        issue_swapped_mma(tmem_base, smem_u32(sW), u, smem_u32(sX), bs, K, idesc, bar);
+      // D[u, bs] = W_hh^T slice [u, 3H] x dgh^T: warp w takes the k-steps w, w+8, ... (mma.sync m16n8k16, fp32 acc)
+      float acc[2][2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+      for (int ks = warp; ks < (K >> 4); ks += nwarps) {
+        uint32_t a0[4], a1[4], bq[4];
+        load_a_frag(aW, u, 0, ks << 4, a0);
+        load_b_frag2(aX, bs, 0, ks << 4, bq);
+        mma_bf16_16816(acc[0][0], a0, bq[0], bq[1]);
+        mma_bf16_16816(acc[0][1], a0, bq[2], bq[3]);
+        if (u > 16) {
+          load_a_frag(aW, u, 16, ks << 4, a1);
+          mma_bf16_16816(acc[1][0], a1, bq[0], bq[1]);
+          mma_bf16_16816(acc[1][1], a1, bq[2], bq[3]);
+        }
       }
-      mbar_wait(bar, phase);
-      phase ^= 1;
-      tc_fence_after();
-      if (tid < 128) tmem_to_smem_cols(tmem_base, sS, s_ld, u, bs);
-      tc_fence_before();
+      {
+        float* r = sR + (size_t)warp * u * bs;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          if (mt * 16 < u) {
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+              const int row = mt * 16 + gid, col = nt * 8 + 2 * tig;
+              r[row * bs + col] = acc[mt][nt][0]; r[row * bs + col + 1] = acc[mt][nt][1];
+              r[(row + 8) * bs + col] = acc[mt][nt][2]; r[(row + 8) * bs + col + 1] = acc[mt][nt][3];
+            }
+          }
+        }
+      }
       __syncthreads();
 #pragma unroll
       for (int k = 0; k < MAX_ITEMS; ++k) {
         if (k < n_items && zreg[k] != 0.f) {
           const int idx = tid + k * PERSIST_THREADS, jj = idx % u, lb = idx / u;
-          dhc[k] += sS[lb * s_ld + jj];
+          float s = 0.f;
+          for (int w = 0; w < nwarps; ++w) s += sR[(size_t)w * u * bs + jj * bs + lb];
+          dhc[k] += s;
         }
       }
-      __syncthreads();     // sS is rewritten by the next step
+      __syncthreads();     // sR / sX are rewritten by the next step
     }
   }
 #pragma unroll
@@ -310,12 +320,6 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_bwd_kernel(con
       const int idx = tid + k * PERSIST_THREADS, jj = idx % u, lb = idx / u;
       if (lb < bs && b0 + lb < p.B) p.dh_carry[(long long)(b0 + lb) * H + j0 + jj] = dhc[k];
     }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, ncols);
   }
 }
 
@@ -344,7 +348,8 @@ static bool plan_gru(int B, int H, int k_rows_fwd, PersistPlan& pl, bool backwar
   const size_t K = backward ? (size_t)3 * H : (size_t)H;
   const size_t rows = backward ? (size_t)u : (size_t)3 * u;
   const size_t w = (K / 64) * rows * 128, x = (K / 64) * pl.bs * 128;
-  const size_t s = (size_t)pl.bs * (rows + 1) * 4 + 64;
+  const size_t s = backward ? (size_t)(PERSIST_THREADS / 32) * pl.u * pl.bs * 4 + 64 : (size_t)pl.bs * (rows + 1) * 4 + 64;
+  if (backward && (pl.u % 16 != 0 || pl.bs != 16)) return false;      // mma.sync tiling of the backward product
   size_t total = w + x + s;
   // the 128-row MMA tile of the last k-block over-reads (128 - rows) * 128 bytes past the weight slice
   const size_t need_tail = (128 - rows) * 128;

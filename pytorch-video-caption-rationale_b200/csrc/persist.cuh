@@ -205,6 +205,35 @@ __device__ __forceinline__ void tmem_to_smem_cols(uint32_t tmem_base, float* S, 
   }
 }
 
+// ---- warp-level mma.sync path for the skinny backward products -------------------------------------------------
+// tcgen05.mma costs ~70 cycles per instruction on these shapes whatever M (64/128), N (16/32), the number of
+// accumulators or issuing threads (measured), i.e. K/16 x 70 cycles per product.  A 16..32-row weight slice
+// times 16..32 videos is only a handful of m16n8k16 tiles, so for the long-K backward products the legacy warp MMA
+// with the K range split over the 8 warps is several times faster; operands stay in the same swizzled layout.
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// A fragment (16 rows x 16 k) of a SW128 operand: rows m0.., k0.. (k0 % 16 == 0)
+__device__ __forceinline__ void load_a_frag(uint32_t base, int rows_alloc, int m0, int k0, uint32_t (&a)[4]) {
+  const int lane = threadIdx.x & 31;
+  const int row = m0 + (lane & 15), k = k0 + ((lane >> 4) << 3);
+  ldmatrix_x4(base + sw128_offset(row, k, rows_alloc), a);      // a0: rows 0-7 k 0-7, a1: rows 8-15 k 0-7, a2/a3: k 8-15
+}
+// B fragments for two n-tiles (16 "videos" x 16 k) of a SW128 operand stored [video][k]:
+// b[0], b[1] = (k 0-7, k 8-15) of videos n0..n0+7;  b[2], b[3] = same for videos n0+8..n0+15
+__device__ __forceinline__ void load_b_frag2(uint32_t base, int rows_alloc, int n0, int k0, uint32_t (&b)[4]) {
+  const int lane = threadIdx.x & 31;
+  const int row = n0 + (lane & 7) + ((lane >> 4) << 3), k = k0 + (((lane >> 3) & 1) << 3);
+  ldmatrix_x4(base + sw128_offset(row, k, rows_alloc), b);
+}
+
 #endif  // __CUDACC__
 
 }  // namespace pvcr
