@@ -330,11 +330,11 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
 //                        B4  dh_{i-1} += W_q^T dq                                         (tcgen05), carry in registers
 // d enc / d proj_key / d v do not feed back into the recurrence and are accumulated after the sweep by
 // attn_grad_hoisted from the saved alpha, d score, dctx and q.
-// In the two MMA phases (B2, B4) warp 7 switches to the MMA-issue role while warps 0..6 stream the K-chunks of the
-// exchange buffer into shared memory, so the next chunk's load overlaps the tcgen05 issue of the current one (chunk
-// hand-over through the mbarriers xready[] / xfree[]); in all other phases the 8 warps work alike.
+// The two products of a step have 16-row weight slices and a long contraction (3H / 4H): they run on warp-level
+// mma.sync (K range of every chunk split over the 8 warps, partial tiles reduced through shared memory), which is
+// several times faster here than tcgen05.mma's ~70 cycles per K=16 step (persist.cuh); the K-chunks of the exchange
+// buffer stream in with cp.async, two in flight, overlapping the MMAs of the previous chunk.
 constexpr int DEC_BWD_THREADS = DEC_THREADS;
-constexpr int DEC_LOADERS = DEC_THREADS - 32;
 template <int NF>
 __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(const DecPersistBwd p) {
   extern __shared__ uint8_t smem_raw[];
@@ -344,7 +344,8 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
   uint8_t* sWB = sWA + (size_t)3 * KBH * u * 128;              // 4*KBH k-blocks
   uint8_t* sX0 = sWB + (size_t)4 * KBH * u * 128;              // chunk buffers: KBH x (bsp x 128 B) each
   uint8_t* sX1 = sX0 + (size_t)KBH * bsp * 128;
-  float* sSA = reinterpret_cast<float*>(sX1 + (size_t)KBH * bsp * 128);
+  float* sR = reinterpret_cast<float*>(sX1 + (size_t)KBH * bsp * 128);     // [8 warps][u][bsp] partial products
+  float* sSA = sR + (size_t)(DEC_THREADS / 32) * u * bsp;
   const int s_ld = u + 1;
   float* sSB = sSA + (size_t)bsp * s_ld;
   const int DG = H >> 3, FG = DEC_THREADS / DG, PW = DG >= 32 ? DG / 32 : 1;
@@ -352,8 +353,6 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
   float* sDa = sP + (size_t)N * PW;         // [N] d alpha -> d score
   float* sAl = sDa + N;                     // [N] alpha
   float* sC = sAl + N;                      // [FG][H]
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sC + (size_t)FG * H) + 15) & ~uintptr_t(7));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int g = blockIdx.x / C, c = blockIdx.x % C;
@@ -363,23 +362,45 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
 
   load_operand_rows(sWA, u, 0, p.wcT, p.wcT_ld, j0, u, H, 3 * H);
   load_operand_rows(sWB, u, 0, p.wcatT, p.wcatT_ld, j0, u, H, 4 * H);
-  if (tid == 0) {
-    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
-    mbar_init(&bars[3], DEC_LOADERS); mbar_init(&bars[4], DEC_LOADERS);      // xready[0], xready[1]
-    fence_barrier_init();
-  }
-  const uint32_t ncols = 2 * bsp <= 32 ? 32u : (2 * bsp <= 64 ? 64u : (2 * bsp <= 128 ? 128u : 256u));
-  if (warp == 0) {
-    tmem_alloc(tmem_slot, ncols);
-    tmem_relinquish();
-  }
-  fence_proxy_async();
-  tc_fence_before();
   __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_a = *tmem_slot, tmem_b = tmem_a + (uint32_t)bsp;
-  const uint32_t idesc = umma_idesc_bf16(64, bsp);      // 64-row A tiles: the slices hold u <= 32 useful rows
   const uint32_t aWA = smem_u32(sWA), aWB = smem_u32(sWB), aX0 = smem_u32(sX0), aX1 = smem_u32(sX1);
+  const int lane = tid & 31, gid = lane >> 2, tig = lane & 3, nwarps = DEC_THREADS / 32;
+  const int ksteps = H >> 4;               // k-steps of 16 per chunk
+  // one 16-row m-tile (u == 16), bsp / 8 n-tiles of 8 videos
+  auto mma_chunk = [&](float (&acc)[4][4], uint32_t aW, int wk0, uint32_t aX) {
+    for (int ks = warp; ks < ksteps; ks += nwarps) {
+      uint32_t a[4], bq[4];
+      load_a_frag(aW, u, 0, wk0 + (ks << 4), a);
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        if (np * 16 < bsp) {
+          load_b_frag2(aX, bsp, np * 16, ks << 4, bq);
+          mma_bf16_16816(acc[2 * np], a, bq[0], bq[1]);
+          mma_bf16_16816(acc[2 * np + 1], a, bq[2], bq[3]);
+        }
+      }
+    }
+  };
+  // partial tiles of the 8 warps -> S[video * s_ld + row]
+  auto reduce_tiles = [&](float (&acc)[4][4], float* S) {
+    float* r = sR + (size_t)warp * u * bsp;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      if (nt * 8 < bsp) {
+        const int col = nt * 8 + 2 * tig;
+        if (gid < u) { r[gid * bsp + col] = acc[nt][0]; r[gid * bsp + col + 1] = acc[nt][1]; }
+        if (gid + 8 < u) { r[(gid + 8) * bsp + col] = acc[nt][2]; r[(gid + 8) * bsp + col + 1] = acc[nt][3]; }
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < u * bsp; idx += DEC_THREADS) {
+      const int row = idx / bsp, col = idx - row * bsp;
+      float s = 0.f;
+      for (int w = 0; w < nwarps; ++w) s += sR[(size_t)w * u * bsp + idx];
+      S[col * s_ld + row] = s;
+    }
+    __syncthreads();
+  };
 
   // attention residency (as in the forward kernel)
   const int vb = min(b0 + c, B - 1);
@@ -415,9 +436,6 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
   float dhc[DEC_ITEMS];
 #pragma unroll
   for (int k = 0; k < DEC_ITEMS; ++k) dhc[k] = 0.f;
-  uint32_t n0 = 0, n1 = 0, phA = 0;       // completions of xfree[0] / xfree[1] consumed so far
-  uint32_t r0 = 0, r1 = 0;                 // completions of xready[0] / xready[1] consumed (MMA role)
-  const bool mma_role = (warp == 7);
   unsigned target = 0;
   const long long xrow = (long long)5 * H;
 
@@ -457,50 +475,39 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
     // ---- B2: dctx = W_c^T [drp|dzp|dnp] ; dh part = W_hh^T [drp|dzp|dghn] -------------------------------------
     group_wait(ctr, target);
     phase_stamp(p.dbg, L - 1 - i, 2);
-    if (mma_role) {
-      if ((tid & 31) == 0) {
-        mbar_wait(&bars[3], r0 & 1); ++r0; tc_fence_after();                  // drp  -> X0
-        issue_mma_chunk(tmem_a, aWA, u, 0, aX0, bsp, H, idesc, false);
-        issue_mma_chunk(tmem_b, aWB, u, KBH, aX0, bsp, H, idesc, false);
-        umma_commit(&bars[0]);
-        mbar_wait(&bars[4], r1 & 1); ++r1; tc_fence_after();                  // dzp  -> X1
-        issue_mma_chunk(tmem_a, aWA, u, KBH, aX1, bsp, H, idesc, true);
-        issue_mma_chunk(tmem_b, aWB, u, 2 * KBH, aX1, bsp, H, idesc, true);
-        umma_commit(&bars[1]);
-        mbar_wait(&bars[3], r0 & 1); ++r0; tc_fence_after();                  // dnp  -> X0, completes dctx
-        issue_mma_chunk(tmem_a, aWA, u, 2 * KBH, aX0, bsp, H, idesc, true);
-        umma_commit(&bars[0]);
-        umma_commit(&bars[2]);
-        mbar_wait(&bars[4], r1 & 1); ++r1; tc_fence_after();                  // dghn -> X1
-        issue_mma_chunk(tmem_b, aWB, u, 3 * KBH, aX1, bsp, H, idesc, true);
-        umma_commit(&bars[1]);
-      }
-      __syncwarp();
-      n0 += 1; n1 += 1;                      // the loaders consumed one completion of each xfree barrier here
-    } else {
-      // two chunks in flight at a time (cp.async): drp -> X0, dzp -> X1, then dnp -> X0, dghn -> X1
-      load_operand_rows_async(sX0, bsp, 0, xg + H, xrow, b0, bsp, b0 + bs, H, DEC_LOADERS);
-      cp_async_commit();
-      load_operand_rows_async(sX1, bsp, 0, xg + 2 * H, xrow, b0, bsp, b0 + bs, H, DEC_LOADERS);
-      cp_async_commit();
-      cp_async_wait<1>(); fence_proxy_async(); mbar_arrive(&bars[3]);
-      cp_async_wait<0>(); fence_proxy_async(); mbar_arrive(&bars[4]);
-      mbar_wait(&bars[0], n0 & 1); ++n0;
-      load_operand_rows_async(sX0, bsp, 0, xg + 4 * H, xrow, b0, bsp, b0 + bs, H, DEC_LOADERS);
-      cp_async_commit();
-      mbar_wait(&bars[1], n1 & 1); ++n1;
-      load_operand_rows_async(sX1, bsp, 0, xg + 3 * H, xrow, b0, bsp, b0 + bs, H, DEC_LOADERS);
-      cp_async_commit();
-      cp_async_wait<1>(); fence_proxy_async(); mbar_arrive(&bars[3]);
-      cp_async_wait<0>(); fence_proxy_async(); mbar_arrive(&bars[4]);
-    }
-    phase_stamp(p.dbg, L - 1 - i, 3);
-    mbar_wait(&bars[2], phA); phA ^= 1;
-    tc_fence_after();
-    phase_stamp(p.dbg, L - 1 - i, 4);
-    if (tid < 128) tmem64_to_smem_cols(tmem_a, sSA, s_ld, u, bsp);
-    tc_fence_before();
+    float accA[4][4], accB[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { accA[nt][e] = 0.f; accB[nt][e] = 0.f; }
+    // chunks drp -> X0, dzp -> X1 in flight; then dnp -> X0, dghn -> X1 behind the MMAs that free the buffers
+    load_operand_rows_async(sX0, bsp, 0, xg + H, xrow, b0, bsp, b0 + bs, H);
+    cp_async_commit();
+    load_operand_rows_async(sX1, bsp, 0, xg + 2 * H, xrow, b0, bsp, b0 + bs, H);
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
+    mma_chunk(accA, aWA, 0, aX0);                 // drp: W_c^T chunk 0, [W_q|W_hh]^T chunk 1
+    mma_chunk(accB, aWB, H, aX0);
+    __syncthreads();
+    load_operand_rows_async(sX0, bsp, 0, xg + 4 * H, xrow, b0, bsp, b0 + bs, H);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    mma_chunk(accA, aWA, H, aX1);                 // dzp
+    mma_chunk(accB, aWB, 2 * H, aX1);
+    __syncthreads();
+    load_operand_rows_async(sX1, bsp, 0, xg + 3 * H, xrow, b0, bsp, b0 + bs, H);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    mma_chunk(accA, aWA, 2 * H, aX0);             // dnp: completes dctx
+    cp_async_wait<0>();
+    __syncthreads();
+    mma_chunk(accB, aWB, 3 * H, aX1);             // dghn
+    phase_stamp(p.dbg, L - 1 - i, 3);
+    phase_stamp(p.dbg, L - 1 - i, 4);
+    reduce_tiles(accA, sSA);
     {
       float* dc = p.dctx_all + (long long)i * B * H;
       for (int idx = tid; idx < u * bs; idx += DEC_THREADS) {
@@ -602,28 +609,14 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
     // ---- B4: dh_{i-1} = dh z + W_hh^T dgh + W_q^T dq -----------------------------------------------------------
     group_wait(ctr, target);
     phase_stamp(p.dbg, L - 1 - i, 8);
-    if (mma_role) {
-      if ((tid & 31) == 0) {
-        mbar_wait(&bars[3], r0 & 1); ++r0; tc_fence_after();                  // dq   -> X0, completes dh
-        issue_mma_chunk(tmem_b, aWB, u, 0, aX0, bsp, H, idesc, true);
-        umma_commit(&bars[0]);
-      }
-      __syncwarp();
-      n0 += 1;
-    } else {
-      mbar_wait(&bars[0], n0 & 1); ++n0;     // chunk dnp retired: X0 is free
-      load_operand_rows_async(sX0, bsp, 0, xg, xrow, b0, bsp, b0 + bs, H, DEC_LOADERS);
-      cp_async_commit();
-      cp_async_wait<0>(); fence_proxy_async(); mbar_arrive(&bars[3]);
-    }
-    phase_stamp(p.dbg, L - 1 - i, 9);
-    mbar_wait(&bars[1], n1 & 1); ++n1;       // chunk dghn retired (X1 free for the next step)
-    mbar_wait(&bars[0], n0 & 1); ++n0;
-    phase_stamp(p.dbg, L - 1 - i, 10);
-    tc_fence_after();
-    if (tid < 128) tmem64_to_smem_cols(tmem_b, sSB, s_ld, u, bsp);
-    tc_fence_before();
+    load_operand_rows_async(sX0, bsp, 0, xg, xrow, b0, bsp, b0 + bs, H);
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
+    mma_chunk(accB, aWB, 0, aX0);                 // dq: completes dh
+    phase_stamp(p.dbg, L - 1 - i, 9);
+    phase_stamp(p.dbg, L - 1 - i, 10);
+    reduce_tiles(accB, sSB);
 #pragma unroll
     for (int k = 0; k < DEC_ITEMS; ++k) {
       if (k < n_items) {
@@ -639,12 +632,6 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
       const int idx = tid + k * DEC_THREADS, jj = idx % u, lb = idx / u;
       if (lb < bs) p.dh_carry[(long long)(b0 + lb) * H + j0 + jj] = dhc[k];
     }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem_a, ncols);
   }
 }
 
@@ -795,7 +782,8 @@ int dec_persist_bwd(const DecPersistBwd& p0, cudaStream_t st) {
   const int H = p.H, KBH = H / 64, DG = H / 8, FG = DEC_THREADS / DG, PW = DG >= 32 ? DG / 32 : 1;
   size_t smem = (size_t)7 * KBH * pl.u * 128 + (size_t)2 * KBH * pl.bsp * 128;
   smem += ((size_t)2 * pl.bsp * (pl.u + 1) + (size_t)p.N * PW + 2 * p.N + (size_t)FG * H) * 4 + 64 + 1024;
-  smem += 16 * 1024;     // the 128-row MMA tile of the last weight k-blocks over-reads up to 16 KB past the slices
+  smem += (size_t)(DEC_THREADS / 32) * pl.u * pl.bsp * 4;        // partial product tiles of the 8 warps
+  PVCR_REQUIRE(pl.u == 16 || pl.u == 8, "dec_persist_bwd: unit slice u=%d not supported by the mma.sync tiling", pl.u);
   PVCR_REQUIRE(smem <= 227 * 1024, "dec_persist_bwd: needs %zu B of shared memory", smem);
   const void* kern = pl.NF == 2 ? (const void*)dec_persist_bwd_kernel<2>
                      : (pl.NF == 5 ? (const void*)dec_persist_bwd_kernel<5> : (const void*)dec_persist_bwd_kernel<10>);
