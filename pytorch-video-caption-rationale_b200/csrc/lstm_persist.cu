@@ -156,10 +156,8 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) lstm_persist_bwd_kernel(co
   const int H = p.H, u = p.u, bs = p.bs, K = 4 * H, KB = K >> 6;
   uint8_t* sW = smem;
   uint8_t* sX = sW + (size_t)KB * u * 128;
-  float* sS = reinterpret_cast<float*>(sX + (size_t)KB * bs * 128);
-  const int s_ld = u + 1;
-  uint64_t* bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sS + (size_t)bs * s_ld + 2) + 7) & ~uintptr_t(7));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  float* sR = reinterpret_cast<float*>(sX + (size_t)KB * bs * 128);     // [8 warps][u][bs] K-slice partial products
+  const int nwarps = PERSIST_THREADS / 32;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int g = blockIdx.x / p.C, c = blockIdx.x % p.C;
@@ -167,27 +165,14 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) lstm_persist_bwd_kernel(co
   unsigned* ctr = p.counters + g * 32;
 
   load_operand_rows(sW, u, 0, p.whhT, p.whhT_ld, j0, u, H, K);
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    fence_barrier_init();
-  }
-  const uint32_t ncols = bs <= 32 ? 32u : 64u;
-  if (warp == 0) {
-    tmem_alloc(tmem_slot, ncols);
-    tmem_relinquish();
-  }
-  fence_proxy_async();
-  tc_fence_before();
   __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t idesc = umma_idesc_bf16(64, bs);            // 64-row tiles: u <= 32 useful rows
+  const uint32_t aW = smem_u32(sW), aX = smem_u32(sX);
+  const int lane = tid & 31, gid = lane >> 2, tig = lane & 3;
 
   const int n_items = (u * bs + PERSIST_THREADS - 1) / PERSIST_THREADS;
   float dhc[LSTM_ITEMS], dcc[LSTM_ITEMS];
 #pragma unroll
   for (int k = 0; k < LSTM_ITEMS; ++k) { dhc[k] = 0.f; dcc[k] = 0.f; }
-  uint32_t phase = 0;
   unsigned arrivals = 0;
 
   for (int s = p.T - 1; s >= 0; --s) {
@@ -230,33 +215,50 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) lstm_persist_bwd_kernel(co
       load_operand_rows_async(sX, bs, 0, xw, K, b0, bs, p.B, K);
       cp_async_commit();
       cp_async_wait<0>();
-      fence_proxy_async();
       __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        issue_swapped_mma(tmem_base, smem_u32(sW), u, smem_u32(sX), bs, K, idesc, bar);
+      // dh carry [u, bs] = W_hh^T slice [u, 4H] x da^T: mma.sync m16n8k16, k-steps dealt over the 8 warps
+      float acc[2][2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+      for (int ks = warp; ks < (K >> 4); ks += nwarps) {
+        uint32_t a0[4], a1[4], bq[4];
+        load_a_frag(aW, u, 0, ks << 4, a0);
+        load_a_frag(aW, u, 16, ks << 4, a1);
+        load_b_frag2(aX, bs, 0, ks << 4, bq);
+        mma_bf16_16816(acc[0][0], a0, bq[0], bq[1]);
+        mma_bf16_16816(acc[0][1], a0, bq[2], bq[3]);
+        mma_bf16_16816(acc[1][0], a1, bq[0], bq[1]);
+        mma_bf16_16816(acc[1][1], a1, bq[2], bq[3]);
       }
-      mbar_wait(bar, phase);
-      phase ^= 1;
-      tc_fence_after();
-      if (tid < 128) tmem64_to_smem_cols(tmem_base, sS, s_ld, u, bs);
-      tc_fence_before();
+      {
+        float* r = sR + (size_t)warp * u * bs;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            const int row = mt * 16 + gid, col = nt * 8 + 2 * tig;
+            r[row * bs + col] = acc[mt][nt][0]; r[row * bs + col + 1] = acc[mt][nt][1];
+            r[(row + 8) * bs + col] = acc[mt][nt][2]; r[(row + 8) * bs + col + 1] = acc[mt][nt][3];
+          }
+      }
       __syncthreads();
 #pragma unroll
       for (int k = 0; k < LSTM_ITEMS; ++k) {
         if (k < n_items) {
           const int idx = tid + k * PERSIST_THREADS, jj = idx % u, lb = idx / u;
-          if (lb < bs && b0 + lb < p.B) dhc[k] = sS[lb * s_ld + jj];
+          if (lb < bs && b0 + lb < p.B) {
+            float s = 0.f;
+            for (int w = 0; w < nwarps; ++w) s += sR[(size_t)w * u * bs + jj * bs + lb];
+            dhc[k] = s;
+          }
         }
       }
       __syncthreads();
     }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, ncols);
   }
 }
 
@@ -279,7 +281,7 @@ static bool plan_lstm(int B, int H, LstmPlan& pl) {
   if (pl.u * pl.bs > LSTM_ITEMS * PERSIST_THREADS) return false;
   const size_t KBf = H / 64, KBb = 4 * H / 64;
   pl.smem_f = KBf * 128 * 128 + KBf * pl.bs * 128 + (size_t)pl.bs * 129 * 4 + 64 + 1024;
-  pl.smem_b = KBb * pl.u * 128 + KBb * pl.bs * 128 + (size_t)pl.bs * 33 * 4 + 64 + 1024 + 16 * 1024;
+  pl.smem_b = KBb * pl.u * 128 + KBb * pl.bs * 128 + (size_t)(PERSIST_THREADS / 32) * pl.u * pl.bs * 4 + 64 + 1024;
   return pl.smem_f <= 227 * 1024 && pl.smem_b <= 227 * 1024;
 }
 
