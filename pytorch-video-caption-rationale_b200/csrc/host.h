@@ -10,10 +10,12 @@ const char* last_error();
 
 // Bump allocator over a caller-provided workspace.  With base == nullptr it only measures (used by the
 // *_workspace_bytes queries, so sizing and carving share one code path).
+struct StageCache;
 struct Arena {
   char* base;
   size_t cap, off;
   bool failed;
+  StageCache* cache = nullptr;   // optional: bf16 planes already staged in this call, keyed by their fp32 source
   Arena(void* b, size_t c) : base(static_cast<char*>(b)), cap(c), off(0), failed(false) {}
   template <class T>
   T* alloc(size_t n) {
@@ -48,6 +50,23 @@ inline Planes alloc_planes(Arena& a, int rows, int K, int nsplit) {
 
 int gemm_store(const OperandView& a, const OperandView& b, const GemmCoords& gc, int grid_z, float* C, long long ldc,
                long long c_zstride, const float* bias, long long bias_zstride, int accumulate, cudaStream_t stream);
+
+// bf16 (single-plane) copies of fp32 matrices staged during one backward call: the hoisted gradient GEMMs share
+// operands (d gi feeds dW_c, dW_e and d emb; the forward pass already staged vid / enc / embedded words), so each
+// source is cast once.  Key = (source pointer, leading dimension, rows, cols); gathers are keyed by their id array.
+struct StageCache {
+  struct Entry { const void* src; long long ld; int R, C; Planes p; };
+  Entry e[24];
+  int n = 0;
+  const Planes* find(const void* src, long long ld, int R, int C) const {
+    for (int i = 0; i < n; ++i)
+      if (e[i].src == src && e[i].ld == ld && e[i].R == R && e[i].C == C) return &e[i].p;
+    return nullptr;
+  }
+  void put(const void* src, long long ld, int R, int C, const Planes& p) {
+    if (n < 24) e[n++] = Entry{src, ld, R, C, p};
+  }
+};
 
 // C[M,N] (+)= A^T B for row-major bf16 A [K rows, M cols], B [K rows, N cols] (MN-major tcgen05 operands)
 int gemm_mn_store(const OperandView& a, const OperandView& b, int M, int N, int K, float* C, long long ldc,

@@ -14,18 +14,42 @@ int grad_w(Arena& a, const float* dy, long long lddy, int R, int N, const float*
   if (nsplit == 1 && !mn_off) {
     // bf16 mode: MN-major tensor-core operands -- dy and x are only cast (gathered / scaled) row-major, the
     // contraction runs over their rows; no transposed copies
-    const size_t m = a.mark();
-    Planes dyp = alloc_planes(a, R, N, 1);
-    Planes xp = alloc_planes(a, R, K, 1);
+    // operands already staged in this call (or by the forward pass) are reused; new ones are staged once and kept
+    StageCache* sc = a.measuring() ? nullptr : a.cache;
+    const bool x_plain = !x_row_scale && x_drop.p <= 0.f;
+    const void* xkey = x_row_ids ? (const void*)x_row_ids : (const void*)x;
+    const long long xkey_ld = x_row_ids ? -1 : ldx;
+    const Planes* dy_hit = sc ? sc->find(dy, lddy, R, N) : nullptr;
+    const Planes* x_hit = sc ? sc->find(xkey, xkey_ld, R, K) : nullptr;
+    Planes dyp, xp;
     int rc = PVCR_OK;
+    if (sc && !dy_hit) {                       // persistent (cached) allocation: outside the mark / release window
+      dyp = alloc_planes(a, R, N, 1);
+      if (a.failed) { set_last_error("grad_w: workspace too small"); return PVCR_ERR_WORKSPACE; }
+      PVCR_TRY(stage(dy, lddy, R, N, dyp, 0, nullptr, NO_DROPOUT, st));
+      sc->put(dy, lddy, R, N, dyp);
+      dy_hit = sc->find(dy, lddy, R, N);
+    }
+    if (sc && !x_hit && x_plain && !x_row_ids) {
+      xp = alloc_planes(a, R, K, 1);
+      if (a.failed) { set_last_error("grad_w: workspace too small"); return PVCR_ERR_WORKSPACE; }
+      PVCR_TRY(cast_split(x, ldx, R, K, xp.ptr, xp.ld, xp.Kp, 1, 0, nullptr, NO_DROPOUT, st));
+      sc->put(xkey, xkey_ld, R, K, xp);
+      x_hit = sc->find(xkey, xkey_ld, R, K);
+    }
+    const size_t m = a.mark();
+    if (!dy_hit) dyp = alloc_planes(a, R, N, 1);
+    if (!x_hit) xp = alloc_planes(a, R, K, 1);
     if (!a.measuring()) {
       if (a.failed) { set_last_error("grad_w: workspace too small"); return PVCR_ERR_WORKSPACE; }
-      rc = stage(dy, lddy, R, N, dyp, 0, nullptr, NO_DROPOUT, st);
-      if (rc == PVCR_OK) {
+      if (!dy_hit) rc = stage(dy, lddy, R, N, dyp, 0, nullptr, NO_DROPOUT, st);
+      if (rc == PVCR_OK && !x_hit) {
         if (x_row_ids) rc = gather_split(x, K, x_row_ids, R, xp.ptr, xp.ld, xp.Kp, 1, x_drop, st);
         else rc = cast_split(x, ldx, R, K, xp.ptr, xp.ld, xp.Kp, 1, 0, x_row_scale, x_drop, st);
       }
-      if (rc == PVCR_OK) rc = gemm_mn_store(dyp.view(), xp.view(), N, K, R, dw, lddw, accumulate, st);
+      if (rc == PVCR_OK)
+        rc = gemm_mn_store((dy_hit ? *dy_hit : dyp).view_rows(0, R), (x_hit ? *x_hit : xp).view_rows(0, R), N, K, R, dw,
+                           lddw, accumulate, st);
     }
     a.release(m);
     return rc;
@@ -46,13 +70,24 @@ int grad_w(Arena& a, const float* dy, long long lddy, int R, int N, const float*
 
 int grad_x(Arena& a, const float* dy, long long lddy, int R, int N, const Planes& wT, float* dx, long long lddx,
            int accumulate, cudaStream_t st) {
+  StageCache* sc = (a.measuring() || wT.nsplit != 1) ? nullptr : a.cache;
+  const Planes* hit = sc ? sc->find(dy, lddy, R, N) : nullptr;
+  if (sc && !hit) {
+    Planes keep = alloc_planes(a, R, N, 1);
+    if (a.failed) { set_last_error("grad_x: workspace too small"); return PVCR_ERR_WORKSPACE; }
+    PVCR_TRY(stage(dy, lddy, R, N, keep, 0, nullptr, NO_DROPOUT, st));
+    sc->put(dy, lddy, R, N, keep);
+    hit = sc->find(dy, lddy, R, N);
+  }
   const size_t m = a.mark();
-  Planes dya = alloc_planes(a, R, N, wT.nsplit);
+  Planes dya;
+  if (!hit) dya = alloc_planes(a, R, N, wT.nsplit);
   int rc = PVCR_OK;
   if (!a.measuring()) {
     if (a.failed) { set_last_error("grad_x: workspace too small"); return PVCR_ERR_WORKSPACE; }
-    rc = stage(dy, lddy, R, N, dya, 0, nullptr, NO_DROPOUT, st);
-    if (rc == PVCR_OK) rc = gemm_planes(dya.view(), wT.view(), R, wT.rows, (int)dya.ld, dx, lddx, nullptr, accumulate, st);
+    if (!hit) rc = stage(dy, lddy, R, N, dya, 0, nullptr, NO_DROPOUT, st);
+    const Planes& A = hit ? *hit : dya;
+    if (rc == PVCR_OK) rc = gemm_planes(A.view(), wT.view(), R, wT.rows, (int)A.ld, dx, lddx, nullptr, accumulate, st);
   }
   a.release(m);
   return rc;

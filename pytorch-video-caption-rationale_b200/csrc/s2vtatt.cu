@@ -107,11 +107,22 @@ static void carve(Arena& a, const PvcrDims& d, int need_frame_grad, AttWs& w) {
   w.ctx_x = a.alloc<bf16>(BL * H);
 }
 
+// bf16 copies kept by the staging cache of one backward call (bf16 mode)
+static size_t stage_cache_need(const PvcrDims& d) {
+  Arena a(nullptr, 0);
+  const int BL = d.B * d.L, BN = d.B * d.N, H = d.H;
+  alloc_planes(a, BL, H, 1); alloc_planes(a, BL, 3 * H, 1); alloc_planes(a, BL, H, 1);      // dq, dgh, h_prev
+  alloc_planes(a, BL, 3 * H, 1); alloc_planes(a, BL, H, 1);                                  // dgi, ctx
+  alloc_planes(a, BN, H, 1);                                                                 // dpk
+  alloc_planes(a, BN, 3 * H, 1); alloc_planes(a, BN, H, 1); alloc_planes(a, BN, 3 * H, 1);   // dgh_enc, h_prev_enc, dgi_enc
+  return a.off + 4096;
+}
+
 size_t s2vtatt_workspace(const PvcrDims& d, int need_frame_grad) {
   Arena a(nullptr, 0);
   AttWs w;
   carve(a, d, need_frame_grad, w);
-  return a.off + scratch_need(d, need_frame_grad) + 1024;
+  return a.off + scratch_need(d, need_frame_grad) + stage_cache_need(d) + 1024;
 }
 
 static int check_dims(const PvcrDims& d) {
@@ -224,9 +235,17 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   Arena a(ws, ws_bytes);
   AttWs w;
   carve(a, d, need_frame_grad, w);
-  if (a.failed || a.off + scratch_need(d, need_frame_grad) > ws_bytes) {
+  if (a.failed || a.off + scratch_need(d, need_frame_grad) + stage_cache_need(d) > ws_bytes) {
     set_last_error("s2vtatt_bwd: workspace too small (%zu bytes)", ws_bytes);
     return PVCR_ERR_WORKSPACE;
+  }
+  StageCache cache;
+  if (ns == 1) {
+    a.cache = &cache;
+    // operands the forward pass already staged as bf16 planes (same values: frame scale / no dropout included)
+    if (!frame_scale) cache.put(vid, V, BN, V, w.x_a);
+    cache.put(w.enc, H, BN, H, w.enc_a);
+    cache.put(s_in, -1, BL, E, w.emb_a);
   }
   // transposed weights for the data-gradient GEMMs
   PVCR_TRY(prep_weight_T(p.dec_w_ih, H + E, H3, H, w.wcT, 0, 1, st));
@@ -334,6 +353,7 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
                                       sizeof(float) * (size_t)(N - 1) * H, B, cudaMemcpyDeviceToDevice, st));
   PVCR_TRY(grad_w(a, w.dgh_enc, H3, BN, H3, w.hprev_enc, H, H, nullptr, nullptr, g.enc_w_hh, H, 0, ns, st));
   PVCR_TRY(colsum(w.dgh_enc, H3, BN, H3, g.enc_b_hh, 0, st));
+  if (ns == 1 && frame_scale) cache.put(vid, V, BN, V, w.x_a);      // x_a = vid * frame_scale, exactly this operand
   PVCR_TRY(grad_w(a, w.dgi_enc, H3, BN, H3, vid, V, V, nullptr, frame_scale, g.enc_w_ih, V, 0, ns, st));
   PVCR_TRY(colsum(w.dgi_enc, H3, BN, H3, g.enc_b_ih, 0, st));
   if (need_frame_grad) {
