@@ -147,7 +147,16 @@ int gemm_mn_store(const OperandView& a, const OperandView& b, int M, int N, int 
       epi.atomic = 1;
     }
   }
-  return launch_gemm_tn_persistent<256, 4, EpiStore, true>(a, b, gc, 1, epi, stream);
+  return launch_gemm_tn_persistent<256, 4, EpiStore, true, true>(a, b, gc, 1, epi, stream);
+}
+
+// C[M,N] (+)= A B for bf16 A [M, K] (K-major) and row-major B [K rows, N cols] (MN-major): data gradients dX = dY W
+// straight from the forward weight planes.  K = rows of b actually present (rows beyond read as zero).
+int gemm_kn_store(const OperandView& a, const OperandView& b, int M, int N, int K, float* C, long long ldc,
+                  int accumulate, cudaStream_t stream) {
+  EpiStore epi{C, ldc, 0, nullptr, 0, accumulate, M, N, 0, 1};
+  GemmCoords gc{M, N, (int)round_up(K, GEMM_BK), 0, 0, 0, 0};
+  return launch_gemm_tn_persistent<256, 4, EpiStore, false, true>(a, b, gc, 1, epi, stream);
 }
 
 // C[z] = A[z] * B[z]^T (+bias) (+C).  Tile choice: 128x256 when N is wide enough to fill the machine, else 128x128.

@@ -139,8 +139,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // B tile in L2); the TMA producer runs ahead across tile boundaries through the same shared-memory ring, the
 // accumulator is double-buffered in TMEM (2 x BN columns), and the four epilogue warps drain tile i while the
 // MMA warp already accumulates tile i+1.
-// MN = true: both operands are MN-major ([k][mn] row-major matrices, C = A^T B), loaded as 64 x 64 TMA boxes.
-template <int BN, int STAGES, class Epi, bool MN = false>
+// A_MN / B_MN: that operand is MN-major (a [k][mn] row-major matrix, i.e. it enters the product transposed),
+// loaded as 64 x 64 TMA boxes.  A_MN && B_MN: C = A^T B (weight gradients); !A_MN && B_MN: C = A B (data gradients
+// dX = dY W with the forward weight planes, no transposed weight copies).
+template <int BN, int STAGES, class Epi, bool A_MN = false, bool B_MN = false>
 __global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1)
 gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                           GemmCoords gc, int tiles_m, int tiles_n, int num_tiles, Epi epi) {
@@ -199,14 +201,17 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_arrive_expect_tx(&full_bar[s], SM::STAGE_BYTES);
           uint8_t* sa = smem + s * SM::STAGE_BYTES;
-          if (MN) {
+          if (A_MN) {
 #pragma unroll
             for (int i = 0; i < GEMM_BM / 64; ++i) tma_load_3d(sa + i * 8192, &tmA, &full_bar[s], m0 + 64 * i, kb * GEMM_BK, az);
+          } else {
+            tma_load_3d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m0, az);
+          }
+          if (B_MN) {
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i)
               tma_load_3d(sa + SM::A_BYTES + i * 8192, &tmB, &full_bar[s], n0 + 64 * i, kb * GEMM_BK, bz);
           } else {
-            tma_load_3d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m0, az);
             tma_load_3d(sa + SM::A_BYTES, &tmB, &full_bar[s], kb * GEMM_BK, n0, bz);
           }
         }
@@ -214,7 +219,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, MN ? 1 : 0, MN ? 1 : 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int it = 0, ti = 0;
       for (int w = blockIdx.x; w < num_tiles; w += gridDim.x, ++ti) {
         const int kb0 = (w % splits) * kb_per;
@@ -229,21 +234,14 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
-          if (MN) {
-            // 64-element mn blocks are 8192 B apart (one 64 x 64 box each), 8-row k groups 1024 B apart; 16 k rows
-            // per instruction = 2048 B
-            const uint64_t da = umma_desc_mn128(sa, 8192, 1024);
-            const uint64_t db = umma_desc_mn128(sa + SM::A_BYTES, 8192, 1024);
+          // MN-major: 64-element mn blocks 8192 B apart (one 64 x 64 box each), 8-row k groups 1024 B apart, 16 k rows
+          // per instruction = 2048 B;  K-major: 16 k elements = 32 B inside the 128-byte swizzle row
+          const uint64_t da = A_MN ? umma_desc_mn128(sa, 8192, 1024) : umma_desc_k128(sa);
+          const uint64_t db = B_MN ? umma_desc_mn128(sa + SM::A_BYTES, 8192, 1024) : umma_desc_k128(sa + SM::A_BYTES);
+          constexpr uint64_t ka = A_MN ? 128 : 2, kbs = B_MN ? 128 : 2;
 #pragma unroll
-            for (int k = 0; k < GEMM_BK / 16; ++k)
-              umma_bf16(tmem_d, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, (kb | k) != 0);
-          } else {
-            const uint64_t da = umma_desc_k128(sa);
-            const uint64_t db = umma_desc_k128(sa + SM::A_BYTES);
-#pragma unroll
-            for (int k = 0; k < GEMM_BK / 16; ++k)
-              umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-          }
+          for (int k = 0; k < GEMM_BK / 16; ++k)
+            umma_bf16(tmem_d, da + (uint64_t)k * ka, db + (uint64_t)k * kbs, idesc, (kb | k) != 0);
           umma_commit(&empty_bar[s]);
         }
         umma_commit(&tmem_full_bar[acc]);
@@ -375,21 +373,16 @@ int launch_gemm_tn(const OperandView& a, const OperandView& b, const GemmCoords&
 
 // MN = true: C[M,N] = A^T B with A = a [K rows, M cols], B = b [K rows, N cols] (row-major bf16, a.rows = b.rows = K
 // need not be padded: rows past the end read as zero through the tensor map).
-template <int BN, int STAGES, class Epi, bool MN = false>
+template <int BN, int STAGES, class Epi, bool A_MN = false, bool B_MN = false>
 int launch_gemm_tn_persistent(const OperandView& a, const OperandView& b, const GemmCoords& gc, int grid_z,
                               const Epi& epi, cudaStream_t stream) {
   using SM = GemmSmem<BN, STAGES>;
   PVCR_REQUIRE(gc.K > 0 && gc.K % GEMM_BK == 0, "gemm: K=%d must be a positive multiple of %d", gc.K, GEMM_BK);
   PVCR_REQUIRE(gc.M > 0 && gc.N > 0 && grid_z > 0, "gemm: empty problem M=%d N=%d z=%d", gc.M, gc.N, grid_z);
   CUtensorMap ta, tb;
-  if (MN) {
-    PVCR_TRY(make_tensor_map_mn(&ta, a, gc.M));
-    PVCR_TRY(make_tensor_map_mn(&tb, b, gc.N));
-  } else {
-    PVCR_TRY(make_tensor_map(&ta, a, gc.K, GEMM_BM));
-    PVCR_TRY(make_tensor_map(&tb, b, gc.K, BN));
-  }
-  auto kern = gemm_tn_persistent_kernel<BN, STAGES, Epi, MN>;
+  if (A_MN) PVCR_TRY(make_tensor_map_mn(&ta, a, gc.M)); else PVCR_TRY(make_tensor_map(&ta, a, gc.K, GEMM_BM));
+  if (B_MN) PVCR_TRY(make_tensor_map_mn(&tb, b, gc.N)); else PVCR_TRY(make_tensor_map(&tb, b, gc.K, BN));
+  auto kern = gemm_tn_persistent_kernel<BN, STAGES, Epi, A_MN, B_MN>;
   static bool attr_set = false;
   static int sms = 0;
   if (!attr_set) {

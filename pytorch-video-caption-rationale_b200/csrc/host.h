@@ -72,6 +72,10 @@ struct StageCache {
 int gemm_mn_store(const OperandView& a, const OperandView& b, int M, int N, int K, float* C, long long ldc,
                   int accumulate, cudaStream_t stream);
 
+// C[M,N] (+)= A B for bf16 A [M, K] (K-major planes) and row-major bf16 B [K rows, N cols] (MN-major operand)
+int gemm_kn_store(const OperandView& a, const OperandView& b, int M, int N, int K, float* C, long long ldc,
+                  int accumulate, cudaStream_t stream);
+
 // C[M,N] (ldc) = A * B^T (+bias) (+C); A = a_view (M rows), B = b_view (N rows), both planes over the same K.
 inline int gemm_planes(const OperandView& a, const OperandView& b, int M, int N, int Kcat, float* C, long long ldc,
                        const float* bias, int accumulate, cudaStream_t st) {
@@ -113,6 +117,10 @@ int grad_w(Arena& a, const float* dy, long long lddy, int R, int N, const float*
 // dx[R,K] (+)= dy wT^T where wT are the transposed B-role planes of w ([K, P*Np]).
 int grad_x(Arena& a, const float* dy, long long lddy, int R, int N, const Planes& wT, float* dx, long long lddx,
            int accumulate, cudaStream_t st);
+
+// bf16 mode: dx[R,Kout] (+)= dy W with the forward weight planes w ([N rows, >= Kout cols]) as MN-major operand.
+int grad_x_fwdw(Arena& a, const float* dy, long long lddy, int R, int N, const Planes& w, int Kout, float* dx,
+                long long lddx, int accumulate, cudaStream_t st);
 
 // ---- GRU layer over a sequence (per-step launches: tcgen05 GEMM h W_hh^T + fused gate kernel) ----------
 struct GruSeq {

@@ -93,6 +93,32 @@ int grad_x(Arena& a, const float* dy, long long lddy, int R, int N, const Planes
   return rc;
 }
 
+// bf16 mode: dx[R,Kout] (+)= dy[R,N] W[N,Kout] with W = the forward weight planes (MN-major B operand): no W^T copy.
+int grad_x_fwdw(Arena& a, const float* dy, long long lddy, int R, int N, const Planes& w, int Kout, float* dx,
+                long long lddx, int accumulate, cudaStream_t st) {
+  StageCache* sc = a.measuring() ? nullptr : a.cache;
+  const Planes* hit = sc ? sc->find(dy, lddy, R, N) : nullptr;
+  if (sc && !hit) {
+    Planes keep = alloc_planes(a, R, N, 1);
+    if (a.failed) { set_last_error("grad_x: workspace too small"); return PVCR_ERR_WORKSPACE; }
+    PVCR_TRY(stage(dy, lddy, R, N, keep, 0, nullptr, NO_DROPOUT, st));
+    sc->put(dy, lddy, R, N, keep);
+    hit = sc->find(dy, lddy, R, N);
+  }
+  const size_t m = a.mark();
+  Planes dya;
+  if (!hit) dya = alloc_planes(a, R, N, 1);
+  int rc = PVCR_OK;
+  if (!a.measuring()) {
+    if (a.failed) { set_last_error("grad_x: workspace too small"); return PVCR_ERR_WORKSPACE; }
+    if (!hit) rc = stage(dy, lddy, R, N, dya, 0, nullptr, NO_DROPOUT, st);
+    const Planes& A = hit ? *hit : dya;
+    if (rc == PVCR_OK) rc = gemm_kn_store(A.view(), w.view_rows(0, N), R, Kout, N, dx, lddx, accumulate, st);
+  }
+  a.release(m);
+  return rc;
+}
+
 int gru_seq_fwd(const GruSeq& s, cudaStream_t st) {
   if (gru_persist_eligible(s)) return gru_persist_fwd(s, st);
   const int H3 = 3 * s.H;

@@ -252,10 +252,12 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   PVCR_TRY(fill_zero(w.wcatT.ptr, sizeof(bf16) * (size_t)w.wcatT.rows * w.wcatT.ld, st));
   PVCR_TRY(prep_weight_T(p.att_wq, H, H, H, w.wcatT, 0, 0, st));
   PVCR_TRY(prep_weight_T(p.dec_w_hh, H, H3, H, w.wcatT, H, 0, st));
-  PVCR_TRY(prep_weight_T(p.att_wk, H, H, H, w.wkT, 0, 1, st));
-  PVCR_TRY(prep_weight_T(p.dec_w_ih + H, H + E, H3, E, w.weT, 0, 1, st));
+  if (ns > 1) {     // bf16 mode multiplies by the forward weight planes directly (MN-major operand)
+    PVCR_TRY(prep_weight_T(p.att_wk, H, H, H, w.wkT, 0, 1, st));
+    PVCR_TRY(prep_weight_T(p.dec_w_ih + H, H + E, H3, E, w.weT, 0, 1, st));
+  }
   PVCR_TRY(prep_weight_T(p.enc_w_hh, H, H3, H, w.whh_encT, 0, 1, st));
-  if (need_frame_grad) PVCR_TRY(prep_weight_T(p.enc_w_ih, V, H3, V, w.wih_encT, 0, 1, st));
+  if (need_frame_grad && ns > 1) PVCR_TRY(prep_weight_T(p.enc_w_ih, V, H3, V, w.wih_encT, 0, 1, st));
 
   const bool persist_dec = dec_persist_eligible(B, N, H, ns, w.enc_a.Kp);
   if (persist_dec) {
@@ -329,13 +331,15 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, w.ctx_all, H, H, nullptr, nullptr, g.dec_w_ih, H + E, 0, ns, st));
   PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, p.emb, E, E, s_in, nullptr, g.dec_w_ih + H, H + E, 0, ns, st));
   PVCR_TRY(colsum(w.dgi_all, H3, BL, H3, g.dec_b_ih, 0, st));
-  PVCR_TRY(grad_x(a, w.dgi_all, H3, BL, H3, w.weT, w.demb_rows, E, 0, st));
+  if (ns == 1) PVCR_TRY(grad_x_fwdw(a, w.dgi_all, H3, BL, H3, w.we, E, w.demb_rows, E, 0, st));
+  else PVCR_TRY(grad_x(a, w.dgi_all, H3, BL, H3, w.weT, w.demb_rows, E, 0, st));
   PVCR_TRY(fill_zero(g.emb, sizeof(float) * (size_t)d.Vc * E, st));
   PVCR_TRY(scatter_add_rows(w.demb_rows, E, s_in, BL, E, g.emb, NO_DROPOUT, st));
   PVCR_TRY(colsum(w.dv_part, H, B, H, g.att_v, 0, st));
   // key projection: dWk = dpk^T enc ; denc += dpk Wk
   PVCR_TRY(grad_w(a, w.dpk, H, BN, H, w.enc, H, H, nullptr, nullptr, g.att_wk, H, 0, ns, st));
-  PVCR_TRY(grad_x(a, w.dpk, H, BN, H, w.wkT, w.denc, H, 1, st));
+  if (ns == 1) PVCR_TRY(grad_x_fwdw(a, w.dpk, H, BN, H, w.wk, H, w.denc, H, 1, st));
+  else PVCR_TRY(grad_x(a, w.dpk, H, BN, H, w.wkT, w.denc, H, 1, st));
 
   // ---- encoder, reverse time (dh_carry already holds the gradient on the final state) ----
   GruSeq es = encoder_seq(d, p, w);
@@ -358,7 +362,8 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   PVCR_TRY(colsum(w.dgi_enc, H3, BN, H3, g.enc_b_ih, 0, st));
   if (need_frame_grad) {
     // d(sel) = dgi W_ih ; d frame_scale[b,n] = sum_v vid[b,n,v] * dsel[b,n,v]   (model/RationaleNet.py:52)
-    PVCR_TRY(grad_x(a, w.dgi_enc, H3, BN, H3, w.wih_encT, w.dxsel, V, 0, st));
+    if (ns == 1) PVCR_TRY(grad_x_fwdw(a, w.dgi_enc, H3, BN, H3, w.wih_enc, V, w.dxsel, V, 0, st));
+    else PVCR_TRY(grad_x(a, w.dgi_enc, H3, BN, H3, w.wih_encT, w.dxsel, V, 0, st));
     PVCR_TRY(rowdot(vid, w.dxsel, BN, V, d_frame_scale, st));
   }
   return PVCR_OK;

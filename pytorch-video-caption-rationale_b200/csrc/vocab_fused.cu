@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* in, long l
 }
 
 struct FusedWs {
-  Planes hs_a, wv, wvT;
+  Planes hs_a, wv;
   float *pmax, *psum, *tgt, *nll, *roww;
   int* pidx;
   bf16* D;
@@ -214,7 +214,6 @@ static void carve_fused(Arena& a, int M, int H, int Vc, FusedWs& w) {
   w.pmax = a.alloc<float>((size_t)M * w.ntiles); w.psum = a.alloc<float>((size_t)M * w.ntiles);
   w.pidx = a.alloc<int>((size_t)M * w.ntiles);
   w.tgt = a.alloc<float>(M); w.nll = a.alloc<float>(M); w.roww = a.alloc<float>(M);
-  w.wvT = alloc_planes(a, H, Vc, 1);
   w.ldD = (long long)cdiv(Vc, CE_BN) * CE_BN;
   w.D = a.alloc<bf16>((size_t)M * w.ldD);
 }
@@ -279,11 +278,11 @@ int vocab_fused_bwd(const float* hs, const float* wv, const float* bv, const lon
     PVCR_CUDA_CHECK(cudaMemset2DAsync(w.D + Vc, sizeof(bf16) * w.ldD, 0, sizeof(bf16) * (w.ldD - Vc), M, st));
   GemmCoords gc{M, Vc, (int)w.hs_a.ld, 0, 0, 0, 0};
   PVCR_TRY((launch_gemm_tn_persistent<CE_BN, 4, EpiCeBwd>(w.hs_a.view(), w.wv.view(), gc, 1, epi, st)));
-  // d hs = dlogits W  (K = Vc padded to 64; the padding columns of D are zeros, of W^T planes too)
-  PVCR_TRY(prep_weight_T(wv, H, Vc, H, w.wvT, 0, 1, st));
+  // d hs = dlogits W: A = dlogits (K-major, padding columns written as zeros), B = the forward weight planes [Vc, H]
+  // as an MN-major operand (rows past Vc read as zero through the tensor map): no W^T copy
   {
     OperandView dv{w.D, w.ldD, 0, M, 1};
-    PVCR_TRY(gemm_planes(dv, w.wvT.view(), M, H, w.wvT.Kp, d_hs, H, nullptr, 0, st));
+    PVCR_TRY(gemm_kn_store(dv, w.wv.view(), M, H, Vc, d_hs, H, 0, st));
   }
   if (dropout_p > 0.f) PVCR_TRY(dropout_apply(d_hs, d_hs, (long long)M * H, dr, st));
   // d W = dlogits^T Dropout(hs): both operands as they are (row-major bf16, MN-major tcgen05 operands); hs_a are
