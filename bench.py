@@ -274,7 +274,7 @@ def run_ours(args):
         "gru_persistent_bwd": N * 2 * rec_step + 3 * H * H * 2,
     }
     # DRAM bytes per launch measured with `ncu --set full` (profiles/): dram__bytes_read.sum + dram__bytes_write.sum
-    ncu_traffic = {"decoder_persistent_bwd": 98.9e6}
+    ncu_traffic = {"decoder_persistent_bwd": 99.6e6, "decoder_persistent_fwd": 59.8e6}      # profiles/r01f_ncu_full.md
     kernels = {}
     for name, v in classes.items():
         ms = v["ms_per_step"]
