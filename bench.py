@@ -146,6 +146,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # the persistent cooperative kernels occupy 128 of the 148 SMs: keep NCCL within the remaining 20 so that the
+        # overlapped gradient all-reduce can be co-resident instead of serialising in front of them
+        os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_ctas))
         dist.init_process_group("nccl", device_id=dev)
     d = DIMS
     B, N, V, H, E, L, Vc = (d[k] for k in ("B", "N", "V", "H", "E", "L", "Vc"))
@@ -334,6 +337,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x2", "bf16x3"])
     ap.add_argument("--dropout", type=float, default=0.2, help="reference default dropout_p (args.py:26)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-ctas", type=int, default=16)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

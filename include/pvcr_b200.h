@@ -112,6 +112,13 @@ int pvcr_s2vtatt_bwd(const PvcrDims* d, const PvcrS2vtAttParams* p, const float*
                      const int64_t* s_in, const float* hs, const float* d_hs, PvcrS2vtAttGrads* g,
                      float* d_frame_scale, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same backward in two halves for data-parallel callers: part 1 = decoder half (on return att_*, dec_*, emb
+ * gradients are final), part 2 = encoder half (enc_* gradients, d_frame_scale), to be called in this order on the same
+ * workspace; part 0 = both.  Lets the decoder gradients' all-reduce overlap the encoder sweep. */
+int pvcr_s2vtatt_bwd_part(const PvcrDims* d, const PvcrS2vtAttParams* p, const float* vid_feats, const float* frame_scale,
+                          const int64_t* s_in, const float* hs, const float* d_hs, PvcrS2vtAttGrads* g,
+                          float* d_frame_scale, void* workspace, size_t workspace_bytes, void* stream, int part);
+
 /* S2VTModel parameters (reference state_dict names, model/S2VTModel.py:36-49). */
 typedef struct {
   const float* emb;       /* embedding.0.weight   [Vc, E]   */

@@ -105,6 +105,8 @@ SIGNATURES = {
                                c_vp]),
     "pvcr_rationale_penalties": (c_int, [c_vp, c_int, c_int, c_vp, c_vp]),
     "pvcr_rationale_penalties_bwd": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
+    "pvcr_s2vtatt_bwd_part": (c_int, [P(PvcrDims), P(PvcrS2vtAttParams), c_vp, c_vp, c_vp, c_vp, c_vp, P(PvcrS2vtAttGrads),
+                                      c_vp, c_vp, c_size, c_vp, c_int]),
     "pvcr_vocab_ce_workspace": (c_size, [c_int, c_int, c_int, c_int, c_int, c_f]),
     "pvcr_vocab_ce_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_u64, c_vp,
                                   c_vp, c_vp, c_vp, c_i64, c_vp, c_size, c_vp]),

@@ -16,7 +16,7 @@ size_t s2vtatt_workspace(const PvcrDims& d, int need_frame_grad);
 int s2vtatt_fwd(const PvcrDims&, const PvcrS2vtAttParams&, const float*, const float*, const long long*, float*, float*,
                 void*, size_t, cudaStream_t);
 int s2vtatt_bwd(const PvcrDims&, const PvcrS2vtAttParams&, const float*, const float*, const long long*, const float*,
-                const float*, PvcrS2vtAttGrads&, float*, void*, size_t, cudaStream_t);
+                const float*, PvcrS2vtAttGrads&, float*, void*, size_t, cudaStream_t, int);
 size_t s2vt_workspace(const PvcrDims& d, int need_frame_grad);
 int s2vt_fwd(const PvcrDims&, const PvcrS2vtParams&, const float*, const float*, const long long*, float*, void*, size_t,
              cudaStream_t);
@@ -78,7 +78,14 @@ int pvcr_s2vtatt_bwd(const PvcrDims* d, const PvcrS2vtAttParams* p, const float*
                      const int64_t* s_in, const float* hs, const float* d_hs, PvcrS2vtAttGrads* g,
                      float* d_frame_scale, void* workspace, size_t workspace_bytes, void* stream) {
   return s2vtatt_bwd(*d, *p, vid_feats, frame_scale, (const long long*)s_in, d_hs, hs, *g, d_frame_scale, workspace,
-                     workspace_bytes, (cudaStream_t)stream);
+                     workspace_bytes, (cudaStream_t)stream, 0);
+}
+int pvcr_s2vtatt_bwd_part(const PvcrDims* d, const PvcrS2vtAttParams* p, const float* vid_feats, const float* frame_scale,
+                          const int64_t* s_in, const float* hs, const float* d_hs, PvcrS2vtAttGrads* g,
+                          float* d_frame_scale, void* workspace, size_t workspace_bytes, void* stream, int part) {
+  if (part < 0 || part > 2) { set_last_error("pvcr_s2vtatt_bwd_part: part=%d not in 0..2", part); return PVCR_ERR_ARG; }
+  return s2vtatt_bwd(*d, *p, vid_feats, frame_scale, (const long long*)s_in, d_hs, hs, *g, d_frame_scale, workspace,
+                     workspace_bytes, (cudaStream_t)stream, part);
 }
 size_t pvcr_s2vt_workspace(const PvcrDims* d, int need_frame_grad) { return s2vt_workspace(*d, need_frame_grad); }
 int pvcr_s2vt_fwd(const PvcrDims* d, const PvcrS2vtParams* p, const float* vid_feats, const float* frame_scale,

@@ -225,9 +225,12 @@ int s2vtatt_fwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   return PVCR_OK;
 }
 
+// part: 0 = whole backward; 1 = decoder half only (every decoder / attention / embedding gradient is final when it
+// returns); 2 = encoder half only (must follow part 1 on the same workspace).  The split lets a data-parallel caller
+// all-reduce the decoder gradients while the encoder sweep runs.
 int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid, const float* frame_scale,
                 const long long* s_in, const float* d_hs, const float* hs, PvcrS2vtAttGrads& g, float* d_frame_scale,
-                void* ws, size_t ws_bytes, cudaStream_t st) {
+                void* ws, size_t ws_bytes, cudaStream_t st, int part) {
   PVCR_TRY(check_dims(d));
   const int B = d.B, N = d.N, V = d.V, H = d.H, E = d.E, L = d.L, ns = d.nsplit;
   const int BN = B * N, BL = B * L, H3 = 3 * H, H4 = 4 * H;
@@ -247,6 +250,7 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
     cache.put(w.enc, H, BN, H, w.enc_a);
     cache.put(s_in, -1, BL, E, w.emb_a);
   }
+  if (part != 2) {
   // transposed weights for the data-gradient GEMMs
   PVCR_TRY(prep_weight_T(p.dec_w_ih, H + E, H3, H, w.wcT, 0, 1, st));
   PVCR_TRY(fill_zero(w.wcatT.ptr, sizeof(bf16) * (size_t)w.wcatT.rows * w.wcatT.ld, st));
@@ -256,7 +260,6 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
     PVCR_TRY(prep_weight_T(p.att_wk, H, H, H, w.wkT, 0, 1, st));
     PVCR_TRY(prep_weight_T(p.dec_w_ih + H, H + E, H3, E, w.weT, 0, 1, st));
   }
-  PVCR_TRY(prep_weight_T(p.enc_w_hh, H, H3, H, w.whh_encT, 0, 1, st));
   if (need_frame_grad && ns > 1) PVCR_TRY(prep_weight_T(p.enc_w_ih, V, H3, V, w.wih_encT, 0, 1, st));
 
   const bool persist_dec = dec_persist_eligible(B, N, H, ns, w.enc_a.Kp);
@@ -341,7 +344,10 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   if (ns == 1) PVCR_TRY(grad_x_fwdw(a, w.dpk, H, BN, H, w.wk, H, w.denc, H, 1, st));
   else PVCR_TRY(grad_x(a, w.dpk, H, BN, H, w.wkT, w.denc, H, 1, st));
 
+  }   // decoder half
+  if (part == 1) return PVCR_OK;
   // ---- encoder, reverse time (dh_carry already holds the gradient on the final state) ----
+  PVCR_TRY(prep_weight_T(p.enc_w_hh, H, H3, H, w.whh_encT, 0, 1, st));
   GruSeq es = encoder_seq(d, p, w);
   GruSeqGrad eg{};
   eg.dh_ext = w.denc; eg.dh_ext_ts = H; eg.dh_ext_ld = (long long)N * H;

@@ -101,6 +101,17 @@ class S2VTAttSequence(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_hs, _d_alphas):
+        gen = S2VTAttSequence.backward_in_parts(ctx, d_hs, parts=(0,))
+        try:
+            while True:
+                next(gen)
+        except StopIteration as done:
+            return done.value
+
+    @staticmethod
+    def backward_in_parts(ctx, d_hs, parts=(1, 2)):
+        """Generator: runs the C backward part by part, yielding after every part but the last (parts=(1, 2): the
+        decoder-half gradients are final at the yield); returns the autograd gradient tuple."""
         vid_c, fs_c, s_c, hs, ws, tensors = ctx.keep
         d_hs = _f32c(d_hs)
         grads = _grad_buffers(ctx.cfg, "grad_out", ATT_SEQ_FIELDS, tensors)
@@ -108,9 +119,12 @@ class S2VTAttSequence(torch.autograd.Function):
         ps = _fill_struct(PvcrS2vtAttParams(), ATT_SEQ_FIELDS, tensors)
         gs = _fill_struct(PvcrS2vtAttGrads(), ATT_SEQ_FIELDS, grads)
         Lb = lib()
-        check(Lb.pvcr_s2vtatt_bwd(ctypes.byref(ctx.dims), ctypes.byref(ps), ptr(vid_c), ptr(fs_c), ptr(s_c), ptr(hs),
-                                  ptr(d_hs), ctypes.byref(gs), ptr(d_fs), ptr(ws), ws.numel(), stream_ptr()),
-              "pvcr_s2vtatt_bwd")
+        for i, part in enumerate(parts):
+            check(Lb.pvcr_s2vtatt_bwd_part(ctypes.byref(ctx.dims), ctypes.byref(ps), ptr(vid_c), ptr(fs_c), ptr(s_c),
+                                           ptr(hs), ptr(d_hs), ctypes.byref(gs), ptr(d_fs), ptr(ws), ws.numel(),
+                                           stream_ptr(), part), "pvcr_s2vtatt_bwd_part")
+            if i + 1 < len(parts):
+                yield grads
         return (None, None, d_fs, None) + tuple(grads[f] for f in ATT_SEQ_FIELDS)
 
 

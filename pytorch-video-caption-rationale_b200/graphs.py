@@ -25,19 +25,21 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        self.graph2 = None
+        self.graphs = [self.graph]          # one graph per stage of model.train_step_stages (a single one otherwise)
         if reducer is not None and hasattr(model, "train_step_stages"):
             with torch.no_grad():
                 gen = model.train_step_stages(*self.static_in)
-                with torch.cuda.graph(self.graph):
-                    next(gen)
-                self.graph2 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph2, pool=self.graph.pool()):
-                    try:
-                        next(gen)
-                        raise RuntimeError("train_step_stages must yield exactly once")
-                    except StopIteration as done:
-                        out = done.value
+                out = None
+                while out is None:
+                    g = self.graphs[-1]
+                    with torch.cuda.graph(g, pool=None if g is self.graph else self.graph.pool()):
+                        try:
+                            next(gen)
+                            more = True
+                        except StopIteration as done:
+                            out, more = done.value, False
+                    if more:
+                        self.graphs.append(torch.cuda.CUDAGraph())
         else:
             with torch.cuda.graph(self.graph):
                 out = model.train_step_grads(*self.static_in)
@@ -57,15 +59,19 @@ class GraphedTrainStep:
         return self.static_out
 
     def _replay(self):
-        self.graph.replay()
-        if self.graph2 is not None:
-            self.reducer.begin(0)              # all-reduce of the early bucket overlaps the rest of the backward
-            self.graph2.replay()
-            for i in range(1, len(self.reducer.buckets)):
+        if len(self.graphs) > 1:
+            # stage i's gradients (bucket i) are final when graph i has run: their all-reduce overlaps graph i+1
+            for i, g in enumerate(self.graphs):
+                g.replay()
+                if i + 1 < len(self.graphs):
+                    self.reducer.begin(i)
+            for i in range(len(self.graphs) - 1, len(self.reducer.buckets)):
                 self.reducer.begin(i)
             self.reducer.finish()
-        elif self.reducer is not None:
-            self.reducer.reduce()
+        else:
+            self.graph.replay()
+            if self.reducer is not None:
+                self.reducer.reduce()
 
     def prefetch(self, *inputs):
         """Start copying the NEXT step's inputs (pinned host tensors) to the device; returns immediately."""

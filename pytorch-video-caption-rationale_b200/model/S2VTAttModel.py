@@ -126,16 +126,29 @@ class S2VTAttModel(nn.Module):
         _, d_hs, d_w, d_b, _, _ = F_.VocabCrossEntropy.backward(c2, one, None, None)
         lin.weight.grad, lin.bias.grad = d_w, d_b
         yield "vocab_grads"
-        grads = F_.S2VTAttSequence.backward(c1, d_hs, None)
+        seq = F_.S2VTAttSequence.backward_in_parts(c1, d_hs, parts=(1, 2))
+        try:
+            part_grads = next(seq)                       # decoder half done
+            for f, p in zip(F_.ATT_SEQ_FIELDS, params):
+                if not f.startswith("enc_"):
+                    p.grad = part_grads[f]
+            yield "decoder_grads"
+            next(seq)
+            raise RuntimeError("backward_in_parts yielded more than once")
+        except StopIteration as done:
+            grads = done.value
         for p, g in zip(params, grads[4:]):
             p.grad = g
         self.last_frame_scale_grad = grads[2]
         return loss, stats[0] / stats[1], pred
 
     def early_grad_params(self):
-        """Parameters whose gradients are complete at the first yield of train_step_stages."""
+        """Per yield of train_step_stages, the parameters whose gradients are final at that point."""
         lin = self.decoder.pred_linear[1]
-        return [lin.bias, lin.weight]
+        d = self.decoder
+        dec = [d.embedding.weight, d.rnn.weight_ih_l0, d.rnn.weight_hh_l0, d.rnn.bias_ih_l0, d.rnn.bias_hh_l0,
+               d.attention.key_layer.weight, d.attention.query_layer.weight, d.attention.energy_layer.weight]
+        return [[lin.bias, lin.weight], dec]
 
     @torch.no_grad()
     def train_step_grads(self, vid_feats, s, s_len, frame_scale=None):

@@ -30,10 +30,14 @@ class GradAllReducer:
         without gather / scatter copies."""
         self.params = [p for p in module.parameters() if p.requires_grad]
         self.group = group
-        early = list(early or [])           # parameters whose gradients are complete first: bucket 0 on its own
+        # early: list of parameter lists whose gradients become final first (one bucket each, in that order)
+        early = list(early or [])
+        if early and not isinstance(early[0], (list, tuple)):
+            early = [early]
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.buckets = [early] if early else []
-        early_ids = {id(p) for p in early}
+        self.buckets = [list(e) for e in early]
+        self.n_early = len(self.buckets)
+        early_ids = {id(p) for e in early for p in e}
         cur, cur_bytes = [], 0
         for p in reversed(self.params):
             if id(p) in early_ids:
