@@ -38,6 +38,12 @@ void pvcr_prof_enable(int on);
 void pvcr_prof_reset(void);
 int pvcr_prof_read(uint64_t* launches, double* ms, double* work);
 
+/* Registers a device-resident uint64 counter that every dropout / Gumbel draw mixes into its seed when the kernel
+ * runs (NULL switches it off).  CUDA-graph replays otherwise repeat the seed baked in at capture; with the counter
+ * incremented once per step (pvcr_b200.graphs does it inside the captured graph) every replay draws fresh masks,
+ * forward and backward of one step still agreeing. */
+void pvcr_set_seed_step(const uint64_t* device_counter);
+
 /* Tuning aid: in-kernel phase timestamps (clock64 of CTA 0, [step][8]) of the last persistent-kernel launch. */
 int pvcr_debug_phase_timing(int on);
 int pvcr_debug_phase_read(long long* out, int steps);

@@ -67,6 +67,7 @@ def _sig(L, name, restype, argtypes):
 # name -> (restype, argtypes); mirrors include/pvcr_b200.h one to one (tests/test_abi.py cross-checks the header)
 P = ctypes.POINTER
 SIGNATURES = {
+    "pvcr_set_seed_step": (None, [c_vp]),
     "pvcr_debug_phase_timing": (c_int, [c_int]),
     "pvcr_debug_phase_read": (c_int, [P(ctypes.c_longlong), c_int]),
     "pvcr_prof_num_classes": (c_int, []),

@@ -24,9 +24,12 @@ __device__ __forceinline__ float philox_uniform(unsigned long long seed, unsigne
                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   return ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);     // (0,1)
 }
+__device__ __forceinline__ unsigned long long stepped_seed(unsigned long long seed, const unsigned long long* step) {
+  return step ? seed + __ldg(step) * 0x9E3779B97F4A7C15ull : seed;
+}
 __device__ __forceinline__ float dropout_scale(const Dropout& d, unsigned long long idx) {
   if (d.p <= 0.f) return 1.f;
-  return philox_uniform(d.seed, d.offset + idx) >= d.p ? 1.f / (1.f - d.p) : 0.f;
+  return philox_uniform(stepped_seed(d.seed, d.step), d.offset + idx) >= d.p ? 1.f / (1.f - d.p) : 0.f;
 }
 
 __device__ __forceinline__ unsigned long long drop_index(const Dropout& d, long long r, int C, int c) {
@@ -732,8 +735,9 @@ __global__ void __launch_bounds__(256) gumbel_fwd_kernel(GumbelArgs a) {
     float u0, u1;
     if (a.noise) { u0 = a.noise[warp * 2]; u1 = a.noise[warp * 2 + 1]; }
     else {  // Exp(1) draws
-      u0 = -logf(philox_uniform(a.seed, (unsigned long long)warp * 2));
-      u1 = -logf(philox_uniform(a.seed, (unsigned long long)warp * 2 + 1));
+      const unsigned long long sd = stepped_seed(a.seed, a.seed_step);
+      u0 = -logf(philox_uniform(sd, (unsigned long long)warp * 2));
+      u1 = -logf(philox_uniform(sd, (unsigned long long)warp * 2 + 1));
     }
     const float y0 = (l0 - logf(u0)) / a.tau, y1 = (l1 - logf(u1)) / a.tau;
     const float m = fmaxf(y0, y1);

@@ -84,7 +84,7 @@ size_t generator_workspace(const PvcrDims& d) {
   return a.off + gen_scratch(d) + 1024;
 }
 
-static Dropout gen_dropout(const PvcrDims& d) { return Dropout{d.dropout_p, d.seed, 0x7000000000ull}; }
+static Dropout gen_dropout(const PvcrDims& d) { return make_dropout(d.dropout_p, d.seed, 0x7000000000ull); }
 
 // noise: [B*N, 2] Exp(1) draws (row b*N + n) or NULL (drawn in-kernel from dims.seed).
 int generator_fwd(const PvcrDims& d, const PvcrGenParams& p, const float* vid, const float* noise, float tau, int hard,
@@ -135,7 +135,7 @@ int generator_fwd(const PvcrDims& d, const PvcrGenParams& p, const float* vid, c
   GumbelArgs ga{};
   ga.B = B; ga.N = N; ga.H = H;
   ga.hf = w.dir[0].h; ga.hb = w.dir[1].h; ga.h_ts = H; ga.h_bs = (long long)N * H;
-  ga.w = p.lin_w; ga.bias = p.lin_b; ga.noise = noise; ga.seed = d.seed; ga.tau = tau; ga.hard = hard;
+  ga.w = p.lin_w; ga.bias = p.lin_b; ga.noise = noise; ga.seed = d.seed; ga.seed_step = seed_step_ptr(); ga.tau = tau; ga.hard = hard;
   ga.drop = gen_dropout(d);
   ga.probs = probs; ga.p1 = p1; ga.y = w.y; ga.pen = pen;
   return gumbel_select_fwd(ga, st);

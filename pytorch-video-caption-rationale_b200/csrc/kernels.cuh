@@ -13,7 +13,17 @@ struct Dropout {
   // element (r, c) of a [R, C] call maps to index ((r * row_mul + row_add) * C + c): lets a step-wise call on
   // B rows reproduce the mask of row b*L + i of the all-steps call (row_mul = L, row_add = i)
   int row_mul = 1, row_add = 0;
+  // optional device counter mixed into the seed (see pvcr_set_seed_step): lets a captured CUDA graph draw a fresh
+  // mask on every replay
+  const unsigned long long* step = nullptr;
 };
+// device counter registered with pvcr_set_seed_step (null when unset); host side of the Dropout.step field
+const unsigned long long* seed_step_ptr();
+inline Dropout make_dropout(float p, unsigned long long seed, unsigned long long offset) {
+  Dropout d{p, seed, offset};
+  d.step = p > 0.f ? seed_step_ptr() : nullptr;
+  return d;
+}
 
 // ---- operand staging: fp32 -> bf16 split planes -------------------------------------------------
 // out[r][p*Cp + c] = term_{role,p}( in[r*ld_in + c] * (row_scale ? row_scale[r] : 1) * dropout ), zero for c >= C.
@@ -140,6 +150,7 @@ struct GumbelArgs {
   const float* bias;                         // [2]
   const float* noise;                        // [B*N, 2] Exp(1) draws (row = b*N + n), or null => philox
   unsigned long long seed;
+  const unsigned long long* seed_step;       // as Dropout.step
   float tau; int hard;
   Dropout drop;                              // dropout on the LSTM outputs
   float* probs;                              // [B,N,2]

@@ -5,6 +5,7 @@
 #include "../../include/pvcr_b200.h"
 #include "common.cuh"
 #include "persist.cuh"
+#include "kernels.cuh"
 
 namespace pvcr {
 
@@ -41,6 +42,8 @@ LaunchScope::~LaunchScope() {
   if (i < g_pending.size()) cudaEventRecord(g_pending[i].b, st);
 }
 
+static const unsigned long long* g_seed_step = nullptr;
+const unsigned long long* seed_step_ptr() { return g_seed_step; }
 static long long* g_phase_buf = nullptr;
 static bool g_phase_on = false;
 constexpr int PHASE_STEPS = 256;
@@ -75,6 +78,12 @@ int pvcr_prof_read(uint64_t* launches, double* ms, double* work) {
     ms[e.cls] += t;
   }
   return PVCR_OK;
+}
+
+// Device counter mixed into every dropout / Gumbel seed at kernel run time (NULL = off).  A CUDA graph captures the
+// pointer, not the value: incrementing the counter between (or inside) replays gives every replay fresh masks.
+void pvcr_set_seed_step(const uint64_t* device_counter) {
+  g_seed_step = reinterpret_cast<const unsigned long long*>(device_counter);
 }
 
 // Tuning aid: in-kernel phase timestamps of the persistent kernels (CTA 0).  enable allocates a small device

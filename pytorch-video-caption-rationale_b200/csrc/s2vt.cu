@@ -125,7 +125,7 @@ static int check_s2vt_dims(const PvcrDims& d) {
   return PVCR_OK;
 }
 
-static Dropout emb_dropout(const PvcrDims& d) { return Dropout{d.dropout_p, d.seed, 0x3000000000ull}; }
+static Dropout emb_dropout(const PvcrDims& d) { return make_dropout(d.dropout_p, d.seed, 0x3000000000ull); }
 
 // weights -> planes, rnn1 over the frames, rnn2 encoding stage
 static int s2vt_encode(const PvcrDims& d, const PvcrS2vtParams& p, S2vtWs& w, const S2vtSeqs& q, const float* vid,
@@ -334,7 +334,8 @@ int s2vt_decode_steps(const PvcrDims& d, const PvcrS2vtParams& p, const float* v
     PVCR_TRY(gather_split(p.emb, E, gw.words, B, gw.emb_step.ptr, gw.emb_step.ld, gw.emb_step.Kp, d.nsplit, ed, st));
     PVCR_TRY(gemm_planes(gw.emb_step.view(), w.w2e.view(), B, H3, (int)gw.emb_step.ld, gw.g2, H3, nullptr, 1, st));
     PVCR_TRY(gru_single_step(d, w.d2, i, w.e2, w.w2h, gw.g2, nullptr, p.rnn2_b_hh, w.gh, st));
-    Dropout od{out_dropout_p, d.seed, 0x5000000000ull, L, i};
+    Dropout od = make_dropout(out_dropout_p, d.seed, 0x5000000000ull);
+    od.row_mul = L; od.row_add = i;
     PVCR_TRY(cast_split(gw.hs + (long long)i * H, (long long)L * H, B, H, gw.hdrop.ptr, gw.hdrop.ld, gw.hdrop.Kp,
                         d.nsplit, 0, nullptr, od, st));
     float* lg = logits ? logits + (long long)i * Vc : gw.logits_step;

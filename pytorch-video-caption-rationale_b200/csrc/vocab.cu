@@ -46,7 +46,7 @@ size_t vocab_ce_workspace(int B, int L, int H, int Vc, int nsplit, float dropout
   return (peak > fused ? peak : fused) + 4096;
 }
 
-static Dropout out_dropout(float p, unsigned long long seed) { return Dropout{p, seed, 0x5000000000ull}; }
+static Dropout out_dropout(float p, unsigned long long seed) { return make_dropout(p, seed, 0x5000000000ull); }
 
 // loss3 = {masked loss, #correct, #mask}; pred [B*L] int64; logits stay in the workspace for vocab_ce_bwd.
 int vocab_ce_fwd(const float* hs, const float* wv, const float* bv, const long long* target, const long long* s_len,

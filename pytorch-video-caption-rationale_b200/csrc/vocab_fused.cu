@@ -224,7 +224,7 @@ size_t vocab_fused_workspace(int M, int H, int Vc) {
   return a.off + 4096;
 }
 
-static Dropout fused_out_dropout(float p, unsigned long long seed) { return Dropout{p, seed, 0x5000000000ull}; }
+static Dropout fused_out_dropout(float p, unsigned long long seed) { return make_dropout(p, seed, 0x5000000000ull); }
 
 int vocab_fused_fwd(const float* hs, const float* wv, const float* bv, const long long* target, const long long* s_len,
                     int B, int L, int H, int Vc, float dropout_p, unsigned long long seed, float* loss3, long long* pred,

@@ -8,6 +8,8 @@ into static device buffers (directly from pinned host memory when given CPU tens
 """
 import torch
 
+from ._lib import lib, ptr
+
 
 class GraphedTrainStep:
     def __init__(self, model, example_inputs, warmup=3, reducer=None):
@@ -16,6 +18,9 @@ class GraphedTrainStep:
         two graphs split where the early gradients are final, and their all-reduce overlaps the second graph."""
         self.model = model
         self.reducer = reducer
+        # per-replay dropout / Gumbel seeds: a device counter incremented by the first captured graph node
+        self.seed_step = torch.zeros(1, dtype=torch.int64, device=example_inputs[0].device)
+        lib().pvcr_set_seed_step(ptr(self.seed_step))
         self.static_in = tuple(t.clone() for t in example_inputs)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -33,6 +38,8 @@ class GraphedTrainStep:
                 while out is None:
                     g = self.graphs[-1]
                     with torch.cuda.graph(g, pool=None if g is self.graph else self.graph.pool()):
+                        if g is self.graph:
+                            self.seed_step.add_(1)
                         try:
                             next(gen)
                             more = True
@@ -42,6 +49,7 @@ class GraphedTrainStep:
                         self.graphs.append(torch.cuda.CUDAGraph())
         else:
             with torch.cuda.graph(self.graph):
+                self.seed_step.add_(1)
                 out = model.train_step_grads(*self.static_in)
         self.static_out = tuple(o.detach() if torch.is_tensor(o) else o for o in out)
         # input pipeline: the next batch is copied host -> device into staging buffers on a side stream while the
@@ -50,6 +58,12 @@ class GraphedTrainStep:
         self._staging = tuple(torch.empty_like(t) for t in self.static_in)
         self._staged = None
         self._handover = None
+
+    def __del__(self):
+        try:
+            lib().pvcr_set_seed_step(None)       # the counter tensor dies with this object
+        except Exception:                        # noqa: BLE001  (interpreter shutdown)
+            pass
 
     def __call__(self, *inputs):
         for dst, src in zip(self.static_in, inputs):

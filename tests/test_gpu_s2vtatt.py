@@ -125,3 +125,30 @@ def test_tape_free_staged_step(tag):
         assert relerr(got[k], g[k]) < 1e-4, (k, relerr(got[k], g[k]))
     early = m.early_grad_params()
     assert len(early) == 2 and all(p.grad is not None for e in early for p in e)
+
+
+def test_graphed_step_matches_eager_and_redraws_dropout():
+    """One CUDA-graph replay == the eager tape-free step (dropout off); with dropout on, consecutive replays draw
+    different masks (device-side seed step) while the inputs stay the same."""
+    from pvcr_b200.graphs import GraphedTrainStep
+    from pvcr_b200.model import S2VTAttModel
+    d, params, g, (B, N, V, H, E, L, Vc) = load_case("s2vtatt_mid")
+    vid = torch.from_numpy(d["vid"]).cuda()
+    s = torch.from_numpy(d["s"]).cuda()
+    s_len = torch.from_numpy(d["s_len"]).cuda()
+    m = to_cuda(S2VTAttModel(FixtureGlove(Vc, E), 0.0, H, V, L, precision="bf16"), params).train()
+    ref_loss, _, _ = m.train_step_grads(vid, s, s_len)
+    ref = {k: v.copy() for k, v in grads_of(m).items()}
+    step = GraphedTrainStep(m, (vid, s, s_len))
+    loss, acc, pred = step(vid, s, s_len)
+    torch.cuda.synchronize()
+    assert abs(loss.item() - ref_loss.item()) < 1e-6 * abs(ref_loss.item())
+    got = grads_of(m)
+    for k in ref:
+        assert relerr(got[k], ref[k]) < 1e-5, k
+    del step
+    m2 = to_cuda(S2VTAttModel(FixtureGlove(Vc, E), 0.5, H, V, L, precision="bf16"), params).train()
+    step2 = GraphedTrainStep(m2, (vid, s, s_len))
+    l1 = step2(vid, s, s_len)[0].item()
+    l2 = step2(vid, s, s_len)[0].item()
+    assert l1 != l2
