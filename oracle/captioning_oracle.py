@@ -37,6 +37,41 @@ def log_softmax(x, axis=-1):
     return y - np.log(np.exp(y).sum(axis=axis, keepdims=True))
 
 
+# ----------------------------------------------------------------------------------------
+# operand-rounding emulation (tests only): models "bf16 tensor-core operands, wide accumulation"
+# ----------------------------------------------------------------------------------------
+_Q = None          # rounding applied to every GEMM operand (None = exact arithmetic, the reference's semantics)
+_QK = None         # rounding of the cached proj_key as the attention kernels hold it (fp16)
+
+
+def bf16_round(x):
+    """Round-to-nearest-even to bfloat16 precision (8 significand bits), returned in the input dtype."""
+    a = np.ascontiguousarray(x, dtype=np.float32)
+    u = a.view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32).astype(x.dtype).reshape(x.shape)
+
+
+def fp16_round(x):
+    return np.asarray(x, dtype=np.float32).astype(np.float16).astype(x.dtype)
+
+
+def set_operand_rounding(q=None, qk=None):
+    """q: rounding of every matrix-product operand; qk: rounding of proj_key inside the attention score.
+    set_operand_rounding(bf16_round, fp16_round) emulates the CUDA path's bf16 mode; () restores exact arithmetic."""
+    global _Q, _QK
+    _Q, _QK = q, qk
+
+
+def _mm(a, b):
+    """a @ b with both operands passed through the operand rounding (if any)."""
+    return a @ b if _Q is None else _Q(a) @ _Q(b)
+
+
+def _q(x):
+    return x if _Q is None else _Q(x)
+
+
 def _sub(params, prefix):
     """View of a parameter dict under ``prefix`` (e.g. 'caption_net.')."""
     n = len(prefix)
@@ -55,7 +90,7 @@ def gru_seq_fwd(gi, w_hh, b_hh, h0):
     hprev = np.empty_like(hs)
     h = h0
     for t in range(T):
-        gh = h @ w_hh.T + b_hh
+        gh = _mm(h, w_hh.T) + b_hh
         r = sigmoid(gi[t, :, :H] + gh[:, :H])
         z = sigmoid(gi[t, :, H:2 * H] + gh[:, H:2 * H])
         n = np.tanh(gi[t, :, 2 * H:] + r * gh[:, 2 * H:])
@@ -83,8 +118,8 @@ def gru_seq_bwd(dhs, dh_last, cache):
         drp = dnp * ghn * r * (1.0 - r)
         dgi[t, :, :H] = drp; dgi[t, :, H:2 * H] = dzp; dgi[t, :, 2 * H:] = dnp
         dgh_all[t, :, :H] = drp; dgh_all[t, :, H:2 * H] = dzp; dgh_all[t, :, 2 * H:] = dnp * r
-        dh = dh * z + dgh_all[t] @ w_hh
-    dw_hh = dgh_all.reshape(T * B, 3 * H).T @ hprev.reshape(T * B, H)
+        dh = dh * z + _mm(dgh_all[t], w_hh)
+    dw_hh = _mm(dgh_all.reshape(T * B, 3 * H).T, hprev.reshape(T * B, H))
     db_hh = dgh_all.sum(axis=(0, 1))
     return dgi, dw_hh, db_hh, dh
 
@@ -137,18 +172,18 @@ def lstm_seq_bwd(dhs, cache):
 # ----------------------------------------------------------------------------------------
 def attention_fwd(q, proj_key, enc, v):
     """q: [B,H] (= W_q h), proj_key/enc: [B,N,H], v: [H] -> ctx [B,H], alphas [B,N], tanh e."""
-    e = np.tanh(q[:, None, :] + proj_key)
+    e = np.tanh(q[:, None, :] + (proj_key if _QK is None else _QK(proj_key)))
     scores = e @ v
     scores = scores - scores.max(axis=1, keepdims=True)
     a = np.exp(scores)
     a = a / a.sum(axis=1, keepdims=True)
-    ctx = np.einsum("bn,bnh->bh", a, enc)
+    ctx = np.einsum("bn,bnh->bh", a, _q(enc))
     return ctx, a, e
 
 
 def attention_bwd(dctx, a, e, enc, v):
     """Returns dq [B,H], dproj_key [B,N,H], denc [B,N,H], dv [H]."""
-    da = np.einsum("bh,bnh->bn", dctx, enc)
+    da = np.einsum("bh,bnh->bn", dctx, _q(enc))
     denc = a[:, :, None] * dctx[:, None, :]
     ds = a * (da - (a * da).sum(axis=1, keepdims=True))
     dv = np.einsum("bn,bnh->h", ds, e)
@@ -214,7 +249,7 @@ def cont_loss(probs):
 def s2vtatt_encode(p, vid):
     """Encoder.forward: hoisted input projection + GRU.  vid [B,N,V] -> enc [B,N,H] + cache."""
     B, N, V = vid.shape
-    gi = (vid.reshape(B * N, V) @ p["encoder.rnn.weight_ih_l0"].T + p["encoder.rnn.bias_ih_l0"])
+    gi = (_mm(vid.reshape(B * N, V), p["encoder.rnn.weight_ih_l0"].T) + p["encoder.rnn.bias_ih_l0"])
     gi = gi.reshape(B, N, -1).transpose(1, 0, 2)
     H = gi.shape[2] // 3
     hs, c = gru_seq_fwd(gi, p["encoder.rnn.weight_hh_l0"], p["encoder.rnn.bias_hh_l0"],
@@ -240,23 +275,23 @@ def s2vtatt_decode_train(p, enc, h0, s, sos_id, max_len):
     emb = p["decoder.embedding.weight"]
     s_in = _dec_in_words(s, sos_id)[:, :L]
     erow = emb[s_in]                                           # [B,L,E]
-    ep = erow.reshape(B * L, -1) @ We.T + b_ih                 # hoisted embedding half of in-proj
+    ep = _mm(erow.reshape(B * L, -1), We.T) + b_ih             # hoisted embedding half of in-proj
     ep = ep.reshape(B, L, 3 * H)
-    pk = (enc.reshape(B * N, H) @ Wk.T).reshape(B, N, H)
+    pk = _mm(enc.reshape(B * N, H), Wk.T).reshape(B, N, H)
     h = h0
     steps = []
     hs = np.empty((B, L, H), enc.dtype)
     for i in range(L):
-        q = h @ Wq.T
+        q = _mm(h, Wq.T)
         ctx, a, e = attention_fwd(q, pk, enc, v)
-        gi = ctx @ Wc.T + ep[:, i]
-        gh = h @ W_hh.T + b_hh
+        gi = _mm(ctx, Wc.T) + ep[:, i]
+        gh = _mm(h, W_hh.T) + b_hh
         r = sigmoid(gi[:, :H] + gh[:, :H]); z = sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
         n = np.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:])
         steps.append(dict(hprev=h, ctx=ctx, a=a, e=e, r=r, z=z, n=n, ghn=gh[:, 2 * H:]))
         h = (1.0 - z) * n + z * h
         hs[:, i] = h
-    logits = hs.reshape(B * L, H) @ p["decoder.pred_linear.1.weight"].T + p["decoder.pred_linear.1.bias"]
+    logits = _mm(hs.reshape(B * L, H), p["decoder.pred_linear.1.weight"].T) + p["decoder.pred_linear.1.bias"]
     cache = dict(steps=steps, hs=hs, pk=pk, enc=enc, erow=erow, s_in=s_in, h0=h0)
     return logits.reshape(B, L, -1), cache
 
@@ -274,9 +309,9 @@ def s2vtatt_decode_bwd(p, cache, dlogits):
     Vc = Wv.shape[0]
     dl = dlogits.reshape(B * L, Vc)
     g = {}
-    g["decoder.pred_linear.1.weight"] = dl.T @ hs.reshape(B * L, H)
-    g["decoder.pred_linear.1.bias"] = dl.sum(axis=0)
-    dhs = (dl @ Wv).reshape(B, L, H)
+    g["decoder.pred_linear.1.weight"] = _mm(dl.T, hs.reshape(B * L, H))
+    g["decoder.pred_linear.1.bias"] = _q(dl).sum(axis=0)
+    dhs = _mm(dl, Wv).reshape(B, L, H)
     dWq = np.zeros_like(Wq); dv = np.zeros_like(v); dWc = np.zeros_like(Wc); dW_hh = np.zeros_like(W_hh)
     db_hh = np.zeros(3 * H, enc.dtype)
     dgi_all = np.empty((B, L, 3 * H), enc.dtype)
@@ -291,16 +326,16 @@ def s2vtatt_decode_bwd(p, cache, dlogits):
         dgi = np.concatenate([drp, dzp, dnp], axis=1)
         dgh = np.concatenate([drp, dzp, dnp * r], axis=1)
         dgi_all[:, i] = dgi
-        dW_hh += dgh.T @ hp; db_hh += dgh.sum(axis=0)
-        dWc += dgi.T @ st["ctx"]
-        dctx = dgi @ Wc
+        dW_hh += _mm(dgh.T, hp); db_hh += dgh.sum(axis=0)
+        dWc += _mm(dgi.T, st["ctx"])
+        dctx = _mm(dgi, Wc)
         dq, de, denc_i, dv_i = attention_bwd(dctx, st["a"], st["e"], enc, v)
         dpk += de; denc += denc_i; dv += dv_i
-        dWq += dq.T @ hp
-        dh = dh * z + dgh @ W_hh + dq @ Wq
+        dWq += _mm(dq.T, hp)
+        dh = dh * z + _mm(dgh, W_hh) + _mm(dq, Wq)
     dgi_flat = dgi_all.reshape(B * L, 3 * H)
-    dWe = dgi_flat.T @ erow.reshape(B * L, -1)
-    derow = dgi_flat @ We
+    dWe = _mm(dgi_flat.T, erow.reshape(B * L, -1))
+    derow = _mm(dgi_flat, We)
     demb = np.zeros_like(p["decoder.embedding.weight"])
     np.add.at(demb, s_in.reshape(-1), derow)
     g["decoder.embedding.weight"] = demb
@@ -310,8 +345,8 @@ def s2vtatt_decode_bwd(p, cache, dlogits):
     g["decoder.rnn.bias_hh_l0"] = db_hh
     g["decoder.attention.query_layer.weight"] = dWq
     g["decoder.attention.energy_layer.weight"] = dv[None, :]
-    g["decoder.attention.key_layer.weight"] = dpk.reshape(B * N, H).T @ enc.reshape(B * N, H)
-    denc += (dpk.reshape(B * N, H) @ Wk).reshape(B, N, H)
+    g["decoder.attention.key_layer.weight"] = _mm(dpk.reshape(B * N, H).T, enc.reshape(B * N, H))
+    denc += _mm(dpk.reshape(B * N, H), Wk).reshape(B, N, H)
     return g, denc, dh
 
 
@@ -321,7 +356,7 @@ def s2vtatt_encode_bwd(p, vid, enc_cache, denc, dh_final, need_dvid=False):
     B, N, V = vid.shape
     dgi, dw_hh, db_hh, _ = gru_seq_bwd(denc.transpose(1, 0, 2), dh_final, enc_cache)
     dgi_bn = dgi.transpose(1, 0, 2).reshape(B * N, -1)
-    g = {"encoder.rnn.weight_ih_l0": dgi_bn.T @ vid.reshape(B * N, V),
+    g = {"encoder.rnn.weight_ih_l0": _mm(dgi_bn.T, vid.reshape(B * N, V)),
          "encoder.rnn.bias_ih_l0": dgi_bn.sum(axis=0),
          "encoder.rnn.weight_hh_l0": dw_hh, "encoder.rnn.bias_hh_l0": db_hh}
     dvid = (dgi_bn @ p["encoder.rnn.weight_ih_l0"]).reshape(B, N, V) if need_dvid else None

@@ -195,6 +195,15 @@ __device__ __forceinline__ float tanh_approx(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// tanh(x) and 1 - tanh(x)^2 from one exponential and one reciprocal, accurate to ~1e-7 relative even where
+// 1 - tanh^2 is tiny (the attention backward needs the derivative's RELATIVE accuracy; tanh.approx's 2^-11 is enough
+// for the forward score only)
+__device__ __forceinline__ void tanh_sech2(float x, float& th, float& sech2) {
+  const float t = __expf(-2.f * fabsf(x));
+  const float r = __fdividef(1.f, 1.f + t);
+  th = copysignf((1.f - t) * r, x);
+  sech2 = 4.f * t * r * r;
+}
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
