@@ -44,6 +44,17 @@ int pvcr_prof_read(uint64_t* launches, double* ms, double* work);
  * forward and backward of one step still agreeing. */
 void pvcr_set_seed_step(const uint64_t* device_counter);
 
+/* Side lane: the library owns a second, lower-priority stream for work that is off the step's critical path (weight
+ * gradients, bias column sums, the embedding scatter), so that it runs next to the persistent recurrent sweeps, which
+ * leave 20 of the 148 SMs free, instead of between them.  Fork and join are event edges (CUDA-graph capturable).
+ *   mode 0: off - everything on the caller's stream;
+ *   mode 1: (default) fork and join inside each call - outputs are complete in stream order when a call returns;
+ *   mode 2: joins deferred - outputs and workspaces of the *_bwd calls are only safe after pvcr_side_join(stream),
+ *           which the caller must issue before consuming gradients, ending a stream capture or freeing workspaces.
+ * pvcr_side_mode returns the previous mode (a value outside 0..2 only queries). */
+int pvcr_side_mode(int mode);
+int pvcr_side_join(void* stream);
+
 /* Tuning aid: in-kernel phase timestamps (clock64 of CTA 0, [step][8]) of the last persistent-kernel launch. */
 int pvcr_debug_phase_timing(int on);
 int pvcr_debug_phase_read(long long* out, int steps);

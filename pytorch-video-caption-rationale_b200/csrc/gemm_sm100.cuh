@@ -341,6 +341,15 @@ struct OperandView {
   int rows, slabs;
 };
 
+// Upper bound on the CTAs of a persistent GEMM launched while a CtaCap is alive on this host thread (0 = all SMs):
+// GEMMs forked onto the side lane next to a persistent recurrent sweep take only the SMs the sweep leaves free.
+int gemm_cta_cap();
+struct CtaCap {
+  int prev;
+  explicit CtaCap(int cap);
+  ~CtaCap();
+};
+
 int make_tensor_map(CUtensorMap* out, const OperandView& v, int K, int box_rows);
 // MN-major operand: bf16 matrix [k_rows, mn_cols] (row stride v.ld, v.rows = k_rows); boxes of 64 (mn) x 64 (k).
 int make_tensor_map_mn(CUtensorMap* out, const OperandView& v, int mn_cols);
@@ -395,7 +404,8 @@ int launch_gemm_tn_persistent(const OperandView& a, const OperandView& b, const 
   const int tiles_m = cdiv(gc.M, GEMM_BM), tiles_n = cdiv(gc.N, BN);
   PVCR_REQUIRE(gc.k_splits <= 1 || grid_z == 1, "gemm: split-K and batched slabs are exclusive");
   const long long num_tiles = (long long)tiles_m * tiles_n * grid_z * (gc.k_splits > 1 ? gc.k_splits : 1);
-  const int grid = (int)(num_tiles < sms ? num_tiles : sms);
+  int grid = (int)(num_tiles < sms ? num_tiles : sms);
+  if (gemm_cta_cap() > 0 && grid > gemm_cta_cap()) grid = gemm_cta_cap();
   {
     LaunchScope ls_(KC_GEMM, stream, 2.0 * gc.M * gc.N * (double)gc.K * grid_z);
     kern<<<grid, GEMM_PERSIST_THREADS, SM::TOTAL + 64, stream>>>(ta, tb, gc, tiles_m, tiles_n, (int)num_tiles, epi);

@@ -8,6 +8,8 @@
 //     tokens (K8/K9), the context half stays in the step;
 //   * W_q and W_hh of the decoder are concatenated so that q = W_q h and gh = W_hh h are one GEMM per step;
 //   * every weight gradient is hoisted out of the time loop into one GEMM over all steps.
+#include <cstdlib>
+
 #include "../../include/pvcr_b200.h"
 #include "host.h"
 
@@ -107,15 +109,22 @@ static void carve(Arena& a, const PvcrDims& d, int need_frame_grad, AttWs& w) {
   w.ctx_x = a.alloc<bf16>(BL * H);
 }
 
-// bf16 copies kept by the staging cache of one backward call (bf16 mode)
-static size_t stage_cache_need(const PvcrDims& d) {
+// bf16 copies kept by the staging cache of one backward call (bf16 mode): the decoder half's planes first, the
+// encoder half's after them.  A part-2 call starts its cache behind the decoder half's region: with deferred side-lane
+// joins the lane may still be reading those planes while part 2 stages its own.
+static size_t dec_cache_need(const PvcrDims& d) {
   Arena a(nullptr, 0);
   const int BL = d.B * d.L, BN = d.B * d.N, H = d.H;
   alloc_planes(a, BL, H, 1); alloc_planes(a, BL, 3 * H, 1); alloc_planes(a, BL, H, 1);      // dq, dgh, h_prev
   alloc_planes(a, BL, 3 * H, 1); alloc_planes(a, BL, H, 1);                                  // dgi, ctx
   alloc_planes(a, BN, H, 1);                                                                 // dpk
+  return a.off + 1024;
+}
+static size_t stage_cache_need(const PvcrDims& d) {
+  Arena a(nullptr, 0);
+  const int BN = d.B * d.N, H = d.H;
   alloc_planes(a, BN, 3 * H, 1); alloc_planes(a, BN, H, 1); alloc_planes(a, BN, 3 * H, 1);   // dgh_enc, h_prev_enc, dgi_enc
-  return a.off + 4096;
+  return dec_cache_need(d) + a.off + 4096;
 }
 
 size_t s2vtatt_workspace(const PvcrDims& d, int need_frame_grad) {
@@ -157,6 +166,15 @@ int s2vtatt_fwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   carve(a, d, 0, w);
   if (a.failed) { set_last_error("s2vtatt_fwd: workspace too small (%zu < %zu)", ws_bytes, a.off); return PVCR_ERR_WORKSPACE; }
 
+  // The hoisted embedding half of the decoder input projection (+ b_ih) depends on nothing the encoder computes:
+  // it runs on the side lane next to the encoder (whose persistent sweep leaves SMs free) and is joined before the
+  // decoder steps.
+  cudaStream_t lane = st;
+  if (side_site(0)) PVCR_TRY(side_fork(st, &lane));
+  PVCR_TRY(prep_weight(p.dec_w_ih + H, H + E, H3, E, w.we, lane));
+  PVCR_TRY(gather_split(p.emb, E, s_in, BL, w.emb_a.ptr, w.emb_a.ld, w.emb_a.Kp, d.nsplit, NO_DROPOUT, lane));
+  PVCR_TRY(gemm_planes(w.emb_a.view(), w.we.view(), BL, H3, (int)w.emb_a.ld, w.ep, H3, p.dec_b_ih, 0, lane));
+
   // weights -> B-role planes
   PVCR_TRY(prep_weight(p.enc_w_ih, V, H3, V, w.wih_enc, st));
   PVCR_TRY(prep_weight(p.enc_w_hh, H, H3, H, w.whh_enc, st));
@@ -164,7 +182,6 @@ int s2vtatt_fwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   PVCR_TRY(prep_weight(p.att_wq, H, H, H, w.wcat, st, 0));
   PVCR_TRY(prep_weight(p.dec_w_hh, H, H3, H, w.wcat, st, H));
   PVCR_TRY(prep_weight(p.dec_w_ih, H + E, H3, H, w.wc, st));
-  PVCR_TRY(prep_weight(p.dec_w_ih + H, H + E, H3, E, w.we, st));
 
   if (w.enc_a.Kp != H) {       // contraction padding of the planes written by the gate kernels must read as zero
     PVCR_TRY(fill_zero(w.enc_a.ptr, sizeof(bf16) * (size_t)BN * w.enc_a.ld, st));
@@ -176,10 +193,9 @@ int s2vtatt_fwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   PVCR_TRY(gemm_planes(w.x_a.view(), w.wih_enc.view(), BN, H3, (int)w.x_a.ld, w.gi_enc, H3, p.enc_b_ih, 0, st));
   PVCR_TRY(gru_seq_fwd(encoder_seq(d, p, w), st));
 
-  // proj_key = enc W_k^T ; hoisted embedding half of the decoder input projection (+ b_ih)
+  // proj_key = enc W_k^T
   PVCR_TRY(gemm_planes(w.enc_a.view(), w.wk.view(), BN, H, (int)w.enc_a.ld, w.pk, H, nullptr, 0, st));
-  PVCR_TRY(gather_split(p.emb, E, s_in, BL, w.emb_a.ptr, w.emb_a.ld, w.emb_a.Kp, d.nsplit, NO_DROPOUT, st));
-  PVCR_TRY(gemm_planes(w.emb_a.view(), w.we.view(), BL, H3, (int)w.emb_a.ld, w.ep, H3, p.dec_b_ih, 0, st));
+  PVCR_TRY(side_join(st));
 
   // decoder steps: one persistent cooperative kernel when the shape allows, else per-step launches
   if (dec_persist_eligible(B, N, H, d.nsplit, w.enc_a.Kp)) {
@@ -243,6 +259,7 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
     return PVCR_ERR_WORKSPACE;
   }
   StageCache cache;
+  if (part == 2) a.alloc<char>(dec_cache_need(d));
   if (ns == 1) {
     a.cache = &cache;
     // operands the forward pass already staged as bf16 planes (same values: frame scale / no dropout included)
@@ -273,11 +290,6 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
     q.dgi_all = w.dgi_all; q.d1_all = w.d1_all; q.dctx_all = w.dctx_all; q.ds_all = w.ds_all;
     q.dh_carry = w.dh_carry; q.xg = w.xg; q.counters = w.sync;
     PVCR_TRY(dec_persist_bwd(q, st));
-    AttnGradArgs ag{};
-    ag.L = L; ag.B = B; ag.N = N; ag.H = H;
-    ag.alpha = w.alpha_all; ag.ds = w.ds_all; ag.dctx = w.dctx_all; ag.q = w.g1_all; ag.q_ld = H4;
-    ag.pk = w.pk; ag.v = p.att_v; ag.dpk = w.dpk; ag.denc = w.denc; ag.dv_part = w.dv_part;
-    PVCR_TRY(attn_grad_hoisted(ag, st));
   } else {
   PVCR_TRY(fill_zero(w.dh_carry, sizeof(float) * (size_t)B * H, st));
   PVCR_TRY(fill_zero(w.dpk, sizeof(float) * (size_t)BN * H, st));
@@ -322,30 +334,55 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   }
 
   // ---- decoder weight gradients, hoisted over all (b, i) rows ----
+  // None of them feeds the encoder half: in bf16 mode they run on the side lane (every operand is cast once into the
+  // staging cache, so no transient scratch is shared between the two streams) while this stream goes on with
+  // d proj_key -> d enc -> encoder sweep.  Persistent GEMMs on the lane can be capped to the SMs a sweep leaves free (PVCR_SIDE_CAP; uncapped measured fastest).
+  const bool fork = persist_dec && ns == 1 && side_site(2);
+  static const int side_cap = getenv("PVCR_SIDE_CAP") ? atoi(getenv("PVCR_SIDE_CAP")) : 0;   // measured: 0 (no cap) 2.56 ms, 40: 2.59, 20: 2.65
+  cudaStream_t ln = st;
+  if (fork) PVCR_TRY(side_fork(st, &ln));          // after the sweep
+  {
+  CtaCap cap_(fork && side_mode() == 2 ? side_cap : 0);
   // h_{i-1} rows in (b, i) order: i = 0 -> encoder final state, i >= 1 -> hs[b, i-1]
   PVCR_CUDA_CHECK(cudaMemcpy2DAsync(w.hprev_dec, sizeof(float) * (size_t)L * H, w.enc + (long long)(N - 1) * H,
-                                    sizeof(float) * (size_t)N * H, sizeof(float) * H, B, cudaMemcpyDeviceToDevice, st));
+                                    sizeof(float) * (size_t)N * H, sizeof(float) * H, B, cudaMemcpyDeviceToDevice, ln));
   if (L > 1)
     PVCR_CUDA_CHECK(cudaMemcpy2DAsync(w.hprev_dec + H, sizeof(float) * (size_t)L * H, hs, sizeof(float) * (size_t)L * H,
-                                      sizeof(float) * (size_t)(L - 1) * H, B, cudaMemcpyDeviceToDevice, st));
-  PVCR_TRY(grad_w(a, w.d1_all, H4, BL, H, w.hprev_dec, H, H, nullptr, nullptr, g.att_wq, H, 0, ns, st));
-  PVCR_TRY(grad_w(a, w.d1_all + H, H4, BL, H3, w.hprev_dec, H, H, nullptr, nullptr, g.dec_w_hh, H, 0, ns, st));
-  PVCR_TRY(colsum(w.d1_all + H, H4, BL, H3, g.dec_b_hh, 0, st));
-  PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, w.ctx_all, H, H, nullptr, nullptr, g.dec_w_ih, H + E, 0, ns, st));
-  PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, p.emb, E, E, s_in, nullptr, g.dec_w_ih + H, H + E, 0, ns, st));
-  PVCR_TRY(colsum(w.dgi_all, H3, BL, H3, g.dec_b_ih, 0, st));
-  if (ns == 1) PVCR_TRY(grad_x_fwdw(a, w.dgi_all, H3, BL, H3, w.we, E, w.demb_rows, E, 0, st));
-  else PVCR_TRY(grad_x(a, w.dgi_all, H3, BL, H3, w.weT, w.demb_rows, E, 0, st));
-  PVCR_TRY(fill_zero(g.emb, sizeof(float) * (size_t)d.Vc * E, st));
-  PVCR_TRY(scatter_add_rows(w.demb_rows, E, s_in, BL, E, g.emb, NO_DROPOUT, st));
-  PVCR_TRY(colsum(w.dv_part, H, B, H, g.att_v, 0, st));
+                                      sizeof(float) * (size_t)(L - 1) * H, B, cudaMemcpyDeviceToDevice, ln));
+  PVCR_TRY(grad_w(a, w.d1_all, H4, BL, H, w.hprev_dec, H, H, nullptr, nullptr, g.att_wq, H, 0, ns, ln));
+  PVCR_TRY(grad_w(a, w.d1_all + H, H4, BL, H3, w.hprev_dec, H, H, nullptr, nullptr, g.dec_w_hh, H, 0, ns, ln));
+  PVCR_TRY(colsum(w.d1_all + H, H4, BL, H3, g.dec_b_hh, 0, ln));
+  PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, w.ctx_all, H, H, nullptr, nullptr, g.dec_w_ih, H + E, 0, ns, ln));
+  PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, p.emb, E, E, s_in, nullptr, g.dec_w_ih + H, H + E, 0, ns, ln));
+  PVCR_TRY(colsum(w.dgi_all, H3, BL, H3, g.dec_b_ih, 0, ln));
+  if (ns == 1) PVCR_TRY(grad_x_fwdw(a, w.dgi_all, H3, BL, H3, w.we, E, w.demb_rows, E, 0, ln));
+  else PVCR_TRY(grad_x(a, w.dgi_all, H3, BL, H3, w.weT, w.demb_rows, E, 0, ln));
+  PVCR_TRY(fill_zero(g.emb, sizeof(float) * (size_t)d.Vc * E, ln));
+  PVCR_TRY(scatter_add_rows(w.demb_rows, E, s_in, BL, E, g.emb, NO_DROPOUT, ln));
+  if (persist_dec) {
+    AttnGradArgs ag{};
+    ag.L = L; ag.B = B; ag.N = N; ag.H = H;
+    ag.alpha = w.alpha_all; ag.ds = w.ds_all; ag.dctx = w.dctx_all; ag.q = w.g1_all; ag.q_ld = H4;
+    ag.pk = w.pk; ag.v = p.att_v; ag.dpk = w.dpk; ag.denc = w.denc; ag.dv_part = w.dv_part;
+    PVCR_TRY(attn_grad_hoisted(ag, st));
+  }
+  if (fork) {
+    // d proj_key is an operand of both streams: cast it once here, then let the lane see it
+    Planes dpk_a = alloc_planes(a, BN, H, 1);
+    if (a.failed) { set_last_error("s2vtatt_bwd: workspace too small (dpk planes)"); return PVCR_ERR_WORKSPACE; }
+    PVCR_TRY(stage(w.dpk, H, BN, H, dpk_a, 0, nullptr, NO_DROPOUT, st));
+    cache.put(w.dpk, H, BN, H, dpk_a);
+    PVCR_TRY(side_fork(st, &ln));
+  }
+  PVCR_TRY(colsum(w.dv_part, H, B, H, g.att_v, 0, ln));
   // key projection: dWk = dpk^T enc ; denc += dpk Wk
-  PVCR_TRY(grad_w(a, w.dpk, H, BN, H, w.enc, H, H, nullptr, nullptr, g.att_wk, H, 0, ns, st));
+  PVCR_TRY(grad_w(a, w.dpk, H, BN, H, w.enc, H, H, nullptr, nullptr, g.att_wk, H, 0, ns, ln));
+  }
   if (ns == 1) PVCR_TRY(grad_x_fwdw(a, w.dpk, H, BN, H, w.wk, H, w.denc, H, 1, st));
   else PVCR_TRY(grad_x(a, w.dpk, H, BN, H, w.wkT, w.denc, H, 1, st));
 
   }   // decoder half
-  if (part == 1) return PVCR_OK;
+  if (part == 1) return side_call_end(st);
   // ---- encoder, reverse time (dh_carry already holds the gradient on the final state) ----
   PVCR_TRY(prep_weight_T(p.enc_w_hh, H, H3, H, w.whh_encT, 0, 1, st));
   GruSeq es = encoder_seq(d, p, w);
@@ -356,13 +393,17 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   eg.dgh = w.dgh_enc; eg.dgh_ts = H3; eg.dgh_ld = (long long)N * H3;
   eg.dgh_a = w.dgh_a; eg.whhT = w.whh_encT; eg.xch = w.xch;
   PVCR_TRY(gru_seq_bwd(es, eg, st));
+  // the two encoder weight gradients are independent: W_hh on the side lane, W_ih here
+  const bool fork2 = ns == 1 && side_site(3);
+  cudaStream_t ln2 = st;
+  if (fork2) PVCR_TRY(side_fork(st, &ln2));
   // h_{t-1} rows in (b, t) order: zero for t = 0
-  PVCR_TRY(fill_zero(w.hprev_enc, sizeof(float) * (size_t)BN * H, st));
+  PVCR_TRY(fill_zero(w.hprev_enc, sizeof(float) * (size_t)BN * H, ln2));
   if (N > 1)
     PVCR_CUDA_CHECK(cudaMemcpy2DAsync(w.hprev_enc + H, sizeof(float) * (size_t)N * H, w.enc, sizeof(float) * (size_t)N * H,
-                                      sizeof(float) * (size_t)(N - 1) * H, B, cudaMemcpyDeviceToDevice, st));
-  PVCR_TRY(grad_w(a, w.dgh_enc, H3, BN, H3, w.hprev_enc, H, H, nullptr, nullptr, g.enc_w_hh, H, 0, ns, st));
-  PVCR_TRY(colsum(w.dgh_enc, H3, BN, H3, g.enc_b_hh, 0, st));
+                                      sizeof(float) * (size_t)(N - 1) * H, B, cudaMemcpyDeviceToDevice, ln2));
+  PVCR_TRY(grad_w(a, w.dgh_enc, H3, BN, H3, w.hprev_enc, H, H, nullptr, nullptr, g.enc_w_hh, H, 0, ns, ln2));
+  PVCR_TRY(colsum(w.dgh_enc, H3, BN, H3, g.enc_b_hh, 0, ln2));
   if (ns == 1 && frame_scale) cache.put(vid, V, BN, V, w.x_a);      // x_a = vid * frame_scale, exactly this operand
   PVCR_TRY(grad_w(a, w.dgi_enc, H3, BN, H3, vid, V, V, nullptr, frame_scale, g.enc_w_ih, V, 0, ns, st));
   PVCR_TRY(colsum(w.dgi_enc, H3, BN, H3, g.enc_b_ih, 0, st));
@@ -372,7 +413,7 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
     else PVCR_TRY(grad_x(a, w.dgi_enc, H3, BN, H3, w.wih_encT, w.dxsel, V, 0, st));
     PVCR_TRY(rowdot(vid, w.dxsel, BN, V, d_frame_scale, st));
   }
-  return PVCR_OK;
+  return side_call_end(st);
 }
 
 // ---- fixed-length greedy decoding (eval branch, model/S2VTAttModel.py:172-191) ---------------------------------

@@ -278,6 +278,12 @@ int vocab_fused_bwd(const float* hs, const float* wv, const float* bv, const lon
     PVCR_CUDA_CHECK(cudaMemset2DAsync(w.D + Vc, sizeof(bf16) * w.ldD, 0, sizeof(bf16) * (w.ldD - Vc), M, st));
   GemmCoords gc{M, Vc, (int)w.hs_a.ld, 0, 0, 0, 0};
   PVCR_TRY((launch_gemm_tn_persistent<CE_BN, 4, EpiCeBwd>(w.hs_a.view(), w.wv.view(), gc, 1, epi, st)));
+  // d W = dlogits^T Dropout(hs) and d b = column sums of dlogits do not feed the rest of the backward: they run on
+  // the side lane next to the d hs product (60 output tiles) and whatever the caller enqueues next.
+  // Both operands as they are (row-major bf16, MN-major tcgen05 operands); hs_a are the planes staged (with the
+  // dropout mask) by the forward pass.
+  cudaStream_t lane = st;
+  if (side_site(1)) PVCR_TRY(side_fork(st, &lane));
   // d hs = dlogits W: A = dlogits (K-major, padding columns written as zeros), B = the forward weight planes [Vc, H]
   // as an MN-major operand (rows past Vc read as zero through the tensor map): no W^T copy
   {
@@ -285,18 +291,17 @@ int vocab_fused_bwd(const float* hs, const float* wv, const float* bv, const lon
     PVCR_TRY(gemm_kn_store(dv, w.wv.view(), M, H, Vc, d_hs, H, 0, st));
   }
   if (dropout_p > 0.f) PVCR_TRY(dropout_apply(d_hs, d_hs, (long long)M * H, dr, st));
-  // d W = dlogits^T Dropout(hs): both operands as they are (row-major bf16, MN-major tcgen05 operands); hs_a are
-  // the planes staged (with the dropout mask) by the forward pass
   {
     OperandView dv{w.D, w.ldD, 0, M, 1};
-    PVCR_TRY(gemm_mn_store(dv, w.hs_a.view(), Vc, H, M, d_wv, H, 0, st));
+    PVCR_TRY(gemm_mn_store(dv, w.hs_a.view(), Vc, H, M, d_wv, H, 0, lane));
   }
-  PVCR_CUDA_CHECK(cudaMemsetAsync(d_bv, 0, sizeof(float) * Vc, st));
+  PVCR_CUDA_CHECK(cudaMemsetAsync(d_bv, 0, sizeof(float) * Vc, lane));
   {
-    LaunchScope ls_(KC_LOSS, st);
-    colsum_bf16_kernel<<<dim3(cdiv(cdiv(Vc, 2), 64), cdiv(M, CS_ROWS)), 256, 0, st>>>(w.D, w.ldD, M, Vc, d_bv);
+    LaunchScope ls_(KC_LOSS, lane);
+    colsum_bf16_kernel<<<dim3(cdiv(cdiv(Vc, 2), 64), cdiv(M, CS_ROWS)), 256, 0, lane>>>(w.D, w.ldD, M, Vc, d_bv);
   }
   PVCR_CUDA_CHECK(cudaGetLastError());
+  PVCR_TRY(side_call_end(st));
   return PVCR_OK;
 }
 

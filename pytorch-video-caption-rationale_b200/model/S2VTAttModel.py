@@ -106,11 +106,25 @@ class S2VTAttModel(nn.Module):
         loss, stats, pred = F_.VocabCrossEntropy.apply(cfg, hs, lin.weight, lin.bias, s, s_len)
         return loss, stats[0] / stats[1], pred
 
-    def train_step_stages(self, vid_feats, s, s_len, frame_scale=None):
+    def train_step_stages(self, vid_feats, s, s_len, frame_scale=None, deferred_join=False):
         """Generator form of the tape-free fwd+bwd: yields once when the vocabulary-projection gradients (out_w, out_b:
         ~47 % of all gradient bytes) are final, so a data-parallel caller can start their all-reduce while the rest of
         the backward runs; returns (loss, acc, pred)."""
         assert self.training and s is not None
+        # deferred_join: the library's side lane (weight-gradient GEMMs etc.) is joined once, at the end of the step,
+        # instead of at the end of every C call; a caller that consumes gradients at the yields must not set it
+        Lb = F_.lib()
+        deferred_join = deferred_join and Lb.pvcr_side_mode(-1) != 0
+        prev_mode = Lb.pvcr_side_mode(2) if deferred_join else None
+        try:
+            out = yield from self._train_step_stages(vid_feats, s, s_len, frame_scale)
+        finally:
+            if deferred_join:
+                F_.check(Lb.pvcr_side_join(F_.stream_ptr()), "pvcr_side_join")
+                Lb.pvcr_side_mode(prev_mode)
+        return out
+
+    def _train_step_stages(self, vid_feats, s, s_len, frame_scale):
         cfg = self._cfg(True)
         params = self._seq_params()
         lin = self.decoder.pred_linear[1]
@@ -155,7 +169,7 @@ class S2VTAttModel(nn.Module):
         """Tape-free fwd+bwd of run_iter (train.py:37-40 + loss.backward()): chains the C-ABI forward and backward
         entry points by hand and (over)writes ``param.grad`` of every parameter.  Stream-ordered and free of autograd
         state, hence capturable in a CUDA graph (pvcr_b200.graphs.GraphedTrainStep).  Returns (loss, acc, pred)."""
-        gen = self.train_step_stages(vid_feats, s, s_len, frame_scale)
+        gen = self.train_step_stages(vid_feats, s, s_len, frame_scale, deferred_join=True)
         try:
             while True:
                 next(gen)
