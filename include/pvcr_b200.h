@@ -37,6 +37,9 @@ const char* pvcr_prof_class_name(int cls);
 void pvcr_prof_enable(int on);
 void pvcr_prof_reset(void);
 int pvcr_prof_read(uint64_t* launches, double* ms, double* work);
+/* Timeline of the event-timed launches since the last reset (host enqueue order): class, start and end in ms relative
+ * to the first launch; returns the number of entries written (<= cap) or a negative error code. */
+int pvcr_prof_timeline(int* cls, float* t0_ms, float* t1_ms, int cap);
 
 /* Registers a device-resident uint64 counter that every dropout / Gumbel draw mixes into its seed when the kernel
  * runs (NULL switches it off).  CUDA-graph replays otherwise repeat the seed baked in at capture; with the counter
@@ -231,6 +234,11 @@ int pvcr_s2vt_decode_steps(const PvcrDims* d, const PvcrS2vtParams* p, const flo
  * (forward) and re-creates them to emit bf16 d logits (backward).
  * _bwd needs the workspace of the matching _fwd untouched; gscale is a device scalar d total / d loss (NULL = 1). */
 size_t pvcr_vocab_ce_workspace(int B, int L, int H, int Vc, int nsplit, float dropout_p);
+/* Optional: stage out_w for a coming pvcr_vocab_ce_fwd on the same workspace on a side lane (see pvcr_side_mode), so
+ * the cast overlaps whatever the caller enqueues in between (the encoder / decoder sweeps).  out_w must not change
+ * until that _fwd; a no-op when the side lanes are off or the fused path does not apply. */
+int pvcr_vocab_ce_prepare(const float* out_w, int B, int L, int H, int Vc, int nsplit, void* workspace,
+                          size_t workspace_bytes, void* stream);
 int pvcr_vocab_ce_fwd(const float* hs, const float* out_w, const float* out_b, const int64_t* target,
                       const int64_t* s_len, int B, int L, int H, int Vc, int nsplit, float dropout_p, uint64_t seed,
                       float* loss3, int64_t* pred, float* lse, float* logits_out, int64_t ld_logits_out,
@@ -252,6 +260,26 @@ int pvcr_masked_ce(const float* logits, int64_t ld, int B, int L, int Vc, const 
                    int64_t ld_d, void* stream);
 int pvcr_rationale_penalties(const float* probs, int B, int N, float* pen, void* stream);
 int pvcr_rationale_penalties_bwd(const float* probs, int B, int N, const float* g_pen, float* dprobs, void* stream);
+
+/* Optimizer step of the reference loop (train.py:104-105,157-160): clip_grad_norm_(params, max_norm) followed by
+ * torch.optim.Adam(lr, betas, eps, weight_decay).step() (L2-style decay: grad += weight_decay * param), fused into
+ * two multi-tensor kernels without host synchronisation.  All tables live in device memory:
+ *   tensors[n]        param / grad / exp_avg / exp_avg_sq pointers and element count of every parameter;
+ *   chunk_tensor[c], chunk_off[c]   chunk c covers elements [off, off + chunk_elems) of tensor chunk_tensor[c];
+ *   partial[n_chunks] scratch; norm_out (nullable) receives the total gradient norm before clipping.
+ * max_norm <= 0 disables clipping.  step_dev (nullable): device step counter, incremented by this call and used for
+ * the bias corrections (CUDA-graph replays advance it); otherwise step_host (>= 1, already incremented) is used. */
+typedef struct {
+  float* param;
+  float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+} PvcrAdamTensor;
+int pvcr_adam_clip_step(const PvcrAdamTensor* tensors, const int32_t* chunk_tensor, const int64_t* chunk_off,
+                        int n_chunks, int chunk_elems, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, float max_norm, int64_t* step_dev, int64_t step_host, float* partial,
+                        float* norm_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -606,3 +606,27 @@ def train_iter_rationale(p, vid, s, s_len, sos_id, max_len, tau, noise, arch="s2
     return dict(loss=loss_ce + lambda_brev * lb + lambda_cont * lc, loss_ce=loss_ce, loss_brev=lambda_brev * lb,
                 loss_cont=lambda_cont * lc, rationale_len=probs[:, :, 1].sum(axis=1).mean(), acc=acc, pred=pred,
                 logits=logits, probs=probs, grads=grads)
+
+
+# ----------------------------------------------------------------------------------------
+# optimizer step (train.py:104-105,157-160): clip_grad_norm_(params, max_norm) + torch.optim.Adam(lr, weight_decay)
+# ----------------------------------------------------------------------------------------
+def clip_adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=2e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                   max_norm=None):
+    """One optimizer step on dicts of arrays (updated in place); ``step`` is the 1-based count of this step.
+    Returns the total gradient norm before clipping.  Follows torch.nn.utils.clip_grad_norm_ (coefficient
+    max_norm / (norm + 1e-6), clamped to 1) and torch.optim.Adam with L2-style decay (grad += weight_decay * param)."""
+    total = np.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for g in grads.values()))
+    coef = 1.0
+    if max_norm is not None and max_norm > 0:
+        coef = min(max_norm / (total + 1e-6), 1.0)
+    b1, b2 = betas
+    bc1, bc2 = 1.0 - b1 ** step, 1.0 - b2 ** step
+    for k in params:
+        g = grads[k] * coef + weight_decay * params[k]
+        exp_avg[k] += (1.0 - b1) * (g - exp_avg[k])
+        exp_avg_sq[k] *= b2
+        exp_avg_sq[k] += (1.0 - b2) * g * g
+        denom = np.sqrt(exp_avg_sq[k]) / np.sqrt(bc2) + eps
+        params[k] -= (lr / bc1) * exp_avg[k] / denom
+    return total

@@ -77,6 +77,7 @@ SIGNATURES = {
     "pvcr_prof_enable": (None, [c_int]),
     "pvcr_prof_reset": (None, []),
     "pvcr_prof_read": (c_int, [P(c_u64), P(ctypes.c_double), P(ctypes.c_double)]),
+    "pvcr_prof_timeline": (c_int, [P(c_int), P(ctypes.c_float), P(ctypes.c_float), c_int]),
     "pvcr_linear_fwd_workspace": (c_size, [c_int, c_int, c_int, c_int]),
     "pvcr_linear_fwd": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_size,
                                 c_vp]),
@@ -110,7 +111,10 @@ SIGNATURES = {
     "pvcr_rationale_penalties_bwd": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
     "pvcr_s2vtatt_bwd_part": (c_int, [P(PvcrDims), P(PvcrS2vtAttParams), c_vp, c_vp, c_vp, c_vp, c_vp, P(PvcrS2vtAttGrads),
                                       c_vp, c_vp, c_size, c_vp, c_int]),
+    "pvcr_adam_clip_step": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_f, c_f, c_f, c_f, c_f, c_f, c_vp, c_i64, c_vp, c_vp,
+                                    c_vp]),
     "pvcr_vocab_ce_workspace": (c_size, [c_int, c_int, c_int, c_int, c_int, c_f]),
+    "pvcr_vocab_ce_prepare": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_size, c_vp]),
     "pvcr_vocab_ce_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_u64, c_vp,
                                   c_vp, c_vp, c_vp, c_i64, c_vp, c_size, c_vp]),
     "pvcr_vocab_ce_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_u64, c_vp, c_vp,

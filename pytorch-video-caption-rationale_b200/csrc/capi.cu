@@ -34,6 +34,7 @@ int generator_fwd(const PvcrDims&, const PvcrGenParams&, const float*, const flo
 int generator_bwd(const PvcrDims&, const PvcrGenParams&, const float*, float, const float*, const float*, const float*,
                   PvcrGenGrads&, void*, size_t, cudaStream_t);
 size_t vocab_ce_workspace(int B, int L, int H, int Vc, int nsplit, float dropout_p);
+int vocab_ce_prepare(const float*, int, int, int, int, int, void*, size_t, cudaStream_t);
 int vocab_ce_fwd(const float*, const float*, const float*, const long long*, const long long*, int, int, int, int, int,
                  float, unsigned long long, float*, long long*, float*, float*, long long, void*, size_t, cudaStream_t);
 int vocab_ce_bwd(const float*, const float*, const float*, const long long*, const long long*, int, int, int, int, int, float,
@@ -145,6 +146,10 @@ int pvcr_rationale_penalties_bwd(const float* probs, int B, int N, const float* 
 }
 size_t pvcr_vocab_ce_workspace(int B, int L, int H, int Vc, int nsplit, float dropout_p) {
   return vocab_ce_workspace(B, L, H, Vc, nsplit, dropout_p);
+}
+int pvcr_vocab_ce_prepare(const float* out_w, int B, int L, int H, int Vc, int nsplit, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  return vocab_ce_prepare(out_w, B, L, H, Vc, nsplit, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 int pvcr_vocab_ce_fwd(const float* hs, const float* out_w, const float* out_b, const int64_t* target,
                       const int64_t* s_len, int B, int L, int H, int Vc, int nsplit, float dropout_p, uint64_t seed,

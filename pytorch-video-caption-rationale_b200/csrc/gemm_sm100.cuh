@@ -155,6 +155,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint8_t* epi_smem = smem + SM::BAR_OFFSET + 256;   // Epi::SMEM_BYTES of staging, split evenly over the 8 epilogue warps
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -260,6 +261,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       const int acc = ti & 1;
       const int row = m0 + q * 32 + lane;
       Epi e = epi;
+      if constexpr (Epi::SMEM_BYTES > 0) e.attach(epi_smem + (warp - 2) * (Epi::SMEM_BYTES / 8));
       e.begin(row, splits > 1 ? w - t * splits : z);
       mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);
       tc_fence_after();
@@ -286,6 +288,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 
 // Plain store epilogue: C = acc (+ bias[n]) (+ C).  fp32 output, arbitrary ldc.
 struct EpiStore {
+  static constexpr int SMEM_BYTES = 0;      // shared-memory staging the persistent kernel reserves for the epilogue warps
   float* C;
   long long ldc, c_zstride;
   const float* bias;
@@ -395,7 +398,7 @@ int launch_gemm_tn_persistent(const OperandView& a, const OperandView& b, const 
   static bool attr_set = false;
   static int sms = 0;
   if (!attr_set) {
-    PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL + 64));
+    PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL + 64 + 256 + Epi::SMEM_BYTES));
     int dev = 0;
     PVCR_CUDA_CHECK(cudaGetDevice(&dev));
     PVCR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -408,7 +411,7 @@ int launch_gemm_tn_persistent(const OperandView& a, const OperandView& b, const 
   if (gemm_cta_cap() > 0 && grid > gemm_cta_cap()) grid = gemm_cta_cap();
   {
     LaunchScope ls_(KC_GEMM, stream, 2.0 * gc.M * gc.N * (double)gc.K * grid_z);
-    kern<<<grid, GEMM_PERSIST_THREADS, SM::TOTAL + 64, stream>>>(ta, tb, gc, tiles_m, tiles_n, (int)num_tiles, epi);
+    kern<<<grid, GEMM_PERSIST_THREADS, SM::TOTAL + 64 + 256 + Epi::SMEM_BYTES, stream>>>(ta, tb, gc, tiles_m, tiles_n, (int)num_tiles, epi);
   }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;

@@ -223,6 +223,28 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_bwd_kernel(con
   }
   unsigned arrivals = 0;
 
+  // Saved activations of a step (written by the forward pass long ago: HBM latency) are fetched one step ahead,
+  // right after the arrive of the previous step, so their latency hides behind the exchange and the product.
+  float pe[MAX_ITEMS], pr[MAX_ITEMS], pz[MAX_ITEMS], pn[MAX_ITEMS], pg[MAX_ITEMS], ph[MAX_ITEMS];
+  auto fetch = [&](int t) {
+#pragma unroll
+    for (int k = 0; k < MAX_ITEMS; ++k) {
+      pe[k] = pr[k] = pz[k] = pn[k] = pg[k] = ph[k] = 0.f;
+      if (k < n_items) {
+        const int idx = tid + k * PERSIST_THREADS, jj = idx % u, lb = idx / u;
+        const int j = j0 + jj, b = b0 + lb;
+        if (lb < bs && b < p.B) {
+          if (p.dh_ext) pe[k] = __ldg(p.dh_ext + (long long)t * p.dh_ext_ts + (long long)b * p.dh_ext_ld + j);
+          const long long o = ((long long)t * p.B + b) * H + j;
+          pr[k] = __ldg(p.r + o); pz[k] = __ldg(p.z + o); pn[k] = __ldg(p.n + o); pg[k] = __ldg(p.ghn + o);
+          if (t > 0) ph[k] = __ldg(p.h + (long long)(t - 1) * p.h_ts + (long long)b * p.h_ld + j);
+          else if (p.h0) ph[k] = __ldg(p.h0 + (long long)b * p.h0_ld + j);
+        }
+      }
+    }
+  };
+  fetch(p.T - 1);
+
   for (int t = p.T - 1; t >= 0; --t) {
     const bool has_prev = (t > 0) || (p.h0 != nullptr);
     bf16* xw = p.xch + (size_t)(t & 1) * p.B * K;
@@ -234,13 +256,8 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_bwd_kernel(con
         const int idx = tid + k * PERSIST_THREADS, jj = idx % u, lb = idx / u;
         const int j = j0 + jj, b = b0 + lb;
         if (lb < bs && b < p.B) {
-          float dh = dhc[k];
-          if (p.dh_ext) dh += p.dh_ext[(long long)t * p.dh_ext_ts + (long long)b * p.dh_ext_ld + j];
-          const long long o = ((long long)t * p.B + b) * H + j;
-          const float r = p.r[o], z = p.z[o], n = p.n[o], ghn = p.ghn[o];
-          float hp = 0.f;
-          if (t > 0) hp = p.h[(long long)(t - 1) * p.h_ts + (long long)b * p.h_ld + j];
-          else if (p.h0) hp = p.h0[(long long)b * p.h0_ld + j];
+          const float dh = dhc[k] + pe[k];
+          const float r = pr[k], z = pz[k], n = pn[k], ghn = pg[k], hp = ph[k];
           const float dn = dh * (1.f - z), dz = dh * (hp - n);
           const float dnp = dn * (1.f - n * n);
           const float dzp = dz * z * (1.f - z);
@@ -248,12 +265,12 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_bwd_kernel(con
           const float dghn = dnp * r;
           float* dgi = p.dgi + (long long)t * p.dgi_ts + (long long)b * p.dgi_ld;
           float* dgh = p.dgh + (long long)t * p.dgh_ts + (long long)b * p.dgh_ld;
-          dgi[j] = drp; dgi[H + j] = dzp; dgi[2 * H + j] = dnp;
-          dgh[j] = drp; dgh[H + j] = dzp; dgh[2 * H + j] = dghn;
-          if (has_prev) {
+          if (has_prev) {          // the exchange operand first: it is what the group waits for
             bf16* x = xw + (long long)b * K;
             x[j] = __float2bfloat16_rn(drp); x[H + j] = __float2bfloat16_rn(dzp); x[2 * H + j] = __float2bfloat16_rn(dghn);
           }
+          dgi[j] = drp; dgi[H + j] = dzp; dgi[2 * H + j] = dnp;
+          dgh[j] = drp; dgh[H + j] = dzp; dgh[2 * H + j] = dghn;
           dhc[k] = dh * z;
           zreg[k] = 1.f;
         }
@@ -262,6 +279,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_bwd_kernel(con
     if (has_prev) {
       group_arrive(ctr);
       ++arrivals;
+      if (t > 0) fetch(t - 1);
       group_wait(ctr, (unsigned)p.C * arrivals);
       load_operand_rows_async(sX, bs, 0, xw, K, b0, bs, p.B, K);
       cp_async_commit();

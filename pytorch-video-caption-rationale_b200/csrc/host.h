@@ -11,9 +11,12 @@ const char* last_error();
 // ---- side lane (side.cu): second, lower-priority stream for work off the step's critical path --------------------
 int side_mode();                                        // 0 off, 1 join at the end of each call, 2 deferred join
 bool side_site(int bit);                                // fork site enabled (PVCR_SIDE_MASK tuning aid; false when off)
-int side_fork(cudaStream_t main, cudaStream_t* lane);   // lane waits for main's current point (*lane == main when off)
-int side_join(cudaStream_t main);                       // main waits for the lane's current point
+int side_fork(cudaStream_t main, cudaStream_t* lane, int id = 0);   // lane `id` waits for main's current point (*lane == main when off)
+int side_join(cudaStream_t main);                       // main waits for every lane's current point
 int side_call_end(cudaStream_t main);                   // join unless mode 2
+enum SideNote { NOTE_ATT_BWD_WEIGHTS = 1, NOTE_VOCAB_WV = 2 };
+void side_note_put(const void* key, int tag);           // one-shot notes between the calls of a step (side.cu)
+bool side_note_take(const void* key, int tag);
 
 // Bump allocator over a caller-provided workspace.  With base == nullptr it only measures (used by the
 // *_workspace_bytes queries, so sizing and carving share one code path).

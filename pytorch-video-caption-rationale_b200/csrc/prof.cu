@@ -80,6 +80,23 @@ int pvcr_prof_read(uint64_t* launches, double* ms, double* work) {
   return PVCR_OK;
 }
 
+// Timeline of the event-timed launches since the last reset: for launch i (in host enqueue order) cls[i] and its
+// start / end in milliseconds relative to the first launch's start.  Returns the number of launches written.
+int pvcr_prof_timeline(int* cls, float* t0, float* t1, int cap) {
+  std::lock_guard<std::mutex> g(g_mu);
+  int n = 0;
+  for (auto& e : g_pending) {
+    if (n >= cap) break;
+    if (cudaEventSynchronize(e.b) != cudaSuccess) return PVCR_ERR_CUDA;
+    float a = 0.f, b = 0.f;
+    if (cudaEventElapsedTime(&a, g_pending[0].a, e.a) != cudaSuccess) return PVCR_ERR_CUDA;
+    if (cudaEventElapsedTime(&b, g_pending[0].a, e.b) != cudaSuccess) return PVCR_ERR_CUDA;
+    cls[n] = e.cls; t0[n] = a; t1[n] = b;
+    ++n;
+  }
+  return n;
+}
+
 // Device counter mixed into every dropout / Gumbel seed at kernel run time (NULL = off).  A CUDA graph captures the
 // pointer, not the value: incrementing the counter between (or inside) replays gives every replay fresh masks.
 void pvcr_set_seed_step(const uint64_t* device_counter) {

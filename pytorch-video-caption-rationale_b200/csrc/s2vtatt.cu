@@ -156,6 +156,17 @@ static GruSeq encoder_seq(const PvcrDims& d, const PvcrS2vtAttParams& p, const A
   return s;
 }
 
+// Transposed weight planes of the backward sweeps (they depend on the parameters only).
+static int att_bwd_weights(const PvcrDims& d, const PvcrS2vtAttParams& p, const AttWs& w, cudaStream_t st) {
+  const int H = d.H, E = d.E, H3 = 3 * H;
+  PVCR_TRY(prep_weight_T(p.dec_w_ih, H + E, H3, H, w.wcT, 0, 1, st));
+  PVCR_TRY(fill_zero(w.wcatT.ptr, sizeof(bf16) * (size_t)w.wcatT.rows * w.wcatT.ld, st));
+  PVCR_TRY(prep_weight_T(p.att_wq, H, H, H, w.wcatT, 0, 0, st));
+  PVCR_TRY(prep_weight_T(p.dec_w_hh, H, H3, H, w.wcatT, H, 0, st));
+  PVCR_TRY(prep_weight_T(p.enc_w_hh, H, H3, H, w.whh_encT, 0, 1, st));
+  return PVCR_OK;
+}
+
 int s2vtatt_fwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid, const float* frame_scale,
                 const long long* s_in, float* hs, float* alphas, void* ws, size_t ws_bytes, cudaStream_t st) {
   PVCR_TRY(check_dims(d));
@@ -166,36 +177,45 @@ int s2vtatt_fwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   carve(a, d, 0, w);
   if (a.failed) { set_last_error("s2vtatt_fwd: workspace too small (%zu < %zu)", ws_bytes, a.off); return PVCR_ERR_WORKSPACE; }
 
-  // The hoisted embedding half of the decoder input projection (+ b_ih) depends on nothing the encoder computes:
-  // it runs on the side lane next to the encoder (whose persistent sweep leaves SMs free) and is joined before the
-  // decoder steps.
-  cudaStream_t lane = st;
-  if (side_site(0)) PVCR_TRY(side_fork(st, &lane));
-  PVCR_TRY(prep_weight(p.dec_w_ih + H, H + E, H3, E, w.we, lane));
-  PVCR_TRY(gather_split(p.emb, E, s_in, BL, w.emb_a.ptr, w.emb_a.ld, w.emb_a.Kp, d.nsplit, NO_DROPOUT, lane));
-  PVCR_TRY(gemm_planes(w.emb_a.view(), w.we.view(), BL, H3, (int)w.emb_a.ld, w.ep, H3, p.dec_b_ih, 0, lane));
-
-  // weights -> B-role planes
+  // Critical chain on the caller's stream: W_ih cast -> frame staging -> input-projection GEMM -> encoder sweep.
+  // Everything else that only depends on the inputs runs on side lanes next to it and is joined before the sweep:
+  //   lane 0: the other weight casts;
+  //   lane 1: the hoisted embedding half of the decoder input projection (+ b_ih);
+  //   lane 2: the transposed weight planes of the backward decoder sweep (the backward call finds a note and skips them).
+  cudaStream_t l0 = st, l1 = st, l2 = st;
+  const bool fork = side_site(0);
+  if (fork) { PVCR_TRY(side_fork(st, &l0, 0)); PVCR_TRY(side_fork(st, &l1, 1)); }
   PVCR_TRY(prep_weight(p.enc_w_ih, V, H3, V, w.wih_enc, st));
-  PVCR_TRY(prep_weight(p.enc_w_hh, H, H3, H, w.whh_enc, st));
-  PVCR_TRY(prep_weight(p.att_wk, H, H, H, w.wk, st));
-  PVCR_TRY(prep_weight(p.att_wq, H, H, H, w.wcat, st, 0));
-  PVCR_TRY(prep_weight(p.dec_w_hh, H, H3, H, w.wcat, st, H));
-  PVCR_TRY(prep_weight(p.dec_w_ih, H + E, H3, H, w.wc, st));
-
-  if (w.enc_a.Kp != H) {       // contraction padding of the planes written by the gate kernels must read as zero
-    PVCR_TRY(fill_zero(w.enc_a.ptr, sizeof(bf16) * (size_t)BN * w.enc_a.ld, st));
-    PVCR_TRY(fill_zero(w.hs_a.ptr, sizeof(bf16) * (size_t)BL * w.hs_a.ld, st));
-    PVCR_TRY(fill_zero(w.ctx_a.ptr, sizeof(bf16) * (size_t)B * w.ctx_a.ld, st));
-  }
-  // encoder: gi = (vid * frame_scale) W_ih^T + b_ih for all frames, then N recurrent steps
   PVCR_TRY(stage(vid, V, BN, V, w.x_a, 0, frame_scale, NO_DROPOUT, st));
   PVCR_TRY(gemm_planes(w.x_a.view(), w.wih_enc.view(), BN, H3, (int)w.x_a.ld, w.gi_enc, H3, p.enc_b_ih, 0, st));
+
+  PVCR_TRY(prep_weight(p.enc_w_hh, H, H3, H, w.whh_enc, l0));
+  PVCR_TRY(prep_weight(p.att_wk, H, H, H, w.wk, l0));
+  PVCR_TRY(prep_weight(p.att_wq, H, H, H, w.wcat, l0, 0));
+  PVCR_TRY(prep_weight(p.dec_w_hh, H, H3, H, w.wcat, l0, H));
+  PVCR_TRY(prep_weight(p.dec_w_ih, H + E, H3, H, w.wc, l0));
+  if (w.enc_a.Kp != H) {       // contraction padding of the planes written by the gate kernels must read as zero
+    PVCR_TRY(fill_zero(w.enc_a.ptr, sizeof(bf16) * (size_t)BN * w.enc_a.ld, l0));
+    PVCR_TRY(fill_zero(w.hs_a.ptr, sizeof(bf16) * (size_t)BL * w.hs_a.ld, l0));
+    PVCR_TRY(fill_zero(w.ctx_a.ptr, sizeof(bf16) * (size_t)B * w.ctx_a.ld, l0));
+  }
+
+  PVCR_TRY(prep_weight(p.dec_w_ih + H, H + E, H3, E, w.we, l1));
+  PVCR_TRY(gather_split(p.emb, E, s_in, BL, w.emb_a.ptr, w.emb_a.ld, w.emb_a.Kp, d.nsplit, NO_DROPOUT, l1));
+  PVCR_TRY(gemm_planes(w.emb_a.view(), w.we.view(), BL, H3, (int)w.emb_a.ld, w.ep, H3, p.dec_b_ih, 0, l1));
+
+  side_note_take(ws, NOTE_ATT_BWD_WEIGHTS);          // a stale note of an earlier forward on this workspace
+  if (fork) {
+    PVCR_TRY(side_fork(st, &l2, 2));
+    PVCR_TRY(att_bwd_weights(d, p, w, l2));
+    side_note_put(ws, NOTE_ATT_BWD_WEIGHTS);
+  }
+  PVCR_TRY(side_join(st));
+  // encoder: N recurrent steps on gi = (vid * frame_scale) W_ih^T + b_ih
   PVCR_TRY(gru_seq_fwd(encoder_seq(d, p, w), st));
 
   // proj_key = enc W_k^T
   PVCR_TRY(gemm_planes(w.enc_a.view(), w.wk.view(), BN, H, (int)w.enc_a.ld, w.pk, H, nullptr, 0, st));
-  PVCR_TRY(side_join(st));
 
   // decoder steps: one persistent cooperative kernel when the shape allows, else per-step launches
   if (dec_persist_eligible(B, N, H, d.nsplit, w.enc_a.Kp)) {
@@ -267,12 +287,9 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
     cache.put(w.enc, H, BN, H, w.enc_a);
     cache.put(s_in, -1, BL, E, w.emb_a);
   }
+  // transposed weights of the sweeps: already staged by the forward call on this workspace, or staged here
+  if (part != 2 && !side_note_take(ws, NOTE_ATT_BWD_WEIGHTS)) PVCR_TRY(att_bwd_weights(d, p, w, st));
   if (part != 2) {
-  // transposed weights for the data-gradient GEMMs
-  PVCR_TRY(prep_weight_T(p.dec_w_ih, H + E, H3, H, w.wcT, 0, 1, st));
-  PVCR_TRY(fill_zero(w.wcatT.ptr, sizeof(bf16) * (size_t)w.wcatT.rows * w.wcatT.ld, st));
-  PVCR_TRY(prep_weight_T(p.att_wq, H, H, H, w.wcatT, 0, 0, st));
-  PVCR_TRY(prep_weight_T(p.dec_w_hh, H, H3, H, w.wcatT, H, 0, st));
   if (ns > 1) {     // bf16 mode multiplies by the forward weight planes directly (MN-major operand)
     PVCR_TRY(prep_weight_T(p.att_wk, H, H, H, w.wkT, 0, 1, st));
     PVCR_TRY(prep_weight_T(p.dec_w_ih + H, H + E, H3, E, w.weT, 0, 1, st));
@@ -338,27 +355,29 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   // staging cache, so no transient scratch is shared between the two streams) while this stream goes on with
   // d proj_key -> d enc -> encoder sweep.  Persistent GEMMs on the lane can be capped to the SMs a sweep leaves free (PVCR_SIDE_CAP; uncapped measured fastest).
   const bool fork = persist_dec && ns == 1 && side_site(2);
-  static const int side_cap = getenv("PVCR_SIDE_CAP") ? atoi(getenv("PVCR_SIDE_CAP")) : 0;   // measured: 0 (no cap) 2.56 ms, 40: 2.59, 20: 2.65
-  cudaStream_t ln = st;
-  if (fork) PVCR_TRY(side_fork(st, &ln));          // after the sweep
+  static const int side_cap = getenv("PVCR_SIDE_CAP") ? atoi(getenv("PVCR_SIDE_CAP")) : 0;   // measured: 0 (no cap) fastest
+  // lane A: gradients fed by [dq | dgh] and h_{i-1};  lane B: gradients fed by dgi;  lane C: d v, d W_k.  No staged
+  // operand is shared between lanes (d proj_key, which this stream needs too, is staged here before lane C forks).
+  cudaStream_t la = st, lb = st, lc = st;
+  if (fork) { PVCR_TRY(side_fork(st, &la, 0)); PVCR_TRY(side_fork(st, &lb, 1)); }          // after the sweep
   {
   CtaCap cap_(fork && side_mode() == 2 ? side_cap : 0);
   // h_{i-1} rows in (b, i) order: i = 0 -> encoder final state, i >= 1 -> hs[b, i-1]
   PVCR_CUDA_CHECK(cudaMemcpy2DAsync(w.hprev_dec, sizeof(float) * (size_t)L * H, w.enc + (long long)(N - 1) * H,
-                                    sizeof(float) * (size_t)N * H, sizeof(float) * H, B, cudaMemcpyDeviceToDevice, ln));
+                                    sizeof(float) * (size_t)N * H, sizeof(float) * H, B, cudaMemcpyDeviceToDevice, la));
   if (L > 1)
     PVCR_CUDA_CHECK(cudaMemcpy2DAsync(w.hprev_dec + H, sizeof(float) * (size_t)L * H, hs, sizeof(float) * (size_t)L * H,
-                                      sizeof(float) * (size_t)(L - 1) * H, B, cudaMemcpyDeviceToDevice, ln));
-  PVCR_TRY(grad_w(a, w.d1_all, H4, BL, H, w.hprev_dec, H, H, nullptr, nullptr, g.att_wq, H, 0, ns, ln));
-  PVCR_TRY(grad_w(a, w.d1_all + H, H4, BL, H3, w.hprev_dec, H, H, nullptr, nullptr, g.dec_w_hh, H, 0, ns, ln));
-  PVCR_TRY(colsum(w.d1_all + H, H4, BL, H3, g.dec_b_hh, 0, ln));
-  PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, w.ctx_all, H, H, nullptr, nullptr, g.dec_w_ih, H + E, 0, ns, ln));
-  PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, p.emb, E, E, s_in, nullptr, g.dec_w_ih + H, H + E, 0, ns, ln));
-  PVCR_TRY(colsum(w.dgi_all, H3, BL, H3, g.dec_b_ih, 0, ln));
-  if (ns == 1) PVCR_TRY(grad_x_fwdw(a, w.dgi_all, H3, BL, H3, w.we, E, w.demb_rows, E, 0, ln));
-  else PVCR_TRY(grad_x(a, w.dgi_all, H3, BL, H3, w.weT, w.demb_rows, E, 0, ln));
-  PVCR_TRY(fill_zero(g.emb, sizeof(float) * (size_t)d.Vc * E, ln));
-  PVCR_TRY(scatter_add_rows(w.demb_rows, E, s_in, BL, E, g.emb, NO_DROPOUT, ln));
+                                      sizeof(float) * (size_t)(L - 1) * H, B, cudaMemcpyDeviceToDevice, la));
+  PVCR_TRY(grad_w(a, w.d1_all + H, H4, BL, H3, w.hprev_dec, H, H, nullptr, nullptr, g.dec_w_hh, H, 0, ns, la));
+  PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, w.ctx_all, H, H, nullptr, nullptr, g.dec_w_ih, H + E, 0, ns, lb));
+  PVCR_TRY(grad_w(a, w.d1_all, H4, BL, H, w.hprev_dec, H, H, nullptr, nullptr, g.att_wq, H, 0, ns, la));
+  PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, p.emb, E, E, s_in, nullptr, g.dec_w_ih + H, H + E, 0, ns, lb));
+  PVCR_TRY(colsum(w.d1_all + H, H4, BL, H3, g.dec_b_hh, 0, la));
+  if (ns == 1) PVCR_TRY(grad_x_fwdw(a, w.dgi_all, H3, BL, H3, w.we, E, w.demb_rows, E, 0, lb));
+  else PVCR_TRY(grad_x(a, w.dgi_all, H3, BL, H3, w.weT, w.demb_rows, E, 0, lb));
+  PVCR_TRY(fill_zero(g.emb, sizeof(float) * (size_t)d.Vc * E, lb));
+  PVCR_TRY(scatter_add_rows(w.demb_rows, E, s_in, BL, E, g.emb, NO_DROPOUT, lb));
+  PVCR_TRY(colsum(w.dgi_all, H3, BL, H3, g.dec_b_ih, 0, lb));
   if (persist_dec) {
     AttnGradArgs ag{};
     ag.L = L; ag.B = B; ag.N = N; ag.H = H;
@@ -372,11 +391,11 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
     if (a.failed) { set_last_error("s2vtatt_bwd: workspace too small (dpk planes)"); return PVCR_ERR_WORKSPACE; }
     PVCR_TRY(stage(w.dpk, H, BN, H, dpk_a, 0, nullptr, NO_DROPOUT, st));
     cache.put(w.dpk, H, BN, H, dpk_a);
-    PVCR_TRY(side_fork(st, &ln));
+    PVCR_TRY(side_fork(st, &lc, 2));
   }
-  PVCR_TRY(colsum(w.dv_part, H, B, H, g.att_v, 0, ln));
+  PVCR_TRY(colsum(w.dv_part, H, B, H, g.att_v, 0, lc));
   // key projection: dWk = dpk^T enc ; denc += dpk Wk
-  PVCR_TRY(grad_w(a, w.dpk, H, BN, H, w.enc, H, H, nullptr, nullptr, g.att_wk, H, 0, ns, ln));
+  PVCR_TRY(grad_w(a, w.dpk, H, BN, H, w.enc, H, H, nullptr, nullptr, g.att_wk, H, 0, ns, lc));
   }
   if (ns == 1) PVCR_TRY(grad_x_fwdw(a, w.dpk, H, BN, H, w.wk, H, w.denc, H, 1, st));
   else PVCR_TRY(grad_x(a, w.dpk, H, BN, H, w.wkT, w.denc, H, 1, st));
@@ -384,7 +403,6 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   }   // decoder half
   if (part == 1) return side_call_end(st);
   // ---- encoder, reverse time (dh_carry already holds the gradient on the final state) ----
-  PVCR_TRY(prep_weight_T(p.enc_w_hh, H, H3, H, w.whh_encT, 0, 1, st));
   GruSeq es = encoder_seq(d, p, w);
   GruSeqGrad eg{};
   eg.dh_ext = w.denc; eg.dh_ext_ts = H; eg.dh_ext_ld = (long long)N * H;

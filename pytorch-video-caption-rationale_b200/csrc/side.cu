@@ -6,6 +6,7 @@
 // Fork / join are event record + stream wait pairs: capturable into a CUDA graph (they become graph edges).
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "../../include/pvcr_b200.h"
 #include "host.h"
@@ -13,34 +14,37 @@
 namespace pvcr {
 
 namespace {
+constexpr int NLANES = 3;
 struct Lane {
   cudaStream_t s = nullptr;
-  cudaEvent_t ev[16];
-  int next = 0;
   bool pending = false;        // work enqueued on the lane since the last join
-  int device = -1;
 };
 std::mutex g_mu;
-Lane g_lane;
+Lane g_lane[NLANES];
+cudaEvent_t g_ev[32];
+int g_next = 0, g_device = -1;
 int g_mode = getenv("PVCR_SIDE_MODE") ? atoi(getenv("PVCR_SIDE_MODE")) : 1;     // tuning override of the default
+int g_nlanes = getenv("PVCR_SIDE_LANES") ? atoi(getenv("PVCR_SIDE_LANES")) : NLANES;   // tuning aid: fold lanes together
 thread_local int g_cta_cap = 0;
 
-int ensure_lane() {
+int ensure_lanes() {
   int dev = 0;
   PVCR_CUDA_CHECK(cudaGetDevice(&dev));
-  if (g_lane.s && g_lane.device == dev) return PVCR_OK;
-  PVCR_REQUIRE(g_lane.s == nullptr, "side lane: one device per process (lane lives on device %d, current %d)",
-               g_lane.device, dev);
+  if (g_lane[0].s && g_device == dev) return PVCR_OK;
+  PVCR_REQUIRE(g_lane[0].s == nullptr, "side lane: one device per process (lanes live on device %d, current %d)",
+               g_device, dev);
   int lo = 0, hi = 0;
   PVCR_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));     // lo = least priority (numerically greatest)
-  PVCR_CUDA_CHECK(cudaStreamCreateWithPriority(&g_lane.s, cudaStreamNonBlocking, lo));
-  for (auto& e : g_lane.ev) PVCR_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  g_lane.device = dev;
+  for (auto& l : g_lane) PVCR_CUDA_CHECK(cudaStreamCreateWithPriority(&l.s, cudaStreamNonBlocking, lo));
+  for (auto& e : g_ev) PVCR_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  g_device = dev;
+  if (g_nlanes < 1) g_nlanes = 1;
+  if (g_nlanes > NLANES) g_nlanes = NLANES;
   return PVCR_OK;
 }
 cudaEvent_t next_event() {
-  cudaEvent_t e = g_lane.ev[g_lane.next];
-  g_lane.next = (g_lane.next + 1) % 16;
+  cudaEvent_t e = g_ev[g_next];
+  g_next = (g_next + 1) % 32;
   return e;
 }
 }  // namespace
@@ -51,29 +55,56 @@ bool side_site(int bit) {
   return g_mode != 0 && ((mask >> bit) & 1);
 }
 
-// The lane waits for everything enqueued on `main` so far.  *out = lane stream (== main when the lane is off).
-int side_fork(cudaStream_t main, cudaStream_t* out) {
+// Lane `id` waits for everything enqueued on `main` so far.  *out = lane stream (== main when the lanes are off).
+// Work on different lanes is unordered; work on one lane runs in enqueue order.
+int side_fork(cudaStream_t main, cudaStream_t* out, int id) {
   *out = main;
   if (g_mode == 0) return PVCR_OK;
   std::lock_guard<std::mutex> g(g_mu);
-  PVCR_TRY(ensure_lane());
+  PVCR_TRY(ensure_lanes());
+  Lane& l = g_lane[(id < 0 ? 0 : id) % g_nlanes];
   cudaEvent_t e = next_event();
   PVCR_CUDA_CHECK(cudaEventRecord(e, main));
-  PVCR_CUDA_CHECK(cudaStreamWaitEvent(g_lane.s, e, 0));
-  g_lane.pending = true;
-  *out = g_lane.s;
+  PVCR_CUDA_CHECK(cudaStreamWaitEvent(l.s, e, 0));
+  l.pending = true;
+  *out = l.s;
   return PVCR_OK;
 }
 
-// `main` waits for everything enqueued on the lane so far.
+// `main` waits for everything enqueued on every lane so far.
 int side_join(cudaStream_t main) {
   std::lock_guard<std::mutex> g(g_mu);
-  if (!g_lane.s || !g_lane.pending) return PVCR_OK;
-  cudaEvent_t e = next_event();
-  PVCR_CUDA_CHECK(cudaEventRecord(e, g_lane.s));
-  PVCR_CUDA_CHECK(cudaStreamWaitEvent(main, e, 0));
-  g_lane.pending = false;
+  for (auto& l : g_lane) {
+    if (!l.s || !l.pending) continue;
+    cudaEvent_t e = next_event();
+    PVCR_CUDA_CHECK(cudaEventRecord(e, l.s));
+    PVCR_CUDA_CHECK(cudaStreamWaitEvent(main, e, 0));
+    l.pending = false;
+  }
   return PVCR_OK;
+}
+
+// One-shot notes between the C-ABI calls of one step, keyed by a workspace pointer: a call that already produced
+// something a later call would otherwise compute (e.g. the forward pass staging the transposed weights of the backward
+// sweep on a lane) leaves a note; the later call takes it.  A call that could have left a note but did not clears it.
+namespace {
+struct Note { const void* key; int tag; };
+std::vector<Note> g_notes;
+}
+void side_note_put(const void* key, int tag) {
+  std::lock_guard<std::mutex> g(g_mu);
+  for (auto& n : g_notes) if (n.key == key && n.tag == tag) return;
+  if (g_notes.size() > 256) g_notes.clear();
+  g_notes.push_back(Note{key, tag});
+}
+bool side_note_take(const void* key, int tag) {
+  std::lock_guard<std::mutex> g(g_mu);
+  for (size_t i = 0; i < g_notes.size(); ++i)
+    if (g_notes[i].key == key && g_notes[i].tag == tag) {
+      g_notes.erase(g_notes.begin() + i);
+      return true;
+    }
+  return false;
 }
 
 // End of a C-ABI call: mode 1 joins here, mode 2 leaves the lane running until pvcr_side_join().

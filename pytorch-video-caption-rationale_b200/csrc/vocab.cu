@@ -16,6 +16,7 @@ int vocab_fused_fwd(const float*, const float*, const float*, const long long*, 
 int vocab_fused_bwd(const float*, const float*, const float*, const long long*, const long long*, int, int, int, int,
                     float, unsigned long long, const float*, float*, float*, float*, const float*, void*, size_t,
                     cudaStream_t);
+int vocab_fused_prepare(const float*, int, int, int, int, void*, size_t, cudaStream_t);
 static bool fused_off() { static const bool off = getenv("PVCR_NO_FUSED_CE") != nullptr; return off; }
 
 struct VocabWs {
@@ -48,6 +49,11 @@ size_t vocab_ce_workspace(int B, int L, int H, int Vc, int nsplit, float dropout
 
 static Dropout out_dropout(float p, unsigned long long seed) { return make_dropout(p, seed, 0x5000000000ull); }
 
+int vocab_ce_prepare(const float* wv, int B, int L, int H, int Vc, int nsplit, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (nsplit != 1 || fused_off()) return PVCR_OK;
+  return vocab_fused_prepare(wv, B, L, H, Vc, ws, ws_bytes, st);
+}
+
 // loss3 = {masked loss, #correct, #mask}; pred [B*L] int64; logits stay in the workspace for vocab_ce_bwd.
 int vocab_ce_fwd(const float* hs, const float* wv, const float* bv, const long long* target, const long long* s_len,
                  int B, int L, int H, int Vc, int nsplit, float dropout_p, unsigned long long seed, float* loss3,
@@ -56,6 +62,7 @@ int vocab_ce_fwd(const float* hs, const float* wv, const float* bv, const long l
   PVCR_REQUIRE(nsplit >= 1 && nsplit <= 3, "vocab_ce_fwd: nsplit=%d", nsplit);
   if (nsplit == 1 && !logits_out && target && !fused_off())
     return vocab_fused_fwd(hs, wv, bv, target, s_len, B, L, H, Vc, dropout_p, seed, loss3, pred, lse, ws, ws_bytes, st);
+  if (side_note_take(ws, NOTE_VOCAB_WV)) PVCR_TRY(side_join(st));     // a prepare whose fused layout is not used here
   const int M = B * L;
   Arena a(ws, ws_bytes);
   VocabWs w;

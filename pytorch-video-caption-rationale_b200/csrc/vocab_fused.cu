@@ -18,6 +18,7 @@ constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
 struct EpiCeFwd {
+  static constexpr int SMEM_BYTES = 0;
   const float* bias;
   float *pmax, *psum; int* pidx;
   int M, N, nparts;
@@ -69,10 +70,17 @@ struct EpiCeFwd {
 };
 
 struct EpiCeBwd {
+  // A thread owns one row of the accumulator, so a direct store scatters 32 rows per warp instruction (one
+  // L1 wavefront per row).  Each epilogue warp instead transposes its 32 x 32 bf16 chunk through 2 KB of shared
+  // memory (16-byte slots XOR-swizzled, conflict free both ways) and stores 8 rows x 64 contiguous bytes per
+  // instruction: 4x fewer LSU wavefronts, which were as long as the MMA main loop of a K = 512 tile.
+  static constexpr int SMEM_BYTES = 8 * 2048;
   const float* bias; const long long* target; const float *lse2, *roww;      // lse2 = lse * log2(e)
   bf16* D; long long ldD;
   int M, N;
   float l2, w; int t;
+  uint4* stage;
+  __device__ __forceinline__ void attach(uint8_t* warp_smem) { stage = reinterpret_cast<uint4*>(warp_smem); }
   __device__ __forceinline__ void begin(int row, int) {
     l2 = 0.f; w = 0.f; t = -1;
     if (row < M) { l2 = lse2[row]; w = roww[row]; t = (int)target[row]; }
@@ -105,11 +113,17 @@ struct EpiCeBwd {
       o[j4 * 2] = __floats2bfloat162_rn(d[0], d[1]);
       o[j4 * 2 + 1] = __floats2bfloat162_rn(d[2], d[3]);
     }
-    if (row < M) {
-      uint4* dst = reinterpret_cast<uint4*>(D + (long long)row * ldD + col0);
+    const int lane = threadIdx.x & 31, row_base = row - lane;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dst[j] = reinterpret_cast<const uint4*>(o)[j];
+    for (int c = 0; c < 4; ++c) stage[lane * 4 + (c ^ ((lane >> 1) & 3))] = reinterpret_cast<const uint4*>(o)[c];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = i * 8 + (lane >> 2), c = lane & 3;
+      const uint4 val = stage[r * 4 + (c ^ ((r >> 1) & 3))];
+      if (row_base + r < M) *reinterpret_cast<uint4*>(D + (long long)(row_base + r) * ldD + col0 + c * 8) = val;
     }
+    __syncwarp();
   }
   __device__ __forceinline__ void end(int, int, int) {}
 };
@@ -226,6 +240,22 @@ size_t vocab_fused_workspace(int M, int H, int Vc) {
 
 static Dropout fused_out_dropout(float p, unsigned long long seed) { return make_dropout(p, seed, 0x5000000000ull); }
 
+// Stage the vocabulary weights (fp32 -> bf16 planes) of a coming vocab_fused_fwd on a side lane: a caller that knows
+// the projection follows (the tape-free train step) issues this before the encoder / decoder sweeps, which takes the
+// 71 MB cast off the critical path between the decoder sweep and the projection.  Leaves a note on the workspace.
+int vocab_fused_prepare(const float* wv, int B, int L, int H, int Vc, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (side_mode() == 0) return PVCR_OK;
+  Arena a(ws, ws_bytes);
+  FusedWs w;
+  carve_fused(a, B * L, H, Vc, w);
+  if (a.failed) { set_last_error("vocab_fused_prepare: workspace too small (%zu < %zu)", ws_bytes, a.off); return PVCR_ERR_WORKSPACE; }
+  cudaStream_t lane;
+  PVCR_TRY(side_fork(st, &lane, 2));
+  PVCR_TRY(prep_weight(wv, H, Vc, H, w.wv, lane));
+  side_note_put(ws, NOTE_VOCAB_WV);
+  return PVCR_OK;
+}
+
 int vocab_fused_fwd(const float* hs, const float* wv, const float* bv, const long long* target, const long long* s_len,
                     int B, int L, int H, int Vc, float dropout_p, unsigned long long seed, float* loss3, long long* pred,
                     float* lse, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -235,7 +265,8 @@ int vocab_fused_fwd(const float* hs, const float* wv, const float* bv, const lon
   carve_fused(a, M, H, Vc, w);
   if (a.failed) { set_last_error("vocab_fused_fwd: workspace too small (%zu < %zu)", ws_bytes, a.off); return PVCR_ERR_WORKSPACE; }
   PVCR_TRY(stage(hs, H, M, H, w.hs_a, 0, nullptr, fused_out_dropout(dropout_p, seed), st));
-  PVCR_TRY(prep_weight(wv, H, Vc, H, w.wv, st));
+  if (side_note_take(ws, NOTE_VOCAB_WV)) PVCR_TRY(side_join(st));       // staged by vocab_fused_prepare on a lane
+  else PVCR_TRY(prep_weight(wv, H, Vc, H, w.wv, st));
   {
     LaunchScope ls_(KC_LOSS, st);
     target_logit_kernel<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(w.hs_a.ptr, w.hs_a.ld, w.wv.ptr, w.wv.ld, bv, target,
@@ -282,8 +313,8 @@ int vocab_fused_bwd(const float* hs, const float* wv, const float* bv, const lon
   // the side lane next to the d hs product (60 output tiles) and whatever the caller enqueues next.
   // Both operands as they are (row-major bf16, MN-major tcgen05 operands); hs_a are the planes staged (with the
   // dropout mask) by the forward pass.
-  cudaStream_t lane = st;
-  if (side_site(1)) PVCR_TRY(side_fork(st, &lane));
+  cudaStream_t lane = st, lane1 = st;
+  if (side_site(1)) { PVCR_TRY(side_fork(st, &lane, 0)); PVCR_TRY(side_fork(st, &lane1, 1)); }
   // d hs = dlogits W: A = dlogits (K-major, padding columns written as zeros), B = the forward weight planes [Vc, H]
   // as an MN-major operand (rows past Vc read as zero through the tensor map): no W^T copy
   {
@@ -295,10 +326,10 @@ int vocab_fused_bwd(const float* hs, const float* wv, const float* bv, const lon
     OperandView dv{w.D, w.ldD, 0, M, 1};
     PVCR_TRY(gemm_mn_store(dv, w.hs_a.view(), Vc, H, M, d_wv, H, 0, lane));
   }
-  PVCR_CUDA_CHECK(cudaMemsetAsync(d_bv, 0, sizeof(float) * Vc, lane));
+  PVCR_CUDA_CHECK(cudaMemsetAsync(d_bv, 0, sizeof(float) * Vc, lane1));
   {
-    LaunchScope ls_(KC_LOSS, lane);
-    colsum_bf16_kernel<<<dim3(cdiv(cdiv(Vc, 2), 64), cdiv(M, CS_ROWS)), 256, 0, lane>>>(w.D, w.ldD, M, Vc, d_bv);
+    LaunchScope ls_(KC_LOSS, lane1);
+    colsum_bf16_kernel<<<dim3(cdiv(cdiv(Vc, 2), 64), cdiv(M, CS_ROWS)), 256, 0, lane1>>>(w.D, w.ldD, M, Vc, d_bv);
   }
   PVCR_CUDA_CHECK(cudaGetLastError());
   PVCR_TRY(side_call_end(st));

@@ -232,7 +232,9 @@ class VocabCrossEntropy(torch.autograd.Function):
         t_c, l_c = _i64c(target), _i64c(s_len)
         Lb = lib()
         nsplit, p, seed = cfg["nsplit"], float(cfg.get("dropout_p", 0.0)), int(cfg.get("seed", 0))
-        ws = _ws(Lb.pvcr_vocab_ce_workspace(B, L, H, Vc, nsplit, p), hs.device)
+        ws = cfg.get("vocab_ws")              # pre-allocated (and possibly pre-staged: vocab_prepare) by the caller
+        if ws is None:
+            ws = _ws(Lb.pvcr_vocab_ce_workspace(B, L, H, Vc, nsplit, p), hs.device)
         loss3 = torch.empty(3, dtype=torch.float32, device=hs.device)
         pred = torch.empty((B, L), dtype=torch.int64, device=hs.device)
         lse = torch.empty((B, L), dtype=torch.float32, device=hs.device)
@@ -260,6 +262,18 @@ class VocabCrossEntropy(torch.autograd.Function):
                                    ptr(d_hs), ptr(d_w), ptr(d_b), ptr(lse), ptr(pred), ptr(ws), ws.numel(),
                                    stream_ptr()), "pvcr_vocab_ce_bwd")
         return None, d_hs, d_w, d_b, None, None
+
+
+def vocab_prepare(cfg, B, L, out_w):
+    """Allocate the workspace of the coming VocabCrossEntropy.forward and start staging out_w on a side lane of the
+    library (pvcr_vocab_ce_prepare); the workspace travels in cfg["vocab_ws"]."""
+    Vc, H = out_w.shape
+    Lb = lib()
+    nsplit, p = cfg["nsplit"], float(cfg.get("dropout_p", 0.0))
+    ws = _ws(Lb.pvcr_vocab_ce_workspace(B, L, H, Vc, nsplit, p), out_w.device)
+    check(Lb.pvcr_vocab_ce_prepare(ptr(_f32c(out_w)), B, L, H, Vc, nsplit, ptr(ws), ws.numel(), stream_ptr()),
+          "pvcr_vocab_ce_prepare")
+    cfg["vocab_ws"] = ws
 
 
 class VocabLogits(torch.autograd.Function):

@@ -132,6 +132,7 @@ class S2VTAttModel(nn.Module):
         cfg["grad_out"] = {f: p.grad for f, p in zip(F_.ATT_SEQ_FIELDS, params) if p.grad is not None}
         cfg["vocab_grad_out"] = {"out_w": lin.weight.grad, "out_b": lin.bias.grad}
         c1, c2 = F_.ManualCtx(), F_.ManualCtx()
+        F_.vocab_prepare(cfg, vid_feats.shape[0], 1 + min(s.shape[1], self.decoder.max_len - 1), lin.weight)      # W_v cast overlaps the sweeps
         hs, alphas = F_.S2VTAttSequence.forward(c1, cfg, vid_feats, frame_scale, self._shifted(s, vid_feats.shape[0]),
                                                 *params)
         self.last_alphas = alphas
