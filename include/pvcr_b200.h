@@ -29,7 +29,8 @@ const char* pvcr_last_error(void);
 int pvcr_version(void);
 
 /* Launch accounting used by bench.py: every kernel launch of the library is counted per kernel class; with
- * pvcr_prof_enable(1) each launch is additionally bracketed by a CUDA-event pair on its stream.
+ * pvcr_prof_enable(1) each launch is additionally bracketed by a CUDA-event pair on its stream (2: also launches
+ * captured into a CUDA graph, as external event-record nodes that every replay re-records).
  * pvcr_prof_read fills launches[], ms[] (summed event durations; synchronises) and work[] (executed tensor-core
  * FLOPs for the GEMM class) for pvcr_prof_num_classes() classes, all since the last pvcr_prof_reset(). */
 int pvcr_prof_num_classes(void);

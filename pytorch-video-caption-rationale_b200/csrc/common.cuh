@@ -47,7 +47,7 @@ void set_last_error(const char* fmt, ...);
 enum KernelClass { KC_GEMM = 0, KC_STAGE, KC_GATE, KC_ATTN, KC_LOSS, KC_GRU_FWD, KC_GRU_BWD, KC_DEC_FWD, KC_DEC_BWD, KC_MISC,
                    KC_COUNT };
 struct LaunchScope {
-  int cls; cudaStream_t st; void* rec;
+  int cls; cudaStream_t st; void* rec; bool ext;
   LaunchScope(int cls, cudaStream_t st, double work = 0.0);
   ~LaunchScope();
 };

@@ -714,6 +714,7 @@ __global__ void __launch_bounds__(AG_DIMS * AG_FG) attn_grad_hoisted_kernel(cons
     const int n = fg + AG_FG * m;
     if (ok && n < N) {
       a.dpk[((long long)b * N + n) * H + d] = acc_pk[m] * vd;
+      if (a.dpk_a) a.dpk_a[((long long)b * N + n) * a.dpk_a_ld + d] = __float2bfloat16_rn(acc_pk[m] * vd);
       a.denc[((long long)b * N + n) * H + d] = acc_en[m];
     }
   }

@@ -189,6 +189,8 @@ struct GruPersistBwd {
   float* dgi; long long dgi_ts, dgi_ld;
   float* dgh; long long dgh_ts, dgh_ld;
   bf16* xch;                                // exchange [2][B][3H] bf16
+  bf16* dgi_p; long long dgi_p_ts, dgi_p_ld;  // optional bf16 copies (nullable)
+  bf16* dgh_p; long long dgh_p_ts, dgh_p_ld;
   unsigned* counters;
 };
 
@@ -271,6 +273,14 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_bwd_kernel(con
           }
           dgi[j] = drp; dgi[H + j] = dzp; dgi[2 * H + j] = dnp;
           dgh[j] = drp; dgh[H + j] = dzp; dgh[2 * H + j] = dghn;
+          if (p.dgi_p) {
+            bf16* q = p.dgi_p + (long long)t * p.dgi_p_ts + (long long)b * p.dgi_p_ld;
+            q[j] = __float2bfloat16_rn(drp); q[H + j] = __float2bfloat16_rn(dzp); q[2 * H + j] = __float2bfloat16_rn(dnp);
+          }
+          if (p.dgh_p) {
+            bf16* q = p.dgh_p + (long long)t * p.dgh_p_ts + (long long)b * p.dgh_p_ld;
+            q[j] = __float2bfloat16_rn(drp); q[H + j] = __float2bfloat16_rn(dzp); q[2 * H + j] = __float2bfloat16_rn(dghn);
+          }
           dhc[k] = dh * z;
           zreg[k] = 1.f;
         }
@@ -433,6 +443,8 @@ int gru_persist_bwd(const GruSeq& s, const GruSeqGrad& g, cudaStream_t st) {
   p.dgi = g.dgi; p.dgi_ts = g.dgi_ts; p.dgi_ld = g.dgi_ld;
   p.dgh = g.dgh; p.dgh_ts = g.dgh_ts; p.dgh_ld = g.dgh_ld;
   p.xch = g.xch;
+  p.dgi_p = g.dgi_p; p.dgi_p_ts = g.dgi_p_ts; p.dgi_p_ld = g.dgi_p_ld;
+  p.dgh_p = g.dgh_p; p.dgh_p_ts = g.dgh_p_ts; p.dgh_p_ld = g.dgh_p_ld;
   p.counters = s.sync;
   PVCR_TRY(fill_zero(s.sync, sizeof(unsigned) * 32 * pl.G, st));
   return coop_launch((const void*)gru_persist_bwd_kernel, pl.G * pl.C, pl.smem, &p, st, "gru_persist_bwd", KC_GRU_BWD);

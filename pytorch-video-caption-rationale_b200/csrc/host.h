@@ -160,6 +160,9 @@ struct GruSeqGrad {
   Planes dgh_a;                            // scratch A-role planes [B, P*(3H)p]
   Planes whhT;                             // transposed B-role planes of W_hh [H, P*(3H)p]
   bf16* xch;                               // [2][B][3H] bf16 exchange buffer of the persistent kernel (nullable)
+  // optional bf16 copies of dgi / dgh written by the persistent kernel (operands of the hoisted gradient GEMMs)
+  bf16* dgi_p = nullptr; long long dgi_p_ts = 0, dgi_p_ld = 0;
+  bf16* dgh_p = nullptr; long long dgh_p_ts = 0, dgh_p_ld = 0;
 };
 // Persistent single-launch implementations (gru_persist.cu); used by gru_seq_* when eligible.
 bool gru_persist_eligible(const GruSeq& s);
@@ -233,6 +236,7 @@ struct AttnGradArgs {
   const float* q; long long q_ld;           // step i: q + i*B*q_ld
   const float *pk, *v;
   float *dpk, *denc, *dv_part;              // [B,N,H], [B,N,H], [B,H]  (all overwritten)
+  bf16* dpk_a = nullptr; long long dpk_a_ld = 0;   // optional bf16 copy of dpk (rows b*N + n)
 };
 int attn_grad_hoisted(const AttnGradArgs& a, cudaStream_t st);
 int dec_persist_bwd(const DecPersistBwd& p, cudaStream_t st);

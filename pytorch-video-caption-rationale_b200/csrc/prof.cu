@@ -13,25 +13,28 @@ struct EventPair { cudaEvent_t a, b; int cls; };
 static std::mutex g_mu;
 static unsigned long long g_launches[KC_COUNT];
 static double g_work[KC_COUNT];
-static bool g_timing = false;
+static int g_timing = 0;        // 1: time eager launches; 2: also launches captured into a CUDA graph (external event nodes)
 static std::vector<EventPair> g_pending;
 static std::vector<EventPair> g_pool;
 static const char* const g_names[KC_COUNT] = {"gemm_tcgen05", "operand_staging", "rnn_gates", "attention",
                                               "loss", "gru_persistent_fwd", "gru_persistent_bwd",
                                               "decoder_persistent_fwd", "decoder_persistent_bwd", "misc"};
 
-LaunchScope::LaunchScope(int c, cudaStream_t s, double work) : cls(c), st(s), rec(nullptr) {
+LaunchScope::LaunchScope(int c, cudaStream_t s, double work) : cls(c), st(s), rec(nullptr), ext(false) {
   std::lock_guard<std::mutex> g(g_mu);
   g_launches[c]++;
   g_work[c] += work;
   if (!g_timing) return;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+  if (cudaStreamIsCapturing(s, &cs) != cudaSuccess) return;
+  const bool capturing = cs != cudaStreamCaptureStatusNone;
+  if (capturing && g_timing < 2) return;
   EventPair ep;
   if (!g_pool.empty()) { ep = g_pool.back(); g_pool.pop_back(); }
   else if (cudaEventCreate(&ep.a) != cudaSuccess || cudaEventCreate(&ep.b) != cudaSuccess) return;
   ep.cls = c;
-  cudaEventRecord(ep.a, s);
+  cudaEventRecordWithFlags(ep.a, s, capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+  ext = capturing;
   g_pending.push_back(ep);
   rec = reinterpret_cast<void*>(g_pending.size());     // 1-based index
 }
@@ -39,7 +42,7 @@ LaunchScope::~LaunchScope() {
   if (!rec) return;
   std::lock_guard<std::mutex> g(g_mu);
   const size_t i = reinterpret_cast<size_t>(rec) - 1;
-  if (i < g_pending.size()) cudaEventRecord(g_pending[i].b, st);
+  if (i < g_pending.size()) cudaEventRecordWithFlags(g_pending[i].b, st, ext ? cudaEventRecordExternal : cudaEventRecordDefault);
 }
 
 static const unsigned long long* g_seed_step = nullptr;
@@ -59,7 +62,7 @@ int pvcr_prof_num_classes(void) { return KC_COUNT; }
 const char* pvcr_prof_class_name(int cls) { return (cls >= 0 && cls < KC_COUNT) ? g_names[cls] : ""; }
 void pvcr_prof_enable(int on) {
   std::lock_guard<std::mutex> g(g_mu);
-  g_timing = on != 0;
+  g_timing = on < 0 ? 0 : (on > 2 ? 2 : on);
 }
 void pvcr_prof_reset(void) {
   std::lock_guard<std::mutex> g(g_mu);

@@ -184,7 +184,7 @@ int s2vtatt_fwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   //   lane 2: the transposed weight planes of the backward decoder sweep (the backward call finds a note and skips them).
   cudaStream_t l0 = st, l1 = st, l2 = st;
   const bool fork = side_site(0);
-  if (fork) { PVCR_TRY(side_fork(st, &l0, 0)); PVCR_TRY(side_fork(st, &l1, 1)); }
+  if (fork) { PVCR_TRY(side_fork(st, &l0, 0)); PVCR_TRY(side_fork(st, &l1, 1)); PVCR_TRY(side_fork(st, &l2, 2)); }
   PVCR_TRY(prep_weight(p.enc_w_ih, V, H3, V, w.wih_enc, st));
   PVCR_TRY(stage(vid, V, BN, V, w.x_a, 0, frame_scale, NO_DROPOUT, st));
   PVCR_TRY(gemm_planes(w.x_a.view(), w.wih_enc.view(), BN, H3, (int)w.x_a.ld, w.gi_enc, H3, p.enc_b_ih, 0, st));
@@ -206,7 +206,6 @@ int s2vtatt_fwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
 
   side_note_take(ws, NOTE_ATT_BWD_WEIGHTS);          // a stale note of an earlier forward on this workspace
   if (fork) {
-    PVCR_TRY(side_fork(st, &l2, 2));
     PVCR_TRY(att_bwd_weights(d, p, w, l2));
     side_note_put(ws, NOTE_ATT_BWD_WEIGHTS);
   }
@@ -372,7 +371,6 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, w.ctx_all, H, H, nullptr, nullptr, g.dec_w_ih, H + E, 0, ns, lb));
   PVCR_TRY(grad_w(a, w.d1_all, H4, BL, H, w.hprev_dec, H, H, nullptr, nullptr, g.att_wq, H, 0, ns, la));
   PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, p.emb, E, E, s_in, nullptr, g.dec_w_ih + H, H + E, 0, ns, lb));
-  PVCR_TRY(colsum(w.d1_all + H, H4, BL, H3, g.dec_b_hh, 0, la));
   if (ns == 1) PVCR_TRY(grad_x_fwdw(a, w.dgi_all, H3, BL, H3, w.we, E, w.demb_rows, E, 0, lb));
   else PVCR_TRY(grad_x(a, w.dgi_all, H3, BL, H3, w.weT, w.demb_rows, E, 0, lb));
   PVCR_TRY(fill_zero(g.emb, sizeof(float) * (size_t)d.Vc * E, lb));
@@ -383,17 +381,18 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
     ag.L = L; ag.B = B; ag.N = N; ag.H = H;
     ag.alpha = w.alpha_all; ag.ds = w.ds_all; ag.dctx = w.dctx_all; ag.q = w.g1_all; ag.q_ld = H4;
     ag.pk = w.pk; ag.v = p.att_v; ag.dpk = w.dpk; ag.denc = w.denc; ag.dv_part = w.dv_part;
+    if (ns == 1) {
+      // d proj_key feeds two GEMMs (d W_k on a lane, d enc here): the kernel emits its bf16 operand planes itself
+      Planes dpk_a = alloc_planes(a, BN, H, 1);
+      if (a.failed) { set_last_error("s2vtatt_bwd: workspace too small (dpk planes)"); return PVCR_ERR_WORKSPACE; }
+      ag.dpk_a = dpk_a.ptr; ag.dpk_a_ld = dpk_a.ld;
+      cache.put(w.dpk, H, BN, H, dpk_a);
+    }
     PVCR_TRY(attn_grad_hoisted(ag, st));
   }
-  if (fork) {
-    // d proj_key is an operand of both streams: cast it once here, then let the lane see it
-    Planes dpk_a = alloc_planes(a, BN, H, 1);
-    if (a.failed) { set_last_error("s2vtatt_bwd: workspace too small (dpk planes)"); return PVCR_ERR_WORKSPACE; }
-    PVCR_TRY(stage(w.dpk, H, BN, H, dpk_a, 0, nullptr, NO_DROPOUT, st));
-    cache.put(w.dpk, H, BN, H, dpk_a);
-    PVCR_TRY(side_fork(st, &lc, 2));
-  }
+  if (fork) PVCR_TRY(side_fork(st, &lc, 2));
   PVCR_TRY(colsum(w.dv_part, H, B, H, g.att_v, 0, lc));
+  PVCR_TRY(colsum(w.d1_all + H, H4, BL, H3, g.dec_b_hh, 0, lc));
   // key projection: dWk = dpk^T enc ; denc += dpk Wk
   PVCR_TRY(grad_w(a, w.dpk, H, BN, H, w.enc, H, H, nullptr, nullptr, g.att_wk, H, 0, ns, lc));
   }
@@ -410,11 +409,20 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   eg.dgi = w.dgi_enc; eg.dgi_ts = H3; eg.dgi_ld = (long long)N * H3;
   eg.dgh = w.dgh_enc; eg.dgh_ts = H3; eg.dgh_ld = (long long)N * H3;
   eg.dgh_a = w.dgh_a; eg.whhT = w.whh_encT; eg.xch = w.xch;
+  const bool enc_planes = ns == 1 && gru_persist_eligible(es);
+  if (enc_planes) {     // the persistent sweep emits the bf16 operand planes of the two weight-gradient GEMMs itself
+    Planes dgi_p = alloc_planes(a, BN, H3, 1), dgh_p = alloc_planes(a, BN, H3, 1);
+    if (a.failed) { set_last_error("s2vtatt_bwd: workspace too small (encoder gradient planes)"); return PVCR_ERR_WORKSPACE; }
+    eg.dgi_p = dgi_p.ptr; eg.dgi_p_ts = dgi_p.ld; eg.dgi_p_ld = (long long)N * dgi_p.ld;
+    eg.dgh_p = dgh_p.ptr; eg.dgh_p_ts = dgh_p.ld; eg.dgh_p_ld = (long long)N * dgh_p.ld;
+    cache.put(w.dgi_enc, H3, BN, H3, dgi_p);
+    cache.put(w.dgh_enc, H3, BN, H3, dgh_p);
+  }
   PVCR_TRY(gru_seq_bwd(es, eg, st));
-  // the two encoder weight gradients are independent: W_hh on the side lane, W_ih here
+  // the two encoder weight gradients are independent: W_hh and the bias column sums on side lanes, W_ih here
   const bool fork2 = ns == 1 && side_site(3);
-  cudaStream_t ln2 = st;
-  if (fork2) PVCR_TRY(side_fork(st, &ln2));
+  cudaStream_t ln2 = st, ln3 = st;
+  if (fork2) { PVCR_TRY(side_fork(st, &ln2, 2)); PVCR_TRY(side_fork(st, &ln3, 1)); }     // lane 2 is idle by now
   // h_{t-1} rows in (b, t) order: zero for t = 0
   PVCR_TRY(fill_zero(w.hprev_enc, sizeof(float) * (size_t)BN * H, ln2));
   if (N > 1)
@@ -422,9 +430,9 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
                                       sizeof(float) * (size_t)(N - 1) * H, B, cudaMemcpyDeviceToDevice, ln2));
   PVCR_TRY(grad_w(a, w.dgh_enc, H3, BN, H3, w.hprev_enc, H, H, nullptr, nullptr, g.enc_w_hh, H, 0, ns, ln2));
   PVCR_TRY(colsum(w.dgh_enc, H3, BN, H3, g.enc_b_hh, 0, ln2));
+  PVCR_TRY(colsum(w.dgi_enc, H3, BN, H3, g.enc_b_ih, 0, ln3));
   if (ns == 1 && frame_scale) cache.put(vid, V, BN, V, w.x_a);      // x_a = vid * frame_scale, exactly this operand
   PVCR_TRY(grad_w(a, w.dgi_enc, H3, BN, H3, vid, V, V, nullptr, frame_scale, g.enc_w_ih, V, 0, ns, st));
-  PVCR_TRY(colsum(w.dgi_enc, H3, BN, H3, g.enc_b_ih, 0, st));
   if (need_frame_grad) {
     // d(sel) = dgi W_ih ; d frame_scale[b,n] = sum_v vid[b,n,v] * dsel[b,n,v]   (model/RationaleNet.py:52)
     if (ns == 1) PVCR_TRY(grad_x_fwdw(a, w.dgi_enc, H3, BN, H3, w.wih_enc, V, w.dxsel, V, 0, st));

@@ -1,4 +1,5 @@
-"""Tuning aid: per-launch timeline (CUDA events on the launching streams) of one eager fwd+bwd step at cfg2."""
+"""Tuning aid: per-launch timeline (CUDA events on the launching streams) of one fwd+bwd step at cfg2, eager or
+(argument "graph") as recorded inside a CUDA-graph replay."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -14,9 +15,17 @@ s_len = torch.randint(1, L + 1, (B,), device="cuda")
 for _ in range(3): m.train_step_grads(vid, s, s_len)
 torch.cuda.synchronize()
 Lb = _lib.lib()
-Lb.pvcr_prof_reset(); Lb.pvcr_prof_enable(1)
-m.train_step_grads(vid, s, s_len)
-torch.cuda.synchronize()
+if len(sys.argv) > 1 and sys.argv[1] == "graph":
+    from pvcr_b200.graphs import GraphedTrainStep
+    Lb.pvcr_prof_reset(); Lb.pvcr_prof_enable(2)
+    step = GraphedTrainStep(m, (vid, s, s_len), warmup=0)
+    Lb.pvcr_prof_enable(0)
+    for _ in range(3): step(vid, s, s_len)
+    torch.cuda.synchronize()
+else:
+    Lb.pvcr_prof_reset(); Lb.pvcr_prof_enable(1)
+    m.train_step_grads(vid, s, s_len)
+    torch.cuda.synchronize()
 cap = 512
 cls = (ctypes.c_int * cap)(); t0 = (ctypes.c_float * cap)(); t1 = (ctypes.c_float * cap)()
 n = Lb.pvcr_prof_timeline(cls, t0, t1, cap)
