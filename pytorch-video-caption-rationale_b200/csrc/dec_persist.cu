@@ -487,6 +487,16 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
           float* d1 = p.d1_all + ((long long)b * L + i) * 4 * H + H;
           dgi[j] = drp; dgi[H + j] = dzp; dgi[2 * H + j] = dnp;
           d1[j] = drp; d1[H + j] = dzp; d1[2 * H + j] = dghn;
+          if (p.dgi_p) {
+            bf16* q = p.dgi_p + ((long long)b * L + i) * p.dgi_p_ld;
+            q[j] = __float2bfloat16_rn(drp); q[H + j] = __float2bfloat16_rn(dzp); q[2 * H + j] = __float2bfloat16_rn(dnp);
+          }
+          if (p.d1_p) {
+            bf16* q = p.d1_p + ((long long)b * L + i) * p.d1_p_ld + H;
+            const float keep = i > 0 ? 1.f : 0.f;
+            q[j] = __float2bfloat16_rn(drp * keep); q[H + j] = __float2bfloat16_rn(dzp * keep);
+            q[2 * H + j] = __float2bfloat16_rn(dghn * keep);
+          }
           dhc[k] = dh * z;
         }
       }
@@ -623,6 +633,7 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
           for (int f = 0; f < FG; ++f) dq += sC[f * H + d];
           p.d1_all[((long long)vb * L + i) * 4 * H + d] = dq;
           xg[(long long)vb * xrow + d] = __float2bfloat16_rn(dq);
+          if (p.d1_p) p.d1_p[((long long)vb * L + i) * p.d1_p_ld + d] = __float2bfloat16_rn(i > 0 ? dq : 0.f);
         }
       }
     }

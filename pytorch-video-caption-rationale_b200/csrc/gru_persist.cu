@@ -277,9 +277,11 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_bwd_kernel(con
             bf16* q = p.dgi_p + (long long)t * p.dgi_p_ts + (long long)b * p.dgi_p_ld;
             q[j] = __float2bfloat16_rn(drp); q[H + j] = __float2bfloat16_rn(dzp); q[2 * H + j] = __float2bfloat16_rn(dnp);
           }
-          if (p.dgh_p) {
-            bf16* q = p.dgh_p + (long long)t * p.dgh_p_ts + (long long)b * p.dgh_p_ld;
-            q[j] = __float2bfloat16_rn(drp); q[H + j] = __float2bfloat16_rn(dzp); q[2 * H + j] = __float2bfloat16_rn(dghn);
+          if (p.dgh_p) {      // rows of a step without a previous state (h_{-1} = 0) are written as zeros: the product
+            bf16* q = p.dgh_p + (long long)t * p.dgh_p_ts + (long long)b * p.dgh_p_ld;      // with h_{t-1} can then
+            const float keep = has_prev ? 1.f : 0.f;                                         // run on shifted h planes
+            q[j] = __float2bfloat16_rn(drp * keep); q[H + j] = __float2bfloat16_rn(dzp * keep);
+            q[2 * H + j] = __float2bfloat16_rn(dghn * keep);
           }
           dhc[k] = dh * z;
           zreg[k] = 1.f;

@@ -226,6 +226,11 @@ struct DecPersistBwd {
   float* ds_all;                            // [L][B][N] d(score)
   float* dh_carry;                          // [B,H] out: gradient on the initial state (encoder final)
   bf16* xg;                                 // exchange [2][B][5H]: [dq | drp | dzp | dghn | dnp]
+  // optional bf16 operand planes of the hoisted gradient GEMMs, rows b*L + i (nullable):
+  //   dgi_p [.,3H] = d gi;  d1_p [.,4H] = [dq | d gh] with the i = 0 rows ZERO, so that the products with h_{i-1}
+  //   can run on the forward's hs planes shifted by one row (the i = 0 rows pair with the encoder state separately)
+  bf16* dgi_p = nullptr; long long dgi_p_ld = 0;
+  bf16* d1_p = nullptr; long long d1_p_ld = 0;
   unsigned* counters;
   long long* dbg;
 };

@@ -296,6 +296,8 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   if (need_frame_grad && ns > 1) PVCR_TRY(prep_weight_T(p.enc_w_ih, V, H3, V, w.wih_encT, 0, 1, st));
 
   const bool persist_dec = dec_persist_eligible(B, N, H, ns, w.enc_a.Kp);
+  Planes dgi_p{}, d1_p{};
+  bool sweep_planes = false;
   if (persist_dec) {
     DecPersistBwd q{};
     q.L = L; q.B = B; q.N = N; q.H = H;
@@ -305,6 +307,13 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
     q.r = w.dr; q.z = w.dz; q.n = w.dn; q.ghn = w.dghn;
     q.dgi_all = w.dgi_all; q.d1_all = w.d1_all; q.dctx_all = w.dctx_all; q.ds_all = w.ds_all;
     q.dh_carry = w.dh_carry; q.xg = w.xg; q.counters = w.sync;
+    if (ns == 1) {          // the sweep emits the bf16 operand planes of the hoisted weight-gradient GEMMs itself
+      dgi_p = alloc_planes(a, BL, H3, 1); d1_p = alloc_planes(a, BL, H4, 1);
+      if (a.failed) { set_last_error("s2vtatt_bwd: workspace too small (decoder gradient planes)"); return PVCR_ERR_WORKSPACE; }
+      q.dgi_p = dgi_p.ptr; q.dgi_p_ld = dgi_p.ld; q.d1_p = d1_p.ptr; q.d1_p_ld = d1_p.ld;
+      cache.put(w.dgi_all, H3, BL, H3, dgi_p);
+      sweep_planes = true;
+    }
     PVCR_TRY(dec_persist_bwd(q, st));
   } else {
   PVCR_TRY(fill_zero(w.dh_carry, sizeof(float) * (size_t)B * H, st));
@@ -361,6 +370,25 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   if (fork) { PVCR_TRY(side_fork(st, &la, 0)); PVCR_TRY(side_fork(st, &lb, 1)); }          // after the sweep
   {
   CtaCap cap_(fork && side_mode() == 2 ? side_cap : 0);
+  if (sweep_planes) {
+    // dW = sum_{b,i} d[b,i]^T h_{i-1}[b]:  rows i >= 1 pair with the forward's hs planes shifted by one row (the sweep
+    // wrote the i = 0 rows of [dq | dgh] as zeros), rows i = 0 pair with the encoder's final state: no h_{i-1} copy
+    const OperandView dq1{d1_p.ptr + d1_p.ld, d1_p.ld, 0, BL - 1, 1}, dgh1{d1_p.ptr + d1_p.ld + H, d1_p.ld, 0, BL - 1, 1};
+    const OperandView hsm{w.hs_a.ptr, w.hs_a.ld, 0, BL - 1, 1};
+    if (BL > 1) {
+      PVCR_TRY(gemm_mn_store(dgh1, hsm, H3, H, BL - 1, g.dec_w_hh, H, 0, la));
+      PVCR_TRY(gemm_mn_store(dq1, hsm, H, H, BL - 1, g.att_wq, H, 0, la));
+    } else {
+      PVCR_TRY(fill_zero(g.dec_w_hh, sizeof(float) * (size_t)H3 * H, la));
+      PVCR_TRY(fill_zero(g.att_wq, sizeof(float) * (size_t)H * H, la));
+    }
+    Planes d0 = alloc_planes(a, B, H4, 1);                   // [dq | dgh] of step 0, rows b
+    if (a.failed) { set_last_error("s2vtatt_bwd: workspace too small (step-0 planes)"); return PVCR_ERR_WORKSPACE; }
+    PVCR_TRY(cast_split(w.d1_all, (long long)L * H4, B, H4, d0.ptr, d0.ld, d0.Kp, 1, 0, nullptr, NO_DROPOUT, la));
+    const OperandView e_last{w.enc_a.ptr + (long long)(N - 1) * w.enc_a.ld, (long long)N * w.enc_a.ld, 0, B, 1};
+    PVCR_TRY(gemm_mn_store(OperandView{d0.ptr + H, d0.ld, 0, B, 1}, e_last, H3, H, B, g.dec_w_hh, H, 1, la));
+    PVCR_TRY(gemm_mn_store(OperandView{d0.ptr, d0.ld, 0, B, 1}, e_last, H, H, B, g.att_wq, H, 1, la));
+  } else {
   // h_{i-1} rows in (b, i) order: i = 0 -> encoder final state, i >= 1 -> hs[b, i-1]
   PVCR_CUDA_CHECK(cudaMemcpy2DAsync(w.hprev_dec, sizeof(float) * (size_t)L * H, w.enc + (long long)(N - 1) * H,
                                     sizeof(float) * (size_t)N * H, sizeof(float) * H, B, cudaMemcpyDeviceToDevice, la));
@@ -368,8 +396,9 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
     PVCR_CUDA_CHECK(cudaMemcpy2DAsync(w.hprev_dec + H, sizeof(float) * (size_t)L * H, hs, sizeof(float) * (size_t)L * H,
                                       sizeof(float) * (size_t)(L - 1) * H, B, cudaMemcpyDeviceToDevice, la));
   PVCR_TRY(grad_w(a, w.d1_all + H, H4, BL, H3, w.hprev_dec, H, H, nullptr, nullptr, g.dec_w_hh, H, 0, ns, la));
-  PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, w.ctx_all, H, H, nullptr, nullptr, g.dec_w_ih, H + E, 0, ns, lb));
   PVCR_TRY(grad_w(a, w.d1_all, H4, BL, H, w.hprev_dec, H, H, nullptr, nullptr, g.att_wq, H, 0, ns, la));
+  }
+  PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, w.ctx_all, H, H, nullptr, nullptr, g.dec_w_ih, H + E, 0, ns, lb));
   PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, p.emb, E, E, s_in, nullptr, g.dec_w_ih + H, H + E, 0, ns, lb));
   if (ns == 1) PVCR_TRY(grad_x_fwdw(a, w.dgi_all, H3, BL, H3, w.we, E, w.demb_rows, E, 0, lb));
   else PVCR_TRY(grad_x(a, w.dgi_all, H3, BL, H3, w.weT, w.demb_rows, E, 0, lb));
@@ -416,19 +445,27 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
     eg.dgi_p = dgi_p.ptr; eg.dgi_p_ts = dgi_p.ld; eg.dgi_p_ld = (long long)N * dgi_p.ld;
     eg.dgh_p = dgh_p.ptr; eg.dgh_p_ts = dgh_p.ld; eg.dgh_p_ld = (long long)N * dgh_p.ld;
     cache.put(w.dgi_enc, H3, BN, H3, dgi_p);
-    cache.put(w.dgh_enc, H3, BN, H3, dgh_p);
   }
   PVCR_TRY(gru_seq_bwd(es, eg, st));
   // the two encoder weight gradients are independent: W_hh and the bias column sums on side lanes, W_ih here
   const bool fork2 = ns == 1 && side_site(3);
   cudaStream_t ln2 = st, ln3 = st;
   if (fork2) { PVCR_TRY(side_fork(st, &ln2, 2)); PVCR_TRY(side_fork(st, &ln3, 1)); }     // lane 2 is idle by now
+  if (enc_planes) {
+    // dW_hh = sum_{b,t} dgh[b,t]^T h_{t-1}[b]: the sweep wrote the t = 0 rows of the dgh planes as zeros (h_{-1} = 0), so
+    // the product runs on the forward's enc planes shifted by one row; no h_{t-1} copy
+    if (BN > 1)
+      PVCR_TRY(gemm_mn_store(OperandView{eg.dgh_p + eg.dgh_p_ts, eg.dgh_p_ts, 0, BN - 1, 1},
+                             OperandView{w.enc_a.ptr, w.enc_a.ld, 0, BN - 1, 1}, H3, H, BN - 1, g.enc_w_hh, H, 0, ln2));
+    else PVCR_TRY(fill_zero(g.enc_w_hh, sizeof(float) * (size_t)H3 * H, ln2));
+  } else {
   // h_{t-1} rows in (b, t) order: zero for t = 0
   PVCR_TRY(fill_zero(w.hprev_enc, sizeof(float) * (size_t)BN * H, ln2));
   if (N > 1)
     PVCR_CUDA_CHECK(cudaMemcpy2DAsync(w.hprev_enc + H, sizeof(float) * (size_t)N * H, w.enc, sizeof(float) * (size_t)N * H,
                                       sizeof(float) * (size_t)(N - 1) * H, B, cudaMemcpyDeviceToDevice, ln2));
   PVCR_TRY(grad_w(a, w.dgh_enc, H3, BN, H3, w.hprev_enc, H, H, nullptr, nullptr, g.enc_w_hh, H, 0, ns, ln2));
+  }
   PVCR_TRY(colsum(w.dgh_enc, H3, BN, H3, g.enc_b_hh, 0, ln2));
   PVCR_TRY(colsum(w.dgi_enc, H3, BN, H3, g.enc_b_ih, 0, ln3));
   if (ns == 1 && frame_scale) cache.put(vid, V, BN, V, w.x_a);      // x_a = vid * frame_scale, exactly this operand
