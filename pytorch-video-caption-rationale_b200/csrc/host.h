@@ -12,6 +12,7 @@ const char* last_error();
 int side_mode();                                        // 0 off, 1 join at the end of each call, 2 deferred join
 bool side_site(int bit);                                // fork site enabled (PVCR_SIDE_MASK tuning aid; false when off)
 int side_fork(cudaStream_t main, cudaStream_t* lane, int id = 0);   // lane `id` waits for main's current point (*lane == main when off)
+int side_join_lane(cudaStream_t main, int id);          // main waits for lane `id`'s current point only
 int side_join(cudaStream_t main);                       // main waits for every lane's current point
 int side_call_end(cudaStream_t main);                   // join unless mode 2
 enum SideNote { NOTE_ATT_BWD_WEIGHTS = 1, NOTE_VOCAB_WV = 2 };

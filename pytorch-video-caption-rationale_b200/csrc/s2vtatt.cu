@@ -177,43 +177,45 @@ int s2vtatt_fwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   carve(a, d, 0, w);
   if (a.failed) { set_last_error("s2vtatt_fwd: workspace too small (%zu < %zu)", ws_bytes, a.off); return PVCR_ERR_WORKSPACE; }
 
-  // Critical chain on the caller's stream: W_ih cast -> frame staging -> input-projection GEMM -> encoder sweep.
-  // Everything else that only depends on the inputs runs on side lanes next to it and is joined before the sweep:
-  //   lane 0: the other weight casts;
-  //   lane 1: the hoisted embedding half of the decoder input projection (+ b_ih);
-  //   lane 2: the transposed weight planes of the backward decoder sweep (the backward call finds a note and skips them).
+  // Critical chain: {W_ih cast | frame staging} -> input-projection GEMM -> {W_hh cast} -> encoder sweep -> proj_key.
+  // Everything else that only depends on the inputs runs on side lanes next to it:
+  //   lane 0: frame staging (joined before the GEMM);
+  //   lane 1: the recurrent / attention weight casts (joined before the sweep);
+  //   lane 2: the hoisted embedding half of the decoder input projection (+ b_ih), then the transposed weight planes of
+  //           the backward sweeps (the backward call finds a note and skips them); joined before the decoder sweep.
   cudaStream_t l0 = st, l1 = st, l2 = st;
   const bool fork = side_site(0);
   if (fork) { PVCR_TRY(side_fork(st, &l0, 0)); PVCR_TRY(side_fork(st, &l1, 1)); PVCR_TRY(side_fork(st, &l2, 2)); }
+  PVCR_TRY(stage(vid, V, BN, V, w.x_a, 0, frame_scale, NO_DROPOUT, l0));
   PVCR_TRY(prep_weight(p.enc_w_ih, V, H3, V, w.wih_enc, st));
-  PVCR_TRY(stage(vid, V, BN, V, w.x_a, 0, frame_scale, NO_DROPOUT, st));
+  if (fork) PVCR_TRY(side_join_lane(st, 0));         // waits for the frame staging only (nothing else is on lane 0 yet)
   PVCR_TRY(gemm_planes(w.x_a.view(), w.wih_enc.view(), BN, H3, (int)w.x_a.ld, w.gi_enc, H3, p.enc_b_ih, 0, st));
+  PVCR_TRY(prep_weight(p.enc_w_hh, H, H3, H, w.whh_enc, l1));
+  if (fork) PVCR_TRY(side_join_lane(st, 1));         // the sweep waits for its W_hh planes only
 
-  PVCR_TRY(prep_weight(p.enc_w_hh, H, H3, H, w.whh_enc, l0));
   PVCR_TRY(prep_weight(p.att_wk, H, H, H, w.wk, l0));
   PVCR_TRY(prep_weight(p.att_wq, H, H, H, w.wcat, l0, 0));
-  PVCR_TRY(prep_weight(p.dec_w_hh, H, H3, H, w.wcat, l0, H));
-  PVCR_TRY(prep_weight(p.dec_w_ih, H + E, H3, H, w.wc, l0));
+  PVCR_TRY(prep_weight(p.dec_w_hh, H, H3, H, w.wcat, l1, H));
+  PVCR_TRY(prep_weight(p.dec_w_ih, H + E, H3, H, w.wc, l1));
   if (w.enc_a.Kp != H) {       // contraction padding of the planes written by the gate kernels must read as zero
-    PVCR_TRY(fill_zero(w.enc_a.ptr, sizeof(bf16) * (size_t)BN * w.enc_a.ld, l0));
-    PVCR_TRY(fill_zero(w.hs_a.ptr, sizeof(bf16) * (size_t)BL * w.hs_a.ld, l0));
-    PVCR_TRY(fill_zero(w.ctx_a.ptr, sizeof(bf16) * (size_t)B * w.ctx_a.ld, l0));
+    PVCR_TRY(fill_zero(w.enc_a.ptr, sizeof(bf16) * (size_t)BN * w.enc_a.ld, st));
+    PVCR_TRY(fill_zero(w.hs_a.ptr, sizeof(bf16) * (size_t)BL * w.hs_a.ld, l1));
+    PVCR_TRY(fill_zero(w.ctx_a.ptr, sizeof(bf16) * (size_t)B * w.ctx_a.ld, l1));
   }
 
-  PVCR_TRY(prep_weight(p.dec_w_ih + H, H + E, H3, E, w.we, l1));
-  PVCR_TRY(gather_split(p.emb, E, s_in, BL, w.emb_a.ptr, w.emb_a.ld, w.emb_a.Kp, d.nsplit, NO_DROPOUT, l1));
-  PVCR_TRY(gemm_planes(w.emb_a.view(), w.we.view(), BL, H3, (int)w.emb_a.ld, w.ep, H3, p.dec_b_ih, 0, l1));
-
+  PVCR_TRY(prep_weight(p.dec_w_ih + H, H + E, H3, E, w.we, l2));
+  PVCR_TRY(gather_split(p.emb, E, s_in, BL, w.emb_a.ptr, w.emb_a.ld, w.emb_a.Kp, d.nsplit, NO_DROPOUT, l2));
+  PVCR_TRY(gemm_planes(w.emb_a.view(), w.we.view(), BL, H3, (int)w.emb_a.ld, w.ep, H3, p.dec_b_ih, 0, l2));
   side_note_take(ws, NOTE_ATT_BWD_WEIGHTS);          // a stale note of an earlier forward on this workspace
   if (fork) {
     PVCR_TRY(att_bwd_weights(d, p, w, l2));
     side_note_put(ws, NOTE_ATT_BWD_WEIGHTS);
   }
-  PVCR_TRY(side_join(st));
   // encoder: N recurrent steps on gi = (vid * frame_scale) W_ih^T + b_ih
   PVCR_TRY(gru_seq_fwd(encoder_seq(d, p, w), st));
 
   // proj_key = enc W_k^T
+  PVCR_TRY(side_join(st));
   PVCR_TRY(gemm_planes(w.enc_a.view(), w.wk.view(), BN, H, (int)w.enc_a.ld, w.pk, H, nullptr, 0, st));
 
   // decoder steps: one persistent cooperative kernel when the shape allows, else per-step launches
@@ -449,8 +451,8 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   PVCR_TRY(gru_seq_bwd(es, eg, st));
   // the two encoder weight gradients are independent: W_hh and the bias column sums on side lanes, W_ih here
   const bool fork2 = ns == 1 && side_site(3);
-  cudaStream_t ln2 = st, ln3 = st;
-  if (fork2) { PVCR_TRY(side_fork(st, &ln2, 2)); PVCR_TRY(side_fork(st, &ln3, 1)); }     // lane 2 is idle by now
+  cudaStream_t ln2 = st, ln3 = st, ln4 = st;
+  if (fork2) { PVCR_TRY(side_fork(st, &ln2, 2)); PVCR_TRY(side_fork(st, &ln3, 1)); PVCR_TRY(side_fork(st, &ln4, 0)); }
   if (enc_planes) {
     // dW_hh = sum_{b,t} dgh[b,t]^T h_{t-1}[b]: the sweep wrote the t = 0 rows of the dgh planes as zeros (h_{-1} = 0), so
     // the product runs on the forward's enc planes shifted by one row; no h_{t-1} copy
@@ -466,7 +468,7 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
                                       sizeof(float) * (size_t)(N - 1) * H, B, cudaMemcpyDeviceToDevice, ln2));
   PVCR_TRY(grad_w(a, w.dgh_enc, H3, BN, H3, w.hprev_enc, H, H, nullptr, nullptr, g.enc_w_hh, H, 0, ns, ln2));
   }
-  PVCR_TRY(colsum(w.dgh_enc, H3, BN, H3, g.enc_b_hh, 0, ln2));
+  PVCR_TRY(colsum(w.dgh_enc, H3, BN, H3, g.enc_b_hh, 0, ln4));
   PVCR_TRY(colsum(w.dgi_enc, H3, BN, H3, g.enc_b_ih, 0, ln3));
   if (ns == 1 && frame_scale) cache.put(vid, V, BN, V, w.x_a);      // x_a = vid * frame_scale, exactly this operand
   PVCR_TRY(grad_w(a, w.dgi_enc, H3, BN, H3, vid, V, V, nullptr, frame_scale, g.enc_w_ih, V, 0, ns, st));

@@ -71,6 +71,18 @@ int side_fork(cudaStream_t main, cudaStream_t* out, int id) {
   return PVCR_OK;
 }
 
+// `main` waits for everything enqueued on lane `id` so far.
+int side_join_lane(cudaStream_t main, int id) {
+  std::lock_guard<std::mutex> g(g_mu);
+  Lane& l = g_lane[(id < 0 ? 0 : id) % g_nlanes];
+  if (!l.s || !l.pending) return PVCR_OK;
+  cudaEvent_t e = next_event();
+  PVCR_CUDA_CHECK(cudaEventRecord(e, l.s));
+  PVCR_CUDA_CHECK(cudaStreamWaitEvent(main, e, 0));
+  // the lane stays "pending": later work may be enqueued on it and a full join is still due
+  return PVCR_OK;
+}
+
 // `main` waits for everything enqueued on every lane so far.
 int side_join(cudaStream_t main) {
   std::lock_guard<std::mutex> g(g_mu);
