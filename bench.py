@@ -131,6 +131,21 @@ def run_reference(args):
         "gpu_launches": 0}), flush=True)
 
 
+def _finish_ranks(world):
+    """End of a multi-rank run.  The step graph holds captured NCCL kernels; tearing the communicator down under it
+    (destroy_process_group / interpreter exit) was observed to hang, so every rank synchronises and leaves directly."""
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -257,8 +272,7 @@ def run_ours(args):
     L_.pvcr_prof_enable(0)
     L_.pvcr_side_mode(side_prev)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish_ranks(world)
         return
 
     peaks = {}
@@ -331,8 +345,7 @@ def run_ours(args):
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _finish_ranks(world)
 
 
 def main():

@@ -6,9 +6,11 @@ The step is the module's tape-free ``train_step_grads`` (no autograd state insid
 into static device buffers (directly from pinned host memory when given CPU tensors); the gradients appear in
 ``param.grad`` (static buffers rewritten by every replay), ready for the all-reduce / optimizer.
 """
+import os
+
 import torch
 
-from ._lib import lib, ptr
+from ._lib import check, lib, ptr, stream_ptr
 
 
 class GraphedTrainStep:
@@ -31,7 +33,46 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         self.graphs = [self.graph]          # one graph per stage of model.train_step_stages (a single one otherwise)
-        if reducer is not None and hasattr(model, "train_step_stages"):
+        self.comm_in_graph = False
+        staged = reducer is not None and hasattr(model, "train_step_stages")
+        if staged and reducer.world > 1 and os.environ.get("PVCR_DP_STAGED") is None:
+            # One graph for everything, NCCL included: every bucket's all-reduce is launched from an auxiliary stream
+            # that waits for the stage's gradients (capture stream + the library's side lanes) without holding the
+            # capture stream back, so the side lanes keep running across the stage boundaries (deferred joins) and
+            # the collectives overlap the remaining backward.
+            self.comm_in_graph = True
+            aux = torch.cuda.Stream()
+
+            def staged_step():
+                main = torch.cuda.current_stream()
+                gen = model.train_step_stages(*self.static_in, deferred_join=True)
+                i = 0
+                while True:
+                    try:
+                        next(gen)
+                    except StopIteration as done:
+                        res = done.value
+                        break
+                    aux.wait_stream(main)
+                    with torch.cuda.stream(aux):
+                        check(lib().pvcr_side_join(stream_ptr()), "pvcr_side_join")     # aux waits for the lanes
+                        reducer.begin(i)
+                    i += 1
+                main.wait_stream(aux)
+                for j in range(i, len(reducer.buckets)):
+                    reducer.begin(j)
+                reducer.finish()
+                return res
+
+            with torch.no_grad():
+                with torch.cuda.stream(side):
+                    staged_step()                  # eager once: communicator / lane set-up outside the capture
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                with torch.cuda.graph(self.graph):
+                    self.seed_step.add_(1)
+                    out = staged_step()
+        elif staged:
             with torch.no_grad():
                 gen = model.train_step_stages(*self.static_in)
                 out = None
@@ -73,7 +114,9 @@ class GraphedTrainStep:
         return self.static_out
 
     def _replay(self):
-        if len(self.graphs) > 1:
+        if self.comm_in_graph:
+            self.graph.replay()
+        elif len(self.graphs) > 1:
             # stage i's gradients (bucket i) are final when graph i has run: their all-reduce overlaps graph i+1
             for i, g in enumerate(self.graphs):
                 g.replay()
