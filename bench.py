@@ -163,8 +163,11 @@ def run_ours(args):
     if world > 1:
         # the persistent cooperative kernels occupy 128 of the 148 SMs: keep NCCL within the remaining 20 so that the
         # overlapped gradient all-reduce can be co-resident instead of serialising in front of them
-        os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_ctas))
-        dist.init_process_group("nccl", device_id=dev)
+        # (per-communicator ncclConfig, not the NCCL_MAX_CTAS environment variable, which would also bind the
+        # wider communicator used for the exposed tail of the gradient all-reduce)
+        opts0 = dist.ProcessGroupNCCL.Options()
+        opts0.config.max_ctas = args.nccl_ctas
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts0)
     d = DIMS
     B, N, V, H, E, L, Vc = (d[k] for k in ("B", "N", "V", "H", "E", "L", "Vc"))
 
@@ -182,7 +185,12 @@ def run_ours(args):
     with torch.no_grad():
         model.decoder.embedding.weight.normal_(0.0, 0.4)
     model = model.to(dev).train()
-    reducer = GradAllReducer(model, flat=True, early=model.early_grad_params())   # grads land in the buckets
+    tail_group = None
+    if world > 1 and args.nccl_tail_ctas != args.nccl_ctas:
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.config.max_ctas = args.nccl_tail_ctas       # communicator for the all-reduces nothing overlaps any more
+        tail_group = dist.new_group(backend="nccl", pg_options=opts)
+    reducer = GradAllReducer(model, flat=True, early=model.early_grad_params(), tail_group=tail_group)   # grads land in the buckets
 
     gen = torch.Generator().manual_seed(1000 + rank)
     vid_h = torch.randn(B, N, V, generator=gen)
@@ -358,6 +366,7 @@ def main():
     ap.add_argument("--dropout", type=float, default=0.2, help="reference default dropout_p (args.py:26)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl-ctas", type=int, default=16)
+    ap.add_argument("--nccl-tail-ctas", type=int, default=64)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -56,11 +56,13 @@ class GraphedTrainStep:
                     aux.wait_stream(main)
                     with torch.cuda.stream(aux):
                         check(lib().pvcr_side_join(stream_ptr()), "pvcr_side_join")     # aux waits for the lanes
-                        reducer.begin(i)
+                        # only the first bucket (vocabulary gradients) really overlaps the backward: the lanes that
+                        # produce the later ones finish with the last sweep
+                        reducer.begin(i, tail=i > 0)
                     i += 1
                 main.wait_stream(aux)
                 for j in range(i, len(reducer.buckets)):
-                    reducer.begin(j)
+                    reducer.begin(j, tail=True)
                 reducer.finish()
                 return res
 

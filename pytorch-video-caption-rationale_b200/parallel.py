@@ -24,12 +24,16 @@ class GradAllReducer:
     produces gradients: vocabulary projection and embedding first), so ``reduce()`` can be issued per bucket on a
     side stream while later buckets are still being computed."""
 
-    def __init__(self, module, bucket_mb=64, group=None, flat=False, early=None):
+    def __init__(self, module, bucket_mb=64, group=None, flat=False, early=None, tail_group=None):
         """flat=True pre-allocates one flat fp32 buffer per bucket and installs views of it as ``param.grad``; the
         tape-free train steps write gradients straight into those views, so ``reduce()`` all-reduces in place
         without gather / scatter copies."""
         self.params = [p for p in module.parameters() if p.requires_grad]
         self.group = group
+        # tail_group: optional second process group (same ranks, a communicator allowed more CTAs) for the buckets whose
+        # all-reduce cannot overlap the backward any more: the overlapped ones must stay within the SMs the persistent
+        # sweeps leave free, the exposed ones should use the whole idle machine
+        self.tail_group = tail_group
         # early: list of parameter lists whose gradients become final first (one bucket each, in that order)
         early = list(early or [])
         if early and not isinstance(early[0], (list, tuple)):
@@ -69,12 +73,13 @@ class GradAllReducer:
         return self._views is not None and all(p.grad is not None and p.grad.data_ptr() == v.data_ptr()
                                                for p, v in zip(self.buckets[i], self._views[i]))
 
-    def begin(self, i):
+    def begin(self, i, tail=False):
         """Start the all-reduce of bucket i (asynchronous: later kernels on the current stream overlap with it)."""
         if self.world == 1:
             return
         assert self._in_place(i), "begin()/finish() need flat=True buckets written in place"
-        self._pending.append((i, dist.all_reduce(self._flat[i], op=dist.ReduceOp.SUM, group=self.group, async_op=True)))
+        group = self.tail_group if (tail and self.tail_group is not None) else self.group
+        self._pending.append((i, dist.all_reduce(self._flat[i], op=dist.ReduceOp.SUM, group=group, async_op=True)))
 
     def finish(self):
         for i, h in self._pending:
