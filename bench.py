@@ -39,7 +39,7 @@ def fwd_bwd_gflop(d):
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled through NVML every 100 ms during the timed region (a background
+    """SM clock and throttle reasons sampled through NVML every 10 ms during the timed region (a background
     thread in this process: `nvidia-smi -lms` in a child process perturbed the launch path measurably)."""
 
     def __init__(self, index):
@@ -75,7 +75,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:             # noqa: BLE001
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.01)
 
     def stop(self):
         if self.thread is None:
@@ -305,7 +305,8 @@ def run_ours(args):
         "gru_persistent_bwd": N * 2 * rec_step + 3 * H * H * 2,
     }
     # DRAM bytes per launch measured with `ncu --set full` (profiles/): dram__bytes_read.sum + dram__bytes_write.sum
-    ncu_traffic = {"decoder_persistent_bwd": 99.6e6, "decoder_persistent_fwd": 59.8e6}      # profiles/r01f_ncu_full.md
+    ncu_traffic = {"decoder_persistent_bwd": 123.8e6, "decoder_persistent_fwd": 58.3e6, "gru_persistent_fwd": 41.0e6,
+                   "gru_persistent_bwd": 113.3e6}      # profiles/r01i_ncu_full.md
     kernels = {}
     for name, v in classes.items():
         ms = v["ms_per_step"]
