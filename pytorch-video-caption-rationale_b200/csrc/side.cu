@@ -142,6 +142,13 @@ int pvcr_side_mode(int mode) {
   return prev;
 }
 
-int pvcr_side_join(void* stream) { return side_join(static_cast<cudaStream_t>(stream)); }
+int pvcr_side_join(void* stream) {
+  {   // the explicit join ends a step: notes about work staged for "the coming call" of that step do not outlive it
+    std::lock_guard<std::mutex> g(g_mu);
+    for (size_t i = 0; i < g_notes.size();)
+      if (g_notes[i].tag == NOTE_VOCAB_WV) g_notes.erase(g_notes.begin() + i); else ++i;
+  }
+  return side_join(static_cast<cudaStream_t>(stream));
+}
 
 }  // extern "C"

@@ -187,3 +187,46 @@ def test_bf16_mode_matches_bf16_operand_oracle():
     assert a_err < 1e-4
     for k, e in errs.items():
         assert e < 2e-3, (k, e)          # measured max 1.3e-3: rounding flips amplified through 70 recurrent steps
+
+
+def test_side_lane_modes_agree():
+    """The library's side lanes only reorder independent work: lanes off (mode 0), joined per call (mode 1, the autograd
+    path) and joined once per step (mode 2, the tape-free step) give the same loss and gradients at the persistent-kernel
+    shape, eager and as a CUDA graph (atomics in the embedding scatter / split-K products reorder sums: 1e-5)."""
+    from oracle import workloads as W
+    from pvcr_b200 import _lib
+    from pvcr_b200.graphs import GraphedTrainStep
+    from pvcr_b200.model import S2VTAttModel
+    B, N, V, H, E, L, Vc = 40, 40, 512, 512, 300, 30, 1200
+    p = W.s2vtatt_params(V, H, E, Vc, 31)
+    vid, s, s_len = W.make_batch(B, N, V, L, Vc, 32)
+    vid, s, s_len = torch.from_numpy(vid).cuda(), torch.from_numpy(s).cuda(), torch.from_numpy(s_len).cuda()
+    Lb = _lib.lib()
+    prev = Lb.pvcr_side_mode(-1)
+    results = {}
+    try:
+        for mode in (0, 1, 2):
+            Lb.pvcr_side_mode(mode)
+            m = to_cuda(S2VTAttModel(FixtureGlove(Vc, E), 0.0, H, V, L, precision="bf16"), p).train()
+            if mode == 1:
+                loss, _, _ = m.forward_loss(vid, s, s_len)
+                loss.backward()
+            else:
+                loss, _, _ = m.train_step_grads(vid, s, s_len)      # mode 2 inside when the lanes are on
+            torch.cuda.synchronize()
+            results[mode] = (loss.item(), grads_of(m))
+        Lb.pvcr_side_mode(1)
+        m = to_cuda(S2VTAttModel(FixtureGlove(Vc, E), 0.0, H, V, L, precision="bf16"), p).train()
+        step = GraphedTrainStep(m, (vid, s, s_len))
+        for _ in range(3):
+            loss = step(vid, s, s_len)[0]
+        torch.cuda.synchronize()
+        results["graph"] = (loss.item(), grads_of(m))
+    finally:
+        Lb.pvcr_side_mode(prev)
+    l0, g0 = results[0]
+    for k in (1, 2, "graph"):
+        lk, gk = results[k]
+        assert abs(lk - l0) < 1e-6 * abs(l0), (k, lk, l0)
+        for name in g0:
+            assert relerr(gk[name], g0[name]) < 1e-5, (k, name, relerr(gk[name], g0[name]))
