@@ -286,6 +286,160 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   }
 }
 
+
+// ---- 2-CTA cluster variant: the B tile is shared by TMA multicast ------------------------------------------------
+// With K = 512 (vocabulary projection) a 128 x 256 tile needs 384 KB of operands for 4096 tensor-pipe cycles: 148 CTAs
+// ask L2 for ~10.5 TB/s, at the chip's L2 -> SM limit, and the tensor pipe idles half of the time.  Here two CTAs of a
+// cluster work on the two 128-row tiles (m0, m0 + 128) of the same 256 columns: each loads its own A tile and HALF of
+// the B tile, multicast to both (cp.async.bulk.tensor ... .multicast::cluster signals the full barrier at the same
+// offset in both CTAs), so a tile costs 256 KB of L2 reads instead of 384 KB.  A stage may be refilled only when BOTH
+// CTAs' MMAs have read it: the empty barriers count two arrivals and every tcgen05.commit on them is multicast.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+
+template <int BN, int STAGES, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_PERSIST_THREADS, 1)
+gemm_tn_mc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh, GemmCoords gc,
+                   int pairs_m, int tiles_n, int num_items, Epi epi) {
+  using SM = GemmSmem<BN, STAGES>;
+  static_assert(2 * BN <= 512, "two accumulators must fit the 512 TMEM columns");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint8_t* epi_smem = smem + SM::BAR_OFFSET + 256;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int total_kb = gc.K / GEMM_BK;
+  constexpr int HALF_ROWS = BN / 2;                  // rows of the B tile this CTA loads (for both)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmBh);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 2);                   // this CTA's and the peer's MMA have read the stage
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                // the peer's barriers exist before anything is multicast to them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int w = cluster_id; w < num_items; w += num_clusters) {
+        const int m0 = (2 * (w % pairs_m) + rank) * GEMM_BM, n0 = (w / pairs_m) * BN;
+        for (int kb = 0; kb < total_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], SM::STAGE_BYTES);
+          uint8_t* sa = smem + s * SM::STAGE_BYTES;
+          tma_load_3d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m0, gc.a_z0);
+          tma_load_3d_mc(sa + SM::A_BYTES + rank * HALF_ROWS * 128, &tmBh, &full_bar[s], kb * GEMM_BK,
+                         n0 + rank * HALF_ROWS, gc.b_z0, (uint16_t)3);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+      int it = 0, ti = 0;
+      for (int w = cluster_id; w < num_items; w += num_clusters, ++ti) {
+        const int acc = ti & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((ti >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < total_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
+          const uint64_t da = umma_desc_k128(sa), db = umma_desc_k128(sa + SM::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k)
+            umma_bf16(tmem_d, da + (uint64_t)k * 2, db + (uint64_t)k * 2, idesc, (kb | k) != 0);
+          umma_commit_mc(&empty_bar[s], (uint16_t)3);
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    constexpr int HALF = BN / 2;
+    int ti = 0;
+    for (int w = cluster_id; w < num_items; w += num_clusters, ++ti) {
+      const int nt = w / pairs_m;
+      const int m0 = (2 * (w % pairs_m) + rank) * GEMM_BM, n0 = nt * BN;
+      const int acc = ti & 1;
+      const int row = m0 + q * 32 + lane;
+      Epi e = epi;
+      if constexpr (Epi::SMEM_BYTES > 0) e.attach(epi_smem + (warp - 2) * (Epi::SMEM_BYTES / 8));
+      e.begin(row, 0);
+      mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);
+      tc_fence_after();
+      float v[32];
+#pragma unroll 1
+      for (int c = half * HALF; c < (half + 1) * HALF; c += 32) {
+        if (n0 + c >= gc.N) break;
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
+        e.chunk(row, n0 + c, 0, v);
+      }
+      e.end(row, nt * 2 + half, 0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                // no CTA leaves while the peer may still signal its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
 // Plain store epilogue: C = acc (+ bias[n]) (+ C).  fp32 output, arbitrary ldc.
 struct EpiStore {
   static constexpr int SMEM_BYTES = 0;      // shared-memory staging the persistent kernel reserves for the epilogue warps
@@ -412,6 +566,40 @@ int launch_gemm_tn_persistent(const OperandView& a, const OperandView& b, const 
   {
     LaunchScope ls_(KC_GEMM, stream, 2.0 * gc.M * gc.N * (double)gc.K * grid_z);
     kern<<<grid, GEMM_PERSIST_THREADS, SM::TOTAL + 64 + 256 + Epi::SMEM_BYTES, stream>>>(ta, tb, gc, tiles_m, tiles_n, (int)num_tiles, epi);
+  }
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  return PVCR_OK;
+}
+
+// K-major x K-major product on the 2-CTA multicast kernel (single slab, no split-K).
+template <int BN, int STAGES, class Epi>
+int launch_gemm_tn_mc2(const OperandView& a, const OperandView& b, const GemmCoords& gc, const Epi& epi,
+                       cudaStream_t stream) {
+  using SM = GemmSmem<BN, STAGES>;
+  PVCR_REQUIRE(gc.K > 0 && gc.K % GEMM_BK == 0, "gemm: K=%d must be a positive multiple of %d", gc.K, GEMM_BK);
+  PVCR_REQUIRE(gc.M > 0 && gc.N > 0 && gc.k_splits <= 1, "gemm (multicast): empty problem or split-K");
+  CUtensorMap ta, tb;
+  PVCR_TRY(make_tensor_map(&ta, a, gc.K, GEMM_BM));
+  PVCR_TRY(make_tensor_map(&tb, b, gc.K, BN / 2));
+  auto kern = gemm_tn_mc2_kernel<BN, STAGES, Epi>;
+  static bool attr_set = false;
+  static int sms = 0;
+  constexpr int SMEM = SM::TOTAL + 64 + 256 + Epi::SMEM_BYTES;
+  if (!attr_set) {
+    PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    int dev = 0;
+    PVCR_CUDA_CHECK(cudaGetDevice(&dev));
+    PVCR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    attr_set = true;
+  }
+  const int pairs_m = cdiv(cdiv(gc.M, GEMM_BM), 2), tiles_n = cdiv(gc.N, BN);
+  const long long num_items = (long long)pairs_m * tiles_n;
+  int clusters = sms / 2;
+  if (gemm_cta_cap() > 1 && clusters > gemm_cta_cap() / 2) clusters = gemm_cta_cap() / 2;
+  if (num_items < clusters) clusters = (int)num_items;
+  {
+    LaunchScope ls_(KC_GEMM, stream, 2.0 * gc.M * gc.N * (double)gc.K);
+    kern<<<2 * clusters, GEMM_PERSIST_THREADS, SMEM, stream>>>(ta, tb, gc, pairs_m, tiles_n, (int)num_items, epi);
   }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;

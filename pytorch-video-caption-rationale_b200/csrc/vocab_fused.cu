@@ -6,6 +6,8 @@
 //             dW = dlogits^T hs), so no fp32 logits / dlogits tensor and no staging pass over them exists.
 // Reference semantics: Dropout + Linear (model/S2VTAttModel.py:145, model/S2VTModel.py:130), calc_masked_loss,
 // calc_masked_accuracy, torch.argmax (train_utils.py:37-71, train.py:38).
+#include <cstdlib>
+
 #include "../../include/pvcr_b200.h"
 #include "host.h"
 
@@ -213,6 +215,15 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* in, long l
   }
 }
 
+// PVCR_CE_MC=1: 2-CTA clusters with the W_v tile multicast to both CTAs (gemm_tn_mc2_kernel).  Parity-green, but
+// measured equal to the 1-CTA kernel (fwd 101 us, step 2.332 vs 2.333 ms): the K = 512 product is limited by what one
+// SM can take in (48 KB of operands per 512 tensor-pipe cycles = 96 B/clk), which multicast does not change - only a
+// cta_group::2 tile (each SM holds half of B) would.  Kept as the stepping stone to that kernel; off by default.
+static bool ce_multicast() {
+  static const bool on = getenv("PVCR_CE_MC") != nullptr;
+  return on;
+}
+
 struct FusedWs {
   Planes hs_a, wv;
   float *pmax, *psum, *tgt, *nll, *roww;
@@ -277,7 +288,8 @@ int vocab_fused_fwd(const float* hs, const float* wv, const float* bv, const lon
   epi.bias = bv; epi.pmax = w.pmax; epi.psum = w.psum; epi.pidx = w.pidx;
   epi.M = M; epi.N = Vc; epi.nparts = w.ntiles;
   GemmCoords gc{M, Vc, (int)w.hs_a.ld, 0, 0, 0, 0};
-  PVCR_TRY((launch_gemm_tn_persistent<CE_BN, 4, EpiCeFwd>(w.hs_a.view(), w.wv.view(), gc, 1, epi, st)));
+  if (ce_multicast()) PVCR_TRY((launch_gemm_tn_mc2<CE_BN, 4, EpiCeFwd>(w.hs_a.view(), w.wv.view(), gc, epi, st)));
+  else PVCR_TRY((launch_gemm_tn_persistent<CE_BN, 4, EpiCeFwd>(w.hs_a.view(), w.wv.view(), gc, 1, epi, st)));
   {
     LaunchScope ls_(KC_LOSS, st);
     ce_finalize_rows_kernel<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(w.pmax, w.psum, w.pidx, w.tgt, M, w.ntiles, lse,
@@ -308,7 +320,8 @@ int vocab_fused_bwd(const float* hs, const float* wv, const float* bv, const lon
   if (w.ldD > Vc)      // chunks lying entirely past Vc are skipped by the GEMM epilogue: their K-padding must read 0
     PVCR_CUDA_CHECK(cudaMemset2DAsync(w.D + Vc, sizeof(bf16) * w.ldD, 0, sizeof(bf16) * (w.ldD - Vc), M, st));
   GemmCoords gc{M, Vc, (int)w.hs_a.ld, 0, 0, 0, 0};
-  PVCR_TRY((launch_gemm_tn_persistent<CE_BN, 4, EpiCeBwd>(w.hs_a.view(), w.wv.view(), gc, 1, epi, st)));
+  if (ce_multicast()) PVCR_TRY((launch_gemm_tn_mc2<CE_BN, 4, EpiCeBwd>(w.hs_a.view(), w.wv.view(), gc, epi, st)));
+  else PVCR_TRY((launch_gemm_tn_persistent<CE_BN, 4, EpiCeBwd>(w.hs_a.view(), w.wv.view(), gc, 1, epi, st)));
   // d W = dlogits^T Dropout(hs) and d b = column sums of dlogits do not feed the rest of the backward: they run on
   // the side lane next to the d hs product (60 output tiles) and whatever the caller enqueues next.
   // Both operands as they are (row-major bf16, MN-major tcgen05 operands); hs_a are the planes staged (with the
