@@ -142,8 +142,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // A_MN / B_MN: that operand is MN-major (a [k][mn] row-major matrix, i.e. it enters the product transposed),
 // loaded as 64 x 64 TMA boxes.  A_MN && B_MN: C = A^T B (weight gradients); !A_MN && B_MN: C = A B (data gradients
 // dX = dY W with the forward weight planes, no transposed weight copies).
-template <int BN, int STAGES, class Epi, bool A_MN = false, bool B_MN = false>
-__global__ void __launch_bounds__(GEMM_PERSIST_THREADS, 1)
+// EW epilogue warps (8 or 16: EW / 4 per TMEM lane quadrant, each draining BN / (EW / 4) columns): epilogues that do real
+// arithmetic per element (fused cross entropy) are issue-latency bound with two warps per SM sub-partition.
+template <int BN, int STAGES, class Epi, bool A_MN = false, bool B_MN = false, int EW = 8>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                           GemmCoords gc, int tiles_m, int tiles_n, int num_tiles, Epi epi) {
   using SM = GemmSmem<BN, STAGES>;
@@ -155,7 +157,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  uint8_t* epi_smem = smem + SM::BAR_OFFSET + 256;   // Epi::SMEM_BYTES of staging, split evenly over the 8 epilogue warps
+  uint8_t* epi_smem = smem + SM::BAR_OFFSET + 256;   // Epi::SMEM_PER_WARP bytes of staging per epilogue warp
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -173,7 +175,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 8);              // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[a], EW);             // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -252,7 +254,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     // warp w drains TMEM lanes 32*(w%4).. of the column half (w-2)/4: two warps per SM sub-partition hide each
     // other's dependency stalls in the epilogue arithmetic
     const int q = warp & 3, half = (warp - 2) >> 2;
-    constexpr int HALF = BN / 2;
+    constexpr int PARTS = EW / 4, HALF = BN / PARTS;
     int ti = 0;
     for (int w = blockIdx.x; w < num_tiles; w += gridDim.x, ++ti) {
       const int t = w / splits;
@@ -261,7 +263,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       const int acc = ti & 1;
       const int row = m0 + q * 32 + lane;
       Epi e = epi;
-      if constexpr (Epi::SMEM_BYTES > 0) e.attach(epi_smem + (warp - 2) * (Epi::SMEM_BYTES / 8));
+      if constexpr (Epi::SMEM_PER_WARP > 0) e.attach(epi_smem + (warp - 2) * Epi::SMEM_PER_WARP);
       e.begin(row, splits > 1 ? w - t * splits : z);
       mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);
       tc_fence_after();
@@ -272,7 +274,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
         e.chunk(row, n0 + c, z, v);
       }
-      e.end(row, (r / tiles_m) * 2 + half, z);      // part index: (N tile, column half)
+      e.end(row, (r / tiles_m) * PARTS + half, z);  // part index: (N tile, column part)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -414,7 +416,7 @@ gemm_tn_mc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int acc = ti & 1;
       const int row = m0 + q * 32 + lane;
       Epi e = epi;
-      if constexpr (Epi::SMEM_BYTES > 0) e.attach(epi_smem + (warp - 2) * (Epi::SMEM_BYTES / 8));
+      if constexpr (Epi::SMEM_PER_WARP > 0) e.attach(epi_smem + (warp - 2) * Epi::SMEM_PER_WARP);
       e.begin(row, 0);
       mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);
       tc_fence_after();
@@ -440,9 +442,200 @@ gemm_tn_mc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
+// ---- CTA-pair variant (tcgen05 cta_group::2): one 256 x BN UMMA tile per pair ---------------------------------------
+// Each CTA of the pair stages its own 128 rows of A and its own BN/2 rows of B (32 KB per k-block instead of 48 KB),
+// the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) which reads both CTAs' shared memory, and each CTA ends up
+// with the 128 x BN accumulator of its rows in its own TMEM.  One SM then takes in 64 B per tensor-pipe cycle at
+// K-block granularity instead of 96 B: the K = 512 vocabulary GEMMs were limited by exactly that.
+//   full[s]      (leader)   2 producer arrivals (.expect_tx, the peer's is remote) + both CTAs' TMA bytes
+//   empty[s]     (each CTA) the leader's tcgen05.commit, multicast to both
+//   tmem_full[a] (each CTA) the leader's tcgen05.commit, multicast to both
+//   tmem_empty[a](leader)   16 arrivals: the 8 epilogue warps of both CTAs (the peer's are remote)
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1,
+                                                int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+
+template <int BN, int STAGES>
+struct Gemm2SmSmem {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;          // this CTA's 128 rows of A
+  static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;         // this CTA's BN/2 rows of B
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;          // barriers / slot / epilogue offset + alignment slack
+};
+
+template <int BN, int STAGES, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_PERSIST_THREADS, 1)
+gemm_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh, GemmCoords gc,
+                   int pairs_m, int tiles_n, int num_items, Epi epi) {
+  using SM = Gemm2SmSmem<BN, STAGES>;
+  static_assert(2 * BN <= 512, "two accumulators must fit the 512 TMEM columns");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint8_t* epi_smem = smem + SM::BAR_OFFSET + 512;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int total_kb = gc.K / GEMM_BK;
+  constexpr int HALF_ROWS = BN / 2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmBh);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 2);                    // used in the leader only
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 16);             // used in the leader only
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)(2 * BN))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int w = cluster_id; w < num_items; w += num_clusters) {
+        const int m0 = (2 * (w % pairs_m) + rank) * GEMM_BM, n0 = (w / pairs_m) * BN + rank * HALF_ROWS;
+        for (int kb = 0; kb < total_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait_cluster(&empty_bar[s], ph ^ 1);
+          const uint32_t lbar = mapa_rank(smem_u32(&full_bar[s]), 0);
+          mbar_arrive_expect_tx_cluster(lbar, SM::STAGE_BYTES);
+          uint8_t* sa = smem + s * SM::STAGE_BYTES;
+          tma_load_3d_2sm(sa, &tmA, lbar, kb * GEMM_BK, m0, gc.a_z0);
+          tma_load_3d_2sm(sa + SM::A_BYTES, &tmBh, lbar, kb * GEMM_BK, n0, gc.b_z0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN);
+      int it = 0, ti = 0;
+      for (int w = cluster_id; w < num_items; w += num_clusters, ++ti) {
+        const int acc = ti & 1;
+        mbar_wait_cluster(&tmem_empty_bar[acc], ((ti >> 1) & 1) ^ 1);      // both CTAs' epilogues drained it
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < total_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait_cluster(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
+          const uint64_t da = umma_desc_k128(sa), db = umma_desc_k128(sa + SM::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k)
+            umma_bf16_2sm(tmem_d, da + (uint64_t)k * 2, db + (uint64_t)k * 2, idesc, (kb | k) != 0);
+          umma_commit_2sm(&empty_bar[s], (uint16_t)3);
+        }
+        umma_commit_2sm(&tmem_full_bar[acc], (uint16_t)3);
+      }
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    constexpr int HALF = BN / 2;
+    int ti = 0;
+    for (int w = cluster_id; w < num_items; w += num_clusters, ++ti) {
+      const int nt = w / pairs_m;
+      const int m0 = (2 * (w % pairs_m) + rank) * GEMM_BM, n0 = nt * BN;
+      const int acc = ti & 1;
+      const int row = m0 + q * 32 + lane;
+      Epi e = epi;
+      if constexpr (Epi::SMEM_PER_WARP > 0) e.attach(epi_smem + (warp - 2) * Epi::SMEM_PER_WARP);
+      e.begin(row, 0);
+      mbar_wait_cluster(&tmem_full_bar[acc], (ti >> 1) & 1);
+      tc_fence_after();
+      float v[32];
+#pragma unroll 1
+      for (int c = half * HALF; c < (half + 1) * HALF; c += 32) {
+        if (n0 + c >= gc.N) break;
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
+        e.chunk(row, n0 + c, 0, v);
+      }
+      e.end(row, nt * 2 + half, 0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty_bar[acc]), 0));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
+  }
+}
+
 // Plain store epilogue: C = acc (+ bias[n]) (+ C).  fp32 output, arbitrary ldc.
 struct EpiStore {
-  static constexpr int SMEM_BYTES = 0;      // shared-memory staging the persistent kernel reserves for the epilogue warps
+  static constexpr int SMEM_PER_WARP = 0;   // shared-memory staging the persistent kernels reserve per epilogue warp
   float* C;
   long long ldc, c_zstride;
   const float* bias;
@@ -539,7 +732,7 @@ int launch_gemm_tn(const OperandView& a, const OperandView& b, const GemmCoords&
 
 // MN = true: C[M,N] = A^T B with A = a [K rows, M cols], B = b [K rows, N cols] (row-major bf16, a.rows = b.rows = K
 // need not be padded: rows past the end read as zero through the tensor map).
-template <int BN, int STAGES, class Epi, bool A_MN = false, bool B_MN = false>
+template <int BN, int STAGES, class Epi, bool A_MN = false, bool B_MN = false, int EW = 8>
 int launch_gemm_tn_persistent(const OperandView& a, const OperandView& b, const GemmCoords& gc, int grid_z,
                               const Epi& epi, cudaStream_t stream) {
   using SM = GemmSmem<BN, STAGES>;
@@ -548,11 +741,11 @@ int launch_gemm_tn_persistent(const OperandView& a, const OperandView& b, const 
   CUtensorMap ta, tb;
   if (A_MN) PVCR_TRY(make_tensor_map_mn(&ta, a, gc.M)); else PVCR_TRY(make_tensor_map(&ta, a, gc.K, GEMM_BM));
   if (B_MN) PVCR_TRY(make_tensor_map_mn(&tb, b, gc.N)); else PVCR_TRY(make_tensor_map(&tb, b, gc.K, BN));
-  auto kern = gemm_tn_persistent_kernel<BN, STAGES, Epi, A_MN, B_MN>;
+  auto kern = gemm_tn_persistent_kernel<BN, STAGES, Epi, A_MN, B_MN, EW>;
   static bool attr_set = false;
   static int sms = 0;
   if (!attr_set) {
-    PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL + 64 + 256 + Epi::SMEM_BYTES));
+    PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL + 64 + 256 + EW * Epi::SMEM_PER_WARP));
     int dev = 0;
     PVCR_CUDA_CHECK(cudaGetDevice(&dev));
     PVCR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -565,7 +758,7 @@ int launch_gemm_tn_persistent(const OperandView& a, const OperandView& b, const 
   if (gemm_cta_cap() > 0 && grid > gemm_cta_cap()) grid = gemm_cta_cap();
   {
     LaunchScope ls_(KC_GEMM, stream, 2.0 * gc.M * gc.N * (double)gc.K * grid_z);
-    kern<<<grid, GEMM_PERSIST_THREADS, SM::TOTAL + 64 + 256 + Epi::SMEM_BYTES, stream>>>(ta, tb, gc, tiles_m, tiles_n, (int)num_tiles, epi);
+    kern<<<grid, 64 + 32 * EW, SM::TOTAL + 64 + 256 + EW * Epi::SMEM_PER_WARP, stream>>>(ta, tb, gc, tiles_m, tiles_n, (int)num_tiles, epi);
   }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
@@ -584,7 +777,41 @@ int launch_gemm_tn_mc2(const OperandView& a, const OperandView& b, const GemmCoo
   auto kern = gemm_tn_mc2_kernel<BN, STAGES, Epi>;
   static bool attr_set = false;
   static int sms = 0;
-  constexpr int SMEM = SM::TOTAL + 64 + 256 + Epi::SMEM_BYTES;
+  constexpr int SMEM = SM::TOTAL + 64 + 256 + 8 * Epi::SMEM_PER_WARP;
+  if (!attr_set) {
+    PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    int dev = 0;
+    PVCR_CUDA_CHECK(cudaGetDevice(&dev));
+    PVCR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    attr_set = true;
+  }
+  const int pairs_m = cdiv(cdiv(gc.M, GEMM_BM), 2), tiles_n = cdiv(gc.N, BN);
+  const long long num_items = (long long)pairs_m * tiles_n;
+  int clusters = sms / 2;
+  if (gemm_cta_cap() > 1 && clusters > gemm_cta_cap() / 2) clusters = gemm_cta_cap() / 2;
+  if (num_items < clusters) clusters = (int)num_items;
+  {
+    LaunchScope ls_(KC_GEMM, stream, 2.0 * gc.M * gc.N * (double)gc.K);
+    kern<<<2 * clusters, GEMM_PERSIST_THREADS, SMEM, stream>>>(ta, tb, gc, pairs_m, tiles_n, (int)num_items, epi);
+  }
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  return PVCR_OK;
+}
+
+// K-major x K-major product on the CTA-pair (cta_group::2) kernel (single slab, no split-K).
+template <int BN, int STAGES, class Epi>
+int launch_gemm_tn_2sm(const OperandView& a, const OperandView& b, const GemmCoords& gc, const Epi& epi,
+                       cudaStream_t stream) {
+  using SM = Gemm2SmSmem<BN, STAGES>;
+  PVCR_REQUIRE(gc.K > 0 && gc.K % GEMM_BK == 0, "gemm: K=%d must be a positive multiple of %d", gc.K, GEMM_BK);
+  PVCR_REQUIRE(gc.M > 0 && gc.N > 0 && gc.k_splits <= 1, "gemm (2-CTA): empty problem or split-K");
+  CUtensorMap ta, tb;
+  PVCR_TRY(make_tensor_map(&ta, a, gc.K, GEMM_BM));
+  PVCR_TRY(make_tensor_map(&tb, b, gc.K, BN / 2));
+  auto kern = gemm_tn_2sm_kernel<BN, STAGES, Epi>;
+  static bool attr_set = false;
+  static int sms = 0;
+  constexpr int SMEM = SM::TOTAL + 8 * Epi::SMEM_PER_WARP;
   if (!attr_set) {
     PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     int dev = 0;

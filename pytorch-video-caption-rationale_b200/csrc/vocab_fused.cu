@@ -20,7 +20,7 @@ constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
 struct EpiCeFwd {
-  static constexpr int SMEM_BYTES = 0;
+  static constexpr int SMEM_PER_WARP = 0;
   const float* bias;
   float *pmax, *psum; int* pidx;
   int M, N, nparts;
@@ -76,7 +76,7 @@ struct EpiCeBwd {
   // L1 wavefront per row).  Each epilogue warp instead transposes its 32 x 32 bf16 chunk through 2 KB of shared
   // memory (16-byte slots XOR-swizzled, conflict free both ways) and stores 8 rows x 64 contiguous bytes per
   // instruction: 4x fewer LSU wavefronts, which were as long as the MMA main loop of a K = 512 tile.
-  static constexpr int SMEM_BYTES = 8 * 2048;
+  static constexpr int SMEM_PER_WARP = 2048;
   const float* bias; const long long* target; const float *lse2, *roww;      // lse2 = lse * log2(e)
   bf16* D; long long ldD;
   int M, N;
@@ -224,6 +224,19 @@ static bool ce_multicast() {
   return on;
 }
 
+// PVCR_CE_2SM=1: CTA-pair (cta_group::2) tiles for the two vocabulary GEMMs (gemm_tn_2sm_kernel)
+static bool ce_pair() {
+  static const bool on = getenv("PVCR_CE_2SM") != nullptr;
+  return on;
+}
+
+// epilogue warps of the 1-CTA fused kernels: 16 (four per SM sub-partition) unless PVCR_CE_EW8 is set (A/B knob)
+static bool ce_ew16() {
+  static const bool off = getenv("PVCR_CE_EW8") != nullptr;
+  return !off && !ce_pair() && !ce_multicast();
+}
+static int ce_parts() { return ce_ew16() ? 4 : 2; }
+
 struct FusedWs {
   Planes hs_a, wv;
   float *pmax, *psum, *tgt, *nll, *roww;
@@ -233,7 +246,7 @@ struct FusedWs {
   int ntiles;
 };
 static void carve_fused(Arena& a, int M, int H, int Vc, FusedWs& w) {
-  w.ntiles = 2 * cdiv(Vc, CE_BN);        // partials per (N tile, column half) of the persistent GEMM epilogue
+  w.ntiles = ce_parts() * cdiv(Vc, CE_BN);     // partials per (N tile, column part) of the persistent GEMM epilogue
   w.hs_a = alloc_planes(a, M, H, 1);
   w.wv = alloc_planes(a, Vc, H, 1);
   w.pmax = a.alloc<float>((size_t)M * w.ntiles); w.psum = a.alloc<float>((size_t)M * w.ntiles);
@@ -288,7 +301,9 @@ int vocab_fused_fwd(const float* hs, const float* wv, const float* bv, const lon
   epi.bias = bv; epi.pmax = w.pmax; epi.psum = w.psum; epi.pidx = w.pidx;
   epi.M = M; epi.N = Vc; epi.nparts = w.ntiles;
   GemmCoords gc{M, Vc, (int)w.hs_a.ld, 0, 0, 0, 0};
-  if (ce_multicast()) PVCR_TRY((launch_gemm_tn_mc2<CE_BN, 4, EpiCeFwd>(w.hs_a.view(), w.wv.view(), gc, epi, st)));
+  if (ce_pair()) PVCR_TRY((launch_gemm_tn_2sm<CE_BN, 5, EpiCeFwd>(w.hs_a.view(), w.wv.view(), gc, epi, st)));
+  else if (ce_multicast()) PVCR_TRY((launch_gemm_tn_mc2<CE_BN, 4, EpiCeFwd>(w.hs_a.view(), w.wv.view(), gc, epi, st)));
+  else if (ce_ew16()) PVCR_TRY((launch_gemm_tn_persistent<CE_BN, 4, EpiCeFwd, false, false, 16>(w.hs_a.view(), w.wv.view(), gc, 1, epi, st)));
   else PVCR_TRY((launch_gemm_tn_persistent<CE_BN, 4, EpiCeFwd>(w.hs_a.view(), w.wv.view(), gc, 1, epi, st)));
   {
     LaunchScope ls_(KC_LOSS, st);
@@ -320,7 +335,9 @@ int vocab_fused_bwd(const float* hs, const float* wv, const float* bv, const lon
   if (w.ldD > Vc)      // chunks lying entirely past Vc are skipped by the GEMM epilogue: their K-padding must read 0
     PVCR_CUDA_CHECK(cudaMemset2DAsync(w.D + Vc, sizeof(bf16) * w.ldD, 0, sizeof(bf16) * (w.ldD - Vc), M, st));
   GemmCoords gc{M, Vc, (int)w.hs_a.ld, 0, 0, 0, 0};
-  if (ce_multicast()) PVCR_TRY((launch_gemm_tn_mc2<CE_BN, 4, EpiCeBwd>(w.hs_a.view(), w.wv.view(), gc, epi, st)));
+  if (ce_pair()) PVCR_TRY((launch_gemm_tn_2sm<CE_BN, 5, EpiCeBwd>(w.hs_a.view(), w.wv.view(), gc, epi, st)));
+  else if (ce_multicast()) PVCR_TRY((launch_gemm_tn_mc2<CE_BN, 4, EpiCeBwd>(w.hs_a.view(), w.wv.view(), gc, epi, st)));
+  else if (ce_ew16()) PVCR_TRY((launch_gemm_tn_persistent<CE_BN, 4, EpiCeBwd, false, false, 16>(w.hs_a.view(), w.wv.view(), gc, 1, epi, st)));
   else PVCR_TRY((launch_gemm_tn_persistent<CE_BN, 4, EpiCeBwd>(w.hs_a.view(), w.wv.view(), gc, 1, epi, st)));
   // d W = dlogits^T Dropout(hs) and d b = column sums of dlogits do not feed the rest of the backward: they run on
   // the side lane next to the d hs product (60 output tiles) and whatever the caller enqueues next.
