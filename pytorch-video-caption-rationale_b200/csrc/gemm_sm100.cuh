@@ -508,8 +508,8 @@ struct Gemm2SmSmem {
   static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;          // barriers / slot / epilogue offset + alignment slack
 };
 
-template <int BN, int STAGES, class Epi>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_PERSIST_THREADS, 1)
+template <int BN, int STAGES, class Epi, int EW = 8>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh, GemmCoords gc,
                    int pairs_m, int tiles_n, int num_items, Epi epi) {
   using SM = Gemm2SmSmem<BN, STAGES>;
@@ -540,7 +540,7 @@ gemm_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 16);             // used in the leader only
+      mbar_init(&tmem_empty_bar[a], 2 * EW);         // used in the leader only
     }
     fence_barrier_init();
   }
@@ -564,7 +564,7 @@ gemm_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int kb = 0; kb < total_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait_cluster(&empty_bar[s], ph ^ 1);
+          mbar_wait(&empty_bar[s], ph ^ 1);
           const uint32_t lbar = mapa_rank(smem_u32(&full_bar[s]), 0);
           mbar_arrive_expect_tx_cluster(lbar, SM::STAGE_BYTES);
           uint8_t* sa = smem + s * SM::STAGE_BYTES;
@@ -579,13 +579,13 @@ gemm_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       int it = 0, ti = 0;
       for (int w = cluster_id; w < num_items; w += num_clusters, ++ti) {
         const int acc = ti & 1;
-        mbar_wait_cluster(&tmem_empty_bar[acc], ((ti >> 1) & 1) ^ 1);      // both CTAs' epilogues drained it
+        mbar_wait(&tmem_empty_bar[acc], ((ti >> 1) & 1) ^ 1);      // both CTAs' epilogues drained it
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < total_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait_cluster(&full_bar[s], ph);
+          mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
           const uint64_t da = umma_desc_k128(sa), db = umma_desc_k128(sa + SM::A_BYTES);
@@ -599,7 +599,7 @@ gemm_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else {
     const int q = warp & 3, half = (warp - 2) >> 2;
-    constexpr int HALF = BN / 2;
+    constexpr int PARTS = EW / 4, HALF = BN / PARTS;
     int ti = 0;
     for (int w = cluster_id; w < num_items; w += num_clusters, ++ti) {
       const int nt = w / pairs_m;
@@ -609,7 +609,7 @@ gemm_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       Epi e = epi;
       if constexpr (Epi::SMEM_PER_WARP > 0) e.attach(epi_smem + (warp - 2) * Epi::SMEM_PER_WARP);
       e.begin(row, 0);
-      mbar_wait_cluster(&tmem_full_bar[acc], (ti >> 1) & 1);
+      mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);
       tc_fence_after();
       float v[32];
 #pragma unroll 1
@@ -618,7 +618,7 @@ gemm_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
         e.chunk(row, n0 + c, 0, v);
       }
-      e.end(row, nt * 2 + half, 0);
+      e.end(row, nt * PARTS + half, 0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty_bar[acc]), 0));
@@ -799,7 +799,7 @@ int launch_gemm_tn_mc2(const OperandView& a, const OperandView& b, const GemmCoo
 }
 
 // K-major x K-major product on the CTA-pair (cta_group::2) kernel (single slab, no split-K).
-template <int BN, int STAGES, class Epi>
+template <int BN, int STAGES, class Epi, int EW = 8>
 int launch_gemm_tn_2sm(const OperandView& a, const OperandView& b, const GemmCoords& gc, const Epi& epi,
                        cudaStream_t stream) {
   using SM = Gemm2SmSmem<BN, STAGES>;
@@ -808,10 +808,10 @@ int launch_gemm_tn_2sm(const OperandView& a, const OperandView& b, const GemmCoo
   CUtensorMap ta, tb;
   PVCR_TRY(make_tensor_map(&ta, a, gc.K, GEMM_BM));
   PVCR_TRY(make_tensor_map(&tb, b, gc.K, BN / 2));
-  auto kern = gemm_tn_2sm_kernel<BN, STAGES, Epi>;
+  auto kern = gemm_tn_2sm_kernel<BN, STAGES, Epi, EW>;
   static bool attr_set = false;
   static int sms = 0;
-  constexpr int SMEM = SM::TOTAL + 8 * Epi::SMEM_PER_WARP;
+  constexpr int SMEM = SM::TOTAL + EW * Epi::SMEM_PER_WARP;
   if (!attr_set) {
     PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     int dev = 0;
@@ -826,7 +826,7 @@ int launch_gemm_tn_2sm(const OperandView& a, const OperandView& b, const GemmCoo
   if (num_items < clusters) clusters = (int)num_items;
   {
     LaunchScope ls_(KC_GEMM, stream, 2.0 * gc.M * gc.N * (double)gc.K);
-    kern<<<2 * clusters, GEMM_PERSIST_THREADS, SMEM, stream>>>(ta, tb, gc, pairs_m, tiles_n, (int)num_items, epi);
+    kern<<<2 * clusters, 64 + 32 * EW, SMEM, stream>>>(ta, tb, gc, pairs_m, tiles_n, (int)num_items, epi);
   }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;

@@ -224,7 +224,9 @@ static bool ce_multicast() {
   return on;
 }
 
-// PVCR_CE_2SM=1: CTA-pair (cta_group::2) tiles for the two vocabulary GEMMs (gemm_tn_2sm_kernel)
+// PVCR_CE_2SM=1: CTA-pair (tcgen05 cta_group::2, M = 256) tiles for the two vocabulary GEMMs (gemm_tn_2sm_kernel).
+// Parity-green; measured SLOWER than the 1-CTA kernel at this shape (the two GEMMs together +0.11 ms with 16 epilogue
+// warps each, 6 x 32 KB stages): kept off, as the base for larger-K products where operand traffic does bind.
 static bool ce_pair() {
   static const bool on = getenv("PVCR_CE_2SM") != nullptr;
   return on;
@@ -233,9 +235,9 @@ static bool ce_pair() {
 // epilogue warps of the 1-CTA fused kernels: 16 (four per SM sub-partition) unless PVCR_CE_EW8 is set (A/B knob)
 static bool ce_ew16() {
   static const bool off = getenv("PVCR_CE_EW8") != nullptr;
-  return !off && !ce_pair() && !ce_multicast();
+  return !off && !ce_multicast();
 }
-static int ce_parts() { return ce_ew16() ? 4 : 2; }
+static int ce_parts() { return (ce_ew16() || ce_pair()) ? 4 : 2; }
 
 struct FusedWs {
   Planes hs_a, wv;
@@ -301,7 +303,7 @@ int vocab_fused_fwd(const float* hs, const float* wv, const float* bv, const lon
   epi.bias = bv; epi.pmax = w.pmax; epi.psum = w.psum; epi.pidx = w.pidx;
   epi.M = M; epi.N = Vc; epi.nparts = w.ntiles;
   GemmCoords gc{M, Vc, (int)w.hs_a.ld, 0, 0, 0, 0};
-  if (ce_pair()) PVCR_TRY((launch_gemm_tn_2sm<CE_BN, 5, EpiCeFwd>(w.hs_a.view(), w.wv.view(), gc, epi, st)));
+  if (ce_pair()) PVCR_TRY((launch_gemm_tn_2sm<CE_BN, 6, EpiCeFwd, 16>(w.hs_a.view(), w.wv.view(), gc, epi, st)));
   else if (ce_multicast()) PVCR_TRY((launch_gemm_tn_mc2<CE_BN, 4, EpiCeFwd>(w.hs_a.view(), w.wv.view(), gc, epi, st)));
   else if (ce_ew16()) PVCR_TRY((launch_gemm_tn_persistent<CE_BN, 4, EpiCeFwd, false, false, 16>(w.hs_a.view(), w.wv.view(), gc, 1, epi, st)));
   else PVCR_TRY((launch_gemm_tn_persistent<CE_BN, 4, EpiCeFwd>(w.hs_a.view(), w.wv.view(), gc, 1, epi, st)));
@@ -335,7 +337,7 @@ int vocab_fused_bwd(const float* hs, const float* wv, const float* bv, const lon
   if (w.ldD > Vc)      // chunks lying entirely past Vc are skipped by the GEMM epilogue: their K-padding must read 0
     PVCR_CUDA_CHECK(cudaMemset2DAsync(w.D + Vc, sizeof(bf16) * w.ldD, 0, sizeof(bf16) * (w.ldD - Vc), M, st));
   GemmCoords gc{M, Vc, (int)w.hs_a.ld, 0, 0, 0, 0};
-  if (ce_pair()) PVCR_TRY((launch_gemm_tn_2sm<CE_BN, 5, EpiCeBwd>(w.hs_a.view(), w.wv.view(), gc, epi, st)));
+  if (ce_pair()) PVCR_TRY((launch_gemm_tn_2sm<CE_BN, 6, EpiCeBwd, 16>(w.hs_a.view(), w.wv.view(), gc, epi, st)));
   else if (ce_multicast()) PVCR_TRY((launch_gemm_tn_mc2<CE_BN, 4, EpiCeBwd>(w.hs_a.view(), w.wv.view(), gc, epi, st)));
   else if (ce_ew16()) PVCR_TRY((launch_gemm_tn_persistent<CE_BN, 4, EpiCeBwd, false, false, 16>(w.hs_a.view(), w.wv.view(), gc, 1, epi, st)));
   else PVCR_TRY((launch_gemm_tn_persistent<CE_BN, 4, EpiCeBwd>(w.hs_a.view(), w.wv.view(), gc, 1, epi, st)));
