@@ -14,12 +14,15 @@ from ._lib import check, lib, ptr, stream_ptr
 
 
 class GraphedTrainStep:
-    def __init__(self, model, example_inputs, warmup=3, reducer=None):
+    def __init__(self, model, example_inputs, warmup=3, reducer=None, optimizer=None):
         """example_inputs: tuple of CUDA tensors, the arguments of model.train_step_grads (fixes shapes/dtypes).
         reducer: a parallel.GradAllReducer(flat=True, early=model.early_grad_params()); the step is then captured as
         two graphs split where the early gradients are final, and their all-reduce overlaps the second graph."""
         self.model = model
         self.reducer = reducer
+        # optimizer: an optim.FusedClipAdam; its clip + Adam kernels are captured behind the backward (and the gradient
+        # all-reduce), so one replay is a whole training iteration (train.py:157-160)
+        self.optimizer = optimizer
         # per-replay dropout / Gumbel seeds: a device counter incremented by the first captured graph node
         self.seed_step = torch.zeros(1, dtype=torch.int64, device=example_inputs[0].device)
         lib().pvcr_set_seed_step(ptr(self.seed_step))
@@ -64,6 +67,8 @@ class GraphedTrainStep:
                 for j in range(i, len(reducer.buckets)):
                     reducer.begin(j, tail=True)
                 reducer.finish()
+                if optimizer is not None:
+                    optimizer.step()
                 return res
 
             with torch.no_grad():
@@ -91,9 +96,17 @@ class GraphedTrainStep:
                     if more:
                         self.graphs.append(torch.cuda.CUDAGraph())
         else:
+            if optimizer is not None:          # pointer table of the optimizer is built outside the capture
+                with torch.cuda.stream(side):
+                    model.train_step_grads(*self.static_in)
+                    optimizer.step()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
             with torch.cuda.graph(self.graph):
                 self.seed_step.add_(1)
                 out = model.train_step_grads(*self.static_in)
+                if optimizer is not None:
+                    optimizer.step()
         self.static_out = tuple(o.detach() if torch.is_tensor(o) else o for o in out)
         # input pipeline: the next batch is copied host -> device into staging buffers on a side stream while the
         # current step computes (what a pinned-memory DataLoader with non_blocking copies gives the reference loop)

@@ -88,3 +88,56 @@ def test_fused_clip_adam_in_cuda_graph_advances_step():
     # constant gradient: every Adam step moves the parameter by exactly lr (bias-corrected m / sqrt(v) = 1)
     assert int(opt.step_count.item()) == 3            # one eager step + two replays (the capture itself does not run)
     assert torch.allclose(prm, torch.full_like(prm, 1.0 - 3 * 1e-2), atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_training_iterations_graph_vs_eager_vs_torch_optimizer():
+    """Three whole training iterations (train.py:157-160: fwd, bwd, clip_grad_norm_, Adam) of S2VTAtt: one CUDA graph per
+    iteration (step + FusedClipAdam captured together) == the eager tape-free step + FusedClipAdam == the eager step +
+    torch's own clip_grad_norm_ / torch.optim.Adam, compared on the parameter updates."""
+    import pvcr_b200  # noqa: F401
+    from pvcr_b200.graphs import GraphedTrainStep
+    from pvcr_b200.model import S2VTAttModel
+    from pvcr_b200.optim import FusedClipAdam
+    from tests.gpu_util import FixtureGlove, load_case, to_cuda
+    d, params, _, (B, N, V, H, E, L, Vc) = load_case("s2vtatt_mid")
+    vid = torch.from_numpy(d["vid"]).cuda()
+    s = torch.from_numpy(d["s"]).cuda()
+    s_len = torch.from_numpy(d["s_len"]).cuda()
+    hp = dict(lr=2e-3, weight_decay=4e-5)
+
+    def fresh():
+        return to_cuda(S2VTAttModel(FixtureGlove(Vc, E), 0.0, H, V, L, precision="bf16x3"), params).train()
+
+    start = {k: v.detach().clone() for k, v in fresh().named_parameters()}
+    # (a) eager step + torch optimizer (the reference's own calls)
+    ma = fresh()
+    oa = torch.optim.Adam(ma.parameters(), **hp)
+    for _ in range(3):
+        ma.train_step_grads(vid, s, s_len)
+        torch.nn.utils.clip_grad_norm_(ma.parameters(), 1.0)
+        oa.step()
+    # (b) eager step + fused optimizer
+    mb = fresh()
+    ob = FusedClipAdam(mb.parameters(), max_norm=1.0, **hp)
+    for _ in range(3):
+        mb.train_step_grads(vid, s, s_len)
+        ob.step()
+    # (c) one graph per iteration; the constructor runs one eager iteration first (optimizer pointer table)
+    mc = fresh()
+    oc = FusedClipAdam(mc.parameters(), max_norm=1.0, **hp)
+    g = GraphedTrainStep(mc, (vid, s, s_len), warmup=0, optimizer=oc)
+    for _ in range(2):
+        g(vid, s, s_len)
+    torch.cuda.synchronize()
+    assert int(oc.step_count.item()) == 3
+
+    def upd(m):
+        return {k: (v.detach() - start[k]).double() for k, v in m.named_parameters()}
+
+    ua, ub, uc = upd(ma), upd(mb), upd(mc)
+    for k in ua:
+        na = ua[k].norm().item()
+        assert na > 0, k
+        assert (ub[k] - ua[k]).norm().item() < 2e-3 * na, (k, "fused vs torch", (ub[k] - ua[k]).norm().item() / na)
+        assert (uc[k] - ub[k]).norm().item() < 2e-3 * na, (k, "graph vs eager", (uc[k] - ub[k]).norm().item() / na)
