@@ -156,6 +156,14 @@ int gemm_kn_store(const OperandView& a, const OperandView& b, int M, int N, int 
                   int accumulate, cudaStream_t stream) {
   EpiStore epi{C, ldc, 0, nullptr, 0, accumulate, M, N, 0, 1};
   GemmCoords gc{M, N, (int)round_up(K, GEMM_BK), 0, 0, 0, 0};
+  // long contraction, fewer tiles than half the SMs (d hs = d logits W_v: 60 tiles, K = 23 040): two K ranges per tile
+  static const int kn_split = getenv("PVCR_KN_SPLIT") ? atoi(getenv("PVCR_KN_SPLIT")) : 1;
+  const long long tiles = (long long)cdiv(M, GEMM_BM) * cdiv(N, 256);
+  if (kn_split > 1 && tiles * kn_split <= 148 && gc.K / GEMM_BK >= 64 * kn_split) {
+    gc.k_splits = kn_split;
+    if (!accumulate) PVCR_CUDA_CHECK(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, stream));
+    epi.atomic = 1;
+  }
   return launch_gemm_tn_persistent<256, 4, EpiStore, false, true>(a, b, gc, 1, epi, stream);
 }
 
