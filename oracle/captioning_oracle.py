@@ -630,3 +630,55 @@ def clip_adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=2e-3, betas=(0.9
         denom = np.sqrt(exp_avg_sq[k]) / np.sqrt(bc2) + eps
         params[k] -= (lr / bc1) * exp_avg[k] / denom
     return total
+
+
+# ----------------------------------------------------------------------------------------
+# beam search over Decoder.forward_step.  The reference ships no beam search: this DEFINES it as
+# the plain fixed-length search over the reference step (S2VTAttModel.py:125-148) -- every hypothesis is extended for
+# exactly max_len steps like the reference's greedy eval branch (:172-191, no early stop), score = sum of
+# log-softmax, the K best of the K x Vc candidates of a video survive (ties: lower flat index beam*Vc + word first) --
+# so that beam 1 IS the reference's greedy decoding.  Pinned by tests/golden/s2vtatt_beam_*.npz, which
+# oracle/gen_golden_beam.py produces by driving the unmodified reference modules with the same search.
+# ----------------------------------------------------------------------------------------
+def beam_select(score, logp, K, first):
+    """score [B,K], logp [B,K,Vc] -> (new score [B,K], parent [B,K], word [B,K]).  At the first step only beam 0 is live."""
+    B, _, Vc = logp.shape
+    cand = score[:, :, None] + logp
+    if first:
+        cand[:, 1:, :] = -np.inf
+    flat = cand.reshape(B, K * Vc)
+    order = np.argsort(-flat, axis=1, kind="stable")[:, :K]          # stable: lower flat index wins ties
+    return np.take_along_axis(flat, order, 1), order // Vc, order % Vc
+
+
+def s2vtatt_beam_search(p, vid, sos_id, max_len, K):
+    """Returns (ids [B,K,L] int64, scores [B,K]) sorted best first."""
+    enc, _ = s2vtatt_encode(p, vid)
+    B, N, H = enc.shape
+    Wq = p["decoder.attention.query_layer.weight"]; Wk = p["decoder.attention.key_layer.weight"]
+    v = p["decoder.attention.energy_layer.weight"][0]
+    W_ih = p["decoder.rnn.weight_ih_l0"]; W_hh = p["decoder.rnn.weight_hh_l0"]
+    b_ih = p["decoder.rnn.bias_ih_l0"]; b_hh = p["decoder.rnn.bias_hh_l0"]
+    Wv = p["decoder.pred_linear.1.weight"]; bv = p["decoder.pred_linear.1.bias"]
+    emb = p["decoder.embedding.weight"]
+    pk = (enc.reshape(B * N, H) @ Wk.T).reshape(B, N, H)
+    encr, pkr = np.repeat(enc, K, axis=0), np.repeat(pk, K, axis=0)         # rows b*K + k
+    h = np.repeat(enc[:, -1], K, axis=0)
+    w = np.full((B * K,), sos_id, np.int64)
+    score = np.zeros((B, K), enc.dtype)
+    ids = np.zeros((B, K, max_len), np.int64)
+    for i in range(max_len):
+        ctx, _a, _e = attention_fwd(h @ Wq.T, pkr, encr, v)
+        gi = np.concatenate([ctx, emb[w]], axis=1) @ W_ih.T + b_ih
+        gh = h @ W_hh.T + b_hh
+        r = sigmoid(gi[:, :H] + gh[:, :H]); z = sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
+        n = np.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:])
+        h = (1.0 - z) * n + z * h
+        logp = log_softmax(h @ Wv.T + bv).reshape(B, K, -1)
+        score, parent, word = beam_select(score, logp, K, first=(i == 0))
+        rows = (np.arange(B)[:, None] * K + parent).reshape(-1)
+        h = h[rows]
+        ids = np.take_along_axis(ids, parent[:, :, None], 1)
+        ids[:, :, i] = word
+        w = word.reshape(-1)
+    return ids, score
