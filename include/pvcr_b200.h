@@ -140,6 +140,17 @@ int pvcr_s2vtatt_bwd_part(const PvcrDims* d, const PvcrS2vtAttParams* p, const f
                           const int64_t* s_in, const float* hs, const float* d_hs, PvcrS2vtAttGrads* g,
                           float* d_frame_scale, void* workspace, size_t workspace_bytes, void* stream, int part);
 
+/* Fixed-length beam search over the decoder step.  The reference has no beam search: the search
+ * is DEFINED (oracle/captioning_oracle.py: s2vtatt_beam_search) as the plain search over Decoder.forward_step
+ * (model/S2VTAttModel.py:125-148) that extends every hypothesis for exactly L steps like the reference's greedy eval
+ * branch (:172-191), scores by the sum of log-softmax and keeps the `beam` best of a video's beam x Vc candidates
+ * (ties: lower beam * Vc + word first) - so that beam = 1 is the reference's greedy decoding.
+ *   ids [B, beam, L] (best hypothesis first), scores [B, beam] (nullable); beam <= 8; nsplit = 3 for fp32-equivalence. */
+size_t pvcr_s2vtatt_beam_workspace(const PvcrDims* d, int beam);
+int pvcr_s2vtatt_beam(const PvcrDims* d, const PvcrS2vtAttParams* p, const float* vid_feats, const float* frame_scale,
+                      int64_t sos_id, int beam, int64_t* ids, float* scores, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
 /* S2VTModel parameters (reference state_dict names, model/S2VTModel.py:36-49). */
 typedef struct {
   const float* emb;       /* embedding.0.weight   [Vc, E]   */

@@ -97,6 +97,9 @@ SIGNATURES = {
     "pvcr_s2vtatt_greedy_workspace": (c_size, [P(PvcrDims)]),
     "pvcr_s2vtatt_greedy": (c_int, [P(PvcrDims), P(PvcrS2vtAttParams), c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_size,
                                     c_vp]),
+    "pvcr_s2vtatt_beam_workspace": (c_size, [P(PvcrDims), c_int]),
+    "pvcr_s2vtatt_beam": (c_int, [P(PvcrDims), P(PvcrS2vtAttParams), c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_size,
+                                  c_vp]),
     "pvcr_s2vt_decode_steps_workspace": (c_size, [P(PvcrDims)]),
     "pvcr_s2vt_decode_steps": (c_int, [P(PvcrDims), P(PvcrS2vtParams), c_vp, c_vp, c_i64, c_vp, P(ctypes.c_int32), c_f,
                                        c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),

@@ -35,6 +35,9 @@ int generator_bwd(const PvcrDims&, const PvcrGenParams&, const float*, float, co
                   PvcrGenGrads&, void*, size_t, cudaStream_t);
 size_t vocab_ce_workspace(int B, int L, int H, int Vc, int nsplit, float dropout_p);
 int vocab_ce_prepare(const float*, int, int, int, int, int, void*, size_t, cudaStream_t);
+size_t s2vtatt_beam_workspace(const PvcrDims& d, int K);
+int s2vtatt_beam(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid, const float* frame_scale, long long sos_id,
+                 int K, long long* ids, float* scores, void* ws, size_t ws_bytes, cudaStream_t st);
 int vocab_ce_fwd(const float*, const float*, const float*, const long long*, const long long*, int, int, int, int, int,
                  float, unsigned long long, float*, long long*, float*, float*, long long, void*, size_t, cudaStream_t);
 int vocab_ce_bwd(const float*, const float*, const float*, const long long*, const long long*, int, int, int, int, int, float,
@@ -146,6 +149,14 @@ int pvcr_rationale_penalties_bwd(const float* probs, int B, int N, const float* 
 }
 size_t pvcr_vocab_ce_workspace(int B, int L, int H, int Vc, int nsplit, float dropout_p) {
   return vocab_ce_workspace(B, L, H, Vc, nsplit, dropout_p);
+}
+size_t pvcr_s2vtatt_beam_workspace(const PvcrDims* d, int beam) { return d ? s2vtatt_beam_workspace(*d, beam) : 0; }
+int pvcr_s2vtatt_beam(const PvcrDims* d, const PvcrS2vtAttParams* p, const float* vid_feats, const float* frame_scale,
+                      int64_t sos_id, int beam, int64_t* ids, float* scores, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  if (!d || !p) { set_last_error("pvcr_s2vtatt_beam: null dims / params"); return PVCR_ERR_ARG; }
+  return s2vtatt_beam(*d, *p, vid_feats, frame_scale, (long long)sos_id, beam, (long long*)ids, scores, workspace,
+                      workspace_bytes, (cudaStream_t)stream);
 }
 int pvcr_vocab_ce_prepare(const float* out_w, int B, int L, int H, int Vc, int nsplit, void* workspace,
                           size_t workspace_bytes, void* stream) {

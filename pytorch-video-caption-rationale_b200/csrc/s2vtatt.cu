@@ -568,4 +568,110 @@ int s2vtatt_greedy(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* v
   return PVCR_OK;
 }
 
+// ---- fixed-length beam search over the decoder step (definition: oracle s2vtatt_beam_search) --------
+// Encoder and proj_key once per video, then K hypotheses per video share them (rows b*K + k of the replicated copies).
+struct BeamWs {
+  AttWs w;                    // encoder side, B rows
+  Planes wv, emb_step, hp, ctx_p;
+  float *encR, *pkR, *hA, *hB, *g1, *g2, *ctx, *alpha, *logits, *scoreA, *scoreB;
+  long long *words, *histA, *histB;
+  int* parent;
+  long long ldl;
+};
+static void carve_beam(Arena& a, const PvcrDims& d, int K, BeamWs& g) {
+  carve(a, d, 0, g.w);
+  const size_t R = (size_t)d.B * K, H = d.H, N = d.N;
+  g.wv = alloc_planes(a, d.Vc, d.H, d.nsplit);
+  g.emb_step = alloc_planes(a, (int)R, d.E, d.nsplit);
+  g.hp = alloc_planes(a, (int)R, d.H, d.nsplit);
+  g.ctx_p = alloc_planes(a, (int)R, d.H, d.nsplit);
+  g.encR = a.alloc<float>(R * N * H); g.pkR = a.alloc<float>(R * N * H);
+  g.hA = a.alloc<float>(R * H); g.hB = a.alloc<float>(R * H);
+  g.g1 = a.alloc<float>(R * 4 * H); g.g2 = a.alloc<float>(R * 3 * H);
+  g.ctx = a.alloc<float>(R * H); g.alpha = a.alloc<float>(R * N);
+  g.ldl = round_up(d.Vc, 4);
+  g.logits = a.alloc<float>(R * g.ldl);
+  g.scoreA = a.alloc<float>(R); g.scoreB = a.alloc<float>(R);
+  g.words = a.alloc<long long>(R); g.histA = a.alloc<long long>(R * d.L); g.histB = a.alloc<long long>(R * d.L);
+  g.parent = a.alloc<int>(R);
+}
+size_t s2vtatt_beam_workspace(const PvcrDims& d, int K) {
+  Arena a(nullptr, 0);
+  BeamWs g;
+  carve_beam(a, d, K < 1 ? 1 : K, g);
+  return a.off + 4096;
+}
+
+int s2vtatt_beam(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid, const float* frame_scale, long long sos_id,
+                 int K, long long* ids, float* scores, void* ws, size_t ws_bytes, cudaStream_t st) {
+  PVCR_TRY(check_dims(d));
+  PVCR_REQUIRE(K >= 1 && K <= 8, "s2vtatt_beam: beam width %d not in 1..8", K);
+  const int B = d.B, N = d.N, V = d.V, H = d.H, E = d.E, L = d.L, Vc = d.Vc, R = B * K;
+  const int BN = B * N, H3 = 3 * H, H4 = 4 * H;
+  Arena a(ws, ws_bytes);
+  BeamWs g;
+  carve_beam(a, d, K, g);
+  if (a.failed) { set_last_error("s2vtatt_beam: workspace too small (%zu < %zu)", ws_bytes, a.off); return PVCR_ERR_WORKSPACE; }
+  AttWs& w = g.w;
+  PVCR_TRY(prep_weight(p.enc_w_ih, V, H3, V, w.wih_enc, st));
+  PVCR_TRY(prep_weight(p.enc_w_hh, H, H3, H, w.whh_enc, st));
+  PVCR_TRY(prep_weight(p.att_wk, H, H, H, w.wk, st));
+  PVCR_TRY(prep_weight(p.att_wq, H, H, H, w.wcat, st, 0));
+  PVCR_TRY(prep_weight(p.dec_w_hh, H, H3, H, w.wcat, st, H));
+  PVCR_TRY(prep_weight(p.dec_w_ih, H + E, H3, H, w.wc, st));
+  PVCR_TRY(prep_weight(p.dec_w_ih + H, H + E, H3, E, w.we, st));
+  PVCR_TRY(prep_weight(p.out_w, H, Vc, H, g.wv, st));
+  if (w.enc_a.Kp != H) {
+    PVCR_TRY(fill_zero(w.enc_a.ptr, sizeof(bf16) * (size_t)BN * w.enc_a.ld, st));
+    PVCR_TRY(fill_zero(g.hp.ptr, sizeof(bf16) * (size_t)R * g.hp.ld, st));
+    PVCR_TRY(fill_zero(g.ctx_p.ptr, sizeof(bf16) * (size_t)R * g.ctx_p.ld, st));
+  }
+  // encoder and proj_key once per video
+  PVCR_TRY(stage(vid, V, BN, V, w.x_a, 0, frame_scale, NO_DROPOUT, st));
+  PVCR_TRY(gemm_planes(w.x_a.view(), w.wih_enc.view(), BN, H3, (int)w.x_a.ld, w.gi_enc, H3, p.enc_b_ih, 0, st));
+  PVCR_TRY(gru_seq_fwd(encoder_seq(d, p, w), st));
+  PVCR_TRY(gemm_planes(w.enc_a.view(), w.wk.view(), BN, H, (int)w.enc_a.ld, w.pk, H, nullptr, 0, st));
+  // K hypotheses per video: rows b*K + k
+  PVCR_TRY(repeat_rows(w.enc, g.encR, B, K, (long long)N * H, st));
+  PVCR_TRY(repeat_rows(w.pk, g.pkR, B, K, (long long)N * H, st));
+  // initial state = encoder final state (frame N-1): gather it with a 2-D copy, then replicate
+  PVCR_CUDA_CHECK(cudaMemcpy2DAsync(g.hB, sizeof(float) * H, w.enc + (long long)(N - 1) * H, sizeof(float) * (size_t)N * H,
+                                    sizeof(float) * H, B, cudaMemcpyDeviceToDevice, st));
+  PVCR_TRY(repeat_rows(g.hB, g.hA, B, K, H, st));
+  PVCR_TRY(fill_i64(g.words, sos_id, R, st));
+  PVCR_TRY(fill_zero(g.scoreA, sizeof(float) * R, st));
+  PVCR_TRY(fill_zero(g.histA, sizeof(long long) * (size_t)R * L, st));
+  float *h_cur = g.hA, *h_new = g.hB, *sc_cur = g.scoreA, *sc_new = g.scoreB;
+  long long *hist_cur = g.histA, *hist_new = g.histB;
+  for (int i = 0; i < L; ++i) {
+    PVCR_TRY(stage(h_cur, H, R, H, g.hp, 0, nullptr, NO_DROPOUT, st));
+    PVCR_TRY(gemm_planes(g.hp.view(), w.wcat.view(), R, H4, (int)w.wcat.ld, g.g1, H4, nullptr, 0, st));
+    AttnFwdArgs at{};
+    at.B = R; at.N = N; at.H = H;
+    at.q = g.g1; at.q_ld = H4; at.pk = g.pkR; at.enc = g.encR; at.v = p.att_v;
+    at.alpha = g.alpha; at.ctx = g.ctx; at.ctx_ld = H;
+    at.ctx_planes = g.ctx_p.ptr; at.ctx_planes_ld = g.ctx_p.ld; at.Hp = g.ctx_p.Kp; at.nsplit = d.nsplit;
+    PVCR_TRY(attn_fwd(at, st));
+    PVCR_TRY(gemm_planes(g.ctx_p.view(), w.wc.view(), R, H3, (int)g.ctx_p.ld, g.g2, H3, nullptr, 0, st));
+    PVCR_TRY(gather_split(p.emb, E, g.words, R, g.emb_step.ptr, g.emb_step.ld, g.emb_step.Kp, d.nsplit, NO_DROPOUT, st));
+    PVCR_TRY(gemm_planes(g.emb_step.view(), w.we.view(), R, H3, (int)g.emb_step.ld, g.g2, H3, p.dec_b_ih, 1, st));
+    GruFwdArgs gf{};
+    gf.B = R; gf.H = H;
+    gf.gi_a = g.g2; gf.gi_a_ld = H3;
+    gf.gh = g.g1 + H; gf.gh_ld = H4; gf.b_hh = p.dec_b_hh;
+    gf.h_prev = h_cur; gf.h_prev_ld = H;
+    gf.h_out = h_new; gf.h_out_ld = H;
+    gf.h_planes = g.hp.ptr; gf.h_planes_ld = g.hp.ld; gf.Hp = g.hp.Kp; gf.nsplit = d.nsplit;
+    PVCR_TRY(gru_gate_fwd(gf, st));
+    PVCR_TRY(gemm_planes(g.hp.view(), g.wv.view(), R, Vc, (int)g.wv.ld, g.logits, g.ldl, p.out_b, 0, st));
+    PVCR_TRY(beam_select(g.logits, g.ldl, B, Vc, K, i == 0, sc_cur, sc_new, g.parent, g.words, st));
+    PVCR_TRY(beam_reorder(h_new, h_cur, R, H, hist_cur, hist_new, L, i, g.parent, g.words, K, st));
+    { float* t = sc_cur; sc_cur = sc_new; sc_new = t; }
+    { long long* t = hist_cur; hist_cur = hist_new; hist_new = t; }
+  }
+  PVCR_CUDA_CHECK(cudaMemcpyAsync(ids, hist_cur, sizeof(long long) * (size_t)R * L, cudaMemcpyDeviceToDevice, st));
+  if (scores) PVCR_CUDA_CHECK(cudaMemcpyAsync(scores, sc_cur, sizeof(float) * R, cudaMemcpyDeviceToDevice, st));
+  return PVCR_OK;
+}
+
 }  // namespace pvcr

@@ -332,6 +332,26 @@ def s2vtatt_greedy(vid, frame_scale, sos_id, max_len, seq_params, out_w, out_b, 
     return ids, logits, alphas
 
 
+def s2vtatt_beam(vid, frame_scale, sos_id, max_len, beam, seq_params, out_w, out_b, nsplit=3):
+    """Fixed-length beam search (pvcr_s2vtatt_beam) -> (ids [B,beam,L] int64, best first; scores [B,beam])."""
+    B, N, V = vid.shape
+    tensors = {f: _f32c(p) for f, p in zip(ATT_SEQ_FIELDS, seq_params)}
+    tensors["out_w"], tensors["out_b"] = _f32c(out_w), _f32c(out_b)
+    H = tensors["enc_w_hh"].shape[1]
+    Vc, E = tensors["emb"].shape
+    dims = make_dims(B, N, V, H, E, max_len, Vc, nsplit, 0.0, 0)
+    vid_c = _f32c(vid)
+    fs_c = None if frame_scale is None else _f32c(frame_scale)
+    Lb = lib()
+    ws = _ws(Lb.pvcr_s2vtatt_beam_workspace(ctypes.byref(dims), int(beam)), vid.device)
+    ids = torch.empty((B, beam, max_len), dtype=torch.int64, device=vid.device)
+    scores = torch.empty((B, beam), dtype=torch.float32, device=vid.device)
+    ps = _fill_struct(PvcrS2vtAttParams(), ATT_PARAM_FIELDS, tensors)
+    check(Lb.pvcr_s2vtatt_beam(ctypes.byref(dims), ctypes.byref(ps), ptr(vid_c), ptr(fs_c), int(sos_id), int(beam),
+                               ptr(ids), ptr(scores), ptr(ws), ws.numel(), stream_ptr()), "pvcr_s2vtatt_beam")
+    return ids, scores
+
+
 def s2vt_decode_steps(vid, frame_scale, sos_id, max_len, seq_params, out_w, out_b, cfg, teacher_words=None,
                       teacher_mask=None, want_logits=True):
     """-> (ids [B,L] arg-max of every step, logits [B,L,Vc] or None, fed [B,L] words fed to every step)."""

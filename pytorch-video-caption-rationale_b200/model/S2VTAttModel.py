@@ -186,3 +186,12 @@ class S2VTAttModel(nn.Module):
                                                 lin.weight, lin.bias)
         self.last_alphas = alphas
         return ids, logits
+
+    @torch.no_grad()
+    def beam_search(self, vid_feats, beam=5, frame_scale=None):
+        """Fixed-length beam search over the decoder step (BASELINE config 5; the reference itself only decodes
+        greedily): -> (ids [B,beam,L], best hypothesis first; scores [B,beam] = sum of log-probabilities).
+        beam=1 reproduces ``greedy``.  fp32-equivalent bf16x3 arithmetic, as for greedy decoding."""
+        d = self.decoder
+        lin = d.pred_linear[1]
+        return F_.s2vtatt_beam(vid_feats, frame_scale, d.sos_id, d.max_len, beam, self._seq_params(), lin.weight, lin.bias)

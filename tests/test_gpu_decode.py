@@ -81,3 +81,23 @@ def test_graphed_greedy_matches_eager():
     ids, logits = g(vid)
     torch.cuda.synchronize()
     assert np.array_equal(ids.cpu().numpy(), d["greedy_ids"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["s2vtatt_tiny", "s2vtatt_mid"])
+@pytest.mark.parametrize("K", [1, 3, 5])
+def test_s2vtatt_beam_search_matches_reference_driven_golden(tag, K):
+    """Beam search: token ids bit-exact and scores to 1e-5 against the search driven over the reference's
+    own Encoder / Decoder.forward_step (oracle/gen_golden_beam.py); beam 1 == the greedy ids of the reference."""
+    import os
+    from pvcr_b200.model import S2VTAttModel
+    from tests.golden_util import GOLDEN
+    d, params, _, (B, N, V, H, E, L, Vc) = load_case(tag)
+    z = np.load(os.path.join(GOLDEN, tag.replace("s2vtatt_", "s2vtatt_beam_") + ".npz"))
+    m = to_cuda(S2VTAttModel(FixtureGlove(Vc, E), 0.0, H, V, L), params).eval()
+    ids, scores = m.beam_search(torch.from_numpy(d["vid"]).cuda(), beam=K)
+    assert ids.shape == (B, K, L) and scores.shape == (B, K)
+    assert np.array_equal(ids.cpu().numpy(), z["ids_k%d" % K])
+    assert np.abs(scores.double().cpu().numpy() - z["score_k%d" % K]).max() < 1e-4
+    if K == 1:
+        assert np.array_equal(ids[:, 0].cpu().numpy(), d["greedy_ids"])
