@@ -61,4 +61,11 @@ for B in (1, 8, 64, 128, 512, 1024):
                 "graph_captions_per_s": B / ms_g * 1e3}
     del gg
 out["cfg5_greedy_s2vtatt"] = sweep
+# cfg5: beam-5 decoding sweep (pvcr_s2vtatt_beam; eager launches)
+bsweep = {}
+for B in (1, 8, 64, 128, 512, 1024):
+    vid = torch.randn(B, N, V, device="cuda")
+    ms = timed(lambda: m.beam_search(vid, beam=5), 3 if B >= 512 else 5)
+    bsweep[B] = {"ms_per_batch": ms, "captions_per_s": B / ms * 1e3}
+out["cfg5_beam5_s2vtatt"] = bsweep
 print(json.dumps(out, indent=1))
