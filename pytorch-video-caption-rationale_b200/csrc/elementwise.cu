@@ -1,6 +1,8 @@
 // Non-GEMM kernels of the captioning path: operand staging (fp32 -> bf16 split planes, transposes,
 // embedding gather / scatter), GRU / LSTM gate math (forward and backward), the additive attention
 // step (forward and backward), cross entropy on materialised logits, and the RationaleNet generator head.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace pvcr {
@@ -528,8 +530,120 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwdArgs a) {
     if (a.ctx_planes) write_split(a.ctx_planes + (long long)b * a.ctx_planes_ld, a.Hp, h, a.nsplit, 0, c);
   }
 }
+// Same step with thread = (8 consecutive dims, frame group): every thread issues the 128-bit loads of all its frames
+// before it uses them (one memory round trip per phase instead of one per frame), scores are reduced by warp shuffles.
+// The step-wise decoders (greedy, beam search, split-precision training) were spending 50 of their ~195 us per step in
+// the kernel above.  Accurate tanhf / expf as above: this path serves the fp32-equivalent modes.
+template <int NF>
+__global__ void __launch_bounds__(256) attn_fwd_vec_kernel(AttnFwdArgs a) {
+  extern __shared__ float sm[];
+  const int H = a.H, N = a.N, b = blockIdx.x;
+  const int DG = H >> 3, FG = 256 / DG, WPF = DG >> 5;      // dim groups, frame groups, warps per frame group (DG % 32 == 0)
+  float* sP = sm;                 // [N][WPF]
+  float* ss = sP + N * WPF;       // [N]
+  float* sC = ss + N;             // [FG][H]
+  const int tid = threadIdx.x, lane = tid & 31, dg = tid % DG, fg = tid / DG, d0 = dg * 8;
+  const float4* q4 = reinterpret_cast<const float4*>(a.q + (long long)b * a.q_ld + d0);
+  const float4* v4 = reinterpret_cast<const float4*>(a.v + d0);
+  const float4 qa = q4[0], qb = q4[1], va = v4[0], vb = v4[1];
+  const float q8[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+  const float v8[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+  const float* pk = a.pk + (long long)b * N * H + d0;
+  const float* enc = a.enc + (long long)b * N * H + d0;
+  float4 x[NF][2];
+#pragma unroll
+  for (int m = 0; m < NF; ++m) {
+    const int n = fg + FG * m;
+    x[m][0] = x[m][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < N) {
+      const float4* p4 = reinterpret_cast<const float4*>(pk + (long long)n * H);
+      x[m][0] = __ldg(p4); x[m][1] = __ldg(p4 + 1);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < NF; ++m) {
+    const int n = fg + FG * m;
+    const float p8[8] = {x[m][0].x, x[m][0].y, x[m][0].z, x[m][0].w, x[m][1].x, x[m][1].y, x[m][1].z, x[m][1].w};
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += v8[e] * tanhf(q8[e] + p8[e]);
+    s = warp_sum(s);
+    if (lane == 0 && n < N) sP[n * WPF + (dg >> 5)] = s;
+  }
+  // the encoder rows of the context phase are independent of the softmax: fetch them now
+#pragma unroll
+  for (int m = 0; m < NF; ++m) {
+    const int n = fg + FG * m;
+    x[m][0] = x[m][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < N) {
+      const float4* e4 = reinterpret_cast<const float4*>(enc + (long long)n * H);
+      x[m][0] = __ldg(e4); x[m][1] = __ldg(e4 + 1);
+    }
+  }
+  __syncthreads();
+  if (tid < 32) {
+    float mx = -INFINITY;
+    for (int n = lane; n < N; n += 32) {
+      float s = 0.f;
+      for (int w = 0; w < WPF; ++w) s += sP[n * WPF + w];
+      ss[n] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float den = 0.f;
+    for (int n = lane; n < N; n += 32) {
+      const float e = expf(ss[n] - mx);
+      ss[n] = e;
+      den += e;
+    }
+    den = warp_sum(den);
+    for (int n = lane; n < N; n += 32) {
+      const float al = ss[n] / den;
+      ss[n] = al;
+      a.alpha[(long long)b * N + n] = al;
+    }
+  }
+  __syncthreads();
+  float c8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int m = 0; m < NF; ++m) {
+    const int n = fg + FG * m;
+    if (n < N) {
+      const float al = ss[n];
+      c8[0] += al * x[m][0].x; c8[1] += al * x[m][0].y; c8[2] += al * x[m][0].z; c8[3] += al * x[m][0].w;
+      c8[4] += al * x[m][1].x; c8[5] += al * x[m][1].y; c8[6] += al * x[m][1].z; c8[7] += al * x[m][1].w;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sC[fg * H + d0 + e] = c8[e];
+  __syncthreads();
+  for (int h = tid; h < H; h += 256) {
+    float c = 0.f;
+    for (int f = 0; f < FG; ++f) c += sC[f * H + h];
+    a.ctx[(long long)b * a.ctx_ld + h] = c;
+    if (a.ctx_planes) write_split(a.ctx_planes + (long long)b * a.ctx_planes_ld, a.Hp, h, a.nsplit, 0, c);
+  }
+}
+
 int attn_fwd(const AttnFwdArgs& a, cudaStream_t st) {
   if (a.B == 0) return PVCR_OK;
+  // vectorised variant: H a multiple of 256 up to 2048 (whole warps per frame group), aligned rows, <= 10 frames per group
+  const int DG = a.H >> 3, FG = DG > 0 && DG <= 256 ? 256 / DG : 0;
+  static const bool vec_off = getenv("PVCR_NO_VEC_ATTN") != nullptr;
+  const bool vec = !vec_off && a.H % 256 == 0 && a.H <= 2048 && FG >= 1 && (a.N + FG - 1) / FG <= 10 && a.q_ld % 4 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.pk) | reinterpret_cast<uintptr_t>(a.enc) |
+                     reinterpret_cast<uintptr_t>(a.v)) & 15) == 0;
+  if (vec) {
+    const int nf = (a.N + FG - 1) / FG;
+    const size_t smem = ((size_t)a.N * (DG >> 5) + a.N + (size_t)FG * a.H) * sizeof(float);
+    PVCR_REQUIRE(smem <= 48 * 1024, "attn_fwd: H=%d N=%d needs %zu B of shared memory", a.H, a.N, smem);
+    { LaunchScope ls_(KC_ATTN, st);
+    if (nf <= 5) attn_fwd_vec_kernel<5><<<a.B, 256, smem, st>>>(a);
+    else attn_fwd_vec_kernel<10><<<a.B, 256, smem, st>>>(a);
+    }
+    PVCR_CUDA_CHECK(cudaGetLastError());
+    return PVCR_OK;
+  }
   const size_t smem = (size_t)(2 * a.H + a.N) * sizeof(float);
   PVCR_REQUIRE(smem <= 48 * 1024, "attn_fwd: H=%d N=%d needs %zu B of shared memory", a.H, a.N, smem);
   { LaunchScope ls_(KC_ATTN, st);

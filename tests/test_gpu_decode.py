@@ -101,3 +101,26 @@ def test_s2vtatt_beam_search_matches_reference_driven_golden(tag, K):
     assert np.abs(scores.double().cpu().numpy() - z["score_k%d" % K]).max() < 1e-4
     if K == 1:
         assert np.array_equal(ids[:, 0].cpu().numpy(), d["greedy_ids"])
+
+
+@pytest.mark.gpu
+def test_greedy_at_full_hidden_size_matches_oracle():
+    """Step-wise decoding at H = 512, N = 40 (the shape class of BASELINE's configs; the golden fixtures are small): this
+    is where the vectorised per-step attention kernel runs.  Token ids equal, attention weights 1e-5, logits 1e-4 against
+    the float64 oracle (vocabulary reduced so numpy finishes in seconds)."""
+    from oracle import captioning_oracle as O
+    from oracle import workloads as W
+    from pvcr_b200.model import S2VTAttModel
+    B, N, V, H, E, L, Vc = 6, 40, 256, 512, 300, 8, 400
+    p = W.s2vtatt_params(V, H, E, Vc, 41)
+    vid, _, _ = W.make_batch(B, N, V, L, Vc, 42)
+    ids_o, logits_o, alphas_o = O.s2vtatt_greedy({k: v.astype(np.float64) for k, v in p.items()}, vid.astype(np.float64),
+                                                 Vc - 4, L)
+    m = to_cuda(S2VTAttModel(FixtureGlove(Vc, E), 0.0, H, V, L), p).eval()
+    ids, logits = m.greedy(torch.from_numpy(vid).cuda())
+    assert np.array_equal(ids.cpu().numpy(), ids_o)
+    assert np.abs(m.last_alphas.double().cpu().numpy() - alphas_o).max() < 1e-5
+    assert relerr(logits.double().cpu().numpy(), logits_o) < 1e-4
+    # beam 1 runs the same step through the beam-search entry point
+    ids_b, _ = m.beam_search(torch.from_numpy(vid).cuda(), beam=1)
+    assert np.array_equal(ids_b[:, 0].cpu().numpy(), ids_o)
