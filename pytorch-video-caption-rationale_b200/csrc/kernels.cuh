@@ -52,8 +52,9 @@ int argmax_rows(const float* in, long long ld, int R, int C, long long* out, lon
 int fill_i64(long long* p, long long v, int n, cudaStream_t st);
 // beam-search bookkeeping (beam.cu)
 int repeat_rows(const float* in, float* out, int rows_in, int K, long long len, cudaStream_t st);
+size_t beam_select_scratch(int B, int K);
 int beam_select(const float* logits, long long ld, int B, int Vc, int K, int first, const float* score_in, float* score_out,
-                int* parent, long long* word, cudaStream_t st);
+                int* parent, long long* word, void* scratch, cudaStream_t st);
 int beam_reorder(const float* h_in, float* h_out, int R, int H, const long long* hist_in, long long* hist_out, int L, int step,
                  const int* parent, const long long* word, int K, cudaStream_t st);
 

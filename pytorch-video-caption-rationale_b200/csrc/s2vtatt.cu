@@ -576,6 +576,7 @@ struct BeamWs {
   float *encR, *pkR, *hA, *hB, *g1, *g2, *ctx, *alpha, *logits, *scoreA, *scoreB;
   long long *words, *histA, *histB;
   int* parent;
+  char* sel_scratch;
   long long ldl;
 };
 static void carve_beam(Arena& a, const PvcrDims& d, int K, BeamWs& g) {
@@ -594,6 +595,7 @@ static void carve_beam(Arena& a, const PvcrDims& d, int K, BeamWs& g) {
   g.scoreA = a.alloc<float>(R); g.scoreB = a.alloc<float>(R);
   g.words = a.alloc<long long>(R); g.histA = a.alloc<long long>(R * d.L); g.histB = a.alloc<long long>(R * d.L);
   g.parent = a.alloc<int>(R);
+  g.sel_scratch = a.alloc<char>(beam_select_scratch(d.B, K));
 }
 size_t s2vtatt_beam_workspace(const PvcrDims& d, int K) {
   Arena a(nullptr, 0);
@@ -664,7 +666,7 @@ int s2vtatt_beam(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid
     gf.h_planes = g.hp.ptr; gf.h_planes_ld = g.hp.ld; gf.Hp = g.hp.Kp; gf.nsplit = d.nsplit;
     PVCR_TRY(gru_gate_fwd(gf, st));
     PVCR_TRY(gemm_planes(g.hp.view(), g.wv.view(), R, Vc, (int)g.wv.ld, g.logits, g.ldl, p.out_b, 0, st));
-    PVCR_TRY(beam_select(g.logits, g.ldl, B, Vc, K, i == 0, sc_cur, sc_new, g.parent, g.words, st));
+    PVCR_TRY(beam_select(g.logits, g.ldl, B, Vc, K, i == 0, sc_cur, sc_new, g.parent, g.words, g.sel_scratch, st));
     PVCR_TRY(beam_reorder(h_new, h_cur, R, H, hist_cur, hist_new, L, i, g.parent, g.words, K, st));
     { float* t = sc_cur; sc_cur = sc_new; sc_new = t; }
     { long long* t = hist_cur; hist_cur = hist_new; hist_new = t; }

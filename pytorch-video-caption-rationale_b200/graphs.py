@@ -192,3 +192,25 @@ class GraphedGreedy:
             self.static_vid.copy_(vid, non_blocking=True)
         self.graph.replay()
         return self.static_out
+
+
+class GraphedBeam:
+    """CUDA-graph capture of fixed-length beam search (model.beam_search) for one batch shape and beam width."""
+
+    def __init__(self, model, example_vid, beam=5):
+        self.static_vid = example_vid.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            model.beam_search(self.static_vid, beam=beam)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_out = model.beam_search(self.static_vid, beam=beam)
+
+    def __call__(self, vid):
+        if vid is not self.static_vid:
+            self.static_vid.copy_(vid, non_blocking=True)
+        self.graph.replay()
+        return self.static_out

@@ -4,7 +4,7 @@ import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import pvcr_b200
-from pvcr_b200.graphs import GraphedGreedy, GraphedTrainStep
+from pvcr_b200.graphs import GraphedBeam, GraphedGreedy, GraphedTrainStep
 from pvcr_b200.model import RationaleNet, S2VTAttModel, S2VTModel
 from tests.gpu_util import FixtureGlove
 
@@ -66,6 +66,10 @@ bsweep = {}
 for B in (1, 8, 64, 128, 512, 1024):
     vid = torch.randn(B, N, V, device="cuda")
     ms = timed(lambda: m.beam_search(vid, beam=5), 3 if B >= 512 else 5)
-    bsweep[B] = {"ms_per_batch": ms, "captions_per_s": B / ms * 1e3}
+    gb = GraphedBeam(m, vid, beam=5)
+    ms_g = timed(lambda: gb(vid), 3 if B >= 512 else 5)
+    bsweep[B] = {"ms_per_batch": ms, "captions_per_s": B / ms * 1e3, "graph_ms_per_batch": ms_g,
+                 "graph_captions_per_s": B / ms_g * 1e3}
+    del gb
 out["cfg5_beam5_s2vtatt"] = bsweep
 print(json.dumps(out, indent=1))

@@ -124,3 +124,17 @@ def test_greedy_at_full_hidden_size_matches_oracle():
     # beam 1 runs the same step through the beam-search entry point
     ids_b, _ = m.beam_search(torch.from_numpy(vid).cuda(), beam=1)
     assert np.array_equal(ids_b[:, 0].cpu().numpy(), ids_o)
+
+
+@pytest.mark.gpu
+def test_graphed_beam_search_equals_eager():
+    from pvcr_b200.graphs import GraphedBeam
+    from pvcr_b200.model import S2VTAttModel
+    d, params, _, (B, N, V, H, E, L, Vc) = load_case("s2vtatt_mid")
+    m = to_cuda(S2VTAttModel(FixtureGlove(Vc, E), 0.0, H, V, L), params).eval()
+    vid = torch.from_numpy(d["vid"]).cuda()
+    ids, scores = m.beam_search(vid, beam=3)
+    g = GraphedBeam(m, vid, beam=3)
+    ids_g, scores_g = g(vid)
+    torch.cuda.synchronize()
+    assert torch.equal(ids, ids_g) and torch.equal(scores, scores_g)
