@@ -102,3 +102,42 @@ def test_data_parallel_grads_equal_single_process(tmp_path):
         assert torch.allclose(g, p.grad, atol=1e-6)
     assert abs(got["loss"].item() - loss.item()) < 1e-6
     assert abs(got["acc"].item() - (3.0 + 4.0) / 8.0) < 1e-6
+
+
+def _dp_flat_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pvcr_b200.parallel import GradAllReducer, shard_batch
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    x, y = torch.randn(8, 6), torch.randn(8, 3)
+    xs, ys = shard_batch((x, y), rank, world)
+    tail = dist.new_group(backend="gloo")             # second communicator for the buckets nothing overlaps any more
+    early = [[model[2].bias, model[2].weight]]        # produced first by the backward: its own bucket, begun early
+    red = GradAllReducer(model, flat=True, early=early, tail_group=tail)
+    loss = ((model(xs) - ys) ** 2).mean()
+    grads = torch.autograd.grad(loss, list(model.parameters()))
+    for p, g in zip(model.parameters(), grads):       # the tape-free steps write into the flat-bucket views in place
+        p.grad.copy_(g)
+    red.begin(0)                                      # overlapped bucket: default group
+    for j in range(1, len(red.buckets)):
+        red.begin(j, tail=True)                       # exposed buckets: tail group
+    red.finish()
+    if rank == 0:
+        torch.save({"grads": [p.grad.clone() for p in model.parameters()], "n_buckets": len(red.buckets)}, out)
+    dist.destroy_process_group()
+
+
+def test_flat_buckets_begin_finish_with_tail_group(tmp_path):
+    """The in-place flat-bucket path the CUDA-graph data-parallel step uses (begin per bucket as it becomes final, tail
+    buckets on a second communicator, finish): reduced gradients == single-process gradients on the whole batch."""
+    out = str(tmp_path / "dpflat.pt")
+    mp.spawn(_dp_flat_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    assert got["n_buckets"] == 2
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    x, y = torch.randn(8, 6), torch.randn(8, 3)
+    ((model(x) - y) ** 2).mean().backward()
+    for g, p in zip(got["grads"], model.parameters()):
+        assert torch.allclose(g, p.grad, atol=1e-6)
