@@ -9,8 +9,9 @@ the reference; optimizer excluded), on one batch of 128 synthetic videos per GPU
 With N > 1 (torchrun, one rank per GPU) each rank runs its own 128 videos and the gradients are averaged by
 NCCL all-reduce inside the timed step (weak scaling).  Rank 0 prints one JSON line.
 
---impl reference times the reference algorithm on the host CPU cores (the numpy oracle port in oracle/, all BLAS
-threads) on a bounded sample of the same workload.
+--impl reference times the reference's own implementation on the host CPU cores: the UNMODIFIED reference modules
+(oracle/_ref, the bytecode oracle/build_ref.py compiles from /root/reference) in torch fp32 on the whole 128-video
+batch, thread count set explicitly; the numpy oracle port only if oracle/_ref did not travel (kind "port").
 """
 import argparse
 import json
@@ -26,7 +27,18 @@ sys.path.insert(0, ROOT)
 WORKLOAD = "cfg2_s2vtatt_msrvtt"
 DIMS = dict(B=128, N=40, V=2048, H=512, E=300, L=30, Vc=23000)
 METRIC = "train videos/sec (fwd+bwd) S2VTAtt MSR-VTT shape"
-CPU_SAMPLE_VIDEOS = 32
+CPU_SAMPLE_VIDEOS = 32          # numpy-port fallback only
+NCU_TRAFFIC_FILE = os.path.join("profiles", "ncu_traffic.json")     # DRAM bytes per launch, from a committed ncu capture
+
+
+def make_config(world, precision, dropout):
+    """The `config` object of the JSON line -- the same for both arms (the reference arm runs THIS workload)."""
+    d = DIMS
+    return dict(workload=WORKLOAD, per_gpu_batch=d["B"], global_batch=d["B"] * world, parallelism="dp%d" % world,
+                precision=precision, dropout_p=dropout,
+                step="CUDA graph of one fwd+bwd (side lanes on; roofline pass times each kernel alone, lanes off)",
+                l2="per-step working set (inputs 42 MB + fp32 weights 101 MB + activations > 1 GB) exceeds "
+                   "the 126 MB L2; no explicit flush", **{k: v for k, v in d.items() if k != "B"})
 
 
 def fwd_bwd_gflop(d):
@@ -88,7 +100,7 @@ class ClockSampler:
 
 
 def cpu_port_videos_per_sec(steps, warmup):
-    """The reference algorithm on the host cores: oracle/captioning_oracle.py (numpy fp32, threaded BLAS),
+    """Fallback CPU arm (only when oracle/_ref is absent): oracle/captioning_oracle.py (numpy fp32, threaded BLAS),
     fwd + masked-CE loss + bwd on a bounded sample of the cfg2 workload."""
     import numpy as np
     from oracle import captioning_oracle as O
@@ -113,20 +125,100 @@ def cpu_cores():
         return os.cpu_count()
 
 
+def reference_batch(device, dropout):
+    """The reference S2VTAttModel (oracle/_ref: unmodified bytecode of /root/reference/model/S2VTAttModel.py) with the
+    seeded cfg2 weights and one seeded cfg2 batch on `device`."""
+    import torch
+    from oracle import reference_runner as R
+    from oracle import workloads as W
+    d = DIMS
+    dims = tuple(d[k] for k in ("B", "N", "V", "H", "E", "L", "Vc"))
+    R.set_device(device)
+    p = W.s2vtatt_params(d["V"], d["H"], d["E"], d["Vc"], 123)
+    model = R.build_s2vtatt(dims, p, dropout_p=dropout, device=device).train()
+    vid, s, s_len = W.make_batch(d["B"], d["N"], d["V"], d["L"], d["Vc"], 124)
+    return model, tuple(torch.from_numpy(x).to(device) for x in (vid, s, s_len))
+
+
+def cpu_reference_videos_per_sec(steps, warmup, dropout):
+    """run_iter + loss.backward() of the reference (train.py:32-44,157-158) on the host cores, the WHOLE 128-video batch
+    per step.  The thread count is set in this process: torchrun exports OMP_NUM_THREADS=1, which would otherwise cut
+    the arm to one core.  -> (videos/s, s per step, threads)."""
+    import torch
+    from oracle import reference_runner as R
+    threads = cpu_cores()
+    torch.set_num_threads(threads)
+    model, (vid, s, s_len) = reference_batch("cpu", dropout)
+    for _ in range(warmup):
+        R.run_iter(model, vid, s, s_len)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss, _, _, _ = R.run_iter(model, vid, s, s_len)
+    dt = (time.perf_counter() - t0) / steps
+    assert torch.isfinite(loss).item()
+    return DIMS["B"] / dt, dt, torch.get_num_threads()
+
+
+def eager_b200_reference(dropout, warmup=3, iters=10):
+    """The incumbent of SURVEY.md section 8(d): the unmodified reference modules in PyTorch eager on THIS GPU (cuDNN RNN,
+    cuBLAS, ATen), fp32 and under torch.autocast(bfloat16); run_iter + backward, CUDA events."""
+    import torch
+    from oracle import reference_runner as R
+    if not R.available():
+        return {"unavailable": "oracle/_ref (reference bytecode) not present on this box"}
+    out = {}
+    model, (vid, s, s_len) = reference_batch("cuda", dropout)
+    try:
+        for name, ctx in (("fp32", None), ("autocast_bf16", torch.bfloat16)):
+            def it():
+                if ctx is None:
+                    return R.run_iter(model, vid, s, s_len)[0]
+                with torch.autocast("cuda", dtype=ctx):
+                    return R.run_iter(model, vid, s, s_len)[0]
+            for _ in range(warmup):
+                it()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                loss = it()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            out[name] = {"value": DIMS["B"] / (ms / 1e3), "unit": "videos/s", "ms_per_step": ms, "iters": iters,
+                         "loss": float(loss.item())}
+        out["what"] = ("unmodified reference S2VTAttModel + train_utils.calc_masked_loss/accuracy + loss.backward() "
+                       "(train.py:32-44,157-158) in PyTorch eager on this GPU, batch %d, dropout %.1f, tf32 off" % (DIMS["B"], dropout))
+    finally:
+        R.set_device("cpu")
+        del model
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 20))
-    warmup = max(1, min(args.warmup, 2))
-    vps, dt = cpu_port_videos_per_sec(steps, warmup)
-    sample = "%d of the %d videos of one %s batch per step (numpy fp32 oracle port, threaded BLAS)" % (
-        CPU_SAMPLE_VIDEOS, DIMS["B"], WORKLOAD)
+    from oracle import reference_runner as R
+    steps, warmup = args.steps, max(args.warmup, 3)
+    if R.available():
+        vps, dt, threads = cpu_reference_videos_per_sec(steps, warmup, args.dropout)
+        kind = "reference"
+        sample = ("the whole %d-video %s batch per step: unmodified reference modules (oracle/_ref bytecode of "
+                  "model/S2VTAttModel.py + train_utils.py), run_iter + loss.backward(), torch fp32 CPU, %d threads" % (
+                      DIMS["B"], WORKLOAD, threads))
+    else:
+        steps, warmup = max(1, min(steps, 20)), max(1, min(warmup, 2))
+        vps, dt = cpu_port_videos_per_sec(steps, warmup)
+        kind, threads = "port", cpu_cores()
+        sample = "%d of the %d videos of one %s batch per step (numpy fp32 oracle port, threaded BLAS; oracle/_ref absent)" % (
+            CPU_SAMPLE_VIDEOS, DIMS["B"], WORKLOAD)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": vps, "unit": "videos/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": dict(workload=WORKLOAD, **DIMS),
-        "cpu_baseline": {"value": vps, "unit": "videos/s", "cores": cpu_cores(), "kind": "port", "sample": sample},
+        "dtype": "f32", "data": "synthetic", "config": make_config(args.gpus, args.precision, args.dropout),
+        "cpu_baseline": {"value": vps, "unit": "videos/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": vps, "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)
 
@@ -144,6 +236,43 @@ def _finish_ranks(world):
     sys.stdout.flush()
     sys.stderr.flush()
     os._exit(0)
+
+
+def check_data_parallel_gradients(model, reducer, inputs, world, dev):
+    """Correctness of the path SCALE times (NCCL all-reduce captured inside the step's CUDA graph), checked after the timed
+    loop: with dropout off (deterministic step) the gradients a graph replay leaves in the buckets must equal, on every
+    rank, the mean over ranks of the gradients the same rank computes locally without any reduction -- and be identical
+    across ranks.  A dropped bucket, a missing 1/G or a bucket reduced before it was final all show up here."""
+    import torch
+    import torch.distributed as dist
+    from pvcr_b200.graphs import GraphedTrainStep
+    drop = model.decoder.pred_linear[0]
+    p_prev = drop.p
+    drop.p = 0.0
+    try:
+        step = GraphedTrainStep(model, inputs, warmup=0, reducer=reducer)
+        step(*inputs)
+        torch.cuda.synchronize()
+        reduced = [b.clone() for b in reducer._flat]
+        model.train_step_grads(*inputs)                    # local gradients, written in place into the same buckets
+        torch.cuda.synchronize()
+        worst, spread = 0.0, 0.0
+        for red, loc in zip(reduced, reducer._flat):
+            mean = loc.clone()
+            dist.all_reduce(mean, op=dist.ReduceOp.SUM)
+            mean /= world
+            worst = max(worst, float(((red - mean).norm() / mean.norm().clamp_min(1e-30)).item()))
+            lo, hi = red.clone(), red.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            spread = max(spread, float(((hi - lo).abs().max() / red.abs().max().clamp_min(1e-30)).item()))
+        del step
+        ok = worst < 1e-4 and spread == 0.0
+        assert ok, "data-parallel gradient check failed: rel err %.3e vs mean of local gradients, rank spread %.3e" % (worst, spread)
+        return {"ok": ok, "buckets": len(reduced), "rel_err_vs_mean_of_local_grads": worst, "max_spread_across_ranks": spread,
+                "what": "in-graph NCCL step (dropout off) vs all-reduce-mean of per-rank eager gradients"}
+    finally:
+        drop.p = p_prev
 
 
 def run_ours(args):
@@ -277,8 +406,13 @@ def run_ours(args):
         model.train_step_grads(vid, s, s_len)
     torch.cuda.synchronize()
     prof = _lib.prof_read()
+    launch_list = _lib.prof_launch_list()
     L_.pvcr_prof_enable(0)
     L_.pvcr_side_mode(side_prev)
+
+    dp_check = None
+    if world > 1:
+        dp_check = check_data_parallel_gradients(model, reducer, (vid, s, s_len), world, dev)
     if rank != 0:
         _finish_ranks(world)
         return
@@ -304,33 +438,49 @@ def run_ours(args):
         "gru_persistent_fwd": N * rec_step + 3 * H * H * 2,
         "gru_persistent_bwd": N * 2 * rec_step + 3 * H * H * 2,
     }
-    # DRAM bytes per launch measured with `ncu --set full` (profiles/): dram__bytes_read.sum + dram__bytes_write.sum
-    ncu_traffic = {"decoder_persistent_bwd": 123.8e6, "decoder_persistent_fwd": 58.3e6, "gru_persistent_fwd": 41.0e6,
-                   "gru_persistent_bwd": 113.3e6}      # profiles/r01i_ncu_full.md
-    kernels = {}
-    for name, v in classes.items():
-        ms = v["ms_per_step"]
+    # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of a committed `ncu --set full` capture
+    traffic, traffic_src = {}, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, NCU_TRAFFIC_FILE)))
+        traffic, traffic_src = tj.get("kernels", {}), tj.get("source")
+    except (OSError, ValueError):
+        pass
+    # one entry per KERNEL LAUNCH of a step (launch i of step 0 averaged with launch i of step 1): every GEMM
+    # instantiation is its own entry with its own executed FLOPs
+    per_step = len(launch_list) // prof_steps if prof_steps and len(launch_list) % prof_steps == 0 else 0
+    kernels, n_gemm = {}, 0
+    for i in range(per_step):
+        name = launch_list[i][0]
+        ms = sum(launch_list[i + k * per_step][1] for k in range(prof_steps)) / prof_steps
+        work = launch_list[i][2]
         if name == "gemm_tcgen05":
-            ach = fwd_bwd_gflop(d) / 1e3 / (ms / 1e3)
-            kernels[name] = {"bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s",
-                             "frac": ach / tensor_peak, "ms_per_step": ms, "launches_per_step": v["launches_per_step"],
-                             "peak_source": peak_src,
-                             "note": "all GEMM launches of a step vs the algorithmic %.1f GFLOP (the fused-CE backward "
-                                     "re-computes the 90 GFLOP vocabulary product: executed %.1f GFLOP)" % (
-                                         fwd_bwd_gflop(d), prof["gemm_tcgen05"][2] / prof_steps / 1e9)}
+            ach = work / 1e12 / (ms / 1e3) if ms > 0 else 0.0
+            kernels["gemm_tcgen05[%02d] %.2f GFLOP" % (n_gemm, work / 1e9)] = {
+                "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak,
+                "ms_per_launch": ms, "executed_gflop": work / 1e9, "peak_source": peak_src, "traffic": None}
+            n_gemm += 1
         elif name in alg_bytes:
-            per_launch_ms = ms / max(v["launches_per_step"], 1)
-            ach = alg_bytes[name] / 1e9 / (per_launch_ms / 1e3)
+            ach = alg_bytes[name] / 1e9 / (ms / 1e3)
             kernels[name] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                             "ms_per_launch": per_launch_ms, "algorithmic_bytes_per_launch": alg_bytes[name],
-                             "traffic": ncu_traffic.get(name), "peak_source": hbm_src}
-    dominant = max((k for k in kernels), key=lambda k: classes[k]["ms_per_step"])
-    roofline = dict(kernels[dominant])
+                             "ms_per_launch": ms, "algorithmic_bytes_per_launch": alg_bytes[name],
+                             "traffic": traffic.get(name), "traffic_source": traffic_src if name in traffic else None,
+                             "peak_source": hbm_src}
+    # `roofline` = the single kernel launch with the largest duration in a step
+    dominant = max(kernels, key=lambda k: kernels[k]["ms_per_launch"]) if kernels else None
+    roofline = dict(kernels[dominant]) if dominant else {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s",
+                                                         "frac": None, "traffic": None}
     roofline["kernel"] = dominant
-    roofline.setdefault("traffic", None)
     roofline["all_kernels"] = kernels
     roofline["class_ms_per_step"] = classes
     roofline["split_planes"] = planes
+    gemm_ms = classes.get("gemm_tcgen05", {}).get("ms_per_step", 0.0)
+    roofline["gemm_class"] = {"ms_per_step": gemm_ms, "algorithmic_gflop": fwd_bwd_gflop(d),
+                              "executed_gflop": prof["gemm_tcgen05"][2] / prof_steps / 1e9 if "gemm_tcgen05" in prof else None,
+                              "tflops_algorithmic": fwd_bwd_gflop(d) / gemm_ms if gemm_ms else None,
+                              "frac": fwd_bwd_gflop(d) / gemm_ms / tensor_peak if gemm_ms else None}
+    # the number that matters for the whole step: algorithmic FLOPs / measured step time / sustained tensor peak
+    roofline["step_frac"] = fwd_bwd_gflop(d) / ms_step / tensor_peak
+    roofline["step_tflops"] = fwd_bwd_gflop(d) / ms_step
 
     # second half of BASELINE.json's metric: greedy captions/sec (eval branch, model/S2VTAttModel.py:172-191) at the
     # same per-GPU batch, fp32-equivalent bf16x3 arithmetic (token ids bit-exact vs the fp32 reference), CUDA-graph
@@ -344,8 +494,16 @@ def run_ours(args):
             gg(vid)
         g_iters = 10
         ms_g = timed(lambda: gg(vid), g_iters) / g_iters
+        # one decoding step streams the bf16 weights once, whatever the batch: W_v + decoder W_ih / W_hh / W_q
+        w_step = (Vc * H + 3 * H * (H + E) + 3 * H * H + H * H) * 2
+        g_bytes = L * w_step + (3 * H * V + 3 * H * H + H * H) * 2          # + encoder / key weights once per batch
+        g_ach = g_bytes / 1e9 / (ms_g / 1e3)
         greedy = {"value": B / (ms_g / 1e3), "unit": "captions/s", "batch": B, "ms_per_batch": ms_g, "max_len": L,
-                  "arithmetic": "bf16x3 (fp32-equivalent; ids bit-exact vs the reference)", "step": "CUDA graph"}
+                  "arithmetic": "bf16x3 (fp32-equivalent; ids bit-exact vs the reference)", "step": "CUDA graph",
+                  "roofline": {"bound": "hbm", "achieved": g_ach, "peak": hbm_peak, "unit": "GB/s", "frac": g_ach / hbm_peak,
+                               "algorithmic_bytes_per_batch": g_bytes, "traffic": None,
+                               "note": "whole decode of one batch (40 encoder + 30 decoder steps, many launches) vs the "
+                                       "bf16 weight bytes SURVEY 8(d) counts; B-independent"}}
         model.train()
         del gg
 
@@ -365,25 +523,34 @@ def run_ours(args):
         del g2, opt
 
     cpu = None
+    eager = None
     if world == 1 and not args.no_cpu_baseline:
-        vps, dt = cpu_port_videos_per_sec(3, 1)
-        cpu = {"value": vps, "unit": "videos/s", "cores": cpu_cores(), "kind": "port",
-               "sample": "%d of the %d videos of one batch per step, 3 steps (numpy fp32 oracle port, threaded BLAS)" % (
-                   CPU_SAMPLE_VIDEOS, B)}
+        from oracle import reference_runner as R
+        if R.available():
+            vps, dt, threads = cpu_reference_videos_per_sec(2, 1, args.dropout)
+            cpu = {"value": vps, "unit": "videos/s", "cores": threads, "kind": "reference",
+                   "sample": "2 steps (after 1 warm-up) of the whole %d-video batch: unmodified reference modules "
+                             "(oracle/_ref), run_iter + loss.backward(), torch fp32 CPU, %d threads" % (B, threads)}
+        else:
+            vps, dt = cpu_port_videos_per_sec(3, 1)
+            cpu = {"value": vps, "unit": "videos/s", "cores": cpu_cores(), "kind": "port",
+                   "sample": "%d of the %d videos of one batch per step, 3 steps (numpy fp32 oracle port, threaded BLAS; "
+                             "oracle/_ref absent)" % (CPU_SAMPLE_VIDEOS, B)}
+    if world == 1 and not args.no_eager:
+        del graphed
+        torch.cuda.empty_cache()
+        eager = eager_b200_reference(args.dropout)
 
     out = {
         "metric": METRIC, "value": B * world / (ms_step / 1e3), "unit": "videos/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else args.precision,
         "data": "synthetic",
-        "config": dict(workload=WORKLOAD, per_gpu_batch=B, global_batch=B * world, parallelism="dp%d" % world,
-                       precision=args.precision, dropout_p=args.dropout,
-                       step="CUDA graph of one fwd+bwd (side lanes on; roofline pass times each kernel alone, lanes off)",
-                       l2="per-step working set (inputs 42 MB + fp32 weights 101 MB + activations > 1 GB) exceeds "
-                          "the 126 MB L2; no explicit flush", **{k: v for k, v in d.items() if k != "B"}),
+        "config": make_config(world, args.precision, args.dropout),
         "e2e": {"value": B * world / (ms_e2e / 1e3), "unit": "videos/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "greedy": greedy, "with_optimizer": with_opt,
+        "reference_eager_b200": eager, "dp_check": dp_check,
     }
     print(json.dumps(out), flush=True)
     _finish_ranks(world)
@@ -400,10 +567,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-greedy", action="store_true")
     ap.add_argument("--no-optimizer", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="skip timing the reference modules in PyTorch eager on the GPU")
     ap.add_argument("--nccl-ctas", type=int, default=16)
     ap.add_argument("--nccl-tail-ctas", type=int, default=64)
     args = ap.parse_args()
     if args.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1; the OpenMP / MKL runtimes read their environment when torch is imported
+        os.environ["OMP_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = str(cpu_cores())
         run_reference(args)
     else:
         run_ours(args)

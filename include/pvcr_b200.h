@@ -41,6 +41,9 @@ int pvcr_prof_read(uint64_t* launches, double* ms, double* work);
 /* Timeline of the event-timed launches since the last reset (host enqueue order): class, start and end in ms relative
  * to the first launch; returns the number of entries written (<= cap) or a negative error code. */
 int pvcr_prof_timeline(int* cls, float* t0_ms, float* t1_ms, int cap);
+/* Every event-timed launch since the last reset (host enqueue order): class, duration, work (executed tensor-core FLOPs
+ * of a GEMM launch, else 0); returns the number of entries written (<= cap) or a negative error code. */
+int pvcr_prof_launch_list(int* cls, float* ms, double* work, int cap);
 
 /* Registers a device-resident uint64 counter that every dropout / Gumbel draw mixes into its seed when the kernel
  * runs (NULL switches it off).  CUDA-graph replays otherwise repeat the seed baked in at capture; with the counter
@@ -240,7 +243,8 @@ int pvcr_s2vt_decode_steps(const PvcrDims* d, const PvcrS2vtParams* p, const flo
  * argmax (train_utils.py:37-71, train.py:38).
  *   hs [B*L,H] (row b*L+l); target [B*L] int64; s_len [B] int64 (1 <= s_len <= L).
  *   loss3 [3] = { mean_b( sum_l nll*mask / s_len ), #correct under mask, #mask };  pred [B*L] int64 argmax
- *   (first max index);  lse [B*L] log-sum-exp per token.  logits_out (optional, ld elements) receives the
+ *   (first max index);  lse [B*L] log-sum-exp per token;  token_nll [B*L] (optional) the unmasked per-token loss
+ *   lse - logit[target], i.e. criterion(logits, target) of train_utils.py:47-48.  logits_out (optional, ld elements) receives the
  *   fp32 logits for callers that need the reference's logits tensor; pass target = NULL to only project.
  * With nsplit = 1 and logits_out = NULL the logits are never materialised: the GEMM epilogue reduces them per tile
  * (forward) and re-creates them to emit bf16 d logits (backward).
@@ -253,13 +257,66 @@ int pvcr_vocab_ce_prepare(const float* out_w, int B, int L, int H, int Vc, int n
                           size_t workspace_bytes, void* stream);
 int pvcr_vocab_ce_fwd(const float* hs, const float* out_w, const float* out_b, const int64_t* target,
                       const int64_t* s_len, int B, int L, int H, int Vc, int nsplit, float dropout_p, uint64_t seed,
-                      float* loss3, int64_t* pred, float* lse, float* logits_out, int64_t ld_logits_out,
-                      void* workspace, size_t workspace_bytes, void* stream);
+                      float* loss3, int64_t* pred, float* lse, float* token_nll, float* logits_out,
+                      int64_t ld_logits_out, void* workspace, size_t workspace_bytes, void* stream);
 int pvcr_vocab_ce_bwd(const float* hs, const float* out_w, const float* out_b, const int64_t* target,
                       const int64_t* s_len, int B, int L,
                       int H, int Vc, int nsplit, float dropout_p, uint64_t seed, const float* gscale, float* d_hs,
                       float* d_out_w, float* d_out_b, float* lse, int64_t* pred, void* workspace,
                       size_t workspace_bytes, void* stream);
+
+/* The decoder halves on caller-given encoder outputs -- `decode(encoder_outs, encoder_final, s)` of both caption nets
+ * (model/S2VTAttModel.py:231-243, model/S2VTModel.py:88-145), which is how the reference's SpatialNet drives a caption
+ * net after its own per-frame encoder loop (model/SpatialNet.py:140).  enc_outs / out1 are [B,N,H] (row b*N + n; the
+ * Python wrapper transposes the reference's [N,B,H]), enc_final / state1 [B,H]; hs [B,L,H] feeds pvcr_vocab_ce_fwd as
+ * usual.  Workspaces: pvcr_s2vtatt_workspace(d, 0) / pvcr_s2vt_workspace(d, 0) with any d->V >= 1.  The _bwd calls need
+ * the workspace of the matching _fwd untouched; they write every gradient of `grads` except the encoder-GRU entries
+ * (enc_* resp. rnn1_w_ih), which may be NULL, plus the gradients on the given encoder outputs and state. */
+int pvcr_s2vtatt_decode_fwd(const PvcrDims* d, const PvcrS2vtAttParams* p, const float* enc_outs, const float* enc_final,
+                            const int64_t* s_in, float* hs, float* alphas, void* workspace, size_t workspace_bytes,
+                            void* stream);
+int pvcr_s2vtatt_decode_bwd(const PvcrDims* d, const PvcrS2vtAttParams* p, const int64_t* s_in, const float* hs,
+                            const float* d_hs, PvcrS2vtAttGrads* grads, float* d_enc_outs, float* d_enc_final,
+                            void* workspace, size_t workspace_bytes, void* stream);
+int pvcr_s2vt_decode_fwd(const PvcrDims* d, const PvcrS2vtParams* p, const float* out1, const float* state1,
+                         const int64_t* s_in, float* hs, void* workspace, size_t workspace_bytes, void* stream);
+int pvcr_s2vt_decode_bwd(const PvcrDims* d, const PvcrS2vtParams* p, const int64_t* s_in, float* hs, const float* d_hs,
+                         PvcrS2vtGrads* grads, float* d_out1, float* d_state1, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* decode() in eval mode: fixed-length greedy decoding from caller-given encoder outputs (the eval branches of
+ * model/S2VTAttModel.py:172-191 and model/S2VTModel.py:147-177 reached through `decode`).  Workspaces:
+ * pvcr_s2vtatt_greedy_workspace / pvcr_s2vt_decode_steps_workspace; outputs as pvcr_s2vtatt_greedy / pvcr_s2vt_decode_steps. */
+int pvcr_s2vtatt_decode_greedy(const PvcrDims* d, const PvcrS2vtAttParams* p, const float* enc_outs, const float* enc_final,
+                               int64_t sos_id, int64_t* ids, float* logits, float* alphas, void* workspace,
+                               size_t workspace_bytes, void* stream);
+int pvcr_s2vt_decode_greedy(const PvcrDims* d, const PvcrS2vtParams* p, const float* out1, const float* state1,
+                            int64_t sos_id, int64_t* ids, float* logits, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
+/* One GRU step  h' = GRU(x, h_prev)  -- `encode_step(vid_feat, rnn_state)` of both caption nets
+ * (model/S2VTAttModel.py:63-78,219-229, model/S2VTModel.py:57-72: `self.rnn(vid_feat.unsqueeze(0), rnn_state)`), the
+ * call SpatialNet makes once per frame (model/SpatialNet.py:127).  x [B,V], h_prev [B,H] or NULL (zeros), torch.nn.GRU
+ * parameter layout (gate order r,z,n).  saved [4*B*H] receives r, z, n, W_hn h + b_hn for the backward.
+ * _bwd: d_x / d_h_prev overwritten (NULL ok); d_w_ih [3H,V], d_w_hh [3H,H], d_b_ih, d_b_hh [3H] overwritten, or added
+ * to when accumulate != 0 (a caller looping over frames accumulates the parameter gradients across its steps). */
+size_t pvcr_gru_step_workspace(int B, int V, int H, int nsplit);
+int pvcr_gru_step_fwd(const float* x, const float* h_prev, const float* w_ih, const float* w_hh, const float* b_ih,
+                      const float* b_hh, int B, int V, int H, int nsplit, float* h_out, float* saved, void* workspace,
+                      size_t workspace_bytes, void* stream);
+int pvcr_gru_step_bwd(const float* d_h, const float* x, const float* h_prev, const float* w_ih, const float* w_hh,
+                      const float* saved, int B, int V, int H, int nsplit, float* d_x, float* d_h_prev, float* d_w_ih,
+                      float* d_w_hh, float* d_b_ih, float* d_b_hh, int accumulate, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* y[i] = x[i] * mask_i / (1 - p): the mask pvcr_vocab_ce_fwd / _bwd draw for Dropout(hs) under (dropout_p, seed), i the
+ * flat index into the [B*L, H] hidden-state matrix (in place allowed).  Replaces nn.Dropout of `pred_linear` / `linear`
+ * (model/S2VTAttModel.py:121-122, model/S2VTModel.py:47-49) for callers that take the materialised-logits route, and lets
+ * the parity tests hand the very same mask to the reference. */
+int pvcr_out_dropout_apply(const float* x, float* y, int64_t n, float dropout_p, uint64_t seed, void* stream);
+/* Test hook: minmax[0] / minmax[1] = smallest / largest uniform the in-kernel Philox generator (dropout masks, Gumbel
+ * noise of F.gumbel_softmax's exponential_(), model/RationaleNet.py:49) produces over indices [idx0, idx0 + n). */
+int pvcr_debug_philox_minmax(uint64_t seed, uint64_t idx0, uint64_t n, float* minmax, void* stream);
 
 /* The loss contract on a materialised logits tensor (callers that use the reference's module API and then its
  * train_utils functions).  pvcr_masked_ce: calc_masked_loss / calc_masked_accuracy / argmax (train_utils.py:37-71,

@@ -262,9 +262,11 @@ def _dec_in_words(s, sos_id):
     return np.concatenate([np.full((B, 1), sos_id, s.dtype), s[:, :L - 1]], axis=1)
 
 
-def s2vtatt_decode_train(p, enc, h0, s, sos_id, max_len):
+def s2vtatt_decode_train(p, enc, h0, s, sos_id, max_len, hs_scale=None):
     """Decoder.forward in training mode (always teacher-forced, S2VTAttModel.py:188-189).
-    enc [B,N,H], h0 [B,H], s [B,L].  Returns logits [B,L,Vc] and a cache."""
+    enc [B,N,H], h0 [B,H], s [B,L].  Returns logits [B,L,Vc] and a cache.
+    hs_scale [B,L,H] (optional): the Dropout of `pred_linear` (S2VTAttModel.py:121-122,145) with a GIVEN mask, as
+    mask / (1 - p) -- what nn.Dropout multiplies the GRU output of step i by before the Linear."""
     B, N, H = enc.shape
     L = max_len
     Wq = p["decoder.attention.query_layer.weight"]; Wk = p["decoder.attention.key_layer.weight"]
@@ -291,8 +293,9 @@ def s2vtatt_decode_train(p, enc, h0, s, sos_id, max_len):
         steps.append(dict(hprev=h, ctx=ctx, a=a, e=e, r=r, z=z, n=n, ghn=gh[:, 2 * H:]))
         h = (1.0 - z) * n + z * h
         hs[:, i] = h
-    logits = _mm(hs.reshape(B * L, H), p["decoder.pred_linear.1.weight"].T) + p["decoder.pred_linear.1.bias"]
-    cache = dict(steps=steps, hs=hs, pk=pk, enc=enc, erow=erow, s_in=s_in, h0=h0)
+    hs_out = hs if hs_scale is None else hs * hs_scale
+    logits = _mm(hs_out.reshape(B * L, H), p["decoder.pred_linear.1.weight"].T) + p["decoder.pred_linear.1.bias"]
+    cache = dict(steps=steps, hs=hs, hs_out=hs_out, hs_scale=hs_scale, pk=pk, enc=enc, erow=erow, s_in=s_in, h0=h0)
     return logits.reshape(B, L, -1), cache
 
 
@@ -309,9 +312,11 @@ def s2vtatt_decode_bwd(p, cache, dlogits):
     Vc = Wv.shape[0]
     dl = dlogits.reshape(B * L, Vc)
     g = {}
-    g["decoder.pred_linear.1.weight"] = _mm(dl.T, hs.reshape(B * L, H))
+    g["decoder.pred_linear.1.weight"] = _mm(dl.T, cache.get("hs_out", hs).reshape(B * L, H))
     g["decoder.pred_linear.1.bias"] = _q(dl).sum(axis=0)
     dhs = _mm(dl, Wv).reshape(B, L, H)
+    if cache.get("hs_scale") is not None:
+        dhs = dhs * cache["hs_scale"]
     dWq = np.zeros_like(Wq); dv = np.zeros_like(v); dWc = np.zeros_like(Wc); dW_hh = np.zeros_like(W_hh)
     db_hh = np.zeros(3 * H, enc.dtype)
     dgi_all = np.empty((B, L, 3 * H), enc.dtype)
@@ -363,10 +368,10 @@ def s2vtatt_encode_bwd(p, vid, enc_cache, denc, dh_final, need_dvid=False):
     return g, dvid
 
 
-def s2vtatt_forward_train(p, vid, s, sos_id, max_len):
+def s2vtatt_forward_train(p, vid, s, sos_id, max_len, hs_scale=None):
     """S2VTAttModel.forward (training).  Returns logits [B,L,Vc], cache (cache['alphas'] [L,B,N])."""
     enc, ec = s2vtatt_encode(p, vid)
-    logits, dc = s2vtatt_decode_train(p, enc, enc[:, -1], s, sos_id, max_len)
+    logits, dc = s2vtatt_decode_train(p, enc, enc[:, -1], s, sos_id, max_len, hs_scale=hs_scale)
     dc["alphas"] = np.stack([st["a"] for st in dc["steps"]])
     return logits, dict(vid=vid, enc_cache=ec, dec_cache=dc, alphas=dc["alphas"])
 
@@ -566,12 +571,12 @@ def generator_bwd(p, cache, dsel, dprobs):
 # ----------------------------------------------------------------------------------------
 # whole training iterations (train.py:32-44, train_rationale.py:30-44 run_iter + backward)
 # ----------------------------------------------------------------------------------------
-def train_iter_s2vtatt(p, vid, s, s_len, sos_id, max_len):
-    logits, cache = s2vtatt_forward_train(p, vid, s, sos_id, max_len)
-    loss, dlogits, _ = masked_loss(logits, s, s_len)
+def train_iter_s2vtatt(p, vid, s, s_len, sos_id, max_len, hs_scale=None):
+    logits, cache = s2vtatt_forward_train(p, vid, s, sos_id, max_len, hs_scale=hs_scale)
+    loss, dlogits, nll = masked_loss(logits, s, s_len)
     acc, pred = masked_accuracy(logits, s, s_len)
     grads, _ = s2vtatt_backward(p, cache, dlogits)
-    return dict(loss=loss, acc=acc, pred=pred, logits=logits, alphas=cache["alphas"], grads=grads)
+    return dict(loss=loss, acc=acc, pred=pred, logits=logits, alphas=cache["alphas"], grads=grads, token_nll=nll)
 
 
 def train_iter_s2vt(p, vid, s, s_len, sos_id, max_len, teacher=None):

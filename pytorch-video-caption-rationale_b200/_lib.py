@@ -78,6 +78,7 @@ SIGNATURES = {
     "pvcr_prof_reset": (None, []),
     "pvcr_prof_read": (c_int, [P(c_u64), P(ctypes.c_double), P(ctypes.c_double)]),
     "pvcr_prof_timeline": (c_int, [P(c_int), P(ctypes.c_float), P(ctypes.c_float), c_int]),
+    "pvcr_prof_launch_list": (c_int, [P(c_int), P(ctypes.c_float), P(ctypes.c_double), c_int]),
     "pvcr_linear_fwd_workspace": (c_size, [c_int, c_int, c_int, c_int]),
     "pvcr_linear_fwd": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_size,
                                 c_vp]),
@@ -119,7 +120,23 @@ SIGNATURES = {
     "pvcr_vocab_ce_workspace": (c_size, [c_int, c_int, c_int, c_int, c_int, c_f]),
     "pvcr_vocab_ce_prepare": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_size, c_vp]),
     "pvcr_vocab_ce_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_u64, c_vp,
-                                  c_vp, c_vp, c_vp, c_i64, c_vp, c_size, c_vp]),
+                                  c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_size, c_vp]),
+    "pvcr_s2vtatt_decode_fwd": (c_int, [P(PvcrDims), P(PvcrS2vtAttParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
+    "pvcr_s2vtatt_decode_bwd": (c_int, [P(PvcrDims), P(PvcrS2vtAttParams), c_vp, c_vp, c_vp, P(PvcrS2vtAttGrads), c_vp, c_vp,
+                                        c_vp, c_size, c_vp]),
+    "pvcr_s2vt_decode_fwd": (c_int, [P(PvcrDims), P(PvcrS2vtParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
+    "pvcr_s2vt_decode_bwd": (c_int, [P(PvcrDims), P(PvcrS2vtParams), c_vp, c_vp, c_vp, P(PvcrS2vtGrads), c_vp, c_vp, c_vp,
+                                     c_size, c_vp]),
+    "pvcr_s2vtatt_decode_greedy": (c_int, [P(PvcrDims), P(PvcrS2vtAttParams), c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
+                                           c_size, c_vp]),
+    "pvcr_s2vt_decode_greedy": (c_int, [P(PvcrDims), P(PvcrS2vtParams), c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_size, c_vp]),
+    "pvcr_gru_step_workspace": (c_size, [c_int, c_int, c_int, c_int]),
+    "pvcr_gru_step_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_size,
+                                  c_vp]),
+    "pvcr_gru_step_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
+                                  c_vp, c_vp, c_int, c_vp, c_size, c_vp]),
+    "pvcr_out_dropout_apply": (c_int, [c_vp, c_vp, c_i64, c_f, c_u64, c_vp]),
+    "pvcr_debug_philox_minmax": (c_int, [c_u64, c_u64, c_u64, c_vp, c_vp]),
     "pvcr_vocab_ce_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_u64, c_vp, c_vp,
                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
 }
@@ -143,6 +160,18 @@ def ptr(t):
 def stream_ptr():
     import torch
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def prof_launch_list(cap=4096):
+    """[(class name, ms, work)] for every event-timed launch since the last pvcr_prof_reset(), in enqueue order."""
+    L = lib()
+    cls = (c_int * cap)()
+    ms = (ctypes.c_float * cap)()
+    work = (ctypes.c_double * cap)()
+    n = L.pvcr_prof_launch_list(cls, ms, work, cap)
+    if n < 0:
+        check(n, "pvcr_prof_launch_list")
+    return [(L.pvcr_prof_class_name(cls[i]).decode(), float(ms[i]), float(work[i])) for i in range(n)]
 
 
 def prof_read():

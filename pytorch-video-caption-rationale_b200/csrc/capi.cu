@@ -39,7 +39,28 @@ size_t s2vtatt_beam_workspace(const PvcrDims& d, int K);
 int s2vtatt_beam(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid, const float* frame_scale, long long sos_id,
                  int K, long long* ids, float* scores, void* ws, size_t ws_bytes, cudaStream_t st);
 int vocab_ce_fwd(const float*, const float*, const float*, const long long*, const long long*, int, int, int, int, int,
-                 float, unsigned long long, float*, long long*, float*, float*, long long, void*, size_t, cudaStream_t);
+                 float, unsigned long long, float*, long long*, float*, float*, float*, long long, void*, size_t,
+                 cudaStream_t);
+int s2vtatt_decode_fwd(const PvcrDims&, const PvcrS2vtAttParams&, const float*, const float*, const long long*, float*,
+                       float*, void*, size_t, cudaStream_t);
+int s2vtatt_decode_bwd(const PvcrDims&, const PvcrS2vtAttParams&, const long long*, const float*, const float*,
+                       PvcrS2vtAttGrads&, float*, float*, void*, size_t, cudaStream_t);
+int s2vt_decode_fwd(const PvcrDims&, const PvcrS2vtParams&, const float*, const float*, const long long*, float*, void*,
+                    size_t, cudaStream_t);
+int s2vt_decode_bwd(const PvcrDims&, const PvcrS2vtParams&, const long long*, const float*, float*, PvcrS2vtGrads&, float*,
+                    float*, void*, size_t, cudaStream_t);
+int s2vtatt_greedy_impl(const PvcrDims&, const PvcrS2vtAttParams&, const float*, const float*, const float*, const float*,
+                        long long, long long*, float*, float*, void*, size_t, cudaStream_t);
+int s2vt_decode_steps_impl(const PvcrDims&, const PvcrS2vtParams&, const float*, const float*, const float*, const float*,
+                           long long, const long long*, const int*, float, long long*, long long*, float*, void*, size_t,
+                           cudaStream_t);
+size_t gru_step_workspace(int B, int V, int H, int nsplit);
+int gru_step_fwd(const float*, const float*, const float*, const float*, const float*, const float*, int, int, int, int,
+                 float*, float*, void*, size_t, cudaStream_t);
+int gru_step_bwd(const float*, const float*, const float*, const float*, const float*, const float*, int, int, int, int,
+                 float*, float*, float*, float*, float*, float*, int, void*, size_t, cudaStream_t);
+int out_dropout_apply(const float*, float*, long long, float, unsigned long long, cudaStream_t);
+int philox_minmax(unsigned long long seed, unsigned long long idx0, unsigned long long n, float* minmax, cudaStream_t st);
 int vocab_ce_bwd(const float*, const float*, const float*, const long long*, const long long*, int, int, int, int, int, float,
                  unsigned long long, const float*, float*, float*, float*, float*, long long*, void*, size_t,
                  cudaStream_t);
@@ -164,11 +185,71 @@ int pvcr_vocab_ce_prepare(const float* out_w, int B, int L, int H, int Vc, int n
 }
 int pvcr_vocab_ce_fwd(const float* hs, const float* out_w, const float* out_b, const int64_t* target,
                       const int64_t* s_len, int B, int L, int H, int Vc, int nsplit, float dropout_p, uint64_t seed,
-                      float* loss3, int64_t* pred, float* lse, float* logits_out, int64_t ld_logits_out,
-                      void* workspace, size_t workspace_bytes, void* stream) {
+                      float* loss3, int64_t* pred, float* lse, float* token_nll, float* logits_out,
+                      int64_t ld_logits_out, void* workspace, size_t workspace_bytes, void* stream) {
   return vocab_ce_fwd(hs, out_w, out_b, (const long long*)target, (const long long*)s_len, B, L, H, Vc, nsplit,
-                      dropout_p, seed, loss3, (long long*)pred, lse, logits_out, ld_logits_out, workspace,
+                      dropout_p, seed, loss3, (long long*)pred, lse, token_nll, logits_out, ld_logits_out, workspace,
                       workspace_bytes, (cudaStream_t)stream);
+}
+int pvcr_s2vtatt_decode_fwd(const PvcrDims* d, const PvcrS2vtAttParams* p, const float* enc_outs, const float* enc_final,
+                            const int64_t* s_in, float* hs, float* alphas, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  if (!d || !p) { set_last_error("pvcr_s2vtatt_decode_fwd: null dims / params"); return PVCR_ERR_ARG; }
+  return s2vtatt_decode_fwd(*d, *p, enc_outs, enc_final, (const long long*)s_in, hs, alphas, workspace, workspace_bytes,
+                            (cudaStream_t)stream);
+}
+int pvcr_s2vtatt_decode_bwd(const PvcrDims* d, const PvcrS2vtAttParams* p, const int64_t* s_in, const float* hs,
+                            const float* d_hs, PvcrS2vtAttGrads* grads, float* d_enc_outs, float* d_enc_final,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  if (!d || !p || !grads) { set_last_error("pvcr_s2vtatt_decode_bwd: null dims / params / grads"); return PVCR_ERR_ARG; }
+  return s2vtatt_decode_bwd(*d, *p, (const long long*)s_in, d_hs, hs, *grads, d_enc_outs, d_enc_final, workspace,
+                            workspace_bytes, (cudaStream_t)stream);
+}
+int pvcr_s2vt_decode_fwd(const PvcrDims* d, const PvcrS2vtParams* p, const float* out1, const float* state1,
+                         const int64_t* s_in, float* hs, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!d || !p) { set_last_error("pvcr_s2vt_decode_fwd: null dims / params"); return PVCR_ERR_ARG; }
+  return s2vt_decode_fwd(*d, *p, out1, state1, (const long long*)s_in, hs, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int pvcr_s2vt_decode_bwd(const PvcrDims* d, const PvcrS2vtParams* p, const int64_t* s_in, float* hs, const float* d_hs,
+                         PvcrS2vtGrads* grads, float* d_out1, float* d_state1, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  if (!d || !p || !grads) { set_last_error("pvcr_s2vt_decode_bwd: null dims / params / grads"); return PVCR_ERR_ARG; }
+  return s2vt_decode_bwd(*d, *p, (const long long*)s_in, d_hs, hs, *grads, d_out1, d_state1, workspace, workspace_bytes,
+                         (cudaStream_t)stream);
+}
+int pvcr_s2vtatt_decode_greedy(const PvcrDims* d, const PvcrS2vtAttParams* p, const float* enc_outs, const float* enc_final,
+                               int64_t sos_id, int64_t* ids, float* logits, float* alphas, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  if (!d || !p || !enc_outs || !enc_final) { set_last_error("pvcr_s2vtatt_decode_greedy: null argument"); return PVCR_ERR_ARG; }
+  return s2vtatt_greedy_impl(*d, *p, nullptr, nullptr, enc_outs, enc_final, (long long)sos_id, (long long*)ids, logits,
+                             alphas, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int pvcr_s2vt_decode_greedy(const PvcrDims* d, const PvcrS2vtParams* p, const float* out1, const float* state1,
+                            int64_t sos_id, int64_t* ids, float* logits, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  if (!d || !p || !out1 || !state1) { set_last_error("pvcr_s2vt_decode_greedy: null argument"); return PVCR_ERR_ARG; }
+  return s2vt_decode_steps_impl(*d, *p, nullptr, nullptr, out1, state1, (long long)sos_id, nullptr, nullptr, 0.f,
+                                (long long*)ids, nullptr, logits, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+size_t pvcr_gru_step_workspace(int B, int V, int H, int nsplit) { return gru_step_workspace(B, V, H, nsplit); }
+int pvcr_gru_step_fwd(const float* x, const float* h_prev, const float* w_ih, const float* w_hh, const float* b_ih,
+                      const float* b_hh, int B, int V, int H, int nsplit, float* h_out, float* saved, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  return gru_step_fwd(x, h_prev, w_ih, w_hh, b_ih, b_hh, B, V, H, nsplit, h_out, saved, workspace, workspace_bytes,
+                      (cudaStream_t)stream);
+}
+int pvcr_gru_step_bwd(const float* d_h, const float* x, const float* h_prev, const float* w_ih, const float* w_hh,
+                      const float* saved, int B, int V, int H, int nsplit, float* d_x, float* d_h_prev, float* d_w_ih,
+                      float* d_w_hh, float* d_b_ih, float* d_b_hh, int accumulate, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  return gru_step_bwd(d_h, x, h_prev, w_ih, w_hh, saved, B, V, H, nsplit, d_x, d_h_prev, d_w_ih, d_w_hh, d_b_ih, d_b_hh,
+                      accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int pvcr_out_dropout_apply(const float* x, float* y, int64_t n, float dropout_p, uint64_t seed, void* stream) {
+  return out_dropout_apply(x, y, (long long)n, dropout_p, seed, (cudaStream_t)stream);
+}
+int pvcr_debug_philox_minmax(uint64_t seed, uint64_t idx0, uint64_t n, float* minmax, void* stream) {
+  return philox_minmax(seed, idx0, n, minmax, (cudaStream_t)stream);
 }
 int pvcr_vocab_ce_bwd(const float* hs, const float* out_w, const float* out_b, const int64_t* target,
                       const int64_t* s_len, int B, int L,

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
       if (lb < bs) {
         const int j = j0 + jj, b = b0 + lb;
         bhr[k] = p.b_hh[j]; bhz[k] = p.b_hh[H + j]; bhn[k] = p.b_hh[2 * H + j];
-        hreg[k] = p.enc[((long long)b * N + (N - 1)) * H + j];
+        hreg[k] = p.h0[(long long)b * p.h0_ld + j];
       }
     }
   }
@@ -142,8 +142,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
       load_operand_rows_async(sX, bsp, 0, p.hs_a + (long long)(i - 1) * p.hs_a_ld, (long long)L * p.hs_a_ld, b0, bsp,
                               b0 + bs, H);
     } else {
-      load_operand_rows_async(sX, bsp, 0, p.enc_a + (long long)(N - 1) * p.enc_ld, (long long)N * p.enc_ld, b0, bsp,
-                              b0 + bs, H);
+      load_operand_rows_async(sX, bsp, 0, p.h0_a, p.h0_a_ld, b0, bsp, b0 + bs, H);
     }
     cp_async_commit();
     cp_async_wait<0>();
@@ -453,7 +452,7 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
           l2_prefetch(p.d_hs + ((long long)b * L + i) * H + j);
           const long long o = ((long long)i * B + b) * H + j;
           l2_prefetch(p.r + o); l2_prefetch(p.z + o); l2_prefetch(p.n + o); l2_prefetch(p.ghn + o);
-          l2_prefetch(i > 0 ? p.hs + ((long long)b * L + (i - 1)) * H + j : p.enc + ((long long)b * N + (N - 1)) * H + j);
+          l2_prefetch(i > 0 ? p.hs + ((long long)b * L + (i - 1)) * H + j : p.h0 + (long long)b * p.h0_ld + j);
         }
       }
     }
@@ -474,7 +473,7 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
           const float dh = dhc[k] + p.d_hs[((long long)b * L + i) * H + j];
           const long long o = ((long long)i * B + b) * H + j;
           const float r = p.r[o], z = p.z[o], n = p.n[o], ghn = p.ghn[o];
-          const float hp = i > 0 ? p.hs[((long long)b * L + (i - 1)) * H + j] : p.enc[((long long)b * N + (N - 1)) * H + j];
+          const float hp = i > 0 ? p.hs[((long long)b * L + (i - 1)) * H + j] : p.h0[(long long)b * p.h0_ld + j];
           const float dn = dh * (1.f - z), dz = dh * (hp - n);
           const float dnp = dn * (1.f - n * n);
           const float dzp = dz * z * (1.f - z);

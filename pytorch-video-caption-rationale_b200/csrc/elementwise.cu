@@ -24,7 +24,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 __device__ __forceinline__ float philox_uniform(unsigned long long seed, unsigned long long idx) {
   const uint4 r = philox4x32_10(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), 0u, 0u),
                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  return ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);     // (0,1)
+  // 23 random bits + 0.5: the largest value is (2^23 - 0.5) / 2^23 = 1 - 2^-24, exactly representable in fp32, the
+  // smallest 2^-24 -- strictly inside (0,1), so -log(u) is finite and > 0 (as torch's exponential_() guarantees).
+  // (24 bits + 0.5 would round 16777215.5 up to 2^24 and return exactly 1.0 once in 2^24 draws.)
+  return ((float)(r.x >> 9) + 0.5f) * (1.0f / 8388608.0f);
 }
 __device__ __forceinline__ unsigned long long stepped_seed(unsigned long long seed, const unsigned long long* step) {
   return step ? seed + __ldg(step) * 0x9E3779B97F4A7C15ull : seed;
@@ -32,6 +35,33 @@ __device__ __forceinline__ unsigned long long stepped_seed(unsigned long long se
 __device__ __forceinline__ float dropout_scale(const Dropout& d, unsigned long long idx) {
   if (d.p <= 0.f) return 1.f;
   return philox_uniform(stepped_seed(d.seed, d.step), d.offset + idx) >= d.p ? 1.f / (1.f - d.p) : 0.f;
+}
+
+// Test hook (pvcr_debug_philox_minmax): smallest and largest uniform over indices [idx0, idx0 + n): both must lie
+// strictly inside (0,1) for the in-kernel Exp(1) / Gumbel draws to be finite.
+__global__ void philox_minmax_kernel(unsigned long long seed, unsigned long long idx0, unsigned long long n,
+                                     unsigned int* minmax_bits) {
+  float mn = 2.f, mx = -1.f;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const float u = philox_uniform(seed, idx0 + i);
+    mn = fminf(mn, u); mx = fmaxf(mx, u);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {      // positive floats order like their bit patterns
+    atomicMin(minmax_bits, __float_as_uint(mn));
+    atomicMax(minmax_bits + 1, __float_as_uint(mx));
+  }
+}
+int philox_minmax(unsigned long long seed, unsigned long long idx0, unsigned long long n, float* minmax, cudaStream_t st) {
+  const unsigned int init[2] = {0x7f7fffffu, 0u};
+  PVCR_CUDA_CHECK(cudaMemcpyAsync(minmax, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  philox_minmax_kernel<<<148 * 8, 256, 0, st>>>(seed, idx0, n, reinterpret_cast<unsigned int*>(minmax));
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  return PVCR_OK;
 }
 
 __device__ __forceinline__ unsigned long long drop_index(const Dropout& d, long long r, int C, int c) {
@@ -326,6 +356,15 @@ int fill_i64(long long* p, long long v, int n, cudaStream_t st) {
   { LaunchScope ls_(KC_MISC, st);
   fill_i64_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, v, n);
   }
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  return PVCR_OK;
+}
+__global__ void add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += x[i];
+}
+int add_inplace(float* y, const float* x, long long n, cudaStream_t st) {
+  if (n <= 0) return PVCR_OK;
+  add_inplace_kernel<<<(int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, st>>>(y, x, n);
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
 }
@@ -771,7 +810,8 @@ __global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ 
     const float lse = s_bcast[1];
     const int b = row / L, l = row % L;
     const long long len = s_len[b];
-    const float w = (l < len ? 1.f / ((float)len * (float)B) : 0.f) * (gscale ? gscale[0] : 1.f);
+    const float cnt = (float)(len < L ? len : L);      // mask.sum(dim=1) of the reference (train_utils.py:50-51)
+    const float w = (l < len ? 1.f / (cnt * (float)B) : 0.f) * (gscale ? gscale[0] : 1.f);
     const long long t = target[row];
     float* d = dlogits + (long long)row * ld_d;
     for (int j = tid; j < Vc; j += 256) d[j] = (expf(x[j] - lse) - (j == t ? 1.f : 0.f)) * w;
@@ -801,7 +841,7 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(const float* nll, co
       corr += (pred[b * L + l] == target[b * L + l]) ? 1.f : 0.f;
       cnt += 1.f;
     }
-    loss += s / (float)len;
+    loss += s / (float)(len < L ? len : L);     // mask.sum(dim=1) == min(s_len, L) (train_utils.py:50-51)
   }
   red[0][threadIdx.x] = loss; red[1][threadIdx.x] = corr; red[2][threadIdx.x] = cnt;
   __syncthreads();

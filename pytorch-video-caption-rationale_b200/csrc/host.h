@@ -16,8 +16,9 @@ int side_join_lane(cudaStream_t main, int id);          // main waits for lane `
 int side_join(cudaStream_t main);                       // main waits for every lane's current point
 int side_call_end(cudaStream_t main);                   // join unless mode 2
 enum SideNote { NOTE_ATT_BWD_WEIGHTS = 1, NOTE_VOCAB_WV = 2 };
-void side_note_put(const void* key, int tag);           // one-shot notes between the calls of a step (side.cu)
-bool side_note_take(const void* key, int tag);
+// one-shot notes between the calls of a step (side.cu), keyed by (workspace, tag) and the data they are about
+void side_note_put(const void* key, int tag, const void* what = nullptr);
+bool side_note_take(const void* key, int tag, const void* what = nullptr);
 
 // Bump allocator over a caller-provided workspace.  With base == nullptr it only measures (used by the
 // *_workspace_bytes queries, so sizing and carving share one code path).
@@ -196,7 +197,9 @@ struct DecPersistFwd {
   const float* v;                           // [H]
   const float* pk;                          // [B,N,H] fp32
   const bf16* enc_a; long long enc_ld;      // rows b*N + n
-  const float* enc;                         // [B,N,H] fp32 (initial state = frame N-1)
+  const float* enc;                         // [B,N,H] fp32
+  const float* h0; long long h0_ld;         // initial state, rows b (forward(): frame N-1 of enc; decode(): encoder_final)
+  const bf16* h0_a; long long h0_a_ld;      // its bf16 operand rows
   const float* ep;                          // [B,L,3H] hoisted embedding projection (+ b_ih)
   float* q_all; long long q_ld;             // step i: q_all + i*B*q_ld, rows b
   bf16* ctx_x;                              // [L][B][H]
@@ -215,7 +218,8 @@ struct DecPersistBwd {
   const float* v;                           // [H]
   const float* pk;                          // [B,N,H]
   const bf16* enc_a; long long enc_ld;
-  const float* enc;                         // [B,N,H] (h_prev of step 0 = frame N-1)
+  const float* enc;                         // [B,N,H]
+  const float* h0; long long h0_ld;         // h_prev of step 0, rows b
   const float* hs;                          // [B,L,H] forward states
   const float* d_hs;                        // [B,L,H] incoming gradient
   const float* q_all; long long q_ld;       // saved q (step i: q_all + i*B*q_ld)

@@ -45,6 +45,7 @@ int colsum(const float* in, long long ld, int R, int C, float* out, int accumula
 // y[i] = a[i] * mask_i/(1-p)  (dropout backward / forward on fp32 data), in place allowed
 int dropout_apply(const float* in, float* out, long long n, Dropout drop, cudaStream_t st);
 int fill_zero(void* p, size_t bytes, cudaStream_t st);
+int add_inplace(float* y, const float* x, long long n, cudaStream_t st);      // y += x
 // out[r * out_stride] = argmax_c in[r*ld + c] (first maximal index), and optionally
 // next[r] = use_teacher ? teacher[r * teacher_stride] : argmax   (the word fed to the next decoding step)
 int argmax_rows(const float* in, long long ld, int R, int C, long long* out, long long out_stride, long long* next,

@@ -9,7 +9,7 @@
 
 namespace pvcr {
 
-struct EventPair { cudaEvent_t a, b; int cls; };
+struct EventPair { cudaEvent_t a, b; int cls; double work; };
 static std::mutex g_mu;
 static unsigned long long g_launches[KC_COUNT];
 static double g_work[KC_COUNT];
@@ -33,6 +33,7 @@ LaunchScope::LaunchScope(int c, cudaStream_t s, double work) : cls(c), st(s), re
   if (!g_pool.empty()) { ep = g_pool.back(); g_pool.pop_back(); }
   else if (cudaEventCreate(&ep.a) != cudaSuccess || cudaEventCreate(&ep.b) != cudaSuccess) return;
   ep.cls = c;
+  ep.work = work;
   cudaEventRecordWithFlags(ep.a, s, capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
   ext = capturing;
   g_pending.push_back(ep);
@@ -95,6 +96,22 @@ int pvcr_prof_timeline(int* cls, float* t0, float* t1, int cap) {
     if (cudaEventElapsedTime(&a, g_pending[0].a, e.a) != cudaSuccess) return PVCR_ERR_CUDA;
     if (cudaEventElapsedTime(&b, g_pending[0].a, e.b) != cudaSuccess) return PVCR_ERR_CUDA;
     cls[n] = e.cls; t0[n] = a; t1[n] = b;
+    ++n;
+  }
+  return n;
+}
+
+// Every event-timed launch since the last reset, in host enqueue order: class, duration in ms, work (executed
+// tensor-core FLOPs for GEMM launches, else 0).  Returns the number of entries written (synchronises).
+int pvcr_prof_launch_list(int* cls, float* ms, double* work, int cap) {
+  std::lock_guard<std::mutex> g(g_mu);
+  int n = 0;
+  for (auto& e : g_pending) {
+    if (n >= cap) break;
+    if (cudaEventSynchronize(e.b) != cudaSuccess) return PVCR_ERR_CUDA;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, e.a, e.b) != cudaSuccess) return PVCR_ERR_CUDA;
+    cls[n] = e.cls; ms[n] = t; work[n] = e.work;
     ++n;
   }
   return n;

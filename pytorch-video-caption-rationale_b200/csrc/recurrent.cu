@@ -171,4 +171,93 @@ int gru_seq_bwd(const GruSeq& s, const GruSeqGrad& g, cudaStream_t st) {
   return PVCR_OK;
 }
 
+// ---- one GRU step as a self-contained op (the reference's `encode_step`, model/S2VTAttModel.py:63-78 and
+// model/S2VTModel.py:57-72: `self.rnn(vid_feat.unsqueeze(0), rnn_state)`), differentiable in x, h_prev and the
+// parameters.  This is the compatibility path for callers that drive the encoder frame by frame from Python
+// (SpatialNet.py:120-138); the sequence entry points hoist the input projection and run a persistent sweep instead.
+size_t linear_fwd_workspace(int M, int N, int K, int nsplit);
+size_t linear_bwd_workspace(int M, int N, int K, int nsplit);
+int linear_fwd(const float* x, long long ldx, const float* w, long long ldw, const float* bias, float* y, long long ldy,
+               int M, int N, int K, int nsplit, void* ws, size_t ws_bytes, cudaStream_t st);
+int linear_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* w, long long ldw, float* dx,
+               long long lddx, float* dw, long long lddw, float* db, int M, int N, int K, int nsplit, int accumulate,
+               void* ws, size_t ws_bytes, cudaStream_t st);
+
+static size_t gru_step_scratch(int B, int V, int H, int nsplit) {
+  size_t m = linear_fwd_workspace(B, 3 * H, V, nsplit);
+  const size_t c[3] = {linear_fwd_workspace(B, 3 * H, H, nsplit), linear_bwd_workspace(B, 3 * H, V, nsplit),
+                       linear_bwd_workspace(B, 3 * H, H, nsplit)};
+  for (size_t v : c) if (v > m) m = v;
+  return m;
+}
+size_t gru_step_workspace(int B, int V, int H, int nsplit) {
+  Arena a(nullptr, 0);
+  a.alloc<float>((size_t)4 * B * 3 * H);        // gi, gh (forward) / dgi, dgh (backward)
+  a.alloc<float>((size_t)B * H);                // W_hh^T dgh before it is added to dh * z
+  return a.off + gru_step_scratch(B, V, H, nsplit) + 1024;
+}
+
+// saved: [4][B,H] = r, z, n, W_hn h + b_hn (kept for the backward).  h_prev null = zeros.
+int gru_step_fwd(const float* x, const float* h_prev, const float* w_ih, const float* w_hh, const float* b_ih,
+                 const float* b_hh, int B, int V, int H, int nsplit, float* h_out, float* saved, void* ws,
+                 size_t ws_bytes, cudaStream_t st) {
+  PVCR_REQUIRE(B > 0 && V > 0 && H > 0 && nsplit >= 1 && nsplit <= 3, "gru_step_fwd: B=%d V=%d H=%d nsplit=%d", B, V, H, nsplit);
+  Arena a(ws, ws_bytes);
+  float* gi = a.alloc<float>((size_t)B * 3 * H);
+  float* gh = a.alloc<float>((size_t)B * 3 * H);
+  a.alloc<float>((size_t)2 * B * 3 * H);
+  a.alloc<float>((size_t)B * H);
+  const size_t need = gru_step_scratch(B, V, H, nsplit);
+  char* scratch = a.alloc<char>(need);
+  if (a.failed) { set_last_error("gru_step_fwd: workspace too small (%zu < %zu)", ws_bytes, a.off); return PVCR_ERR_WORKSPACE; }
+  PVCR_TRY(linear_fwd(x, V, w_ih, V, b_ih, gi, 3 * H, B, 3 * H, V, nsplit, scratch, need, st));
+  if (h_prev) PVCR_TRY(linear_fwd(h_prev, H, w_hh, H, nullptr, gh, 3 * H, B, 3 * H, H, nsplit, scratch, need, st));
+  GruFwdArgs g{};
+  g.B = B; g.H = H;
+  g.gi_a = gi; g.gi_a_ld = 3 * H;
+  g.gh = h_prev ? gh : nullptr; g.gh_ld = 3 * H; g.b_hh = b_hh;
+  g.h_prev = h_prev; g.h_prev_ld = H;
+  g.h_out = h_out; g.h_out_ld = H;
+  g.nsplit = nsplit;
+  const size_t o = (size_t)B * H;
+  g.r = saved; g.z = saved + o; g.n = saved + 2 * o; g.ghn = saved + 3 * o;
+  return gru_gate_fwd(g, st);
+}
+
+// d_x [B,V], d_h_prev [B,H] overwritten (nullable); d_w_* / d_b_* overwritten, or accumulated into when accumulate != 0.
+int gru_step_bwd(const float* d_h, const float* x, const float* h_prev, const float* w_ih, const float* w_hh,
+                 const float* saved, int B, int V, int H, int nsplit, float* d_x, float* d_h_prev, float* d_w_ih,
+                 float* d_w_hh, float* d_b_ih, float* d_b_hh, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st) {
+  PVCR_REQUIRE(B > 0 && V > 0 && H > 0 && nsplit >= 1 && nsplit <= 3, "gru_step_bwd: B=%d V=%d H=%d nsplit=%d", B, V, H, nsplit);
+  Arena a(ws, ws_bytes);
+  a.alloc<float>((size_t)2 * B * 3 * H);
+  float* dgi = a.alloc<float>((size_t)B * 3 * H);
+  float* dgh = a.alloc<float>((size_t)B * 3 * H);
+  float* dhz = a.alloc<float>((size_t)B * H);
+  const size_t need = gru_step_scratch(B, V, H, nsplit);
+  char* scratch = a.alloc<char>(need);
+  if (a.failed) { set_last_error("gru_step_bwd: workspace too small (%zu < %zu)", ws_bytes, a.off); return PVCR_ERR_WORKSPACE; }
+  GruBwdArgs b{};
+  b.B = B; b.H = H;
+  b.dh_a = d_h; b.dh_a_ld = H;
+  const size_t o = (size_t)B * H;
+  b.r = saved; b.z = saved + o; b.n = saved + 2 * o; b.ghn = saved + 3 * o;
+  b.h_prev = h_prev; b.h_prev_ld = H;
+  b.dgi = dgi; b.dgi_ld = 3 * H; b.dgh = dgh; b.dgh_ld = 3 * H;
+  b.nsplit = nsplit;
+  b.dh_direct = dhz; b.dh_direct_ld = H;          // dh * z
+  PVCR_TRY(gru_gate_bwd(b, st));
+  PVCR_TRY(linear_bwd(dgi, 3 * H, x, V, w_ih, V, d_x, V, d_w_ih, V, d_b_ih, B, 3 * H, V, nsplit, accumulate, scratch, need, st));
+  if (h_prev) {
+    PVCR_TRY(linear_bwd(dgh, 3 * H, h_prev, H, w_hh, H, d_h_prev, H, d_w_hh, H, d_b_hh, B, 3 * H, H, nsplit, accumulate,
+                        scratch, need, st));
+    if (d_h_prev) PVCR_TRY(add_inplace(d_h_prev, dhz, (long long)B * H, st));
+  } else {
+    if (d_b_hh) PVCR_TRY(colsum(dgh, 3 * H, B, 3 * H, d_b_hh, accumulate, st));
+    if (d_w_hh && !accumulate) PVCR_TRY(fill_zero(d_w_hh, sizeof(float) * (size_t)3 * H * H, st));
+    if (d_h_prev) PVCR_CUDA_CHECK(cudaMemcpyAsync(d_h_prev, dhz, sizeof(float) * o, cudaMemcpyDeviceToDevice, st));
+  }
+  return PVCR_OK;
+}
+
 }  // namespace pvcr

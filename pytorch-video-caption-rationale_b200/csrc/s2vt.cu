@@ -27,6 +27,8 @@ struct S2vtWs {
   float *gi1, *gi2e, *gi2d, *gh;
   Planes w1hT, w2hT, w2oT, w2eT, w1iT, dgh_a;
   float *dh1, *dh2, *d_h1d, *d_out1, *demb_rows, *dxsel;
+  Planes h0_a;                  // decode(): bf16 rows / fp32 copy of a caller-given rnn1 state
+  float* h0_f;
   unsigned* sync;
   bf16* xch;
 };
@@ -61,6 +63,8 @@ static void carve_s2vt(Arena& a, const PvcrDims& d, int need_frame_grad, S2vtWs&
   w.dxsel = need_frame_grad ? a.alloc<float>(BN * V) : nullptr;
   w.sync = a.alloc<unsigned>(32 * 160);
   w.xch = a.alloc<bf16>((size_t)2 * B * 4 * H);
+  w.h0_a = alloc_planes(a, B, H, ns);
+  w.h0_f = a.alloc<float>((size_t)B * H);
 }
 
 static size_t s2vt_scratch(const PvcrDims& d, int need_frame_grad) {
@@ -108,11 +112,14 @@ static GruSeq make_seq(const PvcrDims& d, const SeqBuf& s, const float* gi, cons
 }
 
 struct S2vtSeqs { GruSeq e1, d1, e2, d2; };
-static S2vtSeqs make_seqs(const PvcrDims& d, const PvcrS2vtParams& p, S2vtWs& w, float* hs) {
+// given: decode() mode (model/S2VTModel.py:88, called by SpatialNet.py:140) -- rnn1's outputs over the frames and its
+// state are caller inputs; the decoding stage of rnn1 starts from the staged copy of that state (h0_f / h0_a).
+static S2vtSeqs make_seqs(const PvcrDims& d, const PvcrS2vtParams& p, S2vtWs& w, float* hs, bool given = false) {
   w.d2.h = hs;
   S2vtSeqs q;
   q.e1 = make_seq(d, w.e1, w.gi1, nullptr, p.rnn1_b_hh, w.w1h, nullptr, w.gh, w.sync);
   q.d1 = make_seq(d, w.d1, nullptr, p.rnn1_b_ih, p.rnn1_b_hh, w.w1h, &w.e1, w.gh, w.sync);
+  if (given) { q.d1.h0 = w.h0_f; q.d1.h0_ld = d.H; q.d1.h0_planes = w.h0_a.ptr; q.d1.h0_planes_ld = w.h0_a.ld; }
   q.e2 = make_seq(d, w.e2, w.gi2e, nullptr, p.rnn2_b_hh, w.w2h, nullptr, w.gh, w.sync);
   q.d2 = make_seq(d, w.d2, w.gi2d, nullptr, p.rnn2_b_hh, w.w2h, &w.e2, w.gh, w.sync);
   return q;
@@ -129,10 +136,11 @@ static Dropout emb_dropout(const PvcrDims& d) { return make_dropout(d.dropout_p,
 
 // weights -> planes, rnn1 over the frames, rnn2 encoding stage
 static int s2vt_encode(const PvcrDims& d, const PvcrS2vtParams& p, S2vtWs& w, const S2vtSeqs& q, const float* vid,
-                       const float* frame_scale, cudaStream_t st) {
+                       const float* frame_scale, cudaStream_t st, const float* out1_given = nullptr,
+                       const float* state1_given = nullptr) {
   const int B = d.B, N = d.N, V = d.V, H = d.H, E = d.E;
   const int BN = B * N, H3 = 3 * H;
-  PVCR_TRY(prep_weight(p.rnn1_w_ih, V, H3, V, w.w1i, st));
+  if (!out1_given) PVCR_TRY(prep_weight(p.rnn1_w_ih, V, H3, V, w.w1i, st));
   PVCR_TRY(prep_weight(p.rnn1_w_hh, H, H3, H, w.w1h, st));
   PVCR_TRY(prep_weight(p.rnn2_w_ih, H + E, H3, H, w.w2o, st));
   PVCR_TRY(prep_weight(p.rnn2_w_ih + H, H + E, H3, E, w.w2e, st));
@@ -141,17 +149,26 @@ static int s2vt_encode(const PvcrDims& d, const PvcrS2vtParams& p, S2vtWs& w, co
     for (SeqBuf* s : {&w.e1, &w.d1, &w.e2, &w.d2})
       PVCR_TRY(fill_zero(s->hp.ptr, sizeof(bf16) * (size_t)s->hp.rows * s->hp.ld, st));
   }
+  if (out1_given) {
+    PVCR_CUDA_CHECK(cudaMemcpyAsync(w.e1.h, out1_given, sizeof(float) * (size_t)BN * H, cudaMemcpyDeviceToDevice, st));
+    PVCR_CUDA_CHECK(cudaMemcpyAsync(w.h0_f, state1_given, sizeof(float) * (size_t)B * H, cudaMemcpyDeviceToDevice, st));
+    if (w.h0_a.Kp != H) PVCR_TRY(fill_zero(w.h0_a.ptr, sizeof(bf16) * (size_t)B * w.h0_a.ld, st));
+    PVCR_TRY(stage(out1_given, H, BN, H, w.e1.hp, 0, nullptr, NO_DROPOUT, st));
+    PVCR_TRY(stage(state1_given, H, B, H, w.h0_a, 0, nullptr, NO_DROPOUT, st));
+  } else {
   PVCR_TRY(stage(vid, V, BN, V, w.x_a, 0, frame_scale, NO_DROPOUT, st));
   PVCR_TRY(gemm_planes(w.x_a.view(), w.w1i.view(), BN, H3, (int)w.x_a.ld, w.gi1, H3, p.rnn1_b_ih, 0, st));
   PVCR_TRY(gru_seq_fwd(q.e1, st));
+  }
   // rnn2 encoding stage: [out1 ; 0] -> only the out1 half of W_ih contributes
   PVCR_TRY(gemm_planes(w.e1.hp.view(), w.w2o.view(), BN, H3, (int)w.e1.hp.ld, w.gi2e, H3, p.rnn2_b_ih, 0, st));
   PVCR_TRY(gru_seq_fwd(q.e2, st));
   return PVCR_OK;
 }
 
-int s2vt_fwd(const PvcrDims& d, const PvcrS2vtParams& p, const float* vid, const float* frame_scale,
-             const long long* s_in, float* hs, void* ws, size_t ws_bytes, cudaStream_t st) {
+static int s2vt_fwd_impl(const PvcrDims& d, const PvcrS2vtParams& p, const float* vid, const float* frame_scale,
+                         const float* out1_given, const float* state1_given, const long long* s_in, float* hs, void* ws,
+                         size_t ws_bytes, cudaStream_t st) {
   PVCR_TRY(check_s2vt_dims(d));
   const int B = d.B, H = d.H, E = d.E, L = d.L;
   const int BL = B * L, H3 = 3 * H;
@@ -159,8 +176,8 @@ int s2vt_fwd(const PvcrDims& d, const PvcrS2vtParams& p, const float* vid, const
   S2vtWs w;
   carve_s2vt(a, d, 0, w);
   if (a.failed) { set_last_error("s2vt_fwd: workspace too small (%zu < %zu)", ws_bytes, a.off); return PVCR_ERR_WORKSPACE; }
-  S2vtSeqs q = make_seqs(d, p, w, hs);
-  PVCR_TRY(s2vt_encode(d, p, w, q, vid, frame_scale, st));
+  S2vtSeqs q = make_seqs(d, p, w, hs, out1_given != nullptr);
+  PVCR_TRY(s2vt_encode(d, p, w, q, vid, frame_scale, st, out1_given, state1_given));
   PVCR_TRY(gru_seq_fwd(q.d1, st));
   // rnn2 decoding stage: [h1_dec ; Dropout(Emb[w])]
   PVCR_TRY(gemm_planes(w.d1.hp.view(), w.w2o.view(), BL, H3, (int)w.d1.hp.ld, w.gi2d, H3, p.rnn2_b_ih, 0, st));
@@ -170,6 +187,15 @@ int s2vt_fwd(const PvcrDims& d, const PvcrS2vtParams& p, const float* vid, const
   return PVCR_OK;
 }
 
+int s2vt_fwd(const PvcrDims& d, const PvcrS2vtParams& p, const float* vid, const float* frame_scale,
+             const long long* s_in, float* hs, void* ws, size_t ws_bytes, cudaStream_t st) {
+  return s2vt_fwd_impl(d, p, vid, frame_scale, nullptr, nullptr, s_in, hs, ws, ws_bytes, st);
+}
+int s2vt_decode_fwd(const PvcrDims& d, const PvcrS2vtParams& p, const float* out1, const float* state1,
+                    const long long* s_in, float* hs, void* ws, size_t ws_bytes, cudaStream_t st) {
+  PVCR_REQUIRE(out1 && state1, "s2vt_decode_fwd: null rnn1 outputs / state");
+  return s2vt_fwd_impl(d, p, nullptr, nullptr, out1, state1, s_in, hs, ws, ws_bytes, st);
+}
 
 // rows (b, t) of h_{t-1}: step 0 takes `first` (row stride first_ld; null = zeros), steps >= 1 the sequence itself
 static int build_hprev(const SeqBuf& s, int B, int H, const float* first, long long first_ld, cudaStream_t st) {
@@ -196,10 +222,11 @@ static GruSeqGrad make_grad(const SeqBuf& s, int H, const float* dh_ext, float* 
   return g;
 }
 
-int s2vt_bwd(const PvcrDims& d, const PvcrS2vtParams& p, const float* vid, const float* frame_scale,
-             const long long* s_in, const float* d_hs, float* hs, PvcrS2vtGrads& g, float* d_frame_scale, void* ws,
-             size_t ws_bytes, cudaStream_t st) {
+static int s2vt_bwd_impl(const PvcrDims& d, const PvcrS2vtParams& p, const float* vid, const float* frame_scale,
+             const long long* s_in, const float* d_hs, float* hs, PvcrS2vtGrads& g, float* d_frame_scale,
+             float* d_out1, float* d_state1, void* ws, size_t ws_bytes, cudaStream_t st) {
   PVCR_TRY(check_s2vt_dims(d));
+  const bool given = d_out1 != nullptr;
   const int B = d.B, N = d.N, V = d.V, H = d.H, E = d.E, L = d.L, ns = d.nsplit;
   const int BN = B * N, BL = B * L, H3 = 3 * H;
   const int need_frame_grad = d_frame_scale != nullptr;
@@ -210,7 +237,7 @@ int s2vt_bwd(const PvcrDims& d, const PvcrS2vtParams& p, const float* vid, const
     set_last_error("s2vt_bwd: workspace too small (%zu bytes)", ws_bytes);
     return PVCR_ERR_WORKSPACE;
   }
-  S2vtSeqs q = make_seqs(d, p, w, hs);
+  S2vtSeqs q = make_seqs(d, p, w, hs, given);
   PVCR_TRY(prep_weight_T(p.rnn1_w_hh, H, H3, H, w.w1hT, 0, 1, st));
   PVCR_TRY(prep_weight_T(p.rnn2_w_hh, H, H3, H, w.w2hT, 0, 1, st));
   PVCR_TRY(prep_weight_T(p.rnn2_w_ih, H + E, H3, H, w.w2oT, 0, 1, st));
@@ -244,6 +271,15 @@ int s2vt_bwd(const PvcrDims& d, const PvcrS2vtParams& p, const float* vid, const
   // ---- rnn1, reverse time ----
   PVCR_TRY(fill_zero(w.dh1, sizeof(float) * (size_t)B * H, st));
   PVCR_TRY(gru_seq_bwd(q.d1, make_grad(w.d1, H, w.d_h1d, w.dh1, w, w.w1hT), st));
+  if (given) {      // decode(): rnn1's frame outputs and state were inputs -- return their gradients, no frame sweep
+    PVCR_CUDA_CHECK(cudaMemcpyAsync(d_out1, w.d_out1, sizeof(float) * (size_t)BN * H, cudaMemcpyDeviceToDevice, st));
+    PVCR_CUDA_CHECK(cudaMemcpyAsync(d_state1, w.dh1, sizeof(float) * (size_t)B * H, cudaMemcpyDeviceToDevice, st));
+    PVCR_TRY(build_hprev(w.d1, B, H, w.h0_f, H, st));
+    PVCR_TRY(grad_w(a, w.d1.dgh, H3, BL, H3, w.d1.hprev, H, H, nullptr, nullptr, g.rnn1_w_hh, H, 0, ns, st));
+    PVCR_TRY(colsum(w.d1.dgh, H3, BL, H3, g.rnn1_b_hh, 0, st));
+    PVCR_TRY(colsum(w.d1.dgi, H3, BL, H3, g.rnn1_b_ih, 0, st));
+    return PVCR_OK;
+  }
   PVCR_TRY(gru_seq_bwd(q.e1, make_grad(w.e1, H, w.d_out1, w.dh1, w, w.w1hT), st));
   PVCR_TRY(build_hprev(w.d1, B, H, w.e1.h + (long long)(N - 1) * H, (long long)N * H, st));
   PVCR_TRY(build_hprev(w.e1, B, H, nullptr, 0, st));
@@ -259,6 +295,18 @@ int s2vt_bwd(const PvcrDims& d, const PvcrS2vtParams& p, const float* vid, const
     PVCR_TRY(rowdot(vid, w.dxsel, BN, V, d_frame_scale, st));
   }
   return PVCR_OK;
+}
+
+int s2vt_bwd(const PvcrDims& d, const PvcrS2vtParams& p, const float* vid, const float* frame_scale,
+             const long long* s_in, const float* d_hs, float* hs, PvcrS2vtGrads& g, float* d_frame_scale, void* ws,
+             size_t ws_bytes, cudaStream_t st) {
+  return s2vt_bwd_impl(d, p, vid, frame_scale, s_in, d_hs, hs, g, d_frame_scale, nullptr, nullptr, ws, ws_bytes, st);
+}
+// Backward of s2vt_decode_fwd: all gradients of `g` except rnn1_w_ih (not on this path), d_out1 [B,N,H], d_state1 [B,H].
+int s2vt_decode_bwd(const PvcrDims& d, const PvcrS2vtParams& p, const long long* s_in, const float* d_hs, float* hs,
+                    PvcrS2vtGrads& g, float* d_out1, float* d_state1, void* ws, size_t ws_bytes, cudaStream_t st) {
+  PVCR_REQUIRE(d_out1 && d_state1, "s2vt_decode_bwd: null gradient outputs");
+  return s2vt_bwd_impl(d, p, nullptr, nullptr, s_in, d_hs, hs, g, nullptr, d_out1, d_state1, ws, ws_bytes, st);
 }
 
 // ---- step-wise decoding with word feedback -----------------------------------------------------------------------
@@ -308,25 +356,30 @@ static int gru_single_step(const PvcrDims& d, const SeqBuf& s, int i, const SeqB
 }
 
 // teacher_mask: HOST array of L ints (coin of step i decides the word fed to step i+1); null = always feed back.
-int s2vt_decode_steps(const PvcrDims& d, const PvcrS2vtParams& p, const float* vid, const float* frame_scale,
+// out1_given / state1_given: decode() mode (see s2vt_decode_fwd) -- vid / frame_scale unused.
+int s2vt_decode_steps_impl(const PvcrDims& d, const PvcrS2vtParams& p, const float* vid, const float* frame_scale,
+                      const float* out1_given, const float* state1_given,
                       long long sos_id, const long long* teacher_words, const int* teacher_mask, float out_dropout_p,
                       long long* ids, long long* fed, float* logits, void* ws, size_t ws_bytes, cudaStream_t st) {
   PVCR_TRY(check_s2vt_dims(d));
+  PVCR_REQUIRE((out1_given != nullptr) == (state1_given != nullptr), "s2vt decode: rnn1 outputs and state come together");
   const int B = d.B, H = d.H, E = d.E, L = d.L, Vc = d.Vc, H3 = 3 * H;
   Arena a(ws, ws_bytes);
   S2vtStepWs gw;
   carve_steps(a, d, gw);
   if (a.failed) { set_last_error("s2vt_decode_steps: workspace too small (%zu < %zu)", ws_bytes, a.off); return PVCR_ERR_WORKSPACE; }
   S2vtWs& w = gw.w;
-  S2vtSeqs q = make_seqs(d, p, w, gw.hs);
-  PVCR_TRY(s2vt_encode(d, p, w, q, vid, frame_scale, st));
+  S2vtSeqs q = make_seqs(d, p, w, gw.hs, out1_given != nullptr);
+  PVCR_TRY(s2vt_encode(d, p, w, q, vid, frame_scale, st, out1_given, state1_given));
+  SeqBuf first1 = w.e1;          // the stage whose last state starts rnn1's decoding steps
+  if (out1_given) { first1 = SeqBuf{}; first1.T = 1; first1.h = w.h0_f; first1.hp = w.h0_a; }
   PVCR_TRY(prep_weight(p.out_w, H, Vc, H, gw.wv, st));
   if (gw.hdrop.Kp != H) PVCR_TRY(fill_zero(gw.hdrop.ptr, sizeof(bf16) * (size_t)B * gw.hdrop.ld, st));
   PVCR_TRY(fill_i64(gw.words, sos_id, B, st));
   for (int i = 0; i < L; ++i) {
     if (fed) PVCR_CUDA_CHECK(cudaMemcpy2DAsync(fed + i, sizeof(long long) * L, gw.words, sizeof(long long),
                                                sizeof(long long), B, cudaMemcpyDeviceToDevice, st));
-    PVCR_TRY(gru_single_step(d, w.d1, i, w.e1, w.w1h, nullptr, p.rnn1_b_ih, p.rnn1_b_hh, w.gh, st));
+    PVCR_TRY(gru_single_step(d, w.d1, i, first1, w.w1h, nullptr, p.rnn1_b_ih, p.rnn1_b_hh, w.gh, st));
     OperandView h1_a{w.d1.hp.ptr + (long long)i * w.d1.hp.ld, (long long)L * w.d1.hp.ld, 0, B, 1};
     PVCR_TRY(gemm_planes(h1_a, w.w2o.view(), B, H3, (int)w.w2o.ld, gw.g2, H3, p.rnn2_b_ih, 0, st));
     Dropout ed = emb_dropout(d);
@@ -346,6 +399,12 @@ int s2vt_decode_steps(const PvcrDims& d, const PvcrS2vtParams& p, const float* v
                          use_teacher, st));
   }
   return PVCR_OK;
+}
+int s2vt_decode_steps(const PvcrDims& d, const PvcrS2vtParams& p, const float* vid, const float* frame_scale,
+                      long long sos_id, const long long* teacher_words, const int* teacher_mask, float out_dropout_p,
+                      long long* ids, long long* fed, float* logits, void* ws, size_t ws_bytes, cudaStream_t st) {
+  return s2vt_decode_steps_impl(d, p, vid, frame_scale, nullptr, nullptr, sos_id, teacher_words, teacher_mask,
+                                out_dropout_p, ids, fed, logits, ws, ws_bytes, st);
 }
 
 }  // namespace pvcr

@@ -19,7 +19,8 @@ struct AttWs {
   // prepared weights (forward)
   Planes wih_enc, whh_enc, wk, wcat, wc, we;
   // forward activations
-  Planes x_a, enc_a, emb_a, ctx_a, hs_a;
+  Planes x_a, enc_a, emb_a, ctx_a, hs_a, h0_a;
+  float* h0_f;
   float *gi_enc, *enc, *er, *ez, *en, *eghn, *gh, *pk, *ep, *g1_all, *alpha_all, *ctx_all, *g2, *dr, *dz, *dn, *dghn;
   // backward
   Planes wcT, wcatT, wkT, weT, whh_encT, wih_encT, dgi_a, d1_a, dgh_a;
@@ -67,6 +68,8 @@ static void carve(Arena& a, const PvcrDims& d, int need_frame_grad, AttWs& w) {
   w.emb_a = alloc_planes(a, (int)BL, E, ns);
   w.ctx_a = alloc_planes(a, B, H, ns);
   w.hs_a = alloc_planes(a, (int)BL, H, ns);
+  w.h0_a = alloc_planes(a, B, H, ns);                 // decode(): bf16 rows of a caller-given initial state
+  w.h0_f = a.alloc<float>((size_t)B * H);
   w.gi_enc = a.alloc<float>(BN * 3 * H);
   w.enc = a.alloc<float>(BN * H);
   w.er = a.alloc<float>(BN * H); w.ez = a.alloc<float>(BN * H); w.en = a.alloc<float>(BN * H); w.eghn = a.alloc<float>(BN * H);
@@ -156,6 +159,16 @@ static GruSeq encoder_seq(const PvcrDims& d, const PvcrS2vtAttParams& p, const A
   return s;
 }
 
+// Initial decoder state h_{-1}.  forward(): the encoder's final state = frame N-1 of its outputs (Decoder.forward is
+// handed encoder_final, model/S2VTAttModel.py:261-262).  decode(): a separate caller-given tensor
+// (model/S2VTAttModel.py:231-243, called by SpatialNet.py:140), staged into h0_f / h0_a by the forward call.
+struct H0 { const float* f; long long f_ld; const bf16* a; long long a_ld; };
+static H0 initial_state(const PvcrDims& d, const AttWs& w, bool given) {
+  if (given) return H0{w.h0_f, d.H, w.h0_a.ptr, w.h0_a.ld};
+  return H0{w.enc + (long long)(d.N - 1) * d.H, (long long)d.N * d.H, w.enc_a.ptr + (long long)(d.N - 1) * w.enc_a.ld,
+            (long long)d.N * w.enc_a.ld};
+}
+
 // Transposed weight planes of the backward sweeps (they depend on the parameters only).
 static int att_bwd_weights(const PvcrDims& d, const PvcrS2vtAttParams& p, const AttWs& w, cudaStream_t st) {
   const int H = d.H, E = d.E, H3 = 3 * H;
@@ -167,9 +180,14 @@ static int att_bwd_weights(const PvcrDims& d, const PvcrS2vtAttParams& p, const 
   return PVCR_OK;
 }
 
-int s2vtatt_fwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid, const float* frame_scale,
-                const long long* s_in, float* hs, float* alphas, void* ws, size_t ws_bytes, cudaStream_t st) {
+// enc_given / final_given (both or neither): decode() mode -- the encoder outputs [B,N,H] and the initial decoder state
+// [B,H] come from the caller (SpatialNet drives its own per-frame encoder loop), vid / frame_scale are unused.
+static int s2vtatt_fwd_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid, const float* frame_scale,
+                            const float* enc_given, const float* final_given, const long long* s_in, float* hs,
+                            float* alphas, void* ws, size_t ws_bytes, cudaStream_t st) {
   PVCR_TRY(check_dims(d));
+  const bool given = enc_given != nullptr;
+  PVCR_REQUIRE(given == (final_given != nullptr), "s2vtatt decode: encoder outputs and final state come together");
   const int B = d.B, N = d.N, V = d.V, H = d.H, E = d.E, L = d.L;
   const int BN = B * N, BL = B * L, H3 = 3 * H, H4 = 4 * H;
   Arena a(ws, ws_bytes);
@@ -186,12 +204,14 @@ int s2vtatt_fwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   cudaStream_t l0 = st, l1 = st, l2 = st;
   const bool fork = side_site(0);
   if (fork) { PVCR_TRY(side_fork(st, &l0, 0)); PVCR_TRY(side_fork(st, &l1, 1)); PVCR_TRY(side_fork(st, &l2, 2)); }
+  if (!given) {
   PVCR_TRY(stage(vid, V, BN, V, w.x_a, 0, frame_scale, NO_DROPOUT, l0));
   PVCR_TRY(prep_weight(p.enc_w_ih, V, H3, V, w.wih_enc, st));
   if (fork) PVCR_TRY(side_join_lane(st, 0));         // waits for the frame staging only (nothing else is on lane 0 yet)
   PVCR_TRY(gemm_planes(w.x_a.view(), w.wih_enc.view(), BN, H3, (int)w.x_a.ld, w.gi_enc, H3, p.enc_b_ih, 0, st));
   PVCR_TRY(prep_weight(p.enc_w_hh, H, H3, H, w.whh_enc, l1));
   if (fork) PVCR_TRY(side_join_lane(st, 1));         // the sweep waits for its W_hh planes only
+  }
 
   PVCR_TRY(prep_weight(p.att_wk, H, H, H, w.wk, l0));
   PVCR_TRY(prep_weight(p.att_wq, H, H, H, w.wcat, l0, 0));
@@ -209,10 +229,20 @@ int s2vtatt_fwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   side_note_take(ws, NOTE_ATT_BWD_WEIGHTS);          // a stale note of an earlier forward on this workspace
   if (fork) {
     PVCR_TRY(att_bwd_weights(d, p, w, l2));
-    side_note_put(ws, NOTE_ATT_BWD_WEIGHTS);
+    side_note_put(ws, NOTE_ATT_BWD_WEIGHTS, p.dec_w_hh);
   }
+  if (given) {
+    // decode(): encoder outputs and the initial state are inputs; stage their fp32 copies and bf16 operand rows
+    PVCR_CUDA_CHECK(cudaMemcpyAsync(w.enc, enc_given, sizeof(float) * (size_t)BN * H, cudaMemcpyDeviceToDevice, st));
+    PVCR_CUDA_CHECK(cudaMemcpyAsync(w.h0_f, final_given, sizeof(float) * (size_t)B * H, cudaMemcpyDeviceToDevice, st));
+    if (w.h0_a.Kp != H) PVCR_TRY(fill_zero(w.h0_a.ptr, sizeof(bf16) * (size_t)B * w.h0_a.ld, st));
+    PVCR_TRY(stage(enc_given, H, BN, H, w.enc_a, 0, nullptr, NO_DROPOUT, st));
+    PVCR_TRY(stage(final_given, H, B, H, w.h0_a, 0, nullptr, NO_DROPOUT, st));
+  } else {
   // encoder: N recurrent steps on gi = (vid * frame_scale) W_ih^T + b_ih
   PVCR_TRY(gru_seq_fwd(encoder_seq(d, p, w), st));
+  }
+  const H0 h0 = initial_state(d, w, given);
 
   // proj_key = enc W_k^T
   PVCR_TRY(side_join(st));
@@ -224,6 +254,7 @@ int s2vtatt_fwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
     q.L = L; q.B = B; q.N = N; q.H = H;
     q.w1 = w.wcat.ptr; q.w1_ld = w.wcat.ld; q.w3 = w.wc.ptr; q.w3_ld = w.wc.ld;
     q.b_hh = p.dec_b_hh; q.v = p.att_v; q.pk = w.pk; q.enc_a = w.enc_a.ptr; q.enc_ld = w.enc_a.ld; q.enc = w.enc;
+    q.h0 = h0.f; q.h0_ld = h0.f_ld; q.h0_a = h0.a; q.h0_a_ld = h0.a_ld;
     q.ep = w.ep; q.q_all = w.g1_all; q.q_ld = H4; q.ctx_x = w.ctx_x; q.ctx_all = w.ctx_all; q.alpha = w.alpha_all;
     q.hs = hs; q.hs_a = w.hs_a.ptr; q.hs_a_ld = w.hs_a.ld;
     q.r = w.dr; q.z = w.dz; q.n = w.dn; q.ghn = w.dghn; q.counters = w.sync;
@@ -231,7 +262,7 @@ int s2vtatt_fwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   } else
   for (int i = 0; i < L; ++i) {
     OperandView hprev_a = (i == 0)
-        ? OperandView{w.enc_a.ptr + (long long)(N - 1) * w.enc_a.ld, (long long)N * w.enc_a.ld, 0, B, 1}
+        ? OperandView{const_cast<bf16*>(h0.a), h0.a_ld, 0, B, 1}
         : OperandView{w.hs_a.ptr + (long long)(i - 1) * w.hs_a.ld, (long long)L * w.hs_a.ld, 0, B, 1};
     float* g1 = w.g1_all + (long long)i * B * H4;
     PVCR_TRY(gemm_planes(hprev_a, w.wcat.view(), B, H4, (int)w.wcat.ld, g1, H4, nullptr, 0, st));
@@ -248,7 +279,7 @@ int s2vtatt_fwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
     g.gi_a = w.g2; g.gi_a_ld = H3;
     g.gi_b = w.ep + (long long)i * H3; g.gi_b_ld = (long long)L * H3;
     g.gh = g1 + H; g.gh_ld = H4; g.b_hh = p.dec_b_hh;
-    if (i == 0) { g.h_prev = w.enc + (long long)(N - 1) * H; g.h_prev_ld = (long long)N * H; }
+    if (i == 0) { g.h_prev = h0.f; g.h_prev_ld = h0.f_ld; }
     else { g.h_prev = hs + (long long)(i - 1) * H; g.h_prev_ld = (long long)L * H; }
     g.h_out = hs + (long long)i * H; g.h_out_ld = (long long)L * H;
     g.h_planes = w.hs_a.ptr + (long long)i * w.hs_a.ld; g.h_planes_ld = (long long)L * w.hs_a.ld;
@@ -262,13 +293,27 @@ int s2vtatt_fwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   return PVCR_OK;
 }
 
+int s2vtatt_fwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid, const float* frame_scale,
+                const long long* s_in, float* hs, float* alphas, void* ws, size_t ws_bytes, cudaStream_t st) {
+  return s2vtatt_fwd_impl(d, p, vid, frame_scale, nullptr, nullptr, s_in, hs, alphas, ws, ws_bytes, st);
+}
+int s2vtatt_decode_fwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* enc_outs, const float* enc_final,
+                       const long long* s_in, float* hs, float* alphas, void* ws, size_t ws_bytes, cudaStream_t st) {
+  PVCR_REQUIRE(enc_outs && enc_final, "s2vtatt_decode_fwd: null encoder outputs / final state");
+  return s2vtatt_fwd_impl(d, p, nullptr, nullptr, enc_outs, enc_final, s_in, hs, alphas, ws, ws_bytes, st);
+}
+
 // part: 0 = whole backward; 1 = decoder half only (every decoder / attention / embedding gradient is final when it
 // returns); 2 = encoder half only (must follow part 1 on the same workspace).  The split lets a data-parallel caller
 // all-reduce the decoder gradients while the encoder sweep runs.
-int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid, const float* frame_scale,
+// d_enc_outs / d_enc_final (both or neither): decode() mode (forward ran through s2vtatt_decode_fwd) -- the gradients on
+// the caller's encoder outputs and initial state are returned instead of being swept through the encoder.
+static int s2vtatt_bwd_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid, const float* frame_scale,
                 const long long* s_in, const float* d_hs, const float* hs, PvcrS2vtAttGrads& g, float* d_frame_scale,
-                void* ws, size_t ws_bytes, cudaStream_t st, int part) {
+                float* d_enc_outs, float* d_enc_final, void* ws, size_t ws_bytes, cudaStream_t st, int part) {
   PVCR_TRY(check_dims(d));
+  const bool given = d_enc_outs != nullptr;
+  if (given) part = 1;
   const int B = d.B, N = d.N, V = d.V, H = d.H, E = d.E, L = d.L, ns = d.nsplit;
   const int BN = B * N, BL = B * L, H3 = 3 * H, H4 = 4 * H;
   const int need_frame_grad = d_frame_scale != nullptr;
@@ -284,12 +329,12 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   if (ns == 1) {
     a.cache = &cache;
     // operands the forward pass already staged as bf16 planes (same values: frame scale / no dropout included)
-    if (!frame_scale) cache.put(vid, V, BN, V, w.x_a);
+    if (!frame_scale && !given) cache.put(vid, V, BN, V, w.x_a);
     cache.put(w.enc, H, BN, H, w.enc_a);
     cache.put(s_in, -1, BL, E, w.emb_a);
   }
   // transposed weights of the sweeps: already staged by the forward call on this workspace, or staged here
-  if (part != 2 && !side_note_take(ws, NOTE_ATT_BWD_WEIGHTS)) PVCR_TRY(att_bwd_weights(d, p, w, st));
+  if (part != 2 && !side_note_take(ws, NOTE_ATT_BWD_WEIGHTS, p.dec_w_hh)) PVCR_TRY(att_bwd_weights(d, p, w, st));
   if (part != 2) {
   if (ns > 1) {     // bf16 mode multiplies by the forward weight planes directly (MN-major operand)
     PVCR_TRY(prep_weight_T(p.att_wk, H, H, H, w.wkT, 0, 1, st));
@@ -297,6 +342,7 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   }
   if (need_frame_grad && ns > 1) PVCR_TRY(prep_weight_T(p.enc_w_ih, V, H3, V, w.wih_encT, 0, 1, st));
 
+  const H0 h0 = initial_state(d, w, given);
   const bool persist_dec = dec_persist_eligible(B, N, H, ns, w.enc_a.Kp);
   Planes dgi_p{}, d1_p{};
   bool sweep_planes = false;
@@ -305,6 +351,7 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
     q.L = L; q.B = B; q.N = N; q.H = H;
     q.wcT = w.wcT.ptr; q.wcT_ld = w.wcT.ld; q.wcatT = w.wcatT.ptr; q.wcatT_ld = w.wcatT.ld;
     q.v = p.att_v; q.pk = w.pk; q.enc_a = w.enc_a.ptr; q.enc_ld = w.enc_a.ld; q.enc = w.enc; q.hs = hs; q.d_hs = d_hs;
+    q.h0 = h0.f; q.h0_ld = h0.f_ld;
     q.q_all = w.g1_all; q.q_ld = H4; q.alpha = w.alpha_all;
     q.r = w.dr; q.z = w.dz; q.n = w.dn; q.ghn = w.dghn;
     q.dgi_all = w.dgi_all; q.d1_all = w.d1_all; q.dctx_all = w.dctx_all; q.ds_all = w.ds_all;
@@ -335,7 +382,7 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
     b.dh_b = d_hs + (long long)i * H; b.dh_b_ld = (long long)L * H;
     const long long o = (long long)i * B * H;
     b.r = w.dr + o; b.z = w.dz + o; b.n = w.dn + o; b.ghn = w.dghn + o;
-    if (i == 0) { b.h_prev = w.enc + (long long)(N - 1) * H; b.h_prev_ld = (long long)N * H; }
+    if (i == 0) { b.h_prev = h0.f; b.h_prev_ld = h0.f_ld; }
     else { b.h_prev = hs + (long long)(i - 1) * H; b.h_prev_ld = (long long)L * H; }
     b.dgi = w.dgi_all + (long long)i * H3; b.dgi_ld = (long long)L * H3;           // rows b*L + i
     b.dgh = w.d1_all + (long long)i * H4 + H; b.dgh_ld = (long long)L * H4;
@@ -387,13 +434,13 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
     Planes d0 = alloc_planes(a, B, H4, 1);                   // [dq | dgh] of step 0, rows b
     if (a.failed) { set_last_error("s2vtatt_bwd: workspace too small (step-0 planes)"); return PVCR_ERR_WORKSPACE; }
     PVCR_TRY(cast_split(w.d1_all, (long long)L * H4, B, H4, d0.ptr, d0.ld, d0.Kp, 1, 0, nullptr, NO_DROPOUT, la));
-    const OperandView e_last{w.enc_a.ptr + (long long)(N - 1) * w.enc_a.ld, (long long)N * w.enc_a.ld, 0, B, 1};
+    const OperandView e_last{const_cast<bf16*>(h0.a), h0.a_ld, 0, B, 1};
     PVCR_TRY(gemm_mn_store(OperandView{d0.ptr + H, d0.ld, 0, B, 1}, e_last, H3, H, B, g.dec_w_hh, H, 1, la));
     PVCR_TRY(gemm_mn_store(OperandView{d0.ptr, d0.ld, 0, B, 1}, e_last, H, H, B, g.att_wq, H, 1, la));
   } else {
   // h_{i-1} rows in (b, i) order: i = 0 -> encoder final state, i >= 1 -> hs[b, i-1]
-  PVCR_CUDA_CHECK(cudaMemcpy2DAsync(w.hprev_dec, sizeof(float) * (size_t)L * H, w.enc + (long long)(N - 1) * H,
-                                    sizeof(float) * (size_t)N * H, sizeof(float) * H, B, cudaMemcpyDeviceToDevice, la));
+  PVCR_CUDA_CHECK(cudaMemcpy2DAsync(w.hprev_dec, sizeof(float) * (size_t)L * H, h0.f, sizeof(float) * (size_t)h0.f_ld,
+                                    sizeof(float) * H, B, cudaMemcpyDeviceToDevice, la));
   if (L > 1)
     PVCR_CUDA_CHECK(cudaMemcpy2DAsync(w.hprev_dec + H, sizeof(float) * (size_t)L * H, hs, sizeof(float) * (size_t)L * H,
                                       sizeof(float) * (size_t)(L - 1) * H, B, cudaMemcpyDeviceToDevice, la));
@@ -431,6 +478,11 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   else PVCR_TRY(grad_x(a, w.dpk, H, BN, H, w.wkT, w.denc, H, 1, st));
 
   }   // decoder half
+  if (given) {      // decode(): hand the gradients on the caller's encoder outputs / initial state back
+    PVCR_CUDA_CHECK(cudaMemcpyAsync(d_enc_outs, w.denc, sizeof(float) * (size_t)BN * H, cudaMemcpyDeviceToDevice, st));
+    PVCR_CUDA_CHECK(cudaMemcpyAsync(d_enc_final, w.dh_carry, sizeof(float) * (size_t)B * H, cudaMemcpyDeviceToDevice, st));
+    return side_call_end(st);
+  }
   if (part == 1) return side_call_end(st);
   // ---- encoder, reverse time (dh_carry already holds the gradient on the final state) ----
   GruSeq es = encoder_seq(d, p, w);
@@ -481,6 +533,20 @@ int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid,
   return side_call_end(st);
 }
 
+int s2vtatt_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid, const float* frame_scale,
+                const long long* s_in, const float* d_hs, const float* hs, PvcrS2vtAttGrads& g, float* d_frame_scale,
+                void* ws, size_t ws_bytes, cudaStream_t st, int part) {
+  return s2vtatt_bwd_impl(d, p, vid, frame_scale, s_in, d_hs, hs, g, d_frame_scale, nullptr, nullptr, ws, ws_bytes, st, part);
+}
+// Backward of s2vtatt_decode_fwd: every decoder / attention / embedding gradient of `g` (its encoder entries are not
+// touched), d_enc_outs [B,N,H] and d_enc_final [B,H].
+int s2vtatt_decode_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const long long* s_in, const float* d_hs,
+                       const float* hs, PvcrS2vtAttGrads& g, float* d_enc_outs, float* d_enc_final, void* ws,
+                       size_t ws_bytes, cudaStream_t st) {
+  PVCR_REQUIRE(d_enc_outs && d_enc_final, "s2vtatt_decode_bwd: null gradient outputs");
+  return s2vtatt_bwd_impl(d, p, nullptr, nullptr, s_in, d_hs, hs, g, nullptr, d_enc_outs, d_enc_final, ws, ws_bytes, st, 1);
+}
+
 // ---- fixed-length greedy decoding (eval branch, model/S2VTAttModel.py:172-191) ---------------------------------
 struct GreedyWs {
   AttWs w;
@@ -503,10 +569,14 @@ size_t s2vtatt_greedy_workspace(const PvcrDims& d) {
   return a.off + 4096;
 }
 
-int s2vtatt_greedy(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid, const float* frame_scale,
+// enc_given / final_given: decode() in eval mode (model/S2VTAttModel.py:231-243 with self.training == False).
+int s2vtatt_greedy_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid, const float* frame_scale,
+                   const float* enc_given, const float* final_given,
                    long long sos_id, long long* ids, float* logits, float* alphas, void* ws, size_t ws_bytes,
                    cudaStream_t st) {
   PVCR_TRY(check_dims(d));
+  const bool given = enc_given != nullptr;
+  PVCR_REQUIRE(given == (final_given != nullptr), "s2vtatt greedy decode: encoder outputs and final state come together");
   const int B = d.B, N = d.N, V = d.V, H = d.H, E = d.E, L = d.L, Vc = d.Vc;
   const int BN = B * N, BL = B * L, H3 = 3 * H, H4 = 4 * H;
   Arena a(ws, ws_bytes);
@@ -527,15 +597,24 @@ int s2vtatt_greedy(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* v
     PVCR_TRY(fill_zero(w.hs_a.ptr, sizeof(bf16) * (size_t)BL * w.hs_a.ld, st));
     PVCR_TRY(fill_zero(w.ctx_a.ptr, sizeof(bf16) * (size_t)B * w.ctx_a.ld, st));
   }
+  if (given) {
+    PVCR_CUDA_CHECK(cudaMemcpyAsync(w.enc, enc_given, sizeof(float) * (size_t)BN * H, cudaMemcpyDeviceToDevice, st));
+    PVCR_CUDA_CHECK(cudaMemcpyAsync(w.h0_f, final_given, sizeof(float) * (size_t)B * H, cudaMemcpyDeviceToDevice, st));
+    if (w.h0_a.Kp != H) PVCR_TRY(fill_zero(w.h0_a.ptr, sizeof(bf16) * (size_t)B * w.h0_a.ld, st));
+    PVCR_TRY(stage(enc_given, H, BN, H, w.enc_a, 0, nullptr, NO_DROPOUT, st));
+    PVCR_TRY(stage(final_given, H, B, H, w.h0_a, 0, nullptr, NO_DROPOUT, st));
+  } else {
   PVCR_TRY(stage(vid, V, BN, V, w.x_a, 0, frame_scale, NO_DROPOUT, st));
   PVCR_TRY(gemm_planes(w.x_a.view(), w.wih_enc.view(), BN, H3, (int)w.x_a.ld, w.gi_enc, H3, p.enc_b_ih, 0, st));
   PVCR_TRY(gru_seq_fwd(encoder_seq(d, p, w), st));
+  }
+  const H0 h0 = initial_state(d, w, given);
   PVCR_TRY(gemm_planes(w.enc_a.view(), w.wk.view(), BN, H, (int)w.enc_a.ld, w.pk, H, nullptr, 0, st));
   PVCR_TRY(fill_i64(gw.words, sos_id, B, st));
   float* hs = gw.hs;
   for (int i = 0; i < L; ++i) {
     OperandView hprev_a = (i == 0)
-        ? OperandView{w.enc_a.ptr + (long long)(N - 1) * w.enc_a.ld, (long long)N * w.enc_a.ld, 0, B, 1}
+        ? OperandView{const_cast<bf16*>(h0.a), h0.a_ld, 0, B, 1}
         : OperandView{w.hs_a.ptr + (long long)(i - 1) * w.hs_a.ld, (long long)L * w.hs_a.ld, 0, B, 1};
     float* g1 = w.g1_all;
     PVCR_TRY(gemm_planes(hprev_a, w.wcat.view(), B, H4, (int)w.wcat.ld, g1, H4, nullptr, 0, st));
@@ -553,7 +632,7 @@ int s2vtatt_greedy(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* v
     g.B = B; g.H = H;
     g.gi_a = w.g2; g.gi_a_ld = H3;
     g.gh = g1 + H; g.gh_ld = H4; g.b_hh = p.dec_b_hh;
-    if (i == 0) { g.h_prev = w.enc + (long long)(N - 1) * H; g.h_prev_ld = (long long)N * H; }
+    if (i == 0) { g.h_prev = h0.f; g.h_prev_ld = h0.f_ld; }
     else { g.h_prev = hs + (long long)(i - 1) * H; g.h_prev_ld = (long long)L * H; }
     g.h_out = hs + (long long)i * H; g.h_out_ld = (long long)L * H;
     g.h_planes = w.hs_a.ptr + (long long)i * w.hs_a.ld; g.h_planes_ld = (long long)L * w.hs_a.ld;
@@ -566,6 +645,11 @@ int s2vtatt_greedy(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* v
     PVCR_TRY(argmax_rows(lg, ldl, B, Vc, ids + i, L, gw.words, nullptr, 0, 0, st));
   }
   return PVCR_OK;
+}
+int s2vtatt_greedy(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid, const float* frame_scale,
+                   long long sos_id, long long* ids, float* logits, float* alphas, void* ws, size_t ws_bytes,
+                   cudaStream_t st) {
+  return s2vtatt_greedy_impl(d, p, vid, frame_scale, nullptr, nullptr, sos_id, ids, logits, alphas, ws, ws_bytes, st);
 }
 
 // ---- fixed-length beam search over the decoder step (definition: oracle s2vtatt_beam_search) --------

@@ -100,23 +100,30 @@ int side_join(cudaStream_t main) {
 // something a later call would otherwise compute (e.g. the forward pass staging the transposed weights of the backward
 // sweep on a lane) leaves a note; the later call takes it.  A call that could have left a note but did not clears it.
 namespace {
-struct Note { const void* key; int tag; };
+struct Note { const void* key; int tag; const void* what; };
 std::vector<Note> g_notes;
 }
-void side_note_put(const void* key, int tag) {
+// `what` names the data the note is about (e.g. the fp32 weight matrix that was staged): a note only matches a taker
+// that asks about the same data, so a workspace address recycled by the caller's allocator cannot make a later call
+// trust planes that were staged from other weights (or never finished: see pvcr_side_join, which drops them).
+void side_note_put(const void* key, int tag, const void* what) {
   std::lock_guard<std::mutex> g(g_mu);
-  for (auto& n : g_notes) if (n.key == key && n.tag == tag) return;
+  for (size_t i = 0; i < g_notes.size();)        // at most one note per (workspace, tag): the newest
+    if (g_notes[i].key == key && g_notes[i].tag == tag) g_notes.erase(g_notes.begin() + i); else ++i;
   if (g_notes.size() > 256) g_notes.clear();
-  g_notes.push_back(Note{key, tag});
+  g_notes.push_back(Note{key, tag, what});
 }
-bool side_note_take(const void* key, int tag) {
+bool side_note_take(const void* key, int tag, const void* what) {
   std::lock_guard<std::mutex> g(g_mu);
-  for (size_t i = 0; i < g_notes.size(); ++i)
+  bool hit = false;
+  for (size_t i = 0; i < g_notes.size();)
     if (g_notes[i].key == key && g_notes[i].tag == tag) {
+      hit = hit || g_notes[i].what == what;      // a note about other data is stale: dropped, not honoured
       g_notes.erase(g_notes.begin() + i);
-      return true;
+    } else {
+      ++i;
     }
-  return false;
+  return hit;
 }
 
 // End of a C-ABI call: mode 1 joins here, mode 2 leaves the lane running until pvcr_side_join().

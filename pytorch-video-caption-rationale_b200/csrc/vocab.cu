@@ -12,7 +12,7 @@ namespace pvcr {
 
 size_t vocab_fused_workspace(int M, int H, int Vc);
 int vocab_fused_fwd(const float*, const float*, const float*, const long long*, const long long*, int, int, int, int,
-                    float, unsigned long long, float*, long long*, float*, void*, size_t, cudaStream_t);
+                    float, unsigned long long, float*, long long*, float*, float*, void*, size_t, cudaStream_t);
 int vocab_fused_bwd(const float*, const float*, const float*, const long long*, const long long*, int, int, int, int,
                     float, unsigned long long, const float*, float*, float*, float*, const float*, void*, size_t,
                     cudaStream_t);
@@ -57,12 +57,13 @@ int vocab_ce_prepare(const float* wv, int B, int L, int H, int Vc, int nsplit, v
 // loss3 = {masked loss, #correct, #mask}; pred [B*L] int64; logits stay in the workspace for vocab_ce_bwd.
 int vocab_ce_fwd(const float* hs, const float* wv, const float* bv, const long long* target, const long long* s_len,
                  int B, int L, int H, int Vc, int nsplit, float dropout_p, unsigned long long seed, float* loss3,
-                 long long* pred, float* lse, float* logits_out, long long ld_logits_out, void* ws, size_t ws_bytes,
-                 cudaStream_t st) {
+                 long long* pred, float* lse, float* token_nll, float* logits_out, long long ld_logits_out, void* ws,
+                 size_t ws_bytes, cudaStream_t st) {
   PVCR_REQUIRE(nsplit >= 1 && nsplit <= 3, "vocab_ce_fwd: nsplit=%d", nsplit);
   if (nsplit == 1 && !logits_out && target && !fused_off())
-    return vocab_fused_fwd(hs, wv, bv, target, s_len, B, L, H, Vc, dropout_p, seed, loss3, pred, lse, ws, ws_bytes, st);
-  if (side_note_take(ws, NOTE_VOCAB_WV)) PVCR_TRY(side_join(st));     // a prepare whose fused layout is not used here
+    return vocab_fused_fwd(hs, wv, bv, target, s_len, B, L, H, Vc, dropout_p, seed, loss3, pred, lse, token_nll, ws,
+                           ws_bytes, st);
+  if (side_note_take(ws, NOTE_VOCAB_WV, wv)) PVCR_TRY(side_join(st));     // a prepare whose fused layout is not used here
   const int M = B * L;
   Arena a(ws, ws_bytes);
   VocabWs w;
@@ -78,6 +79,7 @@ int vocab_ce_fwd(const float* hs, const float* wv, const float* bv, const long l
   if (target) {
     PVCR_TRY(ce_rows(logits, ldl, B, L, Vc, target, s_len, lse, w.nll, pred, nullptr, 0, nullptr, st));
     PVCR_TRY(loss_finalize(w.nll, pred, target, s_len, B, L, loss3, st));
+    if (token_nll) PVCR_CUDA_CHECK(cudaMemcpyAsync(token_nll, w.nll, sizeof(float) * M, cudaMemcpyDeviceToDevice, st));
   }
   return PVCR_OK;
 }
@@ -109,6 +111,12 @@ int vocab_ce_bwd(const float* hs, const float* wv, const float* bv, const long l
   PVCR_TRY(grad_w(a, w.logits, w.ldl, M, Vc, w.hs_drop ? w.hs_drop : hs, H, H, nullptr, nullptr, d_wv, H, 0, nsplit, st));
   PVCR_TRY(colsum(w.logits, w.ldl, M, Vc, d_bv, 0, st));
   return PVCR_OK;
+}
+
+// y = x * mask / (1 - p) with the mask pvcr_vocab_ce_fwd / _bwd draw for Dropout(hs) under (p, seed): element index =
+// flat index into the [B*L, H] matrix.  Used by the materialised-logits backward and by the dropout parity tests.
+int out_dropout_apply(const float* x, float* y, long long n, float p, unsigned long long seed, cudaStream_t st) {
+  return dropout_apply(x, y, n, out_dropout(p, seed), st);
 }
 
 }  // namespace pvcr

@@ -187,7 +187,8 @@ __global__ void row_weights_kernel(const long long* s_len, int B, int L, const f
   lse2[i] = lse[i] * LOG2E;
   const int b = i / L, l = i % L;
   const long long len = s_len[b];
-  w[i] = (l < len ? 1.f / ((float)len * (float)B) : 0.f) * (gscale ? gscale[0] : 1.f);
+  const float cnt = (float)(len < L ? len : L);      // mask.sum(dim=1) of the reference (train_utils.py:50-51)
+  w[i] = (l < len ? 1.f / (cnt * (float)B) : 0.f) * (gscale ? gscale[0] : 1.f);
 }
 
 // out[c] += sum_r in[r*ld + c]  (bf16 in, fp32 accumulate; out pre-zeroed): block = 64 column pairs x 4 row lanes
@@ -278,20 +279,20 @@ int vocab_fused_prepare(const float* wv, int B, int L, int H, int Vc, void* ws, 
   cudaStream_t lane;
   PVCR_TRY(side_fork(st, &lane, 2));
   PVCR_TRY(prep_weight(wv, H, Vc, H, w.wv, lane));
-  side_note_put(ws, NOTE_VOCAB_WV);
+  side_note_put(ws, NOTE_VOCAB_WV, wv);
   return PVCR_OK;
 }
 
 int vocab_fused_fwd(const float* hs, const float* wv, const float* bv, const long long* target, const long long* s_len,
                     int B, int L, int H, int Vc, float dropout_p, unsigned long long seed, float* loss3, long long* pred,
-                    float* lse, void* ws, size_t ws_bytes, cudaStream_t st) {
+                    float* lse, float* token_nll, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int M = B * L;
   Arena a(ws, ws_bytes);
   FusedWs w;
   carve_fused(a, M, H, Vc, w);
   if (a.failed) { set_last_error("vocab_fused_fwd: workspace too small (%zu < %zu)", ws_bytes, a.off); return PVCR_ERR_WORKSPACE; }
   PVCR_TRY(stage(hs, H, M, H, w.hs_a, 0, nullptr, fused_out_dropout(dropout_p, seed), st));
-  if (side_note_take(ws, NOTE_VOCAB_WV)) PVCR_TRY(side_join(st));       // staged by vocab_fused_prepare on a lane
+  if (side_note_take(ws, NOTE_VOCAB_WV, wv)) PVCR_TRY(side_join(st));       // staged by vocab_fused_prepare on a lane
   else PVCR_TRY(prep_weight(wv, H, Vc, H, w.wv, st));
   {
     LaunchScope ls_(KC_LOSS, st);
@@ -313,6 +314,7 @@ int vocab_fused_fwd(const float* hs, const float* wv, const float* bv, const lon
                                                                           w.nll, pred);
   }
   PVCR_CUDA_CHECK(cudaGetLastError());
+  if (token_nll) PVCR_CUDA_CHECK(cudaMemcpyAsync(token_nll, w.nll, sizeof(float) * M, cudaMemcpyDeviceToDevice, st));
   return loss_finalize(w.nll, pred, target, s_len, B, L, loss3, st);
 }
 

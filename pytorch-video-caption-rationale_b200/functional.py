@@ -128,6 +128,84 @@ class S2VTAttSequence(torch.autograd.Function):
         return (None, None, d_fs, None) + tuple(grads[f] for f in ATT_SEQ_FIELDS)
 
 
+class S2VTAttDecode(torch.autograd.Function):
+    """Attention decoder on caller-given encoder outputs: (enc_outs [B,N,H], enc_final [B,H], s_in, params) -> hs,
+    alphas.  `S2VTAttModel.decode` of the reference (model/S2VTAttModel.py:231-243), the entry SpatialNet uses
+    (model/SpatialNet.py:140); differentiable in enc_outs, enc_final and every decoder parameter."""
+
+    @staticmethod
+    def forward(ctx, cfg, enc_outs, enc_final, s_in, *params):
+        B, N, H = enc_outs.shape
+        L = s_in.shape[1]
+        tensors = {f: _f32c(p) for f, p in zip(ATT_SEQ_FIELDS, params)}
+        Vc, E = tensors["emb"].shape
+        dims = make_dims(B, N, 1, H, E, L, Vc, cfg["nsplit"], 0.0, 0)
+        enc_c, fin_c, s_c = _f32c(enc_outs), _f32c(enc_final), _i64c(s_in)
+        Lb = lib()
+        ws = _ws(Lb.pvcr_s2vtatt_workspace(ctypes.byref(dims), 0), enc_c.device)
+        hs = torch.empty((B, L, H), dtype=torch.float32, device=enc_c.device)
+        alphas = torch.empty((L, B, N), dtype=torch.float32, device=enc_c.device)
+        ps = _fill_struct(PvcrS2vtAttParams(), ATT_SEQ_FIELDS, tensors)
+        check(Lb.pvcr_s2vtatt_decode_fwd(ctypes.byref(dims), ctypes.byref(ps), ptr(enc_c), ptr(fin_c), ptr(s_c), ptr(hs),
+                                         ptr(alphas), ptr(ws), ws.numel(), stream_ptr()), "pvcr_s2vtatt_decode_fwd")
+        ctx.dims = dims
+        ctx.keep = (s_c, hs, ws, tensors)
+        ctx.mark_non_differentiable(alphas)
+        return hs, alphas
+
+    @staticmethod
+    def backward(ctx, d_hs, _d_alphas):
+        s_c, hs, ws, tensors = ctx.keep
+        B, N, H = ctx.dims.B, ctx.dims.N, ctx.dims.H
+        dec_fields = [f for f in ATT_SEQ_FIELDS if not f.startswith("enc_")]
+        grads = {f: torch.empty_like(tensors[f]) for f in dec_fields}
+        d_enc = torch.empty((B, N, H), dtype=torch.float32, device=hs.device)
+        d_fin = torch.empty((B, H), dtype=torch.float32, device=hs.device)
+        ps = _fill_struct(PvcrS2vtAttParams(), ATT_SEQ_FIELDS, tensors)
+        gs = _fill_struct(PvcrS2vtAttGrads(), ATT_SEQ_FIELDS, grads)
+        check(lib().pvcr_s2vtatt_decode_bwd(ctypes.byref(ctx.dims), ctypes.byref(ps), ptr(s_c), ptr(hs), ptr(_f32c(d_hs)),
+                                            ctypes.byref(gs), ptr(d_enc), ptr(d_fin), ptr(ws), ws.numel(), stream_ptr()),
+              "pvcr_s2vtatt_decode_bwd")
+        return (None, d_enc, d_fin, None) + tuple(grads.get(f) for f in ATT_SEQ_FIELDS)
+
+
+class GruStep(torch.autograd.Function):
+    """h' = GRU(x, h_prev), one step: `encode_step` of both caption nets (model/S2VTAttModel.py:63-78,
+    model/S2VTModel.py:57-72), called once per frame by SpatialNet (model/SpatialNet.py:127)."""
+
+    @staticmethod
+    def forward(ctx, nsplit, x, h_prev, w_ih, w_hh, b_ih, b_hh):
+        B, V = x.shape
+        H = w_hh.shape[1]
+        x_c = _f32c(x)
+        h_c = None if h_prev is None else _f32c(h_prev)
+        w = tuple(_f32c(t) for t in (w_ih, w_hh, b_ih, b_hh))
+        Lb = lib()
+        ws = _ws(Lb.pvcr_gru_step_workspace(B, V, H, nsplit), x_c.device)
+        h_out = torch.empty((B, H), dtype=torch.float32, device=x_c.device)
+        saved = torch.empty((4, B, H), dtype=torch.float32, device=x_c.device)
+        check(Lb.pvcr_gru_step_fwd(ptr(x_c), ptr(h_c), ptr(w[0]), ptr(w[1]), ptr(w[2]), ptr(w[3]), B, V, H, nsplit,
+                                   ptr(h_out), ptr(saved), ptr(ws), ws.numel(), stream_ptr()), "pvcr_gru_step_fwd")
+        ctx.meta = (B, V, H, nsplit)
+        ctx.keep = (x_c, h_c, w, saved)
+        return h_out
+
+    @staticmethod
+    def backward(ctx, d_h):
+        B, V, H, nsplit = ctx.meta
+        x_c, h_c, w, saved = ctx.keep
+        dev = x_c.device
+        d_x = torch.empty_like(x_c)
+        d_hp = None if h_c is None else torch.empty_like(h_c)
+        d_w = tuple(torch.empty_like(t) for t in w)
+        Lb = lib()
+        ws = _ws(Lb.pvcr_gru_step_workspace(B, V, H, nsplit), dev)
+        check(Lb.pvcr_gru_step_bwd(ptr(_f32c(d_h)), ptr(x_c), ptr(h_c), ptr(w[0]), ptr(w[1]), ptr(saved), B, V, H, nsplit,
+                                   ptr(d_x), ptr(d_hp), ptr(d_w[0]), ptr(d_w[1]), ptr(d_w[2]), ptr(d_w[3]), 0, ptr(ws),
+                                   ws.numel(), stream_ptr()), "pvcr_gru_step_bwd")
+        return (None, d_x, d_hp) + d_w
+
+
 S2VT_SEQ_FIELDS = [f for f in S2VT_PARAM_FIELDS if f not in ("out_w", "out_b")]
 
 
@@ -172,6 +250,44 @@ class S2VTSequence(torch.autograd.Function):
                                ptr(d_hs), ctypes.byref(gs), ptr(d_fs), ptr(ws), ws.numel(), stream_ptr()),
               "pvcr_s2vt_bwd")
         return (None, None, d_fs, None) + tuple(grads[f] for f in S2VT_SEQ_FIELDS)
+
+
+class S2VTDecode(torch.autograd.Function):
+    """S2VT decode on caller-given rnn1 outputs: (out1 [B,N,H], state1 [B,H], s_in, params) -> hs [B,L,H]
+    (model/S2VTModel.py:88-145 up to the vocabulary projection; SpatialNet.py:140)."""
+
+    @staticmethod
+    def forward(ctx, cfg, out1, state1, s_in, *params):
+        B, N, H = out1.shape
+        L = s_in.shape[1]
+        tensors = {f: _f32c(p) for f, p in zip(S2VT_SEQ_FIELDS, params)}
+        Vc, E = tensors["emb"].shape
+        dims = make_dims(B, N, 1, H, E, L, Vc, cfg["nsplit"], cfg.get("emb_dropout_p", 0.0), cfg.get("seed", 0))
+        o_c, st_c, s_c = _f32c(out1), _f32c(state1), _i64c(s_in)
+        Lb = lib()
+        ws = _ws(Lb.pvcr_s2vt_workspace(ctypes.byref(dims), 0), o_c.device)
+        hs = torch.empty((B, L, H), dtype=torch.float32, device=o_c.device)
+        ps = _fill_struct(PvcrS2vtParams(), S2VT_SEQ_FIELDS, tensors)
+        check(Lb.pvcr_s2vt_decode_fwd(ctypes.byref(dims), ctypes.byref(ps), ptr(o_c), ptr(st_c), ptr(s_c), ptr(hs), ptr(ws),
+                                      ws.numel(), stream_ptr()), "pvcr_s2vt_decode_fwd")
+        ctx.dims = dims
+        ctx.keep = (s_c, hs, ws, tensors)
+        return hs
+
+    @staticmethod
+    def backward(ctx, d_hs):
+        s_c, hs, ws, tensors = ctx.keep
+        B, N, H = ctx.dims.B, ctx.dims.N, ctx.dims.H
+        fields = [f for f in S2VT_SEQ_FIELDS if f != "rnn1_w_ih"]
+        grads = {f: torch.empty_like(tensors[f]) for f in fields}
+        d_out1 = torch.empty((B, N, H), dtype=torch.float32, device=hs.device)
+        d_state1 = torch.empty((B, H), dtype=torch.float32, device=hs.device)
+        ps = _fill_struct(PvcrS2vtParams(), S2VT_SEQ_FIELDS, tensors)
+        gs = _fill_struct(PvcrS2vtGrads(), S2VT_SEQ_FIELDS, grads)
+        check(lib().pvcr_s2vt_decode_bwd(ctypes.byref(ctx.dims), ctypes.byref(ps), ptr(s_c), ptr(hs), ptr(_f32c(d_hs)),
+                                         ctypes.byref(gs), ptr(d_out1), ptr(d_state1), ptr(ws), ws.numel(), stream_ptr()),
+              "pvcr_s2vt_decode_bwd")
+        return (None, d_out1, d_state1, None) + tuple(grads.get(f) for f in S2VT_SEQ_FIELDS)
 
 
 class GeneratorSelect(torch.autograd.Function):
@@ -238,9 +354,11 @@ class VocabCrossEntropy(torch.autograd.Function):
         loss3 = torch.empty(3, dtype=torch.float32, device=hs.device)
         pred = torch.empty((B, L), dtype=torch.int64, device=hs.device)
         lse = torch.empty((B, L), dtype=torch.float32, device=hs.device)
+        nll = torch.empty((B, L), dtype=torch.float32, device=hs.device)
         check(Lb.pvcr_vocab_ce_fwd(ptr(hs_c), ptr(w_c), ptr(b_c), ptr(t_c), ptr(l_c), B, L, H, Vc, nsplit, p, seed,
-                                   ptr(loss3), ptr(pred), ptr(lse), None, 0, ptr(ws), ws.numel(), stream_ptr()),
-              "pvcr_vocab_ce_fwd")
+                                   ptr(loss3), ptr(pred), ptr(lse), ptr(nll), None, 0, ptr(ws), ws.numel(),
+                                   stream_ptr()), "pvcr_vocab_ce_fwd")
+        cfg["token_nll"] = nll             # unmasked per-token loss [B,L] (criterion(logits, target), train_utils.py:47-48)
         ctx.cfg = (B, L, H, Vc, nsplit, p, seed)
         ctx.grad_out = cfg.get("vocab_grad_out") or {}
         ctx.keep = (hs_c, w_c, b_c, t_c, l_c, ws, lse, pred)
@@ -289,7 +407,7 @@ class VocabLogits(torch.autograd.Function):
         ws = _ws(Lb.pvcr_vocab_ce_workspace(B, L, H, Vc, nsplit, p), hs.device)
         logits = torch.empty((B, L, Vc), dtype=torch.float32, device=hs.device)
         check(Lb.pvcr_vocab_ce_fwd(ptr(hs_c), ptr(w_c), ptr(b_c), None, None, B, L, H, Vc, nsplit, p, seed, None, None,
-                                   None, ptr(logits), Vc, ptr(ws), ws.numel(), stream_ptr()), "pvcr_vocab_ce_fwd")
+                                   None, None, ptr(logits), Vc, ptr(ws), ws.numel(), stream_ptr()), "pvcr_vocab_ce_fwd")
         ctx.cfg = (B, L, H, Vc, nsplit, p, seed)
         ctx.keep = (hs_c, w_c)
         return logits
@@ -304,10 +422,15 @@ class VocabLogits(torch.autograd.Function):
         d_w = torch.empty_like(w_c)
         d_b = torch.empty((Vc,), dtype=torch.float32, device=hs_c.device)
         ws = _ws(Lb.pvcr_linear_bwd_workspace(B * L, Vc, H, nsplit), hs_c.device)
+        x = hs_c
         if p > 0.0:
-            raise _lib.PvcrError("materialised-logits backward with dropout is not supported: use forward_loss()")
-        check(Lb.pvcr_linear_bwd(ptr(d_logits), Vc, ptr(hs_c), H, ptr(w_c), H, ptr(d_hs), H, ptr(d_w), H, ptr(d_b),
+            # the Linear saw Dropout(hs): regenerate the forward's mask from (p, seed) for d W = d logits^T Dropout(hs) ...
+            x = torch.empty_like(hs_c)
+            check(Lb.pvcr_out_dropout_apply(ptr(hs_c), ptr(x), hs_c.numel(), p, seed, stream_ptr()), "pvcr_out_dropout_apply")
+        check(Lb.pvcr_linear_bwd(ptr(d_logits), Vc, ptr(x), H, ptr(w_c), H, ptr(d_hs), H, ptr(d_w), H, ptr(d_b),
                                  B * L, Vc, H, nsplit, 0, ptr(ws), ws.numel(), stream_ptr()), "pvcr_linear_bwd")
+        if p > 0.0:        # ... and d hs = Dropout'(d logits W)
+            check(Lb.pvcr_out_dropout_apply(ptr(d_hs), ptr(d_hs), d_hs.numel(), p, seed, stream_ptr()), "pvcr_out_dropout_apply")
         return None, d_hs, d_w, d_b
 
 
@@ -330,6 +453,46 @@ def s2vtatt_greedy(vid, frame_scale, sos_id, max_len, seq_params, out_w, out_b, 
     check(Lb.pvcr_s2vtatt_greedy(ctypes.byref(dims), ctypes.byref(ps), ptr(vid_c), ptr(fs_c), int(sos_id), ptr(ids),
                                  ptr(logits), ptr(alphas), ptr(ws), ws.numel(), stream_ptr()), "pvcr_s2vtatt_greedy")
     return ids, logits, alphas
+
+
+def s2vtatt_decode_greedy(enc_outs, enc_final, sos_id, max_len, seq_params, out_w, out_b, nsplit=3):
+    """Greedy decoding from caller-given encoder outputs [B,N,H] / final state [B,H] -> (ids [B,L], logits [B,L,Vc],
+    alphas [L,B,N]); eval branch of S2VTAttModel.decode (model/S2VTAttModel.py:231-243)."""
+    B, N, H = enc_outs.shape
+    tensors = {f: _f32c(p) for f, p in zip(ATT_SEQ_FIELDS, seq_params)}
+    tensors["out_w"], tensors["out_b"] = _f32c(out_w), _f32c(out_b)
+    Vc, E = tensors["emb"].shape
+    dims = make_dims(B, N, 1, H, E, max_len, Vc, nsplit, 0.0, 0)
+    enc_c, fin_c = _f32c(enc_outs), _f32c(enc_final)
+    Lb = lib()
+    ws = _ws(Lb.pvcr_s2vtatt_greedy_workspace(ctypes.byref(dims)), enc_c.device)
+    ids = torch.empty((B, max_len), dtype=torch.int64, device=enc_c.device)
+    logits = torch.empty((B, max_len, Vc), dtype=torch.float32, device=enc_c.device)
+    alphas = torch.empty((max_len, B, N), dtype=torch.float32, device=enc_c.device)
+    ps = _fill_struct(PvcrS2vtAttParams(), ATT_PARAM_FIELDS, tensors)
+    check(Lb.pvcr_s2vtatt_decode_greedy(ctypes.byref(dims), ctypes.byref(ps), ptr(enc_c), ptr(fin_c), int(sos_id), ptr(ids),
+                                        ptr(logits), ptr(alphas), ptr(ws), ws.numel(), stream_ptr()),
+          "pvcr_s2vtatt_decode_greedy")
+    return ids, logits, alphas
+
+
+def s2vt_decode_greedy(out1, state1, sos_id, max_len, seq_params, out_w, out_b, nsplit=3):
+    """Greedy decoding from caller-given rnn1 outputs [B,N,H] / state [B,H] -> (ids [B,L], logits [B,L,Vc]); eval branch
+    of S2VTModel.decode (model/S2VTModel.py:147-177)."""
+    B, N, H = out1.shape
+    tensors = {f: _f32c(p) for f, p in zip(S2VT_SEQ_FIELDS, seq_params)}
+    tensors["out_w"], tensors["out_b"] = _f32c(out_w), _f32c(out_b)
+    Vc, E = tensors["emb"].shape
+    dims = make_dims(B, N, 1, H, E, max_len, Vc, nsplit, 0.0, 0)
+    o_c, st_c = _f32c(out1), _f32c(state1)
+    Lb = lib()
+    ws = _ws(Lb.pvcr_s2vt_decode_steps_workspace(ctypes.byref(dims)), o_c.device)
+    ids = torch.empty((B, max_len), dtype=torch.int64, device=o_c.device)
+    logits = torch.empty((B, max_len, Vc), dtype=torch.float32, device=o_c.device)
+    ps = _fill_struct(PvcrS2vtParams(), S2VT_PARAM_FIELDS, tensors)
+    check(Lb.pvcr_s2vt_decode_greedy(ctypes.byref(dims), ctypes.byref(ps), ptr(o_c), ptr(st_c), int(sos_id), ptr(ids),
+                                     ptr(logits), ptr(ws), ws.numel(), stream_ptr()), "pvcr_s2vt_decode_greedy")
+    return ids, logits
 
 
 def s2vtatt_beam(vid, frame_scale, sos_id, max_len, beam, seq_params, out_w, out_b, nsplit=3):

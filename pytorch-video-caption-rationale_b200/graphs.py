@@ -26,6 +26,10 @@ class GraphedTrainStep:
         # per-replay dropout / Gumbel seeds: a device counter incremented by the first captured graph node
         self.seed_step = torch.zeros(1, dtype=torch.int64, device=example_inputs[0].device)
         lib().pvcr_set_seed_step(ptr(self.seed_step))
+        GraphedTrainStep._seed_owner = self.seed_step.data_ptr()     # the library holds ONE counter pointer per process
+        # the optimizer may only be captured behind the backward when the gradients it sees are final there: with a
+        # reducer whose all-reduce runs outside the graph it has to run after reducer.finish() / reduce() instead
+        self._opt_after_replay = False
         self.static_in = tuple(t.clone() for t in example_inputs)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -80,6 +84,7 @@ class GraphedTrainStep:
                     self.seed_step.add_(1)
                     out = staged_step()
         elif staged:
+            self._opt_after_replay = optimizer is not None
             with torch.no_grad():
                 gen = model.train_step_stages(*self.static_in)
                 out = None
@@ -96,7 +101,10 @@ class GraphedTrainStep:
                     if more:
                         self.graphs.append(torch.cuda.CUDAGraph())
         else:
-            if optimizer is not None:          # pointer table of the optimizer is built outside the capture
+            reduce_outside = reducer is not None and reducer.world > 1       # all-reduce runs after the replay
+            self._opt_after_replay = optimizer is not None and reduce_outside
+            capture_opt = optimizer is not None and not reduce_outside
+            if capture_opt:                    # pointer table of the optimizer is built outside the capture
                 with torch.cuda.stream(side):
                     model.train_step_grads(*self.static_in)
                     optimizer.step()
@@ -105,7 +113,7 @@ class GraphedTrainStep:
             with torch.cuda.graph(self.graph):
                 self.seed_step.add_(1)
                 out = model.train_step_grads(*self.static_in)
-                if optimizer is not None:
+                if capture_opt:
                     optimizer.step()
         self.static_out = tuple(o.detach() if torch.is_tensor(o) else o for o in out)
         # input pipeline: the next batch is copied host -> device into staging buffers on a side stream while the
@@ -115,9 +123,14 @@ class GraphedTrainStep:
         self._staged = None
         self._handover = None
 
+    _seed_owner = None
+
     def __del__(self):
         try:
-            lib().pvcr_set_seed_step(None)       # the counter tensor dies with this object
+            # the counter tensor dies with this object -- unless a younger GraphedTrainStep has registered its own since
+            if GraphedTrainStep._seed_owner == self.seed_step.data_ptr():
+                lib().pvcr_set_seed_step(None)
+                GraphedTrainStep._seed_owner = None
         except Exception:                        # noqa: BLE001  (interpreter shutdown)
             pass
 
@@ -131,7 +144,7 @@ class GraphedTrainStep:
     def _replay(self):
         if self.comm_in_graph:
             self.graph.replay()
-        elif len(self.graphs) > 1:
+        elif len(self.graphs) > 1 and self.reducer is not None:
             # stage i's gradients (bucket i) are final when graph i has run: their all-reduce overlaps graph i+1
             for i, g in enumerate(self.graphs):
                 g.replay()
@@ -144,6 +157,8 @@ class GraphedTrainStep:
             self.graph.replay()
             if self.reducer is not None:
                 self.reducer.reduce()
+        if self._opt_after_replay:             # clip + Adam on the REDUCED gradients (train.py:158-160)
+            self.optimizer.step()
 
     def prefetch(self, *inputs):
         """Start copying the NEXT step's inputs (pinned host tensors) to the device; returns immediately."""

@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as F_
+from ..utils import ixvr
 
 
 class Attention(nn.Module):
@@ -63,6 +64,7 @@ class S2VTAttModel(nn.Module):
         self.precision = precision
         self.teacher_force_prob = 1.0      # set by train.py:145 on every arch; unused here as in the reference
         self.last_alphas = None            # [L,B,N] attention weights of the latest forward (reference never exposes them)
+        self.last_token_nll = None         # [B,L] per-token loss of the latest fused forward_loss / train step
 
     # ---- plumbing -------------------------------------------------------------------------------------------
     def _seq_params(self):
@@ -88,6 +90,39 @@ class S2VTAttModel(nn.Module):
         return hs, cfg
 
     # ---- reference API --------------------------------------------------------------------------------------
+    def reset_parameter(self):
+        """Xavier-normal weights, bias 0.01 (model/S2VTAttModel.py:215-217; never called by the reference constructor)."""
+        self.apply(ixvr)
+
+    def encode_step(self, vid_feat, rnn_state=None):
+        """vid_feat [B,V], rnn_state [1,B,H] | None -> (output [1,B,H], rnn_state [1,B,H]): one encoder GRU step
+        (model/S2VTAttModel.py:63-78,219-229), the call SpatialNet makes per frame (model/SpatialNet.py:127)."""
+        r = self.encoder.rnn
+        h_prev = None if rnn_state is None else rnn_state.reshape(-1, self.hidden_size)
+        nsplit = self.NSPLIT[self.precision] if self.training else 3
+        h = F_.GruStep.apply(nsplit, vid_feat, h_prev, r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0)
+        out = h.unsqueeze(0)
+        return out, out
+
+    def decode(self, encoder_outs, encoder_final, s):
+        """encoder_outs [N,B,H], encoder_final [1,B,H], s [B,L] | None -> logits [B,L,Vc]
+        (model/S2VTAttModel.py:231-243; SpatialNet.py:140)."""
+        lin = self.decoder.pred_linear[1]
+        enc = encoder_outs.transpose(0, 1)
+        fin = encoder_final.reshape(-1, self.hidden_size)
+        if self.training:
+            assert s is not None
+            cfg = self._cfg(True)
+            hs, alphas = F_.S2VTAttDecode.apply(cfg, enc, fin, self._shifted(s, enc.shape[0]), *self._seq_params())
+            self.last_alphas = alphas
+            return F_.VocabLogits.apply(cfg, hs, lin.weight, lin.bias)
+        with torch.no_grad():
+            d = self.decoder
+            _, logits, alphas = F_.s2vtatt_decode_greedy(enc, fin, d.sos_id, d.max_len, self._seq_params(), lin.weight,
+                                                         lin.bias)
+        self.last_alphas = alphas
+        return logits
+
     def forward(self, vid_feats, s=None, frame_scale=None):
         """vid_feats [B,N,V], s [B,L] (required in training) -> logits [B,L,Vc] (model/S2VTAttModel.py:245-264)."""
         lin = self.decoder.pred_linear[1]
@@ -104,6 +139,7 @@ class S2VTAttModel(nn.Module):
         lin = self.decoder.pred_linear[1]
         hs, cfg = self._hidden_states(vid_feats, s, frame_scale)
         loss, stats, pred = F_.VocabCrossEntropy.apply(cfg, hs, lin.weight, lin.bias, s, s_len)
+        self.last_token_nll = cfg.get("token_nll")      # [B,L] unmasked per-token loss (criterion(...), train_utils.py:47-48)
         return loss, stats[0] / stats[1], pred
 
     def train_step_stages(self, vid_feats, s, s_len, frame_scale=None, deferred_join=False):
@@ -116,11 +152,17 @@ class S2VTAttModel(nn.Module):
         Lb = F_.lib()
         deferred_join = deferred_join and Lb.pvcr_side_mode(-1) != 0
         prev_mode = Lb.pvcr_side_mode(2) if deferred_join else None
+        ok = False
         try:
             out = yield from self._train_step_stages(vid_feats, s, s_len, frame_scale)
+            ok = True
         finally:
-            if deferred_join:
+            # deferred joins end here; after an exception (e.g. an allocation failure between two C calls) the lanes are
+            # joined and the one-shot staging notes dropped in any mode, so that nothing of the aborted step is trusted
+            # (or still being written) when a later step reuses the workspace addresses
+            if deferred_join or not ok:
                 F_.check(Lb.pvcr_side_join(F_.stream_ptr()), "pvcr_side_join")
+            if deferred_join:
                 Lb.pvcr_side_mode(prev_mode)
         return out
 
@@ -137,6 +179,7 @@ class S2VTAttModel(nn.Module):
                                                 *params)
         self.last_alphas = alphas
         loss, stats, pred = F_.VocabCrossEntropy.forward(c2, cfg, hs, lin.weight, lin.bias, s, s_len)
+        self.last_token_nll = cfg.get("token_nll")
         one = torch.ones((), dtype=torch.float32, device=hs.device)
         _, d_hs, d_w, d_b, _, _ = F_.VocabCrossEntropy.backward(c2, one, None, None)
         lin.weight.grad, lin.bias.grad = d_w, d_b

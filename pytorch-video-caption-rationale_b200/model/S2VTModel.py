@@ -73,6 +73,45 @@ class S2VTModel(nn.Module):
         return hs, cfg
 
     # ---- reference API --------------------------------------------------------------------------------------
+    def encode_step(self, vid_feat, rnn_state=None):
+        """vid_feat [B,V], rnn_state [1,B,H] | None -> (output [1,B,H], rnn_state [1,B,H]): one rnn1 step
+        (model/S2VTModel.py:57-72; SpatialNet.py:127)."""
+        r = self.rnn1
+        h_prev = None if rnn_state is None else rnn_state.reshape(-1, self.hidden_size)
+        nsplit = self.NSPLIT[self.precision] if self.training else 3
+        h = F_.GruStep.apply(nsplit, vid_feat, h_prev, r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0)
+        out = h.unsqueeze(0)
+        return out, out
+
+    def encode(self, vid_feats):
+        """vid_feats [B,N,V] -> (output [N,B,H], rnn_state [1,B,H]): rnn1 over the frames (model/S2VTModel.py:74-86),
+        step by step through ``encode_step`` (forward() itself hoists the input projection and never calls this)."""
+        state, outs = None, []
+        for n in range(vid_feats.shape[1]):
+            out, state = self.encode_step(vid_feats[:, n], state)
+            outs.append(out)
+        return torch.cat(outs, dim=0), state
+
+    def decode(self, output1, state1, s):
+        """output1 [N,B,H], state1 [1,B,H], s [B,L] | None -> logits [B,L,Vc] (model/S2VTModel.py:88-177; SpatialNet.py:140).
+        Teacher forcing only on this entry (scheduled sampling needs the fused forward())."""
+        lin = self.linear[1]
+        out1 = output1.transpose(0, 1)
+        st1 = state1.reshape(-1, self.hidden_size)
+        if self.training:
+            assert s is not None
+            assert self.teacher_force_prob >= 1.0, "decode(): scheduled sampling is only implemented on forward()"
+            cfg = self._cfg(True)
+            B, L = out1.shape[0], self.max_len
+            sos = torch.full((B, 1), self.sos_id, dtype=torch.long, device=s.device)
+            s_in = torch.cat((sos, s[:, :L - 1]), dim=1)
+            hs = F_.S2VTDecode.apply(cfg, out1, st1, s_in, *self._seq_params())
+            return F_.VocabLogits.apply(cfg, hs, lin.weight, lin.bias)
+        with torch.no_grad():
+            _, logits = F_.s2vt_decode_greedy(out1, st1, self.sos_id, self.max_len, self._seq_params(), lin.weight,
+                                              lin.bias)
+        return logits
+
     def forward(self, vid_feats, s=None, frame_scale=None):
         """vid_feats [B,N,V], s [B,L] (required in training) -> logits [B,L,Vc] (model/S2VTModel.py:179-202)."""
         lin = self.linear[1]
@@ -89,6 +128,7 @@ class S2VTModel(nn.Module):
         lin = self.linear[1]
         hs, cfg = self._hidden_states(vid_feats, s, frame_scale)
         loss, stats, pred = F_.VocabCrossEntropy.apply(cfg, hs, lin.weight, lin.bias, s, s_len)
+        self.last_token_nll = cfg.get("token_nll")
         return loss, stats[0] / stats[1], pred
 
     @torch.no_grad()

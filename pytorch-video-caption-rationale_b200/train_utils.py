@@ -8,9 +8,10 @@ import torch
 from ._lib import check, lib, ptr, stream_ptr
 
 
-def calc_sentence_mask(max_len, s_len):
-    """mask[b, l] = l < s_len[b]  (train_utils.py:22-35)."""
-    return (torch.arange(max_len, device=s_len.device)[None, :] < s_len[:, None]).float()
+def calc_sentence_mask(batch_size, max_len, s_len):
+    """mask[b, l] = l < s_len[b], float [batch_size, max_len]  (train_utils.py:22-35, same signature)."""
+    mask = torch.arange(0, max_len, device=s_len.device).expand(batch_size, -1)
+    return (mask < s_len.unsqueeze(-1)).float()
 
 
 class _MaskedCE(torch.autograd.Function):

@@ -22,7 +22,7 @@ def test_masked_loss_accuracy_on_reference_logits(tag):
     ref = logits.detach().clone().requires_grad_(True)
     B, L, Vc = ref.shape
     nll = torch.nn.functional.cross_entropy(ref.view(B * L, Vc), s.view(-1), reduction="none").view(B, L)
-    mask = TU.calc_sentence_mask(L, s_len)
+    mask = TU.calc_sentence_mask(B, L, s_len)
     ((nll * mask).sum(1) / s_len.float()).mean().backward()
     assert torch.allclose(logits.grad, ref.grad, atol=1e-7, rtol=1e-4)
 
