@@ -31,22 +31,26 @@ CPU_SAMPLE_VIDEOS = 32          # numpy-port fallback only
 NCU_TRAFFIC_FILE = os.path.join("profiles", "ncu_traffic.json")     # DRAM bytes per launch, from a committed ncu capture
 
 
-def make_config(world, precision, dropout):
+def make_config(world, precision, dropout, workload=None):
     """The `config` object of the JSON line -- the same for both arms (the reference arm runs THIS workload)."""
     d = DIMS
-    return dict(workload=WORKLOAD, per_gpu_batch=d["B"], global_batch=d["B"] * world, parallelism="dp%d" % world,
+    return dict(workload=workload or WORKLOAD, per_gpu_batch=d["B"], global_batch=d["B"] * world, parallelism="dp%d" % world,
                 precision=precision, dropout_p=dropout,
                 step="CUDA graph of one fwd+bwd (side lanes on; roofline pass times each kernel alone, lanes off)",
                 l2="per-step working set (inputs 42 MB + fp32 weights 101 MB + activations > 1 GB) exceeds "
                    "the 126 MB L2; no explicit flush", **{k: v for k, v in d.items() if k != "B"})
 
 
-def fwd_bwd_gflop(d):
-    """Algorithmic GFLOP of one fwd+bwd step (SURVEY.md section 8d table, cfg2 column)."""
+def fwd_bwd_gflop(d, rationale=False):
+    """Algorithmic GFLOP of one fwd+bwd step (cfg2 column, cfg3 with rationale=True)."""
     B, N, V, H, E, L, Vc = (d[k] for k in ("B", "N", "V", "H", "E", "L", "Vc"))
     enc_in = 2 * B * N * V * 3 * H
     fwd = (enc_in + 2 * B * N * H * 3 * H + 2 * B * N * H * H + 2 * B * L * H * H + 4 * B * L * N * H +
            2 * B * L * (H + E) * 3 * H + 2 * B * L * H * 3 * H + 2 * B * L * H * Vc)
+    if rationale:      # + generator biLSTM in-proj / recurrent / linear; its in-proj needs no dX, the encoder's now does
+        gen_in = 2 * B * N * V * 8 * H
+        fwd += gen_in + 2 * 2 * B * N * H * 4 * H + 2 * B * N * 2 * H * 2
+        return (3 * fwd - gen_in) / 1e9
     return (3 * fwd - enc_in) / 1e9        # the encoder input projection needs no dX (vid_feats has no grad)
 
 
@@ -246,9 +250,14 @@ def check_data_parallel_gradients(model, reducer, inputs, world, dev):
     import torch
     import torch.distributed as dist
     from pvcr_b200.graphs import GraphedTrainStep
-    drop = model.decoder.pred_linear[0]
-    p_prev = drop.p
-    drop.p = 0.0
+    drops = [m for m in model.modules() if isinstance(m, torch.nn.Dropout)]
+    p_prev = [m.p for m in drops]
+    for m in drops:
+        m.p = 0.0
+    gen_net = getattr(model, "gen", None)          # RationaleNet: fix the Gumbel draws (Exp(1) noise) of the step as well
+    if gen_net is not None:
+        B_, N_ = inputs[0].shape[:2]
+        gen_net.noise = torch.empty(B_ * N_, 2, device=dev).exponential_()
     try:
         step = GraphedTrainStep(model, inputs, warmup=0, reducer=reducer)
         step(*inputs)
@@ -272,7 +281,10 @@ def check_data_parallel_gradients(model, reducer, inputs, world, dev):
         return {"ok": ok, "buckets": len(reduced), "rel_err_vs_mean_of_local_grads": worst, "max_spread_across_ranks": spread,
                 "what": "in-graph NCCL step (dropout off) vs all-reduce-mean of per-rank eager gradients"}
     finally:
-        drop.p = p_prev
+        for m, pv in zip(drops, p_prev):
+            m.p = pv
+        if gen_net is not None:
+            gen_net.noise = None
 
 
 def run_ours(args):
@@ -310,9 +322,19 @@ def run_ours(args):
     g = Glove()
     g.word_vectors = [np.zeros(E, np.float32)] * Vc
     torch.manual_seed(123)
-    model = S2VTAttModel(g, args.dropout, H, V, L, precision=args.precision)
+    if args.workload == "cfg3":
+        # BASELINE.json configs[2]: RationaleNet + S2VTAtt joint training (model/RationaleNet.py, train_rationale.py:30-44),
+        # tau = 1, lambda_brev = lambda_cont = 1 (args.py:47-48); reported under profiles/, not the headline
+        from pvcr_b200.model import RationaleNet
+        wl_name = "cfg3_rationale_s2vtatt_msrvtt"
+        model = RationaleNet(g, args.dropout, H, V, L, 1.0, "s2vt-att", precision=args.precision)
+        emb = model.caption_net.decoder.embedding.weight
+    else:
+        wl_name = WORKLOAD
+        model = S2VTAttModel(g, args.dropout, H, V, L, precision=args.precision)
+        emb = model.decoder.embedding.weight
     with torch.no_grad():
-        model.decoder.embedding.weight.normal_(0.0, 0.4)
+        emb.normal_(0.0, 0.4)
     model = model.to(dev).train()
     tail_group = None
     if world > 1 and args.nccl_tail_ctas != args.nccl_ctas:
@@ -474,19 +496,19 @@ def run_ours(args):
     roofline["class_ms_per_step"] = classes
     roofline["split_planes"] = planes
     gemm_ms = classes.get("gemm_tcgen05", {}).get("ms_per_step", 0.0)
-    roofline["gemm_class"] = {"ms_per_step": gemm_ms, "algorithmic_gflop": fwd_bwd_gflop(d),
+    roofline["gemm_class"] = {"ms_per_step": gemm_ms, "algorithmic_gflop": fwd_bwd_gflop(d, args.workload == "cfg3"),
                               "executed_gflop": prof["gemm_tcgen05"][2] / prof_steps / 1e9 if "gemm_tcgen05" in prof else None,
-                              "tflops_algorithmic": fwd_bwd_gflop(d) / gemm_ms if gemm_ms else None,
-                              "frac": fwd_bwd_gflop(d) / gemm_ms / tensor_peak if gemm_ms else None}
+                              "tflops_algorithmic": fwd_bwd_gflop(d, args.workload == "cfg3") / gemm_ms if gemm_ms else None,
+                              "frac": fwd_bwd_gflop(d, args.workload == "cfg3") / gemm_ms / tensor_peak if gemm_ms else None}
     # the number that matters for the whole step: algorithmic FLOPs / measured step time / sustained tensor peak
-    roofline["step_frac"] = fwd_bwd_gflop(d) / ms_step / tensor_peak
-    roofline["step_tflops"] = fwd_bwd_gflop(d) / ms_step
+    roofline["step_frac"] = fwd_bwd_gflop(d, args.workload == "cfg3") / ms_step / tensor_peak
+    roofline["step_tflops"] = fwd_bwd_gflop(d, args.workload == "cfg3") / ms_step
 
     # second half of BASELINE.json's metric: greedy captions/sec (eval branch, model/S2VTAttModel.py:172-191) at the
     # same per-GPU batch, fp32-equivalent bf16x3 arithmetic (token ids bit-exact vs the fp32 reference), CUDA-graph
     # replay with the features resident; single GPU only (decoding does not communicate: N GPUs are N replicas)
     greedy = None
-    if world == 1 and not args.no_greedy:
+    if world == 1 and not args.no_greedy and args.workload == "cfg2":
         from pvcr_b200.graphs import GraphedGreedy
         model.eval()
         gg = GraphedGreedy(model, vid)
@@ -524,7 +546,7 @@ def run_ours(args):
 
     cpu = None
     eager = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload == "cfg2":
         from oracle import reference_runner as R
         if R.available():
             vps, dt, threads = cpu_reference_videos_per_sec(2, 1, args.dropout)
@@ -536,7 +558,7 @@ def run_ours(args):
             cpu = {"value": vps, "unit": "videos/s", "cores": cpu_cores(), "kind": "port",
                    "sample": "%d of the %d videos of one batch per step, 3 steps (numpy fp32 oracle port, threaded BLAS; "
                              "oracle/_ref absent)" % (CPU_SAMPLE_VIDEOS, B)}
-    if world == 1 and not args.no_eager:
+    if world == 1 and not args.no_eager and args.workload == "cfg2":
         del graphed
         torch.cuda.empty_cache()
         eager = eager_b200_reference(args.dropout)
@@ -546,7 +568,7 @@ def run_ours(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else args.precision,
         "data": "synthetic",
-        "config": make_config(world, args.precision, args.dropout),
+        "config": make_config(world, args.precision, args.dropout, wl_name),
         "e2e": {"value": B * world / (ms_e2e / 1e3), "unit": "videos/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "greedy": greedy, "with_optimizer": with_opt,
@@ -567,6 +589,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-greedy", action="store_true")
     ap.add_argument("--no-optimizer", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"],
+                    help="cfg2 = S2VTAtt (BASELINE.json's metric config, default); cfg3 = RationaleNet + S2VTAtt joint training")
     ap.add_argument("--no-eager", action="store_true", help="skip timing the reference modules in PyTorch eager on the GPU")
     ap.add_argument("--nccl-ctas", type=int, default=16)
     ap.add_argument("--nccl-tail-ctas", type=int, default=64)

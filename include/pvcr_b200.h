@@ -61,6 +61,10 @@ void pvcr_set_seed_step(const uint64_t* device_counter);
  * pvcr_side_mode returns the previous mode (a value outside 0..2 only queries). */
 int pvcr_side_mode(int mode);
 int pvcr_side_join(void* stream);
+/* `stream` waits for ONE lane's current point only (lane in 0..2); the other lanes stay un-joined.  Which lane produces
+ * which gradients in mode 2: after pvcr_s2vtatt_bwd_part(part = 1) lane 1 carries d W_ih(dec) / d embedding / d b_ih(dec),
+ * lane 0 d W_hh(dec) / d W_q, lane 2 d v / d b_hh(dec) / d W_k. */
+int pvcr_side_join_lane(void* stream, int lane);
 
 /* Tuning aid: in-kernel phase timestamps (clock64 of CTA 0, [step][8]) of the last persistent-kernel launch. */
 int pvcr_debug_phase_timing(int on);

@@ -3,11 +3,11 @@
 TEST / BASELINE INFRASTRUCTURE ONLY (see oracle/__init__.py): nothing under pytorch-video-caption-rationale_b200/ may
 import this.  The reference is pure Python (no native code), so "compiling the reference from the
 sources where they lie" means `py_compile`: every file of the path is compiled from /root/reference into a
-sourceless `.pyc` under oracle/_ref/ (git-ignored, not gpurun-ignored: it travels to the GPU box like our own built
-`.so`).  No reference source text is copied into the repository; the GPU box (same image, same CPython 3.12) imports
+bytecode file `<module>.bc` under oracle/_ref/ (git-ignored, not gpurun-ignored: it travels to the GPU box like our own
+built `.so`; the extension is not `.pyc` because snapshot tools commonly drop `*.pyc`).  No reference source text is copied into the repository; the GPU box (same image, same CPython 3.12) imports
 the bytecode.  Run by `__graft_entry__.build()` whenever /root/reference is present.
 
-    python oracle/build_ref.py            # -> oracle/_ref/{utils,train_utils}.pyc, oracle/_ref/model/*.pyc
+    python oracle/build_ref.py            # -> oracle/_ref/{utils,train_utils}.bc, oracle/_ref/model/*.bc
 """
 import os
 import py_compile
@@ -22,13 +22,13 @@ FILES = ["utils.py", "train_utils.py", "model/__init__.py", "model/S2VTModel.py"
 
 
 def build(force=False):
-    """-> list of written .pyc paths ([] when the reference tree is absent, e.g. on the GPU box)."""
+    """-> list of written bytecode paths ([] when the reference tree is absent, e.g. on the GPU box)."""
     if not os.path.isdir(REFERENCE):
         return []
     written = []
     for rel in FILES:
         src = os.path.join(REFERENCE, rel)
-        dst = os.path.join(OUT, rel[:-3] + ".pyc")
+        dst = os.path.join(OUT, rel[:-3] + ".bc")
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         if force or not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
             py_compile.compile(src, cfile=dst, dfile="reference/" + rel, doraise=True,

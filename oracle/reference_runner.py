@@ -8,6 +8,9 @@ train.py:157-158 (train.py itself needs tensorboardX / nlgeval, absent from the 
 in `run_iter` below).
 """
 import importlib
+import importlib.abc
+import importlib.machinery
+import importlib.util
 import os
 import sys
 
@@ -18,7 +21,27 @@ REF = os.path.join(HERE, "_ref")
 
 
 def available():
-    return os.path.exists(os.path.join(REF, "model", "S2VTAttModel.pyc"))
+    return os.path.exists(os.path.join(REF, "model", "S2VTAttModel.bc"))
+
+
+class _RefFinder(importlib.abc.MetaPathFinder):
+    """Imports `utils`, `train_utils`, `model` and `model.*` from the bytecode files oracle/build_ref.py wrote."""
+    NAMES = ("utils", "train_utils", "model")
+
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname.split(".")[0] not in self.NAMES:
+            return None
+        rel = fullname.replace(".", os.sep)
+        pkg = os.path.join(REF, rel, "__init__.bc")
+        mod = os.path.join(REF, rel + ".bc")
+        if os.path.exists(pkg):
+            loader = importlib.machinery.SourcelessFileLoader(fullname, pkg)
+            return importlib.util.spec_from_file_location(fullname, pkg, loader=loader,
+                                                          submodule_search_locations=[os.path.join(REF, rel)])
+        if os.path.exists(mod):
+            loader = importlib.machinery.SourcelessFileLoader(fullname, mod)
+            return importlib.util.spec_from_file_location(fullname, mod, loader=loader)
+        return None
 
 
 _mods = None
@@ -31,17 +54,18 @@ def modules():
         return _mods
     if not available():
         raise RuntimeError("oracle/_ref is missing: run `python oracle/build_ref.py` where /root/reference exists")
-    clash = [m for m in ("utils", "train_utils", "model") if m in sys.modules
+    clash = [m for m in _RefFinder.NAMES if m in sys.modules
              and not str(getattr(sys.modules[m], "__file__", "")).startswith(REF)]
     if clash:
         raise RuntimeError("modules %s already imported from elsewhere" % clash)
-    sys.path.insert(0, REF)
+    finder = _RefFinder()
+    sys.meta_path.insert(0, finder)
     try:
         names = ["utils", "train_utils", "model.S2VTModel", "model.S2VTAttModel", "model.RationaleNet",
                  "model.SpatialNet"]
         _mods = {n: importlib.import_module(n) for n in names}
     finally:
-        sys.path.remove(REF)
+        sys.meta_path.remove(finder)
     return _mods
 
 

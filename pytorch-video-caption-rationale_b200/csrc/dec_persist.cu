@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
 // several times faster here than tcgen05.mma's ~70 cycles per K=16 step (persist.cuh); the K-chunks of the exchange
 // buffer stream in with cp.async, two in flight, overlapping the MMAs of the previous chunk.
 constexpr int DEC_BWD_THREADS = DEC_THREADS;
-template <int NF>
+template <int NF, bool ACC_TANH>
 __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(const DecPersistBwd p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -617,9 +617,17 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float2 pf = __half22float2(pkr[m][e]);
-            const float e0 = tanh_approx(q8[2 * e] + pf.x), e1 = tanh_approx(q8[2 * e + 1] + pf.y);
-            dq8[2 * e] += ds * (1.f - e0 * e0);
-            dq8[2 * e + 1] += ds * (1.f - e1 * e1);
+            if (ACC_TANH) {        // derivative accurate to ~1e-7 relative (ex2 + rcp): see tanh_sech2
+              float t0, t1, g0, g1;
+              tanh_sech2(q8[2 * e] + pf.x, t0, g0);
+              tanh_sech2(q8[2 * e + 1] + pf.y, t1, g1);
+              dq8[2 * e] += ds * g0;
+              dq8[2 * e + 1] += ds * g1;
+            } else {
+              const float e0 = tanh_approx(q8[2 * e] + pf.x), e1 = tanh_approx(q8[2 * e + 1] + pf.y);
+              dq8[2 * e] += ds * (1.f - e0 * e0);
+              dq8[2 * e + 1] += ds * (1.f - e1 * e1);
+            }
           }
         }
       }
@@ -671,7 +679,7 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
 // One CTA per (video, 64-dim tile): thread = (dim, frame group); frames fg + 4m.  alpha, d score, q and dctx of all L
 // steps are staged in shared memory first, so the L x frames inner loops run without global-memory latency.
 constexpr int AG_DIMS = 64, AG_FG = 4;
-template <int NF>
+template <int NF, bool ACC_TANH>
 __global__ void __launch_bounds__(AG_DIMS * AG_FG) attn_grad_hoisted_kernel(const AttnGradArgs a) {
   extern __shared__ float ag_sm[];
   const int L = a.L, B = a.B, N = a.N, H = a.H;
@@ -711,8 +719,10 @@ __global__ void __launch_bounds__(AG_DIMS * AG_FG) attn_grad_hoisted_kernel(cons
     for (int m = 0; m < NF; ++m) {
       if (fg + AG_FG * m < N) {
         const float ds = dsl[AG_FG * m];
-        const float e = tanh_approx(q + pk[m]);      // hardware tanh (2^-11): measured +1e-3 on dW_k vs an exact
-        acc_pk[m] += ds * (1.f - e * e);             // derivative, 8x below the bf16 operand rounding; 2x cheaper
+        float e, g;
+        if (ACC_TANH) tanh_sech2(q + pk[m], e, g);   // accurate derivative (ex2 + rcp)
+        else { e = tanh_approx(q + pk[m]); g = 1.f - e * e; }     // hardware tanh (2^-11): +1e-3 on dW_k, 2x cheaper
+        acc_pk[m] += ds * g;
         acc_en[m] += all[AG_FG * m] * dc;
         dv += ds * e;
       }
@@ -743,8 +753,14 @@ int attn_grad_hoisted(const AttnGradArgs& a, cudaStream_t st) {
   PVCR_REQUIRE(smem <= 48 * 1024, "attn_grad_hoisted: L=%d N=%d needs %zu B of shared memory", a.L, a.N, smem);
   const dim3 grid(a.B, cdiv(a.H, AG_DIMS));
   LaunchScope ls_(KC_ATTN, st);
-  if (a.N <= AG_FG * 10) attn_grad_hoisted_kernel<10><<<grid, AG_DIMS * AG_FG, smem, st>>>(a);
-  else attn_grad_hoisted_kernel<20><<<grid, AG_DIMS * AG_FG, smem, st>>>(a);
+  static const bool approx = getenv("PVCR_TANH_APPROX_BWD") != nullptr;
+  if (approx) {
+    if (a.N <= AG_FG * 10) attn_grad_hoisted_kernel<10, false><<<grid, AG_DIMS * AG_FG, smem, st>>>(a);
+    else attn_grad_hoisted_kernel<20, false><<<grid, AG_DIMS * AG_FG, smem, st>>>(a);
+  } else {
+    if (a.N <= AG_FG * 10) attn_grad_hoisted_kernel<10, true><<<grid, AG_DIMS * AG_FG, smem, st>>>(a);
+    else attn_grad_hoisted_kernel<20, true><<<grid, AG_DIMS * AG_FG, smem, st>>>(a);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
 }
@@ -821,8 +837,12 @@ int dec_persist_bwd(const DecPersistBwd& p0, cudaStream_t st) {
   smem += (size_t)(DEC_THREADS / 32) * pl.u * pl.bsp * 4;        // partial product tiles of the 8 warps
   PVCR_REQUIRE(pl.u == 16 || pl.u == 8, "dec_persist_bwd: unit slice u=%d not supported by the mma.sync tiling", pl.u);
   PVCR_REQUIRE(smem <= 227 * 1024, "dec_persist_bwd: needs %zu B of shared memory", smem);
-  const void* kern = pl.NF == 2 ? (const void*)dec_persist_bwd_kernel<2>
-                     : (pl.NF == 5 ? (const void*)dec_persist_bwd_kernel<5> : (const void*)dec_persist_bwd_kernel<10>);
+  // PVCR_TANH_APPROX_BWD=1: single-MUFU hardware tanh (2^-11) in the attention gradient (A/B knob; measured +1e-3 on d W_q)
+  static const bool approx = getenv("PVCR_TANH_APPROX_BWD") != nullptr;
+  const void* kern = approx ? (pl.NF == 2 ? (const void*)dec_persist_bwd_kernel<2, false>
+                               : (pl.NF == 5 ? (const void*)dec_persist_bwd_kernel<5, false> : (const void*)dec_persist_bwd_kernel<10, false>))
+                            : (pl.NF == 2 ? (const void*)dec_persist_bwd_kernel<2, true>
+                               : (pl.NF == 5 ? (const void*)dec_persist_bwd_kernel<5, true> : (const void*)dec_persist_bwd_kernel<10, true>));
   PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   PVCR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DEC_BWD_THREADS, smem));

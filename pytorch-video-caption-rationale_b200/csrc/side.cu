@@ -149,6 +149,13 @@ int pvcr_side_mode(int mode) {
   return prev;
 }
 
+// `stream` waits for what has been enqueued on ONE lane so far (the other lanes keep running un-joined): lets a
+// data-parallel caller start the all-reduce of a gradient bucket as soon as the lane that produces it is done.
+int pvcr_side_join_lane(void* stream, int lane) {
+  if (lane < 0 || lane >= NLANES) { set_last_error("pvcr_side_join_lane: lane %d not in 0..%d", lane, NLANES - 1); return PVCR_ERR_ARG; }
+  return side_join_lane(static_cast<cudaStream_t>(stream), lane);
+}
+
 int pvcr_side_join(void* stream) {
   {   // the explicit join ends a step: notes about work staged for "the coming call" of that step do not outlive it
     std::lock_guard<std::mutex> g(g_mu);

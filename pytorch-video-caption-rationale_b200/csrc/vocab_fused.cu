@@ -78,6 +78,7 @@ struct EpiCeBwd {
   // instruction: 4x fewer LSU wavefronts, which were as long as the MMA main loop of a K = 512 tile.
   static constexpr int SMEM_PER_WARP = 2048;
   const float* bias; const long long* target; const float *lse2, *roww;      // lse2 = lse * log2(e)
+  const float* gscale;                                                       // device scalar d total / d loss (null = 1)
   bf16* D; long long ldD;
   int M, N;
   float l2, w; int t;
@@ -85,7 +86,7 @@ struct EpiCeBwd {
   __device__ __forceinline__ void attach(uint8_t* warp_smem) { stage = reinterpret_cast<uint4*>(warp_smem); }
   __device__ __forceinline__ void begin(int row, int) {
     l2 = 0.f; w = 0.f; t = -1;
-    if (row < M) { l2 = lse2[row]; w = roww[row]; t = (int)target[row]; }
+    if (row < M) { l2 = lse2[row]; w = roww[row] * (gscale ? __ldg(gscale) : 1.f); t = (int)target[row]; }
   }
   __device__ __forceinline__ void chunk(int row, int col0, int, float (&v)[32]) {
     const bool full = col0 + 32 <= N;
@@ -149,46 +150,74 @@ __global__ void __launch_bounds__(256) target_logit_kernel(const bf16* hs, long 
   if (lane == 0) tgt2[row] = (s + bias[t]) * LOG2E;
 }
 
-// one warp per row: combine the per-tile partials
-__global__ void __launch_bounds__(256) ce_finalize_rows_kernel(const float* pmax, const float* psum, const int* pidx,
-                                                               const float* tgt, int M, int ntiles, float* lse_out,
-                                                               float* nll_out, long long* pred_out) {
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (row >= M) return;
-  float m = -INFINITY; int mi = 0x7fffffff;
-  for (int k = lane; k < ntiles; k += 32) {
-    const float v = pmax[(long long)row * ntiles + k];
-    const int i = pidx[(long long)row * ntiles + k];
-    if (v > m || (v == m && i < mi)) { m = v; mi = i; }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float om = __shfl_xor_sync(0xffffffffu, m, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
-    if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
-  }
-  float s = 0.f;
-  for (int k = lane; k < ntiles; k += 32)
-    s += psum[(long long)row * ntiles + k] * exp2f(pmax[(long long)row * ntiles + k] - m);
-  s = warp_sum(s);
-  if (lane == 0) {
-    const float lse2 = m + log2f(s);              // log2 domain (see EpiCeFwd)
-    lse_out[row] = lse2 * LN2;
-    nll_out[row] = (lse2 - tgt[row]) * LN2;
-    pred_out[row] = mi == 0x7fffffff ? 0 : mi;
-  }
-}
-
-// w[row] = (l < s_len[b]) / (s_len[b] * B) * gscale
-__global__ void row_weights_kernel(const long long* s_len, int B, int L, const float* gscale, float* w,
-                                   const float* lse, float* lse2) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * L) return;
-  lse2[i] = lse[i] * LOG2E;
-  const int b = i / L, l = i % L;
+// Finalize of the fused forward, ONE launch: block b owns the L tokens of video b (one warp per token at a time):
+//   * combines the per-tile partials of the GEMM epilogue into lse / nll / arg-max per token,
+//   * writes what the backward needs per token: lse in the log2 domain and the row weight
+//     (l < s_len[b]) / (min(s_len[b], L) * B) of calc_masked_loss (train_utils.py:47-51),
+//   * reduces the video's masked mean loss / #correct / #mask, and the last block to finish adds the B per-video values in
+//     video order (deterministic) into loss3 -- the former ce_finalize_rows + loss_finalize + row_weights launches.
+constexpr int CE_MAX_L = 256;
+__global__ void __launch_bounds__(256) ce_finalize_kernel(const float* pmax, const float* psum, const int* pidx,
+                                                          const float* tgt, const long long* target, const long long* s_len,
+                                                          int B, int L, int ntiles, float* lse_out, float* nll_out,
+                                                          long long* pred_out, float* lse2_out, float* roww_out,
+                                                          float* token_nll, float* partial, unsigned* counter, float* loss3) {
+  __shared__ float s_nll[CE_MAX_L];
+  __shared__ float s_ok[CE_MAX_L];
+  __shared__ bool last;
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long len = s_len[b];
-  const float cnt = (float)(len < L ? len : L);      // mask.sum(dim=1) of the reference (train_utils.py:50-51)
-  w[i] = (l < len ? 1.f / (cnt * (float)B) : 0.f) * (gscale ? gscale[0] : 1.f);
+  const float cnt = (float)(len < L ? len : L);
+  for (int l = warp; l < L; l += 8) {
+    const int row = b * L + l;
+    float m = -INFINITY; int mi = 0x7fffffff;
+    for (int k = lane; k < ntiles; k += 32) {
+      const float v = pmax[(long long)row * ntiles + k];
+      const int i = pidx[(long long)row * ntiles + k];
+      if (v > m || (v == m && i < mi)) { m = v; mi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, m, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+      if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+    }
+    float s = 0.f;
+    for (int k = lane; k < ntiles; k += 32)
+      s += psum[(long long)row * ntiles + k] * exp2f(pmax[(long long)row * ntiles + k] - m);
+    s = warp_sum(s);
+    if (lane == 0) {
+      const float lse2 = m + log2f(s);              // log2 domain (see EpiCeFwd)
+      const float nll = (lse2 - tgt[row]) * LN2;
+      const long long pr = mi == 0x7fffffff ? 0 : mi;
+      lse_out[row] = lse2 * LN2;
+      nll_out[row] = nll;
+      pred_out[row] = pr;
+      lse2_out[row] = lse2;
+      roww_out[row] = l < len ? 1.f / (cnt * (float)B) : 0.f;
+      if (token_nll) token_nll[row] = nll;
+      s_nll[l] = nll;
+      s_ok[l] = pr == target[row] ? 1.f : 0.f;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sum = 0.f, corr = 0.f, n = 0.f;
+    for (int l = 0; l < L && l < len; ++l) { sum += s_nll[l]; corr += s_ok[l]; n += 1.f; }
+    partial[3 * b] = sum / cnt; partial[3 * b + 1] = corr; partial[3 * b + 2] = n;
+    __threadfence();
+    last = atomicAdd(counter, 1u) == (unsigned)(B - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    float loss = 0.f, corr = 0.f, n = 0.f;
+    for (int i = 0; i < B; ++i) {
+      loss += __ldcg(partial + 3 * i); corr += __ldcg(partial + 3 * i + 1); n += __ldcg(partial + 3 * i + 2);
+    }
+    loss3[0] = loss / (float)B; loss3[1] = corr; loss3[2] = n;
+    *counter = 0u;                                  // ready for the next launch (stream order)
+  }
 }
 
 // out[c] += sum_r in[r*ld + c]  (bf16 in, fp32 accumulate; out pre-zeroed): block = 64 column pairs x 4 row lanes
@@ -242,7 +271,8 @@ static int ce_parts() { return (ce_ew16() || ce_pair()) ? 4 : 2; }
 
 struct FusedWs {
   Planes hs_a, wv;
-  float *pmax, *psum, *tgt, *nll, *roww;
+  float *pmax, *psum, *tgt, *nll, *roww, *lse2, *partial;
+  unsigned* counter;              // zero between launches (the finalize kernel resets it); zeroed by the first forward
   int* pidx;
   bf16* D;
   long long ldD;
@@ -254,7 +284,8 @@ static void carve_fused(Arena& a, int M, int H, int Vc, FusedWs& w) {
   w.wv = alloc_planes(a, Vc, H, 1);
   w.pmax = a.alloc<float>((size_t)M * w.ntiles); w.psum = a.alloc<float>((size_t)M * w.ntiles);
   w.pidx = a.alloc<int>((size_t)M * w.ntiles);
-  w.tgt = a.alloc<float>(M); w.nll = a.alloc<float>(M); w.roww = a.alloc<float>(M);
+  w.tgt = a.alloc<float>(M); w.nll = a.alloc<float>(M); w.roww = a.alloc<float>(M); w.lse2 = a.alloc<float>(M);
+  w.partial = a.alloc<float>((size_t)3 * M); w.counter = a.alloc<unsigned>(32);
   w.ldD = (long long)cdiv(Vc, CE_BN) * CE_BN;
   w.D = a.alloc<bf16>((size_t)M * w.ldD);
 }
@@ -294,12 +325,16 @@ int vocab_fused_fwd(const float* hs, const float* wv, const float* bv, const lon
   PVCR_TRY(stage(hs, H, M, H, w.hs_a, 0, nullptr, fused_out_dropout(dropout_p, seed), st));
   if (side_note_take(ws, NOTE_VOCAB_WV, wv)) PVCR_TRY(side_join(st));       // staged by vocab_fused_prepare on a lane
   else PVCR_TRY(prep_weight(wv, H, Vc, H, w.wv, st));
+  // the target logit of every token only feeds the finalize: it runs on a side lane next to the projection GEMM
+  cudaStream_t lt = st;
+  if (side_site(4)) PVCR_TRY(side_fork(st, &lt, 1));
   {
-    LaunchScope ls_(KC_LOSS, st);
-    target_logit_kernel<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(w.hs_a.ptr, w.hs_a.ld, w.wv.ptr, w.wv.ld, bv, target,
+    LaunchScope ls_(KC_LOSS, lt);
+    target_logit_kernel<<<cdiv((long long)M * 32, 256), 256, 0, lt>>>(w.hs_a.ptr, w.hs_a.ld, w.wv.ptr, w.wv.ld, bv, target,
                                                                       M, H, w.tgt);
   }
   PVCR_CUDA_CHECK(cudaGetLastError());
+  PVCR_CUDA_CHECK(cudaMemsetAsync(w.counter, 0, sizeof(unsigned), lt));
   EpiCeFwd epi{};
   epi.bias = bv; epi.pmax = w.pmax; epi.psum = w.psum; epi.pidx = w.pidx;
   epi.M = M; epi.N = Vc; epi.nparts = w.ntiles;
@@ -308,14 +343,15 @@ int vocab_fused_fwd(const float* hs, const float* wv, const float* bv, const lon
   else if (ce_multicast()) PVCR_TRY((launch_gemm_tn_mc2<CE_BN, 4, EpiCeFwd>(w.hs_a.view(), w.wv.view(), gc, epi, st)));
   else if (ce_ew16()) PVCR_TRY((launch_gemm_tn_persistent<CE_BN, 4, EpiCeFwd, false, false, 16>(w.hs_a.view(), w.wv.view(), gc, 1, epi, st)));
   else PVCR_TRY((launch_gemm_tn_persistent<CE_BN, 4, EpiCeFwd>(w.hs_a.view(), w.wv.view(), gc, 1, epi, st)));
+  if (lt != st) PVCR_TRY(side_join_lane(st, 1));
+  PVCR_REQUIRE(L <= CE_MAX_L, "vocab_fused_fwd: L=%d > %d", L, CE_MAX_L);
   {
     LaunchScope ls_(KC_LOSS, st);
-    ce_finalize_rows_kernel<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(w.pmax, w.psum, w.pidx, w.tgt, M, w.ntiles, lse,
-                                                                          w.nll, pred);
+    ce_finalize_kernel<<<B, 256, 0, st>>>(w.pmax, w.psum, w.pidx, w.tgt, target, s_len, B, L, w.ntiles, lse, w.nll, pred,
+                                          w.lse2, w.roww, token_nll, w.partial, w.counter, loss3);
   }
   PVCR_CUDA_CHECK(cudaGetLastError());
-  if (token_nll) PVCR_CUDA_CHECK(cudaMemcpyAsync(token_nll, w.nll, sizeof(float) * M, cudaMemcpyDeviceToDevice, st));
-  return loss_finalize(w.nll, pred, target, s_len, B, L, loss3, st);
+  return PVCR_OK;
 }
 
 int vocab_fused_bwd(const float* hs, const float* wv, const float* bv, const long long* target, const long long* s_len,
@@ -327,14 +363,10 @@ int vocab_fused_bwd(const float* hs, const float* wv, const float* bv, const lon
   carve_fused(a, M, H, Vc, w);
   if (a.failed) { set_last_error("vocab_fused_bwd: workspace too small"); return PVCR_ERR_WORKSPACE; }
   const Dropout dr = fused_out_dropout(dropout_p, seed);
-  {
-    LaunchScope ls_(KC_LOSS, st);
-    row_weights_kernel<<<cdiv(M, 256), 256, 0, st>>>(s_len, B, L, gscale, w.roww, lse, w.nll);
-  }
-  PVCR_CUDA_CHECK(cudaGetLastError());
-  // recompute the logits tile by tile; the epilogue emits bf16 dlogits (row-major and transposed)
+  // recompute the logits tile by tile; the epilogue emits bf16 dlogits (row-major and transposed).  lse (log2 domain)
+  // and the row weights of calc_masked_loss were left in the workspace by the forward's finalize kernel.
   EpiCeBwd epi{};
-  epi.bias = bv; epi.target = target; epi.lse2 = w.nll; epi.roww = w.roww;     // w.nll reused: lse * log2(e)
+  epi.bias = bv; epi.target = target; epi.lse2 = w.lse2; epi.roww = w.roww; epi.gscale = gscale;
   epi.D = w.D; epi.ldD = w.ldD; epi.M = M; epi.N = Vc;
   if (w.ldD > Vc)      // chunks lying entirely past Vc are skipped by the GEMM epilogue: their K-padding must read 0
     PVCR_CUDA_CHECK(cudaMemset2DAsync(w.D + Vc, sizeof(bf16) * w.ldD, 0, sizeof(bf16) * (w.ldD - Vc), M, st));

@@ -317,13 +317,26 @@ class GeneratorSelect(torch.autograd.Function):
         return probs, p1, pen
 
     @staticmethod
-    def backward(ctx, d_probs, d_p1, d_pen):
+    def backward(ctx, d_probs, d_p1, d_pen, grad_out=None):
+        """grad_out (tape-free callers only): {field: existing gradient buffer} written in place where shape / dtype
+        match (views into a flat all-reduce bucket)."""
         vid_c, ws, tensors = ctx.keep
         dev = vid_c.device
         H4, V = tensors["w_ih"].shape
-        wih_cat = torch.empty((2 * H4, V), dtype=torch.float32, device=dev)       # both directions: one GEMM
-        grads = {f: torch.empty_like(t) for f, t in tensors.items() if f not in ("w_ih", "w_ih_r")}
-        grads["w_ih"], grads["w_ih_r"] = wih_cat[:H4], wih_cat[H4:]
+        grad_out = grad_out or {}
+
+        def usable(f):
+            g = grad_out.get(f)
+            t = tensors[f]
+            return g is not None and g.shape == t.shape and g.dtype == torch.float32 and g.is_contiguous() and g.device == t.device
+
+        grads = {f: (grad_out[f] if usable(f) else torch.empty_like(t)) for f, t in tensors.items()
+                 if f not in ("w_ih", "w_ih_r")}
+        if usable("w_ih") and usable("w_ih_r"):       # adjacent or not: the C side checks and issues one or two GEMMs
+            grads["w_ih"], grads["w_ih_r"] = grad_out["w_ih"], grad_out["w_ih_r"]
+        else:
+            wih_cat = torch.empty((2 * H4, V), dtype=torch.float32, device=dev)       # both directions: one GEMM
+            grads["w_ih"], grads["w_ih_r"] = wih_cat[:H4], wih_cat[H4:]
         ps = _fill_struct(PvcrGenParams(), GEN_PARAM_FIELDS, tensors)
         gs = _fill_struct(PvcrGenGrads(), GEN_PARAM_FIELDS, grads)
         d_probs = None if d_probs is None else _f32c(d_probs)

@@ -54,18 +54,24 @@ class GraphedTrainStep:
                 main = torch.cuda.current_stream()
                 gen = model.train_step_stages(*self.static_in, deferred_join=True)
                 i = 0
+                overlapped = getattr(model, "OVERLAPPED_STAGES", 1)
                 while True:
                     try:
-                        next(gen)
+                        stage = next(gen)
                     except StopIteration as done:
                         res = done.value
                         break
                     aux.wait_stream(main)
                     with torch.cuda.stream(aux):
-                        check(lib().pvcr_side_join(stream_ptr()), "pvcr_side_join")     # aux waits for the lanes
-                        # only the first bucket (vocabulary gradients) really overlaps the backward: the lanes that
-                        # produce the later ones finish with the last sweep
-                        reducer.begin(i, tail=i > 0)
+                        # aux waits for the lane(s) that produce this stage's gradients: one lane when the stage names
+                        # it, else all of them
+                        if isinstance(stage, tuple):
+                            check(lib().pvcr_side_join_lane(stream_ptr(), int(stage[1])), "pvcr_side_join_lane")
+                        else:
+                            check(lib().pvcr_side_join(stream_ptr()), "pvcr_side_join")
+                        # buckets that become final while a persistent sweep is still to come go through the narrow
+                        # communicator (the sweep needs its 128 SMs co-resident); the later ones through the wide one
+                        reducer.begin(i, tail=i >= overlapped)
                     i += 1
                 main.wait_stream(aux)
                 for j in range(i, len(reducer.buckets)):

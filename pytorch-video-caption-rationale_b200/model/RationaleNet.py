@@ -76,23 +76,54 @@ class RationaleNet(nn.Module):
         loss_brev, loss_cont = pen[0] * lambda_brev, pen[1] * lambda_cont
         return acc, loss_ce + loss_brev + loss_cont, loss_ce, loss_brev, loss_cont, pen[0].detach(), pred, probs
 
-    @torch.no_grad()
-    def train_step_grads(self, vid_feats, s, s_len, lambda_brev=1.0, lambda_cont=1.0):
-        """Tape-free fwd+bwd of the joint objective (CUDA-graph capturable); (over)writes every ``param.grad``.
-        -> (loss, acc, pred)."""
+    def train_step_stages(self, vid_feats, s, s_len, lambda_brev=1.0, lambda_cont=1.0, deferred_join=False):
+        """Generator form of the tape-free joint step (train_rationale.py:30-44 + backward): passes the caption network's
+        stages through, yields once more when ALL caption-network gradients are final (the generator's backward -- two
+        LSTM sweeps and the 86-GFLOP input-projection gradient -- still to come), and returns (loss, acc, pred).  A
+        data-parallel caller overlaps each stage's all-reduce with what follows (parallel.GradAllReducer)."""
         assert self.training and s is not None
         gen, cap = self.gen, self.caption_net
         cg = F_.ManualCtx()
         gparams = gen._params()
         probs, p1, pen = F_.GeneratorSelect.forward(cg, gen._cfg(), vid_feats, gen.noise, *gparams)
         p1.requires_grad_(True)          # makes the caption network emit d loss / d frame_scale
-        loss_ce, acc, pred = cap.train_step_grads(vid_feats, s, s_len, frame_scale=p1)
+        if hasattr(cap, "train_step_stages"):
+            loss_ce, acc, pred = yield from cap.train_step_stages(vid_feats, s, s_len, frame_scale=p1,
+                                                                  deferred_join=deferred_join)
+        else:
+            loss_ce, acc, pred = cap.train_step_grads(vid_feats, s, s_len, frame_scale=p1)
+        yield "caption_net_grads"
         dev = vid_feats.device         # fill kernels (no host-to-device copy): stays CUDA-graph capturable
         d_pen = torch.cat([torch.full((1,), float(lambda_brev), device=dev), torch.full((1,), float(lambda_cont), device=dev)])
-        grads = F_.GeneratorSelect.backward(cg, None, cap.last_frame_scale_grad, d_pen)
+        given = {f: p.grad for f, p in zip(F_.GEN_PARAM_FIELDS, gparams) if p.grad is not None}
+        grads = F_.GeneratorSelect.backward(cg, None, cap.last_frame_scale_grad, d_pen, grad_out=given)
         for p, g in zip(gparams, grads[3:]):
             p.grad = g
         return loss_ce + lambda_brev * pen[0] + lambda_cont * pen[1], acc, pred
+
+    def early_grad_params(self):
+        """Per yield of train_step_stages, the parameters whose gradients are final at that point."""
+        cap = self.caption_net
+        early = [list(e) for e in cap.early_grad_params()] if hasattr(cap, "early_grad_params") else []
+        seen = {id(p) for e in early for p in e}
+        early.append([p for p in cap.parameters() if id(p) not in seen])
+        return early
+
+    @property
+    def OVERLAPPED_STAGES(self):
+        # every caption-network bucket is followed by a persistent sweep (the generator's LSTM backward at the latest)
+        return len(self.early_grad_params())
+
+    @torch.no_grad()
+    def train_step_grads(self, vid_feats, s, s_len, lambda_brev=1.0, lambda_cont=1.0):
+        """Tape-free fwd+bwd of the joint objective (CUDA-graph capturable); (over)writes every ``param.grad``.
+        -> (loss, acc, pred)."""
+        gen = self.train_step_stages(vid_feats, s, s_len, lambda_brev, lambda_cont, deferred_join=True)
+        try:
+            while True:
+                next(gen)
+        except StopIteration as done:
+            return done.value
 
     @torch.no_grad()
     def greedy(self, vid_feats):

@@ -190,6 +190,9 @@ class S2VTAttModel(nn.Module):
             for f, p in zip(F_.ATT_SEQ_FIELDS, params):
                 if not f.startswith("enc_"):
                     p.grad = part_grads[f]
+            # the embedding gradient (the bulk of the decoder half: Vc x E) is produced by side lane 1 alone, early in
+            # the shadow of the encoder sweep: a data-parallel caller can start its all-reduce after joining THAT lane
+            yield ("embedding_grad", 1)
             yield "decoder_grads"
             next(seq)
             raise RuntimeError("backward_in_parts yielded more than once")
@@ -201,12 +204,17 @@ class S2VTAttModel(nn.Module):
         return loss, stats[0] / stats[1], pred
 
     def early_grad_params(self):
-        """Per yield of train_step_stages, the parameters whose gradients are final at that point."""
+        """Per yield of train_step_stages, the parameters whose gradients are final at that point (a yield is a name, or
+        a (name, lane) pair when joining that one side lane of the library is enough)."""
         lin = self.decoder.pred_linear[1]
         d = self.decoder
-        dec = [d.embedding.weight, d.rnn.weight_ih_l0, d.rnn.weight_hh_l0, d.rnn.bias_ih_l0, d.rnn.bias_hh_l0,
+        dec = [d.rnn.weight_ih_l0, d.rnn.weight_hh_l0, d.rnn.bias_ih_l0, d.rnn.bias_hh_l0,
                d.attention.key_layer.weight, d.attention.query_layer.weight, d.attention.energy_layer.weight]
-        return [[lin.bias, lin.weight], dec]
+        return [[lin.bias, lin.weight], [d.embedding.weight, d.rnn.weight_ih_l0, d.rnn.bias_ih_l0],
+                [p for p in dec if p is not d.rnn.weight_ih_l0 and p is not d.rnn.bias_ih_l0]]
+
+    # buckets whose all-reduce overlaps a persistent sweep must stay within the SMs the sweep leaves free
+    OVERLAPPED_STAGES = 2
 
     @torch.no_grad()
     def train_step_grads(self, vid_feats, s, s_len, frame_scale=None):
