@@ -26,8 +26,14 @@ constexpr int DEC_THREADS = 256;
 constexpr int DEC_ITEMS = 4;      // (unit, video) pairs per thread: u * bs <= DEC_ITEMS * DEC_THREADS
 
 
-template <int NF>
-__global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const DecPersistFwd p) {
+// TMA: the exchanged operands (h_{i-1} and ctx of the group's videos, 32 KB each) are fetched by KB bulk-tensor copies
+// issued by ONE thread straight into the swizzled operand buffer (tmH0 / tmHs / tmCtx describe enc-final rows, hs_a as
+// (k, video, step) and ctx_x as (k, video, step)) instead of 2048 16-byte cp.async requests spread over the CTA.
+template <int NF, bool ACC_TANH = false, bool TMA = true>
+__global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const DecPersistFwd p,
+                                                                         const __grid_constant__ CUtensorMap tmH0,
+                                                                         const __grid_constant__ CUtensorMap tmHs,
+                                                                         const __grid_constant__ CUtensorMap tmCtx) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int H = p.H, u = p.u, C = p.C, bsp = p.bsp, N = p.N, L = p.L, B = p.B, KB = H >> 6;
@@ -43,7 +49,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
   float* sScore = sP + (size_t)N * PW;      // [N]
   float* sC = sScore + N;                   // [FG][H]
   uint64_t* bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sC + (size_t)FG * H) + 15) & ~uintptr_t(7));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint64_t* bar_x = bar + 1;                 // TMA: the exchanged operand has landed in sX
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int g = blockIdx.x / C, c = blockIdx.x % C;
@@ -58,8 +65,11 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
   }
   if (tid == 0) {
     mbar_init(bar, 1);
+    mbar_init(bar_x, 1);
     fence_barrier_init();
   }
+  uint32_t phase_x = 0;
+  const uint32_t x_bytes = (uint32_t)KB * (uint32_t)bsp * 128u;
   const uint32_t ncols = 2 * bsp <= 32 ? 32u : (2 * bsp <= 64 ? 64u : (2 * bsp <= 128 ? 128u : 256u));
   if (warp == 0) {
     tmem_alloc(tmem_slot, ncols);
@@ -136,6 +146,26 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
     }
     // ---- P1: [q | gh] = [W_q; W_hh] h_{i-1} -------------------------------------------------------------
     phase_stamp(p.dbg, i, 0);
+    if (TMA) {
+      if (tid == 0) {
+        if (i > 0 && ld_acquire_u32(ctr) < target) {
+          const long long t0 = clock64();
+          while (ld_acquire_u32(ctr) < target) {
+            if (clock64() - t0 > 4000000000LL) __trap();
+          }
+        }
+        phase_stamp(p.dbg, i, 1);
+        fence_proxy_async();                  // the other CTAs' generic-proxy stores (acquired above) before async-proxy reads
+        mbar_arrive_expect_tx(bar_x, x_bytes);
+        for (int kb = 0; kb < KB; ++kb)
+          tma_load_3d(sX + (size_t)kb * bsp * 128, i > 0 ? &tmHs : &tmH0, bar_x, kb * 64, b0, i > 0 ? i - 1 : 0);
+        mbar_wait(bar_x, phase_x);
+        phase_stamp(p.dbg, i, 2);
+        tc_fence_after();
+        issue_swapped_mma(tmem_d1, smem_u32(sW1), R1, smem_u32(sX), bsp, H, idesc, bar);
+      }
+      phase_x ^= 1;
+    } else {
     if (i > 0) {
       group_wait(ctr, target);
       phase_stamp(p.dbg, i, 1);
@@ -152,6 +182,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
     if (tid == 0) {
       tc_fence_after();
       issue_swapped_mma(tmem_d1, smem_u32(sW1), R1, smem_u32(sX), bsp, H, idesc, bar);
+    }
     }
     mbar_wait(bar, phase);
     phase ^= 1;
@@ -187,7 +218,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 pf = __half22float2(pkr[m][e]);
-          s += v8[2 * e] * tanh_approx(q8[2 * e] + pf.x) + v8[2 * e + 1] * tanh_approx(q8[2 * e + 1] + pf.y);
+          if (ACC_TANH) s += v8[2 * e] * fast_tanh(q8[2 * e] + pf.x) + v8[2 * e + 1] * fast_tanh(q8[2 * e + 1] + pf.y);
+          else s += v8[2 * e] * tanh_approx(q8[2 * e] + pf.x) + v8[2 * e + 1] * tanh_approx(q8[2 * e + 1] + pf.y);
         }
         sc[m] = s;
       }
@@ -269,6 +301,24 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
     target += (unsigned)C;
     phase_stamp(p.dbg, i, 6);
     // ---- P3: gi_c = W_c ctx -----------------------------------------------------------------------------
+    if (TMA) {
+      if (tid == 0) {
+        if (ld_acquire_u32(ctr) < target) {
+          const long long t0 = clock64();
+          while (ld_acquire_u32(ctr) < target) {
+            if (clock64() - t0 > 4000000000LL) __trap();
+          }
+        }
+        phase_stamp(p.dbg, i, 7);
+        fence_proxy_async();
+        mbar_arrive_expect_tx(bar_x, x_bytes);
+        for (int kb = 0; kb < KB; ++kb) tma_load_3d(sX + (size_t)kb * bsp * 128, &tmCtx, bar_x, kb * 64, b0, i);
+        mbar_wait(bar_x, phase_x);
+        tc_fence_after();
+        issue_swapped_mma(tmem_d2, smem_u32(sW3), R3, smem_u32(sX), bsp, H, idesc, bar);
+      }
+      phase_x ^= 1;
+    } else {
     group_wait(ctr, target);
     phase_stamp(p.dbg, i, 7);
     load_operand_rows_async(sX, bsp, 0, p.ctx_x + (long long)i * B * H, H, b0, bsp, b0 + bs, H);
@@ -279,6 +329,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
     if (tid == 0) {
       tc_fence_after();
       issue_swapped_mma(tmem_d2, smem_u32(sW3), R3, smem_u32(sX), bsp, H, idesc, bar);
+    }
     }
     mbar_wait(bar, phase);
     phase ^= 1;
@@ -334,8 +385,9 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
 // several times faster here than tcgen05.mma's ~70 cycles per K=16 step (persist.cuh); the K-chunks of the exchange
 // buffer stream in with cp.async, two in flight, overlapping the MMAs of the previous chunk.
 constexpr int DEC_BWD_THREADS = DEC_THREADS;
-template <int NF, bool ACC_TANH>
-__global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(const DecPersistBwd p) {
+template <int NF, bool ACC_TANH, bool TMA = true>
+__global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(const DecPersistBwd p,
+                                                                             const __grid_constant__ CUtensorMap tmXg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int H = p.H, u = p.u, C = p.C, bsp = p.bsp, N = p.N, L = p.L, B = p.B, KBH = H >> 6;
@@ -352,6 +404,9 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
   float* sDa = sP + (size_t)N * PW;         // [N] d alpha -> d score
   float* sAl = sDa + N;                     // [N] alpha
   float* sC = sAl + N;                      // [FG][H]
+  uint64_t* bar0 = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sC + (size_t)FG * H) + 15) & ~uintptr_t(7));
+  uint64_t* bar1 = bar0 + 1;                // TMA: chunk buffer X0 / X1 has landed
+  uint32_t ph0 = 0, ph1 = 0;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int g = blockIdx.x / C, c = blockIdx.x % C;
@@ -361,6 +416,11 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
 
   load_operand_rows(sWA, u, 0, p.wcT, p.wcT_ld, j0, u, H, 3 * H);
   load_operand_rows(sWB, u, 0, p.wcatT, p.wcatT_ld, j0, u, H, 4 * H);
+  if (TMA && tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar1, 1);
+    fence_barrier_init();
+  }
   __syncthreads();
   const uint32_t aWA = smem_u32(sWA), aWB = smem_u32(sWB), aX0 = smem_u32(sX0), aX1 = smem_u32(sX1);
   const int lane = tid & 31, gid = lane >> 2, tig = lane & 3, nwarps = DEC_THREADS / 32;
@@ -513,6 +573,27 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
 #pragma unroll
       for (int e = 0; e < 4; ++e) { accA[nt][e] = 0.f; accB[nt][e] = 0.f; }
     // chunks drp -> X0, dzp -> X1 in flight; then dnp -> X0, dghn -> X1 behind the MMAs that free the buffers
+    if (TMA) {
+      // (the group_wait above gave every thread the acquire; its CTA barrier also fences the previous readers of X0 / X1)
+      if (tid == 0) {
+        tma_fetch_operand(sX0, bsp, 0, &tmXg, bar0, H, KBH, b0, i & 1);
+        tma_fetch_operand(sX1, bsp, 0, &tmXg, bar1, 2 * H, KBH, b0, i & 1);
+      }
+      mbar_wait(bar0, ph0); ph0 ^= 1;
+      mma_chunk(accA, aWA, 0, aX0);                 // drp: W_c^T chunk 0, [W_q|W_hh]^T chunk 1
+      mma_chunk(accB, aWB, H, aX0);
+      __syncthreads();
+      if (tid == 0) tma_fetch_operand(sX0, bsp, 0, &tmXg, bar0, 4 * H, KBH, b0, i & 1);
+      mbar_wait(bar1, ph1); ph1 ^= 1;
+      mma_chunk(accA, aWA, H, aX1);                 // dzp
+      mma_chunk(accB, aWB, 2 * H, aX1);
+      __syncthreads();
+      if (tid == 0) tma_fetch_operand(sX1, bsp, 0, &tmXg, bar1, 3 * H, KBH, b0, i & 1);
+      mbar_wait(bar0, ph0); ph0 ^= 1;
+      mma_chunk(accA, aWA, 2 * H, aX0);             // dnp: completes dctx
+      mbar_wait(bar1, ph1); ph1 ^= 1;
+      mma_chunk(accB, aWB, 3 * H, aX1);             // dghn
+    } else {
     load_operand_rows_async(sX0, bsp, 0, xg + H, xrow, b0, bsp, b0 + bs, H);
     cp_async_commit();
     load_operand_rows_async(sX1, bsp, 0, xg + 2 * H, xrow, b0, bsp, b0 + bs, H);
@@ -537,6 +618,7 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
     cp_async_wait<0>();
     __syncthreads();
     mma_chunk(accB, aWB, 3 * H, aX1);             // dghn
+    }
     phase_stamp(p.dbg, L - 1 - i, 3);
     phase_stamp(p.dbg, L - 1 - i, 4);
     reduce_tiles(accA, sSA);
@@ -650,10 +732,15 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
     // ---- B4: dh_{i-1} = dh z + W_hh^T dgh + W_q^T dq -----------------------------------------------------------
     group_wait(ctr, target);
     phase_stamp(p.dbg, L - 1 - i, 8);
+    if (TMA) {
+      if (tid == 0) tma_fetch_operand(sX0, bsp, 0, &tmXg, bar0, 0, KBH, b0, i & 1);
+      mbar_wait(bar0, ph0); ph0 ^= 1;
+    } else {
     load_operand_rows_async(sX0, bsp, 0, xg, xrow, b0, bsp, b0 + bs, H);
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
+    }
     mma_chunk(accB, aWB, 0, aX0);                 // dq: completes dh
     phase_stamp(p.dbg, L - 1 - i, 9);
     phase_stamp(p.dbg, L - 1 - i, 10);
@@ -753,7 +840,7 @@ int attn_grad_hoisted(const AttnGradArgs& a, cudaStream_t st) {
   PVCR_REQUIRE(smem <= 48 * 1024, "attn_grad_hoisted: L=%d N=%d needs %zu B of shared memory", a.L, a.N, smem);
   const dim3 grid(a.B, cdiv(a.H, AG_DIMS));
   LaunchScope ls_(KC_ATTN, st);
-  static const bool approx = getenv("PVCR_TANH_APPROX_BWD") != nullptr;
+  static const bool approx = getenv("PVCR_TANH_ACCURATE_BWD") == nullptr;
   if (approx) {
     if (a.N <= AG_FG * 10) attn_grad_hoisted_kernel<10, false><<<grid, AG_DIMS * AG_FG, smem, st>>>(a);
     else attn_grad_hoisted_kernel<20, false><<<grid, AG_DIMS * AG_FG, smem, st>>>(a);
@@ -811,15 +898,25 @@ int dec_persist_fwd(const DecPersistFwd& p0, cudaStream_t st) {
   DecPersistFwd p = p0;
   p.C = pl.C; p.u = pl.u; p.bsp = pl.bsp;
   p.dbg = getenv("PVCR_PHASE_DEC_BWD") || getenv("PVCR_PHASE_GRU") ? nullptr : debug_phase_buffer();
-  const void* kern = pl.NF == 2 ? (const void*)dec_persist_fwd_kernel<2>
-                     : (pl.NF == 5 ? (const void*)dec_persist_fwd_kernel<5> : (const void*)dec_persist_fwd_kernel<10>);
+  static const bool acc = getenv("PVCR_TANH_ACCURATE_FWD") != nullptr;      // A/B knobs (NF = 10 shape only)
+  static const bool no_tma = getenv("PVCR_NO_TMA_XCHG") != nullptr;
+  const void* kern = pl.NF == 2 ? (no_tma ? (const void*)dec_persist_fwd_kernel<2, false, false> : (const void*)dec_persist_fwd_kernel<2>)
+                     : (pl.NF == 5 ? (no_tma ? (const void*)dec_persist_fwd_kernel<5, false, false> : (const void*)dec_persist_fwd_kernel<5>)
+                                   : (acc ? (const void*)dec_persist_fwd_kernel<10, true>
+                                          : (no_tma ? (const void*)dec_persist_fwd_kernel<10, false, false>
+                                                    : (const void*)dec_persist_fwd_kernel<10>)));
+  // tensor maps of the exchanged operands: (k, video, step) views with one (64 x bsp) box per k-block
+  CUtensorMap tmH0, tmHs, tmCtx;
+  PVCR_TRY(make_tensor_map(&tmH0, OperandView{p.h0_a, p.h0_a_ld, 0, p.B, 1}, p.H, pl.bsp));
+  PVCR_TRY(make_tensor_map(&tmHs, OperandView{p.hs_a, (long long)p.L * p.hs_a_ld, p.hs_a_ld, p.B, p.L}, p.H, pl.bsp));
+  PVCR_TRY(make_tensor_map(&tmCtx, OperandView{p.ctx_x, (long long)p.H, (long long)p.B * p.H, p.B, p.L}, p.H, pl.bsp));
   PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
   int per_sm = 0;
   PVCR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DEC_THREADS, pl.smem));
   const int grid = pl.G * pl.C;
   PVCR_REQUIRE(per_sm * dec_num_sms() >= grid, "dec_persist_fwd: %d CTAs cannot be co-resident", grid);
   PVCR_TRY(fill_zero(p.counters, sizeof(unsigned) * 32 * pl.G, st));
-  void* args[] = {&p};
+  void* args[] = {&p, &tmH0, &tmHs, &tmCtx};
   LaunchScope ls_(KC_DEC_FWD, st);
   PVCR_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(DEC_THREADS), args, pl.smem, st));
   return PVCR_OK;
@@ -837,19 +934,26 @@ int dec_persist_bwd(const DecPersistBwd& p0, cudaStream_t st) {
   smem += (size_t)(DEC_THREADS / 32) * pl.u * pl.bsp * 4;        // partial product tiles of the 8 warps
   PVCR_REQUIRE(pl.u == 16 || pl.u == 8, "dec_persist_bwd: unit slice u=%d not supported by the mma.sync tiling", pl.u);
   PVCR_REQUIRE(smem <= 227 * 1024, "dec_persist_bwd: needs %zu B of shared memory", smem);
-  // PVCR_TANH_APPROX_BWD=1: single-MUFU hardware tanh (2^-11) in the attention gradient (A/B knob; measured +1e-3 on d W_q)
-  static const bool approx = getenv("PVCR_TANH_APPROX_BWD") != nullptr;
-  const void* kern = approx ? (pl.NF == 2 ? (const void*)dec_persist_bwd_kernel<2, false>
+  // PVCR_TANH_ACCURATE_BWD=1: ex2 + rcp instead of the single-MUFU hardware tanh (2^-11) in the attention gradient.
+  // Measured (B = 128 vs the operand-rounded oracle): no gradient error changes in its first three digits, +0.11 ms per step.
+  static const bool approx = getenv("PVCR_TANH_ACCURATE_BWD") == nullptr;
+  static const bool no_tma = getenv("PVCR_NO_TMA_XCHG") != nullptr;         // A/B knob: cp.async exchange loads
+  const void* kern = no_tma ? (pl.NF == 2 ? (const void*)dec_persist_bwd_kernel<2, false, false>
+                               : (pl.NF == 5 ? (const void*)dec_persist_bwd_kernel<5, false, false>
+                                             : (const void*)dec_persist_bwd_kernel<10, false, false>))
+                     : approx ? (pl.NF == 2 ? (const void*)dec_persist_bwd_kernel<2, false>
                                : (pl.NF == 5 ? (const void*)dec_persist_bwd_kernel<5, false> : (const void*)dec_persist_bwd_kernel<10, false>))
                             : (pl.NF == 2 ? (const void*)dec_persist_bwd_kernel<2, true>
                                : (pl.NF == 5 ? (const void*)dec_persist_bwd_kernel<5, true> : (const void*)dec_persist_bwd_kernel<10, true>));
+  CUtensorMap tmXg;        // exchange buffer [2][B][5H] as (k, video, parity)
+  PVCR_TRY(make_tensor_map(&tmXg, OperandView{p.xg, (long long)5 * p.H, (long long)p.B * 5 * p.H, p.B, 2}, 5 * p.H, pl.bsp));
   PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   PVCR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DEC_BWD_THREADS, smem));
   const int grid = pl.G * pl.C;
   PVCR_REQUIRE(per_sm * dec_num_sms() >= grid, "dec_persist_bwd: %d CTAs cannot be co-resident", grid);
   PVCR_TRY(fill_zero(p.counters, sizeof(unsigned) * 32 * pl.G, st));
-  void* args[] = {&p};
+  void* args[] = {&p, &tmXg};
   LaunchScope ls_(KC_DEC_BWD, st);
   PVCR_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(DEC_BWD_THREADS), args, smem, st));
   return PVCR_OK;

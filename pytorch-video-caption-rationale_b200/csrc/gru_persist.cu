@@ -40,7 +40,10 @@ struct GruPersistFwd {
   long long* dbg;
 };
 
-__global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_fwd_kernel(const GruPersistFwd p) {
+template <bool TMA>
+__global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_fwd_kernel(const GruPersistFwd p,
+                                                                             const __grid_constant__ CUtensorMap tmH0,
+                                                                             const __grid_constant__ CUtensorMap tmHp) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int H = p.H, u = p.u, bs = p.bs, KB = H >> 6, Rw = 3 * u;
@@ -50,18 +53,21 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_fwd_kernel(con
   const int s_ld = Rw + 1;
   uint64_t* bar = reinterpret_cast<uint64_t*>(sS + (size_t)bs * s_ld + 2);
   bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bar) + 7) & ~uintptr_t(7));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint64_t* bar_x = bar + 1;                  // TMA: the exchanged h_{t-1} rows have landed in sX
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int g = blockIdx.x / p.C, c = blockIdx.x % p.C;
   const int b0 = g * bs, j0 = c * u;
   unsigned* ctr = p.counters + g * 32;
+  uint32_t phase_x = 0;
 
   // resident weights: local row q*u + jj  <-  W_hh row q*H + j0 + jj
   for (int q = 0; q < 3; ++q)
     load_operand_rows(sW, Rw, q * u, p.whh, p.whh_ld, (long long)q * H + j0, u, (long long)3 * H, H);
   if (tid == 0) {
     mbar_init(bar, 1);
+    mbar_init(bar_x, 1);
     fence_barrier_init();
   }
   const uint32_t ncols = bs <= 32 ? 32u : (bs <= 64 ? 64u : 128u);
@@ -118,6 +124,19 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_fwd_kernel(con
     const bool has_prev = (t > 0) || (p.h0p != nullptr);
     phase_stamp(p.dbg, t, 0);
     if (has_prev) {
+      if (TMA) {
+        if (tid == 0) {
+          if (t > 0) spin_until(ctr, (unsigned)(p.C * t));
+          phase_stamp(p.dbg, t, 1);
+          tma_fetch_operand(sX, bs, 0, t > 0 ? &tmHp : &tmH0, bar_x, 0, KB, b0, t > 0 ? t - 1 : 0);
+          mbar_wait(bar_x, phase_x);
+          phase_stamp(p.dbg, t, 7);
+          phase_stamp(p.dbg, t, 2);
+          tc_fence_after();
+          issue_swapped_mma(tmem_base, smem_u32(sW), Rw, smem_u32(sX), bs, H, idesc, bar);
+        }
+        phase_x ^= 1;
+      } else {
       if (t > 0) {
         group_wait(ctr, (unsigned)(p.C * t));
         phase_stamp(p.dbg, t, 1);
@@ -134,6 +153,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_fwd_kernel(con
       if (tid == 0) {
         tc_fence_after();
         issue_swapped_mma(tmem_base, smem_u32(sW), Rw, smem_u32(sX), bs, H, idesc, bar);
+      }
       }
       mbar_wait(bar, phase);
       phase ^= 1;
@@ -194,7 +214,9 @@ struct GruPersistBwd {
   unsigned* counters;
 };
 
-__global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_bwd_kernel(const GruPersistBwd p) {
+template <bool TMA>
+__global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_bwd_kernel(const GruPersistBwd p,
+                                                                             const __grid_constant__ CUtensorMap tmX) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int H = p.H, u = p.u, bs = p.bs, K = 3 * H, KB = K >> 6;
@@ -202,6 +224,8 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_bwd_kernel(con
   uint8_t* sX = sW + (size_t)KB * u * 128;                   // KB x (bs rows x 128 B)
   float* sR = reinterpret_cast<float*>(sX + (size_t)KB * bs * 128);     // [8 warps][u][bs] K-slice partial products
   const int nwarps = PERSIST_THREADS / 32;
+  uint64_t* bar_x = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sR + (size_t)nwarps * u * bs) + 15) & ~uintptr_t(7));
+  uint32_t phase_x = 0;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int g = blockIdx.x / p.C, c = blockIdx.x % p.C;
@@ -209,6 +233,10 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_bwd_kernel(con
   unsigned* ctr = p.counters + g * 32;
 
   load_operand_rows(sW, u, 0, p.whhT, p.whhT_ld, j0, u, H, K);
+  if (TMA && tid == 0) {
+    mbar_init(bar_x, 1);
+    fence_barrier_init();
+  }
   __syncthreads();
   const uint32_t aW = smem_u32(sW), aX = smem_u32(sX);
   const int lane = tid & 31, gid = lane >> 2, tig = lane & 3;
@@ -292,11 +320,20 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gru_persist_bwd_kernel(con
       group_arrive(ctr);
       ++arrivals;
       if (t > 0) fetch(t - 1);
+      if (TMA) {
+        if (tid == 0) {
+          spin_until(ctr, (unsigned)p.C * arrivals);
+          tma_fetch_operand(sX, bs, 0, &tmX, bar_x, 0, KB, b0, t & 1);
+        }
+        mbar_wait(bar_x, phase_x);       // every thread: the async-proxy writes are visible to its ldmatrix reads
+        phase_x ^= 1;
+      } else {
       group_wait(ctr, (unsigned)p.C * arrivals);
       load_operand_rows_async(sX, bs, 0, xw, K, b0, bs, p.B, K);
       cp_async_commit();
       cp_async_wait<0>();
       __syncthreads();
+      }
       // D[u, bs] = W_hh^T slice [u, 3H] x dgh^T: warp w takes the k-steps w, w+8, ... (mma.sync m16n8k16, fp32 acc)
       float acc[2][2][4];
 #pragma unroll
@@ -389,7 +426,12 @@ static bool plan_gru(int B, int H, int k_rows_fwd, PersistPlan& pl, bool backwar
   return pl.smem <= 227 * 1024;
 }
 
-static int coop_launch(const void* kern, int grid, size_t smem, void* param, cudaStream_t st, const char* what,
+static bool tma_xchg() {
+  static const bool off = getenv("PVCR_NO_TMA_XCHG") != nullptr;      // A/B knob: cp.async exchange loads instead
+  return !off;
+}
+
+static int coop_launch(const void* kern, int grid, size_t smem, void** args, cudaStream_t st, const char* what,
                        int cls) {
   static std::mutex mu;
   {
@@ -399,7 +441,6 @@ static int coop_launch(const void* kern, int grid, size_t smem, void* param, cud
   int per_sm = 0;
   PVCR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PERSIST_THREADS, smem));
   PVCR_REQUIRE(per_sm * num_sms() >= grid, "%s: %d CTAs cannot be co-resident (%d per SM)", what, grid, per_sm);
-  void* args[] = {param};
   LaunchScope ls_(cls, st);
   PVCR_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(PERSIST_THREADS), args, smem, st));
   return PVCR_OK;
@@ -428,7 +469,17 @@ int gru_persist_fwd(const GruSeq& s, cudaStream_t st) {
   p.counters = s.sync;
   p.dbg = getenv("PVCR_PHASE_GRU") ? debug_phase_buffer() : nullptr;
   PVCR_TRY(fill_zero(s.sync, sizeof(unsigned) * 32 * pl.G, st));
-  return coop_launch((const void*)gru_persist_fwd_kernel, pl.G * pl.C, pl.smem, &p, st, "gru_persist_fwd", KC_GRU_FWD);
+  // tensor maps of the exchanged h rows: (k, video, step) over the bf16 state planes; the initial state separately
+  CUtensorMap tmH0, tmHp;
+  PVCR_TRY(make_tensor_map(&tmHp, OperandView{p.hp, p.hp_ld, p.hp_ts, p.B, p.T}, p.H, pl.bs));
+  if (p.h0p) PVCR_TRY(make_tensor_map(&tmH0, OperandView{p.h0p, p.h0p_ld, 0, p.B, 1}, p.H, pl.bs));
+  else tmH0 = tmHp;
+  void* args[] = {&p, &tmH0, &tmHp};
+  // measured (cfg2 encoder, 16 KB per step): the bulk-tensor fetch is no faster than cp.async here (4.32 vs 4.04 us per step;
+  // both are one L2 round trip), unlike the 32..128 KB exchanges of the other three sweeps -- off unless asked for
+  static const bool fwd_tma = getenv("PVCR_GRU_FWD_TMA") != nullptr;
+  const void* kern = (fwd_tma && tma_xchg()) ? (const void*)gru_persist_fwd_kernel<true> : (const void*)gru_persist_fwd_kernel<false>;
+  return coop_launch(kern, pl.G * pl.C, pl.smem, args, st, "gru_persist_fwd", KC_GRU_FWD);
 }
 
 int gru_persist_bwd(const GruSeq& s, const GruSeqGrad& g, cudaStream_t st) {
@@ -449,7 +500,11 @@ int gru_persist_bwd(const GruSeq& s, const GruSeqGrad& g, cudaStream_t st) {
   p.dgh_p = g.dgh_p; p.dgh_p_ts = g.dgh_p_ts; p.dgh_p_ld = g.dgh_p_ld;
   p.counters = s.sync;
   PVCR_TRY(fill_zero(s.sync, sizeof(unsigned) * 32 * pl.G, st));
-  return coop_launch((const void*)gru_persist_bwd_kernel, pl.G * pl.C, pl.smem, &p, st, "gru_persist_bwd", KC_GRU_BWD);
+  CUtensorMap tmX;         // exchange buffer [2][B][3H] as (k, video, parity)
+  PVCR_TRY(make_tensor_map(&tmX, OperandView{p.xch, (long long)3 * p.H, (long long)p.B * 3 * p.H, p.B, 2}, 3 * p.H, pl.bs));
+  void* args[] = {&p, &tmX};
+  const void* kern = tma_xchg() ? (const void*)gru_persist_bwd_kernel<true> : (const void*)gru_persist_bwd_kernel<false>;
+  return coop_launch(kern, pl.G * pl.C, pl.smem, args, st, "gru_persist_bwd", KC_GRU_BWD);
 }
 
 }  // namespace pvcr

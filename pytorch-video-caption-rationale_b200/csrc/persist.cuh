@@ -138,6 +138,29 @@ __device__ __forceinline__ void group_wait(const unsigned* ctr, unsigned target)
   __syncthreads();      // orders every thread's later loads after thread 0's acquire
 }
 
+// ---- exchanged operands by TMA ------------------------------------------------------------------------------------
+// One thread waits for the group counter and then fetches the operand with a few bulk-tensor copies (one 64-column
+// k-block x `rows_alloc` rows box each) straight into the SW128 buffer the MMAs read; completion is an mbarrier
+// transaction count.  Replaces `rows * K / 8` 16-byte cp.async requests spread over the CTA plus a CTA barrier.
+__device__ __forceinline__ void spin_until(const unsigned* ctr, unsigned target) {
+  if (ld_acquire_u32(ctr) < target) {
+    const long long t0 = clock64();
+    while (ld_acquire_u32(ctr) < target) {
+      if (clock64() - t0 > 4000000000LL) __trap();
+    }
+  }
+}
+// k0: first column (multiple of 64), nkb k-blocks -> dst k-blocks [dst_kb0, dst_kb0 + nkb); rows [row0, row0 + rows_alloc)
+// of slab `slab` (rows past the tensor's extent arrive as zeros)
+__device__ __forceinline__ void tma_fetch_operand(uint8_t* dst, int rows_alloc, int dst_kb0, const CUtensorMap* tm,
+                                                  uint64_t* bar, int k0, int nkb, int row0, int slab) {
+  // the acquire that observed the producers' generic-proxy stores orders before the async-proxy reads below
+  fence_proxy_async();
+  mbar_arrive_expect_tx(bar, (uint32_t)nkb * (uint32_t)rows_alloc * 128u);
+  for (int kb = 0; kb < nkb; ++kb)
+    tma_load_3d(dst + (size_t)(dst_kb0 + kb) * rows_alloc * 128, tm, bar, k0 + kb * 64, row0, slab);
+}
+
 // D[128 x N] (TMEM, fp32) = A[128 x K] * B[N x K]^T, both SW128 K-major in shared memory; issued by one thread.
 __device__ __forceinline__ void issue_swapped_mma(uint32_t tmem_d, uint32_t a_base, int a_rows_alloc, uint32_t b_base,
                                                   int b_rows_alloc, int K, uint32_t idesc, uint64_t* done_bar) {

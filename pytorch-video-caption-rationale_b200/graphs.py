@@ -55,6 +55,8 @@ class GraphedTrainStep:
                 gen = model.train_step_stages(*self.static_in, deferred_join=True)
                 i = 0
                 overlapped = getattr(model, "OVERLAPPED_STAGES", 1)
+                if os.environ.get("PVCR_DP_OVERLAPPED"):           # tuning knob
+                    overlapped = int(os.environ["PVCR_DP_OVERLAPPED"])
                 while True:
                     try:
                         stage = next(gen)

@@ -39,6 +39,9 @@ class GradAllReducer:
         if early and not isinstance(early[0], (list, tuple)):
             early = [early]
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        # NCCL averages inside the collective (ncclAvg): no separate 1/G pass over the ~100 MB of gradients behind the
+        # last all-reduce; other backends (gloo in the CPU tests) sum and divide
+        self._avg = dist.is_initialized() and dist.get_backend(group) == "nccl"
         self.buckets = [list(e) for e in early]
         self.n_early = len(self.buckets)
         early_ids = {id(p) for e in early for p in e}
@@ -79,12 +82,14 @@ class GradAllReducer:
             return
         assert self._in_place(i), "begin()/finish() need flat=True buckets written in place"
         group = self.tail_group if (tail and self.tail_group is not None) else self.group
-        self._pending.append((i, dist.all_reduce(self._flat[i], op=dist.ReduceOp.SUM, group=group, async_op=True)))
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        self._pending.append((i, dist.all_reduce(self._flat[i], op=op, group=group, async_op=True)))
 
     def finish(self):
         for i, h in self._pending:
             h.wait()
-            self._flat[i].div_(self.world)
+            if not self._avg:
+                self._flat[i].div_(self.world)
         self._pending = []
 
     def reduce(self):
@@ -99,11 +104,13 @@ class GradAllReducer:
                 grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
                 flat = torch.cat([g.reshape(-1).float() for g in grads])
                 self._flat[i] = flat
-            handles.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+            handles.append(dist.all_reduce(flat, op=op, group=self.group, async_op=True))
         for i, (bucket, h) in enumerate(zip(self.buckets, handles)):
             h.wait()
             flat = self._flat[i]
-            flat.div_(self.world)
+            if not self._avg:
+                flat.div_(self.world)
             if in_place[i]:
                 continue
             off = 0

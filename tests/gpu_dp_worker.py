@@ -77,12 +77,20 @@ def main():
         ropt.step()
     torch.cuda.synchronize()
 
+    # Adam turns tiny gradient differences (two 16-video GEMMs + all-reduce vs one 32-video GEMM) into lr-sized ones on
+    # elements whose gradient is near zero, so parameters agree to a fraction of the distance they moved, not to 1e-6;
+    # what the comparison must exclude is an optimizer fed with un-reduced gradients (replicas would differ: checked
+    # exactly below), a missing 1/G (every update would differ in its clip factor) or no update at all.
+    init = build(kind, dims, 11)
     worst = (0.0, "")
-    for (k, a), (_, b) in zip(m.named_parameters(), ref.named_parameters()):
-        rel = float(((a - b).norm() / b.norm().clamp_min(1e-30)).item())
+    for (k, a), (_, b), (_, c) in zip(m.named_parameters(), ref.named_parameters(), init.named_parameters()):
+        moved = float((b - c).norm().item())
+        diff = float((a - b).norm().item())
+        rel = diff / max(float(b.norm().item()), 1e-30)
         worst = max(worst, (rel, k))
-        assert rel < 2e-5, (kind, k, rel)
-        assert float((a - b).abs().max().item()) < 2e-4, (kind, k)
+        assert moved > 0.0, (kind, k, "parameter never updated")
+        assert diff < 0.05 * moved, (kind, k, diff, moved)
+        assert rel < 2e-3, (kind, k, rel)
     # replicas stay identical
     for k, a in m.named_parameters():
         lo, hi = a.detach().clone(), a.detach().clone()

@@ -147,6 +147,41 @@ def test_reference_spatialnet_class_runs_with_the_dropin(tag, arch):
         assert e < 5e-4 or np.linalg.norm(grads[k]) < 1e-9, (k, e)
 
 
+@pytest.mark.parametrize("tag,arch", CASES)
+def test_dropin_spatialnet_module(tag, arch):
+    """pvcr_b200.model.SpatialNet: reference constructor / forward contract / state_dict keys; loads the golden's
+    reference state_dict key for key and reproduces logits, seq_alphas, loss and every gradient."""
+    from pvcr_b200 import train_utils as TU
+    from pvcr_b200.model import SpatialNet
+    d, params, grads = _load(tag)
+    B, N, Fdim, H, E, L, Vc = (int(x) for x in d["dims"])
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    net = SpatialNet(FixtureGlove(Vc, E), 0.0, H, Fdim, L, arch, precision="bf16x3")
+    assert set(net.state_dict()) == set(params), set(net.state_dict()) ^ set(params)
+    net.load_state_dict({k: torch.from_numpy(np.asarray(v)).float() if np.asarray(v).dtype.kind == "f"
+                         else torch.from_numpy(np.asarray(v)) for k, v in params.items()})
+    net = net.cuda().train()
+    vid = torch.from_numpy(d["vid"]).cuda()
+    s, s_len = torch.from_numpy(d["s"]).cuda(), torch.from_numpy(d["s_len"]).cuda()
+    logits, seq_alphas = net(vid, s)
+    assert relerr(logits.detach().cpu().numpy(), d["logits"]) < 5e-5
+    assert np.abs(seq_alphas.detach().cpu().numpy() - d["seq_alphas"]).max() < 1e-5
+    loss = TU.calc_masked_loss(logits, s, s_len, nn.CrossEntropyLoss(reduction="none"))
+    assert abs(loss.item() - float(d["loss"])) < 5e-6 * abs(float(d["loss"]))
+    loss.backward()
+    for k, prm in net.named_parameters():
+        if prm.grad is None:
+            assert np.abs(grads[k]).max() == 0.0, k
+            continue
+        e = relerr(prm.grad.double().cpu().numpy(), grads[k])
+        assert e < 5e-4 or np.linalg.norm(grads[k]) < 1e-9, (k, e)
+    net.eval()
+    with torch.no_grad():
+        lg, _ = net(vid, None)
+    assert np.array_equal(torch.argmax(lg, dim=2).cpu().numpy(), d["eval_ids"])
+
+
 def test_boundary_surface_matches_reference_signatures():
     """reset_parameter(s), encode_step, decode, encode and calc_sentence_mask(batch_size, max_len, s_len) exist with the
     reference's argument lists (model/S2VTAttModel.py:215-243, model/S2VTModel.py:52-88, train_utils.py:22)."""
