@@ -433,7 +433,7 @@ def run_ours(args):
     L_.pvcr_side_mode(side_prev)
 
     dp_check = None
-    if world > 1:
+    if world > 1 and not os.environ.get("PVCR_DP_SKIP"):
         dp_check = check_data_parallel_gradients(model, reducer, (vid, s, s_len), world, dev)
     if rank != 0:
         _finish_ranks(world)

@@ -65,6 +65,10 @@ int pvcr_side_join(void* stream);
  * which gradients in mode 2: after pvcr_s2vtatt_bwd_part(part = 1) lane 1 carries d W_ih(dec) / d embedding / d b_ih(dec),
  * lane 0 d W_hh(dec) / d W_q, lane 2 d v / d b_hh(dec) / d W_k. */
 int pvcr_side_join_lane(void* stream, int lane);
+/* `stream` waits for a milestone recorded in the middle of a lane's work.  id 0: the embedding gradient written by the
+ * latest pvcr_s2vtatt_bwd_part(part = 1) is final (its lane goes on with other weight gradients) -- the point at which a
+ * data-parallel caller can start all-reducing the largest decoder-side gradient. */
+int pvcr_side_wait_milestone(void* stream, int id);
 
 /* Tuning aid: in-kernel phase timestamps (clock64 of CTA 0, [step][8]) of the last persistent-kernel launch. */
 int pvcr_debug_phase_timing(int on);

@@ -71,6 +71,7 @@ SIGNATURES = {
     "pvcr_side_mode": (c_int, [c_int]),
     "pvcr_side_join": (c_int, [c_vp]),
     "pvcr_side_join_lane": (c_int, [c_vp, c_int]),
+    "pvcr_side_wait_milestone": (c_int, [c_vp, c_int]),
     "pvcr_debug_phase_timing": (c_int, [c_int]),
     "pvcr_debug_phase_read": (c_int, [P(ctypes.c_longlong), c_int]),
     "pvcr_prof_num_classes": (c_int, []),

@@ -17,6 +17,7 @@ typedef __nv_bfloat16 bf16;
 #define PVCR_ERR_DRIVER -4
 
 void set_last_error(const char* fmt, ...);
+int sm_count();          // multiprocessors of the current device (148 on B200); grids and split heuristics are sized from it
 
 #define PVCR_CUDA_CHECK(expr)                                                              \
   do {                                                                                     \

@@ -633,6 +633,8 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
     target += (unsigned)C;
     phase_stamp(p.dbg, L - 1 - i, 5);
     // ---- B3: attention gradient of video vb ------------------------------------------------------------------
+    // the saved attention weights of this step do not depend on the exchange: fetched while the group barrier is pending
+    if (tid < N) sAl[tid] = __ldg(p.alpha + ((long long)i * B + vb) * N + tid);
     group_wait(ctr, target);
     phase_stamp(p.dbg, L - 1 - i, 6);
     {
@@ -678,8 +680,8 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
         for (int n = tid; n < N; n += 32) {
           float s = 0.f;
           for (int w = 0; w < PW; ++w) s += sP[n * PW + w];
-          const float al = __ldg(p.alpha + ((long long)i * B + vb) * N + n);
-          sAl[n] = al; sDa[n] = s;
+          const float al = sAl[n];
+          sDa[n] = s;
           dot += al * s;
         }
         dot = warp_sum(dot);

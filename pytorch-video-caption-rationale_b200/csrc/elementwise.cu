@@ -59,7 +59,7 @@ __global__ void philox_minmax_kernel(unsigned long long seed, unsigned long long
 int philox_minmax(unsigned long long seed, unsigned long long idx0, unsigned long long n, float* minmax, cudaStream_t st) {
   const unsigned int init[2] = {0x7f7fffffu, 0u};
   PVCR_CUDA_CHECK(cudaMemcpyAsync(minmax, init, sizeof(init), cudaMemcpyHostToDevice, st));
-  philox_minmax_kernel<<<148 * 8, 256, 0, st>>>(seed, idx0, n, reinterpret_cast<unsigned int*>(minmax));
+  philox_minmax_kernel<<<sm_count() * 8, 256, 0, st>>>(seed, idx0, n, reinterpret_cast<unsigned int*>(minmax));
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
 }
@@ -157,7 +157,7 @@ int cast_split(const float* in, long long ld_in, int R, int C, bf16* out, long l
     const unsigned groups = (unsigned)(Cp / 8);
     const long long total = (long long)R * groups;
     const long long want = (total + 256 * CAST_UNR - 1) / (256 * CAST_UNR);
-    const int blocks = (int)(want > 148 * 8 ? 148 * 8 : want);
+    const int blocks = (int)(want > sm_count() * 8 ? sm_count() * 8 : want);
     { LaunchScope ls_(KC_STAGE, st);
     cast_bf16_stream_kernel<<<blocks, 256, 0, st>>>(in, ld_in, (unsigned)R, groups, out, ld_out, row_scale);
     }
@@ -165,7 +165,7 @@ int cast_split(const float* in, long long ld_in, int R, int C, bf16* out, long l
     return PVCR_OK;
   }
   const long long total = (long long)R * (Cp / 8);
-  const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  const int blocks = (int)((total + 255) / 256 > sm_count() * 16 ? sm_count() * 16 : (total + 255) / 256);
   { LaunchScope ls_(KC_STAGE, st);
   cast_split_kernel<<<blocks, 256, 0, st>>>(in, ld_in, R, C, out, ld_out, Cp, nsplit, role_b, row_scale, drop);
   }
@@ -285,7 +285,7 @@ int gather_split(const float* table, int E, const long long* ids, int n_ids, bf1
                  int nsplit, Dropout drop, cudaStream_t st) {
   if (n_ids == 0) return PVCR_OK;
   const long long total = (long long)n_ids * Ep;
-  const int blocks = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
+  const int blocks = (int)((total + 255) / 256 > sm_count() * 8 ? sm_count() * 8 : (total + 255) / 256);
   { LaunchScope ls_(KC_STAGE, st);
   gather_split_kernel<<<blocks, 256, 0, st>>>(table, E, ids, n_ids, out, ld_out, Ep, nsplit, drop);
   }
@@ -308,7 +308,7 @@ int scatter_add_rows(const float* rows, long long ld, const long long* ids, int 
                      Dropout drop, cudaStream_t st) {
   if (n_ids == 0) return PVCR_OK;
   const long long total = (long long)n_ids * E;
-  const int blocks = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
+  const int blocks = (int)((total + 255) / 256 > sm_count() * 8 ? sm_count() * 8 : (total + 255) / 256);
   { LaunchScope ls_(KC_MISC, st);
   scatter_add_rows_kernel<<<blocks, 256, 0, st>>>(rows, ld, ids, n_ids, E, table_grad, drop);
   }
@@ -348,7 +348,7 @@ __global__ void dropout_apply_kernel(const float* __restrict__ in, float* __rest
 }
 int dropout_apply(const float* in, float* out, long long n, Dropout drop, cudaStream_t st) {
   if (n == 0) return PVCR_OK;
-  const int blocks = (int)((n + 255) / 256 > 148 * 8 ? 148 * 8 : (n + 255) / 256);
+  const int blocks = (int)((n + 255) / 256 > sm_count() * 8 ? sm_count() * 8 : (n + 255) / 256);
   { LaunchScope ls_(KC_MISC, st);
   dropout_apply_kernel<<<blocks, 256, 0, st>>>(in, out, n, drop);
   }

@@ -138,7 +138,7 @@ int gemm_mn_store(const OperandView& a, const OperandView& b, int M, int N, int 
   const int total_kb = gc.K / GEMM_BK;
   static const bool no_split = getenv("PVCR_NO_SPLITK") != nullptr;
   if (tiles <= 8 && total_kb >= 16 && !no_split) {      // measured: beyond a handful of tiles the atomics cost more than they save
-    int splits = (int)(148 / tiles);
+    int splits = (int)(sm_count() / tiles);
     if (splits > total_kb / 8) splits = total_kb / 8;
     if (splits > 1) {
       const int kb_per = (total_kb + splits - 1) / splits;
@@ -159,7 +159,7 @@ int gemm_kn_store(const OperandView& a, const OperandView& b, int M, int N, int 
   // long contraction, fewer tiles than half the SMs (d hs = d logits W_v: 60 tiles, K = 23 040): two K ranges per tile
   static const int kn_split = getenv("PVCR_KN_SPLIT") ? atoi(getenv("PVCR_KN_SPLIT")) : 1;
   const long long tiles = (long long)cdiv(M, GEMM_BM) * cdiv(N, 256);
-  if (kn_split > 1 && tiles * kn_split <= 148 && gc.K / GEMM_BK >= 64 * kn_split) {
+  if (kn_split > 1 && tiles * kn_split <= sm_count() && gc.K / GEMM_BK >= 64 * kn_split) {
     gc.k_splits = kn_split;
     if (!accumulate) PVCR_CUDA_CHECK(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, stream));
     epi.atomic = 1;
@@ -176,13 +176,13 @@ int gemm_store(const OperandView& a, const OperandView& b, const GemmCoords& gc,
   static const bool no_persist = getenv("PVCR_NO_PERSIST_GEMM") != nullptr;
   if (gc.N >= 256 && tiles256 >= 64 && !no_persist)
     return launch_gemm_tn_persistent<256, 4, EpiStore>(a, b, gc, grid_z, epi, stream);
-  if (gc.N >= 256 && tiles256 >= 148) return launch_gemm_tn<256, 4, EpiStore>(a, b, gc, grid_z, epi, stream);
+  if (gc.N >= 256 && tiles256 >= sm_count()) return launch_gemm_tn<256, 4, EpiStore>(a, b, gc, grid_z, epi, stream);
   // few output tiles but a long contraction (weight / data gradients over all timesteps): split K across CTAs
   const long long tiles128 = (long long)cdiv(gc.N, 128) * cdiv(gc.M, GEMM_BM);
   const int total_kb = gc.K / GEMM_BK;
   static const bool no_split = getenv("PVCR_NO_SPLITK") != nullptr;
   if (grid_z == 1 && tiles128 <= 24 && total_kb >= 32 && !no_split) {     // measured: atomics lose beyond ~24 tiles
-    int splits = (int)((296 + tiles128 - 1) / tiles128);
+    int splits = (int)((2 * sm_count() + tiles128 - 1) / tiles128);
     if (splits > total_kb / 8) splits = total_kb / 8;
     if (splits > 1) {
       const int kb_per = (total_kb + splits - 1) / splits;

@@ -15,6 +15,7 @@ int side_fork(cudaStream_t main, cudaStream_t* lane, int id = 0);   // lane `id`
 int side_join_lane(cudaStream_t main, int id);          // main waits for lane `id`'s current point only
 int side_join(cudaStream_t main);                       // main waits for every lane's current point
 int side_call_end(cudaStream_t main);                   // join unless mode 2
+int side_milestone(int id, cudaStream_t lane);          // record milestone `id` at the lane's current point (side.cu)
 enum SideNote { NOTE_ATT_BWD_WEIGHTS = 1, NOTE_VOCAB_WV = 2 };
 // one-shot notes between the calls of a step (side.cu), keyed by (workspace, tag) and the data they are about
 void side_note_put(const void* key, int tag, const void* what = nullptr);

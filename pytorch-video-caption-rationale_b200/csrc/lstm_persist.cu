@@ -150,7 +150,9 @@ struct LstmPersistBwd {
   unsigned* counters;
 };
 
-__global__ void __launch_bounds__(PERSIST_THREADS, 1) lstm_persist_bwd_kernel(const LstmPersistBwd p) {
+template <bool TMA>
+__global__ void __launch_bounds__(PERSIST_THREADS, 1) lstm_persist_bwd_kernel(const LstmPersistBwd p,
+                                                                              const __grid_constant__ CUtensorMap tmX) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int H = p.H, u = p.u, bs = p.bs, K = 4 * H, KB = K >> 6;
@@ -158,6 +160,8 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) lstm_persist_bwd_kernel(co
   uint8_t* sX = sW + (size_t)KB * u * 128;
   float* sR = reinterpret_cast<float*>(sX + (size_t)KB * bs * 128);     // [8 warps][u][bs] K-slice partial products
   const int nwarps = PERSIST_THREADS / 32;
+  uint64_t* bar_x = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sR + (size_t)nwarps * u * bs) + 15) & ~uintptr_t(7));
+  uint32_t phase_x = 0;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int g = blockIdx.x / p.C, c = blockIdx.x % p.C;
@@ -165,6 +169,10 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) lstm_persist_bwd_kernel(co
   unsigned* ctr = p.counters + g * 32;
 
   load_operand_rows(sW, u, 0, p.whhT, p.whhT_ld, j0, u, H, K);
+  if (TMA && tid == 0) {
+    mbar_init(bar_x, 1);
+    fence_barrier_init();
+  }
   __syncthreads();
   const uint32_t aW = smem_u32(sW), aX = smem_u32(sX);
   const int lane = tid & 31, gid = lane >> 2, tig = lane & 3;
@@ -211,11 +219,20 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) lstm_persist_bwd_kernel(co
     if (s > 0) {
       group_arrive(ctr);
       ++arrivals;
+      if (TMA) {      // one thread fetches the group's 64 KB of gate gradients with bulk-tensor copies (persist.cuh)
+        if (tid == 0) {
+          spin_until(ctr, (unsigned)p.C * arrivals);
+          tma_fetch_operand(sX, bs, 0, &tmX, bar_x, 0, KB, b0, s & 1);
+        }
+        mbar_wait(bar_x, phase_x);
+        phase_x ^= 1;
+      } else {
       group_wait(ctr, (unsigned)p.C * arrivals);
       load_operand_rows_async(sX, bs, 0, xw, K, b0, bs, p.B, K);
       cp_async_commit();
       cp_async_wait<0>();
       __syncthreads();
+      }
       // dh carry [u, bs] = W_hh^T slice [u, 4H] x da^T: mma.sync m16n8k16, k-steps dealt over the 8 warps
       float acc[2][2][4];
 #pragma unroll
@@ -291,12 +308,11 @@ bool lstm_persist_eligible(int B, int H, int nsplit, int Hp) {
   return !off && nsplit == 1 && Hp == H && plan_lstm(B, H, pl);
 }
 
-static int lstm_coop(const void* kern, int grid, size_t smem, void* param, cudaStream_t st, int cls, const char* what) {
+static int lstm_coop(const void* kern, int grid, size_t smem, void** args, cudaStream_t st, int cls, const char* what) {
   PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   PVCR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PERSIST_THREADS, smem));
   PVCR_REQUIRE(per_sm * lstm_num_sms() >= grid, "%s: %d CTAs cannot be co-resident", what, grid);
-  void* args[] = {param};
   LaunchScope ls_(cls, st);
   PVCR_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(PERSIST_THREADS), args, smem, st));
   return PVCR_OK;
@@ -314,7 +330,8 @@ int lstm_persist_fwd(const LstmSeqArgs& s, cudaStream_t st) {
   p.si = s.si; p.sf = s.sf; p.sg = s.sg; p.so = s.so; p.sc = s.sc;
   p.counters = s.sync;
   PVCR_TRY(fill_zero(s.sync, sizeof(unsigned) * 32 * pl.G, st));
-  return lstm_coop((const void*)lstm_persist_fwd_kernel, pl.G * pl.C, pl.smem_f, &p, st, KC_GRU_FWD, "lstm_persist_fwd");
+  void* args[] = {&p};
+  return lstm_coop((const void*)lstm_persist_fwd_kernel, pl.G * pl.C, pl.smem_f, args, st, KC_GRU_FWD, "lstm_persist_fwd");
 }
 
 int lstm_persist_bwd(const LstmSeqArgs& s, const Planes& whhT, const float* dh_ext, long long dh_ext_ts,
@@ -329,7 +346,14 @@ int lstm_persist_bwd(const LstmSeqArgs& s, const Planes& whhT, const float* dh_e
   p.da = da; p.da_ts = da_ts; p.da_ld = da_ld; p.xch = xch;
   p.counters = s.sync;
   PVCR_TRY(fill_zero(s.sync, sizeof(unsigned) * 32 * pl.G, st));
-  return lstm_coop((const void*)lstm_persist_bwd_kernel, pl.G * pl.C, pl.smem_b, &p, st, KC_GRU_BWD, "lstm_persist_bwd");
+  // measured (cfg3, 64 KB of gate gradients per step): the bulk-tensor fetch is 4 % SLOWER than cp.async in this kernel
+  // (0.295 vs 0.284 ms per direction), unlike the GRU / decoder backward sweeps -- off unless asked for
+  static const bool no_tma = getenv("PVCR_LSTM_BWD_TMA") == nullptr || getenv("PVCR_NO_TMA_XCHG") != nullptr;
+  CUtensorMap tmX;         // exchange buffer [2][B][4H] as (k, video, parity)
+  PVCR_TRY(make_tensor_map(&tmX, OperandView{p.xch, (long long)4 * p.H, (long long)p.B * 4 * p.H, p.B, 2}, 4 * p.H, pl.bs));
+  void* args[] = {&p, &tmX};
+  const void* kern = no_tma ? (const void*)lstm_persist_bwd_kernel<false> : (const void*)lstm_persist_bwd_kernel<true>;
+  return lstm_coop(kern, pl.G * pl.C, pl.smem_b, args, st, KC_GRU_BWD, "lstm_persist_bwd");
 }
 
 }  // namespace pvcr

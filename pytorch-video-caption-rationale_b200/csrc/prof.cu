@@ -46,6 +46,16 @@ LaunchScope::~LaunchScope() {
   if (i < g_pending.size()) cudaEventRecordWithFlags(g_pending[i].b, st, ext ? cudaEventRecordExternal : cudaEventRecordDefault);
 }
 
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
 static const unsigned long long* g_seed_step = nullptr;
 const unsigned long long* seed_step_ptr() { return g_seed_step; }
 static long long* g_phase_buf = nullptr;

@@ -345,7 +345,7 @@ static int s2vtatt_bwd_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const
   const H0 h0 = initial_state(d, w, given);
   const bool persist_dec = dec_persist_eligible(B, N, H, ns, w.enc_a.Kp);
   Planes dgi_p{}, d1_p{};
-  bool sweep_planes = false;
+  bool sweep_planes = false, emb_zeroed = false;
   if (persist_dec) {
     DecPersistBwd q{};
     q.L = L; q.B = B; q.N = N; q.H = H;
@@ -362,6 +362,14 @@ static int s2vtatt_bwd_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const
       q.dgi_p = dgi_p.ptr; q.dgi_p_ld = dgi_p.ld; q.d1_p = d1_p.ptr; q.d1_p_ld = d1_p.ld;
       cache.put(w.dgi_all, H3, BL, H3, dgi_p);
       sweep_planes = true;
+    }
+    // the dense embedding gradient is zeroed on lane 1 in the shadow of the sweep (nothing there depends on the sweep)
+    static const bool emb_early = getenv("PVCR_NO_EMB_EARLY_ZERO") == nullptr;      // A/B knob
+    if (ns == 1 && side_site(2) && emb_early) {
+      cudaStream_t lz;
+      PVCR_TRY(side_fork(st, &lz, 1));
+      PVCR_TRY(fill_zero(g.emb, sizeof(float) * (size_t)d.Vc * E, lz));
+      emb_zeroed = true;
     }
     PVCR_TRY(dec_persist_bwd(q, st));
   } else {
@@ -447,12 +455,24 @@ static int s2vtatt_bwd_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const
   PVCR_TRY(grad_w(a, w.d1_all + H, H4, BL, H3, w.hprev_dec, H, H, nullptr, nullptr, g.dec_w_hh, H, 0, ns, la));
   PVCR_TRY(grad_w(a, w.d1_all, H4, BL, H, w.hprev_dec, H, H, nullptr, nullptr, g.att_wq, H, 0, ns, la));
   }
-  PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, w.ctx_all, H, H, nullptr, nullptr, g.dec_w_ih, H + E, 0, ns, lb));
-  PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, p.emb, E, E, s_in, nullptr, g.dec_w_ih + H, H + E, 0, ns, lb));
+  // lane B: the embedding gradient FIRST (the largest decoder-side gradient, 27.6 MB at cfg2: a data-parallel caller
+  // starts its all-reduce at the milestone below, under the encoder sweep), then the two halves of d W_ih and d b_ih
+  // PVCR_EMB_FIRST=1: embedding gradient before the two halves of d W_ih on this lane.  Measured on one GPU: +16 us per
+  // step (2.160 vs 2.144 ms), and no gain at 2 GPUs from the earlier all-reduce start -- off.
+  static const bool emb_first = getenv("PVCR_EMB_FIRST") != nullptr;
+  if (!emb_first) {
+    PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, w.ctx_all, H, H, nullptr, nullptr, g.dec_w_ih, H + E, 0, ns, lb));
+    PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, p.emb, E, E, s_in, nullptr, g.dec_w_ih + H, H + E, 0, ns, lb));
+  }
   if (ns == 1) PVCR_TRY(grad_x_fwdw(a, w.dgi_all, H3, BL, H3, w.we, E, w.demb_rows, E, 0, lb));
   else PVCR_TRY(grad_x(a, w.dgi_all, H3, BL, H3, w.weT, w.demb_rows, E, 0, lb));
-  PVCR_TRY(fill_zero(g.emb, sizeof(float) * (size_t)d.Vc * E, lb));
+  if (!emb_zeroed) PVCR_TRY(fill_zero(g.emb, sizeof(float) * (size_t)d.Vc * E, lb));
   PVCR_TRY(scatter_add_rows(w.demb_rows, E, s_in, BL, E, g.emb, NO_DROPOUT, lb));
+  if (fork) PVCR_TRY(side_milestone(0, lb));
+  if (emb_first) {
+    PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, w.ctx_all, H, H, nullptr, nullptr, g.dec_w_ih, H + E, 0, ns, lb));
+    PVCR_TRY(grad_w(a, w.dgi_all, H3, BL, H3, p.emb, E, E, s_in, nullptr, g.dec_w_ih + H, H + E, 0, ns, lb));
+  }
   PVCR_TRY(colsum(w.dgi_all, H3, BL, H3, g.dec_b_ih, 0, lb));
   if (persist_dec) {
     AttnGradArgs ag{};

@@ -96,6 +96,22 @@ int side_join(cudaStream_t main) {
   return PVCR_OK;
 }
 
+// Milestones: an event recorded in the MIDDLE of a lane's work by the C code that enqueues it (e.g. "the embedding
+// gradient is final" while more weight-gradient GEMMs follow on the same lane); pvcr_side_wait_milestone makes a caller's
+// stream wait for exactly that point instead of the lane's tail.
+namespace {
+cudaEvent_t g_milestone[4] = {nullptr, nullptr, nullptr, nullptr};
+bool g_milestone_set[4] = {false, false, false, false};
+}
+int side_milestone(int id, cudaStream_t lane) {
+  std::lock_guard<std::mutex> g(g_mu);
+  if (id < 0 || id >= 4) return PVCR_OK;
+  if (!g_milestone[id]) PVCR_CUDA_CHECK(cudaEventCreateWithFlags(&g_milestone[id], cudaEventDisableTiming));
+  PVCR_CUDA_CHECK(cudaEventRecord(g_milestone[id], lane));
+  g_milestone_set[id] = true;
+  return PVCR_OK;
+}
+
 // One-shot notes between the C-ABI calls of one step, keyed by a workspace pointer: a call that already produced
 // something a later call would otherwise compute (e.g. the forward pass staging the transposed weights of the backward
 // sweep on a lane) leaves a note; the later call takes it.  A call that could have left a note but did not clears it.
@@ -154,6 +170,16 @@ int pvcr_side_mode(int mode) {
 int pvcr_side_join_lane(void* stream, int lane) {
   if (lane < 0 || lane >= NLANES) { set_last_error("pvcr_side_join_lane: lane %d not in 0..%d", lane, NLANES - 1); return PVCR_ERR_ARG; }
   return side_join_lane(static_cast<cudaStream_t>(stream), lane);
+}
+
+// `stream` waits for milestone `id` of the latest call that recorded it (0: the embedding gradient of
+// pvcr_s2vtatt_bwd_part(part = 1) is final).  No-op if that milestone was never recorded (lanes off).
+int pvcr_side_wait_milestone(void* stream, int id) {
+  std::lock_guard<std::mutex> g(g_mu);
+  if (id < 0 || id >= 4) { set_last_error("pvcr_side_wait_milestone: id %d not in 0..3", id); return PVCR_ERR_ARG; }
+  if (!g_milestone_set[id]) return PVCR_OK;
+  PVCR_CUDA_CHECK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), g_milestone[id], 0));
+  return PVCR_OK;
 }
 
 int pvcr_side_join(void* stream) {

@@ -67,7 +67,9 @@ class GraphedTrainStep:
                     with torch.cuda.stream(aux):
                         # aux waits for the lane(s) that produce this stage's gradients: one lane when the stage names
                         # it, else all of them
-                        if isinstance(stage, tuple):
+                        if isinstance(stage, tuple) and stage[1] == "milestone":
+                            check(lib().pvcr_side_wait_milestone(stream_ptr(), int(stage[2])), "pvcr_side_wait_milestone")
+                        elif isinstance(stage, tuple):
                             check(lib().pvcr_side_join_lane(stream_ptr(), int(stage[1])), "pvcr_side_join_lane")
                         else:
                             check(lib().pvcr_side_join(stream_ptr()), "pvcr_side_join")

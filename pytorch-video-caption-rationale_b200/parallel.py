@@ -56,6 +56,8 @@ class GradAllReducer:
                 cur, cur_bytes = [], 0
         if cur:
             self.buckets.append(cur)
+        import os
+        self._skip = {int(x) for x in os.environ.get("PVCR_DP_SKIP", "").split(",") if x.strip()}
         self._flat = [None] * len(self.buckets)
         self._views = None
         self._pending = []
@@ -81,6 +83,8 @@ class GradAllReducer:
         if self.world == 1:
             return
         assert self._in_place(i), "begin()/finish() need flat=True buckets written in place"
+        if i in self._skip:              # tuning aid (PVCR_DP_SKIP="1,2"): leave a bucket un-reduced to find the exposed one
+            return
         group = self.tail_group if (tail and self.tail_group is not None) else self.group
         op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
         self._pending.append((i, dist.all_reduce(self._flat[i], op=op, group=group, async_op=True)))

