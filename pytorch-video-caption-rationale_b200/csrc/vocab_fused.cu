@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) target_logit_kernel(const bf16* hs, long 
 //   * reduces the video's masked mean loss / #correct / #mask, and the last block to finish adds the B per-video values in
 //     video order (deterministic) into loss3 -- the former ce_finalize_rows + loss_finalize + row_weights launches.
 constexpr int CE_MAX_L = 256;
-__global__ void __launch_bounds__(256) ce_finalize_kernel(const float* pmax, const float* psum, const int* pidx,
+__global__ void __launch_bounds__(1024) ce_finalize_kernel(const float* pmax, const float* psum, const int* pidx,
                                                           const float* tgt, const long long* target, const long long* s_len,
                                                           int B, int L, int ntiles, float* lse_out, float* nll_out,
                                                           long long* pred_out, float* lse2_out, float* roww_out,
@@ -165,10 +165,10 @@ __global__ void __launch_bounds__(256) ce_finalize_kernel(const float* pmax, con
   __shared__ float s_nll[CE_MAX_L];
   __shared__ float s_ok[CE_MAX_L];
   __shared__ bool last;
-  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const long long len = s_len[b];
   const float cnt = (float)(len < L ? len : L);
-  for (int l = warp; l < L; l += 8) {
+  for (int l = warp; l < L; l += nwarps) {        // one warp per token (L <= 32: all tokens of the video in parallel)
     const int row = b * L + l;
     float m = -INFINITY; int mi = 0x7fffffff;
     for (int k = lane; k < ntiles; k += 32) {
@@ -347,7 +347,7 @@ int vocab_fused_fwd(const float* hs, const float* wv, const float* bv, const lon
   PVCR_REQUIRE(L <= CE_MAX_L, "vocab_fused_fwd: L=%d > %d", L, CE_MAX_L);
   {
     LaunchScope ls_(KC_LOSS, st);
-    ce_finalize_kernel<<<B, 256, 0, st>>>(w.pmax, w.psum, w.pidx, w.tgt, target, s_len, B, L, w.ntiles, lse, w.nll, pred,
+    ce_finalize_kernel<<<B, 32 * (L < 32 ? L : 32), 0, st>>>(w.pmax, w.psum, w.pidx, w.tgt, target, s_len, B, L, w.ntiles, lse, w.nll, pred,
                                           w.lse2, w.roww, token_nll, w.partial, w.counter, loss3);
   }
   PVCR_CUDA_CHECK(cudaGetLastError());

@@ -81,8 +81,11 @@ class Trainer:
         self._sums = torch.zeros(2, dtype=torch.float32, device=dev)     # running (loss, acc) since the last metrics()
         self._count = 0
         self._primed = False
+        self._last_h2d = None
 
     def _stage(self, data):
+        if self._last_h2d is not None:       # the previous copy out of the pinned buffers must have finished reading them
+            self._last_h2d.synchronize()
         for dst, k in zip(self._pinned, ('vid_feats', 'sent', 'sent_len')):
             src = data[k]
             if src.is_cuda:
@@ -96,10 +99,12 @@ class Trainer:
         step WITHOUT synchronising (they are overwritten by the next call)."""
         if not self._primed:
             self.step.prefetch(*self._stage(data))
+            self._last_h2d = self.step._staged
         loss, acc, pred = self.step.step_prefetched()
         self._primed = False
         if next_data is not None:
             self.step.prefetch(*self._stage(next_data))
+            self._last_h2d = self.step._staged
             self._primed = True
         self._sums += torch.stack((loss.detach(), acc.detach()))
         self._count += 1
