@@ -317,6 +317,39 @@ int pvcr_gru_step_bwd(const float* d_h, const float* x, const float* h_prev, con
                       float* d_w_hh, float* d_b_ih, float* d_b_hh, int accumulate, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* SpatialNet front (model/SpatialNet.py:76-86,106): conv_feats = ReLU(BN(Conv3x3(ReLU(BN(Conv3x3(x)))))) on the K x K grid
+ * features of every frame, x = vid_feats.view(I = B*N, F, K, K) fp32 channels-first as the reference hands it over.
+ * Convolution = nine tcgen05 GEMMs on row-shifted views of one flat zero-padded channels-last matrix (csrc/conv.cu); BatchNorm2d
+ * with torch's defaults (training: batch statistics, running estimates updated in place with `momentum`; eval: running
+ * estimates).  Outputs: conv_feats [I*K*K, H] channels-last (row i*K*K + y*K + x: the keys of the spatial attention) and,
+ * if non-NULL, feats_cl [I*K*K, F] = the input features in the same row order (its values).  _bwd: gradients of the eight
+ * parameter tensors from d_conv_feats (the input features need none); needs the workspace of the matching _fwd untouched. */
+typedef struct {
+  const float *conv1_w, *conv1_b;   /* [H, F, 3, 3], [H]   state_dict: conv.0.weight / .bias */
+  const float *bn1_w, *bn1_b;       /* [H], [H]            conv.1.weight / .bias */
+  const float *conv2_w, *conv2_b;   /* [H, H, 3, 3], [H]   conv.3.weight / .bias */
+  const float *bn2_w, *bn2_b;       /* [H], [H]            conv.4.weight / .bias */
+} PvcrSpatialFrontParams;
+size_t pvcr_spatial_front_workspace(int I, int K, int F, int H, int nsplit);
+int pvcr_spatial_front_fwd(int I, int K, int F, int H, int nsplit, const float* vid_feats, const PvcrSpatialFrontParams* p,
+                           float* bn1_running_mean, float* bn1_running_var, float* bn2_running_mean, float* bn2_running_var,
+                           int training, float eps, float momentum, float* conv_feats, float* feats_cl, void* workspace,
+                           size_t workspace_bytes, void* stream);
+int pvcr_spatial_front_bwd(int I, int K, int F, int H, int nsplit, const PvcrSpatialFrontParams* p, int training,
+                           const float* d_conv_feats, PvcrSpatialFrontParams* grads, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* One step of SpatialNet's per-frame attention over the K*K cells (model/SpatialNet.py:27-53, called at :124):
+ *   scores[b,c] = v . tanh(q[b] + proj_key[b,c]);  alpha = softmax_c(scores);  ctx[b] = sum_c alpha[b,c] feats[b,c]
+ * q [B,H] (row stride q_ld) = query_layer(encoder state); proj_key [B,Kc,H] and feats [B,Kc,Fv] with explicit batch strides
+ * (a frame's slice of a [B,N,Kc,.] tensor); alpha [B,Kc], ctx [B,Fv] out.  _bwd: dq [B,H], dproj_key [B,Kc,H] (contiguous) and
+ * dv_part [B,H] (sum over b = gradient of energy_layer.weight) from dctx [B,Fv]; the features need no gradient. */
+int pvcr_spatial_attn_fwd(int B, int Kc, int H, int Fv, const float* q, int64_t q_ld, const float* proj_key, int64_t pk_batch_stride,
+                          const float* feats, int64_t feats_batch_stride, const float* v, float* alpha, float* ctx, void* stream);
+int pvcr_spatial_attn_bwd(int B, int Kc, int H, int Fv, const float* dctx, const float* q, int64_t q_ld, const float* proj_key,
+                          int64_t pk_batch_stride, const float* feats, int64_t feats_batch_stride, const float* v,
+                          const float* alpha, float* dq, float* dproj_key, float* dv_part, void* stream);
+
 /* y[i] = x[i] * mask_i / (1 - p): the mask pvcr_vocab_ce_fwd / _bwd draw for Dropout(hs) under (dropout_p, seed), i the
  * flat index into the [B*L, H] hidden-state matrix (in place allowed).  Replaces nn.Dropout of `pred_linear` / `linear`
  * (model/S2VTAttModel.py:121-122, model/S2VTModel.py:47-49) for callers that take the materialised-logits route, and lets

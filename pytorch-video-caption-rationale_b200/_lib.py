@@ -31,6 +31,7 @@ ATT_PARAM_FIELDS = ["enc_w_ih", "enc_w_hh", "enc_b_ih", "enc_b_hh", "emb", "dec_
                     "dec_b_hh", "att_wk", "att_wq", "att_v", "out_w", "out_b"]
 S2VT_PARAM_FIELDS = ["emb", "rnn1_w_ih", "rnn1_w_hh", "rnn1_b_ih", "rnn1_b_hh", "rnn2_w_ih", "rnn2_w_hh", "rnn2_b_ih",
                      "rnn2_b_hh", "out_w", "out_b"]
+FRONT_PARAM_FIELDS = ["conv1_w", "conv1_b", "bn1_w", "bn1_b", "conv2_w", "conv2_b", "bn2_w", "bn2_b"]
 GEN_PARAM_FIELDS = ["w_ih", "w_hh", "b_ih", "b_hh", "w_ih_r", "w_hh_r", "b_ih_r", "b_hh_r", "lin_w", "lin_b"]
 
 
@@ -44,6 +45,7 @@ PvcrS2vtParams = _ptr_struct("PvcrS2vtParams", S2VT_PARAM_FIELDS)
 PvcrS2vtGrads = _ptr_struct("PvcrS2vtGrads", S2VT_PARAM_FIELDS)
 PvcrGenParams = _ptr_struct("PvcrGenParams", GEN_PARAM_FIELDS)
 PvcrGenGrads = _ptr_struct("PvcrGenGrads", GEN_PARAM_FIELDS)
+PvcrSpatialFrontParams = _ptr_struct("PvcrSpatialFrontParams", FRONT_PARAM_FIELDS)
 
 
 def lib():
@@ -137,6 +139,14 @@ SIGNATURES = {
                                   c_vp]),
     "pvcr_gru_step_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
                                   c_vp, c_vp, c_int, c_vp, c_size, c_vp]),
+    "pvcr_spatial_front_workspace": (c_size, [c_int, c_int, c_int, c_int, c_int]),
+    "pvcr_spatial_front_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_vp, P(PvcrSpatialFrontParams), c_vp, c_vp, c_vp, c_vp,
+                                       c_int, c_f, c_f, c_vp, c_vp, c_vp, c_size, c_vp]),
+    "pvcr_spatial_front_bwd": (c_int, [c_int, c_int, c_int, c_int, c_int, P(PvcrSpatialFrontParams), c_int, c_vp,
+                                       P(PvcrSpatialFrontParams), c_vp, c_size, c_vp]),
+    "pvcr_spatial_attn_fwd": (c_int, [c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "pvcr_spatial_attn_bwd": (c_int, [c_int, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
+                                      c_vp, c_vp]),
     "pvcr_out_dropout_apply": (c_int, [c_vp, c_vp, c_i64, c_f, c_u64, c_vp]),
     "pvcr_debug_philox_minmax": (c_int, [c_u64, c_u64, c_u64, c_vp, c_vp]),
     "pvcr_vocab_ce_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_u64, c_vp, c_vp,

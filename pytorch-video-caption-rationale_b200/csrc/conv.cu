@@ -1,0 +1,562 @@
+// SpatialNet front: two Conv3x3 (stride 1, pad 1) + BatchNorm2d + ReLU blocks on the K x K grid features of every frame
+// (reference model/SpatialNet.py:76-86,106: self.conv = Sequential(Conv2d(F, H, 3, 1, 1), BatchNorm2d(H), ReLU(),
+// Conv2d(H, H, 3, 1, 1), BatchNorm2d(H), ReLU()) applied to vid_feats.view(B*N, F, K, K)), forward and hand-written backward.
+//
+// Convolution = implicit GEMM on the tcgen05 GEMM kernels over a FLAT ZERO-PADDED channels-last layout: image i, padded
+// cell (y, x) in [0, K+2)^2 is row G + i*P + y*(K+2) + x of a [rows, channels] matrix (P = (K+2)^2, G guard rows of zeros
+// at both ends).  In that layout a 3x3 tap (dy, dx) is a ROW OFFSET dy*(K+2) + dx, so
+//     Y[r, :] = b + sum_{taps s} X[r + off_s, :] W_s^T            (valid for the interior rows; border rows are discarded)
+// is nine GEMMs on shifted views of the same bf16 planes accumulating into one fp32 output -- no im2col tensor.  The same
+// holds backwards: dX[r, :] = sum_s dY[r - off_s, :] W_s on the zero-bordered dY, and dW_s = X[. + off_s]^T dY is a
+// contraction over the rows (MN-major tcgen05 operands: both matrices as they lie).  Cost of the padding: (K+2)^2 / K^2 of
+// the useful FLOPs (1.78x at K = 6).  BatchNorm uses batch statistics over the interior rows in training (biased variance
+// for the normalisation, unbiased for the running estimate, momentum 0.1, eps 1e-5 -- torch.nn.BatchNorm2d defaults).
+#include <cstdlib>
+
+#include "../../include/pvcr_b200.h"
+#include "host.h"
+
+namespace pvcr {
+
+namespace {
+
+struct Geo {
+  int I, K, Kp, P, G;          // images, grid, padded grid, padded cells per image, guard rows
+  long long R, Rtot;           // I*P rows that the GEMMs produce; R + 2G rows allocated
+  __host__ __device__ bool interior(long long r, int& cell) const {
+    const int p = (int)(r % P), y = p / Kp, x = p - y * Kp;
+    cell = (y - 1) * K + (x - 1);
+    return y >= 1 && y <= K && x >= 1 && x <= K;
+  }
+};
+Geo make_geo(int I, int K) {
+  Geo g;
+  g.I = I; g.K = K; g.Kp = K + 2; g.P = g.Kp * g.Kp; g.G = (int)round_up(g.Kp + 1, 8);
+  g.R = (long long)I * g.P; g.Rtot = g.R + 2 * g.G;
+  return g;
+}
+
+// vid [I, C, K, K] fp32 (channels first, as the reference hands it over) -> xp [Rtot, C] fp32 padded channels-last (borders
+// of every image zero; guards zeroed by the caller) and, optionally, feats [I*K*K, C] fp32 channels-last (the values the
+// spatial attention averages, model/SpatialNet.py:109-112).  Block = (image, 64-channel tile), transposed through smem.
+__global__ void __launch_bounds__(256) nchw_to_padded_cl_kernel(const float* __restrict__ vid, int C, Geo g,
+                                                                float* __restrict__ xp, float* __restrict__ feats) {
+  extern __shared__ float tile[];                       // [64][KK + 1]
+  const int img = blockIdx.x, c0 = blockIdx.y * 64, KK = g.K * g.K, ldt = KK + 1;
+  const float* src = vid + ((long long)img * C + c0) * KK;
+  const int nch = min(64, C - c0);
+  for (int i = threadIdx.x; i < nch * KK; i += blockDim.x) tile[(i / KK) * ldt + (i % KK)] = src[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < g.P * 64; i += blockDim.x) {
+    const int p = i >> 6, c = i & 63;
+    if (c >= nch) continue;
+    const int y = p / g.Kp, x = p - y * g.Kp;
+    const bool in = y >= 1 && y <= g.K && x >= 1 && x <= g.K;
+    const int cell = (y - 1) * g.K + (x - 1);
+    const float v = in ? tile[c * ldt + cell] : 0.f;
+    xp[((long long)g.G + (long long)img * g.P + p) * C + c0 + c] = v;
+    if (in && feats) feats[((long long)img * KK + cell) * C + c0 + c] = v;
+  }
+}
+
+// w [Co, Ci, 3, 3] -> ws [9][Co, Ci] (tap-major), or back (gradient): w[(co*Ci + ci)*9 + s] <-> ws[(s*Co + co)*Ci + ci]
+__global__ void conv_weight_taps_kernel(const float* __restrict__ w, float* __restrict__ ws, long long n, int Co, int Ci,
+                                        int to_taps) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(i % 9);
+    const long long cc = i / 9;              // co*Ci + ci
+    const long long j = (long long)s * Co * Ci + cc;
+    if (to_taps) ws[j] = w[i];
+    else const_cast<float*>(w)[i] = ws[j];
+  }
+}
+
+// Per-channel sums over the INTERIOR rows of y [R, C]: sums[0][c] += sum y, sums[1][c] += sum y^2 (double accumulators).
+// Block = 32 channels x 8 row lanes over a chunk of rows.
+constexpr int BN_ROWS = 1024;
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ y, int C, Geo g, double* __restrict__ sums) {
+  __shared__ float ps[8][33], pq[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+  const long long r0 = (long long)blockIdx.y * BN_ROWS, r1 = min(g.R, r0 + BN_ROWS);
+  float s = 0.f, q = 0.f;
+  if (c < C) {
+    for (long long r = r0 + rl; r < r1; r += 8) {
+      int cell;
+      if (g.interior(r, cell)) {
+        const float v = y[r * C + c];
+        s += v; q += v * v;
+      }
+    }
+  }
+  ps[rl][threadIdx.x & 31] = s; pq[rl][threadIdx.x & 31] = q;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a += ps[i][threadIdx.x]; b += pq[i][threadIdx.x]; }
+    atomicAdd(sums + c, (double)a);
+    atomicAdd(sums + C + c, (double)b);
+  }
+}
+
+// mean / invstd from the sums (training) or from the running estimates (eval); training also updates the running estimates
+__global__ void bn_finalize_kernel(const double* sums, int C, double count, float eps, float momentum, int training,
+                                   float* running_mean, float* running_var, float* mean, float* invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (training) {
+    const double m = sums[c] / count;
+    double var = sums[C + c] / count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[c] = (float)m;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  } else {
+    mean[c] = running_mean[c];
+    invstd[c] = rsqrtf(running_var[c] + eps);
+  }
+}
+
+// z = relu((y - mean) * invstd * gamma + beta) on the interior rows.  padded_out [Rtot, C]: zero on border rows (the next
+// convolution's zero padding); compact_out [I*K*K, C]: interior rows only (what the attention consumes).
+__global__ void bn_relu_apply_kernel(const float* __restrict__ y, int C, Geo g, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, float* __restrict__ padded_out,
+                                     float* __restrict__ compact_out) {
+  const long long total = g.R * (C / 4);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (C / 4);
+    const int c = (int)(i % (C / 4)) * 4;
+    int cell;
+    const bool in = g.interior(r, cell);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in) {
+      const float4 v = *reinterpret_cast<const float4*>(y + r * C + c);
+      const float4 m = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
+      const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+      o.x = fmaxf((v.x - m.x) * is.x * ga.x + be.x, 0.f); o.y = fmaxf((v.y - m.y) * is.y * ga.y + be.y, 0.f);
+      o.z = fmaxf((v.z - m.z) * is.z * ga.z + be.z, 0.f); o.w = fmaxf((v.w - m.w) * is.w * ga.w + be.w, 0.f);
+    }
+    if (padded_out) *reinterpret_cast<float4*>(padded_out + ((long long)g.G + r) * C + c) = o;
+    if (compact_out && in) *reinterpret_cast<float4*>(compact_out + ((r / g.P) * (g.K * g.K) + cell) * C + c) = o;
+  }
+}
+
+// Backward of BN (batch statistics) + ReLU, pass 1: sums[0][c] = sum dyhat (= d beta), sums[1][c] = sum dyhat * xhat
+// (= d gamma) over the interior rows, with dyhat = dz * [bn(y) > 0].  dz comes compact ([I*K*K, C]) or padded ([., C] with
+// row offset dz_row0, interior rows used).
+__global__ void __launch_bounds__(256) bn_relu_bwd_stats_kernel(const float* __restrict__ y, int C, Geo g,
+                                                                const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                const float* __restrict__ dz, int dz_compact,
+                                                                double* __restrict__ sums) {
+  __shared__ float ps[8][33], pq[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+  const long long r0 = (long long)blockIdx.y * BN_ROWS, r1 = min(g.R, r0 + BN_ROWS);
+  float s = 0.f, q = 0.f;
+  if (c < C) {
+    const float m = mean[c], is = invstd[c], ga = gamma[c], be = beta[c];
+    for (long long r = r0 + rl; r < r1; r += 8) {
+      int cell;
+      if (g.interior(r, cell)) {
+        const float xh = (y[r * C + c] - m) * is;
+        const long long dr = dz_compact ? (r / g.P) * (g.K * g.K) + cell : r;
+        const float d = (xh * ga + be > 0.f) ? dz[dr * C + c] : 0.f;
+        s += d; q += d * xh;
+      }
+    }
+  }
+  ps[rl][threadIdx.x & 31] = s; pq[rl][threadIdx.x & 31] = q;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a += ps[i][threadIdx.x]; b += pq[i][threadIdx.x]; }
+    atomicAdd(sums + c, (double)a);
+    atomicAdd(sums + C + c, (double)b);
+  }
+}
+// pass 2: dy = gamma * invstd * (dyhat - dbeta / M - xhat * dgamma / M) on the interior rows (training; eval: gamma * invstd *
+// dyhat), zero on border rows, written at rows G + r of dy [Rtot, C]; also d gamma / d beta out (fp32).
+__global__ void bn_relu_bwd_apply_kernel(const float* __restrict__ y, int C, Geo g, const float* __restrict__ mean,
+                                         const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, const float* __restrict__ dz, int dz_compact,
+                                         const double* __restrict__ sums, double count, int training,
+                                         float* __restrict__ dy) {
+  const long long total = g.R * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C;
+    const int c = (int)(i % C);
+    int cell;
+    float o = 0.f;
+    if (g.interior(r, cell)) {
+      const float is = invstd[c], ga = gamma[c];
+      const float xh = (y[i] - mean[c]) * is;
+      const long long dr = dz_compact ? (r / g.P) * (g.K * g.K) + cell : r;
+      const float d = (xh * ga + beta[c] > 0.f) ? dz[dr * C + c] : 0.f;
+      o = training ? ga * is * (d - (float)(sums[c] / count) - xh * (float)(sums[C + c] / count)) : ga * is * d;
+    }
+    dy[((long long)g.G + r) * C + c] = o;
+  }
+}
+__global__ void bn_param_grads_kernel(const double* sums, int C, float* dgamma, float* dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) { dbeta[c] = (float)sums[c]; dgamma[c] = (float)sums[C + c]; }
+}
+// out[c] = sum_r in[r, c] over R rows (double atomics; for the conv bias gradient on the zero-bordered dY)
+__global__ void __launch_bounds__(256) colsum_rows_kernel(const float* __restrict__ in, int C, long long R, double* __restrict__ sums) {
+  __shared__ float ps[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+  const long long r0 = (long long)blockIdx.y * BN_ROWS, r1 = min(R, r0 + BN_ROWS);
+  float s = 0.f;
+  if (c < C)
+    for (long long r = r0 + rl; r < r1; r += 8) s += in[r * C + c];
+  ps[rl][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a += ps[i][threadIdx.x];
+    atomicAdd(sums + c, (double)a);
+  }
+}
+__global__ void double_to_float_kernel(const double* in, float* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+
+int grid_for(long long n) { const long long b = (n + 255) / 256; return (int)(b > (long long)sm_count() * 16 ? (long long)sm_count() * 16 : b); }
+
+struct Layer {                 // one Conv3x3 + BN + ReLU block
+  int Ci, Co;
+  float* xpf;                  // [Rtot, Ci] fp32 padded input (zero borders / guards)
+  Planes xp;                   // its bf16 planes (A role), Rtot rows
+  Planes w[9];                 // taps, B role [Co, Ci]
+  Planes wT[9];                // transposed taps [Ci, Co] (B role of dX = dY W)   (backward)
+  float* wtaps;                // [9][Co, Ci] fp32
+  float* y;                    // [R, Co] fp32 conv output (pre-BN)
+  float *mean, *invstd;        // [Co]
+  double* sums;                // [2*Co] scratch
+  float* dy;                   // [Rtot, Co] fp32 zero-bordered gradient on y        (backward)
+  float* dwtaps;               // [9][Co, Ci]                                        (backward)
+};
+struct FrontWs {
+  Geo g;
+  Layer l1, l2;
+  float* dz1;                  // [Rtot, H]: gradient on the first block's output in padded rows (backward)
+};
+
+void carve_layer(Arena& a, const Geo& g, int Ci, int Co, int ns, Layer& l) {
+  l.Ci = Ci; l.Co = Co;
+  l.xpf = a.alloc<float>((size_t)g.Rtot * Ci);
+  l.xp = alloc_planes(a, (int)g.Rtot, Ci, ns);
+  for (int s = 0; s < 9; ++s) l.w[s] = alloc_planes(a, Co, Ci, ns);
+  for (int s = 0; s < 9; ++s) l.wT[s] = alloc_planes(a, Ci, Co, ns);
+  l.wtaps = a.alloc<float>((size_t)9 * Co * Ci);
+  l.y = a.alloc<float>((size_t)g.R * Co);
+  l.mean = a.alloc<float>(Co); l.invstd = a.alloc<float>(Co);
+  l.sums = a.alloc<double>((size_t)2 * Co);
+  l.dy = a.alloc<float>((size_t)g.Rtot * Co);
+  l.dwtaps = a.alloc<float>((size_t)9 * Co * Ci);
+}
+size_t front_scratch(const Geo& g, int F, int H, int ns) {
+  // transient planes of the backward: dY planes (A role, Rtot rows) + grad_w's own scratch for one tap
+  Arena a(nullptr, 0);
+  alloc_planes(a, (int)g.Rtot, H, ns);
+  const size_t gw = grad_w_scratch((int)g.R, H, F > H ? F : H, ns);
+  return a.off + gw + 4096;
+}
+void carve_front(Arena& a, int I, int K, int F, int H, int ns, FrontWs& w) {
+  w.g = make_geo(I, K);
+  carve_layer(a, w.g, F, H, ns, w.l1);
+  carve_layer(a, w.g, H, H, ns, w.l2);
+  w.dz1 = a.alloc<float>((size_t)w.g.Rtot * H);
+}
+
+int off_of(const Geo& g, int s) { return (s / 3 - 1) * g.Kp + (s % 3 - 1); }
+
+// y[R, Co] = bias + sum_s X[. + off_s] W_s^T
+int conv_forward(const Geo& g, const Layer& l, const float* w, const float* bias, int ns, cudaStream_t st) {
+  const long long n = (long long)9 * l.Co * l.Ci;
+  conv_weight_taps_kernel<<<grid_for(n), 256, 0, st>>>(w, l.wtaps, n, l.Co, l.Ci, 1);
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  PVCR_TRY(stage(l.xpf, l.Ci, (int)g.Rtot, l.Ci, l.xp, 0, nullptr, NO_DROPOUT, st));
+  for (int s = 0; s < 9; ++s) {
+    PVCR_TRY(prep_weight(l.wtaps + (size_t)s * l.Co * l.Ci, l.Ci, l.Co, l.Ci, l.w[s], st));
+    const OperandView av{l.xp.ptr + ((long long)g.G + off_of(g, s)) * l.xp.ld, l.xp.ld, 0, (int)g.R, 1};
+    PVCR_TRY(gemm_planes(av, l.w[s].view(), (int)g.R, l.Co, (int)l.xp.ld, l.y, l.Co, s == 0 ? bias : nullptr, s > 0, st));
+  }
+  return PVCR_OK;
+}
+
+int bn_forward(const Geo& g, const Layer& l, const float* gamma, const float* beta, float* running_mean, float* running_var,
+               int training, float eps, float momentum, float* padded_out, float* compact_out, cudaStream_t st) {
+  const int C = l.Co;
+  PVCR_REQUIRE(C % 4 == 0, "spatial front: channel count %d must be a multiple of 4", C);
+  if (training) {
+    PVCR_TRY(fill_zero(l.sums, sizeof(double) * 2 * C, st));
+    bn_stats_kernel<<<dim3(cdiv(C, 32), (unsigned)cdiv(g.R, BN_ROWS)), 256, 0, st>>>(l.y, C, g, l.sums);
+    PVCR_CUDA_CHECK(cudaGetLastError());
+  }
+  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(l.sums, C, (double)g.I * g.K * g.K, eps, momentum, training, running_mean,
+                                                   running_var, l.mean, l.invstd);
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  bn_relu_apply_kernel<<<grid_for(g.R * (C / 4)), 256, 0, st>>>(l.y, C, g, l.mean, l.invstd, gamma, beta, padded_out, compact_out);
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  return PVCR_OK;
+}
+
+// BN + ReLU backward into l.dy (zero-bordered, guards zeroed here), d gamma / d beta out
+int bn_backward(const Geo& g, const Layer& l, const float* gamma, const float* beta, const float* dz, int dz_compact,
+                int training, float* dgamma, float* dbeta, cudaStream_t st) {
+  const int C = l.Co;
+  PVCR_TRY(fill_zero(l.sums, sizeof(double) * 2 * C, st));
+  bn_relu_bwd_stats_kernel<<<dim3(cdiv(C, 32), (unsigned)cdiv(g.R, BN_ROWS)), 256, 0, st>>>(l.y, C, g, l.mean, l.invstd, gamma, beta,
+                                                                                          dz, dz_compact, l.sums);
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  PVCR_TRY(fill_zero(l.dy, sizeof(float) * (size_t)g.G * C, st));
+  PVCR_TRY(fill_zero(l.dy + ((size_t)g.G + g.R) * C, sizeof(float) * (size_t)g.G * C, st));
+  bn_relu_bwd_apply_kernel<<<grid_for(g.R * C), 256, 0, st>>>(l.y, C, g, l.mean, l.invstd, gamma, beta, dz, dz_compact, l.sums,
+                                                             (double)g.I * g.K * g.K, training, l.dy);
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  bn_param_grads_kernel<<<cdiv(C, 128), 128, 0, st>>>(l.sums, C, dgamma, dbeta);
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  return PVCR_OK;
+}
+
+// conv backward from l.dy: d bias, d W (all nine taps), and optionally dX[Rtot-guarded rows] = sum_s dY[. - off_s] W_s
+int conv_backward(Arena& a, const Geo& g, const Layer& l, int ns, float* dw, float* dbias, float* dx_padded, cudaStream_t st) {
+  const int Co = l.Co, Ci = l.Ci;
+  // d bias = column sums of dY (borders are zero)
+  PVCR_TRY(fill_zero(l.sums, sizeof(double) * Co, st));
+  colsum_rows_kernel<<<dim3(cdiv(Co, 32), (unsigned)cdiv(g.R, BN_ROWS)), 256, 0, st>>>(l.dy + (size_t)g.G * Co, Co, g.R, l.sums);
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  double_to_float_kernel<<<cdiv(Co, 128), 128, 0, st>>>(l.sums, dbias, Co);
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  const size_t m = a.mark();
+  Planes dyp = alloc_planes(a, (int)g.Rtot, Co, ns);
+  if (a.failed) { set_last_error("spatial front backward: workspace too small (dY planes)"); return PVCR_ERR_WORKSPACE; }
+  PVCR_TRY(stage(l.dy, Co, (int)g.Rtot, Co, dyp, 0, nullptr, NO_DROPOUT, st));
+  // d W_s = dY^T X[. + off_s]: contraction over the R rows
+  for (int s = 0; s < 9; ++s) {
+    float* dws = l.dwtaps + (size_t)s * Co * Ci;
+    if (ns == 1) {
+      const OperandView dv{dyp.ptr + (long long)g.G * dyp.ld, dyp.ld, 0, (int)g.R, 1};
+      const OperandView xv{l.xp.ptr + ((long long)g.G + off_of(g, s)) * l.xp.ld, l.xp.ld, 0, (int)g.R, 1};
+      PVCR_TRY(gemm_mn_store(dv, xv, Co, Ci, (int)g.R, dws, Ci, 0, st));
+    } else {
+      PVCR_TRY(grad_w(a, l.dy + (size_t)g.G * Co, Co, (int)g.R, Co, l.xpf + ((long long)g.G + off_of(g, s)) * Ci, Ci, Ci, nullptr,
+                      nullptr, dws, Ci, 0, ns, st));
+    }
+  }
+  const long long n = (long long)9 * Co * Ci;
+  conv_weight_taps_kernel<<<grid_for(n), 256, 0, st>>>(dw, l.dwtaps, n, Co, Ci, 0);
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  if (dx_padded) {
+    // dX[r] = sum_s dY[r - off_s] W_s   (B operand: transposed tap planes [Ci, Co], contraction over Co)
+    for (int s = 0; s < 9; ++s) {
+      PVCR_TRY(prep_weight_T(l.wtaps + (size_t)s * Co * Ci, Ci, Co, Ci, l.wT[s], 0, 1, st));
+      const OperandView dv{dyp.ptr + ((long long)g.G - off_of(g, s)) * dyp.ld, dyp.ld, 0, (int)g.R, 1};
+      PVCR_TRY(gemm_planes(dv, l.wT[s].view(), (int)g.R, Ci, (int)dyp.ld, dx_padded, Ci, nullptr, s > 0, st));
+    }
+  }
+  a.release(m);
+  return PVCR_OK;
+}
+
+}  // namespace
+
+size_t spatial_front_workspace(int I, int K, int F, int H, int nsplit) {
+  Arena a(nullptr, 0);
+  FrontWs w;
+  carve_front(a, I, K, F, H, nsplit, w);
+  return a.off + front_scratch(w.g, F, H, nsplit) + 4096;
+}
+
+int spatial_front_fwd(int I, int K, int F, int H, int nsplit, const float* vid, const PvcrSpatialFrontParams& p,
+                      float* running1_mean, float* running1_var, float* running2_mean, float* running2_var, int training,
+                      float eps, float momentum, float* conv_feats, float* feats_cl, void* ws, size_t ws_bytes, cudaStream_t st) {
+  PVCR_REQUIRE(I > 0 && K > 0 && F > 0 && H > 0 && nsplit >= 1 && nsplit <= 3, "spatial_front_fwd: I=%d K=%d F=%d H=%d nsplit=%d",
+               I, K, F, H, nsplit);
+  Arena a(ws, ws_bytes);
+  FrontWs w;
+  carve_front(a, I, K, F, H, nsplit, w);
+  if (a.failed) { set_last_error("spatial_front_fwd: workspace too small (%zu < %zu)", ws_bytes, a.off); return PVCR_ERR_WORKSPACE; }
+  const Geo& g = w.g;
+  // guards of both padded inputs
+  for (Layer* l : {&w.l1, &w.l2}) {
+    PVCR_TRY(fill_zero(l->xpf, sizeof(float) * (size_t)g.G * l->Ci, st));
+    PVCR_TRY(fill_zero(l->xpf + ((size_t)g.G + g.R) * l->Ci, sizeof(float) * (size_t)g.G * l->Ci, st));
+  }
+  nchw_to_padded_cl_kernel<<<dim3(I, cdiv(F, 64)), 256, sizeof(float) * 64 * (K * K + 1), st>>>(vid, F, g, w.l1.xpf, feats_cl);
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  PVCR_TRY(conv_forward(g, w.l1, p.conv1_w, p.conv1_b, nsplit, st));
+  PVCR_TRY(bn_forward(g, w.l1, p.bn1_w, p.bn1_b, running1_mean, running1_var, training, eps, momentum, w.l2.xpf, nullptr, st));
+  PVCR_TRY(conv_forward(g, w.l2, p.conv2_w, p.conv2_b, nsplit, st));
+  PVCR_TRY(bn_forward(g, w.l2, p.bn2_w, p.bn2_b, running2_mean, running2_var, training, eps, momentum, nullptr, conv_feats, st));
+  return PVCR_OK;
+}
+
+// d_conv_feats [I*K*K, H] -> gradients of both blocks' parameters (the input features need none).  Needs the workspace of
+// the matching spatial_front_fwd untouched.
+int spatial_front_bwd(int I, int K, int F, int H, int nsplit, const PvcrSpatialFrontParams& p, int training,
+                      const float* d_conv_feats, PvcrSpatialFrontParams& gr, void* ws, size_t ws_bytes, cudaStream_t st) {
+  Arena a(ws, ws_bytes);
+  FrontWs w;
+  carve_front(a, I, K, F, H, nsplit, w);
+  if (a.failed || a.off + front_scratch(w.g, F, H, nsplit) > ws_bytes) {
+    set_last_error("spatial_front_bwd: workspace too small (%zu bytes)", ws_bytes);
+    return PVCR_ERR_WORKSPACE;
+  }
+  const Geo& g = w.g;
+  PVCR_TRY(bn_backward(g, w.l2, p.bn2_w, p.bn2_b, d_conv_feats, 1, training, const_cast<float*>(gr.bn2_w), const_cast<float*>(gr.bn2_b), st));
+  PVCR_TRY(conv_backward(a, g, w.l2, nsplit, const_cast<float*>(gr.conv2_w), const_cast<float*>(gr.conv2_b), w.dz1 + (size_t)g.G * H, st));
+  // dz1 rows are the padded rows of the first block's output: interior rows carry its gradient
+  PVCR_TRY(bn_backward(g, w.l1, p.bn1_w, p.bn1_b, w.dz1 + (size_t)g.G * H, 0, training, const_cast<float*>(gr.bn1_w),
+                       const_cast<float*>(gr.bn1_b), st));
+  PVCR_TRY(conv_backward(a, g, w.l1, nsplit, const_cast<float*>(gr.conv1_w), const_cast<float*>(gr.conv1_b), nullptr, st));
+  return PVCR_OK;
+}
+
+// ---- per-frame spatial attention over the K*K cells (model/SpatialNet.py:27-53) -----------------------------------------
+// scores[b,c] = v . tanh(q[b] + pk[b,c]);  alpha = softmax_c;  ctx[b] = sum_c alpha[b,c] feats[b,c]  -- keys of width H, values of
+// width Fv (the frame's input features), unlike the temporal attention of the decoder where both are H wide.
+// One CTA per video: warps over cells for the scores, threads over the value columns for the context (coalesced rows).
+constexpr int SA_MAX_CELLS = 256;
+__global__ void __launch_bounds__(256) spatial_attn_fwd_kernel(int Kc, int H, int Fv, const float* __restrict__ q, long long q_ld,
+                                                               const float* __restrict__ pk, long long pk_bs,
+                                                               const float* __restrict__ feats, long long feats_bs,
+                                                               const float* __restrict__ v, float* __restrict__ alpha,
+                                                               float* __restrict__ ctx) {
+  extern __shared__ float sm[];
+  float* sq = sm;            // [H]
+  float* sv = sq + H;        // [H]
+  float* sa = sv + H;        // [Kc]
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int d = tid; d < H; d += 256) { sq[d] = q[(long long)b * q_ld + d]; sv[d] = v[d]; }
+  __syncthreads();
+  const float* pkb = pk + (long long)b * pk_bs;
+  for (int c = warp; c < Kc; c += 8) {
+    float s = 0.f;
+    for (int d = lane; d < H; d += 32) s += sv[d] * tanhf(sq[d] + pkb[(long long)c * H + d]);
+    s = warp_sum(s);
+    if (lane == 0) sa[c] = s;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float mx = -INFINITY;
+    for (int c = lane; c < Kc; c += 32) mx = fmaxf(mx, sa[c]);
+    mx = warp_max(mx);
+    float den = 0.f;
+    for (int c = lane; c < Kc; c += 32) { const float e = expf(sa[c] - mx); sa[c] = e; den += e; }
+    den = warp_sum(den);
+    const float inv = 1.f / den;
+    for (int c = lane; c < Kc; c += 32) { const float al = sa[c] * inv; sa[c] = al; alpha[(long long)b * Kc + c] = al; }
+  }
+  __syncthreads();
+  const float* fb = feats + (long long)b * feats_bs;
+  for (int f = tid; f < Fv; f += 256) {
+    float acc = 0.f;
+    for (int c = 0; c < Kc; ++c) acc += sa[c] * fb[(long long)c * Fv + f];
+    ctx[(long long)b * Fv + f] = acc;
+  }
+}
+
+// Backward: d alpha[c] = dctx . feats[c];  d score = alpha (d alpha - sum alpha d alpha);  with e = tanh(q + pk[c]):
+// dq[d] = sum_c ds[c] v[d] (1 - e^2),  dpk[c,d] = ds[c] v[d] (1 - e^2),  dv_part[b,d] = sum_c ds[c] e   (features need no gradient)
+__global__ void __launch_bounds__(256) spatial_attn_bwd_kernel(int Kc, int H, int Fv, const float* __restrict__ dctx,
+                                                               const float* __restrict__ q, long long q_ld,
+                                                               const float* __restrict__ pk, long long pk_bs,
+                                                               const float* __restrict__ feats, long long feats_bs,
+                                                               const float* __restrict__ v, const float* __restrict__ alpha,
+                                                               float* __restrict__ dq, float* __restrict__ dpk,
+                                                               float* __restrict__ dv_part) {
+  extern __shared__ float sm[];
+  float* sds = sm;           // [Kc] d alpha -> d score
+  float* sal = sds + Kc;     // [Kc]
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* fb = feats + (long long)b * feats_bs;
+  const float* dc = dctx + (long long)b * Fv;
+  for (int c = warp; c < Kc; c += 8) {
+    float s = 0.f;
+    for (int f = lane; f < Fv; f += 32) s += dc[f] * fb[(long long)c * Fv + f];
+    s = warp_sum(s);
+    if (lane == 0) { sds[c] = s; sal[c] = alpha[(long long)b * Kc + c]; }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float dot = 0.f;
+    for (int c = lane; c < Kc; c += 32) dot += sal[c] * sds[c];
+    dot = warp_sum(dot);
+    for (int c = lane; c < Kc; c += 32) sds[c] = sal[c] * (sds[c] - dot);
+  }
+  __syncthreads();
+  const float* pkb = pk + (long long)b * pk_bs;
+  float* dpkb = dpk + (long long)b * Kc * H;
+  for (int d = tid; d < H; d += 256) {
+    const float qd = q[(long long)b * q_ld + d], vd = v[d];
+    float aq = 0.f, av = 0.f;
+    for (int c = 0; c < Kc; ++c) {
+      const float e = tanhf(qd + pkb[(long long)c * H + d]);
+      const float g = sds[c] * vd * (1.f - e * e);
+      dpkb[(long long)c * H + d] = g;
+      aq += g; av += sds[c] * e;
+    }
+    dq[(long long)b * H + d] = aq;
+    dv_part[(long long)b * H + d] = av;
+  }
+}
+
+}  // namespace pvcr
+
+using namespace pvcr;
+
+extern "C" {
+
+int pvcr_spatial_attn_fwd(int B, int Kc, int H, int Fv, const float* q, int64_t q_ld, const float* proj_key, int64_t pk_batch_stride,
+                          const float* feats, int64_t feats_batch_stride, const float* v, float* alpha, float* ctx, void* stream) {
+  if (B <= 0 || Kc <= 0 || Kc > SA_MAX_CELLS || H <= 0 || Fv <= 0) { set_last_error("pvcr_spatial_attn_fwd: B=%d Kc=%d H=%d Fv=%d", B, Kc, H, Fv); return PVCR_ERR_ARG; }
+  const size_t smem = sizeof(float) * ((size_t)2 * H + Kc);
+  if (smem > 48 * 1024) { set_last_error("pvcr_spatial_attn_fwd: H=%d too large", H); return PVCR_ERR_ARG; }
+  { LaunchScope ls_(KC_ATTN, (cudaStream_t)stream);
+  spatial_attn_fwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(Kc, H, Fv, q, q_ld, proj_key, pk_batch_stride, feats,
+                                                                   feats_batch_stride, v, alpha, ctx);
+  }
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  return PVCR_OK;
+}
+int pvcr_spatial_attn_bwd(int B, int Kc, int H, int Fv, const float* dctx, const float* q, int64_t q_ld, const float* proj_key,
+                          int64_t pk_batch_stride, const float* feats, int64_t feats_batch_stride, const float* v,
+                          const float* alpha, float* dq, float* dproj_key, float* dv_part, void* stream) {
+  if (B <= 0 || Kc <= 0 || Kc > SA_MAX_CELLS || H <= 0 || Fv <= 0) { set_last_error("pvcr_spatial_attn_bwd: B=%d Kc=%d H=%d Fv=%d", B, Kc, H, Fv); return PVCR_ERR_ARG; }
+  { LaunchScope ls_(KC_ATTN, (cudaStream_t)stream);
+  spatial_attn_bwd_kernel<<<B, 256, sizeof(float) * 2 * Kc, (cudaStream_t)stream>>>(Kc, H, Fv, dctx, q, q_ld, proj_key, pk_batch_stride,
+                                                                                  feats, feats_batch_stride, v, alpha, dq, dproj_key, dv_part);
+  }
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  return PVCR_OK;
+}
+
+size_t pvcr_spatial_front_workspace(int I, int K, int F, int H, int nsplit) { return spatial_front_workspace(I, K, F, H, nsplit); }
+int pvcr_spatial_front_fwd(int I, int K, int F, int H, int nsplit, const float* vid_feats, const PvcrSpatialFrontParams* p,
+                           float* bn1_running_mean, float* bn1_running_var, float* bn2_running_mean, float* bn2_running_var,
+                           int training, float eps, float momentum, float* conv_feats, float* feats_cl, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  if (!p || !vid_feats || !conv_feats) { set_last_error("pvcr_spatial_front_fwd: null argument"); return PVCR_ERR_ARG; }
+  return spatial_front_fwd(I, K, F, H, nsplit, vid_feats, *p, bn1_running_mean, bn1_running_var, bn2_running_mean,
+                           bn2_running_var, training, eps, momentum, conv_feats, feats_cl, workspace, workspace_bytes,
+                           (cudaStream_t)stream);
+}
+int pvcr_spatial_front_bwd(int I, int K, int F, int H, int nsplit, const PvcrSpatialFrontParams* p, int training,
+                           const float* d_conv_feats, PvcrSpatialFrontParams* grads, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  if (!p || !grads || !d_conv_feats) { set_last_error("pvcr_spatial_front_bwd: null argument"); return PVCR_ERR_ARG; }
+  return spatial_front_bwd(I, K, F, H, nsplit, *p, training, d_conv_feats, *grads, workspace, workspace_bytes,
+                           (cudaStream_t)stream);
+}
+
+}  // extern "C"

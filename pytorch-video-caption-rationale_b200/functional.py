@@ -9,8 +9,9 @@ import itertools
 import torch
 
 from . import _lib
-from ._lib import (ATT_PARAM_FIELDS, GEN_PARAM_FIELDS, S2VT_PARAM_FIELDS, PvcrDims, PvcrGenGrads, PvcrGenParams,
-                   PvcrS2vtAttGrads, PvcrS2vtAttParams, PvcrS2vtGrads, PvcrS2vtParams, check, lib, ptr, stream_ptr)
+from ._lib import (ATT_PARAM_FIELDS, FRONT_PARAM_FIELDS, GEN_PARAM_FIELDS, S2VT_PARAM_FIELDS, PvcrDims, PvcrGenGrads,
+                   PvcrGenParams, PvcrS2vtAttGrads, PvcrS2vtAttParams, PvcrS2vtGrads, PvcrS2vtParams, PvcrSpatialFrontParams,
+                   check, lib, ptr, stream_ptr)
 
 _seed_counter = itertools.count(1)
 
@@ -551,3 +552,108 @@ def s2vt_decode_steps(vid, frame_scale, sos_id, max_len, seq_params, out_w, out_
                                     mask, float(cfg.get("dropout_p", 0.0)), ptr(ids), ptr(fed), ptr(logits), ptr(ws),
                                     ws.numel(), stream_ptr()), "pvcr_s2vt_decode_steps")
     return ids, logits, fed
+
+
+class Linear(torch.autograd.Function):
+    """y = x W^T (+ b) on the tcgen05 GEMM with hand-written gradients (pvcr_linear_fwd / pvcr_linear_bwd): the nn.Linear
+    layers of SpatialNet's attention (key_layer / query_layer, model/SpatialNet.py:23-25,39-41)."""
+
+    @staticmethod
+    def forward(ctx, nsplit, x, w, b=None):
+        x_c, w_c = _f32c(x), _f32c(w)
+        b_c = None if b is None else _f32c(b)
+        M, K = x_c.shape
+        N = w_c.shape[0]
+        Lb = lib()
+        ws = _ws(Lb.pvcr_linear_fwd_workspace(M, N, K, nsplit), x_c.device)
+        y = torch.empty((M, N), dtype=torch.float32, device=x_c.device)
+        check(Lb.pvcr_linear_fwd(ptr(x_c), K, ptr(w_c), K, ptr(b_c), ptr(y), N, M, N, K, nsplit, ptr(ws), ws.numel(),
+                                 stream_ptr()), "pvcr_linear_fwd")
+        ctx.meta = (M, N, K, nsplit, b is not None)
+        ctx.keep = (x_c, w_c)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        M, N, K, nsplit, has_b = ctx.meta
+        x_c, w_c = ctx.keep
+        dy_c = _f32c(dy)
+        need_dx = ctx.needs_input_grad[1]
+        dx = torch.empty_like(x_c) if need_dx else None
+        dw = torch.empty_like(w_c)
+        db = torch.empty((N,), dtype=torch.float32, device=x_c.device) if has_b else None
+        Lb = lib()
+        ws = _ws(Lb.pvcr_linear_bwd_workspace(M, N, K, nsplit), x_c.device)
+        check(Lb.pvcr_linear_bwd(ptr(dy_c), N, ptr(x_c), K, ptr(w_c), K, ptr(dx), K, ptr(dw), K, ptr(db), M, N, K, nsplit, 0,
+                                 ptr(ws), ws.numel(), stream_ptr()), "pvcr_linear_bwd")
+        return None, dx, dw, db
+
+
+class SpatialFront(torch.autograd.Function):
+    """Two Conv3x3 + BatchNorm2d + ReLU blocks on the grid features of every frame (model/SpatialNet.py:76-86,106):
+    (vid [I,F,K,K], 8 parameter tensors, 4 running-stat buffers) -> conv_feats [I*K*K, H] (differentiable in the
+    parameters), feats_cl [I*K*K, F] (the input in channels-last row order).  Running estimates are updated in place in
+    training, as torch.nn.BatchNorm2d does."""
+
+    @staticmethod
+    def forward(ctx, cfg, vid, rm1, rv1, rm2, rv2, *params):
+        I, F, K, _ = vid.shape
+        tensors = {f: _f32c(p) for f, p in zip(FRONT_PARAM_FIELDS, params)}
+        H = tensors["conv1_w"].shape[0]
+        vid_c = _f32c(vid)
+        nsplit, training = int(cfg["nsplit"]), int(cfg["training"])
+        Lb = lib()
+        ws = _ws(Lb.pvcr_spatial_front_workspace(I, K, F, H, nsplit), vid.device)
+        conv_feats = torch.empty((I * K * K, H), dtype=torch.float32, device=vid.device)
+        feats_cl = torch.empty((I * K * K, F), dtype=torch.float32, device=vid.device)
+        ps = _fill_struct(PvcrSpatialFrontParams(), FRONT_PARAM_FIELDS, tensors)
+        check(Lb.pvcr_spatial_front_fwd(I, K, F, H, nsplit, ptr(vid_c), ctypes.byref(ps), ptr(rm1), ptr(rv1), ptr(rm2), ptr(rv2),
+                                        training, float(cfg.get("eps", 1e-5)), float(cfg.get("momentum", 0.1)),
+                                        ptr(conv_feats), ptr(feats_cl), ptr(ws), ws.numel(), stream_ptr()),
+              "pvcr_spatial_front_fwd")
+        ctx.meta = (I, K, F, H, nsplit, training)
+        ctx.keep = (ws, tensors)
+        ctx.mark_non_differentiable(feats_cl)
+        return conv_feats, feats_cl
+
+    @staticmethod
+    def backward(ctx, d_conv_feats, _d_feats):
+        I, K, F, H, nsplit, training = ctx.meta
+        ws, tensors = ctx.keep
+        grads = {f: torch.empty_like(t) for f, t in tensors.items()}
+        ps = _fill_struct(PvcrSpatialFrontParams(), FRONT_PARAM_FIELDS, tensors)
+        gs = _fill_struct(PvcrSpatialFrontParams(), FRONT_PARAM_FIELDS, grads)
+        check(lib().pvcr_spatial_front_bwd(I, K, F, H, nsplit, ctypes.byref(ps), training, ptr(_f32c(d_conv_feats)),
+                                           ctypes.byref(gs), ptr(ws), ws.numel(), stream_ptr()), "pvcr_spatial_front_bwd")
+        return (None, None, None, None, None, None) + tuple(grads[f] for f in FRONT_PARAM_FIELDS)
+
+
+class SpatialAttnStep(torch.autograd.Function):
+    """One frame's attention over the K*K cells (model/SpatialNet.py:27-53): (q [B,H], proj_key [B,Kc,H], feats [B,Kc,F],
+    v [H]) -> context [B,F], alphas [B,Kc].  Differentiable in q, proj_key and v (the features are inputs)."""
+
+    @staticmethod
+    def forward(ctx, q, pk, feats, v):
+        B, Kc, H = pk.shape
+        Fv = feats.shape[2]
+        q_c, pk_c, f_c, v_c = _f32c(q), _f32c(pk), _f32c(feats), _f32c(v).reshape(-1)
+        alpha = torch.empty((B, Kc), dtype=torch.float32, device=q_c.device)
+        out = torch.empty((B, Fv), dtype=torch.float32, device=q_c.device)
+        check(lib().pvcr_spatial_attn_fwd(B, Kc, H, Fv, ptr(q_c), H, ptr(pk_c), Kc * H, ptr(f_c), Kc * Fv, ptr(v_c), ptr(alpha),
+                                          ptr(out), stream_ptr()), "pvcr_spatial_attn_fwd")
+        ctx.meta = (B, Kc, H, Fv, tuple(v.shape))
+        ctx.keep = (q_c, pk_c, f_c, v_c, alpha)
+        ctx.mark_non_differentiable(alpha)
+        return out, alpha
+
+    @staticmethod
+    def backward(ctx, dctx, _dalpha):
+        B, Kc, H, Fv, vshape = ctx.meta
+        q_c, pk_c, f_c, v_c, alpha = ctx.keep
+        dq = torch.empty_like(q_c)
+        dpk = torch.empty_like(pk_c)
+        dv_part = torch.empty((B, H), dtype=torch.float32, device=q_c.device)
+        check(lib().pvcr_spatial_attn_bwd(B, Kc, H, Fv, ptr(_f32c(dctx)), ptr(q_c), H, ptr(pk_c), Kc * H, ptr(f_c), Kc * Fv,
+                                          ptr(v_c), ptr(alpha), ptr(dq), ptr(dpk), ptr(dv_part), stream_ptr()),
+              "pvcr_spatial_attn_bwd")
+        return dq, dpk, None, dv_part.sum(dim=0).reshape(vshape)

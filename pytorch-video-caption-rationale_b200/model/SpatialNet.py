@@ -1,27 +1,35 @@
-"""SpatialNet (BASELINE config 4) around the B200 caption networks -- FIRST STAGE.
+"""SpatialNet (BASELINE config 4) on the B200 kernels.
 
 Same constructor, ``forward(vid_feats [B,N,F,K,K], s) -> (logits [B,L,Vc], seq_alphas [B,N,K,K])`` contract and
-``state_dict`` keys as the reference (model/SpatialNet.py:55-142).  What runs where today:
+``state_dict`` keys as the reference (model/SpatialNet.py:55-142).  The torch.nn layers below are parameter / buffer
+containers only (so reference checkpoints load key for key, BatchNorm running statistics included); the arithmetic runs in
+libpvcr_b200.so:
 
-* the caption network behind ``encode_step`` / ``decode`` (per-frame encoder GRU step, whole decoder with attention,
-  vocabulary projection, their hand-written backward passes) runs on the sm_100a kernels of libpvcr_b200.so;
-* the front of the network -- two Conv3x3 + BatchNorm + ReLU blocks and the per-frame spatial attention over the K*K
-  cells (model/SpatialNet.py:76-86, 27-53, 120-138) -- is still expressed with torch.nn ops (cuDNN / cuBLAS library
-  calls), exactly the reference's arithmetic; hand-written kernels for it (implicit-GEMM convolution on the tcgen05 GEMM,
-  spatial attention fused into the encoder step) are the open part of row f1.
+* the two Conv3x3 + BatchNorm2d + ReLU blocks (:76-86,106) -- nine tcgen05 GEMMs per convolution on row-shifted views of a flat
+  zero-padded channels-last matrix, BatchNorm statistics / apply kernels, hand-written backward (csrc/conv.cu,
+  ``functional.SpatialFront``);
+* ``key_layer`` hoisted out of the frame loop (the reference re-applies it per frame, :39; it does not depend on the
+  recurrent state) and ``query_layer`` per frame -- ``functional.Linear`` (pvcr_linear_fwd/bwd);
+* the per-frame attention over the K*K cells (:27-53) -- ``functional.SpatialAttnStep`` (pvcr_spatial_attn_fwd/bwd);
+* the caption network behind ``encode_step`` / ``decode`` (per-frame encoder GRU step, persistent decoder sweeps,
+  vocabulary projection).
+
+Still a per-frame launch chain (query GEMM, attention, GRU-step GEMMs and gates: the encoder input depends on the attention
+of the same step, so nothing of it can be hoisted); a persistent fused spatial-attention + GRU sweep is the open part
+(DESIGN.md section 7).  torch supplies memory, views / transposes between layouts and the autograd tape.
 
 Parity: tests/test_gpu_boundary.py against goldens of the unmodified reference SpatialNet (oracle/gen_golden_spatial.py).
 """
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
+from .. import functional as F_
 from .S2VTAttModel import S2VTAttModel
 from .S2VTModel import S2VTModel
 
 
 class Attention(nn.Module):
-    """Bahdanau attention over the K*K cells of one frame (model/SpatialNet.py:14-53): returns (context, alphas)."""
+    """Parameter container of the spatial attention (model/SpatialNet.py:14-25)."""
 
     def __init__(self, hidden_size):
         super().__init__()
@@ -29,20 +37,10 @@ class Attention(nn.Module):
         self.query_layer = nn.Linear(hidden_size, hidden_size, bias=False)
         self.energy_layer = nn.Linear(hidden_size, 1, bias=False)
 
-    def project_keys(self, conv_feats):
-        """key_layer applied to every frame's cells at once (the reference re-applies it inside its frame loop,
-        model/SpatialNet.py:39; it does not depend on the recurrent state, so it is hoisted)."""
-        return self.key_layer(conv_feats)
-
-    def forward(self, query, proj_key, feats):
-        """query [B,H] (encoder state), proj_key [B,K^2,H], feats [B,K^2,F] -> context [B,F], alphas [B,K^2]."""
-        q = self.query_layer(query)
-        scores = self.energy_layer(torch.tanh(q.unsqueeze(1) + proj_key)).squeeze(-1)
-        alphas = F.softmax(scores, dim=1)
-        return torch.bmm(alphas.unsqueeze(1), feats).squeeze(1), alphas
-
 
 class SpatialNet(nn.Module):
+    NSPLIT = {'bf16': 1, 'bf16x2': 2, 'bf16x3': 3}
+
     def __init__(self, glove_loader, dropout_p, hidden_size, vid_feat_size, max_len, arch, precision='bf16'):
         super().__init__()
         if arch == 's2vt':
@@ -56,19 +54,38 @@ class SpatialNet(nn.Module):
             nn.Conv2d(hidden_size, hidden_size, 3, 1, 1), nn.BatchNorm2d(hidden_size), nn.ReLU())
         self.attention = Attention(hidden_size)
         self.hidden_size = hidden_size
+        self.precision = precision
+
+    def _front(self, x):
+        """x [I,F,K,K] -> conv_feats [I*K*K, H], feats_cl [I*K*K, F]."""
+        c1, b1, c2, b2 = self.conv[0], self.conv[1], self.conv[3], self.conv[4]
+        cfg = {"nsplit": self.NSPLIT[self.precision] if self.training else 3, "training": self.training, "eps": b1.eps,
+               "momentum": b1.momentum}
+        out = F_.SpatialFront.apply(cfg, x, b1.running_mean, b1.running_var, b2.running_mean, b2.running_var, c1.weight,
+                                    c1.bias, b1.weight, b1.bias, c2.weight, c2.bias, b2.weight, b2.bias)
+        if self.training:
+            with torch.no_grad():
+                b1.num_batches_tracked += 1
+                b2.num_batches_tracked += 1
+        return out
 
     def forward(self, vid_feats, s=None):
         B, N, Fd, K, _ = vid_feats.shape
-        cells = K * K
-        conv = self.conv(vid_feats.reshape(-1, Fd, K, K)).view(B, N, -1, cells).transpose(2, 3)      # B x N x K^2 x H
-        feats = vid_feats.view(B, N, Fd, cells).transpose(2, 3)                                      # B x N x K^2 x F
-        proj_key = self.attention.project_keys(conv)
-        state = torch.zeros(1, B, self.hidden_size, device=vid_feats.device, dtype=vid_feats.dtype)
+        cells, H = K * K, self.hidden_size
+        ns = self.NSPLIT[self.precision] if self.training else 3
+        conv_feats, feats_cl = self._front(vid_feats.reshape(B * N, Fd, K, K))
+        proj_key = F_.Linear.apply(ns, conv_feats, self.attention.key_layer.weight)
+        # frame-major copies so that every frame's [B, K*K, .] slice is contiguous (unbind: its backward is one stack)
+        pk_frames = proj_key.view(B, N, cells, H).transpose(0, 1).contiguous().unbind(0)
+        feat_frames = feats_cl.view(B, N, cells, Fd).transpose(0, 1).contiguous().unbind(0)
+        state = torch.zeros(1, B, H, device=vid_feats.device, dtype=torch.float32)
         outs, seq_alphas = [], []
+        v = self.attention.energy_layer.weight
         for i in range(N):
-            context, alphas = self.attention(state.squeeze(0), proj_key[:, i], feats[:, i])
-            out, state = self.caption_net.encode_step(context, state)        # sm_100a GRU step (pvcr_gru_step_fwd/bwd)
+            q = F_.Linear.apply(ns, state.squeeze(0), self.attention.query_layer.weight)
+            context, alphas = F_.SpatialAttnStep.apply(q, pk_frames[i], feat_frames[i], v)
+            out, state = self.caption_net.encode_step(context, state)
             outs.append(out)
             seq_alphas.append(alphas.view(-1, K, K).unsqueeze(1))
-        logits = self.caption_net.decode(torch.cat(outs, dim=0), state, s)    # sm_100a decoder + vocabulary projection
+        logits = self.caption_net.decode(torch.cat(outs, dim=0), state, s)
         return logits, torch.cat(seq_alphas, dim=1)
