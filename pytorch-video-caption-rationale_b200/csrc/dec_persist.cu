@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
   const int DG = H >> 3, FG = DEC_THREADS / DG, PW = DG >= 32 ? DG / 32 : 1;
   float* sP = sS3 + (size_t)bsp * s3_ld;    // [N][PW]
   float* sScore = sP + (size_t)N * PW;      // [N]
-  float* sC = sScore + N;                   // [FG][H]
+  float* sC = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sScore + N) + 15) & ~uintptr_t(15));   // [FG][H], float4 access
   uint64_t* bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sC + (size_t)FG * H) + 15) & ~uintptr_t(7));
   uint64_t* bar_x = bar + 1;                 // TMA: the exchanged operand has landed in sX
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
@@ -198,15 +198,33 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
         qout[(long long)(b0 + lb) * p.q_ld + j0 + jj] = sS1[lb * s1_ld + jj];
       }
     }
-    group_arrive(ctr);
-    target += (unsigned)C;
+    if (p.xq == 0) { group_arrive(ctr); target += (unsigned)C; }
     phase_stamp(p.dbg, i, 4);
     // ---- P2: attention of video vb ---------------------------------------------------------------------
-    group_wait(ctr, target);
-    phase_stamp(p.dbg, i, 5);
+    // q of this video arrives in 16-float pieces from the group's CTAs: behind the group barrier (xq 0), or polled on the
+    // data itself (persist.cuh) by every thread for its own 8 values (xq 1) or by warp 0 for the CTA (xq 2)
     {
-      const float4* q4 = reinterpret_cast<const float4*>(p.q_all + (long long)i * B * p.q_ld + (long long)vb * p.q_ld + d0);
-      const float4 qa = __ldcg(q4), qb = __ldcg(q4 + 1);
+      const float* qrow = p.q_all + (long long)i * B * p.q_ld + (long long)vb * p.q_ld;
+      float4 qa, qb;
+      if (p.xq == 0) {
+        group_wait(ctr, target);
+        phase_stamp(p.dbg, i, 5);
+        qa = __ldcg(reinterpret_cast<const float4*>(qrow + d0)); qb = __ldcg(reinterpret_cast<const float4*>(qrow + d0) + 1);
+      } else if (p.xq == 1) {
+        phase_stamp(p.dbg, i, 5);
+        poll_f8(qrow + d0, qa, qb);
+      } else {
+        if (warp == 0) {
+          for (int c = tid * 8; c < H; c += 256) {
+            float4 a, b;
+            poll_f8(qrow + c, a, b);
+            *reinterpret_cast<float4*>(sC + c) = a; *reinterpret_cast<float4*>(sC + c + 4) = b;
+          }
+        }
+        __syncthreads();
+        phase_stamp(p.dbg, i, 5);
+        qa = *reinterpret_cast<const float4*>(sC + d0); qb = *reinterpret_cast<const float4*>(sC + d0 + 4);
+      }
       const float q8[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
       if (p.dbg && tid == 0 && blockIdx.x == 0 && q8[0] == 123.456f) p.dbg[0] = 0;   // force the load to complete
       phase_stamp(p.dbg, i, 8);
@@ -385,7 +403,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) dec_persist_fwd_kernel(const D
 // several times faster here than tcgen05.mma's ~70 cycles per K=16 step (persist.cuh); the K-chunks of the exchange
 // buffer stream in with cp.async, two in flight, overlapping the MMAs of the previous chunk.
 constexpr int DEC_BWD_THREADS = DEC_THREADS;
-template <int NF, bool ACC_TANH, bool TMA = true>
+// ITEMS: (unit, video) pairs per thread (2 at the cfg2 shape: u * C = 512 pairs on 256 threads).
+template <int NF, bool ACC_TANH, bool TMA = true, int ITEMS = DEC_ITEMS>
 __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(const DecPersistBwd p,
                                                                              const __grid_constant__ CUtensorMap tmXg) {
   extern __shared__ uint8_t smem_raw[];
@@ -396,14 +415,14 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
   uint8_t* sX0 = sWB + (size_t)4 * KBH * u * 128;              // chunk buffers: KBH x (bsp x 128 B) each
   uint8_t* sX1 = sX0 + (size_t)KBH * bsp * 128;
   float* sR = reinterpret_cast<float*>(sX1 + (size_t)KBH * bsp * 128);     // [8 warps][u][bsp] partial products
-  float* sSA = sR + (size_t)(DEC_THREADS / 32) * u * bsp;
+  float* sSA = sR + (size_t)(DEC_THREADS / 32) * u * (bsp + 1);
   const int s_ld = u + 1;
   float* sSB = sSA + (size_t)bsp * s_ld;
   const int DG = H >> 3, FG = DEC_THREADS / DG, PW = DG >= 32 ? DG / 32 : 1;
   float* sP = sSB + (size_t)bsp * s_ld;     // [N][PW]
   float* sDa = sP + (size_t)N * PW;         // [N] d alpha -> d score
   float* sAl = sDa + N;                     // [N] alpha
-  float* sC = sAl + N;                      // [FG][H]
+  float* sC = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sAl + N) + 15) & ~uintptr_t(15));      // [FG][H], float4 access
   uint64_t* bar0 = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sC + (size_t)FG * H) + 15) & ~uintptr_t(7));
   uint64_t* bar1 = bar0 + 1;                // TMA: chunk buffer X0 / X1 has landed
   uint32_t ph0 = 0, ph1 = 0;
@@ -440,25 +459,27 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
       }
     }
   };
-  // partial tiles of the 8 warps -> S[video * s_ld + row]
-  auto reduce_tiles = [&](float (&acc)[4][4], float* S) {
-    float* r = sR + (size_t)warp * u * bsp;
+  // partial tiles of the 8 warps -> shared memory [warp][row][bsp + 1] (padded: the summing threads walk rows fastest);
+  // after the CTA barrier every thread sums the 8 partials of ITS (unit, video) pairs itself (tile_sum) -- no second
+  // staging buffer, no second barrier before the consumer
+  const int r_ld = bsp + 1;
+  auto spill_tiles = [&](float (&acc)[4][4]) {
+    float* r = sR + (size_t)warp * u * r_ld;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       if (nt * 8 < bsp) {
         const int col = nt * 8 + 2 * tig;
-        if (gid < u) { r[gid * bsp + col] = acc[nt][0]; r[gid * bsp + col + 1] = acc[nt][1]; }
-        if (gid + 8 < u) { r[(gid + 8) * bsp + col] = acc[nt][2]; r[(gid + 8) * bsp + col + 1] = acc[nt][3]; }
+        if (gid < u) { r[gid * r_ld + col] = acc[nt][0]; r[gid * r_ld + col + 1] = acc[nt][1]; }
+        if (gid + 8 < u) { r[(gid + 8) * r_ld + col] = acc[nt][2]; r[(gid + 8) * r_ld + col + 1] = acc[nt][3]; }
       }
     }
     __syncthreads();
-    for (int idx = tid; idx < u * bsp; idx += DEC_THREADS) {
-      const int row = idx / bsp, col = idx - row * bsp;
-      float s = 0.f;
-      for (int w = 0; w < nwarps; ++w) s += sR[(size_t)w * u * bsp + idx];
-      S[col * s_ld + row] = s;
-    }
-    __syncthreads();
+  };
+  auto tile_sum = [&](int row, int col) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < DEC_THREADS / 32; ++w) s += sR[((size_t)w * u + row) * r_ld + col];
+    return s;
   };
 
   // attention residency (as in the forward kernel)
@@ -492,9 +513,9 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
   }
 
   const int n_items = (u * C + DEC_THREADS - 1) / DEC_THREADS;
-  float dhc[DEC_ITEMS];
+  float dhc[ITEMS];
 #pragma unroll
-  for (int k = 0; k < DEC_ITEMS; ++k) dhc[k] = 0.f;
+  for (int k = 0; k < ITEMS; ++k) dhc[k] = 0.f;
   unsigned target = 0;
   const long long xrow = (long long)5 * H;
 
@@ -504,7 +525,7 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
   auto l2_prefetch = [](const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); };
   auto fetch = [&](int i) {
 #pragma unroll
-    for (int k = 0; k < DEC_ITEMS; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
       if (k < n_items) {
         const int idx = tid + k * DEC_THREADS, jj = idx % u, lb = idx / u;
         if (lb < bs && (jj & 7) == 0) {              // one request per 32-byte sector
@@ -520,20 +541,41 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
     if (tid >= 32 && tid < 32 + (H >> 3)) l2_prefetch(p.q_all + (long long)i * B * p.q_ld + (long long)vb * p.q_ld + (tid - 32) * 8);
   };
 
+  // Saved activations of the step to process next, in registers: loaded (from L2, where `fetch` put them a step earlier)
+  // just before the last group barrier of the previous step, so that their latency hides behind that barrier.
+  float sv[ITEMS][6];
+  auto load_saved = [&](int i) {
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) sv[k][a] = 0.f;
+      if (k < n_items) {
+        const int idx = tid + k * DEC_THREADS, jj = idx % u, lb = idx / u;
+        if (lb < bs) {
+          const int j = j0 + jj, b = b0 + lb;
+          const long long o = ((long long)i * B + b) * H + j;
+          sv[k][0] = __ldcg(p.d_hs + ((long long)b * L + i) * H + j);
+          sv[k][1] = __ldcg(p.r + o); sv[k][2] = __ldcg(p.z + o); sv[k][3] = __ldcg(p.n + o); sv[k][4] = __ldcg(p.ghn + o);
+          sv[k][5] = i > 0 ? __ldcg(p.hs + ((long long)b * L + (i - 1)) * H + j) : __ldcg(p.h0 + (long long)b * p.h0_ld + j);
+        }
+      }
+    }
+  };
+  load_saved(L - 1);
+
   for (int i = L - 1; i >= 0; --i) {
     bf16* xg = p.xg + (size_t)(i & 1) * B * xrow;
     phase_stamp(p.dbg, L - 1 - i, 0);
     // ---- B1: gate gradients ---------------------------------------------------------------------------------
 #pragma unroll
-    for (int k = 0; k < DEC_ITEMS; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
       if (k < n_items) {
         const int idx = tid + k * DEC_THREADS, jj = idx % u, lb = idx / u;
         if (lb < bs) {
           const int j = j0 + jj, b = b0 + lb;
-          const float dh = dhc[k] + p.d_hs[((long long)b * L + i) * H + j];
-          const long long o = ((long long)i * B + b) * H + j;
-          const float r = p.r[o], z = p.z[o], n = p.n[o], ghn = p.ghn[o];
-          const float hp = i > 0 ? p.hs[((long long)b * L + (i - 1)) * H + j] : p.h0[(long long)b * p.h0_ld + j];
+          const float dh = dhc[k] + sv[k][0];
+          const float r = sv[k][1], z = sv[k][2], n = sv[k][3], ghn = sv[k][4];
+          const float hp = sv[k][5];
           const float dn = dh * (1.f - z), dz = dh * (hp - n);
           const float dnp = dn * (1.f - n * n);
           const float dzp = dz * z * (1.f - z);
@@ -621,25 +663,36 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
     }
     phase_stamp(p.dbg, L - 1 - i, 3);
     phase_stamp(p.dbg, L - 1 - i, 4);
-    reduce_tiles(accA, sSA);
+    spill_tiles(accA);
     {
       float* dc = p.dctx_all + (long long)i * B * H;
       for (int idx = tid; idx < u * bs; idx += DEC_THREADS) {
         const int jj = idx % u, lb = idx / u;
-        dc[(long long)(b0 + lb) * H + j0 + jj] = sSA[lb * s_ld + jj];
+        dc[(long long)(b0 + lb) * H + j0 + jj] = tile_sum(jj, lb);
       }
     }
-    group_arrive(ctr);
-    target += (unsigned)C;
     phase_stamp(p.dbg, L - 1 - i, 5);
     // ---- B3: attention gradient of video vb ------------------------------------------------------------------
-    // the saved attention weights of this step do not depend on the exchange: fetched while the group barrier is pending
+    // the saved attention weights of this step do not depend on the exchange: fetched while dctx is on its way
     if (tid < N) sAl[tid] = __ldg(p.alpha + ((long long)i * B + vb) * N + tid);
-    group_wait(ctr, target);
     phase_stamp(p.dbg, L - 1 - i, 6);
     {
-      const float4* c4 = reinterpret_cast<const float4*>(p.dctx_all + ((long long)i * B + vb) * H + d0);
-      const float4 ca = __ldcg(c4), cb = __ldcg(c4 + 1);
+      // dctx of this video arrives in 16-float pieces from the group's CTAs: polled on the data itself, no barrier
+      float4 ca, cb;
+      const float* drow = p.dctx_all + ((long long)i * B + vb) * H;
+      if (p.xd == 1) {
+        poll_f8(drow + d0, ca, cb);
+      } else {
+        if (warp == 0) {
+          for (int c = tid * 8; c < H; c += 256) {
+            float4 a, b;
+            poll_f8(drow + c, a, b);
+            *reinterpret_cast<float4*>(sC + c) = a; *reinterpret_cast<float4*>(sC + c + 4) = b;
+          }
+        }
+        __syncthreads();
+        ca = *reinterpret_cast<const float4*>(sC + d0); cb = *reinterpret_cast<const float4*>(sC + d0 + 4);
+      }
       const float dc8[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
       const float4* q4 = reinterpret_cast<const float4*>(p.q_all + (long long)i * B * p.q_ld + (long long)vb * p.q_ld + d0);
       const float4 qa = __ldg(q4), qb = __ldg(q4 + 1);
@@ -732,6 +785,7 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
     group_arrive(ctr);
     target += (unsigned)C;
     // ---- B4: dh_{i-1} = dh z + W_hh^T dgh + W_q^T dq -----------------------------------------------------------
+    if (i > 0) load_saved(i - 1);
     group_wait(ctr, target);
     phase_stamp(p.dbg, L - 1 - i, 8);
     if (TMA) {
@@ -746,18 +800,18 @@ __global__ void __launch_bounds__(DEC_BWD_THREADS, 1) dec_persist_bwd_kernel(con
     mma_chunk(accB, aWB, 0, aX0);                 // dq: completes dh
     phase_stamp(p.dbg, L - 1 - i, 9);
     phase_stamp(p.dbg, L - 1 - i, 10);
-    reduce_tiles(accB, sSB);
+    spill_tiles(accB);
 #pragma unroll
-    for (int k = 0; k < DEC_ITEMS; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
       if (k < n_items) {
         const int idx = tid + k * DEC_THREADS, jj = idx % u, lb = idx / u;
-        if (lb < bs) dhc[k] += sSB[lb * s_ld + jj];
+        if (lb < bs) dhc[k] += tile_sum(jj, lb);
       }
     }
-    __syncthreads();
+    __syncthreads();          // sR is rewritten by the next step's B2
   }
 #pragma unroll
-  for (int k = 0; k < DEC_ITEMS; ++k) {
+  for (int k = 0; k < ITEMS; ++k) {
     if (k < n_items) {
       const int idx = tid + k * DEC_THREADS, jj = idx % u, lb = idx / u;
       if (lb < bs) p.dh_carry[(long long)(b0 + lb) * H + j0 + jj] = dhc[k];
@@ -918,6 +972,10 @@ int dec_persist_fwd(const DecPersistFwd& p0, cudaStream_t st) {
   const int grid = pl.G * pl.C;
   PVCR_REQUIRE(per_sm * dec_num_sms() >= grid, "dec_persist_fwd: %d CTAs cannot be co-resident", grid);
   PVCR_TRY(fill_zero(p.counters, sizeof(unsigned) * 32 * pl.G, st));
+  static const int xq = getenv("PVCR_DEC_FWD_XCHG") ? atoi(getenv("PVCR_DEC_FWD_XCHG")) : 2;     // A/B knob
+  p.xq = xq;
+  if (p.xq)      // arm the q slots with the sentinel the consumers poll for (0xFF bytes; persist.cuh)
+    PVCR_CUDA_CHECK(cudaMemset2DAsync(p.q_all, sizeof(float) * p.q_ld, 0xFF, sizeof(float) * p.H, (size_t)p.L * p.B, st));
   void* args[] = {&p, &tmH0, &tmHs, &tmCtx};
   LaunchScope ls_(KC_DEC_FWD, st);
   PVCR_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(DEC_THREADS), args, pl.smem, st));
@@ -932,8 +990,8 @@ int dec_persist_bwd(const DecPersistBwd& p0, cudaStream_t st) {
   p.dbg = getenv("PVCR_PHASE_DEC_BWD") ? debug_phase_buffer() : nullptr;
   const int H = p.H, KBH = H / 64, DG = H / 8, FG = DEC_THREADS / DG, PW = DG >= 32 ? DG / 32 : 1;
   size_t smem = (size_t)7 * KBH * pl.u * 128 + (size_t)2 * KBH * pl.bsp * 128;
-  smem += ((size_t)2 * pl.bsp * (pl.u + 1) + (size_t)p.N * PW + 2 * p.N + (size_t)FG * H) * 4 + 64 + 1024;
-  smem += (size_t)(DEC_THREADS / 32) * pl.u * pl.bsp * 4;        // partial product tiles of the 8 warps
+  smem += ((size_t)2 * pl.bsp * (pl.u + 1) + (size_t)p.N * PW + 2 * p.N + (size_t)FG * H) * 4 + 64 + 16 + 1024;
+  smem += (size_t)(DEC_THREADS / 32) * pl.u * (pl.bsp + 1) * 4;  // partial product tiles of the 8 warps (padded rows)
   PVCR_REQUIRE(pl.u == 16 || pl.u == 8, "dec_persist_bwd: unit slice u=%d not supported by the mma.sync tiling", pl.u);
   PVCR_REQUIRE(smem <= 227 * 1024, "dec_persist_bwd: needs %zu B of shared memory", smem);
   // PVCR_TANH_ACCURATE_BWD=1: ex2 + rcp instead of the single-MUFU hardware tanh (2^-11) in the attention gradient.
@@ -947,6 +1005,7 @@ int dec_persist_bwd(const DecPersistBwd& p0, cudaStream_t st) {
                                : (pl.NF == 5 ? (const void*)dec_persist_bwd_kernel<5, false> : (const void*)dec_persist_bwd_kernel<10, false>))
                             : (pl.NF == 2 ? (const void*)dec_persist_bwd_kernel<2, true>
                                : (pl.NF == 5 ? (const void*)dec_persist_bwd_kernel<5, true> : (const void*)dec_persist_bwd_kernel<10, true>));
+  if (!no_tma && approx && pl.NF == 10 && pl.u * pl.C <= 2 * DEC_THREADS) kern = (const void*)dec_persist_bwd_kernel<10, false, true, 2>;
   CUtensorMap tmXg;        // exchange buffer [2][B][5H] as (k, video, parity)
   PVCR_TRY(make_tensor_map(&tmXg, OperandView{p.xg, (long long)5 * p.H, (long long)p.B * 5 * p.H, p.B, 2}, 5 * p.H, pl.bsp));
   PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -955,6 +1014,10 @@ int dec_persist_bwd(const DecPersistBwd& p0, cudaStream_t st) {
   const int grid = pl.G * pl.C;
   PVCR_REQUIRE(per_sm * dec_num_sms() >= grid, "dec_persist_bwd: %d CTAs cannot be co-resident", grid);
   PVCR_TRY(fill_zero(p.counters, sizeof(unsigned) * 32 * pl.G, st));
+  static const int xd = getenv("PVCR_DEC_BWD_XCHG") ? atoi(getenv("PVCR_DEC_BWD_XCHG")) : 1;      // A/B knob (1 or 2)
+  p.xd = xd == 2 ? 2 : 1;
+  // arm the dctx slots with the sentinel the consumers poll for (0xFF bytes; persist.cuh)
+  PVCR_CUDA_CHECK(cudaMemsetAsync(p.dctx_all, 0xFF, sizeof(float) * (size_t)p.L * p.B * p.H, st));
   void* args[] = {&p, &tmXg};
   LaunchScope ls_(KC_DEC_BWD, st);
   PVCR_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(DEC_BWD_THREADS), args, smem, st));

@@ -211,6 +211,7 @@ struct DecPersistFwd {
   float *r, *z, *n, *ghn;                   // [L][B,H]
   unsigned* counters;
   long long* dbg;                           // phase timestamps (tuning aid, nullable)
+  int xq = 0;                               // q hand-over P1 -> P2: 0 group barrier, 1 every thread polls its words, 2 warp 0 polls
 };
 struct DecPersistBwd {
   int L, B, N, H, C, u, bsp;
@@ -239,6 +240,7 @@ struct DecPersistBwd {
   bf16* d1_p = nullptr; long long d1_p_ld = 0;
   unsigned* counters;
   long long* dbg;
+  int xd = 1;                               // dctx hand-over B2 -> B3 by polling the data: 1 every thread its words, 2 warp 0 for the CTA
 };
 // dpk / denc / dv from the per-step quantities saved by the backward sweep (hoisted out of the time loop)
 struct AttnGradArgs {

@@ -138,6 +138,34 @@ __device__ __forceinline__ void group_wait(const unsigned* ctr, unsigned target)
   __syncthreads();      // orders every thread's later loads after thread 0's acquire
 }
 
+// ---- small all-to-one exchanges by polling the DATA --------------------------------------------------------------
+// When a phase hands a few hundred floats to ONE consumer thread block (q and dctx of a video: 16 values from each of a
+// group's 32 CTAs), the consumer threads poll the words they need until none carries the sentinel the buffer was filled
+// with before the launch (0xFFFFFFFF, a NaN the kernels never produce).  No release fence, counter update, counter poll
+// and CTA barrier on the way: one store propagation + one load round trip instead of ~1.3 us.
+constexpr unsigned XCH_SENTINEL = 0xFFFFFFFFu;
+__device__ __forceinline__ float4 ld_volatile_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool has_sentinel(const float4& a, const float4& b) {
+  return __float_as_uint(a.x) == XCH_SENTINEL || __float_as_uint(a.y) == XCH_SENTINEL || __float_as_uint(a.z) == XCH_SENTINEL ||
+         __float_as_uint(a.w) == XCH_SENTINEL || __float_as_uint(b.x) == XCH_SENTINEL || __float_as_uint(b.y) == XCH_SENTINEL ||
+         __float_as_uint(b.z) == XCH_SENTINEL || __float_as_uint(b.w) == XCH_SENTINEL;
+}
+// 8 consecutive floats at p (32-byte aligned), polled until all have been written
+__device__ __forceinline__ void poll_f8(const float* p, float4& a, float4& b) {
+  a = ld_volatile_f4(p); b = ld_volatile_f4(p + 4);
+  if (has_sentinel(a, b)) {
+    const long long t0 = clock64();
+    do {
+      a = ld_volatile_f4(p); b = ld_volatile_f4(p + 4);
+      if (clock64() - t0 > 4000000000LL) __trap();
+    } while (has_sentinel(a, b));
+  }
+}
+
 // ---- exchanged operands by TMA ------------------------------------------------------------------------------------
 // One thread waits for the group counter and then fetches the operand with a few bulk-tensor copies (one 64-column
 // k-block x `rows_alloc` rows box each) straight into the SW128 buffer the MMAs read; completion is an mbarrier
