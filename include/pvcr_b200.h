@@ -298,6 +298,16 @@ int pvcr_s2vt_decode_bwd(const PvcrDims* d, const PvcrS2vtParams* p, const int64
 int pvcr_s2vtatt_decode_greedy(const PvcrDims* d, const PvcrS2vtAttParams* p, const float* enc_outs, const float* enc_final,
                                int64_t sos_id, int64_t* ids, float* logits, float* alphas, void* workspace,
                                size_t workspace_bytes, void* stream);
+/* The same decoder with the parameter-only work separated from the per-batch work (eval loops decode batch after batch
+ * with fixed parameters: eval.py / eval_attention.py call model(vid_feats, None) once per batch).  Exactly one of
+ * vid_feats / (enc_outs, enc_final) is given.  Without PVCR_DECODE_REUSE_PREPARED the call first stages the weight planes
+ * and the word table  T[w] = W_e Emb[w] + b_ih  (the decoder input projection of every vocabulary word; a decoding step
+ * reads row T[argmax]) into the workspace; with it the call trusts that the SAME workspace was prepared by an earlier call
+ * with the same dims and parameter values (and not written by anybody else since) and skips that work. */
+#define PVCR_DECODE_REUSE_PREPARED 1
+int pvcr_s2vtatt_greedy_ex(const PvcrDims* d, const PvcrS2vtAttParams* p, const float* vid_feats, const float* frame_scale,
+                           const float* enc_outs, const float* enc_final, int64_t sos_id, int64_t* ids, float* logits,
+                           float* alphas, void* workspace, size_t workspace_bytes, int flags, void* stream);
 int pvcr_s2vt_decode_greedy(const PvcrDims* d, const PvcrS2vtParams* p, const float* out1, const float* state1,
                             int64_t sos_id, int64_t* ids, float* logits, void* workspace, size_t workspace_bytes,
                             void* stream);

@@ -131,6 +131,8 @@ SIGNATURES = {
     "pvcr_s2vt_decode_fwd": (c_int, [P(PvcrDims), P(PvcrS2vtParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
     "pvcr_s2vt_decode_bwd": (c_int, [P(PvcrDims), P(PvcrS2vtParams), c_vp, c_vp, c_vp, P(PvcrS2vtGrads), c_vp, c_vp, c_vp,
                                      c_size, c_vp]),
+    "pvcr_s2vtatt_greedy_ex": (c_int, [P(PvcrDims), P(PvcrS2vtAttParams), c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
+                                       c_size, c_int, c_vp]),
     "pvcr_s2vtatt_decode_greedy": (c_int, [P(PvcrDims), P(PvcrS2vtAttParams), c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
                                            c_size, c_vp]),
     "pvcr_s2vt_decode_greedy": (c_int, [P(PvcrDims), P(PvcrS2vtParams), c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_size, c_vp]),

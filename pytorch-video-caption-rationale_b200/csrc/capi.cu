@@ -50,7 +50,7 @@ int s2vt_decode_fwd(const PvcrDims&, const PvcrS2vtParams&, const float*, const 
 int s2vt_decode_bwd(const PvcrDims&, const PvcrS2vtParams&, const long long*, const float*, float*, PvcrS2vtGrads&, float*,
                     float*, void*, size_t, cudaStream_t);
 int s2vtatt_greedy_impl(const PvcrDims&, const PvcrS2vtAttParams&, const float*, const float*, const float*, const float*,
-                        long long, long long*, float*, float*, void*, size_t, cudaStream_t);
+                        long long, long long*, float*, float*, void*, size_t, cudaStream_t, int);
 int s2vt_decode_steps_impl(const PvcrDims&, const PvcrS2vtParams&, const float*, const float*, const float*, const float*,
                            long long, const long long*, const int*, float, long long*, long long*, float*, void*, size_t,
                            cudaStream_t);
@@ -222,7 +222,18 @@ int pvcr_s2vtatt_decode_greedy(const PvcrDims* d, const PvcrS2vtAttParams* p, co
                                size_t workspace_bytes, void* stream) {
   if (!d || !p || !enc_outs || !enc_final) { set_last_error("pvcr_s2vtatt_decode_greedy: null argument"); return PVCR_ERR_ARG; }
   return s2vtatt_greedy_impl(*d, *p, nullptr, nullptr, enc_outs, enc_final, (long long)sos_id, (long long*)ids, logits,
-                             alphas, workspace, workspace_bytes, (cudaStream_t)stream);
+                             alphas, workspace, workspace_bytes, (cudaStream_t)stream, 0);
+}
+int pvcr_s2vtatt_greedy_ex(const PvcrDims* d, const PvcrS2vtAttParams* p, const float* vid_feats, const float* frame_scale,
+                           const float* enc_outs, const float* enc_final, int64_t sos_id, int64_t* ids, float* logits,
+                           float* alphas, void* workspace, size_t workspace_bytes, int flags, void* stream) {
+  if (!d || !p || !ids || (!vid_feats && !enc_outs)) { set_last_error("pvcr_s2vtatt_greedy_ex: null argument"); return PVCR_ERR_ARG; }
+  if ((enc_outs != nullptr) != (enc_final != nullptr)) {
+    set_last_error("pvcr_s2vtatt_greedy_ex: enc_outs and enc_final come together"); return PVCR_ERR_ARG;
+  }
+  return s2vtatt_greedy_impl(*d, *p, enc_outs ? nullptr : vid_feats, enc_outs ? nullptr : frame_scale, enc_outs, enc_final,
+                             (long long)sos_id, (long long*)ids, logits, alphas, workspace, workspace_bytes,
+                             (cudaStream_t)stream, flags);
 }
 int pvcr_s2vt_decode_greedy(const PvcrDims* d, const PvcrS2vtParams* p, const float* out1, const float* state1,
                             int64_t sos_id, int64_t* ids, float* logits, void* workspace, size_t workspace_bytes,

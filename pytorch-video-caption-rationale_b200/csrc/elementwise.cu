@@ -429,10 +429,11 @@ __global__ void gru_gate_fwd_kernel(GruFwdArgs a) {
   if (idx >= a.B * a.H) return;
   const int b = idx / a.H, j = idx % a.H, H = a.H;
   float gi[3], gh[3];
+  const long long rb = a.gi_b_rows ? a.gi_b_rows[b] : (long long)b;
 #pragma unroll
   for (int g = 0; g < 3; ++g) {
     float x = a.gi_a ? a.gi_a[(long long)b * a.gi_a_ld + g * H + j] : 0.f;
-    if (a.gi_b) x += a.gi_b[(long long)b * a.gi_b_ld + g * H + j];
+    if (a.gi_b) x += a.gi_b[rb * a.gi_b_ld + g * H + j];
     if (a.gi_bias) x += a.gi_bias[g * H + j];
     gi[g] = x;
     gh[g] = a.b_hh[g * H + j] + (a.gh ? a.gh[(long long)b * a.gh_ld + g * H + j] : 0.f);

@@ -64,6 +64,7 @@ struct GruFwdArgs {
   int B, H;
   const float* gi_a; long long gi_a_ld;     // [B,3H] (nullable: the step has no input, e.g. S2VT rnn1 while decoding)
   const float* gi_b; long long gi_b_ld;     // optional second addend
+  const long long* gi_b_rows = nullptr;     // optional: video b reads row gi_b_rows[b] of gi_b (a table indexed by word id)
   const float* gi_bias;                     // optional [3H] bias addend
   const float* gh; long long gh_ld;         // [B,3H] W_hh h (no bias) or null (h_prev == 0)
   const float* b_hh;                        // [3H]

@@ -570,14 +570,15 @@ int s2vtatt_decode_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const long
 // ---- fixed-length greedy decoding (eval branch, model/S2VTAttModel.py:172-191) ---------------------------------
 struct GreedyWs {
   AttWs w;
-  Planes wv, emb_step;
-  float *logits_step, *hs;
+  Planes wv, emb_all;
+  float *logits_step, *hs, *emb_table;
   long long* words;
 };
 static void carve_greedy(Arena& a, const PvcrDims& d, GreedyWs& g) {
   carve(a, d, 0, g.w);
   g.wv = alloc_planes(a, d.Vc, d.H, d.nsplit);
-  g.emb_step = alloc_planes(a, d.B, d.E, d.nsplit);
+  g.emb_all = alloc_planes(a, d.Vc, d.E, d.nsplit);              // the whole embedding table as an A-role operand (prepare only)
+  g.emb_table = a.alloc<float>((size_t)d.Vc * 3 * d.H);           // W_e Emb[w] + b_ih for EVERY word w
   g.logits_step = a.alloc<float>((size_t)d.B * round_up(d.Vc, 4));
   g.hs = a.alloc<float>((size_t)d.B * d.L * d.H);
   g.words = a.alloc<long long>(d.B);
@@ -593,7 +594,7 @@ size_t s2vtatt_greedy_workspace(const PvcrDims& d) {
 int s2vtatt_greedy_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid, const float* frame_scale,
                    const float* enc_given, const float* final_given,
                    long long sos_id, long long* ids, float* logits, float* alphas, void* ws, size_t ws_bytes,
-                   cudaStream_t st) {
+                   cudaStream_t st, int flags) {
   PVCR_TRY(check_dims(d));
   const bool given = enc_given != nullptr;
   PVCR_REQUIRE(given == (final_given != nullptr), "s2vtatt greedy decode: encoder outputs and final state come together");
@@ -604,14 +605,25 @@ int s2vtatt_greedy_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const flo
   carve_greedy(a, d, gw);
   if (a.failed) { set_last_error("s2vtatt_greedy: workspace too small (%zu < %zu)", ws_bytes, a.off); return PVCR_ERR_WORKSPACE; }
   AttWs& w = gw.w;
+  // Parameter-only work: the weight planes and the word table  T[w] = W_e Emb[w] + b_ih  (decoder input projection of
+  // EVERY vocabulary word, one [Vc,E] x [E,3H] GEMM) -- a decoding step then reads row T[argmax] instead of gathering the
+  // embedding and multiplying it.  A caller that decodes batch after batch with unchanged parameters keeps the workspace
+  // and passes PVCR_DECODE_REUSE_PREPARED: everything in this block is skipped.
+  if (!(flags & PVCR_DECODE_REUSE_PREPARED)) {
+  if (!given) {
   PVCR_TRY(prep_weight(p.enc_w_ih, V, H3, V, w.wih_enc, st));
   PVCR_TRY(prep_weight(p.enc_w_hh, H, H3, H, w.whh_enc, st));
+  }
   PVCR_TRY(prep_weight(p.att_wk, H, H, H, w.wk, st));
   PVCR_TRY(prep_weight(p.att_wq, H, H, H, w.wcat, st, 0));
   PVCR_TRY(prep_weight(p.dec_w_hh, H, H3, H, w.wcat, st, H));
   PVCR_TRY(prep_weight(p.dec_w_ih, H + E, H3, H, w.wc, st));
   PVCR_TRY(prep_weight(p.dec_w_ih + H, H + E, H3, E, w.we, st));
   PVCR_TRY(prep_weight(p.out_w, H, Vc, H, gw.wv, st));
+  if (gw.emb_all.Kp != E) PVCR_TRY(fill_zero(gw.emb_all.ptr, sizeof(bf16) * (size_t)Vc * gw.emb_all.ld, st));
+  PVCR_TRY(stage(p.emb, E, Vc, E, gw.emb_all, 0, nullptr, NO_DROPOUT, st));
+  PVCR_TRY(gemm_planes(gw.emb_all.view(), w.we.view(), Vc, H3, (int)gw.emb_all.ld, gw.emb_table, H3, p.dec_b_ih, 0, st));
+  }
   if (w.enc_a.Kp != H) {
     PVCR_TRY(fill_zero(w.enc_a.ptr, sizeof(bf16) * (size_t)BN * w.enc_a.ld, st));
     PVCR_TRY(fill_zero(w.hs_a.ptr, sizeof(bf16) * (size_t)BL * w.hs_a.ld, st));
@@ -646,11 +658,10 @@ int s2vtatt_greedy_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const flo
     at.ctx_planes = w.ctx_a.ptr; at.ctx_planes_ld = w.ctx_a.ld; at.Hp = w.ctx_a.Kp; at.nsplit = d.nsplit;
     PVCR_TRY(attn_fwd(at, st));
     PVCR_TRY(gemm_planes(w.ctx_a.view(), w.wc.view(), B, H3, (int)w.ctx_a.ld, w.g2, H3, nullptr, 0, st));
-    PVCR_TRY(gather_split(p.emb, E, gw.words, B, gw.emb_step.ptr, gw.emb_step.ld, gw.emb_step.Kp, d.nsplit, NO_DROPOUT, st));
-    PVCR_TRY(gemm_planes(gw.emb_step.view(), w.we.view(), B, H3, (int)gw.emb_step.ld, w.g2, H3, p.dec_b_ih, 1, st));
     GruFwdArgs g{};
     g.B = B; g.H = H;
     g.gi_a = w.g2; g.gi_a_ld = H3;
+    g.gi_b = gw.emb_table; g.gi_b_ld = H3; g.gi_b_rows = gw.words;      // + W_e Emb[word] + b_ih
     g.gh = g1 + H; g.gh_ld = H4; g.b_hh = p.dec_b_hh;
     if (i == 0) { g.h_prev = h0.f; g.h_prev_ld = h0.f_ld; }
     else { g.h_prev = hs + (long long)(i - 1) * H; g.h_prev_ld = (long long)L * H; }
@@ -669,7 +680,7 @@ int s2vtatt_greedy_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const flo
 int s2vtatt_greedy(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid, const float* frame_scale,
                    long long sos_id, long long* ids, float* logits, float* alphas, void* ws, size_t ws_bytes,
                    cudaStream_t st) {
-  return s2vtatt_greedy_impl(d, p, vid, frame_scale, nullptr, nullptr, sos_id, ids, logits, alphas, ws, ws_bytes, st);
+  return s2vtatt_greedy_impl(d, p, vid, frame_scale, nullptr, nullptr, sos_id, ids, logits, alphas, ws, ws_bytes, st, 0);
 }
 
 // ---- fixed-length beam search over the decoder step (definition: oracle s2vtatt_beam_search) --------

@@ -389,6 +389,10 @@ int vocab_fused_bwd(const float* hs, const float* wv, const float* bv, const lon
   }
   if (dropout_p > 0.f) PVCR_TRY(dropout_apply(d_hs, d_hs, (long long)M * H, dr, st));
   {
+    // A/B knob: cap the CTAs of d W so that it leaves the d hs product (critical path) most of the machine and goes on
+    // in the shadow of the decoder sweep that follows (<= SMs the sweep leaves free, or the sweep waits for it)
+    static const int dwv_cap = getenv("PVCR_DWV_CAP") ? atoi(getenv("PVCR_DWV_CAP")) : 0;
+    CtaCap cap_(lane != st ? dwv_cap : 0);
     OperandView dv{w.D, w.ldD, 0, M, 1};
     PVCR_TRY(gemm_mn_store(dv, w.hs_a.view(), Vc, H, M, d_wv, H, 0, lane));
   }

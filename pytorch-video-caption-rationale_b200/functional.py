@@ -448,46 +448,82 @@ class VocabLogits(torch.autograd.Function):
         return None, d_hs, d_w, d_b
 
 
-def s2vtatt_greedy(vid, frame_scale, sos_id, max_len, seq_params, out_w, out_b, nsplit=3):
-    """-> (ids [B,L] int64, logits [B,L,Vc], alphas [L,B,N]); eval branch of S2VTAttModel."""
-    B, N, V = vid.shape
+class DecodePlan:
+    """Workspace of pvcr_s2vtatt_greedy_ex kept between calls, with the fingerprint of what it was prepared from: the staged
+    weight planes and the word table T[w] = W_e Emb[w] + b_ih are parameter-only work, so an eval loop that decodes batch
+    after batch pays for them once.  The fingerprint is (shape, storage address and autograd version of every parameter
+    tensor): in-place updates (optimizer steps, load_state_dict) change the version, re-allocated parameters the address.
+    Writes through ``.data`` are invisible to it -- call ``invalidate()`` after those."""
+
+    def __init__(self):
+        self.ws = None
+        self.key = None
+
+    def invalidate(self):
+        self.key = None
+
+    def lookup(self, key, nbytes, device):
+        """-> (workspace, reuse flag)."""
+        if self.ws is None or self.ws.numel() != int(nbytes) or self.ws.device != device:
+            self.ws, self.key = _ws(nbytes, device), None
+        reuse = self.key == key
+        self.key = key
+        return self.ws, reuse
+
+
+def _fingerprint(dims_tuple, srcs):
+    return dims_tuple + tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in srcs)
+
+
+def s2vtatt_greedy(vid, frame_scale, sos_id, max_len, seq_params, out_w, out_b, nsplit=3, plan=None, return_logits=True,
+                   enc_outs=None, enc_final=None):
+    """-> (ids [B,L] int64, logits [B,L,Vc] or None, alphas [L,B,N]); eval branch of S2VTAttModel (from the frames, or from
+    caller-given encoder outputs [B,N,H] / final state [B,H]: decode() in eval mode).  ``plan``: a DecodePlan that keeps the
+    prepared weights between calls."""
+    given = enc_outs is not None
+    srcs = list(seq_params) + [out_w, out_b]
     tensors = {f: _f32c(p) for f, p in zip(ATT_SEQ_FIELDS, seq_params)}
     tensors["out_w"], tensors["out_b"] = _f32c(out_w), _f32c(out_b)
     H = tensors["enc_w_hh"].shape[1]
     Vc, E = tensors["emb"].shape
+    if given:
+        B, N, _ = enc_outs.shape
+        V = 1
+        a_c, b_c = _f32c(enc_outs), _f32c(enc_final)
+        dev = a_c.device
+    else:
+        B, N, V = vid.shape
+        a_c = _f32c(vid)
+        b_c = None if frame_scale is None else _f32c(frame_scale)
+        dev = a_c.device
     dims = make_dims(B, N, V, H, E, max_len, Vc, nsplit, 0.0, 0)
-    vid_c = _f32c(vid)
-    fs_c = None if frame_scale is None else _f32c(frame_scale)
     Lb = lib()
-    ws = _ws(Lb.pvcr_s2vtatt_greedy_workspace(ctypes.byref(dims)), vid.device)
-    ids = torch.empty((B, max_len), dtype=torch.int64, device=vid.device)
-    logits = torch.empty((B, max_len, Vc), dtype=torch.float32, device=vid.device)
-    alphas = torch.empty((max_len, B, N), dtype=torch.float32, device=vid.device)
+    nbytes = Lb.pvcr_s2vtatt_greedy_workspace(ctypes.byref(dims))
+    flags = 0
+    zero_copy = all(tensors[f].data_ptr() == p.data_ptr() for f, p in zip(ATT_SEQ_FIELDS, seq_params)) and \
+        tensors["out_w"].data_ptr() == out_w.data_ptr() and tensors["out_b"].data_ptr() == out_b.data_ptr()
+    if plan is not None and zero_copy:                 # (a converted copy has no stable identity: prepare every call)
+        ws, reuse = plan.lookup(_fingerprint((B, N, V, H, E, max_len, Vc, nsplit, given), srcs), nbytes, dev)
+        flags = 1 if reuse else 0                      # PVCR_DECODE_REUSE_PREPARED
+    else:
+        ws = _ws(nbytes, dev)
+    ids = torch.empty((B, max_len), dtype=torch.int64, device=dev)
+    logits = torch.empty((B, max_len, Vc), dtype=torch.float32, device=dev) if return_logits else None
+    alphas = torch.empty((max_len, B, N), dtype=torch.float32, device=dev)
     ps = _fill_struct(PvcrS2vtAttParams(), ATT_PARAM_FIELDS, tensors)
-    check(Lb.pvcr_s2vtatt_greedy(ctypes.byref(dims), ctypes.byref(ps), ptr(vid_c), ptr(fs_c), int(sos_id), ptr(ids),
-                                 ptr(logits), ptr(alphas), ptr(ws), ws.numel(), stream_ptr()), "pvcr_s2vtatt_greedy")
+    check(Lb.pvcr_s2vtatt_greedy_ex(ctypes.byref(dims), ctypes.byref(ps), None if given else ptr(a_c),
+                                    None if given else ptr(b_c), ptr(a_c) if given else None, ptr(b_c) if given else None,
+                                    int(sos_id), ptr(ids), ptr(logits), ptr(alphas), ptr(ws), ws.numel(), flags,
+                                    stream_ptr()), "pvcr_s2vtatt_greedy_ex")
     return ids, logits, alphas
 
 
-def s2vtatt_decode_greedy(enc_outs, enc_final, sos_id, max_len, seq_params, out_w, out_b, nsplit=3):
+def s2vtatt_decode_greedy(enc_outs, enc_final, sos_id, max_len, seq_params, out_w, out_b, nsplit=3, plan=None,
+                          return_logits=True):
     """Greedy decoding from caller-given encoder outputs [B,N,H] / final state [B,H] -> (ids [B,L], logits [B,L,Vc],
     alphas [L,B,N]); eval branch of S2VTAttModel.decode (model/S2VTAttModel.py:231-243)."""
-    B, N, H = enc_outs.shape
-    tensors = {f: _f32c(p) for f, p in zip(ATT_SEQ_FIELDS, seq_params)}
-    tensors["out_w"], tensors["out_b"] = _f32c(out_w), _f32c(out_b)
-    Vc, E = tensors["emb"].shape
-    dims = make_dims(B, N, 1, H, E, max_len, Vc, nsplit, 0.0, 0)
-    enc_c, fin_c = _f32c(enc_outs), _f32c(enc_final)
-    Lb = lib()
-    ws = _ws(Lb.pvcr_s2vtatt_greedy_workspace(ctypes.byref(dims)), enc_c.device)
-    ids = torch.empty((B, max_len), dtype=torch.int64, device=enc_c.device)
-    logits = torch.empty((B, max_len, Vc), dtype=torch.float32, device=enc_c.device)
-    alphas = torch.empty((max_len, B, N), dtype=torch.float32, device=enc_c.device)
-    ps = _fill_struct(PvcrS2vtAttParams(), ATT_PARAM_FIELDS, tensors)
-    check(Lb.pvcr_s2vtatt_decode_greedy(ctypes.byref(dims), ctypes.byref(ps), ptr(enc_c), ptr(fin_c), int(sos_id), ptr(ids),
-                                        ptr(logits), ptr(alphas), ptr(ws), ws.numel(), stream_ptr()),
-          "pvcr_s2vtatt_decode_greedy")
-    return ids, logits, alphas
+    return s2vtatt_greedy(None, None, sos_id, max_len, seq_params, out_w, out_b, nsplit, plan, return_logits,
+                          enc_outs=enc_outs, enc_final=enc_final)
 
 
 def s2vt_decode_greedy(out1, state1, sos_id, max_len, seq_params, out_w, out_b, nsplit=3):

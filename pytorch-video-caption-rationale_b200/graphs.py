@@ -198,18 +198,20 @@ class GraphedGreedy:
     """CUDA-graph capture of fixed-length greedy captioning (model.greedy) for one batch shape: at small batches the
     step-wise decode is launch-latency bound, a single graph launch removes the host from the loop."""
 
-    def __init__(self, model, example_vid):
+    def __init__(self, model, example_vid, return_logits=True):
+        """The warm-up call prepares the weights (model.greedy keeps them in its DecodePlan), so the captured graph holds
+        the per-batch work only: it is valid for as long as the parameters keep their values (re-create it after training)."""
         self.model = model
         self.static_vid = example_vid.clone()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            model.greedy(self.static_vid)
+            model.greedy(self.static_vid, return_logits=return_logits)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            out = model.greedy(self.static_vid)
+            out = model.greedy(self.static_vid, return_logits=return_logits)
         self.static_out = tuple(o for o in out)
 
     def __call__(self, vid):

@@ -121,7 +121,7 @@ class S2VTAttModel(nn.Module):
         with torch.no_grad():
             d = self.decoder
             _, logits, alphas = F_.s2vtatt_decode_greedy(enc, fin, d.sos_id, d.max_len, self._seq_params(), lin.weight,
-                                                         lin.bias)
+                                                         lin.bias, plan=self._plan("decode"))
         self.last_alphas = alphas
         return logits
 
@@ -236,13 +236,33 @@ class S2VTAttModel(nn.Module):
         except StopIteration as done:
             return done.value
 
+    def _plan(self, which):
+        """Prepared-weights cache of the decoding entry points (functional.DecodePlan), one per entry point."""
+        plans = self.__dict__.setdefault("_decode_plans", {})
+        if which not in plans:
+            plans[which] = F_.DecodePlan()
+        return plans[which]
+
+    def invalidate_decode_cache(self):
+        """Forget the weights prepared for decoding (needed only after parameter writes autograd cannot see, e.g. through
+        ``.data``; optimizer steps, ``load_state_dict`` and ``train()`` are noticed)."""
+        for pl in self.__dict__.get("_decode_plans", {}).values():
+            pl.invalidate()
+
+    def train(self, mode=True):
+        if mode:
+            self.invalidate_decode_cache()
+        return super().train(mode)
+
     @torch.no_grad()
-    def greedy(self, vid_feats, frame_scale=None):
-        """Fixed-length greedy decoding (eval branch, model/S2VTAttModel.py:172-191): -> (ids [B,L], logits [B,L,Vc])."""
+    def greedy(self, vid_feats, frame_scale=None, return_logits=True):
+        """Fixed-length greedy decoding (eval branch, model/S2VTAttModel.py:172-191): -> (ids [B,L], logits [B,L,Vc]);
+        ``return_logits=False`` skips materialising the logits (captioning needs the ids only) and returns None for them."""
         d = self.decoder
         lin = d.pred_linear[1]
         ids, logits, alphas = F_.s2vtatt_greedy(vid_feats, frame_scale, d.sos_id, d.max_len, self._seq_params(),
-                                                lin.weight, lin.bias)
+                                                lin.weight, lin.bias, plan=self._plan("greedy"),
+                                                return_logits=return_logits)
         self.last_alphas = alphas
         return ids, logits
 
