@@ -235,7 +235,13 @@ __device__ __forceinline__ void split3(float x, bf16& t0, bf16& t1, bf16& t2) {
 __host__ __device__ inline int split_planes(int nsplit) { return nsplit == 1 ? 1 : (nsplit == 2 ? 3 : 6); }
 // 0-based term index held by plane p; tables packed 2 bits per plane:
 //   nsplit 2: A = {1,0,0}  B = {0,1,0}        nsplit 3: A = {2,1,0,1,0,0}  B = {0,1,2,0,1,0}
+// role_b == 2: COMPACT weight planes -- the nsplit distinct terms once each (plane t = term t); the GEMM producer maps the
+// K-block of virtual plane p to stored plane B_TERM[p] (GemmCoords::b_kp / b_terms), so a weight is stored and streamed
+// nsplit times instead of {1,3,6} times.
+__host__ __device__ inline int split_planes_role(int nsplit, int role_b) { return role_b == 2 ? nsplit : split_planes(nsplit); }
+__host__ __device__ inline unsigned split_b_terms(int nsplit) { return nsplit == 1 ? 0u : (nsplit == 2 ? 4u : 292u); }
 __host__ __device__ inline int split_term(int nsplit, int role_b, int p) {
+  if (role_b == 2) return p;
   const unsigned code = nsplit == 1 ? 0u : (nsplit == 2 ? (role_b ? 4u : 1u) : (role_b ? 292u : 70u));
   return (int)((code >> (2 * p)) & 3u);
 }

@@ -71,7 +71,7 @@ __device__ __forceinline__ unsigned long long drop_index(const Dropout& d, long 
 __device__ __forceinline__ void write_split(bf16* row_out, int Kp, int k, int nsplit, int role_b, float x) {
   bf16 t[3];
   split3(x, t[0], t[1], t[2]);
-  const int P = split_planes(nsplit);
+  const int P = split_planes_role(nsplit, role_b);
   for (int p = 0; p < P; ++p) row_out[(long long)p * Kp + k] = t[split_term(nsplit, role_b, p)];
 }
 
@@ -83,7 +83,7 @@ __global__ void cast_split_kernel(const float* __restrict__ in, long long ld_in,
                                   const float* __restrict__ row_scale, Dropout drop) {
   const int groups = Cp / 8;
   const long long total = (long long)R * groups;
-  const int P = split_planes(nsplit);
+  const int P = split_planes_role(nsplit, role_b);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / groups), c0 = (int)(i % groups) * 8;

@@ -198,4 +198,83 @@ int gemm_store(const OperandView& a, const OperandView& b, const GemmCoords& gc,
   return launch_gemm_tn<128, 3, EpiStore>(a, b, gc, grid_z, epi, stream);
 }
 
+// ---- projection + row arg-max in one pass (greedy decoding: logits_i = h_i W_v^T + b, word_{i+1} = argmax) -------------
+// The epilogue keeps a running (max, first index) per accumulator row and column part while it adds the bias (and stores
+// the logits when the caller wants them); a one-warp-per-row kernel combines the parts.  The logits are not read back.
+struct EpiArgmax {
+  static constexpr int SMEM_PER_WARP = 0;
+  float* C; long long ldc;              // nullable: logits not materialised
+  const float* bias;
+  float* pmax; int* pidx;
+  int M, N, nparts;
+  float m_run; int i_run;
+  __device__ __forceinline__ void begin(int, int) { m_run = -INFINITY; i_run = 0x7fffffff; }
+  __device__ __forceinline__ void chunk(int row, int col0, int, float (&v)[32]) {
+    if (row >= M) return;
+    const bool full = col0 + 32 <= N;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (full || col0 + j < N) {
+        v[j] += bias ? __ldg(bias + col0 + j) : 0.f;
+        if (v[j] > m_run) { m_run = v[j]; i_run = col0 + j; }      // ascending columns: the first maximum wins
+      }
+    }
+    if (C) {
+      float* c = C + (long long)row * ldc + col0;
+      if (full && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < N) c[j] = v[j];
+      }
+    }
+  }
+  __device__ __forceinline__ void end(int row, int part, int) {
+    if (row < M) { pmax[(long long)row * nparts + part] = m_run; pidx[(long long)row * nparts + part] = i_run; }
+  }
+};
+__global__ void __launch_bounds__(128) argmax_parts_kernel(const float* __restrict__ pmax, const int* __restrict__ pidx, int R,
+                                                           int nparts, long long* out, long long out_stride, long long* next) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= R) return;
+  float m = -INFINITY;
+  int mi = 0x7fffffff;
+  for (int j = lane; j < nparts; j += 32) {
+    const float v = pmax[(long long)row * nparts + j];
+    const int i = pidx[(long long)row * nparts + j];
+    if (v > m || (v == m && i < mi)) { m = v; mi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+  }
+  if (lane == 0) {
+    if (mi == 0x7fffffff) mi = 0;                      // all-NaN row: torch.argmax returns an index too
+    out[(long long)row * out_stride] = mi;
+    if (next) next[row] = mi;
+  }
+}
+size_t gemm_argmax_scratch(int M, int N) { return (size_t)M * cdiv(N, 256) * 2 * (sizeof(float) + sizeof(int)) + 256; }
+// logits (nullable) [M, ldc] = A B^T + bias;  out[row * out_stride] = next[row] = argmax_n.  scratch: gemm_argmax_scratch bytes.
+int gemm_argmax(const OperandView& a, const OperandView& b, int M, int N, int Kcat, const float* bias, float* logits,
+                long long ldc, long long* out, long long out_stride, long long* next, void* scratch, cudaStream_t st) {
+  GemmCoords gc{M, N, Kcat, 0, 0, 0, 0};
+  if (b.kp) { gc.b_kp = b.kp; gc.b_terms = split_b_terms(b.terms); }
+  const int nparts = cdiv(N, 256) * 2;
+  EpiArgmax epi{};
+  epi.C = logits; epi.ldc = ldc; epi.bias = bias; epi.M = M; epi.N = N; epi.nparts = nparts;
+  epi.pmax = reinterpret_cast<float*>(scratch);
+  epi.pidx = reinterpret_cast<int*>(epi.pmax + (size_t)M * nparts);
+  PVCR_TRY((launch_gemm_tn_persistent<256, 4, EpiArgmax>(a, b, gc, 1, epi, st)));
+  { LaunchScope ls_(KC_LOSS, st);
+    argmax_parts_kernel<<<cdiv(M, 4), 128, 0, st>>>(epi.pmax, epi.pidx, M, nparts, out, out_stride, next);
+  }
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  return PVCR_OK;
+}
+
 }  // namespace pvcr

@@ -32,6 +32,15 @@ struct GemmCoords {
   int a_z0, a_zmul;     // slab coordinate of A for grid z:  a_z0 + z * a_zmul
   int b_z0, b_zmul;
   int k_splits;         // > 1: grid z enumerates K ranges instead of slabs (epilogue must accumulate atomically)
+  // compact B planes (common.cuh split_term role 2): K-block at virtual column k = p * b_kp + off reads the stored
+  // column  term(p) * b_kp + off,  term(p) = (b_terms >> 2p) & 3.  b_kp == 0: B is stored as it is multiplied.
+  int b_kp = 0;
+  unsigned b_terms = 0;
+  __host__ __device__ int b_col(int k) const {
+    if (b_kp == 0) return k;
+    const int p = k / b_kp;
+    return (int)((b_terms >> (2 * p)) & 3u) * b_kp + (k - p * b_kp);
+  }
 };
 
 #ifdef __CUDACC__
@@ -88,7 +97,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_arrive_expect_tx(&full_bar[s], SM::STAGE_BYTES);
         uint8_t* sa = smem + s * SM::STAGE_BYTES;
         tma_load_3d(sa, &tmA, &full_bar[s], (kb0 + kb) * GEMM_BK, m0, az);
-        tma_load_3d(sa + SM::A_BYTES, &tmB, &full_bar[s], (kb0 + kb) * GEMM_BK, n0, bz);
+        tma_load_3d(sa + SM::A_BYTES, &tmB, &full_bar[s], gc.b_col((kb0 + kb) * GEMM_BK), n0, bz);
       }
     }
   } else if (warp == 1) {
@@ -215,7 +224,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             for (int i = 0; i < BN / 64; ++i)
               tma_load_3d(sa + SM::A_BYTES + i * 8192, &tmB, &full_bar[s], n0 + 64 * i, kb * GEMM_BK, bz);
           } else {
-            tma_load_3d(sa + SM::A_BYTES, &tmB, &full_bar[s], kb * GEMM_BK, n0, bz);
+            tma_load_3d(sa + SM::A_BYTES, &tmB, &full_bar[s], gc.b_col(kb * GEMM_BK), n0, bz);
           }
         }
       }
@@ -689,6 +698,7 @@ struct OperandView {
   const bf16* ptr;
   long long ld, slab_stride;
   int rows, slabs;
+  int kp = 0, terms = 0;      // compact B-role planes: `terms` stored planes of kp columns each (0: plain)
 };
 
 // Upper bound on the CTAs of a persistent GEMM launched while a CtaCap is alive on this host thread (0 = all SMs):
@@ -713,7 +723,8 @@ int launch_gemm_tn(const OperandView& a, const OperandView& b, const GemmCoords&
   PVCR_REQUIRE(gc.M > 0 && gc.N > 0 && grid_z > 0, "gemm: empty problem M=%d N=%d z=%d", gc.M, gc.N, grid_z);
   CUtensorMap ta, tb;
   PVCR_TRY(make_tensor_map(&ta, a, gc.K, GEMM_BM));
-  PVCR_TRY(make_tensor_map(&tb, b, gc.K, BN));
+  PVCR_TRY(make_tensor_map(&tb, b, b.kp ? b.kp * b.terms : gc.K, BN));
+  PVCR_REQUIRE((b.kp != 0) == (gc.b_kp != 0), "gemm: compact B planes need GemmCoords::b_kp (and vice versa)");
   auto kern = gemm_tn_kernel<BN, STAGES, Epi>;
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
@@ -740,7 +751,8 @@ int launch_gemm_tn_persistent(const OperandView& a, const OperandView& b, const 
   PVCR_REQUIRE(gc.M > 0 && gc.N > 0 && grid_z > 0, "gemm: empty problem M=%d N=%d z=%d", gc.M, gc.N, grid_z);
   CUtensorMap ta, tb;
   if (A_MN) PVCR_TRY(make_tensor_map_mn(&ta, a, gc.M)); else PVCR_TRY(make_tensor_map(&ta, a, gc.K, GEMM_BM));
-  if (B_MN) PVCR_TRY(make_tensor_map_mn(&tb, b, gc.N)); else PVCR_TRY(make_tensor_map(&tb, b, gc.K, BN));
+  if (B_MN) PVCR_TRY(make_tensor_map_mn(&tb, b, gc.N)); else PVCR_TRY(make_tensor_map(&tb, b, b.kp ? b.kp * b.terms : gc.K, BN));
+  PVCR_REQUIRE((b.kp != 0) == (gc.b_kp != 0) && !(B_MN && b.kp), "gemm: compact B planes need GemmCoords::b_kp (K-major B only)");
   auto kern = gemm_tn_persistent_kernel<BN, STAGES, Epi, A_MN, B_MN, EW>;
   static bool attr_set = false;
   static int sms = 0;

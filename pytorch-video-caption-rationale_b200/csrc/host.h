@@ -48,11 +48,24 @@ struct Planes {
   bf16* ptr;
   long long ld;
   int rows, K, Kp, nsplit;
+  bool compact = false;          // B-role planes holding each term once (common.cuh split_term role 2)
   int P() const { return split_planes(nsplit); }
-  OperandView view() const { return OperandView{ptr, ld, 0, rows, 1}; }
+  OperandView view() const {
+    OperandView v{ptr, ld, 0, rows, 1};
+    if (compact) { v.kp = Kp; v.terms = nsplit; }
+    return v;
+  }
   // rows [r0, r0+nr)
   OperandView view_rows(int r0, int nr) const { return OperandView{ptr + (long long)r0 * ld, ld, 0, nr, 1}; }
 };
+// weight planes in the compact layout (a no-op distinction for nsplit == 1)
+inline Planes alloc_planes_compact(Arena& a, int rows, int K, int nsplit) {
+  Planes p;
+  p.rows = rows; p.K = K; p.Kp = (int)round_up(K, 64); p.nsplit = nsplit; p.compact = nsplit > 1;
+  p.ld = (long long)nsplit * p.Kp;
+  p.ptr = a.alloc<bf16>((size_t)rows * p.ld);
+  return p;
+}
 inline Planes alloc_planes(Arena& a, int rows, int K, int nsplit) {
   Planes p;
   p.rows = rows; p.K = K; p.Kp = (int)round_up(K, 64); p.nsplit = nsplit;
@@ -63,6 +76,11 @@ inline Planes alloc_planes(Arena& a, int rows, int K, int nsplit) {
 
 int gemm_store(const OperandView& a, const OperandView& b, const GemmCoords& gc, int grid_z, float* C, long long ldc,
                long long c_zstride, const float* bias, long long bias_zstride, int accumulate, cudaStream_t stream);
+
+// projection + row arg-max in one pass (gemm.cu): logits (nullable) = A B^T + bias, out[row * out_stride] = next[row] = argmax
+size_t gemm_argmax_scratch(int M, int N);
+int gemm_argmax(const OperandView& a, const OperandView& b, int M, int N, int Kcat, const float* bias, float* logits,
+                long long ldc, long long* out, long long out_stride, long long* next, void* scratch, cudaStream_t st);
 
 // bf16 (single-plane) copies of fp32 matrices staged during one backward call: the hoisted gradient GEMMs share
 // operands (d gi feeds dW_c, dW_e and d emb; the forward pass already staged vid / enc / embedded words), so each
@@ -93,6 +111,10 @@ int gemm_kn_store(const OperandView& a, const OperandView& b, int M, int N, int 
 inline int gemm_planes(const OperandView& a, const OperandView& b, int M, int N, int Kcat, float* C, long long ldc,
                        const float* bias, int accumulate, cudaStream_t st) {
   GemmCoords gc{M, N, Kcat, 0, 0, 0, 0};
+  if (b.kp) {                               // compact weight planes: Kcat is the contraction the A planes span
+    gc.b_kp = b.kp;
+    gc.b_terms = split_b_terms(b.terms);
+  }
   return gemm_store(a, b, gc, 1, C, ldc, 0, bias, 0, accumulate, st);
 }
 
@@ -107,7 +129,7 @@ inline int stage(const float* in, long long ld_in, int R, int C, const Planes& p
 
 // weight [N,K] fp32 -> B-role planes [N, P*Kp]
 inline int prep_weight(const float* w, long long ldw, int N, int K, const Planes& p, cudaStream_t st, int row0 = 0) {
-  return stage(w, ldw, N, K, p, 1, nullptr, NO_DROPOUT, st, row0);
+  return stage(w, ldw, N, K, p, p.compact ? 2 : 1, nullptr, NO_DROPOUT, st, row0);
 }
 // weight [N,K] fp32 -> transposed B-role planes [K, P*Np] occupying contraction columns n_off .. n_off+N-1
 inline int prep_weight_T(const float* w, long long ldw, int N, int K, const Planes& p, int n_off, int zero_pad,

@@ -573,15 +573,17 @@ struct GreedyWs {
   Planes wv, emb_all;
   float *logits_step, *hs, *emb_table;
   long long* words;
+  void* argmax_scratch;
 };
 static void carve_greedy(Arena& a, const PvcrDims& d, GreedyWs& g) {
   carve(a, d, 0, g.w);
-  g.wv = alloc_planes(a, d.Vc, d.H, d.nsplit);
+  g.wv = alloc_planes_compact(a, d.Vc, d.H, d.nsplit);           // each term of W_v once: the planes stay L2-resident between steps
   g.emb_all = alloc_planes(a, d.Vc, d.E, d.nsplit);              // the whole embedding table as an A-role operand (prepare only)
   g.emb_table = a.alloc<float>((size_t)d.Vc * 3 * d.H);           // W_e Emb[w] + b_ih for EVERY word w
   g.logits_step = a.alloc<float>((size_t)d.B * round_up(d.Vc, 4));
   g.hs = a.alloc<float>((size_t)d.B * d.L * d.H);
   g.words = a.alloc<long long>(d.B);
+  g.argmax_scratch = a.alloc<char>(gemm_argmax_scratch(d.B, d.Vc));
 }
 size_t s2vtatt_greedy_workspace(const PvcrDims& d) {
   Arena a(nullptr, 0);
@@ -644,20 +646,29 @@ int s2vtatt_greedy_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const flo
   PVCR_TRY(gemm_planes(w.enc_a.view(), w.wk.view(), BN, H, (int)w.enc_a.ld, w.pk, H, nullptr, 0, st));
   PVCR_TRY(fill_i64(gw.words, sos_id, B, st));
   float* hs = gw.hs;
-  for (int i = 0; i < L; ++i) {
+  // Step i: [q | gh] = [W_q; W_hh] h_{i-1} -> attention -> W_c ctx   (needs h_{i-1} only)
+  //         gates with T[word_i] -> h_i -> logits_i -> word_{i+1}    (the only place the fed-back word enters)
+  // so the first half of step i+1 does not wait for the vocabulary projection and arg-max of step i: it runs on a side
+  // lane next to them and the two meet again at the gates of step i+1.
+  auto recurrent_half = [&](int i, cudaStream_t s) -> int {
     OperandView hprev_a = (i == 0)
         ? OperandView{const_cast<bf16*>(h0.a), h0.a_ld, 0, B, 1}
         : OperandView{w.hs_a.ptr + (long long)(i - 1) * w.hs_a.ld, (long long)L * w.hs_a.ld, 0, B, 1};
-    float* g1 = w.g1_all;
-    PVCR_TRY(gemm_planes(hprev_a, w.wcat.view(), B, H4, (int)w.wcat.ld, g1, H4, nullptr, 0, st));
+    PVCR_TRY(gemm_planes(hprev_a, w.wcat.view(), B, H4, (int)w.wcat.ld, w.g1_all, H4, nullptr, 0, s));
     AttnFwdArgs at{};
     at.B = B; at.N = N; at.H = H;
-    at.q = g1; at.q_ld = H4; at.pk = w.pk; at.enc = w.enc; at.v = p.att_v;
+    at.q = w.g1_all; at.q_ld = H4; at.pk = w.pk; at.enc = w.enc; at.v = p.att_v;
     at.alpha = alphas ? alphas + (long long)i * B * N : w.alpha_all;
     at.ctx = w.ctx_all; at.ctx_ld = H;
     at.ctx_planes = w.ctx_a.ptr; at.ctx_planes_ld = w.ctx_a.ld; at.Hp = w.ctx_a.Kp; at.nsplit = d.nsplit;
-    PVCR_TRY(attn_fwd(at, st));
-    PVCR_TRY(gemm_planes(w.ctx_a.view(), w.wc.view(), B, H3, (int)w.ctx_a.ld, w.g2, H3, nullptr, 0, st));
+    PVCR_TRY(attn_fwd(at, s));
+    PVCR_TRY(gemm_planes(w.ctx_a.view(), w.wc.view(), B, H3, (int)w.ctx_a.ld, w.g2, H3, nullptr, 0, s));
+    return PVCR_OK;
+  };
+  static const bool overlap_off = getenv("PVCR_NO_DECODE_OVERLAP") != nullptr;       // A/B knob
+  PVCR_TRY(recurrent_half(0, st));
+  for (int i = 0; i < L; ++i) {
+    float* g1 = w.g1_all;
     GruFwdArgs g{};
     g.B = B; g.H = H;
     g.gi_a = w.g2; g.gi_a_ld = H3;
@@ -669,12 +680,20 @@ int s2vtatt_greedy_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const flo
     g.h_planes = w.hs_a.ptr + (long long)i * w.hs_a.ld; g.h_planes_ld = (long long)L * w.hs_a.ld;
     g.Hp = w.hs_a.Kp; g.nsplit = d.nsplit;
     PVCR_TRY(gru_gate_fwd(g, st));
+    bool forked = false;
+    if (i + 1 < L) {
+      cudaStream_t lane = st;
+      if (!overlap_off && side_site(3)) { PVCR_TRY(side_fork(st, &lane, 0)); forked = lane != st; }
+      PVCR_TRY(recurrent_half(i + 1, lane));
+    }
     OperandView h_a{w.hs_a.ptr + (long long)i * w.hs_a.ld, (long long)L * w.hs_a.ld, 0, B, 1};
-    float* lg = logits ? logits + (long long)i * Vc : gw.logits_step;
-    const long long ldl = logits ? (long long)L * Vc : round_up(Vc, 4);
-    PVCR_TRY(gemm_planes(h_a, gw.wv.view(), B, Vc, (int)gw.wv.ld, lg, ldl, p.out_b, 0, st));
-    PVCR_TRY(argmax_rows(lg, ldl, B, Vc, ids + i, L, gw.words, nullptr, 0, 0, st));
+    // logits_i and word_{i+1} in one pass: the arg-max is taken in the GEMM epilogue (the logits are stored only when the
+    // caller asked for them and never read back)
+    PVCR_TRY(gemm_argmax(h_a, gw.wv.view(), B, Vc, (int)w.hs_a.ld, p.out_b, logits ? logits + (long long)i * Vc : nullptr,
+                         (long long)L * Vc, ids + i, L, gw.words, gw.argmax_scratch, st));
+    if (forked) PVCR_TRY(side_join_lane(st, 0));
   }
+  PVCR_TRY(side_call_end(st));
   return PVCR_OK;
 }
 int s2vtatt_greedy(const PvcrDims& d, const PvcrS2vtAttParams& p, const float* vid, const float* frame_scale,
