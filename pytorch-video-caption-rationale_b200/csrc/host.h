@@ -177,6 +177,20 @@ struct GruSeq {
 };
 int gru_seq_fwd(const GruSeq& s, cudaStream_t st);
 
+// persistent GRU forward sweep in plain fp32 arithmetic (gru_f32_persist.cu): decoding, where operands may not be rounded
+struct GruF32Fwd {
+  int T, B, H, C;                              // C (CTAs per group of 32 videos) is filled in by the launcher
+  const float* gi; long long gi_ts, gi_ld;     // input projections of step t (b_ih included): gi + t*gi_ts, row b at b*gi_ld
+  const float* w_hh;                           // [3H, H] fp32, the parameter itself
+  const float* b_hh;
+  const float* h0; long long h0_ld;            // initial state (null => zeros)
+  float* h; long long h_ts, h_ld;              // h_t at h + t*h_ts, row b at b*h_ld
+  unsigned* counters;                          // >= 32 * ceil(B/32), zeroed by the launcher
+  long long* dbg = nullptr;                    // phase timestamps (tuning aid)
+};
+bool gru_f32_persist_eligible(int B, int H);
+int gru_f32_persist_fwd(const GruF32Fwd& p, cudaStream_t st);
+
 struct GruSeqGrad {
   const float* dh_ext; long long dh_ext_ts, dh_ext_ld;   // gradient on every h_t (nullable)
   float* dh_carry;                         // [B,H]: in = gradient on the final state, out = gradient on h0

@@ -640,7 +640,19 @@ int s2vtatt_greedy_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const flo
   } else {
   PVCR_TRY(stage(vid, V, BN, V, w.x_a, 0, frame_scale, NO_DROPOUT, st));
   PVCR_TRY(gemm_planes(w.x_a.view(), w.wih_enc.view(), BN, H3, (int)w.x_a.ld, w.gi_enc, H3, p.enc_b_ih, 0, st));
-  PVCR_TRY(gru_seq_fwd(encoder_seq(d, p, w), st));
+  if (gru_f32_persist_eligible(B, H)) {
+    // the N encoder steps in one launch, exact fp32 on the CUDA cores (gru_f32_persist.cu)
+    GruF32Fwd q{};
+    q.T = N; q.B = B; q.H = H;
+    q.gi = w.gi_enc; q.gi_ts = H3; q.gi_ld = (long long)N * H3;
+    q.w_hh = p.enc_w_hh; q.b_hh = p.enc_b_hh;
+    q.h = w.enc; q.h_ts = H; q.h_ld = (long long)N * H;
+    q.counters = w.sync;
+    PVCR_TRY(gru_f32_persist_fwd(q, st));
+    PVCR_TRY(stage(w.enc, H, BN, H, w.enc_a, 0, nullptr, NO_DROPOUT, st));      // split planes of all N outputs in one pass
+  } else {
+    PVCR_TRY(gru_seq_fwd(encoder_seq(d, p, w), st));
+  }
   }
   const H0 h0 = initial_state(d, w, given);
   PVCR_TRY(gemm_planes(w.enc_a.view(), w.wk.view(), BN, H, (int)w.enc_a.ld, w.pk, H, nullptr, 0, st));
