@@ -258,18 +258,24 @@ __global__ void __launch_bounds__(128) argmax_parts_kernel(const float* __restri
     if (next) next[row] = mi;
   }
 }
-size_t gemm_argmax_scratch(int M, int N) { return (size_t)M * cdiv(N, 256) * 2 * (sizeof(float) + sizeof(int)) + 256; }
+size_t gemm_argmax_scratch(int M, int N) { return (size_t)M * cdiv(N, 192) * 2 * (sizeof(float) + sizeof(int)) + 256; }
 // logits (nullable) [M, ldc] = A B^T + bias;  out[row * out_stride] = next[row] = argmax_n.  scratch: gemm_argmax_scratch bytes.
 int gemm_argmax(const OperandView& a, const OperandView& b, int M, int N, int Kcat, const float* bias, float* logits,
                 long long ldc, long long* out, long long out_stride, long long* next, void* scratch, cudaStream_t st) {
   GemmCoords gc{M, N, Kcat, 0, 0, 0, 0};
   if (b.kp) { gc.b_kp = b.kp; gc.b_terms = split_b_terms(b.terms); }
-  const int nparts = cdiv(N, 256) * 2;
+  // Tile width (A/B knob PVCR_ARGMAX_BN=192): Vc = 23 000 gives 90 tiles of 256 columns (61 % of the SMs) or 120 of 192;
+  // measured, the narrower tiles are SLOWER inside the decode loop (3.04 -> 3.17 ms per batch): the SMs the 256-wide
+  // tiling leaves free are what the overlapped query / attention / context half of the next step runs on.
+  static const int bn_knob = getenv("PVCR_ARGMAX_BN") ? atoi(getenv("PVCR_ARGMAX_BN")) : 0;
+  const int bn = bn_knob == 192 ? 192 : 256;
+  const int nparts = cdiv(N, bn) * 2;
   EpiArgmax epi{};
   epi.C = logits; epi.ldc = ldc; epi.bias = bias; epi.M = M; epi.N = N; epi.nparts = nparts;
   epi.pmax = reinterpret_cast<float*>(scratch);
   epi.pidx = reinterpret_cast<int*>(epi.pmax + (size_t)M * nparts);
-  PVCR_TRY((launch_gemm_tn_persistent<256, 4, EpiArgmax>(a, b, gc, 1, epi, st)));
+  if (bn == 192) PVCR_TRY((launch_gemm_tn_persistent<192, 4, EpiArgmax>(a, b, gc, 1, epi, st)));
+  else PVCR_TRY((launch_gemm_tn_persistent<256, 4, EpiArgmax>(a, b, gc, 1, epi, st)));
   { LaunchScope ls_(KC_LOSS, st);
     argmax_parts_kernel<<<cdiv(M, 4), 128, 0, st>>>(epi.pmax, epi.pidx, M, nparts, out, out_stride, next);
   }

@@ -27,6 +27,9 @@ struct GemmSmem {
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
 };
 
+// TMEM allocations are powers of two >= 32 columns
+__host__ __device__ constexpr int tmem_cols_pow2(int c) { return c <= 32 ? 32 : (c <= 64 ? 64 : (c <= 128 ? 128 : (c <= 256 ? 256 : 512))); }
+
 struct GemmCoords {
   int M, N, K;          // K = concatenated (all split planes), multiple of GEMM_BK
   int a_z0, a_zmul;     // slab coordinate of A for grid z:  a_z0 + z * a_zmul
@@ -189,7 +192,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_alloc(tmem_slot, tmem_cols_pow2(2 * BN));
     tmem_relinquish();
   }
   tc_fence_before();
@@ -293,7 +296,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, tmem_cols_pow2(2 * BN));
   }
 }
 
