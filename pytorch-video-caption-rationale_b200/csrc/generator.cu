@@ -33,7 +33,7 @@ static LstmSeqArgs dir_seq(const PvcrDims& d, const PvcrGenParams& p, const GenW
   s.h = r.h; s.h_ts = H; s.h_ld = (long long)N * H;
   s.hp = r.hp.ptr; s.hp_ts = r.hp.ld; s.hp_ld = (long long)N * r.hp.ld;
   s.si = r.i; s.sf = r.f; s.sg = r.g; s.so = r.o; s.sc = r.c;
-  s.sync = w.sync;
+  s.sync = w.sync + (size_t)k * 32 * 160;       // each direction its own group counters (the two may run side by side)
   return s;
 }
 
@@ -62,8 +62,8 @@ static void carve_gen(Arena& a, const PvcrDims& d, GenWs& w) {
   w.dc = a.alloc<float>((size_t)B * H);
   w.dhf = a.alloc<float>(BN * H); w.dhb = a.alloc<float>(BN * H);
   w.dlogit = a.alloc<float>(BN * 2);
-  w.sync = a.alloc<unsigned>(32 * 160);
-  w.xch = a.alloc<bf16>((size_t)2 * B * 4 * H);
+  w.sync = a.alloc<unsigned>(2 * 32 * 160);
+  w.xch = a.alloc<bf16>((size_t)2 * 2 * B * 4 * H);      // [direction][2][B][4H]
 }
 
 static size_t gen_scratch(const PvcrDims& d) {
@@ -104,7 +104,20 @@ int generator_fwd(const PvcrDims& d, const PvcrGenParams& p, const float* vid, c
   PVCR_CUDA_CHECK(cudaMemcpyAsync(w.bias_cat + H4, p.b_ih_r, sizeof(float) * H4, cudaMemcpyDeviceToDevice, st));
   PVCR_TRY(stage(vid, V, BN, V, w.x_a, 0, nullptr, NO_DROPOUT, st));
   PVCR_TRY(gemm_planes(w.x_a.view(), w.wih.view(), BN, H8, (int)w.x_a.ld, w.gi, H8, w.bias_cat, 0, st));
-  for (int k = 0; k < 2; ++k) {
+  // The two directions are independent: when both fit the SMs with 32-video groups (2 x 64 CTAs at B = 128, H = 512)
+  // the reverse sweep runs on a side lane next to the forward one instead of behind it.
+  bool paired = false;
+  if (lstm_persist_pair_ok(B, H, d.nsplit, w.dir[0].hp.Kp) && side_site(4)) {
+    cudaStream_t lane = st;
+    PVCR_TRY(side_fork(st, &lane, 0));
+    if (lane != st) {
+      PVCR_TRY(lstm_persist_fwd(dir_seq(d, p, w, 0), st, true));
+      PVCR_TRY(lstm_persist_fwd(dir_seq(d, p, w, 1), lane, true));
+      PVCR_TRY(side_join_lane(st, 0));
+      paired = true;
+    }
+  }
+  for (int k = 0; k < 2 && !paired; ++k) {
     DirBuf& r = w.dir[k];
     if (r.hp.Kp != H) PVCR_TRY(fill_zero(r.hp.ptr, sizeof(bf16) * (size_t)BN * r.hp.ld, st));
     const float* b_hh = k ? p.b_hh_r : p.b_hh;
@@ -162,14 +175,32 @@ int generator_bwd(const PvcrDims& d, const PvcrGenParams& p, const float* vid, f
   gb.dhf = w.dhf; gb.dhb = w.dhb; gb.dw = g.lin_w; gb.dbias = g.lin_b; gb.scratch = w.dlogit;
   PVCR_TRY(gumbel_select_bwd(gb, st));
   if (w.da_a.Kp != H4) PVCR_TRY(fill_zero(w.da_a.ptr, sizeof(bf16) * (size_t)B * w.da_a.ld, st));
+  // Pairing the two BACKWARD sweeps the same way is measured slower (cfg3: 655 us for the pair vs 2 x 314 us one after the
+  // other): a 32-video group's gate gradients (128 KB) do not fit beside the W_hh^T slice, so they come back in two
+  // serialised 64 KB passes per step.  Off unless asked for.
+  static const bool pair_bwd = getenv("PVCR_LSTM_PAIR_BWD") != nullptr;
+  bool paired = false;
+  if (pair_bwd && lstm_persist_pair_ok(B, H, ns, w.dir[0].hp.Kp) && side_site(4)) {
+    for (int k = 0; k < 2; ++k) PVCR_TRY(prep_weight_T(k ? p.w_hh_r : p.w_hh, H, H4, H, w.dir[k].whhT, 0, 1, st));
+    cudaStream_t lane = st;
+    PVCR_TRY(side_fork(st, &lane, 0));
+    if (lane != st) {
+      for (int k = 0; k < 2; ++k)
+        PVCR_TRY(lstm_persist_bwd(dir_seq(d, p, w, k), w.dir[k].whhT, k ? w.dhb : w.dhf, H, (long long)N * H,
+                                  w.dgi + (long long)k * H4, H8, (long long)N * H8, w.xch + (size_t)k * 2 * B * H4,
+                                  k ? lane : st, true));
+      PVCR_TRY(side_join_lane(st, 0));
+      paired = true;
+    }
+  }
   for (int k = 0; k < 2; ++k) {
     DirBuf& r = w.dir[k];
-    PVCR_TRY(prep_weight_T(k ? p.w_hh_r : p.w_hh, H, H4, H, r.whhT, 0, 1, st));
+    if (!paired) PVCR_TRY(prep_weight_T(k ? p.w_hh_r : p.w_hh, H, H4, H, r.whhT, 0, 1, st));
     PVCR_TRY(fill_zero(w.dh_carry, sizeof(float) * (size_t)B * H, st));
     PVCR_TRY(fill_zero(w.dc, sizeof(float) * (size_t)B * H, st));
     const float* dh_ext = k ? w.dhb : w.dhf;
-    const bool persist = lstm_persist_eligible(B, H, ns, r.hp.Kp);
-    if (persist)
+    const bool persist = paired || lstm_persist_eligible(B, H, ns, r.hp.Kp);
+    if (persist && !paired)
       PVCR_TRY(lstm_persist_bwd(dir_seq(d, p, w, k), r.whhT, dh_ext, H, (long long)N * H, w.dgi + (long long)k * H4, H8,
                                 (long long)N * H8, w.xch, st));
     for (int s = N - 1; s >= 0 && !persist; --s) {

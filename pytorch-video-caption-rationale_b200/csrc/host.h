@@ -221,9 +221,11 @@ struct LstmSeqArgs {
   unsigned* sync;
 };
 bool lstm_persist_eligible(int B, int H, int nsplit, int Hp);
-int lstm_persist_fwd(const LstmSeqArgs& s, cudaStream_t st);
+bool lstm_persist_pair_ok(int B, int H, int nsplit, int Hp);      // both directions fit the SMs side by side (32-video groups)
+int lstm_persist_fwd(const LstmSeqArgs& s, cudaStream_t st, bool wide = false);
 int lstm_persist_bwd(const LstmSeqArgs& s, const Planes& whhT, const float* dh_ext, long long dh_ext_ts,
-                     long long dh_ext_ld, float* da, long long da_ts, long long da_ld, bf16* xch, cudaStream_t st);
+                     long long dh_ext_ld, float* da, long long da_ts, long long da_ld, bf16* xch, cudaStream_t st,
+                     bool wide = false);
 
 // ---- persistent attention decoder (dec_persist.cu) ---------------------------------------------------------
 struct DecPersistFwd {

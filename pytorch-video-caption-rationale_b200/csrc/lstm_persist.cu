@@ -12,6 +12,7 @@
 namespace pvcr {
 
 constexpr int LSTM_ITEMS = 4;
+constexpr int LSTM_XB = 16;      // videos per exchange pass of the backward kernel
 
 struct LstmPersistFwd {
   int T, B, H, bs, C, u, rev;
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) lstm_persist_bwd_kernel(co
   const int H = p.H, u = p.u, bs = p.bs, K = 4 * H, KB = K >> 6;
   uint8_t* sW = smem;
   uint8_t* sX = sW + (size_t)KB * u * 128;
-  float* sR = reinterpret_cast<float*>(sX + (size_t)KB * bs * 128);     // [8 warps][u][bs] K-slice partial products
+  float* sR = reinterpret_cast<float*>(sX + (size_t)KB * LSTM_XB * 128);     // [8 warps][u][bs] K-slice partial products
   const int nwarps = PERSIST_THREADS / 32;
   uint64_t* bar_x = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sR + (size_t)nwarps * u * bs) + 15) & ~uintptr_t(7));
   uint32_t phase_x = 0;
@@ -219,21 +220,24 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) lstm_persist_bwd_kernel(co
     if (s > 0) {
       group_arrive(ctr);
       ++arrivals;
-      if (TMA) {      // one thread fetches the group's 64 KB of gate gradients with bulk-tensor copies (persist.cuh)
+      // the group's gate gradients come back 16 videos at a time (64 KB at H = 512): one pass for the 16-video groups,
+      // two for the 32-video groups of the paired-direction launch (W_hh^T slice + 32 videos would not fit shared memory)
+      for (int hb = 0; hb < bs / LSTM_XB; ++hb) {
+      if (TMA) {      // one thread fetches the 64 KB with bulk-tensor copies (persist.cuh)
         if (tid == 0) {
-          spin_until(ctr, (unsigned)p.C * arrivals);
-          tma_fetch_operand(sX, bs, 0, &tmX, bar_x, 0, KB, b0, s & 1);
+          if (hb == 0) spin_until(ctr, (unsigned)p.C * arrivals);
+          tma_fetch_operand(sX, LSTM_XB, 0, &tmX, bar_x, 0, KB, b0 + hb * LSTM_XB, s & 1);
         }
         mbar_wait(bar_x, phase_x);
         phase_x ^= 1;
       } else {
-      group_wait(ctr, (unsigned)p.C * arrivals);
-      load_operand_rows_async(sX, bs, 0, xw, K, b0, bs, p.B, K);
+      if (hb == 0) group_wait(ctr, (unsigned)p.C * arrivals);
+      load_operand_rows_async(sX, LSTM_XB, 0, xw, K, b0 + hb * LSTM_XB, LSTM_XB, p.B, K);
       cp_async_commit();
       cp_async_wait<0>();
       __syncthreads();
       }
-      // dh carry [u, bs] = W_hh^T slice [u, 4H] x da^T: mma.sync m16n8k16, k-steps dealt over the 8 warps
+      // dh carry [u, 16] = W_hh^T slice [u, 4H] x da^T: mma.sync m16n8k16, k-steps dealt over the 8 warps
       float acc[2][2][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
@@ -245,14 +249,14 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) lstm_persist_bwd_kernel(co
         uint32_t a0[4], a1[4], bq[4];
         load_a_frag(aW, u, 0, ks << 4, a0);
         load_a_frag(aW, u, 16, ks << 4, a1);
-        load_b_frag2(aX, bs, 0, ks << 4, bq);
+        load_b_frag2(aX, LSTM_XB, 0, ks << 4, bq);
         mma_bf16_16816(acc[0][0], a0, bq[0], bq[1]);
         mma_bf16_16816(acc[0][1], a0, bq[2], bq[3]);
         mma_bf16_16816(acc[1][0], a1, bq[0], bq[1]);
         mma_bf16_16816(acc[1][1], a1, bq[2], bq[3]);
       }
       {
-        float* r = sR + (size_t)warp * u * bs;
+        float* r = sR + (size_t)warp * u * bs + hb * LSTM_XB;
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -261,6 +265,8 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) lstm_persist_bwd_kernel(co
             r[row * bs + col] = acc[mt][nt][0]; r[row * bs + col + 1] = acc[mt][nt][1];
             r[(row + 8) * bs + col] = acc[mt][nt][2]; r[(row + 8) * bs + col + 1] = acc[mt][nt][3];
           }
+      }
+      if (hb + 1 < bs / LSTM_XB) __syncthreads();       // every warp is done with sX before the next pass refills it
       }
       __syncthreads();
 #pragma unroll
@@ -291,14 +297,16 @@ static int lstm_num_sms() {
 }
 
 struct LstmPlan { int bs, C, u, G; size_t smem_f, smem_b; };
-static bool plan_lstm(int B, int H, LstmPlan& pl) {
+// wide: groups of 32 videos instead of 16 -- half the CTAs per direction, so that the two directions of a bidirectional
+// LSTM can run side by side (lstm_persist_pair_ok)
+static bool plan_lstm(int B, int H, LstmPlan& pl, bool wide = false) {
   if (H % 64 != 0 || H % 32 != 0) return false;
-  pl.u = 32; pl.C = H / 32; pl.bs = 16; pl.G = (B + 15) / 16;
+  pl.u = 32; pl.C = H / 32; pl.bs = wide ? 32 : 16; pl.G = (B + pl.bs - 1) / pl.bs;
   if ((long long)pl.G * pl.C > lstm_num_sms()) return false;
   if (pl.u * pl.bs > LSTM_ITEMS * PERSIST_THREADS) return false;
   const size_t KBf = H / 64, KBb = 4 * H / 64;
   pl.smem_f = KBf * 128 * 128 + KBf * pl.bs * 128 + (size_t)pl.bs * 129 * 4 + 64 + 1024;
-  pl.smem_b = KBb * pl.u * 128 + KBb * pl.bs * 128 + (size_t)(PERSIST_THREADS / 32) * pl.u * pl.bs * 4 + 64 + 1024;
+  pl.smem_b = KBb * pl.u * 128 + KBb * LSTM_XB * 128 + (size_t)(PERSIST_THREADS / 32) * pl.u * pl.bs * 4 + 64 + 1024;
   return pl.smem_f <= 227 * 1024 && pl.smem_b <= 227 * 1024;
 }
 
@@ -306,6 +314,12 @@ bool lstm_persist_eligible(int B, int H, int nsplit, int Hp) {
   LstmPlan pl;
   static const bool off = getenv("PVCR_NO_PERSIST_LSTM") != nullptr;
   return !off && nsplit == 1 && Hp == H && plan_lstm(B, H, pl);
+}
+// both directions co-resident: 2 x (groups of 32 videos x H/32 CTAs) fit the SMs
+bool lstm_persist_pair_ok(int B, int H, int nsplit, int Hp) {
+  LstmPlan pl;
+  static const bool off = getenv("PVCR_NO_LSTM_PAIR") != nullptr;      // A/B knob
+  return !off && lstm_persist_eligible(B, H, nsplit, Hp) && plan_lstm(B, H, pl, true) && 2 * pl.G * pl.C <= lstm_num_sms();
 }
 
 static int lstm_coop(const void* kern, int grid, size_t smem, void** args, cudaStream_t st, int cls, const char* what) {
@@ -318,9 +332,9 @@ static int lstm_coop(const void* kern, int grid, size_t smem, void** args, cudaS
   return PVCR_OK;
 }
 
-int lstm_persist_fwd(const LstmSeqArgs& s, cudaStream_t st) {
+int lstm_persist_fwd(const LstmSeqArgs& s, cudaStream_t st, bool wide) {
   LstmPlan pl;
-  PVCR_REQUIRE(plan_lstm(s.B, s.H, pl), "lstm_persist_fwd: shape B=%d H=%d not supported", s.B, s.H);
+  PVCR_REQUIRE(plan_lstm(s.B, s.H, pl, wide), "lstm_persist_fwd: shape B=%d H=%d not supported", s.B, s.H);
   LstmPersistFwd p{};
   p.T = s.T; p.B = s.B; p.H = s.H; p.bs = pl.bs; p.C = pl.C; p.u = pl.u; p.rev = s.rev;
   p.whh = s.whh.ptr; p.whh_ld = s.whh.ld; p.b_hh = s.b_hh;
@@ -335,9 +349,9 @@ int lstm_persist_fwd(const LstmSeqArgs& s, cudaStream_t st) {
 }
 
 int lstm_persist_bwd(const LstmSeqArgs& s, const Planes& whhT, const float* dh_ext, long long dh_ext_ts,
-                     long long dh_ext_ld, float* da, long long da_ts, long long da_ld, bf16* xch, cudaStream_t st) {
+                     long long dh_ext_ld, float* da, long long da_ts, long long da_ld, bf16* xch, cudaStream_t st, bool wide) {
   LstmPlan pl;
-  PVCR_REQUIRE(plan_lstm(s.B, s.H, pl), "lstm_persist_bwd: shape B=%d H=%d not supported", s.B, s.H);
+  PVCR_REQUIRE(plan_lstm(s.B, s.H, pl, wide), "lstm_persist_bwd: shape B=%d H=%d not supported", s.B, s.H);
   LstmPersistBwd p{};
   p.T = s.T; p.B = s.B; p.H = s.H; p.bs = pl.bs; p.C = pl.C; p.u = pl.u; p.rev = s.rev;
   p.whhT = whhT.ptr; p.whhT_ld = whhT.ld;
@@ -350,7 +364,7 @@ int lstm_persist_bwd(const LstmSeqArgs& s, const Planes& whhT, const float* dh_e
   // (0.295 vs 0.284 ms per direction), unlike the GRU / decoder backward sweeps -- off unless asked for
   static const bool no_tma = getenv("PVCR_LSTM_BWD_TMA") == nullptr || getenv("PVCR_NO_TMA_XCHG") != nullptr;
   CUtensorMap tmX;         // exchange buffer [2][B][4H] as (k, video, parity)
-  PVCR_TRY(make_tensor_map(&tmX, OperandView{p.xch, (long long)4 * p.H, (long long)p.B * 4 * p.H, p.B, 2}, 4 * p.H, pl.bs));
+  PVCR_TRY(make_tensor_map(&tmX, OperandView{p.xch, (long long)4 * p.H, (long long)p.B * 4 * p.H, p.B, 2}, 4 * p.H, LSTM_XB));
   void* args[] = {&p, &tmX};
   const void* kern = no_tma ? (const void*)lstm_persist_bwd_kernel<false> : (const void*)lstm_persist_bwd_kernel<true>;
   return lstm_coop(kern, pl.G * pl.C, pl.smem_b, args, st, KC_GRU_BWD, "lstm_persist_bwd");
