@@ -138,3 +138,77 @@ def test_graphed_beam_search_equals_eager():
     ids_g, scores_g = g(vid)
     torch.cuda.synchronize()
     assert torch.equal(ids, ids_g) and torch.equal(scores, scores_g)
+
+
+def test_decode_plan_reuses_and_invalidates():
+    """The weights prepared for decoding (split planes + the word table W_e Emb[w] + b_ih) are kept between calls:
+    a second call on the same parameters skips the preparation and must return the same bits; a parameter update that
+    autograd can see (in-place op -> version counter) must be noticed; ids-only decoding returns the same ids."""
+    from pvcr_b200.model import S2VTAttModel
+    d, params, _, (B, N, V, H, E, L, Vc) = load_case("s2vtatt_mid")
+    m = to_cuda(S2VTAttModel(FixtureGlove(Vc, E), 0.0, H, V, L), params).eval()
+    vid = torch.from_numpy(d["vid"]).cuda()
+    ids0, logits0 = m.greedy(vid)
+    plan = m._plan("greedy")
+    key0 = plan.key
+    assert key0 is not None
+    ids1, logits1 = m.greedy(vid)                       # prepared weights reused (PVCR_DECODE_REUSE_PREPARED)
+    assert plan.key == key0
+    # (split-K partial sums are added atomically: the logits of two runs may differ in their last bits)
+    assert torch.equal(ids0, ids1) and relerr(logits1.cpu().numpy(), logits0.cpu().numpy()) < 1e-6
+    assert np.array_equal(ids1.cpu().numpy(), d["greedy_ids"])
+    ids2, none = m.greedy(vid, return_logits=False)
+    assert none is None and torch.equal(ids2, ids0)
+    # another batch on the same prepared weights: the per-batch half of the workspace must not leak between calls
+    vid_b = torch.flip(vid, dims=[0]).contiguous()
+    ids_b, logits_b = m.greedy(vid_b)
+    assert torch.equal(ids_b, torch.flip(ids0, dims=[0]))
+    assert relerr(logits_b.cpu().numpy(), np.flip(d["greedy_logits"], axis=0)) < 2e-5
+    # an in-place parameter update changes the fingerprint: the table and planes are rebuilt
+    with torch.no_grad():
+        m.decoder.embedding.weight.mul_(0.5)
+    ids3, logits3 = m.greedy(vid)
+    assert plan.key != key0
+    fresh = to_cuda(S2VTAttModel(FixtureGlove(Vc, E), 0.0, H, V, L), params).eval()
+    with torch.no_grad():
+        fresh.decoder.embedding.weight.mul_(0.5)
+    ids4, logits4 = fresh.greedy(vid)
+    assert torch.equal(ids3, ids4) and relerr(logits3.cpu().numpy(), logits4.cpu().numpy()) < 1e-6
+    assert relerr(logits3.cpu().numpy(), logits0.cpu().numpy()) > 1e-3
+    # train() drops the cache
+    m.train()
+    assert plan.key is None
+
+
+def test_greedy_ex_reuse_flag_c_abi():
+    """pvcr_s2vtatt_greedy_ex through ctypes: prepare + run, then run with PVCR_DECODE_REUSE_PREPARED on the same
+    workspace -> identical ids and logits; decode from given encoder outputs agrees with the model's decode()."""
+    import ctypes
+    from pvcr_b200 import _lib, functional as F_
+    from pvcr_b200.model import S2VTAttModel
+    d, params, _, (B, N, V, H, E, L, Vc) = load_case("s2vtatt_tiny")
+    m = to_cuda(S2VTAttModel(FixtureGlove(Vc, E), 0.0, H, V, L), params).eval()
+    vid = torch.from_numpy(d["vid"]).cuda()
+    Lb = _lib.lib()
+    tensors = {f: p.detach().contiguous() for f, p in zip(F_.ATT_SEQ_FIELDS, m._seq_params())}
+    lin = m.decoder.pred_linear[1]
+    tensors["out_w"], tensors["out_b"] = lin.weight.detach().contiguous(), lin.bias.detach().contiguous()
+    ps = F_._fill_struct(_lib.PvcrS2vtAttParams(), _lib.ATT_PARAM_FIELDS, tensors)
+    dims = F_.make_dims(B, N, V, H, E, L, Vc, 3, 0.0, 0)
+    ws = torch.empty(int(Lb.pvcr_s2vtatt_greedy_workspace(ctypes.byref(dims))), dtype=torch.uint8, device="cuda")
+    outs = []
+    for flags in (0, 1, 1):
+        ids = torch.empty((B, L), dtype=torch.int64, device="cuda")
+        logits = torch.empty((B, L, Vc), dtype=torch.float32, device="cuda")
+        _lib.check(Lb.pvcr_s2vtatt_greedy_ex(ctypes.byref(dims), ctypes.byref(ps), _lib.ptr(vid), None, None, None,
+                                             m.decoder.sos_id, _lib.ptr(ids), _lib.ptr(logits), None, _lib.ptr(ws),
+                                             ws.numel(), flags, _lib.stream_ptr()), "greedy_ex")
+        outs.append((ids, logits))
+    torch.cuda.synchronize()
+    assert np.array_equal(outs[0][0].cpu().numpy(), d["greedy_ids"])
+    for ids, logits in outs[1:]:
+        assert torch.equal(ids, outs[0][0]) and relerr(logits.cpu().numpy(), outs[0][1].cpu().numpy()) < 1e-6
+    # both inputs at once / neither is an argument error, not a crash
+    rc = Lb.pvcr_s2vtatt_greedy_ex(ctypes.byref(dims), ctypes.byref(ps), None, None, None, None, 0, _lib.ptr(outs[0][0]),
+                                   None, None, _lib.ptr(ws), ws.numel(), 0, _lib.stream_ptr())
+    assert rc != 0
