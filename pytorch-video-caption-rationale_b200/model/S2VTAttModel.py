@@ -243,6 +243,12 @@ class S2VTAttModel(nn.Module):
             plans[which] = F_.DecodePlan()
         return plans[which]
 
+    def __getstate__(self):
+        # the prepared decode workspaces (hundreds of MB of derived data) are neither pickled nor deep-copied
+        state = self.__dict__.copy()
+        state.pop("_decode_plans", None)
+        return state
+
     def invalidate_decode_cache(self):
         """Forget the weights prepared for decoding (needed only after parameter writes autograd cannot see, e.g. through
         ``.data``; optimizer steps, ``load_state_dict`` and ``train()`` are noticed)."""

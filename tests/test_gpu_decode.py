@@ -212,3 +212,72 @@ def test_greedy_ex_reuse_flag_c_abi():
     rc = Lb.pvcr_s2vtatt_greedy_ex(ctypes.byref(dims), ctypes.byref(ps), None, None, None, None, 0, _lib.ptr(outs[0][0]),
                                    None, None, _lib.ptr(ws), ws.numel(), 0, _lib.stream_ptr())
     assert rc != 0
+
+
+def _decided(ids, ids_ref, logits_ref, tol=1e-6):
+    """ids equal to the float64 oracle's wherever the oracle is decided: a video may leave the reference sequence only at a
+    step whose float64 top-2 margin is below `tol` (everything after that step is a different, equally valid, decode)."""
+    for b in range(ids.shape[0]):
+        for l in range(ids.shape[1]):
+            if ids[b, l] != ids_ref[b, l]:
+                top2 = np.sort(logits_ref[b, l])[-2:]
+                assert top2[1] - top2[0] < tol, (b, l, ids[b, l], ids_ref[b, l], top2)
+                break
+
+
+@pytest.mark.parametrize("B,H", [(1, 64), (3, 128), (33, 128), (70, 256), (130, 64)])
+def test_greedy_batch_and_width_sweep_vs_oracle(B, H):
+    """The decode path's persistent fp32 encoder kernel (gru_f32_persist.cu) serves groups of 32 videos with H/16 CTAs each:
+    batches that are not multiples of 32 (tail group partly empty), a single video, and B = 130 at H = 64 (5 groups);
+    ids equal to the float64 oracle's, logits 2e-5."""
+    from oracle import captioning_oracle as O
+    from oracle import workloads as W
+    from pvcr_b200.model import S2VTAttModel
+    N, V, E, L, Vc = 12, 96, 40, 6, 300
+    p = W.s2vtatt_params(V, H, E, Vc, 300 + B)
+    vid, _, _ = W.make_batch(B, N, V, L, Vc, 400 + B)
+    ids_o, logits_o, alphas_o = O.s2vtatt_greedy({k: v.astype(np.float64) for k, v in p.items()}, vid.astype(np.float64),
+                                                 Vc - 4, L)
+    m = to_cuda(S2VTAttModel(FixtureGlove(Vc, E), 0.0, H, V, L), p).eval()
+    ids, logits = m.greedy(torch.from_numpy(vid).cuda())
+    _decided(ids.cpu().numpy(), ids_o, logits_o)
+    if np.array_equal(ids.cpu().numpy(), ids_o):
+        assert relerr(logits.double().cpu().numpy(), logits_o) < 2e-5
+        assert np.abs(m.last_alphas.double().cpu().numpy() - alphas_o).max() < 1e-5
+
+
+def test_greedy_bf16x2_compact_planes():
+    """nsplit = 2 through the decode entry point: the vocabulary weight is stored as two compact planes (terms 0, 1) and
+    the GEMM producer maps the three virtual K planes {0,1,0} to them.  fp32-level logits (3 products: 1e-4)."""
+    from oracle import captioning_oracle as O
+    from oracle import workloads as W
+    from pvcr_b200 import functional as F_
+    from pvcr_b200.model import S2VTAttModel
+    B, N, V, H, E, L, Vc = 9, 10, 64, 128, 40, 5, 700
+    p = W.s2vtatt_params(V, H, E, Vc, 77)
+    vid, _, _ = W.make_batch(B, N, V, L, Vc, 78)
+    ids_o, logits_o, _ = O.s2vtatt_greedy({k: v.astype(np.float64) for k, v in p.items()}, vid.astype(np.float64), Vc - 4, L)
+    m = to_cuda(S2VTAttModel(FixtureGlove(Vc, E), 0.0, H, V, L), p).eval()
+    lin = m.decoder.pred_linear[1]
+    with torch.no_grad():
+        ids, logits, _ = F_.s2vtatt_greedy(torch.from_numpy(vid).cuda(), None, m.decoder.sos_id, L, m._seq_params(), lin.weight,
+                                           lin.bias, nsplit=2)
+    _decided(ids.cpu().numpy(), ids_o, logits_o, tol=1e-3)
+    if np.array_equal(ids.cpu().numpy(), ids_o):
+        assert relerr(logits.double().cpu().numpy(), logits_o) < 1e-4
+
+
+def test_stepwise_encoder_fallback_agrees():
+    """The step-wise tensor-core encoder (bf16x3) that larger batches fall back to and the fp32 persistent kernel give the
+    same token ids (separate processes: the knob is read once)."""
+    import os, subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    outs = []
+    for env in ({}, {"PVCR_NO_F32_GRU": "1"}):
+        r = subprocess.run([sys.executable, os.path.join(here, "gpu_knob_f32gru.py")], env=dict(os.environ, **env),
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        line = [l for l in r.stdout.splitlines() if l.startswith("IDS")][0].split()
+        outs.append(line)
+    assert outs[0][1] == outs[1][1], outs
+    assert abs(float(outs[0][2]) - float(outs[1][2])) < 1e-5 * float(outs[0][2])
