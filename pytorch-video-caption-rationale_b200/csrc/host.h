@@ -176,6 +176,9 @@ struct GruSeq {
   unsigned* sync;                          // >= ceil(B/16) counters for the persistent kernels (null: per-step path)
 };
 int gru_seq_fwd(const GruSeq& s, cudaStream_t st);
+// cluster / distributed-shared-memory variant of the persistent forward sweep (gru_cluster.cu)
+bool gru_cluster_eligible(const GruSeq& s);
+int gru_cluster_fwd(const GruSeq& s, cudaStream_t st);
 
 // persistent GRU forward sweep in plain fp32 arithmetic (gru_f32_persist.cu): decoding, where operands may not be rounded
 struct GruF32Fwd {

@@ -120,6 +120,7 @@ int grad_x_fwdw(Arena& a, const float* dy, long long lddy, int R, int N, const P
 }
 
 int gru_seq_fwd(const GruSeq& s, cudaStream_t st) {
+  if (gru_persist_eligible(s) && gru_cluster_eligible(s)) return gru_cluster_fwd(s, st);
   if (gru_persist_eligible(s)) return gru_persist_fwd(s, st);
   const int H3 = 3 * s.H;
   for (int t = 0; t < s.T; ++t) {
