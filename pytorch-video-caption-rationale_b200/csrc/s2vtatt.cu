@@ -570,7 +570,7 @@ int s2vtatt_decode_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const long
 // ---- fixed-length greedy decoding (eval branch, model/S2VTAttModel.py:172-191) ---------------------------------
 struct GreedyWs {
   AttWs w;
-  Planes wv, emb_all;
+  Planes wv, emb_all, wcat_c, wc_c;      // weights of the per-step products: each split term stored once (compact planes)
   float *logits_step, *hs, *emb_table;
   long long* words;
   void* argmax_scratch;
@@ -578,6 +578,8 @@ struct GreedyWs {
 static void carve_greedy(Arena& a, const PvcrDims& d, GreedyWs& g) {
   carve(a, d, 0, g.w);
   g.wv = alloc_planes_compact(a, d.Vc, d.H, d.nsplit);           // each term of W_v once: the planes stay L2-resident between steps
+  g.wcat_c = alloc_planes_compact(a, 4 * d.H, d.H, d.nsplit);
+  g.wc_c = alloc_planes_compact(a, 3 * d.H, d.H, d.nsplit);
   g.emb_all = alloc_planes(a, d.Vc, d.E, d.nsplit);              // the whole embedding table as an A-role operand (prepare only)
   g.emb_table = a.alloc<float>((size_t)d.Vc * 3 * d.H);           // W_e Emb[w] + b_ih for EVERY word w
   g.logits_step = a.alloc<float>((size_t)d.B * round_up(d.Vc, 4));
@@ -617,9 +619,9 @@ int s2vtatt_greedy_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const flo
   PVCR_TRY(prep_weight(p.enc_w_hh, H, H3, H, w.whh_enc, st));
   }
   PVCR_TRY(prep_weight(p.att_wk, H, H, H, w.wk, st));
-  PVCR_TRY(prep_weight(p.att_wq, H, H, H, w.wcat, st, 0));
-  PVCR_TRY(prep_weight(p.dec_w_hh, H, H3, H, w.wcat, st, H));
-  PVCR_TRY(prep_weight(p.dec_w_ih, H + E, H3, H, w.wc, st));
+  PVCR_TRY(prep_weight(p.att_wq, H, H, H, gw.wcat_c, st, 0));
+  PVCR_TRY(prep_weight(p.dec_w_hh, H, H3, H, gw.wcat_c, st, H));
+  PVCR_TRY(prep_weight(p.dec_w_ih, H + E, H3, H, gw.wc_c, st));
   PVCR_TRY(prep_weight(p.dec_w_ih + H, H + E, H3, E, w.we, st));
   PVCR_TRY(prep_weight(p.out_w, H, Vc, H, gw.wv, st));
   if (gw.emb_all.Kp != E) PVCR_TRY(fill_zero(gw.emb_all.ptr, sizeof(bf16) * (size_t)Vc * gw.emb_all.ld, st));
@@ -666,7 +668,7 @@ int s2vtatt_greedy_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const flo
     OperandView hprev_a = (i == 0)
         ? OperandView{const_cast<bf16*>(h0.a), h0.a_ld, 0, B, 1}
         : OperandView{w.hs_a.ptr + (long long)(i - 1) * w.hs_a.ld, (long long)L * w.hs_a.ld, 0, B, 1};
-    PVCR_TRY(gemm_planes(hprev_a, w.wcat.view(), B, H4, (int)w.wcat.ld, w.g1_all, H4, nullptr, 0, s));
+    PVCR_TRY(gemm_planes(hprev_a, gw.wcat_c.view(), B, H4, (int)w.hs_a.ld, w.g1_all, H4, nullptr, 0, s));
     AttnFwdArgs at{};
     at.B = B; at.N = N; at.H = H;
     at.q = w.g1_all; at.q_ld = H4; at.pk = w.pk; at.enc = w.enc; at.v = p.att_v;
@@ -674,7 +676,7 @@ int s2vtatt_greedy_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const flo
     at.ctx = w.ctx_all; at.ctx_ld = H;
     at.ctx_planes = w.ctx_a.ptr; at.ctx_planes_ld = w.ctx_a.ld; at.Hp = w.ctx_a.Kp; at.nsplit = d.nsplit;
     PVCR_TRY(attn_fwd(at, s));
-    PVCR_TRY(gemm_planes(w.ctx_a.view(), w.wc.view(), B, H3, (int)w.ctx_a.ld, w.g2, H3, nullptr, 0, s));
+    PVCR_TRY(gemm_planes(w.ctx_a.view(), gw.wc_c.view(), B, H3, (int)w.ctx_a.ld, w.g2, H3, nullptr, 0, s));
     return PVCR_OK;
   };
   static const bool overlap_off = getenv("PVCR_NO_DECODE_OVERLAP") != nullptr;       // A/B knob
