@@ -9,8 +9,8 @@
 //   * W_hh rows of 16 hidden units (48 rows x H fp32, padded pitch) resident in shared memory per CTA,
 //   * the batch cut into groups of 32 videos served by H/16 CTAs; per step the group's h_{t-1} (32 x H fp32) comes back
 //     from L2 into shared memory (cp.async) behind the group's arrive counter (persist.cuh),
-//   * thread = (K half, one hidden unit, four videos): all three gates of its unit, so the GRU cell is applied in
-//     registers after one shared-memory hand-over between the two K halves,
+//   * the product as 6 x 8 register tiles (3 gates of 2 units x 8 videos per thread, the K range dealt over the 8 warps),
+//     the 8 partial sums combined through shared memory, then one thread per (unit, video) pair applies the GRU cell,
 //   * h_t written as fp32 rows (the encoder output); the caller casts them to the bf16 split planes the following GEMMs
 //     consume in one pass after the sweep.
 // No rounding of operands anywhere: results differ from torch's fp32 GRU by summation order only.
@@ -24,22 +24,26 @@ namespace pvcr {
 
 constexpr int GF_U = 16;          // hidden units per CTA
 constexpr int GF_BG = 32;         // videos per group
-constexpr int GF_THREADS = 256;   // 2 K-halves x 16 units x 8 video quads
+constexpr int GF_THREADS = 256;   // 8 warps = 8 K slices; lane = (unit pair, video quad)
 constexpr int GF_OP = GF_U + 4;   // pitch of the output staging rows
 
-// Thread (ks, jj, vq): K-half ks, hidden unit jj, videos vq, vq+8, vq+16, vq+24 of the group -- a 3 gates x 4 videos
-// register tile, 7 shared-memory loads (16 B) per 48 FMAs.  Row pitch H + 4 floats for both W and h: the 8 lanes of a
-// quarter warp (consecutive videos / 4 consecutive units) fall on disjoint banks.
+// Matvec mapping: warp w owns the K range [w, w+1) * H/8; lane (jp = lane / 4, vq = lane % 4) accumulates the 3 gates of
+// units 2jp, 2jp+1 for the 8 videos vq, vq+4, ..., vq+28 over that range: a 6 x 8 register tile, 14 shared-memory loads
+// (16 B) per 192 FMAs -- a 128-bit ld.shared occupies the SM's load path ~3.5 cycles per warp instruction whether or not
+// its lanes broadcast, so loads per FMA is what bounds this loop (the first version's 3 x 4 tile: 7 loads per 48 FMAs,
+// 6.4 us per step).  The 8 partial sums of every (gate, unit, video) go through shared memory; thread q then owns the
+// (unit, video) pairs q and q + 256 for the GRU cell.  Row pitch H + 4 floats for both W and h keeps the quarter-warp
+// phases of the 16-byte loads on disjoint banks.
 __global__ void __launch_bounds__(GF_THREADS, 1) gru_f32_persist_fwd_kernel(const GruF32Fwd p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int H = p.H, T = p.T, B = p.B, C = p.C, K4 = H >> 2, ld_s = H + 4;
   float* sW = reinterpret_cast<float*>(smem_raw);                 // [3 * GF_U][H + 4]
   float* sH = sW + (size_t)3 * GF_U * ld_s;                       // [GF_BG][H + 4]: h_{t-1} of the group
-  float* sP = sH + (size_t)GF_BG * ld_s;                          // [128][12]: partial sums of the upper K half
-  float* sO = sP + 128 * 12;                                      // [GF_BG][GF_OP]: h_t of this CTA's units
-  const int tid = threadIdx.x, ks = tid >> 7, jj = (tid & 127) >> 3, vq = tid & 7;
+  float* sP = sH + (size_t)GF_BG * ld_s;                          // [8 warps][3 gates][GF_BG][GF_U] partial sums
+  float* sO = sP + 8 * 3 * GF_BG * GF_U;                          // [GF_BG][GF_OP]: h_t of this CTA's units
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, jp = lane >> 2, vq = lane & 3;
   const int grp = blockIdx.x / C, cta = blockIdx.x - grp * C;
-  const int j0 = cta * GF_U, j = j0 + jj, b0 = grp * GF_BG;
+  const int j0 = cta * GF_U, b0 = grp * GF_BG;
   unsigned* ctr = p.counters + grp * 32;
   unsigned target = 0;
 
@@ -49,28 +53,28 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gru_f32_persist_fwd_kernel(cons
     const float4 v = __ldg(reinterpret_cast<const float4*>(p.w_hh + ((long long)(r / GF_U) * H + j0 + (r % GF_U)) * H) + k4);
     *reinterpret_cast<float4*>(sW + (size_t)r * ld_s + 4 * k4) = v;
   }
+  // cell role: pairs (video cv0, unit cj) and (cv0 + 16, cj)
+  const int cj = tid & 15, cv0 = tid >> 4, j = j0 + cj;
   const float bhr = p.b_hh[j], bhz = p.b_hh[H + j], bhn = p.b_hh[2 * H + j];
   const uint32_t sH_u32 = smem_u32(sH);
   __syncthreads();
 
   for (int t = 0; t < T; ++t) {
     // this step's input projections (independent of the recurrence: in flight across the barrier)
-    float gi[4][3];
+    float gi[2][3];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int b = b0 + vq + 8 * i;
+    for (int i = 0; i < 2; ++i) {
+      const int b = b0 + cv0 + 16 * i;
       gi[i][0] = gi[i][1] = gi[i][2] = 0.f;
-      if (ks == 0 && b < B) {
+      if (b < B) {
         const float* s = p.gi + (long long)t * p.gi_ts + (long long)b * p.gi_ld + j;
         gi[i][0] = __ldg(s); gi[i][1] = __ldg(s + H); gi[i][2] = __ldg(s + 2 * H);
       }
     }
     phase_stamp(p.dbg, t, 0);
     const bool has_prev = t > 0 || p.h0 != nullptr;
-    float acc[4][3];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.f;
-    float hprev[4] = {0.f, 0.f, 0.f, 0.f};
+    float gh[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+    float hprev[2] = {0.f, 0.f};
     if (has_prev) {
       const float* src = t > 0 ? p.h + (long long)(t - 1) * p.h_ts : p.h0;
       const long long ld = t > 0 ? p.h_ld : p.h0_ld;
@@ -89,47 +93,61 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gru_f32_persist_fwd_kernel(cons
       cp_async_wait<0>();
       __syncthreads();
       phase_stamp(p.dbg, t, 2);
-      const float* wr = sW + (size_t)jj * ld_s + (size_t)ks * (H >> 1);
-      const float* wz = wr + (size_t)GF_U * ld_s;
-      const float* wn = wz + (size_t)GF_U * ld_s;
-      const float* hv = sH + (size_t)vq * ld_s + (size_t)ks * (H >> 1);
-      const int K4h = K4 >> 1;
-#pragma unroll 4
-      for (int k4 = 0; k4 < K4h; ++k4) {
-        const float4 a = *reinterpret_cast<const float4*>(wr + 4 * k4);
-        const float4 b = *reinterpret_cast<const float4*>(wz + 4 * k4);
-        const float4 c = *reinterpret_cast<const float4*>(wn + 4 * k4);
+      {
+        const int K4w = K4 >> 3;                                  // 16-byte columns of this warp's K slice
+        const float* w0 = sW + (size_t)(2 * jp) * ld_s + (size_t)warp * K4w * 4;
+        const float* hv = sH + (size_t)vq * ld_s + (size_t)warp * K4w * 4;
+        float acc[8][6];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 h = *reinterpret_cast<const float4*>(hv + (size_t)(8 * i) * ld_s + 4 * k4);
-          acc[i][0] = fmaf(a.w, h.w, fmaf(a.z, h.z, fmaf(a.y, h.y, fmaf(a.x, h.x, acc[i][0]))));
-          acc[i][1] = fmaf(b.w, h.w, fmaf(b.z, h.z, fmaf(b.y, h.y, fmaf(b.x, h.x, acc[i][1]))));
-          acc[i][2] = fmaf(c.w, h.w, fmaf(c.z, h.z, fmaf(c.y, h.y, fmaf(c.x, h.x, acc[i][2]))));
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int r = 0; r < 6; ++r) acc[i][r] = 0.f;
+#pragma unroll 2
+        for (int k4 = 0; k4 < K4w; ++k4) {
+          float4 w[6];
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            w[2 * g] = *reinterpret_cast<const float4*>(w0 + (size_t)(g * GF_U) * ld_s + 4 * k4);
+            w[2 * g + 1] = *reinterpret_cast<const float4*>(w0 + (size_t)(g * GF_U + 1) * ld_s + 4 * k4);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 h = *reinterpret_cast<const float4*>(hv + (size_t)(4 * i) * ld_s + 4 * k4);
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+              acc[i][r] = fmaf(w[r].w, h.w, fmaf(w[r].z, h.z, fmaf(w[r].y, h.y, fmaf(w[r].x, h.x, acc[i][r]))));
+          }
         }
-      }
-      if (ks == 1) {
-        float* o = sP + (size_t)(tid & 127) * 12;
+        // partial sums -> sP[warp][gate][video][unit]
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { o[3 * i] = acc[i][0]; o[3 * i + 1] = acc[i][1]; o[3 * i + 2] = acc[i][2]; }
-      } else {
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) hprev[i] = sH[(size_t)(vq + 8 * i) * ld_s + j];
+          for (int g = 0; g < 3; ++g) {
+            float* o = sP + ((size_t)(warp * 3 + g) * GF_BG + (vq + 4 * i)) * GF_U + 2 * jp;
+            *reinterpret_cast<float2*>(o) = make_float2(acc[i][2 * g], acc[i][2 * g + 1]);
+          }
       }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) hprev[i] = sH[(size_t)(cv0 + 16 * i) * ld_s + j];
       __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          float s = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) s += sP[((size_t)(w * 3 + g) * GF_BG + cv0 + 16 * i) * GF_U + cj];
+          gh[i][g] = s;
+        }
     }
     phase_stamp(p.dbg, t, 3);
-    // GRU cell (torch gate order r, z, n; same expressions as gru_gate_fwd_kernel) on the lower-K-half threads
-    if (ks == 0) {
-      const float* o = sP + (size_t)tid * 12;
+    // GRU cell (torch gate order r, z, n; same expressions as gru_gate_fwd_kernel)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float gr = acc[i][0], gz = acc[i][1], gn = acc[i][2];
-        if (has_prev) { gr += o[3 * i]; gz += o[3 * i + 1]; gn += o[3 * i + 2]; }
-        const float r = 1.f / (1.f + expf(-(gi[i][0] + gr + bhr)));
-        const float z = 1.f / (1.f + expf(-(gi[i][1] + gz + bhz)));
-        const float n = tanhf(gi[i][2] + r * (gn + bhn));
-        sO[(vq + 8 * i) * GF_OP + jj] = (1.f - z) * n + z * hprev[i];
-      }
+    for (int i = 0; i < 2; ++i) {
+      const float r = 1.f / (1.f + expf(-(gi[i][0] + gh[i][0] + bhr)));
+      const float z = 1.f / (1.f + expf(-(gi[i][1] + gh[i][1] + bhz)));
+      const float n = tanhf(gi[i][2] + r * (gh[i][2] + bhn));
+      sO[(cv0 + 16 * i) * GF_OP + cj] = (1.f - z) * n + z * hprev[i];
     }
     __syncthreads();
     // h_t of this CTA's 16 units: 64 contiguous bytes per video, one float4 per thread
@@ -145,10 +163,10 @@ __global__ void __launch_bounds__(GF_THREADS, 1) gru_f32_persist_fwd_kernel(cons
 }
 
 static bool plan_f32(int B, int H, int& C, int& G, size_t& smem) {
-  if (H % GF_U != 0 || H % 8 != 0 || H > 512) return false;
+  if (H % GF_U != 0 || H % 32 != 0 || H > 512) return false;
   C = H / GF_U;
   G = (B + GF_BG - 1) / GF_BG;
-  smem = ((size_t)(3 * GF_U + GF_BG) * (H + 4) + 128 * 12 + GF_BG * GF_OP) * sizeof(float);
+  smem = ((size_t)(3 * GF_U + GF_BG) * (H + 4) + 8 * 3 * GF_BG * GF_U + GF_BG * GF_OP) * sizeof(float);
   return C <= 32 && (long long)G * C <= sm_count() && smem <= 227 * 1024;
 }
 
