@@ -147,6 +147,30 @@ __global__ void __launch_bounds__(256) cast_bf16_stream_kernel(const float* __re
   }
 }
 
+// K-blocked copy of operand planes: [R, ld] (ld a multiple of 64) -> [ld / 64][R][64], so that the 64-column block of any
+// row range is ONE contiguous run of memory.  A weight matrix that is streamed from HBM launch after launch (decoding: the
+// W_v planes, 70 MB per step) is then fetched in multi-KB runs instead of one 128-byte piece per row.
+__global__ void __launch_bounds__(256) block_planes_kernel(const uint4* __restrict__ in, long long groups, long long R,
+                                                           uint4* __restrict__ out) {
+  const long long total = R * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / groups, g = i - r * groups;
+    out[((g >> 3) * R + r) * 8 + (g & 7)] = in[i];
+  }
+}
+int block_planes(const bf16* in, long long ld, int R, bf16* out, cudaStream_t st) {
+  PVCR_REQUIRE(ld % 64 == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+               "block_planes: ld=%lld must be a multiple of 64 and the buffers 16-byte aligned", ld);
+  if (R == 0) return PVCR_OK;
+  const long long total = (long long)R * (ld / 8);
+  const int blocks = (int)((total + 255) / 256 > sm_count() * 16 ? sm_count() * 16 : (total + 255) / 256);
+  { LaunchScope ls_(KC_STAGE, st);
+  block_planes_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(in), ld / 8, R, reinterpret_cast<uint4*>(out));
+  }
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  return PVCR_OK;
+}
+
 int cast_split(const float* in, long long ld_in, int R, int C, bf16* out, long long ld_out, int Cp, int nsplit,
                int role_b, const float* row_scale, Dropout drop, cudaStream_t st) {
   PVCR_REQUIRE(Cp % 8 == 0 && Cp >= C && ld_out % 8 == 0, "cast_split: bad padding Cp=%d C=%d ld_out=%lld", Cp, C, ld_out);
@@ -424,12 +448,45 @@ int fill_zero(void* p, size_t bytes, cudaStream_t st) {
 // GRU gates (torch gate order r,z,n):  r = s(gi_r+gh_r)  z = s(gi_z+gh_z)  n = tanh(gi_n + r*gh_n)
 //                                      h' = (1-z)*n + z*h
 // ------------------------------------------------------------------------------------------------
-__global__ void gru_gate_fwd_kernel(GruFwdArgs a) {
+__global__ void __launch_bounds__(256) gru_gate_fwd_kernel(GruFwdArgs a) {
+  __shared__ long long s_word[9];                      // H >= 32 (host check): a block of 256 threads touches <= 9 videos
+  pdl_launch_dependents();                             // a programmatically launched successor may set itself up now
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int b_first = 0;
+  if (a.am_pmax) {
+    // fed-back word of every video this block touches: warp w combines the partial arg-max of video b_first + w, ...
+    // (same rule as argmax_parts_kernel: larger value, then lower index; an all-NaN row gives index 0)
+    b_first = (int)(((long long)blockIdx.x * blockDim.x) / a.H);
+    int b_last = (int)(((long long)blockIdx.x * blockDim.x + blockDim.x - 1) / a.H);
+    if (b_last >= a.B) b_last = a.B - 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int bb = b_first + warp; bb <= b_last; bb += 8) {
+      float m = -INFINITY;
+      int mi = 0x7fffffff;
+      for (int k = lane; k < a.am_nparts; k += 32) {
+        const float v = a.am_pmax[(long long)bb * a.am_nparts + k];
+        const int i = a.am_pidx[(long long)bb * a.am_nparts + k];
+        if (v > m || (v == m && i < mi)) { m = v; mi = i; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, m, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+      }
+      if (lane == 0) {
+        if (mi == 0x7fffffff) mi = 0;
+        s_word[bb - b_first] = mi;
+        // the block that holds unit 0 of the video publishes the id
+        if ((long long)bb * a.H >= (long long)blockIdx.x * blockDim.x && a.am_out) a.am_out[(long long)bb * a.am_out_stride] = mi;
+      }
+    }
+    __syncthreads();
+  }
   if (idx >= a.B * a.H) return;
   const int b = idx / a.H, j = idx % a.H, H = a.H;
   float gi[3], gh[3];
-  const long long rb = a.gi_b_rows ? a.gi_b_rows[b] : (long long)b;
+  const long long rb = a.am_pmax ? s_word[b - b_first] : (a.gi_b_rows ? a.gi_b_rows[b] : (long long)b);
 #pragma unroll
   for (int g = 0; g < 3; ++g) {
     float x = a.gi_a ? a.gi_a[(long long)b * a.gi_a_ld + g * H + j] : 0.f;
@@ -452,6 +509,8 @@ __global__ void gru_gate_fwd_kernel(GruFwdArgs a) {
 int gru_gate_fwd(const GruFwdArgs& a, cudaStream_t st) {
   const int total = a.B * a.H;
   if (total == 0) return PVCR_OK;
+  PVCR_REQUIRE(!a.am_pmax || (a.H >= 32 && a.gi_b && a.am_pidx && a.am_nparts > 0),
+               "gru_gate_fwd: folded arg-max needs H >= 32, the word table and the partials (H=%d)", a.H);
   { LaunchScope ls_(KC_GATE, st);
   gru_gate_fwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(a);
   }
@@ -621,7 +680,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwdArgs a) {
 // before it uses them (one memory round trip per phase instead of one per frame), scores are reduced by warp shuffles.
 // The step-wise decoders (greedy, beam search, split-precision training) were spending 50 of their ~195 us per step in
 // the kernel above.  Accurate tanhf / expf as above: this path serves the fp32-equivalent modes.
-template <int NF>
+template <int NF, bool PROJ = false>
 __global__ void __launch_bounds__(256) attn_fwd_vec_kernel(AttnFwdArgs a) {
   extern __shared__ float sm[];
   const int H = a.H, N = a.N, b = blockIdx.x;
@@ -632,8 +691,7 @@ __global__ void __launch_bounds__(256) attn_fwd_vec_kernel(AttnFwdArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, dg = tid % DG, fg = tid / DG, d0 = dg * 8;
   const float4* q4 = reinterpret_cast<const float4*>(a.q + (long long)b * a.q_ld + d0);
   const float4* v4 = reinterpret_cast<const float4*>(a.v + d0);
-  const float4 qa = q4[0], qb = q4[1], va = v4[0], vb = v4[1];
-  const float q8[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+  const float4 va = v4[0], vb = v4[1];
   const float v8[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
   const float* pk = a.pk + (long long)b * N * H + d0;
   const float* enc = a.enc + (long long)b * N * H + d0;
@@ -647,6 +705,12 @@ __global__ void __launch_bounds__(256) attn_fwd_vec_kernel(AttnFwdArgs a) {
       x[m][0] = __ldg(p4); x[m][1] = __ldg(p4 + 1);
     }
   }
+  // the keys and v do not depend on the step: when launched programmatically (decode loop) they were fetched while the
+  // predecessor, which produces the query, was still running
+  pdl_wait();
+  pdl_launch_dependents();
+  const float4 qa = q4[0], qb = q4[1];
+  const float q8[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
   for (int m = 0; m < NF; ++m) {
     const int n = fg + FG * m;
@@ -658,13 +722,15 @@ __global__ void __launch_bounds__(256) attn_fwd_vec_kernel(AttnFwdArgs a) {
     if (lane == 0 && n < N) sP[n * WPF + (dg >> 5)] = s;
   }
   // the encoder rows of the context phase are independent of the softmax: fetch them now
+  if (!PROJ) {
 #pragma unroll
-  for (int m = 0; m < NF; ++m) {
-    const int n = fg + FG * m;
-    x[m][0] = x[m][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n < N) {
-      const float4* e4 = reinterpret_cast<const float4*>(enc + (long long)n * H);
-      x[m][0] = __ldg(e4); x[m][1] = __ldg(e4 + 1);
+    for (int m = 0; m < NF; ++m) {
+      const int n = fg + FG * m;
+      x[m][0] = x[m][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n < N) {
+        const float4* e4 = reinterpret_cast<const float4*>(enc + (long long)n * H);
+        x[m][0] = __ldg(e4); x[m][1] = __ldg(e4 + 1);
+      }
     }
   }
   __syncthreads();
@@ -691,6 +757,29 @@ __global__ void __launch_bounds__(256) attn_fwd_vec_kernel(AttnFwdArgs a) {
     }
   }
   __syncthreads();
+  if (PROJ) {
+    // out[b, :] = sum_n alpha_n val[b, n, :]: a thread owns 4 consecutive output columns, 8 frames' 16-byte loads in flight.
+    // (Measured alternative: items of (4 columns, half of the frames) with 20 loads in flight -- 14.9 instead of 16.9 us alone,
+    // but 146 registers per thread: one CTA per SM, and the 128 CTAs no longer fit the SMs the vocabulary GEMM running next
+    // to this kernel leaves free: 1.95 instead of 1.77 ms per batch.)
+    const int W4 = a.W >> 2;
+    const float4* val = reinterpret_cast<const float4*>(a.val + (long long)b * N * a.W);
+    for (int c4 = tid; c4 < W4; c4 += 256) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int n0 = 0; n0 < N; n0 += 8) {
+        float4 y[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) y[k] = n0 + k < N ? __ldg(val + (long long)(n0 + k) * W4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float al = n0 + k < N ? ss[n0 + k] : 0.f;
+          acc.x += al * y[k].x; acc.y += al * y[k].y; acc.z += al * y[k].z; acc.w += al * y[k].w;
+        }
+      }
+      *reinterpret_cast<float4*>(a.out + (long long)b * a.out_ld + 4 * c4) = acc;
+    }
+    return;
+  }
   float c8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int m = 0; m < NF; ++m) {
@@ -712,8 +801,34 @@ __global__ void __launch_bounds__(256) attn_fwd_vec_kernel(AttnFwdArgs a) {
   }
 }
 
+bool attn_fwd_projected_ok(int N, int H, int W) {
+  const int DG = H >> 3, FG = DG > 0 && DG <= 256 ? 256 / DG : 0;
+  return H % 256 == 0 && H <= 2048 && FG >= 1 && (N + FG - 1) / FG <= 10 && W % 4 == 0;
+}
+
 int attn_fwd(const AttnFwdArgs& a, cudaStream_t st) {
   if (a.B == 0) return PVCR_OK;
+  if (a.val) {
+    PVCR_REQUIRE(attn_fwd_projected_ok(a.N, a.H, a.W) && a.out && a.out_ld % 4 == 0 && a.q_ld % 4 == 0 &&
+                     ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.pk) | reinterpret_cast<uintptr_t>(a.val) |
+                       reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(a.v)) & 15) == 0,
+                 "attn_fwd (projected values): shape N=%d H=%d W=%d / alignment not supported", a.N, a.H, a.W);
+    const int DG = a.H >> 3, FG = 256 / DG, nf = (a.N + FG - 1) / FG;
+    const size_t smem = ((size_t)a.N * (DG >> 5) + a.N + (size_t)FG * a.H) * sizeof(float);
+    PVCR_REQUIRE(smem <= 48 * 1024, "attn_fwd: H=%d N=%d needs %zu B of shared memory", a.H, a.N, smem);
+    { LaunchScope ls_(KC_ATTN, st);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(a.B); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    if (pdl_enabled()) { cfg.attrs = at; cfg.numAttrs = 1; }
+    if (nf <= 5) PVCR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_fwd_vec_kernel<5, true>, a));
+    else PVCR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_fwd_vec_kernel<10, true>, a));
+    }
+    PVCR_CUDA_CHECK(cudaGetLastError());
+    return PVCR_OK;
+  }
   // vectorised variant: H a multiple of 256 up to 2048 (whole warps per frame group), aligned rows, <= 10 frames per group
   const int DG = a.H >> 3, FG = DG > 0 && DG <= 256 ? 256 / DG : 0;
   static const bool vec_off = getenv("PVCR_NO_VEC_ATTN") != nullptr;

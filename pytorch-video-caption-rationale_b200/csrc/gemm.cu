@@ -52,13 +52,14 @@ struct MapKeyHash {
 static_assert(sizeof(MapKey) % 8 == 0, "MapKey must be 8-byte granular");
 
 // 3-D tensor map over (k, row, slab), box = 64 x box_rows x 1, 128-byte swizzle, OOB elements read as zero.
-int make_tensor_map(CUtensorMap* out, const OperandView& v, int K, int box_rows) {
+int make_tensor_map(CUtensorMap* out, const OperandView& v, int K, int box_rows, int box_k) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   MapKey key;
   memset(&key, 0, sizeof(key));
   key.ptr = v.ptr; key.ld = v.ld; key.slab_stride = v.slab_stride; key.rows = v.rows; key.slabs = v.slabs;
-  key.K = K; key.box_rows = box_rows;
+  key.K = K; key.box_rows = box_rows + (box_k == GEMM_BK ? 0 : 1 << 20);
+  PVCR_REQUIRE(box_k == GEMM_BK || box_k == 32, "tensor map: box of %d columns not supported", box_k);
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -74,10 +75,11 @@ int make_tensor_map(CUtensorMap* out, const OperandView& v, int K, int box_rows)
   PVCR_REQUIRE(slab_stride % 8 == 0, "tensor map: slab stride %lld must be a multiple of 8", slab_stride);
   cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)v.rows, (cuuint64_t)slabs};
   cuuint64_t gstr[2] = {(cuuint64_t)v.ld * 2, (cuuint64_t)slab_stride * 2};
-  cuuint32_t box[3] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(v.ptr), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_k == GEMM_BK ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed (%d): ptr=%p K=%d rows=%d slabs=%d ld=%lld slab=%lld", (int)r,
@@ -172,6 +174,16 @@ int gemm_store(const OperandView& a, const OperandView& b, const GemmCoords& gc,
                long long c_zstride, const float* bias, long long bias_zstride, int accumulate,
                cudaStream_t stream) {
   EpiStore epi{C, ldc, c_zstride, bias, bias_zstride, accumulate, gc.M, gc.N, 0, 1};
+  // skinny bf16x3 products on compact weight planes (decoding: [q | gh] = h [W_q; W_hh]^T with M = batch <= 256): the split3
+  // kernel on 64-column tiles instead of six split-K ranges + atomics.  A/B knob: PVCR_NO_SPLIT3_STORE=1.
+  static const bool s3_off = getenv("PVCR_NO_SPLIT3_STORE") != nullptr;
+  if (!s3_off && b.kp && b.terms == 3 && gc.K == 6 * b.kp && grid_z == 1 && gc.M <= 256 && gc.k_splits <= 1) {
+    GemmCoords g3 = gc;
+    g3.K = b.kp; g3.b_kp = 0; g3.b_terms = 0; g3.b_evict_last = 1;
+    static const int bk_knob = getenv("PVCR_SPLIT3_STORE_BK") ? atoi(getenv("PVCR_SPLIT3_STORE_BK")) : 64;
+    if (bk_knob == 32) return launch_gemm_split3<64, EpiStore, 4, 32>(a, b, g3, b.kp, epi, stream);
+    return launch_gemm_split3<64, EpiStore, 4>(a, b, g3, b.kp, epi, stream);
+  }
   const long long tiles256 = (long long)cdiv(gc.N, 256) * cdiv(gc.M, GEMM_BM) * grid_z;
   static const bool no_persist = getenv("PVCR_NO_PERSIST_GEMM") != nullptr;
   if (gc.N >= 256 && tiles256 >= 64 && !no_persist)
@@ -223,11 +235,11 @@ struct EpiArgmax {
       float* c = C + (long long)row * ldc + col0;
       if (full && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else {
+        for (int j = 0; j < 32; j += 4) __stcs(reinterpret_cast<float4*>(c + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+      } else {                                  // streaming stores: the logits are not read back inside the decode loop
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (col0 + j < N) c[j] = v[j];
+          if (col0 + j < N) __stcs(c + j, v[j]);
       }
     }
   }
@@ -258,24 +270,56 @@ __global__ void __launch_bounds__(128) argmax_parts_kernel(const float* __restri
     if (next) next[row] = mi;
   }
 }
-size_t gemm_argmax_scratch(int M, int N) { return (size_t)M * cdiv(N, 192) * 2 * (sizeof(float) + sizeof(int)) + 256; }
+size_t gemm_argmax_scratch(int M, int N) { return (size_t)M * cdiv(N, 128) * 2 * (sizeof(float) + sizeof(int)) + 256; }
 // logits (nullable) [M, ldc] = A B^T + bias;  out[row * out_stride] = next[row] = argmax_n.  scratch: gemm_argmax_scratch bytes.
+// out == nullptr: the combine pass is left to the consumer (gru_gate_fwd folds it into the next step's gate kernel);
+// parts (nullable) receives where the (max, index) partials are and how many there are per row.
 int gemm_argmax(const OperandView& a, const OperandView& b, int M, int N, int Kcat, const float* bias, float* logits,
-                long long ldc, long long* out, long long out_stride, long long* next, void* scratch, cudaStream_t st) {
+                long long ldc, long long* out, long long out_stride, long long* next, void* scratch, cudaStream_t st,
+                ArgmaxParts* parts) {
   GemmCoords gc{M, N, Kcat, 0, 0, 0, 0};
   if (b.kp) { gc.b_kp = b.kp; gc.b_terms = split_b_terms(b.terms); }
+  // the W_v planes are read again by the next step's launch: ask L2 to evict them last (A/B knob PVCR_DECODE_WV_HINT=0)
+  static const int wv_hint = getenv("PVCR_DECODE_WV_HINT") ? atoi(getenv("PVCR_DECODE_WV_HINT")) : -1;
   // Tile width (A/B knob PVCR_ARGMAX_BN=192): Vc = 23 000 gives 90 tiles of 256 columns (61 % of the SMs) or 120 of 192;
   // measured, the narrower tiles are SLOWER inside the decode loop (3.04 -> 3.17 ms per batch): the SMs the 256-wide
   // tiling leaves free are what the overlapped query / attention / context half of the next step runs on.
   static const int bn_knob = getenv("PVCR_ARGMAX_BN") ? atoi(getenv("PVCR_ARGMAX_BN")) : 0;
   const int bn = bn_knob == 192 ? 192 : 256;
-  const int nparts = cdiv(N, bn) * 2;
+  // bf16x3 with compact W_v planes: the split3 kernel loads every term block once per K chunk (half the L2 -> SM traffic of
+  // walking the six virtual planes) on 160-column tiles (144 CTAs for Vc = 23 000).  A/B knob: PVCR_ARGMAX_SPLIT3=0 / 128.
+  static const int s3_knob = getenv("PVCR_ARGMAX_SPLIT3") ? atoi(getenv("PVCR_ARGMAX_SPLIT3")) : 128;
+  const bool s3 = s3_knob != 0 && b.kp && b.terms == 3 && Kcat == 6 * b.kp && bn_knob == 0;
+  const int nparts = s3 ? (s3_knob == 128 ? cdiv(N, 128) * 2 : cdiv(N, 160)) : cdiv(N, bn) * 2;
+  // L2 policy of the W_v loads: 70 MB of planes do not stay in L2 from one step to the next anyway (measured: 73 MB of DRAM
+  // reads per launch with any policy), so the split3 kernel, which reads every byte once, streams them evict_first and leaves
+  // the L2 to what the other half of the step re-reads (projected frames, keys); the generic kernel re-reads planes within a
+  // launch and keeps evict_last.  PVCR_DECODE_WV_HINT = 0 / 1 / 2 overrides.
+  gc.b_evict_last = wv_hint >= 0 ? wv_hint : (s3 ? 2 : 1);
   EpiArgmax epi{};
   epi.C = logits; epi.ldc = ldc; epi.bias = bias; epi.M = M; epi.N = N; epi.nparts = nparts;
   epi.pmax = reinterpret_cast<float*>(scratch);
   epi.pidx = reinterpret_cast<int*>(epi.pmax + (size_t)M * nparts);
-  if (bn == 192) PVCR_TRY((launch_gemm_tn_persistent<192, 4, EpiArgmax>(a, b, gc, 1, epi, st)));
+  if (s3) {
+    GemmCoords g3 = gc;
+    g3.K = b.kp; g3.b_kp = 0; g3.b_terms = 0;
+    // L2 prefetch of the CTA's W_v blocks ahead of the ring: measured SLOWER (33.4 -> 37.3 us alone, 1.95 -> 2.06 ms per batch:
+    // the prefetches queue in front of the ring's own loads in the TMA unit); off unless PVCR_WV_PREFETCH=1
+    static const bool prefetch_on = getenv("PVCR_WV_PREFETCH") != nullptr;
+    g3.b_prefetch = prefetch_on && g3.b_evict_last == 2;
+    // 128-column tiles on at most 90 CTAs (two tiles each at Vc = 23 000): the other SMs run the recurrent half of the next
+    // step next to it (measured: 144 CTAs of 160 columns 2.22 / 2.04 ms per batch, 90 CTAs of 128 columns 2.13 / 1.86)
+    static const int cta_knob = getenv("PVCR_ARGMAX_CTAS") ? atoi(getenv("PVCR_ARGMAX_CTAS")) : 90;
+    CtaCap cap(cta_knob > 0 ? cta_knob : gemm_cta_cap());
+    static const int bk_knob = getenv("PVCR_ARGMAX_BK") ? atoi(getenv("PVCR_ARGMAX_BK")) : 64;
+    if (s3_knob == 128 && bk_knob == 32) PVCR_TRY((launch_gemm_split3<128, EpiArgmax, 8, 32>(a, b, g3, b.kp, epi, st)));
+    else if (s3_knob == 128) PVCR_TRY((launch_gemm_split3<128, EpiArgmax, 8>(a, b, g3, b.kp, epi, st)));
+    else PVCR_TRY((launch_gemm_split3<160, EpiArgmax, 4>(a, b, g3, b.kp, epi, st)));
+  }
+  else if (bn == 192) PVCR_TRY((launch_gemm_tn_persistent<192, 4, EpiArgmax>(a, b, gc, 1, epi, st)));
   else PVCR_TRY((launch_gemm_tn_persistent<256, 4, EpiArgmax>(a, b, gc, 1, epi, st)));
+  if (parts) { parts->pmax = epi.pmax; parts->pidx = epi.pidx; parts->nparts = nparts; }
+  if (!out) return PVCR_OK;
   { LaunchScope ls_(KC_LOSS, st);
     argmax_parts_kernel<<<cdiv(M, 4), 128, 0, st>>>(epi.pmax, epi.pidx, M, nparts, out, out_stride, next);
   }

@@ -39,6 +39,10 @@ struct GemmCoords {
   // column  term(p) * b_kp + off,  term(p) = (b_terms >> 2p) & 3.  b_kp == 0: B is stored as it is multiplied.
   int b_kp = 0;
   unsigned b_terms = 0;
+  int b_blocked = 0;     // split3 kernel: B is K-blocked ([term * b_blocked + chunk][row][64], b_blocked = chunks per term)
+  int b_prefetch = 0;    // split3 kernel: request every B block of a CTA's tiles into L2 up front (B streamed from HBM)
+  int b_evict_last = 0;  // persistent / split3 kernel, K-major B: L2 hint of the B loads (1 = evict_last: re-read by the next
+                         // launch and small enough to stay; 2 = evict_first: streamed once, must not displace resident data)
   __host__ __device__ int b_col(int k) const {
     if (b_kp == 0) return k;
     const int p = k / b_kp;
@@ -202,6 +206,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 
   if (warp == 0) {
     if (lane == 0) {
+      const uint64_t b_policy = gc.b_evict_last == 2 ? l2_policy_evict_first() : l2_policy_evict_last();
       int it = 0;                                    // running k-block counter across tiles
       for (int w = blockIdx.x; w < num_tiles; w += gridDim.x) {
         const int t = w / splits, kb0 = (w - t * splits) * kb_per;
@@ -226,6 +231,8 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i)
               tma_load_3d(sa + SM::A_BYTES + i * 8192, &tmB, &full_bar[s], n0 + 64 * i, kb * GEMM_BK, bz);
+          } else if (gc.b_evict_last) {
+            tma_load_3d_hint(sa + SM::A_BYTES, &tmB, &full_bar[s], gc.b_col(kb * GEMM_BK), n0, bz, b_policy);
           } else {
             tma_load_3d(sa + SM::A_BYTES, &tmB, &full_bar[s], gc.b_col(kb * GEMM_BK), n0, bz);
           }
@@ -300,6 +307,176 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   }
 }
 
+
+// ---- split-precision (bf16x3) product with every operand block loaded ONCE per K chunk ---------------------------------
+// C = sum over the six term pairs (a2,b0) (a1,b1) (a0,b2) (a1,b0) (a0,b1) (a0,b0) of A_term B_term^T.  The generic kernels
+// above walk the six virtual planes one after the other, so every stored term of both operands crosses L2 -> SM two to three
+// times (48 KB per 128 x 256 x 64 product block).  Here a pipeline stage holds the three A terms and the three B terms of one
+// 64-column K chunk (3 x 16 KB + 3 x BN x 128 B) and the MMA warp issues the six products from it: half the operand traffic
+// for the skinny decoding products (M = batch <= 128 rows: the vocabulary projection streams W_v's 70 MB once per step and is
+// bound by exactly that).  A: split planes in A-role order (term t at plane 2 - t, common.cuh), a_kp columns per plane;
+// B: compact planes (term t at plane t), b_kp columns per plane; gc.K = columns of ONE plane (multiple of 64).
+// BK = 64 (128-byte swizzle rows) or 32 (64-byte swizzle rows: half-size stages, twice as many of them in flight)
+template <int BN, int BK = GEMM_BK>
+struct GemmSplit3Smem {
+  static_assert(BK == 64 || BK == 32, "K chunk");
+  static constexpr int A_BYTES = GEMM_BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = 3 * A_BYTES + 3 * B_BYTES;
+  static constexpr int STAGES = (227 * 1024 - 2048) / STAGE_BYTES > 6 ? 6 : (227 * 1024 - 2048) / STAGE_BYTES;
+  static_assert(STAGES >= 2, "tile too wide for two pipeline stages");
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;          // barriers / slot + alignment slack
+};
+
+template <int BN, class Epi, int EW, int BK = GEMM_BK>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
+gemm_split3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmCoords gc,
+                   int a_kp, int b_kp, int tiles_m, int tiles_n, int num_tiles, Epi epi) {
+  using SM = GemmSplit3Smem<BN, BK>;
+  constexpr int STAGES = SM::STAGES;
+  static_assert(2 * BN <= 512 && BN % 16 == 0 && (BN * 128) % 1024 == 0, "tile width");
+  static_assert(BN % (EW / 4) == 0 && (BN / (EW / 4)) % 32 == 0, "each epilogue warp drains whole 32-column chunks");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int chunks = gc.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], EW);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, tmem_cols_pow2(2 * BN));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // launched programmatically (decode loop): everything above overlapped the predecessor's tail; its output (the A planes)
+  // may be read, and C written, only from here on
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint64_t b_policy = gc.b_evict_last == 2 ? l2_policy_evict_first() : l2_policy_evict_last();
+      int it = 0;
+      // B streamed from HBM (b_prefetch): the bytes in flight of the shared-memory ring (STAGES x 3 x B_BYTES per SM) are far
+      // below bandwidth x latency, so every B block of this CTA's tiles is first requested into L2 -- the ring then runs at L2
+      // latency while DRAM streams at its own pace.  (B does not depend on the predecessor: this could even precede pdl_wait.)
+      if (gc.b_prefetch && tiles_m == 1) {                // (several row tiles share a B tile: nothing to stream ahead)
+        for (int w = blockIdx.x; w < num_tiles; w += gridDim.x) {
+          const int n0 = w * BN;
+          for (int c = 0; c < chunks; ++c)
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+              const int bk = gc.b_blocked ? (c * BK) % GEMM_BK : t * b_kp + c * BK;
+              const int bz = gc.b_blocked ? t * gc.b_blocked + (c * BK) / GEMM_BK : gc.b_z0;
+              tma_prefetch_l2_3d(&tmB, bk, n0, bz);
+            }
+        }
+      }
+      for (int w = blockIdx.x; w < num_tiles; w += gridDim.x) {
+        const int m0 = (w % tiles_m) * GEMM_BM, n0 = (w / tiles_m) * BN;
+        for (int c = 0; c < chunks; ++c, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], SM::STAGE_BYTES);
+          uint8_t* sa = smem + s * SM::STAGE_BYTES;
+          uint8_t* sb = sa + 3 * SM::A_BYTES;
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+            tma_load_3d(sa + t * SM::A_BYTES, &tmA, &full_bar[s], (2 - t) * a_kp + c * BK, m0, gc.a_z0);
+            const int bk = gc.b_blocked ? (c * BK) % GEMM_BK : t * b_kp + c * BK;
+            const int bz = gc.b_blocked ? t * gc.b_blocked + (c * BK) / GEMM_BK : gc.b_z0;
+            if (gc.b_evict_last) tma_load_3d_hint(sb + t * SM::B_BYTES, &tmB, &full_bar[s], bk, n0, bz, b_policy);
+            else tma_load_3d(sb + t * SM::B_BYTES, &tmB, &full_bar[s], bk, n0, bz);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+      int it = 0, ti = 0;
+      for (int w = blockIdx.x; w < num_tiles; w += gridDim.x, ++ti) {
+        const int acc = ti & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((ti >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int c = 0; c < chunks; ++c, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
+          const uint32_t sb = sa + 3 * SM::A_BYTES;
+          // smallest products first (the order of the six virtual planes of the generic kernels)
+          constexpr int TA[6] = {2, 1, 0, 1, 0, 0}, TB[6] = {0, 1, 2, 0, 1, 0};
+#pragma unroll
+          for (int p = 0; p < 6; ++p) {
+            const uint64_t da = BK == 64 ? umma_desc_k128(sa + TA[p] * SM::A_BYTES) : umma_desc_k64(sa + TA[p] * SM::A_BYTES);
+            const uint64_t db = BK == 64 ? umma_desc_k128(sb + TB[p] * SM::B_BYTES) : umma_desc_k64(sb + TB[p] * SM::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (c | p | k) != 0);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    constexpr int PARTS = EW / 4, HALF = BN / PARTS;
+    int ti = 0;
+    for (int w = blockIdx.x; w < num_tiles; w += gridDim.x, ++ti) {
+      const int m0 = (w % tiles_m) * GEMM_BM, n0 = (w / tiles_m) * BN;
+      const int acc = ti & 1;
+      const int row = m0 + q * 32 + lane;
+      Epi e = epi;
+      e.begin(row, 0);
+      mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);
+      tc_fence_after();
+      float v[32];
+#pragma unroll 1
+      for (int c = half * HALF; c < (half + 1) * HALF; c += 32) {
+        if (n0 + c >= gc.N) break;
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
+        e.chunk(row, n0 + c, 0, v);
+      }
+      e.end(row, (w / tiles_m) * PARTS + half, 0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols_pow2(2 * BN));
+  }
+}
 
 // ---- 2-CTA cluster variant: the B tile is shared by TMA multicast ------------------------------------------------
 // With K = 512 (vocabulary projection) a 128 x 256 tile needs 384 KB of operands for 4096 tensor-pipe cycles: 148 CTAs
@@ -702,7 +879,11 @@ struct OperandView {
   long long ld, slab_stride;
   int rows, slabs;
   int kp = 0, terms = 0;      // compact B-role planes: `terms` stored planes of kp columns each (0: plain)
+  const bf16* blocked = nullptr;   // optional second copy in the K-blocked layout [terms * kp / 64][rows][64] (block_planes)
 };
+
+// where gemm_argmax left the per-row (max, index) partials of its column parts
+struct ArgmaxParts { const float* pmax; const int* pidx; int nparts; };
 
 // Upper bound on the CTAs of a persistent GEMM launched while a CtaCap is alive on this host thread (0 = all SMs):
 // GEMMs forked onto the side lane next to a persistent recurrent sweep take only the SMs the sweep leaves free.
@@ -713,7 +894,8 @@ struct CtaCap {
   ~CtaCap();
 };
 
-int make_tensor_map(CUtensorMap* out, const OperandView& v, int K, int box_rows);
+// box_k = 64: 128-byte swizzle rows (default);  32: 64-byte swizzle rows
+int make_tensor_map(CUtensorMap* out, const OperandView& v, int K, int box_rows, int box_k = GEMM_BK);
 // MN-major operand: bf16 matrix [k_rows, mn_cols] (row stride v.ld, v.rows = k_rows); boxes of 64 (mn) x 64 (k).
 int make_tensor_map_mn(CUtensorMap* out, const OperandView& v, int mn_cols);
 
@@ -774,6 +956,53 @@ int launch_gemm_tn_persistent(const OperandView& a, const OperandView& b, const 
   {
     LaunchScope ls_(KC_GEMM, stream, 2.0 * gc.M * gc.N * (double)gc.K * grid_z);
     kern<<<grid, 64 + 32 * EW, SM::TOTAL + 64 + 256 + EW * Epi::SMEM_PER_WARP, stream>>>(ta, tb, gc, tiles_m, tiles_n, (int)num_tiles, epi);
+  }
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  return PVCR_OK;
+}
+
+// bf16x3 product from A-role split planes (6 planes of a_kp columns) and compact B planes (3 terms of b.kp columns):
+// gc.K = columns of one plane.  Epilogues without per-warp shared memory only.
+template <int BN, class Epi, int EW, int BK = GEMM_BK>
+int launch_gemm_split3(const OperandView& a, const OperandView& b, GemmCoords gc, int a_kp, const Epi& epi, cudaStream_t stream) {
+  using SM = GemmSplit3Smem<BN, BK>;
+  static_assert(Epi::SMEM_PER_WARP == 0, "split3 kernel: register-only epilogues");
+  PVCR_REQUIRE(gc.K > 0 && gc.K % GEMM_BK == 0 && gc.K <= a_kp && gc.K <= b.kp, "gemm (split3): K=%d vs planes of %d / %d columns", gc.K, a_kp, b.kp);
+  PVCR_REQUIRE(gc.M > 0 && gc.N > 0 && b.terms == 3 && gc.k_splits <= 1, "gemm (split3): needs three compact B terms, no split-K");
+  CUtensorMap ta, tb;
+  PVCR_TRY(make_tensor_map(&ta, a, 6 * a_kp, GEMM_BM, BK));
+  static const bool blocked_off = getenv("PVCR_NO_WV_BLOCKED") != nullptr;      // A/B knob
+  if (b.blocked && !blocked_off) {
+    PVCR_REQUIRE(b.kp % GEMM_BK == 0 && b.slabs == 1, "gemm (split3): blocked B planes need kp %% 64 == 0 and one slab");
+    OperandView bb{b.blocked, GEMM_BK, (long long)b.rows * GEMM_BK, b.rows, b.terms * b.kp / GEMM_BK};
+    PVCR_TRY(make_tensor_map(&tb, bb, GEMM_BK, BN, BK));
+    gc.b_blocked = b.kp / GEMM_BK;
+  } else {
+    PVCR_TRY(make_tensor_map(&tb, b, b.kp * b.terms, BN, BK));
+  }
+  auto kern = gemm_split3_kernel<BN, Epi, EW, BK>;
+  static bool attr_set = false;
+  static int sms = 0;
+  if (!attr_set) {
+    PVCR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    int dev = 0;
+    PVCR_CUDA_CHECK(cudaGetDevice(&dev));
+    PVCR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    attr_set = true;
+  }
+  const int tiles_m = cdiv(gc.M, GEMM_BM), tiles_n = cdiv(gc.N, BN);
+  const long long num_tiles = (long long)tiles_m * tiles_n;
+  int grid = (int)(num_tiles < sms ? num_tiles : sms);
+  if (gemm_cta_cap() > 0 && grid > gemm_cta_cap()) grid = gemm_cta_cap();
+  {
+    LaunchScope ls_(KC_GEMM, stream, 2.0 * gc.M * gc.N * (double)gc.K * 6);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 32 * EW); cfg.dynamicSmemBytes = SM::TOTAL; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    if (pdl_enabled()) { cfg.attrs = at; cfg.numAttrs = 1; }
+    PVCR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, gc, a_kp, (int)b.kp, tiles_m, tiles_n, (int)num_tiles, epi));
   }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;

@@ -80,7 +80,8 @@ int gemm_store(const OperandView& a, const OperandView& b, const GemmCoords& gc,
 // projection + row arg-max in one pass (gemm.cu): logits (nullable) = A B^T + bias, out[row * out_stride] = next[row] = argmax
 size_t gemm_argmax_scratch(int M, int N);
 int gemm_argmax(const OperandView& a, const OperandView& b, int M, int N, int Kcat, const float* bias, float* logits,
-                long long ldc, long long* out, long long out_stride, long long* next, void* scratch, cudaStream_t st);
+                long long ldc, long long* out, long long out_stride, long long* next, void* scratch, cudaStream_t st,
+                ArgmaxParts* parts = nullptr);
 
 // bf16 (single-plane) copies of fp32 matrices staged during one backward call: the hoisted gradient GEMMs share
 // operands (d gi feeds dW_c, dW_e and d emb; the forward pass already staged vid / enc / embedded words), so each

@@ -31,6 +31,7 @@ int cast_split(const float* in, long long ld_in, int R, int C, bf16* out, long l
                int role_b, const float* row_scale, Dropout drop, cudaStream_t st);
 // out[c][p*Rp + r_off + r] = term_{role,p}( src(r)[c] * (row_scale ? row_scale[r] : 1) ) for r < R, where
 // src(r) = in + (row_ids ? row_ids[r] : r) * ld_in.  With zero_pad, columns r_off+R .. Rp-1 are zero-filled.
+int block_planes(const bf16* in, long long ld, int R, bf16* out, cudaStream_t st);      // [R, ld] -> [ld / 64][R][64]
 int transpose_split(const float* in, long long ld_in, int R, int C, bf16* out, long long ld_out, int Rp, int r_off,
                     int zero_pad, int nsplit, int role_b, const long long* row_ids, const float* row_scale,
                     cudaStream_t st, Dropout drop);     // drop: element index r*C + c (as gather_split)
@@ -65,6 +66,11 @@ struct GruFwdArgs {
   const float* gi_a; long long gi_a_ld;     // [B,3H] (nullable: the step has no input, e.g. S2VT rnn1 while decoding)
   const float* gi_b; long long gi_b_ld;     // optional second addend
   const long long* gi_b_rows = nullptr;     // optional: video b reads row gi_b_rows[b] of gi_b (a table indexed by word id)
+  // optional (greedy decoding): the row index of video b is the arg-max over am_nparts (max, index) partials that the
+  // vocabulary GEMM's epilogue left for row b (gemm_argmax with out == nullptr) -- the combine pass of the previous step
+  // folded into this kernel: one launch less on the fed-back-word path.  The word goes to am_out[b * am_out_stride].
+  const float* am_pmax = nullptr; const int* am_pidx = nullptr; int am_nparts = 0;
+  long long* am_out = nullptr; long long am_out_stride = 0;
   const float* gi_bias;                     // optional [3H] bias addend
   const float* gh; long long gh_ld;         // [B,3H] W_hh h (no bias) or null (h_prev == 0)
   const float* b_hh;                        // [3H]
@@ -123,8 +129,13 @@ struct AttnFwdArgs {
   float* alpha;                             // [B,N]
   float* ctx; long long ctx_ld;             // [B,H]
   bf16* ctx_planes; long long ctx_planes_ld; int Hp, nsplit;
+  // projected-value mode (decoding): val [B,N,W] = enc W_c^T hoisted out of the step loop; the kernel then writes
+  // out [B,W] = sum_n alpha_n val[b,n,:] (= W_c ctx) instead of ctx -- no context vector, no GEMM behind the attention
+  const float* val = nullptr; int W = 0;
+  float* out = nullptr; long long out_ld = 0;
 };
 int attn_fwd(const AttnFwdArgs& a, cudaStream_t st);
+bool attn_fwd_projected_ok(int N, int H, int W);      // shapes the projected-value mode serves
 struct AttnBwdArgs {
   int B, N, H;
   const float* dctx; long long dctx_ld;

@@ -571,13 +571,15 @@ int s2vtatt_decode_bwd(const PvcrDims& d, const PvcrS2vtAttParams& p, const long
 struct GreedyWs {
   AttWs w;
   Planes wv, emb_all, wcat_c, wc_c;      // weights of the per-step products: each split term stored once (compact planes)
-  float *logits_step, *hs, *emb_table;
+  bf16* wv_blocked;                      // W_v planes again, K-blocked (block_planes): what the per-step projection streams
+  float *logits_step, *hs, *emb_table, *pc;
   long long* words;
   void* argmax_scratch;
 };
 static void carve_greedy(Arena& a, const PvcrDims& d, GreedyWs& g) {
   carve(a, d, 0, g.w);
   g.wv = alloc_planes_compact(a, d.Vc, d.H, d.nsplit);           // each term of W_v once: the planes stay L2-resident between steps
+  g.wv_blocked = a.alloc<bf16>((size_t)d.Vc * g.wv.ld);
   g.wcat_c = alloc_planes_compact(a, 4 * d.H, d.H, d.nsplit);
   g.wc_c = alloc_planes_compact(a, 3 * d.H, d.H, d.nsplit);
   g.emb_all = alloc_planes(a, d.Vc, d.E, d.nsplit);              // the whole embedding table as an A-role operand (prepare only)
@@ -586,6 +588,7 @@ static void carve_greedy(Arena& a, const PvcrDims& d, GreedyWs& g) {
   g.hs = a.alloc<float>((size_t)d.B * d.L * d.H);
   g.words = a.alloc<long long>(d.B);
   g.argmax_scratch = a.alloc<char>(gemm_argmax_scratch(d.B, d.Vc));
+  g.pc = a.alloc<float>((size_t)d.B * d.N * 3 * d.H);            // enc W_c^T: the context projection of every frame
 }
 size_t s2vtatt_greedy_workspace(const PvcrDims& d) {
   Arena a(nullptr, 0);
@@ -624,6 +627,7 @@ int s2vtatt_greedy_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const flo
   PVCR_TRY(prep_weight(p.dec_w_ih, H + E, H3, H, gw.wc_c, st));
   PVCR_TRY(prep_weight(p.dec_w_ih + H, H + E, H3, E, w.we, st));
   PVCR_TRY(prep_weight(p.out_w, H, Vc, H, gw.wv, st));
+  PVCR_TRY(block_planes(gw.wv.ptr, gw.wv.ld, Vc, gw.wv_blocked, st));
   if (gw.emb_all.Kp != E) PVCR_TRY(fill_zero(gw.emb_all.ptr, sizeof(bf16) * (size_t)Vc * gw.emb_all.ld, st));
   PVCR_TRY(stage(p.emb, E, Vc, E, gw.emb_all, 0, nullptr, NO_DROPOUT, st));
   PVCR_TRY(gemm_planes(gw.emb_all.view(), w.we.view(), Vc, H3, (int)gw.emb_all.ld, gw.emb_table, H3, p.dec_b_ih, 0, st));
@@ -659,12 +663,21 @@ int s2vtatt_greedy_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const flo
   const H0 h0 = initial_state(d, w, given);
   PVCR_TRY(gemm_planes(w.enc_a.view(), w.wk.view(), BN, H, (int)w.enc_a.ld, w.pk, H, nullptr, 0, st));
   PVCR_TRY(fill_i64(gw.words, sos_id, B, st));
+  // W_c ctx = sum_n alpha_n (W_c enc_n): the context projection is hoisted to ONE [B N, H] x [H, 3H] GEMM per batch and the
+  // attention kernel sums the projected frames -- no context vector, no per-step GEMM behind the attention
+  static const bool pc_off = getenv("PVCR_NO_DECODE_PC") != nullptr;                 // A/B knob
+  const bool use_pc = !pc_off && attn_fwd_projected_ok(N, H, H3);
+  if (use_pc) PVCR_TRY(gemm_planes(w.enc_a.view(), gw.wc_c.view(), BN, H3, (int)w.enc_a.ld, gw.pc, H3, nullptr, 0, st));
   float* hs = gw.hs;
   // Step i: [q | gh] = [W_q; W_hh] h_{i-1} -> attention -> W_c ctx   (needs h_{i-1} only)
   //         gates with T[word_i] -> h_i -> logits_i -> word_{i+1}    (the only place the fed-back word enters)
   // so the first half of step i+1 does not wait for the vocabulary projection and arg-max of step i: it runs on a side
   // lane next to them and the two meet again at the gates of step i+1.
+  // The chain gates -> [q | gh] product -> attention is launched programmatically (PdlScope): each kernel's launch latency
+  // and prologue overlap the tail of its predecessor.  A/B knob: PVCR_NO_DECODE_PDL.
+  static const bool pdl_off = getenv("PVCR_NO_DECODE_PDL") != nullptr;
   auto recurrent_half = [&](int i, cudaStream_t s) -> int {
+    PdlScope pdl(!pdl_off && i > 0);
     OperandView hprev_a = (i == 0)
         ? OperandView{const_cast<bf16*>(h0.a), h0.a_ld, 0, B, 1}
         : OperandView{w.hs_a.ptr + (long long)(i - 1) * w.hs_a.ld, (long long)L * w.hs_a.ld, 0, B, 1};
@@ -675,11 +688,17 @@ int s2vtatt_greedy_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const flo
     at.alpha = alphas ? alphas + (long long)i * B * N : w.alpha_all;
     at.ctx = w.ctx_all; at.ctx_ld = H;
     at.ctx_planes = w.ctx_a.ptr; at.ctx_planes_ld = w.ctx_a.ld; at.Hp = w.ctx_a.Kp; at.nsplit = d.nsplit;
+    if (use_pc) { at.val = gw.pc; at.W = H3; at.out = w.g2; at.out_ld = H3; }
     PVCR_TRY(attn_fwd(at, s));
-    PVCR_TRY(gemm_planes(w.ctx_a.view(), gw.wc_c.view(), B, H3, (int)w.ctx_a.ld, w.g2, H3, nullptr, 0, s));
+    if (!use_pc) PVCR_TRY(gemm_planes(w.ctx_a.view(), gw.wc_c.view(), B, H3, (int)w.ctx_a.ld, w.g2, H3, nullptr, 0, s));
     return PVCR_OK;
   };
   static const bool overlap_off = getenv("PVCR_NO_DECODE_OVERLAP") != nullptr;       // A/B knob
+  // The (max, index) partials of step i's vocabulary GEMM are combined by the gate kernel of step i+1 (which is where the
+  // fed-back word is needed): one launch less on the critical path of every step.  A/B knob: PVCR_NO_DECODE_FOLD_ARGMAX.
+  static const bool fold_off = getenv("PVCR_NO_DECODE_FOLD_ARGMAX") != nullptr;
+  const bool fold = !fold_off && H >= 32;
+  ArgmaxParts parts{};
   PVCR_TRY(recurrent_half(0, st));
   for (int i = 0; i < L; ++i) {
     float* g1 = w.g1_all;
@@ -687,6 +706,10 @@ int s2vtatt_greedy_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const flo
     g.B = B; g.H = H;
     g.gi_a = w.g2; g.gi_a_ld = H3;
     g.gi_b = gw.emb_table; g.gi_b_ld = H3; g.gi_b_rows = gw.words;      // + W_e Emb[word] + b_ih
+    if (fold && i > 0) {                                                // word_i = arg-max of step i-1, combined here
+      g.am_pmax = parts.pmax; g.am_pidx = parts.pidx; g.am_nparts = parts.nparts;
+      g.am_out = ids + (i - 1); g.am_out_stride = L;
+    }
     g.gh = g1 + H; g.gh_ld = H4; g.b_hh = p.dec_b_hh;
     if (i == 0) { g.h_prev = h0.f; g.h_prev_ld = h0.f_ld; }
     else { g.h_prev = hs + (long long)(i - 1) * H; g.h_prev_ld = (long long)L * H; }
@@ -702,8 +725,11 @@ int s2vtatt_greedy_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const flo
     // logits_i and word_{i+1} in one pass: the arg-max is taken in the GEMM epilogue (the logits are stored only when the
     // caller asked for them and never read back)
     if (i + 1 < L) PVCR_TRY(recurrent_half(i + 1, st));
-    PVCR_TRY(gemm_argmax(h_a, gw.wv.view(), B, Vc, (int)w.hs_a.ld, p.out_b, logits ? logits + (long long)i * Vc : nullptr,
-                         (long long)L * Vc, ids + i, L, gw.words, gw.argmax_scratch, lane));
+    const bool combine_here = !fold || i + 1 == L;
+    OperandView wv_v = gw.wv.view();
+    wv_v.blocked = gw.wv_blocked;
+    PVCR_TRY(gemm_argmax(h_a, wv_v, B, Vc, (int)w.hs_a.ld, p.out_b, logits ? logits + (long long)i * Vc : nullptr,
+                         (long long)L * Vc, combine_here ? ids + i : nullptr, L, gw.words, gw.argmax_scratch, lane, &parts));
     if (lane != st) PVCR_TRY(side_join_lane(st, 0));
   }
   PVCR_TRY(side_call_end(st));

@@ -145,6 +145,10 @@ bool side_note_take(const void* key, int tag, const void* what) {
 // End of a C-ABI call: mode 1 joins here, mode 2 leaves the lane running until pvcr_side_join().
 int side_call_end(cudaStream_t main) { return g_mode == 2 ? PVCR_OK : side_join(main); }
 
+static thread_local bool g_pdl = false;
+bool pdl_enabled() { return g_pdl; }
+PdlScope::PdlScope(bool on) : prev(g_pdl) { g_pdl = on; }
+PdlScope::~PdlScope() { g_pdl = prev; }
 int gemm_cta_cap() { return g_cta_cap; }
 CtaCap::CtaCap(int cap) : prev(g_cta_cap) { g_cta_cap = cap; }
 CtaCap::~CtaCap() { g_cta_cap = prev; }

@@ -11,13 +11,14 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 N, V, H, E, L, Vc = 40, 2048, 512, 300, 30, 23000
 m = S2VTAttModel(FixtureGlove(Vc, E), 0.2, H, V, L).cuda().eval()
 vid = torch.randn(B, N, V, device="cuda")
+RL = os.environ.get("PVCR_PROBE_NOLOGITS") is None
 with torch.no_grad():
-    for _ in range(2): m.greedy(vid)
+    for _ in range(2): m.greedy(vid, return_logits=RL)
 torch.cuda.synchronize()
 Lb = _lib.lib()
 Lb.pvcr_prof_reset(); Lb.pvcr_prof_enable(1)
 with torch.no_grad():
-    m.greedy(vid)
+    m.greedy(vid, return_logits=RL)
 torch.cuda.synchronize()
 Lb.pvcr_prof_enable(0)
 cap = 2048
