@@ -174,10 +174,10 @@ int gemm_store(const OperandView& a, const OperandView& b, const GemmCoords& gc,
                long long c_zstride, const float* bias, long long bias_zstride, int accumulate,
                cudaStream_t stream) {
   EpiStore epi{C, ldc, c_zstride, bias, bias_zstride, accumulate, gc.M, gc.N, 0, 1};
-  // skinny bf16x3 products on compact weight planes (decoding: [q | gh] = h [W_q; W_hh]^T with M = batch <= 256): the split3
+  // skinny bf16x3 products on compact weight planes (decoding: [q | gh] = h [W_q; W_hh]^T with M = batch <= 128): the split3
   // kernel on 64-column tiles instead of six split-K ranges + atomics.  A/B knob: PVCR_NO_SPLIT3_STORE=1.
   static const bool s3_off = getenv("PVCR_NO_SPLIT3_STORE") != nullptr;
-  if (!s3_off && b.kp && b.terms == 3 && gc.K == 6 * b.kp && grid_z == 1 && gc.M <= 256 && gc.k_splits <= 1) {
+  if (!s3_off && b.kp && b.terms == 3 && gc.K == 6 * b.kp && grid_z == 1 && gc.M <= GEMM_BM && gc.k_splits <= 1) {
     GemmCoords g3 = gc;
     g3.K = b.kp; g3.b_kp = 0; g3.b_terms = 0; g3.b_evict_last = 1;
     static const int bk_knob = getenv("PVCR_SPLIT3_STORE_BK") ? atoi(getenv("PVCR_SPLIT3_STORE_BK")) : 64;
@@ -270,7 +270,19 @@ __global__ void __launch_bounds__(128) argmax_parts_kernel(const float* __restri
     if (next) next[row] = mi;
   }
 }
-size_t gemm_argmax_scratch(int M, int N) { return (size_t)M * cdiv(N, 128) * 2 * (sizeof(float) + sizeof(int)) + 256; }
+int gemv_f32_parts(int rows);
+size_t gemm_argmax_scratch(int M, int N) {
+  const int parts = cdiv(N, 128) * 2 > gemv_f32_parts(N) ? cdiv(N, 128) * 2 : gemv_f32_parts(N);
+  return (size_t)M * parts * (sizeof(float) + sizeof(int)) + 256;
+}
+int argmax_combine(const float* pmax, const int* pidx, int R, int nparts, long long* out, long long out_stride, long long* next,
+                   cudaStream_t st) {
+  { LaunchScope ls_(KC_LOSS, st);
+    argmax_parts_kernel<<<cdiv(R, 4), 128, 0, st>>>(pmax, pidx, R, nparts, out, out_stride, next);
+  }
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  return PVCR_OK;
+}
 // logits (nullable) [M, ldc] = A B^T + bias;  out[row * out_stride] = next[row] = argmax_n.  scratch: gemm_argmax_scratch bytes.
 // out == nullptr: the combine pass is left to the consumer (gru_gate_fwd folds it into the next step's gate kernel);
 // parts (nullable) receives where the (max, index) partials are and how many there are per row.
@@ -289,13 +301,15 @@ int gemm_argmax(const OperandView& a, const OperandView& b, int M, int N, int Kc
   // bf16x3 with compact W_v planes: the split3 kernel loads every term block once per K chunk (half the L2 -> SM traffic of
   // walking the six virtual planes) on 160-column tiles (144 CTAs for Vc = 23 000).  A/B knob: PVCR_ARGMAX_SPLIT3=0 / 128.
   static const int s3_knob = getenv("PVCR_ARGMAX_SPLIT3") ? atoi(getenv("PVCR_ARGMAX_SPLIT3")) : 128;
-  const bool s3 = s3_knob != 0 && b.kp && b.terms == 3 && Kcat == 6 * b.kp && bn_knob == 0;
+  // (one row tile only: beyond 128 rows the product turns compute-bound -- B = 1024 decodes 103 k captions/s on the generic
+  // 256-column tiles, 90 k on this kernel -- and the wide tiles re-read less of A)
+  const bool s3 = s3_knob != 0 && b.kp && b.terms == 3 && Kcat == 6 * b.kp && bn_knob == 0 && M <= GEMM_BM;
   const int nparts = s3 ? (s3_knob == 128 ? cdiv(N, 128) * 2 : cdiv(N, 160)) : cdiv(N, bn) * 2;
   // L2 policy of the W_v loads: 70 MB of planes do not stay in L2 from one step to the next anyway (measured: 73 MB of DRAM
   // reads per launch with any policy), so the split3 kernel, which reads every byte once, streams them evict_first and leaves
   // the L2 to what the other half of the step re-reads (projected frames, keys); the generic kernel re-reads planes within a
-  // launch and keeps evict_last.  PVCR_DECODE_WV_HINT = 0 / 1 / 2 overrides.
-  gc.b_evict_last = wv_hint >= 0 ? wv_hint : (s3 ? 2 : 1);
+  // launch and gives no hint (evict_last measured 1 % slower there).  PVCR_DECODE_WV_HINT = 0 / 1 / 2 overrides.
+  gc.b_evict_last = wv_hint >= 0 ? wv_hint : (s3 ? 2 : 0);
   EpiArgmax epi{};
   epi.C = logits; epi.ldc = ldc; epi.bias = bias; epi.M = M; epi.N = N; epi.nparts = nparts;
   epi.pmax = reinterpret_cast<float*>(scratch);

@@ -192,6 +192,24 @@ struct GruF32Fwd {
   unsigned* counters;                          // >= 32 * ceil(B/32), zeroed by the launcher
   long long* dbg = nullptr;                    // phase timestamps (tuning aid)
 };
+// row-streaming fp32 product for decoding <= 4 videos (gemv_f32.cu): out[b, j] = x[b, :] . W[j, :] (+ bias[j]) over the rows of
+// w0 stacked on w1; arg-max mode (pmax / pidx set) leaves gemv_f32_parts(rows) (max, first index) partials per video
+struct GemvF32 {
+  int B, K;
+  const float* x; long long x_ld;
+  const float* w0; long long w0_ld; int rows0;
+  const float* w1; long long w1_ld; int rows1;
+  const float* bias;
+  float* out; long long out_ld;          // nullable in arg-max mode
+  float* pmax; int* pidx;                // [B][parts]
+  int stream;                            // weights read once per launch and too large for L2: evict-first loads
+};
+bool gemv_f32_eligible(int B, int K);
+int gemv_f32_parts(int rows);
+int gemv_f32(const GemvF32& p, cudaStream_t st);
+// arg-max over per-row (max, index) partials (gemm.cu): out[row * out_stride] = next[row] = index
+int argmax_combine(const float* pmax, const int* pidx, int R, int nparts, long long* out, long long out_stride, long long* next,
+                   cudaStream_t st);
 bool gru_f32_persist_eligible(int B, int H);
 int gru_f32_persist_fwd(const GruF32Fwd& p, cudaStream_t st);
 

@@ -666,7 +666,9 @@ int s2vtatt_greedy_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const flo
   // W_c ctx = sum_n alpha_n (W_c enc_n): the context projection is hoisted to ONE [B N, H] x [H, 3H] GEMM per batch and the
   // attention kernel sums the projected frames -- no context vector, no per-step GEMM behind the attention
   static const bool pc_off = getenv("PVCR_NO_DECODE_PC") != nullptr;                 // A/B knob
-  const bool use_pc = !pc_off && attn_fwd_projected_ok(N, H, H3);
+  // (only while the projected frames, B N 3H fp32, stay L2-resident next to the keys: 31 MB at B = 128; at B = 512 they would
+  // be re-read from HBM every step: 80 k captions/s instead of 81 k without, 90 k instead of 103 k at B = 1024)
+  const bool use_pc = !pc_off && attn_fwd_projected_ok(N, H, H3) && (size_t)B * N * H3 * sizeof(float) <= ((size_t)40 << 20);
   if (use_pc) PVCR_TRY(gemm_planes(w.enc_a.view(), gw.wc_c.view(), BN, H3, (int)w.enc_a.ld, gw.pc, H3, nullptr, 0, st));
   float* hs = gw.hs;
   // Step i: [q | gh] = [W_q; W_hh] h_{i-1} -> attention -> W_c ctx   (needs h_{i-1} only)
@@ -676,12 +678,26 @@ int s2vtatt_greedy_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const flo
   // The chain gates -> [q | gh] product -> attention is launched programmatically (PdlScope): each kernel's launch latency
   // and prologue overlap the tail of its predecessor.  A/B knob: PVCR_NO_DECODE_PDL.
   static const bool pdl_off = getenv("PVCR_NO_DECODE_PDL") != nullptr;
+  // A handful of videos (B <= 4): the per-step products are matrix-vector products, taken from the fp32 parameters on the
+  // CUDA cores (gemv_f32.cu: 4 bytes per weight and step instead of three bf16 terms through 128-row tiles).  Knob: PVCR_NO_DECODE_GEMV.
+  static const bool gemv_off = getenv("PVCR_NO_DECODE_GEMV") != nullptr;
+  const bool small = !gemv_off && gemv_f32_eligible(B, H) && h0.f_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(h0.f) & 15) == 0;
   auto recurrent_half = [&](int i, cudaStream_t s) -> int {
-    PdlScope pdl(!pdl_off && i > 0);
+    PdlScope pdl(!pdl_off && i > 0 && !small);
     OperandView hprev_a = (i == 0)
         ? OperandView{const_cast<bf16*>(h0.a), h0.a_ld, 0, B, 1}
         : OperandView{w.hs_a.ptr + (long long)(i - 1) * w.hs_a.ld, (long long)L * w.hs_a.ld, 0, B, 1};
-    PVCR_TRY(gemm_planes(hprev_a, gw.wcat_c.view(), B, H4, (int)w.hs_a.ld, w.g1_all, H4, nullptr, 0, s));
+    if (small) {
+      GemvF32 q{};
+      q.B = B; q.K = H;
+      q.x = i == 0 ? h0.f : gw.hs + (long long)(i - 1) * H; q.x_ld = i == 0 ? h0.f_ld : (long long)L * H;
+      q.w0 = p.att_wq; q.w0_ld = H; q.rows0 = H;
+      q.w1 = p.dec_w_hh; q.w1_ld = H; q.rows1 = H3;
+      q.out = w.g1_all; q.out_ld = H4;
+      PVCR_TRY(gemv_f32(q, s));
+    } else {
+      PVCR_TRY(gemm_planes(hprev_a, gw.wcat_c.view(), B, H4, (int)w.hs_a.ld, w.g1_all, H4, nullptr, 0, s));
+    }
     AttnFwdArgs at{};
     at.B = B; at.N = N; at.H = H;
     at.q = w.g1_all; at.q_ld = H4; at.pk = w.pk; at.enc = w.enc; at.v = p.att_v;
@@ -728,6 +744,20 @@ int s2vtatt_greedy_impl(const PvcrDims& d, const PvcrS2vtAttParams& p, const flo
     const bool combine_here = !fold || i + 1 == L;
     OperandView wv_v = gw.wv.view();
     wv_v.blocked = gw.wv_blocked;
+    if (small) {
+      GemvF32 q{};
+      q.B = B; q.K = H;
+      q.x = hs + (long long)i * H; q.x_ld = (long long)L * H;
+      q.w0 = p.out_w; q.w0_ld = H; q.rows0 = Vc;
+      q.bias = p.out_b;
+      q.out = logits ? logits + (long long)i * Vc : nullptr; q.out_ld = (long long)L * Vc;
+      const int np = gemv_f32_parts(Vc);
+      q.pmax = reinterpret_cast<float*>(gw.argmax_scratch); q.pidx = reinterpret_cast<int*>(q.pmax + (size_t)B * np);
+      q.stream = 1;
+      PVCR_TRY(gemv_f32(q, lane));
+      parts.pmax = q.pmax; parts.pidx = q.pidx; parts.nparts = np;
+      if (combine_here) PVCR_TRY(argmax_combine(q.pmax, q.pidx, B, np, ids + i, L, gw.words, lane));
+    } else
     PVCR_TRY(gemm_argmax(h_a, wv_v, B, Vc, (int)w.hs_a.ld, p.out_b, logits ? logits + (long long)i * Vc : nullptr,
                          (long long)L * Vc, combine_here ? ids + i : nullptr, L, gw.words, gw.argmax_scratch, lane, &parts));
     if (lane != st) PVCR_TRY(side_join_lane(st, 0));
