@@ -184,6 +184,15 @@ int gemm_store(const OperandView& a, const OperandView& b, const GemmCoords& gc,
     if (bk_knob == 32) return launch_gemm_split3<64, EpiStore, 4, 32>(a, b, g3, b.kp, epi, stream);
     return launch_gemm_split3<64, EpiStore, 4>(a, b, g3, b.kp, epi, stream);
   }
+  // several row tiles of a bf16x3 product on compact planes (decoding B > 128: [q | gh], W_c ctx): 256-column tiles, 32-column
+  // K chunks -- half the operand traffic per tile of the six-plane walk.  A/B knob: PVCR_NO_SPLIT3_STORE_BIG=1.
+  static const bool s3_big_off = getenv("PVCR_NO_SPLIT3_STORE_BIG") != nullptr;
+  if (!s3_off && !s3_big_off && b.kp && b.terms == 3 && gc.K == 6 * b.kp && grid_z == 1 && gc.M > GEMM_BM && gc.N >= 256 &&
+      gc.k_splits <= 1) {
+    GemmCoords g3 = gc;
+    g3.K = b.kp; g3.b_kp = 0; g3.b_terms = 0;
+    return launch_gemm_split3<256, EpiStore, 8, 32>(a, b, g3, b.kp, epi, stream);
+  }
   const long long tiles256 = (long long)cdiv(gc.N, 256) * cdiv(gc.M, GEMM_BM) * grid_z;
   static const bool no_persist = getenv("PVCR_NO_PERSIST_GEMM") != nullptr;
   if (gc.N >= 256 && tiles256 >= 64 && !no_persist)
@@ -303,13 +312,19 @@ int gemm_argmax(const OperandView& a, const OperandView& b, int M, int N, int Kc
   static const int s3_knob = getenv("PVCR_ARGMAX_SPLIT3") ? atoi(getenv("PVCR_ARGMAX_SPLIT3")) : 128;
   // (one row tile only: beyond 128 rows the product turns compute-bound -- B = 1024 decodes 103 k captions/s on the generic
   // 256-column tiles, 90 k on this kernel -- and the wide tiles re-read less of A)
-  const bool s3 = s3_knob != 0 && b.kp && b.terms == 3 && Kcat == 6 * b.kp && bn_knob == 0 && M <= GEMM_BM;
-  const int nparts = s3 ? (s3_knob == 128 ? cdiv(N, 128) * 2 : cdiv(N, 160)) : cdiv(N, bn) * 2;
+  // 256: 256-column tiles on 32-column K chunks (3 stages of 72 KB): the least operand traffic per FLOP of all variants
+  // (1.15 MB per 128 x 256 tile against 2.3 MB on the generic kernel) -- for several row tiles (B > 128), where the step is
+  // bound by what an SM can take in, and as an A/B variant at B <= 128
+  static const int s3_big = getenv("PVCR_ARGMAX_SPLIT3_BIG") ? atoi(getenv("PVCR_ARGMAX_SPLIT3_BIG")) : 1;
+  const bool s3_ok = s3_knob != 0 && b.kp && b.terms == 3 && Kcat == 6 * b.kp && bn_knob == 0;
+  const bool s3_256 = s3_ok && (s3_knob == 256 || (M > GEMM_BM && s3_big));
+  const bool s3 = s3_ok && (M <= GEMM_BM || s3_256);
+  const int nparts = s3 ? (s3_256 ? cdiv(N, 256) * 2 : (s3_knob == 128 ? cdiv(N, 128) * 2 : cdiv(N, 160))) : cdiv(N, bn) * 2;
   // L2 policy of the W_v loads: 70 MB of planes do not stay in L2 from one step to the next anyway (measured: 73 MB of DRAM
   // reads per launch with any policy), so the split3 kernel, which reads every byte once, streams them evict_first and leaves
   // the L2 to what the other half of the step re-reads (projected frames, keys); the generic kernel re-reads planes within a
   // launch and gives no hint (evict_last measured 1 % slower there).  PVCR_DECODE_WV_HINT = 0 / 1 / 2 overrides.
-  gc.b_evict_last = wv_hint >= 0 ? wv_hint : (s3 ? 2 : 0);
+  gc.b_evict_last = wv_hint >= 0 ? wv_hint : (s3 && M <= GEMM_BM ? 2 : 0);      // (row tiles side by side share a W_v tile)
   EpiArgmax epi{};
   epi.C = logits; epi.ldc = ldc; epi.bias = bias; epi.M = M; epi.N = N; epi.nparts = nparts;
   epi.pmax = reinterpret_cast<float*>(scratch);
@@ -324,9 +339,10 @@ int gemm_argmax(const OperandView& a, const OperandView& b, int M, int N, int Kc
     // 128-column tiles on at most 90 CTAs (two tiles each at Vc = 23 000): the other SMs run the recurrent half of the next
     // step next to it (measured: 144 CTAs of 160 columns 2.22 / 2.04 ms per batch, 90 CTAs of 128 columns 2.13 / 1.86)
     static const int cta_knob = getenv("PVCR_ARGMAX_CTAS") ? atoi(getenv("PVCR_ARGMAX_CTAS")) : 90;
-    CtaCap cap(cta_knob > 0 ? cta_knob : gemm_cta_cap());
+    CtaCap cap(M > GEMM_BM ? gemm_cta_cap() : (cta_knob > 0 ? cta_knob : gemm_cta_cap()));
     static const int bk_knob = getenv("PVCR_ARGMAX_BK") ? atoi(getenv("PVCR_ARGMAX_BK")) : 64;
-    if (s3_knob == 128 && bk_knob == 32) PVCR_TRY((launch_gemm_split3<128, EpiArgmax, 8, 32>(a, b, g3, b.kp, epi, st)));
+    if (s3_256) PVCR_TRY((launch_gemm_split3<256, EpiArgmax, 8, 32>(a, b, g3, b.kp, epi, st)));
+    else if (s3_knob == 128 && bk_knob == 32) PVCR_TRY((launch_gemm_split3<128, EpiArgmax, 8, 32>(a, b, g3, b.kp, epi, st)));
     else if (s3_knob == 128) PVCR_TRY((launch_gemm_split3<128, EpiArgmax, 8>(a, b, g3, b.kp, epi, st)));
     else PVCR_TRY((launch_gemm_split3<160, EpiArgmax, 4>(a, b, g3, b.kp, epi, st)));
   }
