@@ -237,6 +237,7 @@ struct Layer {                 // one Conv3x3 + BN + ReLU block
   Planes xp;                   // its bf16 planes (A role), Rtot rows
   Planes w[9];                 // taps, B role [Co, Ci]
   Planes wT[9];                // transposed taps [Ci, Co] (B role of dX = dY W)   (backward)
+  Planes w_all, wT_all;        // single-plane mode: the nine taps side by side along K ([Co, 9 Ci], [Ci, 9 Co]) for the fused launch
   float* wtaps;                // [9][Co, Ci] fp32
   float* y;                    // [R, Co] fp32 conv output (pre-BN)
   float *mean, *invstd;        // [Co]
@@ -256,6 +257,8 @@ void carve_layer(Arena& a, const Geo& g, int Ci, int Co, int ns, Layer& l) {
   l.xp = alloc_planes(a, (int)g.Rtot, Ci, ns);
   for (int s = 0; s < 9; ++s) l.w[s] = alloc_planes(a, Co, Ci, ns);
   for (int s = 0; s < 9; ++s) l.wT[s] = alloc_planes(a, Ci, Co, ns);
+  l.w_all = alloc_planes(a, Co, 9 * Ci, 1);
+  l.wT_all = alloc_planes(a, Ci, 9 * Co, 1);
   l.wtaps = a.alloc<float>((size_t)9 * Co * Ci);
   l.y = a.alloc<float>((size_t)g.R * Co);
   l.mean = a.alloc<float>(Co); l.invstd = a.alloc<float>(Co);
@@ -278,6 +281,12 @@ void carve_front(Arena& a, int I, int K, int F, int H, int ns, FrontWs& w) {
 }
 
 int off_of(const Geo& g, int s) { return (s / 3 - 1) * g.Kp + (s % 3 - 1); }
+// single-plane (bf16) mode with 64-aligned channel counts: the nine taps of a convolution in ONE launch, accumulated in TMEM
+// (gemm_taps); otherwise nine launches accumulating through the fp32 output.  A/B knob: PVCR_NO_CONV_FUSED_TAPS=1.
+bool fused_taps(int ns, int Ci, int Co) {
+  static const bool off = getenv("PVCR_NO_CONV_FUSED_TAPS") != nullptr;
+  return !off && ns == 1 && Ci % 64 == 0 && Co % 64 == 0 && Co >= 256 && Ci >= 256;
+}
 
 // y[R, Co] = bias + sum_s X[. + off_s] W_s^T
 int conv_forward(const Geo& g, const Layer& l, const float* w, const float* bias, int ns, cudaStream_t st) {
@@ -285,6 +294,17 @@ int conv_forward(const Geo& g, const Layer& l, const float* w, const float* bias
   conv_weight_taps_kernel<<<grid_for(n), 256, 0, st>>>(w, l.wtaps, n, l.Co, l.Ci, 1);
   PVCR_CUDA_CHECK(cudaGetLastError());
   PVCR_TRY(stage(l.xpf, l.Ci, (int)g.Rtot, l.Ci, l.xp, 0, nullptr, NO_DROPOUT, st));
+  if (fused_taps(ns, l.Ci, l.Co)) {
+    int off[9];
+    for (int s = 0; s < 9; ++s) {
+      // tap s -> columns [s Ci, (s + 1) Ci) of the side-by-side weight plane
+      PVCR_TRY(cast_split(l.wtaps + (size_t)s * l.Co * l.Ci, l.Ci, l.Co, l.Ci, l.w_all.ptr + (size_t)s * l.Ci, l.w_all.ld, l.Ci, 1, 1,
+                          nullptr, NO_DROPOUT, st));
+      off[s] = g.G + off_of(g, s);
+    }
+    const OperandView av{l.xp.ptr, l.xp.ld, 0, (int)g.Rtot, 1};
+    return gemm_taps(av, l.w_all.view(), (int)g.R, l.Co, l.Ci, 9, off, l.y, l.Co, bias, st);
+  }
   for (int s = 0; s < 9; ++s) {
     PVCR_TRY(prep_weight(l.wtaps + (size_t)s * l.Co * l.Ci, l.Ci, l.Co, l.Ci, l.w[s], st));
     const OperandView av{l.xp.ptr + ((long long)g.G + off_of(g, s)) * l.xp.ld, l.xp.ld, 0, (int)g.R, 1};
@@ -358,6 +378,15 @@ int conv_backward(Arena& a, const Geo& g, const Layer& l, int ns, float* dw, flo
   PVCR_CUDA_CHECK(cudaGetLastError());
   if (dx_padded) {
     // dX[r] = sum_s dY[r - off_s] W_s   (B operand: transposed tap planes [Ci, Co], contraction over Co)
+    if (fused_taps(ns, Co, Ci)) {
+      int off[9];
+      for (int s = 0; s < 9; ++s) {
+        PVCR_TRY(prep_weight_T(l.wtaps + (size_t)s * Co * Ci, Ci, Co, Ci, l.wT_all, s * Co, 0, st));
+        off[s] = g.G - off_of(g, s);
+      }
+      const OperandView dv{dyp.ptr, dyp.ld, 0, (int)g.Rtot, 1};
+      PVCR_TRY(gemm_taps(dv, l.wT_all.view(), (int)g.R, Ci, Co, 9, off, dx_padded, Ci, nullptr, st));
+    } else
     for (int s = 0; s < 9; ++s) {
       PVCR_TRY(prep_weight_T(l.wtaps + (size_t)s * Co * Ci, Ci, Co, Ci, l.wT[s], 0, 1, st));
       const OperandView dv{dyp.ptr + ((long long)g.G - off_of(g, s)) * dyp.ld, dyp.ld, 0, (int)g.R, 1};

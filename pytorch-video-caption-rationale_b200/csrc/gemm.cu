@@ -193,6 +193,10 @@ int gemm_store(const OperandView& a, const OperandView& b, const GemmCoords& gc,
     g3.K = b.kp; g3.b_kp = 0; g3.b_terms = 0;
     return launch_gemm_split3<256, EpiStore, 8, 32>(a, b, g3, b.kp, epi, stream);
   }
+  if (gc.a_taps) {       // shifted-row taps: persistent kernel only (its producer maps k-blocks to (tap, column block))
+    PVCR_REQUIRE(gc.N >= 256 && grid_z == 1 && gc.K % (gc.a_taps * GEMM_BK) == 0, "gemm (taps): N=%d K=%d taps=%d", gc.N, gc.K, gc.a_taps);
+    return launch_gemm_tn_persistent<256, 4, EpiStore>(a, b, gc, 1, epi, stream);
+  }
   const long long tiles256 = (long long)cdiv(gc.N, 256) * cdiv(gc.M, GEMM_BM) * grid_z;
   static const bool no_persist = getenv("PVCR_NO_PERSIST_GEMM") != nullptr;
   if (gc.N >= 256 && tiles256 >= 64 && !no_persist)

@@ -39,6 +39,12 @@ struct GemmCoords {
   // column  term(p) * b_kp + off,  term(p) = (b_terms >> 2p) & 3.  b_kp == 0: B is stored as it is multiplied.
   int b_kp = 0;
   unsigned b_terms = 0;
+  // shifted-row taps (persistent kernel, K-major A): the K range is a_taps blocks of a_tap_kb k-blocks; block s reads the A
+  // columns of ONE tap-width matrix at rows m0 + a_tap_off[s] -- a 3 x 3 convolution over a flat zero-padded channels-last
+  // layout is nine row-shifted products accumulated in the SAME TMEM tile (conv.cu), no im2col and no fp32 accumulation
+  // through global memory between the taps
+  int a_taps = 0, a_tap_kb = 0;
+  int a_tap_off[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   int b_blocked = 0;     // split3 kernel: B is K-blocked ([term * b_blocked + chunk][row][64], b_blocked = chunks per term)
   int b_prefetch = 0;    // split3 kernel: request every B block of a CTA's tiles into L2 up front (B streamed from HBM)
   int b_evict_last = 0;  // persistent / split3 kernel, K-major B: L2 hint of the B loads (1 = evict_last: re-read by the next
@@ -224,6 +230,9 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           if (A_MN) {
 #pragma unroll
             for (int i = 0; i < GEMM_BM / 64; ++i) tma_load_3d(sa + i * 8192, &tmA, &full_bar[s], m0 + 64 * i, kb * GEMM_BK, az);
+          } else if (gc.a_taps) {
+            const int tap = kb / gc.a_tap_kb;
+            tma_load_3d(sa, &tmA, &full_bar[s], (kb - tap * gc.a_tap_kb) * GEMM_BK, m0 + gc.a_tap_off[tap], az);
           } else {
             tma_load_3d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m0, az);
           }
@@ -935,7 +944,10 @@ int launch_gemm_tn_persistent(const OperandView& a, const OperandView& b, const 
   PVCR_REQUIRE(gc.K > 0 && gc.K % GEMM_BK == 0, "gemm: K=%d must be a positive multiple of %d", gc.K, GEMM_BK);
   PVCR_REQUIRE(gc.M > 0 && gc.N > 0 && grid_z > 0, "gemm: empty problem M=%d N=%d z=%d", gc.M, gc.N, grid_z);
   CUtensorMap ta, tb;
-  if (A_MN) PVCR_TRY(make_tensor_map_mn(&ta, a, gc.M)); else PVCR_TRY(make_tensor_map(&ta, a, gc.K, GEMM_BM));
+  if (A_MN) PVCR_TRY(make_tensor_map_mn(&ta, a, gc.M));
+  else PVCR_TRY(make_tensor_map(&ta, a, gc.a_taps ? gc.a_tap_kb * GEMM_BK : gc.K, GEMM_BM));
+  PVCR_REQUIRE(!gc.a_taps || (!A_MN && gc.k_splits <= 1 && gc.a_taps <= 9 && gc.K == gc.a_taps * gc.a_tap_kb * GEMM_BK),
+               "gemm: shifted-row taps need a K-major A, no split-K and K = taps x tap width");
   if (B_MN) PVCR_TRY(make_tensor_map_mn(&tb, b, gc.N)); else PVCR_TRY(make_tensor_map(&tb, b, b.kp ? b.kp * b.terms : gc.K, BN));
   PVCR_REQUIRE((b.kp != 0) == (gc.b_kp != 0) && !(B_MN && b.kp), "gemm: compact B planes need GemmCoords::b_kp (K-major B only)");
   auto kern = gemm_tn_persistent_kernel<BN, STAGES, Epi, A_MN, B_MN, EW>;

@@ -119,6 +119,17 @@ inline int gemm_planes(const OperandView& a, const OperandView& b, int M, int N,
   return gemm_store(a, b, gc, 1, C, ldc, 0, bias, 0, accumulate, st);
 }
 
+// C[M,N] (ldc) = sum_s A[. + off[s]] * B_s^T (+bias): `a` is ONE K-major matrix of Kt columns (all its rows: the shifted reads
+// stay inside a.rows, rows outside read as zero), `b` holds the taps side by side along K ([N, taps * Kt]); off[s] is the row
+// of `a` that output row 0 reads for tap s.  One launch, the taps accumulate in TMEM (gemm_sm100.cuh: GemmCoords::a_taps).
+inline int gemm_taps(const OperandView& a, const OperandView& b, int M, int N, int Kt, int taps, const int* off, float* C,
+                     long long ldc, const float* bias, cudaStream_t st) {
+  GemmCoords gc{M, N, taps * Kt, 0, 0, 0, 0};
+  gc.a_taps = taps; gc.a_tap_kb = Kt / GEMM_BK;
+  for (int s = 0; s < taps; ++s) gc.a_tap_off[s] = off[s];
+  return gemm_store(a, b, gc, 1, C, ldc, 0, bias, 0, 0, st);
+}
+
 static const Dropout NO_DROPOUT = {0.f, 0ull, 0ull};
 
 // fp32 [R,C] -> planes (role A or B), optional row scale / dropout

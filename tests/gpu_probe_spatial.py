@@ -57,7 +57,7 @@ out["ours"] = {"ms_per_step": ms, "videos_per_s": B / (ms / 1e3), "loss": float(
 torch.cuda.empty_cache()
 try:
     from oracle import reference_runner as R
-    if R.available():
+    if R.available() and os.environ.get("PVCR_PROBE_NO_REF") is None:
         R.set_device("cuda")
         ref = R.modules()["model.SpatialNet"].SpatialNet(R.FakeGlove(Vc, E), 0.2, H, F, L, "s2vt-att").cuda().train()
         tu = R.modules()["train_utils"]

@@ -50,3 +50,11 @@ def _run_decode(env):
 def test_decode_variant_ids_bit_exact(env):
     """Greedy ids stay bit-exact against the reference fixture (full cfg5 size) and the oracle under every decode-loop knob."""
     _run_decode(env)
+
+
+def test_conv_taps_one_launch_per_tap_variant():
+    """The nine-launch convolution (what the split-precision modes and odd channel counts use) under the single-plane mode."""
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_spatial_front.py"), "-m", "gpu", "-x", "-q", "-k",
+                        "conv_bn_relu_front"], env=dict(os.environ, PVCR_NO_CONV_FUSED_TAPS="1"), capture_output=True, text=True,
+                       timeout=1200, cwd=os.path.dirname(HERE))
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-2000:])
