@@ -361,7 +361,16 @@ int conv_backward(Arena& a, const Geo& g, const Layer& l, int ns, float* dw, flo
   Planes dyp = alloc_planes(a, (int)g.Rtot, Co, ns);
   if (a.failed) { set_last_error("spatial front backward: workspace too small (dY planes)"); return PVCR_ERR_WORKSPACE; }
   PVCR_TRY(stage(l.dy, Co, (int)g.Rtot, Co, dyp, 0, nullptr, NO_DROPOUT, st));
-  // d W_s = dY^T X[. + off_s]: contraction over the R rows
+  // d W_s = dY^T X[. + off_s]: contraction over the R rows.  Single-plane mode with more output tiles per tap than the split-K
+  // path serves: the nine taps as ONE batched launch (32 tiles per tap on 148 SMs otherwise).  Knob: PVCR_NO_CONV_FUSED_TAPS.
+  const bool dw_batched = fused_taps(ns, Ci, Co) && (long long)cdiv(Co, GEMM_BM) * cdiv(Ci, 256) > 8;
+  if (dw_batched) {
+    int koff[9];
+    for (int s = 0; s < 9; ++s) koff[s] = g.G + off_of(g, s);
+    const OperandView dv{dyp.ptr + (long long)g.G * dyp.ld, dyp.ld, 0, (int)g.R, 1};
+    const OperandView xv{l.xp.ptr, l.xp.ld, 0, (int)g.Rtot, 1};
+    PVCR_TRY(gemm_mn_taps_store(dv, xv, Co, Ci, (int)g.R, 9, koff, l.dwtaps, Ci, (long long)Co * Ci, st));
+  } else
   for (int s = 0; s < 9; ++s) {
     float* dws = l.dwtaps + (size_t)s * Co * Ci;
     if (ns == 1) {

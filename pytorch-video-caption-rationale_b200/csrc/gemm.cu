@@ -152,6 +152,18 @@ int gemm_mn_store(const OperandView& a, const OperandView& b, int M, int N, int 
   return launch_gemm_tn_persistent<256, 4, EpiStore, true, true>(a, b, gc, 1, epi, stream);
 }
 
+// Nine products sharing A:  C_s[M,N] = A^T B[koff[s] + k, :]  (s < taps <= 9), one batched launch (C_s = C + s * c_stride).
+// a: [K rows, M cols], b: [>= max koff + K rows, N cols], both row-major bf16; rows of `a` past its end read as zero.
+int gemm_mn_taps_store(const OperandView& a, const OperandView& b, int M, int N, int K, int taps, const int* koff, float* C,
+                       long long ldc, long long c_stride, cudaStream_t stream) {
+  PVCR_REQUIRE(taps >= 1 && taps <= 9, "gemm_mn_taps_store: %d taps", taps);
+  EpiStore epi{C, ldc, c_stride, nullptr, 0, 0, M, N, 0, 1};
+  GemmCoords gc{M, N, (int)round_up(K, GEMM_BK), 0, 0, 0, 0};
+  gc.b_z_koff = 1;
+  for (int s = 0; s < taps; ++s) gc.a_tap_off[s] = koff[s];
+  return launch_gemm_tn_persistent<256, 4, EpiStore, true, true>(a, b, gc, taps, epi, stream);
+}
+
 // C[M,N] (+)= A B for bf16 A [M, K] (K-major) and row-major B [K rows, N cols] (MN-major): data gradients dX = dY W
 // straight from the forward weight planes.  K = rows of b actually present (rows beyond read as zero).
 int gemm_kn_store(const OperandView& a, const OperandView& b, int M, int N, int K, float* C, long long ldc,

@@ -45,6 +45,9 @@ struct GemmCoords {
   // through global memory between the taps
   int a_taps = 0, a_tap_kb = 0;
   int a_tap_off[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  // b_z_koff (persistent kernel, MN-major B, batched over z <= 9): slab z reads B's k rows at kb * 64 + a_tap_off[z] -- the nine
+  // weight-gradient products d W_s = dY^T X[. + off_s] of a convolution as ONE batched launch (9 x the tiles of one tap)
+  int b_z_koff = 0;
   int b_blocked = 0;     // split3 kernel: B is K-blocked ([term * b_blocked + chunk][row][64], b_blocked = chunks per term)
   int b_prefetch = 0;    // split3 kernel: request every B block of a CTA's tiles into L2 up front (B streamed from HBM)
   int b_evict_last = 0;  // persistent / split3 kernel, K-major B: L2 hint of the B loads (1 = evict_last: re-read by the next
@@ -239,7 +242,8 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           if (B_MN) {
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i)
-              tma_load_3d(sa + SM::A_BYTES + i * 8192, &tmB, &full_bar[s], n0 + 64 * i, kb * GEMM_BK, bz);
+              tma_load_3d(sa + SM::A_BYTES + i * 8192, &tmB, &full_bar[s], n0 + 64 * i,
+                          kb * GEMM_BK + (gc.b_z_koff ? gc.a_tap_off[z] : 0), bz);
           } else if (gc.b_evict_last) {
             tma_load_3d_hint(sa + SM::A_BYTES, &tmB, &full_bar[s], gc.b_col(kb * GEMM_BK), n0, bz, b_policy);
           } else {

@@ -74,6 +74,8 @@ inline Planes alloc_planes(Arena& a, int rows, int K, int nsplit) {
   return p;
 }
 
+int gemm_mn_taps_store(const OperandView& a, const OperandView& b, int M, int N, int K, int taps, const int* koff, float* C,
+                       long long ldc, long long c_stride, cudaStream_t stream);
 int gemm_store(const OperandView& a, const OperandView& b, const GemmCoords& gc, int grid_z, float* C, long long ldc,
                long long c_zstride, const float* bias, long long bias_zstride, int accumulate, cudaStream_t stream);
 

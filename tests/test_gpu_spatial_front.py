@@ -17,7 +17,8 @@ def _stack(F, H):
 
 @pytest.mark.parametrize("precision,tol", [("bf16x3", 3e-4), ("bf16", 8e-2)])
 # (4, 256, 256, 6): channel counts served by the fused nine-tap launch of the single-plane mode (csrc/conv.cu: fused_taps)
-@pytest.mark.parametrize("I,F,H,K", [(6, 24, 32, 3), (10, 128, 64, 6), (7, 72, 48, 5), (4, 256, 256, 6)])
+# (2, 1024, 512, 4): enough weight-gradient tiles per tap for the batched nine-tap d W launch
+@pytest.mark.parametrize("I,F,H,K", [(6, 24, 32, 3), (10, 128, 64, 6), (7, 72, 48, 5), (4, 256, 256, 6), (2, 1024, 512, 4)])
 def test_conv_bn_relu_front_matches_torch(I, F, H, K, precision, tol):
     from pvcr_b200 import functional as F_
     torch.manual_seed(I * 100 + K)
