@@ -549,6 +549,190 @@ __global__ void __launch_bounds__(256) spatial_attn_bwd_kernel(int Kc, int H, in
   }
 }
 
+
+// ---- vectorised variants (H a multiple of 256 up to 1024, Fv a multiple of 4, 16-byte aligned rows) ---------------------------
+// The kernels above walk their cells with one 4-byte load in flight per thread and dependent iteration; at cfg4 (36 cells, keys
+// 512 wide, values 2048 wide, 369 KB per video and frame, every byte from HBM) that ran at 0.7 TB/s.  Here every thread issues
+// the 16-byte loads of up to 10-12 cells before it uses them, scores are reduced by warp shuffles (as attn_fwd_vec_kernel).
+constexpr int SAV_NC = 10;       // cells per thread and pass in the score / key phases
+constexpr int SAV_CC = 12;       // cells per pass in the value phases
+__global__ void __launch_bounds__(256) spatial_attn_fwd_vec_kernel(int Kc, int H, int Fv, const float* __restrict__ q, long long q_ld,
+                                                                   const float* __restrict__ pk, long long pk_bs,
+                                                                   const float* __restrict__ feats, long long feats_bs,
+                                                                   const float* __restrict__ v, float* __restrict__ alpha,
+                                                                   float* __restrict__ ctx) {
+  extern __shared__ float sm[];
+  const int DG = H >> 3, FG = 256 / DG, WPF = DG >> 5;          // dim groups of 8, cell groups, warps per cell group
+  float* sP = sm;                  // [Kc][WPF]
+  float* sa = sP + Kc * WPF;       // [Kc]
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, dg = tid % DG, fg = tid / DG, d0 = dg * 8;
+  const float4* q4 = reinterpret_cast<const float4*>(q + (long long)b * q_ld + d0);
+  const float4* v4 = reinterpret_cast<const float4*>(v + d0);
+  const float4 qa = q4[0], qb = q4[1], va = v4[0], vb = v4[1];
+  const float q8[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+  const float v8[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+  const float* pkb = pk + (long long)b * pk_bs + d0;
+  for (int c0 = 0; c0 < Kc; c0 += FG * SAV_NC) {
+    float4 x[SAV_NC][2];
+#pragma unroll
+    for (int m = 0; m < SAV_NC; ++m) {
+      const int c = c0 + fg + FG * m;
+      x[m][0] = x[m][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < Kc) {
+        const float4* p4 = reinterpret_cast<const float4*>(pkb + (long long)c * H);
+        x[m][0] = __ldg(p4); x[m][1] = __ldg(p4 + 1);
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < SAV_NC; ++m) {
+      const int c = c0 + fg + FG * m;
+      const float p8[8] = {x[m][0].x, x[m][0].y, x[m][0].z, x[m][0].w, x[m][1].x, x[m][1].y, x[m][1].z, x[m][1].w};
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v8[e] * tanhf(q8[e] + p8[e]);
+      s = warp_sum(s);
+      if (lane == 0 && c < Kc) sP[c * WPF + ((dg >> 5))] = s;
+    }
+  }
+  __syncthreads();
+  if (tid < 32) {
+    float mx = -INFINITY;
+    for (int c = lane; c < Kc; c += 32) {
+      float s = 0.f;
+      for (int w = 0; w < WPF; ++w) s += sP[c * WPF + w];
+      sa[c] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float den = 0.f;
+    for (int c = lane; c < Kc; c += 32) { const float e = expf(sa[c] - mx); sa[c] = e; den += e; }
+    den = warp_sum(den);
+    const float inv = 1.f / den;
+    for (int c = lane; c < Kc; c += 32) { const float al = sa[c] * inv; sa[c] = al; alpha[(long long)b * Kc + c] = al; }
+  }
+  __syncthreads();
+  const int F4 = Fv >> 2;
+  const float4* fb = reinterpret_cast<const float4*>(feats + (long long)b * feats_bs);
+  for (int f4 = tid; f4 < F4; f4 += 256) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c0 = 0; c0 < Kc; c0 += SAV_CC) {
+      float4 y[SAV_CC];
+#pragma unroll
+      for (int k = 0; k < SAV_CC; ++k) y[k] = c0 + k < Kc ? __ldcs(fb + (long long)(c0 + k) * F4 + f4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < SAV_CC; ++k) {
+        const float al = c0 + k < Kc ? sa[c0 + k] : 0.f;
+        acc.x += al * y[k].x; acc.y += al * y[k].y; acc.z += al * y[k].z; acc.w += al * y[k].w;
+      }
+    }
+    *reinterpret_cast<float4*>(ctx + (long long)b * Fv + 4 * f4) = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) spatial_attn_bwd_vec_kernel(int Kc, int H, int Fv, const float* __restrict__ dctx,
+                                                                   const float* __restrict__ q, long long q_ld,
+                                                                   const float* __restrict__ pk, long long pk_bs,
+                                                                   const float* __restrict__ feats, long long feats_bs,
+                                                                   const float* __restrict__ v, const float* __restrict__ alpha,
+                                                                   float* __restrict__ dq, float* __restrict__ dpk,
+                                                                   float* __restrict__ dv_part) {
+  extern __shared__ float sm[];
+  const int Q4 = H >> 2, CH = 256 / Q4;                          // 16-byte dim columns, cell groups of the key phase
+  float* sds = sm;                 // [Kc] d alpha -> d score
+  float* sal = sds + Kc;           // [Kc]
+  float* sW = sal + Kc;            // [8][Kc] per-warp partial d alpha
+  float* sR = sW + 8 * Kc + ((4 - ((10 * Kc) & 3)) & 3);        // [2][CH][H] partial dq / dv of the cell groups (16-byte aligned)
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // d alpha[c] = dctx . feats[c]
+  const int F4 = Fv >> 2;
+  const float4* fb = reinterpret_cast<const float4*>(feats + (long long)b * feats_bs);
+  const float4* dc4 = reinterpret_cast<const float4*>(dctx + (long long)b * Fv);
+  for (int c0 = 0; c0 < Kc; c0 += SAV_CC) {
+    float part[SAV_CC];
+#pragma unroll
+    for (int k = 0; k < SAV_CC; ++k) part[k] = 0.f;
+    for (int f4 = tid; f4 < F4; f4 += 256) {
+      const float4 d4 = __ldg(dc4 + f4);
+      float4 y[SAV_CC];
+#pragma unroll
+      for (int k = 0; k < SAV_CC; ++k) y[k] = c0 + k < Kc ? __ldcs(fb + (long long)(c0 + k) * F4 + f4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < SAV_CC; ++k) part[k] += d4.x * y[k].x + d4.y * y[k].y + d4.z * y[k].z + d4.w * y[k].w;
+    }
+#pragma unroll
+    for (int k = 0; k < SAV_CC; ++k) {
+      const float s = warp_sum(part[k]);
+      if (lane == 0 && c0 + k < Kc) sW[warp * Kc + c0 + k] = s;
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < Kc; c += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += sW[w * Kc + c];
+    sds[c] = s;
+    sal[c] = alpha[(long long)b * Kc + c];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float dot = 0.f;
+    for (int c = lane; c < Kc; c += 32) dot += sal[c] * sds[c];
+    dot = warp_sum(dot);
+    for (int c = lane; c < Kc; c += 32) sds[c] = sal[c] * (sds[c] - dot);
+  }
+  __syncthreads();
+  // keys: thread = (4 dims, cell group); cells ch, ch + CH, ...
+  const int d4i = tid % Q4, ch = tid / Q4;
+  const float4 qd = __ldg(reinterpret_cast<const float4*>(q + (long long)b * q_ld) + d4i);
+  const float4 vd = __ldg(reinterpret_cast<const float4*>(v) + d4i);
+  const float4* pkb = reinterpret_cast<const float4*>(pk + (long long)b * pk_bs);
+  float4* dpkb = reinterpret_cast<float4*>(dpk + (long long)b * Kc * H);
+  float4 aq = make_float4(0.f, 0.f, 0.f, 0.f), av = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c0 = ch; c0 < Kc; c0 += CH * SAV_NC) {
+    float4 x[SAV_NC];
+#pragma unroll
+    for (int m = 0; m < SAV_NC; ++m) {
+      const int c = c0 + CH * m;
+      x[m] = c < Kc ? __ldg(pkb + (long long)c * Q4 + d4i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int m = 0; m < SAV_NC; ++m) {
+      const int c = c0 + CH * m;
+      if (c < Kc) {
+        const float ds = sds[c];
+        const float ex = tanhf(qd.x + x[m].x), ey = tanhf(qd.y + x[m].y), ez = tanhf(qd.z + x[m].z), ew = tanhf(qd.w + x[m].w);
+        const float4 g = make_float4(ds * vd.x * (1.f - ex * ex), ds * vd.y * (1.f - ey * ey), ds * vd.z * (1.f - ez * ez),
+                                     ds * vd.w * (1.f - ew * ew));
+        dpkb[(long long)c * Q4 + d4i] = g;
+        aq.x += g.x; aq.y += g.y; aq.z += g.z; aq.w += g.w;
+        av.x += ds * ex; av.y += ds * ey; av.z += ds * ez; av.w += ds * ew;
+      }
+    }
+  }
+  reinterpret_cast<float4*>(sR)[ch * Q4 + d4i] = aq;
+  reinterpret_cast<float4*>(sR)[(CH + ch) * Q4 + d4i] = av;
+  __syncthreads();
+  if (ch == 0) {
+    float4 a = aq, w = av;
+    for (int k = 1; k < CH; ++k) {
+      const float4 a2 = reinterpret_cast<const float4*>(sR)[k * Q4 + d4i], w2 = reinterpret_cast<const float4*>(sR)[(CH + k) * Q4 + d4i];
+      a.x += a2.x; a.y += a2.y; a.z += a2.z; a.w += a2.w;
+      w.x += w2.x; w.y += w2.y; w.z += w2.z; w.w += w2.w;
+    }
+    reinterpret_cast<float4*>(dq + (long long)b * H)[d4i] = a;
+    reinterpret_cast<float4*>(dv_part + (long long)b * H)[d4i] = w;
+  }
+}
+
+static bool spatial_attn_vec_ok(int Kc, int H, int Fv, long long q_ld, long long pk_bs, long long feats_bs, const void* p0,
+                                const void* p1, const void* p2, const void* p3, const void* p4, const void* p5) {
+  static const bool off = getenv("PVCR_NO_VEC_SPATIAL_ATTN") != nullptr;       // A/B knob
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1) | reinterpret_cast<uintptr_t>(p2) |
+                         reinterpret_cast<uintptr_t>(p3) | reinterpret_cast<uintptr_t>(p4) | reinterpret_cast<uintptr_t>(p5);
+  return !off && H % 256 == 0 && H <= 1024 && Fv % 4 == 0 && q_ld % 4 == 0 && pk_bs % 4 == 0 && feats_bs % 4 == 0 && (bits & 15) == 0 &&
+         Kc <= SA_MAX_CELLS;
+}
+
 }  // namespace pvcr
 
 using namespace pvcr;
@@ -558,6 +742,15 @@ extern "C" {
 int pvcr_spatial_attn_fwd(int B, int Kc, int H, int Fv, const float* q, int64_t q_ld, const float* proj_key, int64_t pk_batch_stride,
                           const float* feats, int64_t feats_batch_stride, const float* v, float* alpha, float* ctx, void* stream) {
   if (B <= 0 || Kc <= 0 || Kc > SA_MAX_CELLS || H <= 0 || Fv <= 0) { set_last_error("pvcr_spatial_attn_fwd: B=%d Kc=%d H=%d Fv=%d", B, Kc, H, Fv); return PVCR_ERR_ARG; }
+  if (spatial_attn_vec_ok(Kc, H, Fv, q_ld, pk_batch_stride, feats_batch_stride, q, proj_key, feats, v, ctx, ctx)) {
+    const size_t smem_v = sizeof(float) * ((size_t)Kc * ((H >> 3) >> 5) + Kc);
+    { LaunchScope ls_(KC_ATTN, (cudaStream_t)stream);
+    spatial_attn_fwd_vec_kernel<<<B, 256, smem_v, (cudaStream_t)stream>>>(Kc, H, Fv, q, q_ld, proj_key, pk_batch_stride, feats,
+                                                                         feats_batch_stride, v, alpha, ctx);
+    }
+    PVCR_CUDA_CHECK(cudaGetLastError());
+    return PVCR_OK;
+  }
   const size_t smem = sizeof(float) * ((size_t)2 * H + Kc);
   if (smem > 48 * 1024) { set_last_error("pvcr_spatial_attn_fwd: H=%d too large", H); return PVCR_ERR_ARG; }
   { LaunchScope ls_(KC_ATTN, (cudaStream_t)stream);
@@ -571,6 +764,16 @@ int pvcr_spatial_attn_bwd(int B, int Kc, int H, int Fv, const float* dctx, const
                           int64_t pk_batch_stride, const float* feats, int64_t feats_batch_stride, const float* v,
                           const float* alpha, float* dq, float* dproj_key, float* dv_part, void* stream) {
   if (B <= 0 || Kc <= 0 || Kc > SA_MAX_CELLS || H <= 0 || Fv <= 0) { set_last_error("pvcr_spatial_attn_bwd: B=%d Kc=%d H=%d Fv=%d", B, Kc, H, Fv); return PVCR_ERR_ARG; }
+  if (spatial_attn_vec_ok(Kc, H, Fv, q_ld, pk_batch_stride, feats_batch_stride, q, proj_key, feats, v, dctx, dproj_key) &&
+      ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dv_part)) & 15) == 0) {
+    const size_t smem_v = sizeof(float) * ((size_t)10 * Kc + 4 + (size_t)2 * (256 / (H >> 2)) * H);
+    { LaunchScope ls_(KC_ATTN, (cudaStream_t)stream);
+    spatial_attn_bwd_vec_kernel<<<B, 256, smem_v, (cudaStream_t)stream>>>(Kc, H, Fv, dctx, q, q_ld, proj_key, pk_batch_stride, feats,
+                                                                         feats_batch_stride, v, alpha, dq, dproj_key, dv_part);
+    }
+    PVCR_CUDA_CHECK(cudaGetLastError());
+    return PVCR_OK;
+  }
   { LaunchScope ls_(KC_ATTN, (cudaStream_t)stream);
   spatial_attn_bwd_kernel<<<B, 256, sizeof(float) * 2 * Kc, (cudaStream_t)stream>>>(Kc, H, Fv, dctx, q, q_ld, proj_key, pk_batch_stride,
                                                                                   feats, feats_batch_stride, v, alpha, dq, dproj_key, dv_part);
