@@ -672,24 +672,29 @@ class SpatialAttnStep(torch.autograd.Function):
     def forward(ctx, q, pk, feats, v):
         B, Kc, H = pk.shape
         Fv = feats.shape[2]
-        q_c, pk_c, f_c, v_c = _f32c(q), _f32c(pk), _f32c(feats), _f32c(v).reshape(-1)
+        q_c, pk_c, v_c = _f32c(q), _f32c(pk), _f32c(v).reshape(-1)
+        # the features (inputs, no gradient) may be a batch-strided view -- one frame of a [B, N, Kc, F] tensor: no frame-major copy
+        if feats.dtype == torch.float32 and feats.stride(2) == 1 and feats.stride(1) == Fv and feats.stride(0) >= Kc * Fv:
+            f_c, f_bs = feats.detach(), feats.stride(0)
+        else:
+            f_c, f_bs = _f32c(feats), Kc * Fv
         alpha = torch.empty((B, Kc), dtype=torch.float32, device=q_c.device)
         out = torch.empty((B, Fv), dtype=torch.float32, device=q_c.device)
-        check(lib().pvcr_spatial_attn_fwd(B, Kc, H, Fv, ptr(q_c), H, ptr(pk_c), Kc * H, ptr(f_c), Kc * Fv, ptr(v_c), ptr(alpha),
+        check(lib().pvcr_spatial_attn_fwd(B, Kc, H, Fv, ptr(q_c), H, ptr(pk_c), Kc * H, ptr(f_c), f_bs, ptr(v_c), ptr(alpha),
                                           ptr(out), stream_ptr()), "pvcr_spatial_attn_fwd")
-        ctx.meta = (B, Kc, H, Fv, tuple(v.shape))
+        ctx.meta = (B, Kc, H, Fv, tuple(v.shape), f_bs)
         ctx.keep = (q_c, pk_c, f_c, v_c, alpha)
         ctx.mark_non_differentiable(alpha)
         return out, alpha
 
     @staticmethod
     def backward(ctx, dctx, _dalpha):
-        B, Kc, H, Fv, vshape = ctx.meta
+        B, Kc, H, Fv, vshape, f_bs = ctx.meta
         q_c, pk_c, f_c, v_c, alpha = ctx.keep
         dq = torch.empty_like(q_c)
         dpk = torch.empty_like(pk_c)
         dv_part = torch.empty((B, H), dtype=torch.float32, device=q_c.device)
-        check(lib().pvcr_spatial_attn_bwd(B, Kc, H, Fv, ptr(_f32c(dctx)), ptr(q_c), H, ptr(pk_c), Kc * H, ptr(f_c), Kc * Fv,
+        check(lib().pvcr_spatial_attn_bwd(B, Kc, H, Fv, ptr(_f32c(dctx)), ptr(q_c), H, ptr(pk_c), Kc * H, ptr(f_c), f_bs,
                                           ptr(v_c), ptr(alpha), ptr(dq), ptr(dpk), ptr(dv_part), stream_ptr()),
               "pvcr_spatial_attn_bwd")
         return dq, dpk, None, dv_part.sum(dim=0).reshape(vshape)

@@ -77,13 +77,14 @@ class SpatialNet(nn.Module):
         proj_key = F_.Linear.apply(ns, conv_feats, self.attention.key_layer.weight)
         # frame-major copies so that every frame's [B, K*K, .] slice is contiguous (unbind: its backward is one stack)
         pk_frames = proj_key.view(B, N, cells, H).transpose(0, 1).contiguous().unbind(0)
-        feat_frames = feats_cl.view(B, N, cells, Fd).transpose(0, 1).contiguous().unbind(0)
+        # (the features need no gradient: frame i is read in place as a batch-strided view, no frame-major copy of 1.5 GB at cfg4)
+        feat_view = feats_cl.detach().view(B, N, cells, Fd)
         state = torch.zeros(1, B, H, device=vid_feats.device, dtype=torch.float32)
         outs, seq_alphas = [], []
         v = self.attention.energy_layer.weight
         for i in range(N):
             q = F_.Linear.apply(ns, state.squeeze(0), self.attention.query_layer.weight)
-            context, alphas = F_.SpatialAttnStep.apply(q, pk_frames[i], feat_frames[i], v)
+            context, alphas = F_.SpatialAttnStep.apply(q, pk_frames[i], feat_view[:, i], v)
             out, state = self.caption_net.encode_step(context, state)
             outs.append(out)
             seq_alphas.append(alphas.view(-1, K, K).unsqueeze(1))
