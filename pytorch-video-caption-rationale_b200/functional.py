@@ -96,7 +96,7 @@ class S2VTAttSequence(torch.autograd.Function):
         ctx.dims = dims
         ctx.need_fg = need_fg
         ctx.cfg = cfg
-        ctx.keep = (vid_c, fs_c, s_c, hs, ws, tensors)
+        ctx.keep = (vid_c, fs_c, s_c, hs.detach(), ws, tensors)     # detached alias: the returned hs gets grad_fn = this node (no cycle)
         ctx.mark_non_differentiable(alphas)
         return hs, alphas
 
@@ -150,7 +150,7 @@ class S2VTAttDecode(torch.autograd.Function):
         check(Lb.pvcr_s2vtatt_decode_fwd(ctypes.byref(dims), ctypes.byref(ps), ptr(enc_c), ptr(fin_c), ptr(s_c), ptr(hs),
                                          ptr(alphas), ptr(ws), ws.numel(), stream_ptr()), "pvcr_s2vtatt_decode_fwd")
         ctx.dims = dims
-        ctx.keep = (s_c, hs, ws, tensors)
+        ctx.keep = (s_c, hs.detach(), ws, tensors)     # detached alias: the returned hs gets grad_fn = this node (no cycle)
         ctx.mark_non_differentiable(alphas)
         return hs, alphas
 
@@ -235,7 +235,7 @@ class S2VTSequence(torch.autograd.Function):
         ctx.dims = dims
         ctx.need_fg = need_fg
         ctx.cfg = cfg
-        ctx.keep = (vid_c, fs_c, s_c, hs, ws, tensors)
+        ctx.keep = (vid_c, fs_c, s_c, hs.detach(), ws, tensors)     # detached alias: the returned hs gets grad_fn = this node (no cycle)
         return hs
 
     @staticmethod
@@ -272,7 +272,7 @@ class S2VTDecode(torch.autograd.Function):
         check(Lb.pvcr_s2vt_decode_fwd(ctypes.byref(dims), ctypes.byref(ps), ptr(o_c), ptr(st_c), ptr(s_c), ptr(hs), ptr(ws),
                                       ws.numel(), stream_ptr()), "pvcr_s2vt_decode_fwd")
         ctx.dims = dims
-        ctx.keep = (s_c, hs, ws, tensors)
+        ctx.keep = (s_c, hs.detach(), ws, tensors)     # detached alias: the returned hs gets grad_fn = this node (no cycle)
         return hs
 
     @staticmethod

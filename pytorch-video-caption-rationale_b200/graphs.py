@@ -194,6 +194,56 @@ class GraphedTrainStep:
         return self.static_out
 
 
+class GraphedAutogradStep:
+    """CUDA-graph capture of ``loss = loss_fn(); loss.backward()`` WITH the autograd tape inside the capture, for the drop-in
+    modules whose step is a chain of autograd Functions rather than one tape-free ``train_step_grads`` -- SpatialNet's frame
+    loop (model/SpatialNet.py:120-140: query GEMM, attention, encoder step per frame = ~1 500 launches per fwd+bwd, host-bound
+    in eager mode).  ``loss_fn`` takes no arguments and reads its inputs from tensors that stay alive (copy new batches into
+    them); the gradients appear in ``param.grad`` (static buffers of the graph's pool, rewritten by every replay)."""
+
+    def __init__(self, model, loss_fn, warmup=2):
+        self.model = model
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        dev = self.params[0].device
+        self.seed_step = torch.zeros(1, dtype=torch.int64, device=dev)
+        lib().pvcr_set_seed_step(ptr(self.seed_step))
+        GraphedTrainStep._seed_owner = self.seed_step.data_ptr()
+
+        def step():
+            # torch.autograd.grad, not .backward(): no AccumulateGrad nodes (they remember the stream of an earlier eager
+            # iteration, and a hand-over to the default stream invalidates the capture)
+            loss = loss_fn()
+            return loss.detach(), torch.autograd.grad(loss, self.params, allow_unused=True)
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.seed_step.add_(1)
+            self.static_loss, grads = step()
+        for p, g in zip(self.params, grads):         # static buffers of the graph's pool, rewritten by every replay
+            p.grad = g
+
+    def replay(self):
+        self.graph.replay()
+        return self.static_loss
+
+    __call__ = replay
+
+    def __del__(self):
+        try:
+            if GraphedTrainStep._seed_owner == self.seed_step.data_ptr():
+                lib().pvcr_set_seed_step(None)
+                GraphedTrainStep._seed_owner = None
+        except Exception:                        # noqa: BLE001  (interpreter shutdown)
+            pass
+
+
 class GraphedGreedy:
     """CUDA-graph capture of fixed-length greedy captioning (model.greedy) for one batch shape: at small batches the
     step-wise decode is launch-latency bound, a single graph launch removes the host from the loop."""

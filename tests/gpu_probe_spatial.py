@@ -54,6 +54,23 @@ conv_flops_useful = 2 * B * N * K * K * 9 * (F * H + H * H) * 3 - 2 * B * N * K 
 out["ours"] = {"ms_per_step": ms, "videos_per_s": B / (ms / 1e3), "loss": float(ours().item()),
                "class_ms": {k: round(v[1], 3) for k, v in prof.items() if v[0]},
                "gemm_executed_tflop": prof["gemm_tcgen05"][2] / 1e12, "conv_useful_tflop": conv_flops_useful / 1e12}
+if os.environ.get("PVCR_PROBE_GRAPH"):
+    # host-side time of one eager step (launch-bound?) and the same step captured as ONE CUDA graph (autograd tape inside the capture)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ours()
+    host_ms = (time.perf_counter() - t0) / 3 * 1e3
+    torch.cuda.synchronize()
+    out["ours"]["host_issue_ms_per_step"] = host_ms
+    try:
+        from pvcr_b200.graphs import GraphedAutogradStep
+        gs = GraphedAutogradStep(net, lambda: TU.calc_masked_loss(net(vid, s)[0], s, s_len, crit))
+        ms_g = timed(gs.replay)
+        out["ours_graph"] = {"ms_per_step": ms_g, "videos_per_s": B / (ms_g / 1e3), "loss": float(gs.replay().item())}
+        del gs
+    except Exception as e:      # noqa: BLE001
+        out["ours_graph_error"] = repr(e)[:400]
 torch.cuda.empty_cache()
 try:
     from oracle import reference_runner as R
