@@ -349,6 +349,24 @@ int pvcr_spatial_front_bwd(int I, int K, int F, int H, int nsplit, const PvcrSpa
                            const float* d_conv_feats, PvcrSpatialFrontParams* grads, void* workspace, size_t workspace_bytes,
                            void* stream);
 
+/* SpatialNet's whole frame loop in one call per direction (model/SpatialNet.py:114-138): for every frame t
+ *   q = query_layer(h_{t-1});  alpha_t, ctx_t = attention over the K*K cells (:27-53; keys proj_key = key_layer(conv_feats), values
+ *   feats = the frame's input features);  h_t = GRU(ctx_t, h_{t-1}) = caption_net.encode_step (:127), h_{-1} = 0 (:114).
+ * proj_key [B,N,Kc,H] and feats [B,N,Kc,F] fp32 as pvcr_spatial_front_fwd / key_layer leave them; w_q [H,H] = query_layer.weight,
+ * v [H] = energy_layer.weight, w_ih [3H,F] / w_hh [3H,H] / b_ih / b_hh = the encoder GRU (torch.nn.GRU layout).  Outputs:
+ * outs [N,B,H] (torch.cat of the per-frame outputs, :129-132; the final state is its last frame), alphas [N,B,Kc].  The weights are
+ * staged once per call, q and W_hh h come from one stacked product, the parameter gradients are products over all frames.
+ * _bwd takes the forward call's workspace (unchanged in between), its outs / alphas, and d_outs [N,B,H]; it overwrites d_proj_key
+ * [B,N,Kc,H] and the six parameter gradients.  The features need no gradient. */
+size_t pvcr_spatial_encode_workspace(int B, int N, int Kc, int H, int F, int nsplit);
+int pvcr_spatial_encode_fwd(int B, int N, int Kc, int H, int F, int nsplit, const float* proj_key, const float* feats, const float* w_q,
+                            const float* v, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* outs,
+                            float* alphas, void* workspace, size_t workspace_bytes, void* stream);
+int pvcr_spatial_encode_bwd(int B, int N, int Kc, int H, int F, int nsplit, const float* proj_key, const float* feats, const float* w_q,
+                            const float* v, const float* w_ih, const float* w_hh, const float* outs, const float* alphas,
+                            const float* d_outs, float* d_proj_key, float* d_w_q, float* d_v, float* d_w_ih, float* d_w_hh,
+                            float* d_b_ih, float* d_b_hh, void* workspace, size_t workspace_bytes, void* stream);
+
 /* One step of SpatialNet's per-frame attention over the K*K cells (model/SpatialNet.py:27-53, called at :124):
  *   scores[b,c] = v . tanh(q[b] + proj_key[b,c]);  alpha = softmax_c(scores);  ctx[b] = sum_c alpha[b,c] feats[b,c]
  * q [B,H] (row stride q_ld) = query_layer(encoder state); proj_key [B,Kc,H] and feats [B,Kc,Fv] with explicit batch strides

@@ -149,6 +149,9 @@ SIGNATURES = {
     "pvcr_spatial_attn_fwd": (c_int, [c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "pvcr_spatial_attn_bwd": (c_int, [c_int, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
                                       c_vp, c_vp]),
+    "pvcr_spatial_encode_workspace": (c_size, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "pvcr_spatial_encode_fwd": (c_int, [c_int] * 6 + [c_vp] * 10 + [c_vp, c_size, c_vp]),
+    "pvcr_spatial_encode_bwd": (c_int, [c_int] * 6 + [c_vp] * 16 + [c_vp, c_size, c_vp]),
     "pvcr_out_dropout_apply": (c_int, [c_vp, c_vp, c_i64, c_f, c_u64, c_vp]),
     "pvcr_debug_philox_minmax": (c_int, [c_u64, c_u64, c_u64, c_vp, c_vp]),
     "pvcr_vocab_ce_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_u64, c_vp, c_vp,

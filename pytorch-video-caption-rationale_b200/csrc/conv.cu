@@ -511,8 +511,8 @@ __global__ void __launch_bounds__(256) spatial_attn_bwd_kernel(int Kc, int H, in
                                                                const float* __restrict__ pk, long long pk_bs,
                                                                const float* __restrict__ feats, long long feats_bs,
                                                                const float* __restrict__ v, const float* __restrict__ alpha,
-                                                               float* __restrict__ dq, float* __restrict__ dpk,
-                                                               float* __restrict__ dv_part) {
+                                                               float* __restrict__ dq, long long dq_ld, float* __restrict__ dpk,
+                                                               long long dpk_bs, float* __restrict__ dv_part) {
   extern __shared__ float sm[];
   float* sds = sm;           // [Kc] d alpha -> d score
   float* sal = sds + Kc;     // [Kc]
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(256) spatial_attn_bwd_kernel(int Kc, int H, in
   }
   __syncthreads();
   const float* pkb = pk + (long long)b * pk_bs;
-  float* dpkb = dpk + (long long)b * Kc * H;
+  float* dpkb = dpk + (long long)b * dpk_bs;
   for (int d = tid; d < H; d += 256) {
     const float qd = q[(long long)b * q_ld + d], vd = v[d];
     float aq = 0.f, av = 0.f;
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(256) spatial_attn_bwd_kernel(int Kc, int H, in
       dpkb[(long long)c * H + d] = g;
       aq += g; av += sds[c] * e;
     }
-    dq[(long long)b * H + d] = aq;
+    dq[(long long)b * dq_ld + d] = aq;
     dv_part[(long long)b * H + d] = av;
   }
 }
@@ -634,8 +634,8 @@ __global__ void __launch_bounds__(256) spatial_attn_bwd_vec_kernel(int Kc, int H
                                                                    const float* __restrict__ pk, long long pk_bs,
                                                                    const float* __restrict__ feats, long long feats_bs,
                                                                    const float* __restrict__ v, const float* __restrict__ alpha,
-                                                                   float* __restrict__ dq, float* __restrict__ dpk,
-                                                                   float* __restrict__ dv_part) {
+                                                                   float* __restrict__ dq, long long dq_ld, float* __restrict__ dpk,
+                                                                   long long dpk_bs, float* __restrict__ dv_part) {
   extern __shared__ float sm[];
   const int Q4 = H >> 2, CH = 256 / Q4;                          // 16-byte dim columns, cell groups of the key phase
   float* sds = sm;                 // [Kc] d alpha -> d score
@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(256) spatial_attn_bwd_vec_kernel(int Kc, int H
   const float4 qd = __ldg(reinterpret_cast<const float4*>(q + (long long)b * q_ld) + d4i);
   const float4 vd = __ldg(reinterpret_cast<const float4*>(v) + d4i);
   const float4* pkb = reinterpret_cast<const float4*>(pk + (long long)b * pk_bs);
-  float4* dpkb = reinterpret_cast<float4*>(dpk + (long long)b * Kc * H);
+  float4* dpkb = reinterpret_cast<float4*>(dpk + (long long)b * dpk_bs);
   float4 aq = make_float4(0.f, 0.f, 0.f, 0.f), av = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int c0 = ch; c0 < Kc; c0 += CH * SAV_NC) {
     float4 x[SAV_NC];
@@ -719,7 +719,7 @@ __global__ void __launch_bounds__(256) spatial_attn_bwd_vec_kernel(int Kc, int H
       a.x += a2.x; a.y += a2.y; a.z += a2.z; a.w += a2.w;
       w.x += w2.x; w.y += w2.y; w.z += w2.z; w.w += w2.w;
     }
-    reinterpret_cast<float4*>(dq + (long long)b * H)[d4i] = a;
+    reinterpret_cast<float4*>(dq + (long long)b * dq_ld)[d4i] = a;
     reinterpret_cast<float4*>(dv_part + (long long)b * H)[d4i] = w;
   }
 }
@@ -733,6 +733,50 @@ static bool spatial_attn_vec_ok(int Kc, int H, int Fv, long long q_ld, long long
          Kc <= SA_MAX_CELLS;
 }
 
+// launchers (also used by the fused frame sweep, spatial_sweep.cu): dq rows dq_ld apart, dproj_key videos dpk_bs apart
+int spatial_attn_fwd_launch(int B, int Kc, int H, int Fv, const float* q, long long q_ld, const float* proj_key, long long pk_batch_stride,
+                            const float* feats, long long feats_batch_stride, const float* v, float* alpha, float* ctx, cudaStream_t stream) {
+  if (B <= 0 || Kc <= 0 || Kc > SA_MAX_CELLS || H <= 0 || Fv <= 0) { set_last_error("pvcr_spatial_attn_fwd: B=%d Kc=%d H=%d Fv=%d", B, Kc, H, Fv); return PVCR_ERR_ARG; }
+  if (spatial_attn_vec_ok(Kc, H, Fv, q_ld, pk_batch_stride, feats_batch_stride, q, proj_key, feats, v, ctx, ctx)) {
+    const size_t smem_v = sizeof(float) * ((size_t)Kc * ((H >> 3) >> 5) + Kc);
+    { LaunchScope ls_(KC_ATTN, stream);
+    spatial_attn_fwd_vec_kernel<<<B, 256, smem_v, stream>>>(Kc, H, Fv, q, q_ld, proj_key, pk_batch_stride, feats,
+                                                           feats_batch_stride, v, alpha, ctx);
+    }
+    PVCR_CUDA_CHECK(cudaGetLastError());
+    return PVCR_OK;
+  }
+  const size_t smem = sizeof(float) * ((size_t)2 * H + Kc);
+  if (smem > 48 * 1024) { set_last_error("pvcr_spatial_attn_fwd: H=%d too large", H); return PVCR_ERR_ARG; }
+  { LaunchScope ls_(KC_ATTN, stream);
+  spatial_attn_fwd_kernel<<<B, 256, smem, stream>>>(Kc, H, Fv, q, q_ld, proj_key, pk_batch_stride, feats, feats_batch_stride, v, alpha, ctx);
+  }
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  return PVCR_OK;
+}
+int spatial_attn_bwd_launch(int B, int Kc, int H, int Fv, const float* dctx, const float* q, long long q_ld, const float* proj_key,
+                            long long pk_batch_stride, const float* feats, long long feats_batch_stride, const float* v,
+                            const float* alpha, float* dq, long long dq_ld, float* dproj_key, long long dpk_batch_stride,
+                            float* dv_part, cudaStream_t stream) {
+  if (B <= 0 || Kc <= 0 || Kc > SA_MAX_CELLS || H <= 0 || Fv <= 0) { set_last_error("pvcr_spatial_attn_bwd: B=%d Kc=%d H=%d Fv=%d", B, Kc, H, Fv); return PVCR_ERR_ARG; }
+  if (spatial_attn_vec_ok(Kc, H, Fv, q_ld, pk_batch_stride, feats_batch_stride, q, proj_key, feats, v, dctx, dproj_key) &&
+      ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dv_part)) & 15) == 0 && dq_ld % 4 == 0 && dpk_batch_stride % 4 == 0) {
+    const size_t smem_v = sizeof(float) * ((size_t)10 * Kc + 4 + (size_t)2 * (256 / (H >> 2)) * H);
+    { LaunchScope ls_(KC_ATTN, stream);
+    spatial_attn_bwd_vec_kernel<<<B, 256, smem_v, stream>>>(Kc, H, Fv, dctx, q, q_ld, proj_key, pk_batch_stride, feats, feats_batch_stride,
+                                                           v, alpha, dq, dq_ld, dproj_key, dpk_batch_stride, dv_part);
+    }
+    PVCR_CUDA_CHECK(cudaGetLastError());
+    return PVCR_OK;
+  }
+  { LaunchScope ls_(KC_ATTN, stream);
+  spatial_attn_bwd_kernel<<<B, 256, sizeof(float) * 2 * Kc, stream>>>(Kc, H, Fv, dctx, q, q_ld, proj_key, pk_batch_stride, feats,
+                                                                     feats_batch_stride, v, alpha, dq, dq_ld, dproj_key, dpk_batch_stride, dv_part);
+  }
+  PVCR_CUDA_CHECK(cudaGetLastError());
+  return PVCR_OK;
+}
+
 }  // namespace pvcr
 
 using namespace pvcr;
@@ -741,45 +785,13 @@ extern "C" {
 
 int pvcr_spatial_attn_fwd(int B, int Kc, int H, int Fv, const float* q, int64_t q_ld, const float* proj_key, int64_t pk_batch_stride,
                           const float* feats, int64_t feats_batch_stride, const float* v, float* alpha, float* ctx, void* stream) {
-  if (B <= 0 || Kc <= 0 || Kc > SA_MAX_CELLS || H <= 0 || Fv <= 0) { set_last_error("pvcr_spatial_attn_fwd: B=%d Kc=%d H=%d Fv=%d", B, Kc, H, Fv); return PVCR_ERR_ARG; }
-  if (spatial_attn_vec_ok(Kc, H, Fv, q_ld, pk_batch_stride, feats_batch_stride, q, proj_key, feats, v, ctx, ctx)) {
-    const size_t smem_v = sizeof(float) * ((size_t)Kc * ((H >> 3) >> 5) + Kc);
-    { LaunchScope ls_(KC_ATTN, (cudaStream_t)stream);
-    spatial_attn_fwd_vec_kernel<<<B, 256, smem_v, (cudaStream_t)stream>>>(Kc, H, Fv, q, q_ld, proj_key, pk_batch_stride, feats,
-                                                                         feats_batch_stride, v, alpha, ctx);
-    }
-    PVCR_CUDA_CHECK(cudaGetLastError());
-    return PVCR_OK;
-  }
-  const size_t smem = sizeof(float) * ((size_t)2 * H + Kc);
-  if (smem > 48 * 1024) { set_last_error("pvcr_spatial_attn_fwd: H=%d too large", H); return PVCR_ERR_ARG; }
-  { LaunchScope ls_(KC_ATTN, (cudaStream_t)stream);
-  spatial_attn_fwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(Kc, H, Fv, q, q_ld, proj_key, pk_batch_stride, feats,
-                                                                   feats_batch_stride, v, alpha, ctx);
-  }
-  PVCR_CUDA_CHECK(cudaGetLastError());
-  return PVCR_OK;
+  return spatial_attn_fwd_launch(B, Kc, H, Fv, q, q_ld, proj_key, pk_batch_stride, feats, feats_batch_stride, v, alpha, ctx, (cudaStream_t)stream);
 }
 int pvcr_spatial_attn_bwd(int B, int Kc, int H, int Fv, const float* dctx, const float* q, int64_t q_ld, const float* proj_key,
                           int64_t pk_batch_stride, const float* feats, int64_t feats_batch_stride, const float* v,
                           const float* alpha, float* dq, float* dproj_key, float* dv_part, void* stream) {
-  if (B <= 0 || Kc <= 0 || Kc > SA_MAX_CELLS || H <= 0 || Fv <= 0) { set_last_error("pvcr_spatial_attn_bwd: B=%d Kc=%d H=%d Fv=%d", B, Kc, H, Fv); return PVCR_ERR_ARG; }
-  if (spatial_attn_vec_ok(Kc, H, Fv, q_ld, pk_batch_stride, feats_batch_stride, q, proj_key, feats, v, dctx, dproj_key) &&
-      ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dv_part)) & 15) == 0) {
-    const size_t smem_v = sizeof(float) * ((size_t)10 * Kc + 4 + (size_t)2 * (256 / (H >> 2)) * H);
-    { LaunchScope ls_(KC_ATTN, (cudaStream_t)stream);
-    spatial_attn_bwd_vec_kernel<<<B, 256, smem_v, (cudaStream_t)stream>>>(Kc, H, Fv, dctx, q, q_ld, proj_key, pk_batch_stride, feats,
-                                                                         feats_batch_stride, v, alpha, dq, dproj_key, dv_part);
-    }
-    PVCR_CUDA_CHECK(cudaGetLastError());
-    return PVCR_OK;
-  }
-  { LaunchScope ls_(KC_ATTN, (cudaStream_t)stream);
-  spatial_attn_bwd_kernel<<<B, 256, sizeof(float) * 2 * Kc, (cudaStream_t)stream>>>(Kc, H, Fv, dctx, q, q_ld, proj_key, pk_batch_stride,
-                                                                                  feats, feats_batch_stride, v, alpha, dq, dproj_key, dv_part);
-  }
-  PVCR_CUDA_CHECK(cudaGetLastError());
-  return PVCR_OK;
+  return spatial_attn_bwd_launch(B, Kc, H, Fv, dctx, q, q_ld, proj_key, pk_batch_stride, feats, feats_batch_stride, v, alpha, dq, H,
+                                 dproj_key, (long long)Kc * H, dv_part, (cudaStream_t)stream);
 }
 
 size_t pvcr_spatial_front_workspace(int I, int K, int F, int H, int nsplit) { return spatial_front_workspace(I, K, F, H, nsplit); }

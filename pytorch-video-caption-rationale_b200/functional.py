@@ -698,3 +698,40 @@ class SpatialAttnStep(torch.autograd.Function):
                                           ptr(v_c), ptr(alpha), ptr(dq), ptr(dpk), ptr(dv_part), stream_ptr()),
               "pvcr_spatial_attn_bwd")
         return dq, dpk, None, dv_part.sum(dim=0).reshape(vshape)
+
+
+class SpatialEncode(torch.autograd.Function):
+    """SpatialNet's whole frame loop (model/SpatialNet.py:114-138) in one library call per direction
+    (pvcr_spatial_encode_fwd / _bwd, csrc/spatial_sweep.cu): (proj_key [B,N,Kc,H], feats [B,N,Kc,F], query_layer.weight,
+    energy_layer.weight, the encoder GRU's four parameters) -> outs [N,B,H], alphas [N,B,Kc].  Differentiable in proj_key and the
+    parameters (the features are inputs)."""
+
+    @staticmethod
+    def forward(ctx, nsplit, pk, feats, w_q, v, w_ih, w_hh, b_ih, b_hh):
+        B, N, Kc, H = pk.shape
+        Fv = feats.shape[3]
+        pk_c, f_c = _f32c(pk), _f32c(feats)
+        w = tuple(_f32c(t) for t in (w_q, v, w_ih, w_hh, b_ih, b_hh))
+        Lb = lib()
+        ws = _ws(Lb.pvcr_spatial_encode_workspace(B, N, Kc, H, Fv, nsplit), pk_c.device)
+        outs = torch.empty((N, B, H), dtype=torch.float32, device=pk_c.device)
+        alphas = torch.empty((N, B, Kc), dtype=torch.float32, device=pk_c.device)
+        check(Lb.pvcr_spatial_encode_fwd(B, N, Kc, H, Fv, nsplit, ptr(pk_c), ptr(f_c), ptr(w[0]), ptr(w[1]), ptr(w[2]), ptr(w[3]),
+                                         ptr(w[4]), ptr(w[5]), ptr(outs), ptr(alphas), ptr(ws), ws.numel(), stream_ptr()),
+              "pvcr_spatial_encode_fwd")
+        ctx.meta = (B, N, Kc, H, Fv, nsplit, tuple(v.shape))
+        ctx.keep = (pk_c, f_c, w, outs.detach(), alphas, ws)     # detached alias: the returned outs gets grad_fn = this node
+        ctx.mark_non_differentiable(alphas)
+        return outs, alphas
+
+    @staticmethod
+    def backward(ctx, d_outs, _d_alphas):
+        B, N, Kc, H, Fv, nsplit, vshape = ctx.meta
+        pk_c, f_c, w, outs, alphas, ws = ctx.keep
+        d_pk = torch.empty_like(pk_c)
+        g = tuple(torch.empty_like(t) for t in w)
+        check(lib().pvcr_spatial_encode_bwd(B, N, Kc, H, Fv, nsplit, ptr(pk_c), ptr(f_c), ptr(w[0]), ptr(w[1]), ptr(w[2]), ptr(w[3]),
+                                            ptr(outs), ptr(alphas), ptr(_f32c(d_outs)), ptr(d_pk), ptr(g[0]), ptr(g[1]), ptr(g[2]),
+                                            ptr(g[3]), ptr(g[4]), ptr(g[5]), ptr(ws), ws.numel(), stream_ptr()),
+              "pvcr_spatial_encode_bwd")
+        return None, d_pk, None, g[0], g[1].reshape(vshape), g[2], g[3], g[4], g[5]

@@ -20,6 +20,8 @@ of the same step, so nothing of it can be hoisted); a persistent fused spatial-a
 
 Parity: tests/test_gpu_boundary.py against goldens of the unmodified reference SpatialNet (oracle/gen_golden_spatial.py).
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -75,13 +77,23 @@ class SpatialNet(nn.Module):
         ns = self.NSPLIT[self.precision] if self.training else 3
         conv_feats, feats_cl = self._front(vid_feats.reshape(B * N, Fd, K, K))
         proj_key = F_.Linear.apply(ns, conv_feats, self.attention.key_layer.weight)
+        v = self.attention.energy_layer.weight
+        if os.environ.get("PVCR_SPATIAL_STEPWISE") is None:
+            # the whole frame loop in one library call per direction (csrc/spatial_sweep.cu): weights staged once, q and W_hh h from
+            # one stacked product, parameter gradients as products over all frames
+            rnn = self.caption_net.encoder.rnn if isinstance(self.caption_net, S2VTAttModel) else self.caption_net.rnn1
+            outs, alphas = F_.SpatialEncode.apply(ns, proj_key.view(B, N, cells, H), feats_cl.detach().view(B, N, cells, Fd),
+                                                  self.attention.query_layer.weight, v, rnn.weight_ih_l0, rnn.weight_hh_l0,
+                                                  rnn.bias_ih_l0, rnn.bias_hh_l0)
+            logits = self.caption_net.decode(outs, outs[N - 1:], s)
+            return logits, alphas.view(N, B, K, K).transpose(0, 1).contiguous()
+        # step-wise variant (A/B knob, and the shape of the reference's loop): one Linear + attention + encode_step per frame
         # frame-major copies so that every frame's [B, K*K, .] slice is contiguous (unbind: its backward is one stack)
         pk_frames = proj_key.view(B, N, cells, H).transpose(0, 1).contiguous().unbind(0)
         # (the features need no gradient: frame i is read in place as a batch-strided view, no frame-major copy of 1.5 GB at cfg4)
         feat_view = feats_cl.detach().view(B, N, cells, Fd)
         state = torch.zeros(1, B, H, device=vid_feats.device, dtype=torch.float32)
         outs, seq_alphas = [], []
-        v = self.attention.energy_layer.weight
         for i in range(N):
             q = F_.Linear.apply(ns, state.squeeze(0), self.attention.query_layer.weight)
             context, alphas = F_.SpatialAttnStep.apply(q, pk_frames[i], feat_view[:, i], v)

@@ -147,11 +147,17 @@ def test_reference_spatialnet_class_runs_with_the_dropin(tag, arch):
         assert e < 5e-4 or np.linalg.norm(grads[k]) < 1e-9, (k, e)
 
 
+@pytest.mark.parametrize("stepwise", [False, True])
 @pytest.mark.parametrize("tag,arch", CASES)
-def test_dropin_spatialnet_module(tag, arch):
+def test_dropin_spatialnet_module(tag, arch, stepwise, monkeypatch):
     """pvcr_b200.model.SpatialNet: reference constructor / forward contract / state_dict keys; loads the golden's
-    reference state_dict key for key and reproduces logits, seq_alphas, loss and every gradient."""
+    reference state_dict key for key and reproduces logits, seq_alphas, loss and every gradient -- with the frame loop as one
+    library call per direction (pvcr_spatial_encode_fwd/bwd, the default) and as the step-wise Function chain."""
     from pvcr_b200 import train_utils as TU
+    if stepwise:
+        monkeypatch.setenv("PVCR_SPATIAL_STEPWISE", "1")
+    else:
+        monkeypatch.delenv("PVCR_SPATIAL_STEPWISE", raising=False)
     from pvcr_b200.model import SpatialNet
     d, params, grads = _load(tag)
     B, N, Fdim, H, E, L, Vc = (int(x) for x in d["dims"])
@@ -180,6 +186,49 @@ def test_dropin_spatialnet_module(tag, arch):
     with torch.no_grad():
         lg, _ = net(vid, None)
     assert np.array_equal(torch.argmax(lg, dim=2).cpu().numpy(), d["eval_ids"])
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16", 3e-2), ("bf16x2", 2e-3)])
+def test_spatialnet_frame_sweep_vs_stepwise(precision, tol, monkeypatch):
+    """The benchmarked arithmetic modes: the fused frame loop (csrc/spatial_sweep.cu) against the step-wise chain on the same
+    weights and inputs at a shape the vectorised attention kernels serve (H = 256, F = 512, 4 x 4 cells), and the same step
+    captured as one CUDA graph (GraphedAutogradStep) against the eager one."""
+    from pvcr_b200 import train_utils as TU
+    from pvcr_b200.graphs import GraphedAutogradStep
+    from pvcr_b200.model import SpatialNet
+    B, N, Fd, K, H, E, L, Vc = 6, 5, 512, 4, 256, 32, 7, 300
+    torch.manual_seed(11)
+    net = SpatialNet(FixtureGlove(Vc, E), 0.0, H, Fd, L, "s2vt-att", precision=precision).cuda().train()
+    vid = torch.randn(B, N, Fd, K, K, device="cuda")
+    s = torch.randint(0, Vc - 4, (B, L), device="cuda")
+    s_len = torch.randint(1, L + 1, (B,), device="cuda")
+    crit = nn.CrossEntropyLoss(reduction="none")
+
+    def run():
+        net.zero_grad(set_to_none=True)
+        logits, al = net(vid, s)
+        loss = TU.calc_masked_loss(logits, s, s_len, crit)
+        loss.backward()
+        return loss.item(), al.detach().clone(), {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
+
+    monkeypatch.setenv("PVCR_SPATIAL_STEPWISE", "1")
+    l0, a0, g0 = run()
+    monkeypatch.delenv("PVCR_SPATIAL_STEPWISE")
+    l1, a1, g1 = run()
+    assert abs(l0 - l1) < tol * abs(l0)
+    assert (a0 - a1).abs().max().item() < tol
+    assert set(g0) == set(g1)
+    for k in g0:
+        e = relerr(g1[k].double().cpu().numpy(), g0[k].double().cpu().numpy())
+        assert e < tol or g0[k].norm().item() < 1e-9, (k, e)
+    # the same step as one CUDA graph: same kernels, same order -> the eager result to rounding of the atomics
+    gs = GraphedAutogradStep(net, lambda: TU.calc_masked_loss(net(vid, s)[0], s, s_len, crit))
+    lg = gs.replay().item()
+    assert abs(lg - l1) < 1e-5 * abs(l1)
+    for k, prm in net.named_parameters():
+        if k in g1:
+            e = relerr(prm.grad.double().cpu().numpy(), g1[k].double().cpu().numpy())
+            assert e < 1e-4 or g1[k].norm().item() < 1e-9, (k, e)
 
 
 def test_boundary_surface_matches_reference_signatures():
