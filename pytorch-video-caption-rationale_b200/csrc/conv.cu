@@ -39,8 +39,11 @@ Geo make_geo(int I, int K) {
 // vid [I, C, K, K] fp32 (channels first, as the reference hands it over) -> xp [Rtot, C] fp32 padded channels-last (borders
 // of every image zero; guards zeroed by the caller) and, optionally, feats [I*K*K, C] fp32 channels-last (the values the
 // spatial attention averages, model/SpatialNet.py:109-112).  Block = (image, 64-channel tile), transposed through smem.
+// Single-plane mode: xb (bf16 planes of the padded matrix, row stride ldb) is written INSTEAD of the fp32 xp -- the convolution's A
+// operand directly, no 2.7 GB fp32 padded copy written and re-read by a cast at cfg4.
 __global__ void __launch_bounds__(256) nchw_to_padded_cl_kernel(const float* __restrict__ vid, int C, Geo g,
-                                                                float* __restrict__ xp, float* __restrict__ feats) {
+                                                                float* __restrict__ xp, float* __restrict__ feats,
+                                                                bf16* __restrict__ xb, long long ldb) {
   extern __shared__ float tile[];                       // [64][KK + 1]
   const int img = blockIdx.x, c0 = blockIdx.y * 64, KK = g.K * g.K, ldt = KK + 1;
   const float* src = vid + ((long long)img * C + c0) * KK;
@@ -54,7 +57,8 @@ __global__ void __launch_bounds__(256) nchw_to_padded_cl_kernel(const float* __r
     const bool in = y >= 1 && y <= g.K && x >= 1 && x <= g.K;
     const int cell = (y - 1) * g.K + (x - 1);
     const float v = in ? tile[c * ldt + cell] : 0.f;
-    xp[((long long)g.G + (long long)img * g.P + p) * C + c0 + c] = v;
+    if (xb) xb[((long long)g.G + (long long)img * g.P + p) * ldb + c0 + c] = __float2bfloat16_rn(v);
+    else xp[((long long)g.G + (long long)img * g.P + p) * C + c0 + c] = v;
     if (in && feats) feats[((long long)img * KK + cell) * C + c0 + c] = v;
   }
 }
@@ -72,31 +76,54 @@ __global__ void conv_weight_taps_kernel(const float* __restrict__ w, float* __re
 }
 
 // Per-channel sums over the INTERIOR rows of y [R, C]: sums[0][c] += sum y, sums[1][c] += sum y^2 (double accumulators).
-// Block = 32 channels x 8 row lanes over a chunk of rows.
+// Block = 32 channel quads (16-byte loads) x 8 row lanes over a chunk of rows, four rows in flight per thread; border rows (44 % of
+// the padded layout at K = 6) are never read.  (The first version read 4 bytes per thread and dependent iteration: these
+// reductions over 0.67 GB ran at ~1 TB/s and were 5 ms of the cfg4 step.)
 constexpr int BN_ROWS = 1024;
+constexpr int BN_UNROLL = 4;
+__device__ __forceinline__ void bn_block_reduce(float4 s, float4 q, bool two, int C, int c, double* __restrict__ sums) {
+  __shared__ float4 ps[8][33], pq[8][33];
+  const int rl = threadIdx.x >> 5, l = threadIdx.x & 31;
+  ps[rl][l] = s;
+  if (two) pq[rl][l] = q;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    float4 a = ps[0][l], b = two ? pq[0][l] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      const float4 x = ps[i][l];
+      a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+      if (two) { const float4 y = pq[i][l]; b.x += y.x; b.y += y.y; b.z += y.z; b.w += y.w; }
+    }
+    atomicAdd(sums + c, (double)a.x); atomicAdd(sums + c + 1, (double)a.y);
+    atomicAdd(sums + c + 2, (double)a.z); atomicAdd(sums + c + 3, (double)a.w);
+    if (two) {
+      atomicAdd(sums + C + c, (double)b.x); atomicAdd(sums + C + c + 1, (double)b.y);
+      atomicAdd(sums + C + c + 2, (double)b.z); atomicAdd(sums + C + c + 3, (double)b.w);
+    }
+  }
+}
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ y, int C, Geo g, double* __restrict__ sums) {
-  __shared__ float ps[8][33], pq[8][33];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4, rl = threadIdx.x >> 5;
   const long long r0 = (long long)blockIdx.y * BN_ROWS, r1 = min(g.R, r0 + BN_ROWS);
-  float s = 0.f, q = 0.f;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
   if (c < C) {
-    for (long long r = r0 + rl; r < r1; r += 8) {
-      int cell;
-      if (g.interior(r, cell)) {
-        const float v = y[r * C + c];
-        s += v; q += v * v;
+    for (long long r = r0 + rl; r < r1; r += 8 * BN_UNROLL) {
+      float4 v[BN_UNROLL];
+#pragma unroll
+      for (int u = 0; u < BN_UNROLL; ++u) {
+        const long long rr = r + 8 * u;
+        int cell;
+        v[u] = (rr < r1 && g.interior(rr, cell)) ? __ldg(reinterpret_cast<const float4*>(y + rr * C + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < BN_UNROLL; ++u) {
+        s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w;
+        q.x += v[u].x * v[u].x; q.y += v[u].y * v[u].y; q.z += v[u].z * v[u].z; q.w += v[u].w * v[u].w;
       }
     }
   }
-  ps[rl][threadIdx.x & 31] = s; pq[rl][threadIdx.x & 31] = q;
-  __syncthreads();
-  if (rl == 0 && c < C) {
-    float a = 0.f, b = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { a += ps[i][threadIdx.x]; b += pq[i][threadIdx.x]; }
-    atomicAdd(sums + c, (double)a);
-    atomicAdd(sums + C + c, (double)b);
-  }
+  bn_block_reduce(s, q, true, C, c, sums);
 }
 
 // mean / invstd from the sums (training) or from the running estimates (eval); training also updates the running estimates
@@ -126,7 +153,7 @@ __global__ void bn_finalize_kernel(const double* sums, int C, double count, floa
 __global__ void bn_relu_apply_kernel(const float* __restrict__ y, int C, Geo g, const float* __restrict__ mean,
                                      const float* __restrict__ invstd, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, float* __restrict__ padded_out,
-                                     float* __restrict__ compact_out) {
+                                     float* __restrict__ compact_out, bf16* __restrict__ padded_bf, long long ld_bf) {
   const long long total = g.R * (C / 4);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / (C / 4);
@@ -142,6 +169,12 @@ __global__ void bn_relu_apply_kernel(const float* __restrict__ y, int C, Geo g, 
       o.z = fmaxf((v.z - m.z) * is.z * ga.z + be.z, 0.f); o.w = fmaxf((v.w - m.w) * is.w * ga.w + be.w, 0.f);
     }
     if (padded_out) *reinterpret_cast<float4*>(padded_out + ((long long)g.G + r) * C + c) = o;
+    if (padded_bf) {               // single-plane mode: the next convolution's bf16 A operand directly
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const unsigned*>(&lo); pk.y = *reinterpret_cast<const unsigned*>(&hi);
+      *reinterpret_cast<uint2*>(padded_bf + ((long long)g.G + r) * ld_bf + c) = pk;
+    }
     if (compact_out && in) *reinterpret_cast<float4*>(compact_out + ((r / g.P) * (g.K * g.K) + cell) * C + c) = o;
   }
 }
@@ -154,31 +187,38 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_stats_kernel(const float* __r
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                 const float* __restrict__ dz, int dz_compact,
                                                                 double* __restrict__ sums) {
-  __shared__ float ps[8][33], pq[8][33];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4, rl = threadIdx.x >> 5;
   const long long r0 = (long long)blockIdx.y * BN_ROWS, r1 = min(g.R, r0 + BN_ROWS);
-  float s = 0.f, q = 0.f;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
   if (c < C) {
-    const float m = mean[c], is = invstd[c], ga = gamma[c], be = beta[c];
-    for (long long r = r0 + rl; r < r1; r += 8) {
-      int cell;
-      if (g.interior(r, cell)) {
-        const float xh = (y[r * C + c] - m) * is;
-        const long long dr = dz_compact ? (r / g.P) * (g.K * g.K) + cell : r;
-        const float d = (xh * ga + be > 0.f) ? dz[dr * C + c] : 0.f;
-        s += d; q += d * xh;
+    const float4 m = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+    for (long long r = r0 + rl; r < r1; r += 8 * BN_UNROLL) {
+      float4 v[BN_UNROLL], d[BN_UNROLL];
+      bool in[BN_UNROLL];
+#pragma unroll
+      for (int u = 0; u < BN_UNROLL; ++u) {
+        const long long rr = r + 8 * u;
+        int cell = 0;
+        in[u] = rr < r1 && g.interior(rr, cell);
+        if (in[u]) {
+          const long long dr = dz_compact ? (rr / g.P) * (g.K * g.K) + cell : rr;
+          v[u] = __ldg(reinterpret_cast<const float4*>(y + rr * C + c));
+          d[u] = __ldg(reinterpret_cast<const float4*>(dz + dr * C + c));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < BN_UNROLL; ++u) {
+        if (!in[u]) continue;
+        const float hx = (v[u].x - m.x) * is.x, hy = (v[u].y - m.y) * is.y, hz = (v[u].z - m.z) * is.z, hw = (v[u].w - m.w) * is.w;
+        const float dx = (hx * ga.x + be.x > 0.f) ? d[u].x : 0.f, dy = (hy * ga.y + be.y > 0.f) ? d[u].y : 0.f;
+        const float dzz = (hz * ga.z + be.z > 0.f) ? d[u].z : 0.f, dw = (hw * ga.w + be.w > 0.f) ? d[u].w : 0.f;
+        s.x += dx; s.y += dy; s.z += dzz; s.w += dw;
+        q.x += dx * hx; q.y += dy * hy; q.z += dzz * hz; q.w += dw * hw;
       }
     }
   }
-  ps[rl][threadIdx.x & 31] = s; pq[rl][threadIdx.x & 31] = q;
-  __syncthreads();
-  if (rl == 0 && c < C) {
-    float a = 0.f, b = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { a += ps[i][threadIdx.x]; b += pq[i][threadIdx.x]; }
-    atomicAdd(sums + c, (double)a);
-    atomicAdd(sums + C + c, (double)b);
-  }
+  bn_block_reduce(s, q, true, C, c, sums);
 }
 // pass 2: dy = gamma * invstd * (dyhat - dbeta / M - xhat * dgamma / M) on the interior rows (training; eval: gamma * invstd *
 // dyhat), zero on border rows, written at rows G + r of dy [Rtot, C]; also d gamma / d beta out (fp32).
@@ -187,42 +227,57 @@ __global__ void bn_relu_bwd_apply_kernel(const float* __restrict__ y, int C, Geo
                                          const float* __restrict__ beta, const float* __restrict__ dz, int dz_compact,
                                          const double* __restrict__ sums, double count, int training,
                                          float* __restrict__ dy) {
-  const long long total = g.R * C;
+  const int C4 = C / 4;
+  const long long total = g.R * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / C;
-    const int c = (int)(i % C);
+    const long long r = i / C4;
+    const int c = (int)(i % C4) * 4;
     int cell;
-    float o = 0.f;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (g.interior(r, cell)) {
-      const float is = invstd[c], ga = gamma[c];
-      const float xh = (y[i] - mean[c]) * is;
       const long long dr = dz_compact ? (r / g.P) * (g.K * g.K) + cell : r;
-      const float d = (xh * ga + beta[c] > 0.f) ? dz[dr * C + c] : 0.f;
-      o = training ? ga * is * (d - (float)(sums[c] / count) - xh * (float)(sums[C + c] / count)) : ga * is * d;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(y + r * C + c));
+      const float4 d = __ldg(reinterpret_cast<const float4*>(dz + dr * C + c));
+      const float4 m = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
+      const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+      const float vv[4] = {v.x, v.y, v.z, v.w}, dd[4] = {d.x, d.y, d.z, d.w}, mm[4] = {m.x, m.y, m.z, m.w};
+      const float ii[4] = {is.x, is.y, is.z, is.w}, gg[4] = {ga.x, ga.y, ga.z, ga.w}, bb[4] = {be.x, be.y, be.z, be.w};
+      float oo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float xh = (vv[e] - mm[e]) * ii[e];
+        const float dh = (xh * gg[e] + bb[e] > 0.f) ? dd[e] : 0.f;
+        oo[e] = training ? gg[e] * ii[e] * (dh - (float)(sums[c + e] / count) - xh * (float)(sums[C + c + e] / count)) : gg[e] * ii[e] * dh;
+      }
+      o = make_float4(oo[0], oo[1], oo[2], oo[3]);
     }
-    dy[((long long)g.G + r) * C + c] = o;
+    *reinterpret_cast<float4*>(dy + ((long long)g.G + r) * C + c) = o;
   }
 }
 __global__ void bn_param_grads_kernel(const double* sums, int C, float* dgamma, float* dbeta) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) { dbeta[c] = (float)sums[c]; dgamma[c] = (float)sums[C + c]; }
 }
-// out[c] = sum_r in[r, c] over R rows (double atomics; for the conv bias gradient on the zero-bordered dY)
-__global__ void __launch_bounds__(256) colsum_rows_kernel(const float* __restrict__ in, int C, long long R, double* __restrict__ sums) {
-  __shared__ float ps[8][33];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
-  const long long r0 = (long long)blockIdx.y * BN_ROWS, r1 = min(R, r0 + BN_ROWS);
-  float s = 0.f;
-  if (c < C)
-    for (long long r = r0 + rl; r < r1; r += 8) s += in[r * C + c];
-  ps[rl][threadIdx.x & 31] = s;
-  __syncthreads();
-  if (rl == 0 && c < C) {
-    float a = 0.f;
+// sums[c] += sum over the INTERIOR rows of in[r, c] (double atomics; the conv bias gradient on the zero-bordered dY: its border
+// rows are zero and are not read)
+__global__ void __launch_bounds__(256) colsum_rows_kernel(const float* __restrict__ in, int C, Geo g, double* __restrict__ sums) {
+  const int c = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4, rl = threadIdx.x >> 5;
+  const long long r0 = (long long)blockIdx.y * BN_ROWS, r1 = min(g.R, r0 + BN_ROWS);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+    for (long long r = r0 + rl; r < r1; r += 8 * BN_UNROLL) {
+      float4 v[BN_UNROLL];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a += ps[i][threadIdx.x];
-    atomicAdd(sums + c, (double)a);
+      for (int u = 0; u < BN_UNROLL; ++u) {
+        const long long rr = r + 8 * u;
+        int cell;
+        v[u] = (rr < r1 && g.interior(rr, cell)) ? __ldg(reinterpret_cast<const float4*>(in + rr * C + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < BN_UNROLL; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+    }
   }
+  bn_block_reduce(s, s, false, C, c, sums);
 }
 __global__ void double_to_float_kernel(const double* in, float* out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -289,11 +344,21 @@ bool fused_taps(int ns, int Ci, int Co) {
 }
 
 // y[R, Co] = bias + sum_s X[. + off_s] W_s^T
+// single-plane mode with 64-aligned channels: the producer of a layer's padded input writes its bf16 planes directly (no fp32 xpf)
+bool direct_planes(int ns, int Ci) {
+  static const bool off = getenv("PVCR_NO_FRONT_DIRECT_BF16") != nullptr;       // A/B knob
+  return !off && ns == 1 && Ci % 64 == 0;
+}
+int zero_plane_guards(const Geo& g, const Layer& l, cudaStream_t st) {
+  PVCR_TRY(fill_zero(l.xp.ptr, sizeof(bf16) * (size_t)g.G * l.xp.ld, st));
+  return fill_zero(l.xp.ptr + ((size_t)g.G + g.R) * l.xp.ld, sizeof(bf16) * (size_t)g.G * l.xp.ld, st);
+}
+
 int conv_forward(const Geo& g, const Layer& l, const float* w, const float* bias, int ns, cudaStream_t st) {
   const long long n = (long long)9 * l.Co * l.Ci;
   conv_weight_taps_kernel<<<grid_for(n), 256, 0, st>>>(w, l.wtaps, n, l.Co, l.Ci, 1);
   PVCR_CUDA_CHECK(cudaGetLastError());
-  PVCR_TRY(stage(l.xpf, l.Ci, (int)g.Rtot, l.Ci, l.xp, 0, nullptr, NO_DROPOUT, st));
+  if (!direct_planes(ns, l.Ci)) PVCR_TRY(stage(l.xpf, l.Ci, (int)g.Rtot, l.Ci, l.xp, 0, nullptr, NO_DROPOUT, st));
   if (fused_taps(ns, l.Ci, l.Co)) {
     int off[9];
     for (int s = 0; s < 9; ++s) {
@@ -314,18 +379,23 @@ int conv_forward(const Geo& g, const Layer& l, const float* w, const float* bias
 }
 
 int bn_forward(const Geo& g, const Layer& l, const float* gamma, const float* beta, float* running_mean, float* running_var,
-               int training, float eps, float momentum, float* padded_out, float* compact_out, cudaStream_t st) {
+               int training, float eps, float momentum, float* padded_out, float* compact_out, cudaStream_t st,
+               bf16* padded_bf = nullptr, long long ld_bf = 0) {
   const int C = l.Co;
   PVCR_REQUIRE(C % 4 == 0, "spatial front: channel count %d must be a multiple of 4", C);
   if (training) {
     PVCR_TRY(fill_zero(l.sums, sizeof(double) * 2 * C, st));
-    bn_stats_kernel<<<dim3(cdiv(C, 32), (unsigned)cdiv(g.R, BN_ROWS)), 256, 0, st>>>(l.y, C, g, l.sums);
+    { LaunchScope ls_(KC_MISC, st);
+    bn_stats_kernel<<<dim3(cdiv(C, 128), (unsigned)cdiv(g.R, BN_ROWS)), 256, 0, st>>>(l.y, C, g, l.sums);
+    }
     PVCR_CUDA_CHECK(cudaGetLastError());
   }
   bn_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(l.sums, C, (double)g.I * g.K * g.K, eps, momentum, training, running_mean,
                                                    running_var, l.mean, l.invstd);
   PVCR_CUDA_CHECK(cudaGetLastError());
-  bn_relu_apply_kernel<<<grid_for(g.R * (C / 4)), 256, 0, st>>>(l.y, C, g, l.mean, l.invstd, gamma, beta, padded_out, compact_out);
+  { LaunchScope ls_(KC_MISC, st);
+  bn_relu_apply_kernel<<<grid_for(g.R * (C / 4)), 256, 0, st>>>(l.y, C, g, l.mean, l.invstd, gamma, beta, padded_out, compact_out, padded_bf, ld_bf);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
 }
@@ -334,14 +404,19 @@ int bn_forward(const Geo& g, const Layer& l, const float* gamma, const float* be
 int bn_backward(const Geo& g, const Layer& l, const float* gamma, const float* beta, const float* dz, int dz_compact,
                 int training, float* dgamma, float* dbeta, cudaStream_t st) {
   const int C = l.Co;
+  PVCR_REQUIRE(C % 4 == 0, "spatial front: channel count %d must be a multiple of 4", C);
   PVCR_TRY(fill_zero(l.sums, sizeof(double) * 2 * C, st));
-  bn_relu_bwd_stats_kernel<<<dim3(cdiv(C, 32), (unsigned)cdiv(g.R, BN_ROWS)), 256, 0, st>>>(l.y, C, g, l.mean, l.invstd, gamma, beta,
+  { LaunchScope ls_(KC_MISC, st);
+  bn_relu_bwd_stats_kernel<<<dim3(cdiv(C, 128), (unsigned)cdiv(g.R, BN_ROWS)), 256, 0, st>>>(l.y, C, g, l.mean, l.invstd, gamma, beta,
                                                                                           dz, dz_compact, l.sums);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   PVCR_TRY(fill_zero(l.dy, sizeof(float) * (size_t)g.G * C, st));
   PVCR_TRY(fill_zero(l.dy + ((size_t)g.G + g.R) * C, sizeof(float) * (size_t)g.G * C, st));
-  bn_relu_bwd_apply_kernel<<<grid_for(g.R * C), 256, 0, st>>>(l.y, C, g, l.mean, l.invstd, gamma, beta, dz, dz_compact, l.sums,
+  { LaunchScope ls_(KC_MISC, st);
+  bn_relu_bwd_apply_kernel<<<grid_for(g.R * (C / 4)), 256, 0, st>>>(l.y, C, g, l.mean, l.invstd, gamma, beta, dz, dz_compact, l.sums,
                                                              (double)g.I * g.K * g.K, training, l.dy);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   bn_param_grads_kernel<<<cdiv(C, 128), 128, 0, st>>>(l.sums, C, dgamma, dbeta);
   PVCR_CUDA_CHECK(cudaGetLastError());
@@ -353,7 +428,9 @@ int conv_backward(Arena& a, const Geo& g, const Layer& l, int ns, float* dw, flo
   const int Co = l.Co, Ci = l.Ci;
   // d bias = column sums of dY (borders are zero)
   PVCR_TRY(fill_zero(l.sums, sizeof(double) * Co, st));
-  colsum_rows_kernel<<<dim3(cdiv(Co, 32), (unsigned)cdiv(g.R, BN_ROWS)), 256, 0, st>>>(l.dy + (size_t)g.G * Co, Co, g.R, l.sums);
+  { LaunchScope ls_(KC_MISC, st);
+  colsum_rows_kernel<<<dim3(cdiv(Co, 128), (unsigned)cdiv(g.R, BN_ROWS)), 256, 0, st>>>(l.dy + (size_t)g.G * Co, Co, g, l.sums);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   double_to_float_kernel<<<cdiv(Co, 128), 128, 0, st>>>(l.sums, dbias, Co);
   PVCR_CUDA_CHECK(cudaGetLastError());
@@ -427,13 +504,19 @@ int spatial_front_fwd(int I, int K, int F, int H, int nsplit, const float* vid, 
   const Geo& g = w.g;
   // guards of both padded inputs
   for (Layer* l : {&w.l1, &w.l2}) {
+    if (direct_planes(nsplit, l->Ci)) { PVCR_TRY(zero_plane_guards(g, *l, st)); continue; }
     PVCR_TRY(fill_zero(l->xpf, sizeof(float) * (size_t)g.G * l->Ci, st));
     PVCR_TRY(fill_zero(l->xpf + ((size_t)g.G + g.R) * l->Ci, sizeof(float) * (size_t)g.G * l->Ci, st));
   }
-  nchw_to_padded_cl_kernel<<<dim3(I, cdiv(F, 64)), 256, sizeof(float) * 64 * (K * K + 1), st>>>(vid, F, g, w.l1.xpf, feats_cl);
+  const bool d1 = direct_planes(nsplit, F), d2 = direct_planes(nsplit, H);
+  { LaunchScope ls_(KC_MISC, st);
+  nchw_to_padded_cl_kernel<<<dim3(I, cdiv(F, 64)), 256, sizeof(float) * 64 * (K * K + 1), st>>>(vid, F, g, d1 ? nullptr : w.l1.xpf, feats_cl,
+                                                                                               d1 ? w.l1.xp.ptr : nullptr, w.l1.xp.ld);
+  }
   PVCR_CUDA_CHECK(cudaGetLastError());
   PVCR_TRY(conv_forward(g, w.l1, p.conv1_w, p.conv1_b, nsplit, st));
-  PVCR_TRY(bn_forward(g, w.l1, p.bn1_w, p.bn1_b, running1_mean, running1_var, training, eps, momentum, w.l2.xpf, nullptr, st));
+  PVCR_TRY(bn_forward(g, w.l1, p.bn1_w, p.bn1_b, running1_mean, running1_var, training, eps, momentum, d2 ? nullptr : w.l2.xpf, nullptr, st,
+                      d2 ? w.l2.xp.ptr : nullptr, w.l2.xp.ld));
   PVCR_TRY(conv_forward(g, w.l2, p.conv2_w, p.conv2_b, nsplit, st));
   PVCR_TRY(bn_forward(g, w.l2, p.bn2_w, p.bn2_b, running2_mean, running2_var, training, eps, momentum, nullptr, conv_feats, st));
   return PVCR_OK;
