@@ -23,8 +23,12 @@ namespace {
 struct Geo {
   int I, K, Kp, P, G;          // images, grid, padded grid, padded cells per image, guard rows
   long long R, Rtot;           // I*P rows that the GEMMs produce; R + 2G rows allocated
-  __host__ __device__ bool interior(long long r, int& cell) const {
-    const int p = (int)(r % P), y = p / Kp, x = p - y * Kp;
+  // interior test in 32-bit arithmetic for row r0 + k of a chunk whose first row r0 sits at position p0 = r0 % P of its image
+  // (the kernels compute p0 and r0 / P once per thread): dimg = images past r0's, cell = interior cell index
+  __host__ __device__ bool interior_at(int p0, int k, int& cell, int& dimg) const {
+    const int pk = p0 + k;
+    dimg = pk / P;
+    const int p = pk - dimg * P, y = p / Kp, x = p - y * Kp;
     cell = (y - 1) * K + (x - 1);
     return y >= 1 && y <= K && x >= 1 && x <= K;
   }
@@ -44,22 +48,43 @@ Geo make_geo(int I, int K) {
 __global__ void __launch_bounds__(256) nchw_to_padded_cl_kernel(const float* __restrict__ vid, int C, Geo g,
                                                                 float* __restrict__ xp, float* __restrict__ feats,
                                                                 bf16* __restrict__ xb, long long ldb) {
-  extern __shared__ float tile[];                       // [64][KK + 1]
-  const int img = blockIdx.x, c0 = blockIdx.y * 64, KK = g.K * g.K, ldt = KK + 1;
+  extern __shared__ float tile[];                       // [KK][65] cell-major, then the cell of every padded position (-1: border)
+  const int img = blockIdx.x, c0 = blockIdx.y * 64, KK = g.K * g.K;
+  int* tab = reinterpret_cast<int*>(tile + KK * 65);
   const float* src = vid + ((long long)img * C + c0) * KK;
   const int nch = min(64, C - c0);
-  for (int i = threadIdx.x; i < nch * KK; i += blockDim.x) tile[(i / KK) * ldt + (i % KK)] = src[i];
-  __syncthreads();
-  for (int i = threadIdx.x; i < g.P * 64; i += blockDim.x) {
-    const int p = i >> 6, c = i & 63;
-    if (c >= nch) continue;
+  for (int p = threadIdx.x; p < g.P; p += 256) {
     const int y = p / g.Kp, x = p - y * g.Kp;
-    const bool in = y >= 1 && y <= g.K && x >= 1 && x <= g.K;
-    const int cell = (y - 1) * g.K + (x - 1);
-    const float v = in ? tile[c * ldt + cell] : 0.f;
-    if (xb) xb[((long long)g.G + (long long)img * g.P + p) * ldb + c0 + c] = __float2bfloat16_rn(v);
-    else xp[((long long)g.G + (long long)img * g.P + p) * C + c0 + c] = v;
-    if (in && feats) feats[((long long)img * KK + cell) * C + c0 + c] = v;
+    tab[p] = (y >= 1 && y <= g.K && x >= 1 && x <= g.K) ? (y - 1) * g.K + (x - 1) : -1;
+  }
+  {                                                     // element i = (channel i / KK, cell i % KK), advanced without divisions
+    int ch = threadIdx.x / KK, ce = threadIdx.x - ch * KK;
+    const int dq = 256 / KK, dr = 256 - dq * KK;
+    for (int i = threadIdx.x; i < nch * KK; i += 256) {
+      tile[ce * 65 + ch] = __ldcs(src + i);
+      ch += dq; ce += dr;
+      if (ce >= KK) { ce -= KK; ++ch; }
+    }
+  }
+  __syncthreads();
+  const long long row0 = (long long)g.G + (long long)img * g.P;
+  if (nch == 64 && xb && (C & 1) == 0) {                // two channels per thread: 128-byte bf16 / 256-byte fp32 rows per warp
+    for (int i = threadIdx.x; i < g.P * 32; i += 256) {
+      const int p = i >> 5, c = (i & 31) * 2, cell = tab[p];
+      float v0 = 0.f, v1 = 0.f;
+      if (cell >= 0) { v0 = tile[cell * 65 + c]; v1 = tile[cell * 65 + c + 1]; }
+      *reinterpret_cast<__nv_bfloat162*>(xb + (row0 + p) * ldb + c0 + c) = __floats2bfloat162_rn(v0, v1);
+      if (cell >= 0 && feats) *reinterpret_cast<float2*>(feats + ((long long)img * KK + cell) * C + c0 + c) = make_float2(v0, v1);
+    }
+    return;
+  }
+  for (int i = threadIdx.x; i < g.P * 64; i += 256) {
+    const int p = i >> 6, c = i & 63, cell = tab[p];
+    if (c >= nch) continue;
+    const float v = cell >= 0 ? tile[cell * 65 + c] : 0.f;
+    if (xb) xb[(row0 + p) * ldb + c0 + c] = __float2bfloat16_rn(v);
+    else xp[(row0 + p) * C + c0 + c] = v;
+    if (cell >= 0 && feats) feats[((long long)img * KK + cell) * C + c0 + c] = v;
   }
 }
 
@@ -108,13 +133,16 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
   const long long r0 = (long long)blockIdx.y * BN_ROWS, r1 = min(g.R, r0 + BN_ROWS);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
   if (c < C) {
-    for (long long r = r0 + rl; r < r1; r += 8 * BN_UNROLL) {
+    const int p0 = (int)(r0 % g.P), n = (int)(r1 - r0);
+    const float* yb = y + r0 * C + c;
+    for (int k0 = rl; k0 < n; k0 += 8 * BN_UNROLL) {
       float4 v[BN_UNROLL];
 #pragma unroll
       for (int u = 0; u < BN_UNROLL; ++u) {
-        const long long rr = r + 8 * u;
-        int cell;
-        v[u] = (rr < r1 && g.interior(rr, cell)) ? __ldg(reinterpret_cast<const float4*>(y + rr * C + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int k = k0 + 8 * u;
+        int cell, dimg;
+        v[u] = (k < n && g.interior_at(p0, k, cell, dimg)) ? __ldg(reinterpret_cast<const float4*>(yb + (long long)k * C))
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int u = 0; u < BN_UNROLL; ++u) {
@@ -148,18 +176,22 @@ __global__ void bn_finalize_kernel(const double* sums, int C, double count, floa
   }
 }
 
+constexpr int APPLY_ROWS = 32;      // rows per block of the two apply kernels (32-bit index arithmetic inside a block)
 // z = relu((y - mean) * invstd * gamma + beta) on the interior rows.  padded_out [Rtot, C]: zero on border rows (the next
 // convolution's zero padding); compact_out [I*K*K, C]: interior rows only (what the attention consumes).
 __global__ void bn_relu_apply_kernel(const float* __restrict__ y, int C, Geo g, const float* __restrict__ mean,
                                      const float* __restrict__ invstd, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, float* __restrict__ padded_out,
                                      float* __restrict__ compact_out, bf16* __restrict__ padded_bf, long long ld_bf) {
-  const long long total = g.R * (C / 4);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / (C / 4);
-    const int c = (int)(i % (C / 4)) * 4;
-    int cell;
-    const bool in = g.interior(r, cell);
+  const int C4 = C / 4;
+  const long long r0 = (long long)blockIdx.x * APPLY_ROWS;
+  const int n = (int)min((long long)APPLY_ROWS, g.R - r0), p0 = (int)(r0 % g.P);
+  const long long img0 = r0 / g.P;
+  for (int i = threadIdx.x; i < n * C4; i += blockDim.x) {
+    const int k = i / C4, c = (i - k * C4) * 4;
+    const long long r = r0 + k;
+    int cell, dimg;
+    const bool in = g.interior_at(p0, k, cell, dimg);
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (in) {
       const float4 v = *reinterpret_cast<const float4*>(y + r * C + c);
@@ -175,7 +207,7 @@ __global__ void bn_relu_apply_kernel(const float* __restrict__ y, int C, Geo g, 
       pk.x = *reinterpret_cast<const unsigned*>(&lo); pk.y = *reinterpret_cast<const unsigned*>(&hi);
       *reinterpret_cast<uint2*>(padded_bf + ((long long)g.G + r) * ld_bf + c) = pk;
     }
-    if (compact_out && in) *reinterpret_cast<float4*>(compact_out + ((r / g.P) * (g.K * g.K) + cell) * C + c) = o;
+    if (compact_out && in) *reinterpret_cast<float4*>(compact_out + ((img0 + dimg) * (g.K * g.K) + cell) * C + c) = o;
   }
 }
 
@@ -193,16 +225,19 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_stats_kernel(const float* __r
   if (c < C) {
     const float4 m = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
     const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
-    for (long long r = r0 + rl; r < r1; r += 8 * BN_UNROLL) {
+    const int p0 = (int)(r0 % g.P), n = (int)(r1 - r0);
+    const long long img0 = r0 / g.P;
+    for (int k0 = rl; k0 < n; k0 += 8 * BN_UNROLL) {
       float4 v[BN_UNROLL], d[BN_UNROLL];
       bool in[BN_UNROLL];
 #pragma unroll
       for (int u = 0; u < BN_UNROLL; ++u) {
-        const long long rr = r + 8 * u;
-        int cell = 0;
-        in[u] = rr < r1 && g.interior(rr, cell);
+        const int k = k0 + 8 * u;
+        int cell = 0, dimg = 0;
+        in[u] = k < n && g.interior_at(p0, k, cell, dimg);
         if (in[u]) {
-          const long long dr = dz_compact ? (rr / g.P) * (g.K * g.K) + cell : rr;
+          const long long rr = r0 + k;
+          const long long dr = dz_compact ? (img0 + dimg) * (g.K * g.K) + cell : rr;
           v[u] = __ldg(reinterpret_cast<const float4*>(y + rr * C + c));
           d[u] = __ldg(reinterpret_cast<const float4*>(dz + dr * C + c));
         }
@@ -228,14 +263,16 @@ __global__ void bn_relu_bwd_apply_kernel(const float* __restrict__ y, int C, Geo
                                          const double* __restrict__ sums, double count, int training,
                                          float* __restrict__ dy) {
   const int C4 = C / 4;
-  const long long total = g.R * C4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / C4;
-    const int c = (int)(i % C4) * 4;
-    int cell;
+  const long long r0 = (long long)blockIdx.x * APPLY_ROWS;
+  const int n = (int)min((long long)APPLY_ROWS, g.R - r0), p0 = (int)(r0 % g.P);
+  const long long img0 = r0 / g.P;
+  for (int i = threadIdx.x; i < n * C4; i += blockDim.x) {
+    const int k = i / C4, c = (i - k * C4) * 4;
+    const long long r = r0 + k;
+    int cell, dimg;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (g.interior(r, cell)) {
-      const long long dr = dz_compact ? (r / g.P) * (g.K * g.K) + cell : r;
+    if (g.interior_at(p0, k, cell, dimg)) {
+      const long long dr = dz_compact ? (img0 + dimg) * (g.K * g.K) + cell : r;
       const float4 v = __ldg(reinterpret_cast<const float4*>(y + r * C + c));
       const float4 d = __ldg(reinterpret_cast<const float4*>(dz + dr * C + c));
       const float4 m = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
@@ -265,13 +302,16 @@ __global__ void __launch_bounds__(256) colsum_rows_kernel(const float* __restric
   const long long r0 = (long long)blockIdx.y * BN_ROWS, r1 = min(g.R, r0 + BN_ROWS);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (c < C) {
-    for (long long r = r0 + rl; r < r1; r += 8 * BN_UNROLL) {
+    const int p0 = (int)(r0 % g.P), n = (int)(r1 - r0);
+    const float* ib = in + r0 * C + c;
+    for (int k0 = rl; k0 < n; k0 += 8 * BN_UNROLL) {
       float4 v[BN_UNROLL];
 #pragma unroll
       for (int u = 0; u < BN_UNROLL; ++u) {
-        const long long rr = r + 8 * u;
-        int cell;
-        v[u] = (rr < r1 && g.interior(rr, cell)) ? __ldg(reinterpret_cast<const float4*>(in + rr * C + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int k = k0 + 8 * u;
+        int cell, dimg;
+        v[u] = (k < n && g.interior_at(p0, k, cell, dimg)) ? __ldg(reinterpret_cast<const float4*>(ib + (long long)k * C))
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int u = 0; u < BN_UNROLL; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
@@ -394,7 +434,7 @@ int bn_forward(const Geo& g, const Layer& l, const float* gamma, const float* be
                                                    running_var, l.mean, l.invstd);
   PVCR_CUDA_CHECK(cudaGetLastError());
   { LaunchScope ls_(KC_MISC, st);
-  bn_relu_apply_kernel<<<grid_for(g.R * (C / 4)), 256, 0, st>>>(l.y, C, g, l.mean, l.invstd, gamma, beta, padded_out, compact_out, padded_bf, ld_bf);
+  bn_relu_apply_kernel<<<(unsigned)cdiv(g.R, APPLY_ROWS), 256, 0, st>>>(l.y, C, g, l.mean, l.invstd, gamma, beta, padded_out, compact_out, padded_bf, ld_bf);
   }
   PVCR_CUDA_CHECK(cudaGetLastError());
   return PVCR_OK;
@@ -414,7 +454,7 @@ int bn_backward(const Geo& g, const Layer& l, const float* gamma, const float* b
   PVCR_TRY(fill_zero(l.dy, sizeof(float) * (size_t)g.G * C, st));
   PVCR_TRY(fill_zero(l.dy + ((size_t)g.G + g.R) * C, sizeof(float) * (size_t)g.G * C, st));
   { LaunchScope ls_(KC_MISC, st);
-  bn_relu_bwd_apply_kernel<<<grid_for(g.R * (C / 4)), 256, 0, st>>>(l.y, C, g, l.mean, l.invstd, gamma, beta, dz, dz_compact, l.sums,
+  bn_relu_bwd_apply_kernel<<<(unsigned)cdiv(g.R, APPLY_ROWS), 256, 0, st>>>(l.y, C, g, l.mean, l.invstd, gamma, beta, dz, dz_compact, l.sums,
                                                              (double)g.I * g.K * g.K, training, l.dy);
   }
   PVCR_CUDA_CHECK(cudaGetLastError());
@@ -510,7 +550,7 @@ int spatial_front_fwd(int I, int K, int F, int H, int nsplit, const float* vid, 
   }
   const bool d1 = direct_planes(nsplit, F), d2 = direct_planes(nsplit, H);
   { LaunchScope ls_(KC_MISC, st);
-  nchw_to_padded_cl_kernel<<<dim3(I, cdiv(F, 64)), 256, sizeof(float) * 64 * (K * K + 1), st>>>(vid, F, g, d1 ? nullptr : w.l1.xpf, feats_cl,
+  nchw_to_padded_cl_kernel<<<dim3(I, cdiv(F, 64)), 256, sizeof(float) * (65 * K * K + g.P), st>>>(vid, F, g, d1 ? nullptr : w.l1.xpf, feats_cl,
                                                                                                d1 ? w.l1.xp.ptr : nullptr, w.l1.xp.ld);
   }
   PVCR_CUDA_CHECK(cudaGetLastError());

@@ -49,11 +49,15 @@ L_ = _lib.lib()
 ms = timed(ours)
 L_.pvcr_prof_reset(); L_.pvcr_prof_enable(1)
 ours(); torch.cuda.synchronize()
-prof = _lib.prof_read(); L_.pvcr_prof_enable(0)
+prof = _lib.prof_read(); launches = _lib.prof_launch_list(); L_.pvcr_prof_enable(0)
 conv_flops_useful = 2 * B * N * K * K * 9 * (F * H + H * H) * 3 - 2 * B * N * K * K * 9 * F * H      # fwd + dW + dX (no dX for layer 1)
 out["ours"] = {"ms_per_step": ms, "videos_per_s": B / (ms / 1e3), "loss": float(ours().item()),
                "class_ms": {k: round(v[1], 3) for k, v in prof.items() if v[0]},
                "gemm_executed_tflop": prof["gemm_tcgen05"][2] / 1e12, "conv_useful_tflop": conv_flops_useful / 1e12}
+out["ours"]["launches"] = len(launches)
+out["ours"]["misc_launch_ms"] = [round(ms, 3) for cls, ms, _ in launches if cls == "misc" and ms > 0.05]
+out["ours"]["staging_launch_ms"] = [round(ms, 3) for cls, ms, _ in launches if cls == "operand_staging" and ms > 0.05]
+out["ours"]["gemm_launch_ms"] = [round(ms, 3) for cls, ms, _ in launches if cls == "gemm_tcgen05" and ms > 0.2]
 if os.environ.get("PVCR_PROBE_GRAPH"):
     # host-side time of one eager step (launch-bound?) and the same step captured as ONE CUDA graph (autograd tape inside the capture)
     torch.cuda.synchronize()
