@@ -2,15 +2,19 @@
 // (reference model/SpatialNet.py:76-86,106: self.conv = Sequential(Conv2d(F, H, 3, 1, 1), BatchNorm2d(H), ReLU(),
 // Conv2d(H, H, 3, 1, 1), BatchNorm2d(H), ReLU()) applied to vid_feats.view(B*N, F, K, K)), forward and hand-written backward.
 //
-// Convolution = implicit GEMM on the tcgen05 GEMM kernels over a FLAT ZERO-PADDED channels-last layout: image i, padded
-// cell (y, x) in [0, K+2)^2 is row G + i*P + y*(K+2) + x of a [rows, channels] matrix (P = (K+2)^2, G guard rows of zeros
-// at both ends).  In that layout a 3x3 tap (dy, dx) is a ROW OFFSET dy*(K+2) + dx, so
-//     Y[r, :] = b + sum_{taps s} X[r + off_s, :] W_s^T            (valid for the interior rows; border rows are discarded)
+// Convolution = implicit GEMM on the tcgen05 GEMM kernels over a FLAT ZERO-PADDED channels-last layout with SHARED padding:
+// image i, position (y, x) in [0, K+1)^2 is row G + i*P + y*(K+1) + x of a [rows, channels] matrix (P = (K+1)^2, G guard rows
+// of zeros at both ends); cells y < K, x < K are the image, column x = K and line y = K are zeros.  The zero column is the right
+// padding of its line AND the left padding of the next one, the zero line the bottom padding of its image AND the top padding
+// of the next (the first image's top / left neighbours are the guard rows).  In that layout a 3x3 tap (dy, dx) is a ROW
+// OFFSET dy*(K+1) + dx, so
+//     Y[r, :] = b + sum_{taps s} X[r + off_s, :] W_s^T            (valid for the image rows; zero rows/columns are discarded)
 // is nine GEMMs on shifted views of the same bf16 planes accumulating into one fp32 output -- no im2col tensor.  The same
 // holds backwards: dX[r, :] = sum_s dY[r - off_s, :] W_s on the zero-bordered dY, and dW_s = X[. + off_s]^T dY is a
-// contraction over the rows (MN-major tcgen05 operands: both matrices as they lie).  Cost of the padding: (K+2)^2 / K^2 of
-// the useful FLOPs (1.78x at K = 6).  BatchNorm uses batch statistics over the interior rows in training (biased variance
-// for the normalisation, unbiased for the running estimate, momentum 0.1, eps 1e-5 -- torch.nn.BatchNorm2d defaults).
+// contraction over the rows (MN-major tcgen05 operands: both matrices as they lie).  Cost of the padding: (K+1)^2 / K^2 of
+// the useful FLOPs (1.36x at K = 6; a private border per image, (K+2)^2 rows, cost 1.78x).  BatchNorm uses batch statistics
+// over the image rows in training (biased variance for the normalisation, unbiased for the running estimate, momentum 0.1,
+// eps 1e-5 -- torch.nn.BatchNorm2d defaults).
 #include <cstdlib>
 
 #include "../../include/pvcr_b200.h"
@@ -21,7 +25,7 @@ namespace pvcr {
 namespace {
 
 struct Geo {
-  int I, K, Kp, P, G;          // images, grid, padded grid, padded cells per image, guard rows
+  int I, K, Kp, P, G;          // images, grid, line width K + 1, positions per image (K + 1)^2, guard rows
   long long R, Rtot;           // I*P rows that the GEMMs produce; R + 2G rows allocated
   // interior test in 32-bit arithmetic for row r0 + k of a chunk whose first row r0 sits at position p0 = r0 % P of its image
   // (the kernels compute p0 and r0 / P once per thread): dimg = images past r0's, cell = interior cell index
@@ -29,13 +33,13 @@ struct Geo {
     const int pk = p0 + k;
     dimg = pk / P;
     const int p = pk - dimg * P, y = p / Kp, x = p - y * Kp;
-    cell = (y - 1) * K + (x - 1);
-    return y >= 1 && y <= K && x >= 1 && x <= K;
+    cell = y * K + x;
+    return y < K && x < K;
   }
 };
 Geo make_geo(int I, int K) {
   Geo g;
-  g.I = I; g.K = K; g.Kp = K + 2; g.P = g.Kp * g.Kp; g.G = (int)round_up(g.Kp + 1, 8);
+  g.I = I; g.K = K; g.Kp = K + 1; g.P = g.Kp * g.Kp; g.G = (int)round_up(g.Kp + 1, 8);
   g.R = (long long)I * g.P; g.Rtot = g.R + 2 * g.G;
   return g;
 }
@@ -55,7 +59,7 @@ __global__ void __launch_bounds__(256) nchw_to_padded_cl_kernel(const float* __r
   const int nch = min(64, C - c0);
   for (int p = threadIdx.x; p < g.P; p += 256) {
     const int y = p / g.Kp, x = p - y * g.Kp;
-    tab[p] = (y >= 1 && y <= g.K && x >= 1 && x <= g.K) ? (y - 1) * g.K + (x - 1) : -1;
+    tab[p] = (y < g.K && x < g.K) ? y * g.K + x : -1;
   }
   {                                                     // element i = (channel i / KK, cell i % KK), advanced without divisions
     int ch = threadIdx.x / KK, ce = threadIdx.x - ch * KK;

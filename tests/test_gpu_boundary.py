@@ -219,6 +219,9 @@ def test_spatialnet_frame_sweep_vs_stepwise(precision, tol, monkeypatch):
     assert (a0 - a1).abs().max().item() < tol
     assert set(g0) == set(g1)
     for k in g0:
+        if k in ("conv.0.bias", "conv.3.bias"):      # a bias in front of a batch-statistics BatchNorm: zero gradient up to rounding
+            assert g0[k].norm().item() < 1e-6 and g1[k].norm().item() < 1e-6, k
+            continue
         e = relerr(g1[k].double().cpu().numpy(), g0[k].double().cpu().numpy())
         assert e < tol or g0[k].norm().item() < 1e-9, (k, e)
     # the same step as one CUDA graph: same kernels, same order -> the eager result to rounding of the atomics
@@ -226,7 +229,7 @@ def test_spatialnet_frame_sweep_vs_stepwise(precision, tol, monkeypatch):
     lg = gs.replay().item()
     assert abs(lg - l1) < 1e-5 * abs(l1)
     for k, prm in net.named_parameters():
-        if k in g1:
+        if k in g1 and k not in ("conv.0.bias", "conv.3.bias"):
             e = relerr(prm.grad.double().cpu().numpy(), g1[k].double().cpu().numpy())
             assert e < 1e-4 or g1[k].norm().item() < 1e-9, (k, e)
 
