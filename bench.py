@@ -587,6 +587,36 @@ def run_ours(args):
         torch.cuda.empty_cache()
         eager = eager_b200_reference(args.dropout)
 
+    # BASELINE.json configs[3]: SpatialNet fwd + masked loss + bwd on synthetic grid features (B x 40 frames x 2048
+    # channels x 6 x 6 cells), the whole step as one CUDA graph with the autograd tape inside (GraphedAutogradStep).  An extra
+    # key beside the headline; its parity is tests/test_gpu_boundary.py and tests/test_gpu_spatial_front.py.
+    spatial = None
+    if world == 1 and not args.no_spatial and args.workload == "cfg2":
+        try:
+            torch.cuda.empty_cache()
+            from pvcr_b200 import train_utils as TU
+            from pvcr_b200.graphs import GraphedAutogradStep
+            from pvcr_b200.model import SpatialNet
+            Fs, Ks = 2048, 6
+            net = SpatialNet(g, args.dropout, H, Fs, L, "s2vt-att", precision=args.precision).to(dev).train()
+            vid4 = torch.randn(B, N, Fs, Ks, Ks, device=dev)
+            crit = torch.nn.CrossEntropyLoss(reduction="none")
+            gs4 = GraphedAutogradStep(net, lambda: TU.calc_masked_loss(net(vid4, s)[0], s, s_len, crit))
+            for _ in range(2):
+                gs4.replay()
+            k4 = max(3, args.steps // 4)
+            ms_4 = timed(gs4.replay, k4) / k4
+            conv_tflop = 2 * B * N * Ks * Ks * 9 * (Fs * H + H * H) * 3 / 1e12 - 2 * B * N * Ks * Ks * 9 * Fs * H / 1e12
+            spatial = {"value": B / (ms_4 / 1e3), "unit": "videos/s", "ms_per_step": ms_4, "steps": k4,
+                       "loss": float(gs4.static_loss.item()), "conv_useful_tflop_per_step": conv_tflop,
+                       "workload": "cfg4_spatialnet: B=%d x %d frames x %d channels x %dx%d cells, H=%d, L=%d, Vc=%d, dropout %.1f, %s; "
+                                   "fwd + calc_masked_loss + bwd, one CUDA graph, input resident (1.5 GB: larger than L2)"
+                                   % (B, N, Fs, Ks, Ks, H, L, Vc, args.dropout, args.precision)}
+            del gs4, net, vid4
+            torch.cuda.empty_cache()
+        except Exception as e:            # noqa: BLE001  (an extra key must not take the headline line down)
+            spatial = {"error": repr(e)[:300]}
+
     out = {
         "metric": METRIC, "value": B * world / (ms_step / 1e3), "unit": "videos/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
@@ -597,6 +627,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "greedy": greedy, "with_optimizer": with_opt,
         "reference_eager_b200": eager, "dp_check": dp_check, "precision_bf16x2": x2,
+        "spatialnet_cfg4": spatial,
     }
     print(json.dumps(out), flush=True)
     _finish_ranks(world)
@@ -617,6 +648,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"],
                     help="cfg2 = S2VTAtt (BASELINE.json's metric config, default); cfg3 = RationaleNet + S2VTAtt joint training")
     ap.add_argument("--no-eager", action="store_true", help="skip timing the reference modules in PyTorch eager on the GPU")
+    ap.add_argument("--no-spatial", action="store_true", help="skip timing SpatialNet (BASELINE.json configs[3])")
     ap.add_argument("--nccl-ctas", type=int, default=16)
     ap.add_argument("--nccl-tail-ctas", type=int, default=64)
     args = ap.parse_args()
