@@ -681,15 +681,16 @@ __global__ void __launch_bounds__(256) spatial_attn_bwd_kernel(int Kc, int H, in
 // The kernels above walk their cells with one 4-byte load in flight per thread and dependent iteration; at cfg4 (36 cells, keys
 // 512 wide, values 2048 wide, 369 KB per video and frame, every byte from HBM) that ran at 0.7 TB/s.  Here every thread issues
 // the 16-byte loads of up to 10-12 cells before it uses them, scores are reduced by warp shuffles (as attn_fwd_vec_kernel).
-constexpr int SAV_NC = 10;       // cells per thread and pass in the score / key phases
+// NC = cells per thread and pass in the score / key phases (template parameter: 10 with 256 threads, 5 with 512)
 constexpr int SAV_CC = 12;       // cells per pass in the value phases
-__global__ void __launch_bounds__(256) spatial_attn_fwd_vec_kernel(int Kc, int H, int Fv, const float* __restrict__ q, long long q_ld,
+template <int NT, int NC>
+__global__ void __launch_bounds__(NT) spatial_attn_fwd_vec_kernel(int Kc, int H, int Fv, const float* __restrict__ q, long long q_ld,
                                                                    const float* __restrict__ pk, long long pk_bs,
                                                                    const float* __restrict__ feats, long long feats_bs,
                                                                    const float* __restrict__ v, float* __restrict__ alpha,
                                                                    float* __restrict__ ctx) {
   extern __shared__ float sm[];
-  const int DG = H >> 3, FG = 256 / DG, WPF = DG >> 5;          // dim groups of 8, cell groups, warps per cell group
+  const int DG = H >> 3, FG = NT / DG, WPF = DG >> 5;          // dim groups of 8, cell groups, warps per cell group
   float* sP = sm;                  // [Kc][WPF]
   float* sa = sP + Kc * WPF;       // [Kc]
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, dg = tid % DG, fg = tid / DG, d0 = dg * 8;
@@ -699,10 +700,10 @@ __global__ void __launch_bounds__(256) spatial_attn_fwd_vec_kernel(int Kc, int H
   const float q8[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
   const float v8[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
   const float* pkb = pk + (long long)b * pk_bs + d0;
-  for (int c0 = 0; c0 < Kc; c0 += FG * SAV_NC) {
-    float4 x[SAV_NC][2];
+  for (int c0 = 0; c0 < Kc; c0 += FG * NC) {
+    float4 x[NC][2];
 #pragma unroll
-    for (int m = 0; m < SAV_NC; ++m) {
+    for (int m = 0; m < NC; ++m) {
       const int c = c0 + fg + FG * m;
       x[m][0] = x[m][1] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c < Kc) {
@@ -711,7 +712,7 @@ __global__ void __launch_bounds__(256) spatial_attn_fwd_vec_kernel(int Kc, int H
       }
     }
 #pragma unroll
-    for (int m = 0; m < SAV_NC; ++m) {
+    for (int m = 0; m < NC; ++m) {
       const int c = c0 + fg + FG * m;
       const float p8[8] = {x[m][0].x, x[m][0].y, x[m][0].z, x[m][0].w, x[m][1].x, x[m][1].y, x[m][1].z, x[m][1].w};
       float s = 0.f;
@@ -740,7 +741,7 @@ __global__ void __launch_bounds__(256) spatial_attn_fwd_vec_kernel(int Kc, int H
   __syncthreads();
   const int F4 = Fv >> 2;
   const float4* fb = reinterpret_cast<const float4*>(feats + (long long)b * feats_bs);
-  for (int f4 = tid; f4 < F4; f4 += 256) {
+  for (int f4 = tid; f4 < F4; f4 += NT) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int c0 = 0; c0 < Kc; c0 += SAV_CC) {
       float4 y[SAV_CC];
@@ -756,7 +757,8 @@ __global__ void __launch_bounds__(256) spatial_attn_fwd_vec_kernel(int Kc, int H
   }
 }
 
-__global__ void __launch_bounds__(256) spatial_attn_bwd_vec_kernel(int Kc, int H, int Fv, const float* __restrict__ dctx,
+template <int NT, int NC>
+__global__ void __launch_bounds__(NT) spatial_attn_bwd_vec_kernel(int Kc, int H, int Fv, const float* __restrict__ dctx,
                                                                    const float* __restrict__ q, long long q_ld,
                                                                    const float* __restrict__ pk, long long pk_bs,
                                                                    const float* __restrict__ feats, long long feats_bs,
@@ -764,11 +766,12 @@ __global__ void __launch_bounds__(256) spatial_attn_bwd_vec_kernel(int Kc, int H
                                                                    float* __restrict__ dq, long long dq_ld, float* __restrict__ dpk,
                                                                    long long dpk_bs, float* __restrict__ dv_part) {
   extern __shared__ float sm[];
-  const int Q4 = H >> 2, CH = 256 / Q4;                          // 16-byte dim columns, cell groups of the key phase
+  const int Q4 = H >> 2, CH = NT / Q4;                          // 16-byte dim columns, cell groups of the key phase
   float* sds = sm;                 // [Kc] d alpha -> d score
   float* sal = sds + Kc;           // [Kc]
   float* sW = sal + Kc;            // [8][Kc] per-warp partial d alpha
-  float* sR = sW + 8 * Kc + ((4 - ((10 * Kc) & 3)) & 3);        // [2][CH][H] partial dq / dv of the cell groups (16-byte aligned)
+  constexpr int NW = NT / 32;
+  float* sR = sW + NW * Kc + ((4 - (((2 + NW) * Kc) & 3)) & 3);        // [2][CH][H] partial dq / dv of the cell groups (16-byte aligned)
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // d alpha[c] = dctx . feats[c]
   const int F4 = Fv >> 2;
@@ -778,7 +781,7 @@ __global__ void __launch_bounds__(256) spatial_attn_bwd_vec_kernel(int Kc, int H
     float part[SAV_CC];
 #pragma unroll
     for (int k = 0; k < SAV_CC; ++k) part[k] = 0.f;
-    for (int f4 = tid; f4 < F4; f4 += 256) {
+    for (int f4 = tid; f4 < F4; f4 += NT) {
       const float4 d4 = __ldg(dc4 + f4);
       float4 y[SAV_CC];
 #pragma unroll
@@ -793,10 +796,10 @@ __global__ void __launch_bounds__(256) spatial_attn_bwd_vec_kernel(int Kc, int H
     }
   }
   __syncthreads();
-  for (int c = tid; c < Kc; c += 256) {
+  for (int c = tid; c < Kc; c += NT) {
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += sW[w * Kc + c];
+    for (int w = 0; w < NW; ++w) s += sW[w * Kc + c];
     sds[c] = s;
     sal[c] = alpha[(long long)b * Kc + c];
   }
@@ -815,15 +818,15 @@ __global__ void __launch_bounds__(256) spatial_attn_bwd_vec_kernel(int Kc, int H
   const float4* pkb = reinterpret_cast<const float4*>(pk + (long long)b * pk_bs);
   float4* dpkb = reinterpret_cast<float4*>(dpk + (long long)b * dpk_bs);
   float4 aq = make_float4(0.f, 0.f, 0.f, 0.f), av = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int c0 = ch; c0 < Kc; c0 += CH * SAV_NC) {
-    float4 x[SAV_NC];
+  for (int c0 = ch; c0 < Kc; c0 += CH * NC) {
+    float4 x[NC];
 #pragma unroll
-    for (int m = 0; m < SAV_NC; ++m) {
+    for (int m = 0; m < NC; ++m) {
       const int c = c0 + CH * m;
       x[m] = c < Kc ? __ldg(pkb + (long long)c * Q4 + d4i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int m = 0; m < SAV_NC; ++m) {
+    for (int m = 0; m < NC; ++m) {
       const int c = c0 + CH * m;
       if (c < Kc) {
         const float ds = sds[c];
@@ -851,6 +854,12 @@ __global__ void __launch_bounds__(256) spatial_attn_bwd_vec_kernel(int Kc, int H
   }
 }
 
+// Forward: 512 threads per video (16 warps: twice the loads in flight per SM -- one CTA per video leaves the SM to a single CTA -- and
+// half the serialized load batches per phase) when the key width splits evenly.  A/B knob: PVCR_SPATIAL_ATTN_NT=256.
+static bool spatial_attn_wide(int H) {
+  static const int nt = getenv("PVCR_SPATIAL_ATTN_NT") ? atoi(getenv("PVCR_SPATIAL_ATTN_NT")) : 512;
+  return nt == 512 && (H == 256 || H == 512 || H == 1024);
+}
 static bool spatial_attn_vec_ok(int Kc, int H, int Fv, long long q_ld, long long pk_bs, long long feats_bs, const void* p0,
                                 const void* p1, const void* p2, const void* p3, const void* p4, const void* p5) {
   static const bool off = getenv("PVCR_NO_VEC_SPATIAL_ATTN") != nullptr;       // A/B knob
@@ -867,8 +876,12 @@ int spatial_attn_fwd_launch(int B, int Kc, int H, int Fv, const float* q, long l
   if (spatial_attn_vec_ok(Kc, H, Fv, q_ld, pk_batch_stride, feats_batch_stride, q, proj_key, feats, v, ctx, ctx)) {
     const size_t smem_v = sizeof(float) * ((size_t)Kc * ((H >> 3) >> 5) + Kc);
     { LaunchScope ls_(KC_ATTN, stream);
-    spatial_attn_fwd_vec_kernel<<<B, 256, smem_v, stream>>>(Kc, H, Fv, q, q_ld, proj_key, pk_batch_stride, feats,
-                                                           feats_batch_stride, v, alpha, ctx);
+    if (spatial_attn_wide(H))
+      spatial_attn_fwd_vec_kernel<512, 5><<<B, 512, smem_v, stream>>>(Kc, H, Fv, q, q_ld, proj_key, pk_batch_stride, feats,
+                                                                     feats_batch_stride, v, alpha, ctx);
+    else
+      spatial_attn_fwd_vec_kernel<256, 10><<<B, 256, smem_v, stream>>>(Kc, H, Fv, q, q_ld, proj_key, pk_batch_stride, feats,
+                                                                      feats_batch_stride, v, alpha, ctx);
     }
     PVCR_CUDA_CHECK(cudaGetLastError());
     return PVCR_OK;
@@ -888,10 +901,20 @@ int spatial_attn_bwd_launch(int B, int Kc, int H, int Fv, const float* dctx, con
   if (B <= 0 || Kc <= 0 || Kc > SA_MAX_CELLS || H <= 0 || Fv <= 0) { set_last_error("pvcr_spatial_attn_bwd: B=%d Kc=%d H=%d Fv=%d", B, Kc, H, Fv); return PVCR_ERR_ARG; }
   if (spatial_attn_vec_ok(Kc, H, Fv, q_ld, pk_batch_stride, feats_batch_stride, q, proj_key, feats, v, dctx, dproj_key) &&
       ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dv_part)) & 15) == 0 && dq_ld % 4 == 0 && dpk_batch_stride % 4 == 0) {
-    const size_t smem_v = sizeof(float) * ((size_t)10 * Kc + 4 + (size_t)2 * (256 / (H >> 2)) * H);
+    // measured at cfg4 (tests/gpu_probe_spatial_attn.py): forward 45.2 -> 27.1 us per launch with 512 threads, backward 24.6 -> 33.6 us:
+    // the backward stays on 256 threads unless PVCR_SPATIAL_ATTN_BWD_NT=512
+    static const bool bwd_wide = getenv("PVCR_SPATIAL_ATTN_BWD_NT") && atoi(getenv("PVCR_SPATIAL_ATTN_BWD_NT")) == 512;
+    int nt = bwd_wide && spatial_attn_wide(H) ? 512 : 256;
+    if (sizeof(float) * ((size_t)(2 + nt / 32) * Kc + 4 + (size_t)2 * (nt / (H >> 2)) * H) > 48 * 1024) nt = 256;
+    const size_t smem_v = sizeof(float) * ((size_t)(2 + nt / 32) * Kc + 4 + (size_t)2 * (nt / (H >> 2)) * H);
     { LaunchScope ls_(KC_ATTN, stream);
-    spatial_attn_bwd_vec_kernel<<<B, 256, smem_v, stream>>>(Kc, H, Fv, dctx, q, q_ld, proj_key, pk_batch_stride, feats, feats_batch_stride,
-                                                           v, alpha, dq, dq_ld, dproj_key, dpk_batch_stride, dv_part);
+    if (nt == 512) {
+      spatial_attn_bwd_vec_kernel<512, 5><<<B, 512, smem_v, stream>>>(Kc, H, Fv, dctx, q, q_ld, proj_key, pk_batch_stride, feats,
+                                                                     feats_batch_stride, v, alpha, dq, dq_ld, dproj_key, dpk_batch_stride, dv_part);
+    } else {
+      spatial_attn_bwd_vec_kernel<256, 10><<<B, 256, smem_v, stream>>>(Kc, H, Fv, dctx, q, q_ld, proj_key, pk_batch_stride, feats,
+                                                                      feats_batch_stride, v, alpha, dq, dq_ld, dproj_key, dpk_batch_stride, dv_part);
+    }
     }
     PVCR_CUDA_CHECK(cudaGetLastError());
     return PVCR_OK;
