@@ -28,10 +28,10 @@ def run_iter(opts, data, model, criterion=None, return_pred=False):
     reference) is accepted for signature compatibility; the masked loss is evaluated inside the kernels."""
     dev = _device_of(model)
     vid_feats, s, s_len = data['vid_feats'].to(dev), data['sent'].to(dev), data['sent_len'].to(dev)
-    if model.training:
+    if model.training and hasattr(model, 'forward_loss'):
         out = model.forward_loss(vid_feats, s, s_len)
         loss, acc, pred = out[0], out[1], out[2]
-    else:
+    else:                                        # eval, and SpatialNet in training (train_spatial.py:30-39: logits materialised)
         from . import train_utils as TU
         logits = model(vid_feats, s)
         if isinstance(logits, tuple):            # SpatialNet / RationaleNet return (logits, extra)

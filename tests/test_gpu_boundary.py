@@ -234,6 +234,27 @@ def test_spatialnet_frame_sweep_vs_stepwise(precision, tol, monkeypatch):
             assert e < 1e-4 or g1[k].norm().item() < 1e-9, (k, e)
 
 
+def test_run_iter_serves_spatialnet_in_training():
+    """trainer.run_iter with a SpatialNet: the reference's train_spatial.py:30-39 contract ((acc, loss[, pred]), autograd loss)."""
+    from pvcr_b200 import train_utils as TU
+    from pvcr_b200.model import SpatialNet
+    from pvcr_b200.trainer import run_iter
+    B, N, Fd, K, H, E, L, Vc = 4, 3, 64, 3, 32, 16, 5, 50
+    torch.manual_seed(2)
+    net = SpatialNet(FixtureGlove(Vc, E), 0.0, H, Fd, L, "s2vt-att", precision="bf16x3").cuda().train()
+    data = {"vid_feats": torch.randn(B, N, Fd, K, K), "sent": torch.randint(0, Vc - 4, (B, L)), "sent_len": torch.randint(1, L + 1, (B,))}
+    acc, loss, pred = run_iter(None, data, net, nn.CrossEntropyLoss(reduction="none"), return_pred=True)
+    assert pred.shape == (B, L) and 0.0 <= float(acc) <= 1.0
+    loss.backward()
+    got = {k: p.grad for k, p in net.named_parameters() if p.grad is not None}
+    assert all(torch.isfinite(g).all() for g in got.values())
+    assert {"conv.0.weight", "conv.3.weight", "attention.key_layer.weight", "attention.query_layer.weight",
+            "attention.energy_layer.weight"} <= set(got)
+    logits, _ = net(data["vid_feats"].cuda(), data["sent"].cuda())
+    want = TU.calc_masked_loss(logits, data["sent"].cuda(), data["sent_len"].cuda(), None)
+    assert abs(float(loss) - float(want)) < 1e-6 * abs(float(want))
+
+
 def test_boundary_surface_matches_reference_signatures():
     """reset_parameter(s), encode_step, decode, encode and calc_sentence_mask(batch_size, max_len, s_len) exist with the
     reference's argument lists (model/S2VTAttModel.py:215-243, model/S2VTModel.py:52-88, train_utils.py:22)."""
