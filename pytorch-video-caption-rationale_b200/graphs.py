@@ -13,7 +13,41 @@ import torch
 from ._lib import check, lib, ptr, stream_ptr
 
 
-class GraphedTrainStep:
+class _InputPipeline:
+    """Input side shared by the graphed steps: the next batch is copied host -> device into staging buffers on a side stream
+    while the current step computes (what a pinned-memory DataLoader with non_blocking copies gives the reference loop)."""
+
+    def _init_pipeline(self):
+        self._copy_stream = torch.cuda.Stream()
+        self._staging = tuple(torch.empty_like(t) for t in self.static_in)
+        self._staged = None
+        self._handover = None
+
+    def prefetch(self, *inputs):
+        """Start copying the NEXT step's inputs (pinned host tensors) to the device; returns immediately."""
+        cs = self._copy_stream
+        if self._handover is not None:
+            cs.wait_event(self._handover)                 # staging buffers must have been handed over, nothing more
+        with torch.cuda.stream(cs):
+            for dst, src in zip(self._staging, inputs):
+                dst.copy_(src, non_blocking=True)
+            self._staged = torch.cuda.Event()
+            self._staged.record(cs)
+
+    def step_prefetched(self):
+        """Run one step on the inputs handed to the latest prefetch()."""
+        assert self._staged is not None, "call prefetch() first"
+        torch.cuda.current_stream().wait_event(self._staged)
+        for dst, src in zip(self.static_in, self._staging):
+            dst.copy_(src, non_blocking=True)              # device-to-device hand-over (tens of microseconds)
+        self._handover = torch.cuda.Event()
+        self._handover.record(torch.cuda.current_stream())
+        self._staged = None
+        self._replay()
+        return self.static_out
+
+
+class GraphedTrainStep(_InputPipeline):
     def __init__(self, model, example_inputs, warmup=3, reducer=None, optimizer=None):
         """example_inputs: tuple of CUDA tensors, the arguments of model.train_step_grads (fixes shapes/dtypes).
         reducer: a parallel.GradAllReducer(flat=True, early=model.early_grad_params()); the step is then captured as
@@ -126,12 +160,7 @@ class GraphedTrainStep:
                 if capture_opt:
                     optimizer.step()
         self.static_out = tuple(o.detach() if torch.is_tensor(o) else o for o in out)
-        # input pipeline: the next batch is copied host -> device into staging buffers on a side stream while the
-        # current step computes (what a pinned-memory DataLoader with non_blocking copies gives the reference loop)
-        self._copy_stream = torch.cuda.Stream()
-        self._staging = tuple(torch.empty_like(t) for t in self.static_in)
-        self._staged = None
-        self._handover = None
+        self._init_pipeline()
 
     _seed_owner = None
 
@@ -170,70 +199,99 @@ class GraphedTrainStep:
         if self._opt_after_replay:             # clip + Adam on the REDUCED gradients (train.py:158-160)
             self.optimizer.step()
 
-    def prefetch(self, *inputs):
-        """Start copying the NEXT step's inputs (pinned host tensors) to the device; returns immediately."""
-        cs = self._copy_stream
-        if self._handover is not None:
-            cs.wait_event(self._handover)                 # staging buffers must have been handed over, nothing more
-        with torch.cuda.stream(cs):
-            for dst, src in zip(self._staging, inputs):
-                dst.copy_(src, non_blocking=True)
-            self._staged = torch.cuda.Event()
-            self._staged.record(cs)
 
-    def step_prefetched(self):
-        """Run one step on the inputs handed to the latest prefetch()."""
-        assert self._staged is not None, "call prefetch() first"
-        torch.cuda.current_stream().wait_event(self._staged)
-        for dst, src in zip(self.static_in, self._staging):
-            dst.copy_(src, non_blocking=True)              # device-to-device hand-over (tens of microseconds)
-        self._handover = torch.cuda.Event()
-        self._handover.record(torch.cuda.current_stream())
-        self._staged = None
-        self._replay()
-        return self.static_out
+class GraphedAutogradStep(_InputPipeline):
+    """CUDA-graph capture of ``loss = loss_fn(...); backward`` WITH the autograd tape inside the capture, for the drop-in
+    modules whose step is a chain of autograd Functions rather than one tape-free ``train_step_grads`` -- SpatialNet
+    (model/SpatialNet.py:100-142; train_spatial.py:30-39,  ~500 launches per fwd+bwd, host-bound in eager mode).
 
+    ``loss_fn(*inputs)`` returns the loss or a tuple whose first element is the loss (the rest, e.g. accuracy and
+    predictions, must not require grad).  ``example_inputs`` (CUDA tensors) fix the shapes: they are cloned into static
+    buffers that ``__call__(*inputs)`` / ``prefetch`` + ``step_prefetched`` refill; without them ``loss_fn()`` reads tensors
+    the caller keeps alive.  The gradients appear in ``param.grad`` (static buffers, rewritten by every replay).  With an
+    ``optimizer`` (optim.FusedClipAdam) its clip + Adam kernels are captured behind the backward: one replay = one training
+    iteration (train_spatial.py: run_iter + backward + clip_grad_norm_ + optimizer.step)."""
 
-class GraphedAutogradStep:
-    """CUDA-graph capture of ``loss = loss_fn(); loss.backward()`` WITH the autograd tape inside the capture, for the drop-in
-    modules whose step is a chain of autograd Functions rather than one tape-free ``train_step_grads`` -- SpatialNet's frame
-    loop (model/SpatialNet.py:120-140: query GEMM, attention, encoder step per frame = ~1 500 launches per fwd+bwd, host-bound
-    in eager mode).  ``loss_fn`` takes no arguments and reads its inputs from tensors that stay alive (copy new batches into
-    them); the gradients appear in ``param.grad`` (static buffers of the graph's pool, rewritten by every replay)."""
-
-    def __init__(self, model, loss_fn, warmup=2):
+    def __init__(self, model, loss_fn, warmup=2, example_inputs=(), optimizer=None):
         self.model = model
+        self.optimizer = optimizer
         self.params = [p for p in model.parameters() if p.requires_grad]
         dev = self.params[0].device
+        self.static_in = tuple(t.clone() for t in example_inputs)
         self.seed_step = torch.zeros(1, dtype=torch.int64, device=dev)
         lib().pvcr_set_seed_step(ptr(self.seed_step))
         GraphedTrainStep._seed_owner = self.seed_step.data_ptr()
+        if optimizer is not None:
+            # the optimizer's pointer table wants one gradient buffer per parameter at a fixed address: allocated here, the
+            # captured backward copies into them (parameters the loss does not reach keep a zero gradient)
+            for p in self.params:
+                p.grad = torch.zeros_like(p)
 
         def step():
             # torch.autograd.grad, not .backward(): no AccumulateGrad nodes (they remember the stream of an earlier eager
             # iteration, and a hand-over to the default stream invalidates the capture)
-            loss = loss_fn()
-            return loss.detach(), torch.autograd.grad(loss, self.params, allow_unused=True)
+            out = loss_fn(*self.static_in)
+            loss = out[0] if isinstance(out, (tuple, list)) else out
+            grads = torch.autograd.grad(loss, self.params, allow_unused=True)
+            if optimizer is not None:
+                with torch.no_grad():
+                    for p, g in zip(self.params, grads):
+                        if g is not None:
+                            p.grad.copy_(g)
+                optimizer.step()
+            rest = tuple(o.detach() for o in out[1:]) if isinstance(out, (tuple, list)) else ()
+            return (loss.detach(),) + rest, grads
 
+        keep = None
+        buffers = [(b, b.clone()) for b in model.buffers()]       # BatchNorm running statistics: the warm-up steps update them
+        if optimizer is not None:          # the warm-up steps must not train the model
+            keep = ([p.detach().clone() for p in self.params], [m.clone() for m in optimizer.exp_avg],
+                    [v.clone() for v in optimizer.exp_avg_sq], optimizer.step_count.clone())
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(warmup):
+            for _ in range(max(1, warmup)):
                 step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.seed_step.add_(1)
-            self.static_loss, grads = step()
-        for p, g in zip(self.params, grads):         # static buffers of the graph's pool, rewritten by every replay
-            p.grad = g
+            self.static_out, grads = step()
+        if optimizer is None:
+            for p, g in zip(self.params, grads):         # static buffers of the graph's pool, rewritten by every replay
+                p.grad = g
+        else:
+            torch.cuda.synchronize()
+            with torch.no_grad():
+                for p, k in zip(self.params, keep[0]):
+                    p.copy_(k)
+                for m, k in zip(optimizer.exp_avg, keep[1]):
+                    m.copy_(k)
+                for v, k in zip(optimizer.exp_avg_sq, keep[2]):
+                    v.copy_(k)
+                optimizer.step_count.copy_(keep[3])
+        with torch.no_grad():
+            for b, k in buffers:
+                b.copy_(k)
+        self.static_loss = self.static_out[0]
+        self._init_pipeline()
+
+    def _replay(self):
+        self.graph.replay()
 
     def replay(self):
         self.graph.replay()
         return self.static_loss
 
-    __call__ = replay
+    def __call__(self, *inputs):
+        if not inputs:
+            return self.replay()
+        for dst, src in zip(self.static_in, inputs):
+            if src is not dst:
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
 
     def __del__(self):
         try:

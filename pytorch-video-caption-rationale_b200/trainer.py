@@ -6,7 +6,8 @@ iteration around it, on the B200 kernels.
   (dataset.py:118-139: 'vid_feats' [B,N,V] float, 'sent' [B,L] long, 'sent_len' [B] long).  In training mode it goes
   through the fused ``model.forward_loss`` (logits never materialised) and returns an autograd loss, so the reference
   loop ``optimizer.zero_grad(); loss.backward(); clip_grad_norm_(); optimizer.step()`` (train.py:157-160) works unchanged.
-* ``Trainer`` -- the same iteration without the host in the loop: forward, backward, ``clip_grad_norm_`` and Adam
+* ``Trainer`` -- the same iteration without the host in the loop (S2VT / S2VTAtt / RationaleNet through their tape-free
+  ``train_step_grads``; SpatialNet, train_spatial.py, through ``graphs.GraphedAutogradStep``): forward, backward, ``clip_grad_norm_`` and Adam
   captured as ONE CUDA graph (graphs.GraphedTrainStep + optim.FusedClipAdam, gradient all-reduce included when
   data-parallel), the NEXT batch copied host -> device from pinned staging buffers on a copy stream while the current
   step computes, and no device -> host synchronisation per iteration (the reference syncs twice: train.py:151
@@ -68,7 +69,22 @@ class Trainer:
         # capturing the step executes it (pointer tables, communicator set-up) -- the example batch must not train the
         # model: parameters and optimizer state are put back afterwards
         keep = [p.detach().clone() for p in model.parameters()]
-        self.step = GraphedTrainStep(self.model, dev_example, warmup=1, reducer=reducer, optimizer=self.optimizer)
+        if hasattr(model, 'train_step_grads'):
+            self.step = GraphedTrainStep(self.model, dev_example, warmup=1, reducer=reducer, optimizer=self.optimizer)
+        else:
+            # SpatialNet (train_spatial.py:30-39,  the same iteration around a module whose step is a chain of autograd
+            # Functions): forward + masked loss / accuracy / predictions + backward + clip + Adam as one graph, tape inside
+            assert reducer is None, "data-parallel training is implemented for the modules with train_step_stages"
+            from . import train_utils as TU
+            from .graphs import GraphedAutogradStep
+
+            def loss_fn(vid_feats, s, s_len):
+                logits = self.model(vid_feats, s)
+                logits = logits[0] if isinstance(logits, tuple) else logits
+                loss, stats, pred = TU._MaskedCE.apply(logits, s, s_len)
+                return loss, stats[0] / stats[1], pred
+
+            self.step = GraphedAutogradStep(self.model, loss_fn, warmup=1, example_inputs=dev_example, optimizer=self.optimizer)
         torch.cuda.synchronize()
         with torch.no_grad():
             for p, k in zip(model.parameters(), keep):

@@ -252,7 +252,7 @@ def test_run_iter_serves_spatialnet_in_training():
             "attention.energy_layer.weight"} <= set(got)
     logits, _ = net(data["vid_feats"].cuda(), data["sent"].cuda())
     want = TU.calc_masked_loss(logits, data["sent"].cuda(), data["sent_len"].cuda(), None)
-    assert abs(float(loss) - float(want)) < 1e-6 * abs(float(want))
+    assert abs(loss.item() - want.item()) < 1e-6 * abs(want.item())
 
 
 def test_boundary_surface_matches_reference_signatures():

@@ -71,3 +71,42 @@ def test_trainer_iterations_match_the_manual_loop():
     assert tr2.n_iter == 3 and tr2.epoch == 1
     for (k, a), (_, b) in zip(m.named_parameters(), m2.named_parameters()):
         assert torch.equal(a, b), k
+
+
+def test_trainer_drives_spatialnet():
+    """Trainer on a SpatialNet (train_spatial.py's loop): the graph-captured iteration (autograd tape + clip + Adam inside one CUDA
+    graph) against the manual loop run_iter + backward + FusedClipAdam on a second copy of the model."""
+    import copy
+    from pvcr_b200.model import SpatialNet
+    from pvcr_b200.optim import FusedClipAdam
+    from pvcr_b200.trainer import Trainer, run_iter
+    B, N, Fd, K, H, E, L, Vc = 6, 4, 64, 3, 64, 16, 6, 60
+    torch.manual_seed(4)
+    m = SpatialNet(FixtureGlove(Vc, E), 0.0, H, Fd, L, "s2vt-att", precision="bf16x3").cuda().train()
+    ref = copy.deepcopy(m)
+    data = {"vid_feats": torch.randn(B, N, Fd, K, K), "sent": torch.randint(0, Vc - 4, (B, L)), "sent_len": torch.randint(1, L + 1, (B,))}
+    before = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    tr = Trainer(m, data, lr=2e-3, weight_decay=4e-5, max_norm=1.0)
+    for k, v in m.state_dict().items():          # building the trainer trained nothing and left the BatchNorm statistics alone
+        assert torch.equal(v, before[k]), k
+    losses = []
+    for it in range(3):
+        loss, acc, pred = tr.train_iter(data, next_data=data if it < 2 else None)
+        losses.append(float(loss.item()))
+        assert pred.shape == (B, L) and 0.0 <= float(acc) <= 1.0
+    assert losses[2] < losses[0]
+    opt = FusedClipAdam(ref.parameters(), lr=2e-3, weight_decay=4e-5, max_norm=1.0)
+    for p in ref.parameters():
+        p.grad = torch.zeros_like(p)
+    for it in range(3):
+        for p in ref.parameters():
+            p.grad.zero_()
+        acc, l = run_iter(None, data, ref, None)
+        assert abs(float(l.item()) - losses[it]) < 2e-5 * abs(losses[it]), (it, float(l.item()), losses[it])
+        l.backward()
+        opt.step()
+    for (k, a), (_, b) in zip(m.state_dict().items(), ref.state_dict().items()):
+        if a.dtype.is_floating_point:
+            assert relerr(a.detach().cpu().numpy(), b.detach().cpu().numpy()) < 2e-4, k
+        else:
+            assert torch.equal(a, b), k
