@@ -67,3 +67,20 @@ def test_ops_fail_loudly_without_cuda():
     from pvcr_b200 import functional as F_
     with pytest.raises(AssertionError, match="no CPU path"):
         F_._f32c(torch.zeros(2))
+
+
+def test_spatial_encode_host_side():
+    """pvcr_spatial_encode_*: the workspace query is host arithmetic (grows with the frame count, covers the saved activations), and
+    a null argument is refused with an error code and message before anything touches the device."""
+    import pvcr_b200  # noqa: F401
+    from pvcr_b200 import _lib
+    L = _lib.lib()
+    B, Kc, H, F = 128, 36, 512, 2048
+    w40, w41 = L.pvcr_spatial_encode_workspace(B, 40, Kc, H, F, 1), L.pvcr_spatial_encode_workspace(B, 41, Kc, H, F, 1)
+    per_frame = B * (4 * H + 4 * H + F + 3 * H + 4 * H + H) * 4       # qgh, saved gates, ctx | dgi, d1, dv partials (fp32)
+    assert w41 - w40 >= per_frame and w41 - w40 < 2 * per_frame + (1 << 20)
+    assert L.pvcr_spatial_encode_workspace(B, 40, Kc, H, F, 3) > w40          # split planes are wider
+    rc = L.pvcr_spatial_encode_fwd(B, 40, Kc, H, F, 1, None, None, None, None, None, None, None, None, None, None, None, 0, None)
+    assert rc != 0 and b"null argument" in L.pvcr_last_error()
+    rc = L.pvcr_spatial_encode_bwd(B, 40, Kc, H, F, 1, *([None] * 16), None, 0, None)
+    assert rc != 0 and b"null argument" in L.pvcr_last_error()
