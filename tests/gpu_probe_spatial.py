@@ -46,6 +46,13 @@ def ours():
 
 
 L_ = _lib.lib()
+if os.environ.get("PVCR_PROBE_NCU"):
+    # exactly one steady-state eager step between cudaProfilerStart / Stop: ncu --profile-from-start off ... (profiles/r02t_cfg4_launches.csv)
+    ours(); ours(); torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    ours(); torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    sys.exit(0)
 ms = timed(ours)
 L_.pvcr_prof_reset(); L_.pvcr_prof_enable(1)
 ours(); torch.cuda.synchronize()
